@@ -1,0 +1,229 @@
+// Per-cluster autodiff interpreter: forward value sweep + pull-style reverse
+// sweeps over a compiled cluster program (formats in internal.hpp).
+//
+// Replaces, for one cluster of rows at a time, the reference's update_values
+// (autodiff/expression_graph.hpp:85-96) and append_triplets (:106-153). The
+// arithmetic of every op follows SURVEY Appendix B / expression.hpp literally
+// (e.g. ∂(l/r)/∂r = a * -l / (r * r), :634-636) and is compiled without FMA
+// contraction, so that it rounds like the reference's x86-64 build; only the
+// transcendental functions can differ (CUDA libdevice vs glibc, ≤ 1-2 ulp).
+//
+// The body is written once as a function of (lane, NLANES): the kernels run it
+// with one warp per cluster (NLANES = 32, levels separated by __syncwarp),
+// and tests/emu runs the very same code on the host with NLANES = 1 to check
+// the program encoding without a GPU. It is not a CPU path of the product:
+// nothing in libslpb.so calls it on the host.
+#pragma once
+
+#include <cmath>
+#include <cstdint>
+
+#include "internal.hpp"
+
+#if defined(__CUDACC__)
+#define SLPB_HD __host__ __device__ __forceinline__
+#else
+#define SLPB_HD inline
+#endif
+
+namespace slpb {
+
+SLPB_HD double ad_op_value(uint8_t op, double l, double r) {
+  switch (op) {
+    case SLPB_OP_SUB: return l - r;
+    case SLPB_OP_ADD: return l + r;
+    case SLPB_OP_DIV: return l / r;
+    case SLPB_OP_MUL: return l * r;
+    case SLPB_OP_NEG: return -l;
+    case SLPB_OP_ABS: return fabs(l);
+    case SLPB_OP_ACOS: return acos(l);
+    case SLPB_OP_ASIN: return asin(l);
+    case SLPB_OP_ATAN: return atan(l);
+    case SLPB_OP_ATAN2: return atan2(l, r);
+    case SLPB_OP_CBRT: return cbrt(l);
+    case SLPB_OP_COS: return cos(l);
+    case SLPB_OP_COSH: return cosh(l);
+    case SLPB_OP_ERF: return erf(l);
+    case SLPB_OP_EXP: return exp(l);
+    case SLPB_OP_HYPOT: return hypot(l, r);
+    case SLPB_OP_IS_NONNEG: return l >= 0.0 ? 1.0 : 0.0;
+    case SLPB_OP_IS_POS: return l > 0.0 ? 1.0 : 0.0;
+    case SLPB_OP_LOG: return log(l);
+    case SLPB_OP_LOG10: return log10(l);
+    case SLPB_OP_MAX: return l < r ? r : l;   // std::max(l, r)
+    case SLPB_OP_MIN: return r < l ? r : l;   // std::min(l, r)
+    case SLPB_OP_POW: return pow(l, r);
+    case SLPB_OP_SIGN: return l < 0.0 ? -1.0 : (l == 0.0 ? 0.0 : 1.0);
+    case SLPB_OP_SIN: return sin(l);
+    case SLPB_OP_SINH: return sinh(l);
+    case SLPB_OP_SQRT: return sqrt(l);
+    case SLPB_OP_TAN: return tan(l);
+    case SLPB_OP_TANH: return tanh(l);
+    default: return 0.0;
+  }
+}
+
+/// Adjoint-weighted partial of parent `op(l, r)` (adjoint a) w.r.t. its left
+/// (side 0) or right (side 1) argument.
+SLPB_HD double ad_op_grad(uint8_t op, uint8_t side, double a, double l,
+                          double r) {
+  if (side == 0) {
+    switch (op) {
+      case SLPB_OP_SUB: case SLPB_OP_ADD: return a;
+      case SLPB_OP_DIV: return a / r;
+      case SLPB_OP_MUL: return a * r;
+      case SLPB_OP_NEG: return -a;
+      case SLPB_OP_ABS: return l < 0.0 ? -a : (l > 0.0 ? a : 0.0);
+      case SLPB_OP_ACOS: return -a / sqrt(1.0 - l * l);
+      case SLPB_OP_ASIN: return a / sqrt(1.0 - l * l);
+      case SLPB_OP_ATAN: return a / (1.0 + l * l);
+      case SLPB_OP_ATAN2: return a * r / (l * l + r * r);
+      case SLPB_OP_CBRT: { double c = cbrt(l); return a / (3.0 * c * c); }
+      case SLPB_OP_COS: return a * -sin(l);
+      case SLPB_OP_COSH: return a * sinh(l);
+      case SLPB_OP_ERF:
+        return a * (2.0 * 0.564189583547756286948079451560772586) *
+               exp(-l * l);
+      case SLPB_OP_EXP: return a * exp(l);
+      case SLPB_OP_HYPOT: return a * l / hypot(l, r);
+      case SLPB_OP_LOG: return a / l;
+      case SLPB_OP_LOG10:
+        return a / (2.302585092994045684017991454684364208 * l);
+      case SLPB_OP_MAX: return l >= r ? a : 0.0;
+      case SLPB_OP_MIN: return l <= r ? a : 0.0;
+      case SLPB_OP_POW: return a * pow(l, r - 1.0) * r;
+      case SLPB_OP_SIN: return a * cos(l);
+      case SLPB_OP_SINH: return a * cosh(l);
+      case SLPB_OP_SQRT: return a / (2.0 * sqrt(l));
+      case SLPB_OP_TAN: { double c = cos(l); return a / (c * c); }
+      case SLPB_OP_TANH: { double c = cosh(l); return a / (c * c); }
+      default: return 0.0;
+    }
+  }
+  switch (op) {
+    case SLPB_OP_SUB: return -a;
+    case SLPB_OP_ADD: return a;
+    case SLPB_OP_DIV: return a * -l / (r * r);
+    case SLPB_OP_MUL: return a * l;
+    case SLPB_OP_ATAN2: return a * -l / (l * l + r * r);
+    case SLPB_OP_HYPOT: return a * r / hypot(l, r);
+    case SLPB_OP_MAX: return l >= r ? 0.0 : a;
+    case SLPB_OP_MIN: return l <= r ? 0.0 : a;
+    case SLPB_OP_POW: return a * pow(l, r) * log(l);
+    default: return 0.0;
+  }
+}
+
+struct NoSync {
+  SLPB_HD void operator()() const {}
+};
+
+/// Runs one cluster. `scratch` holds n_slots values followed by n_adj
+/// adjoints. `stage` receives value outputs and derivative outputs.
+template <int NLANES, typename Sync>
+SLPB_HD void ad_run_cluster(int lane, const uint32_t* __restrict__ P,
+                            const uint32_t* __restrict__ B,
+                            const double* __restrict__ leaf,
+                            double* __restrict__ stage, double* scratch,
+                            Sync sync) {
+  const int n_slots = static_cast<int>(P[0]);
+  const int n_leaf = static_cast<int>(P[2]);
+  const int n_const = static_cast<int>(P[3]);
+  const int n_fwd_levels = static_cast<int>(P[4]);
+  const int n_rev_levels = static_cast<int>(P[5]);
+  const int n_val_out = static_cast<int>(P[6]);
+  const int n_adj_out = static_cast<int>(P[7]);
+  double* vals = scratch;
+  double* adj = scratch + n_slots;
+
+  // binding layout: leaf_index | pad | const_val | val_out | adj_out
+  const int32_t* leaf_index = reinterpret_cast<const int32_t*>(B);
+  const int const_off = (n_leaf + 1) & ~1;
+  const double* const_val = reinterpret_cast<const double*>(B + const_off);
+  const int32_t* val_out_stage =
+      reinterpret_cast<const int32_t*>(B + const_off + 2 * n_const);
+  const int32_t* adj_out_stage = val_out_stage + n_val_out;
+
+  const uint16_t* leaf_slot = reinterpret_cast<const uint16_t*>(P + P[8]);
+  const uint16_t* const_slot = reinterpret_cast<const uint16_t*>(P + P[9]);
+  for (int i = lane; i < n_leaf; i += NLANES) {
+    vals[leaf_slot[i]] = leaf[leaf_index[i]];
+  }
+  for (int i = lane; i < n_const; i += NLANES) {
+    vals[const_slot[i]] = const_val[i];
+  }
+  sync();
+
+  // ---- forward sweep, level by level ----------------------------------------
+  const uint32_t* fwd_lvl = P + P[10];
+  const FwdInstr* fwd = reinterpret_cast<const FwdInstr*>(P + P[11]);
+  for (int L = 0; L < n_fwd_levels; ++L) {
+    const int b = static_cast<int>(fwd_lvl[L]);
+    const int e = static_cast<int>(fwd_lvl[L + 1]);
+    for (int i = b + lane; i < e; i += NLANES) {
+      const FwdInstr in = fwd[i];
+      vals[in.dst] = ad_op_value(in.op, vals[in.a], vals[in.b]);
+    }
+    sync();
+  }
+  const uint16_t* val_out_slot = reinterpret_cast<const uint16_t*>(P + P[15]);
+  for (int i = lane; i < n_val_out; i += NLANES) {
+    stage[val_out_stage[i]] = vals[val_out_slot[i]];
+  }
+
+  // ---- reverse sweeps: each visit pulls from its parents' adjoints ----------
+  const uint32_t* rev_lvl = P + P[12];
+  const Visit* visit = reinterpret_cast<const Visit*>(P + P[13]);
+  const Contrib* contrib = reinterpret_cast<const Contrib*>(P + P[14]);
+  for (int L = 0; L < n_rev_levels; ++L) {
+    const int b = static_cast<int>(rev_lvl[L]);
+    const int e = static_cast<int>(rev_lvl[L + 1]);
+    for (int i = b + lane; i < e; i += NLANES) {
+      const Visit v = visit[i];
+      double a;
+      if (v.n_contrib == 0) {
+        a = static_cast<double>(v.seed);
+      } else {
+        // adjoint starts at 0 and accumulates in the row's parent order
+        a = 0.0;
+        const Contrib* c = contrib + v.contrib_begin;
+        for (int k = 0; k < v.n_contrib; ++k) {
+          const Contrib ck = c[k];
+          a += ad_op_grad(ck.op, ck.side, adj[ck.parent_adj], vals[ck.l],
+                          vals[ck.r]);
+        }
+      }
+      adj[v.adj] = a;
+    }
+    sync();
+  }
+  const uint16_t* adj_out_slot = reinterpret_cast<const uint16_t*>(P + P[16]);
+  for (int i = lane; i < n_adj_out; i += NLANES) {
+    stage[adj_out_stage[i]] = adj[adj_out_slot[i]];
+  }
+}
+
+/// Scale reference of a gather source: −1 → 1, −2 → d_f, k ≥ 0 → d_c[k].
+SLPB_HD double gather_entry(int e, const int32_t* __restrict__ ptr,
+                            const int32_t* __restrict__ src_idx,
+                            const int32_t* __restrict__ src_scale,
+                            const double* __restrict__ stage, double d_f,
+                            const double* __restrict__ d_c) {
+  double acc = 0.0;
+  const int b = ptr[e], en = ptr[e + 1];
+  for (int k = b; k < en; ++k) {
+    const int32_t raw = src_idx[k];
+    double v = stage[raw & 0x7fffffff];
+    if (raw < 0) v = -v;
+    const int32_t sc = src_scale[k];
+    if (sc == -2) {
+      v = d_f * v;
+    } else if (sc >= 0) {
+      v = d_c[sc] * v;
+    }
+    acc = (k == b) ? v : acc + v;
+  }
+  return acc;
+}
+
+}  // namespace slpb

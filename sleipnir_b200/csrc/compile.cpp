@@ -1,0 +1,763 @@
+// Host-side compiler: uploaded expression tape + row descriptors → cluster
+// programs for the autodiff sweep kernels (see internal.hpp for the formats).
+//
+// What it preserves from the reference (include/sleipnir/autodiff):
+//   * the per-row parent→child order of expression_graph.hpp:28-78 — adjoint
+//     contributions into a node are pulled in exactly the order in which
+//     append_triplets (:119-145) would have pushed them, so sums round alike;
+//   * "every wrt leaf of a row emits a triplet, even a zero one" (:147-152),
+//     which keeps the sparsity patterns static;
+//   * LINEAR rows are constants (jacobian.hpp:84-89): they never reach the
+//     device programs, only the constant part of the stage arrays.
+// What it adds: rows that share interior nodes are fused into one cluster and
+// evaluated once (the reference re-walks shared sub-graphs per row,
+// jacobian.hpp:139-141); long root sums (Σ_k u_k² costs) are split into
+// independent terms so a 5000-term chain does not serialise on one warp.
+#include <algorithm>
+#include <cstring>
+#include <numeric>
+#include <unordered_map>
+
+#include "internal.hpp"
+
+namespace slpb {
+
+int64_t Pattern::find(int32_t r, int32_t c) const {
+  const int32_t* b = rowidx.data() + colptr[c];
+  const int32_t* e = rowidx.data() + colptr[c + 1];
+  const int32_t* it = std::lower_bound(b, e, r);
+  if (it == e || *it != r) return -1;
+  return it - rowidx.data();
+}
+
+namespace {
+
+constexpr int kSplitThreshold = 16;  // root sums shorter than this stay whole
+
+struct SubRow {
+  int out = 0;          // slpb_output
+  int32_t row = 0;
+  int8_t seed = 1;
+  bool is_value = false;
+  std::vector<int32_t> nodes;                       // parent→child order
+  std::vector<uint8_t> flags;                       // per node: kActive|kValue
+  std::vector<std::pair<int32_t, int32_t>> outs;    // (stage slot, node)
+  int32_t value_stage = -1;                         // value rows
+};
+
+constexpr uint8_t kActive = 1;  // the node's adjoint reaches an output leaf
+constexpr uint8_t kValue = 2;   // the node's value is read by some partial
+
+/// Which operand values the partial of `op` w.r.t. `side` reads
+/// (bit 0: lhs value, bit 1: rhs value); see ad_op_grad in ad_core.hpp.
+uint8_t grad_value_needs(uint8_t op, int side) {
+  switch (op) {
+    case SLPB_OP_ADD: case SLPB_OP_SUB: case SLPB_OP_NEG: return 0;
+    case SLPB_OP_MUL: return side == 0 ? 2 : 1;
+    case SLPB_OP_DIV: return side == 0 ? 2 : 3;
+    default: return 3;
+  }
+}
+
+bool is_sum_op(uint8_t op) {
+  return op == SLPB_OP_ADD || op == SLPB_OP_SUB || op == SLPB_OP_NEG;
+}
+
+Pattern pattern_from_positions(int32_t rows, int32_t cols,
+                               std::vector<std::pair<int32_t, int32_t>>& pos) {
+  // pos: (col, row) pairs
+  std::sort(pos.begin(), pos.end());
+  pos.erase(std::unique(pos.begin(), pos.end()), pos.end());
+  Pattern p;
+  p.rows = rows;
+  p.cols = cols;
+  p.colptr.assign(cols + 1, 0);
+  p.rowidx.reserve(pos.size());
+  for (auto& [c, r] : pos) {
+    ++p.colptr[c + 1];
+    p.rowidx.push_back(r);
+  }
+  for (int32_t c = 0; c < cols; ++c) p.colptr[c + 1] += p.colptr[c];
+  return p;
+}
+
+/// Growing gather description: sources are appended per final entry.
+struct GatherBuilder {
+  std::vector<std::vector<std::pair<int32_t, int32_t>>> src;  // (idx, scale)
+  explicit GatherBuilder(int64_t n) : src(n) {}
+  void add(int64_t entry, int32_t stage, int32_t scale, bool negate = false) {
+    src[entry].emplace_back(negate ? (stage | int32_t(0x80000000)) : stage,
+                            scale);
+  }
+  Gather finish() const {
+    Gather g;
+    g.ptr.assign(src.size() + 1, 0);
+    for (size_t e = 0; e < src.size(); ++e) {
+      g.ptr[e + 1] = g.ptr[e] + static_cast<int32_t>(src[e].size());
+    }
+    g.src_idx.reserve(g.ptr.back());
+    g.src_scale.reserve(g.ptr.back());
+    for (const auto& list : src) {
+      for (auto [i, s] : list) {
+        g.src_idx.push_back(i);
+        g.src_scale.push_back(s);
+      }
+    }
+    return g;
+  }
+};
+
+struct Compiler {
+  const Tape& tape;
+  std::string& error;
+
+  // scratch indexed by node id
+  std::vector<int32_t> pos;       // position in the current row list, −1 idle
+  std::vector<int32_t> cnt;       // in-row parent count
+  std::vector<int32_t> stamp;     // generic visitation stamp
+  std::vector<int32_t> local;     // local slot in the current cluster
+  std::vector<int32_t> owner;     // first sub-row that touched an interior node
+  std::vector<int32_t> outcol;    // output column of a node in the current row
+  int32_t stamp_counter = 0;
+
+  Compiler(const Tape& t, std::string& err) : tape{t}, error{err} {
+    pos.assign(t.n_nodes, -1);
+    cnt.assign(t.n_nodes, 0);
+    stamp.assign(t.n_nodes, 0);
+    local.assign(t.n_nodes, -1);
+    outcol.assign(t.n_nodes, -1);
+  }
+
+  bool is_interior(int32_t node) const { return tape.lhs[node] >= 0; }
+
+  /// Splits `list` (a whole row) into sub-rows at a long root sum.
+  /// `make` is called once per sub-row with (seed, nodes).
+  template <typename F>
+  void split_row(const int32_t* list, int32_t len, F&& make) {
+    if (len == 0) return;
+    const int32_t root = list[0];
+    // in-row parent counts
+    for (int32_t i = 0; i < len; ++i) {
+      const int32_t nd = list[i];
+      if (tape.lhs[nd] >= 0) ++cnt[tape.lhs[nd]];
+      if (tape.rhs[nd] >= 0) ++cnt[tape.rhs[nd]];
+    }
+    std::vector<std::pair<int32_t, int8_t>> terms;
+    std::vector<std::pair<int32_t, int8_t>> stack{{root, int8_t(1)}};
+    while (!stack.empty()) {
+      auto [nd, sg] = stack.back();
+      stack.pop_back();
+      const uint8_t op = tape.op[nd];
+      if (is_sum_op(op) && (nd == root || cnt[nd] == 1)) {
+        if (op == SLPB_OP_NEG) {
+          stack.emplace_back(tape.lhs[nd], int8_t(-sg));
+        } else {
+          // push rhs first so that lhs is expanded first (left-to-right terms)
+          stack.emplace_back(tape.rhs[nd],
+                             op == SLPB_OP_SUB ? int8_t(-sg) : sg);
+          stack.emplace_back(tape.lhs[nd], sg);
+        }
+      } else {
+        terms.emplace_back(nd, sg);
+      }
+    }
+    for (int32_t i = 0; i < len; ++i) cnt[list[i]] = 0;
+
+    if (static_cast<int>(terms.size()) < kSplitThreshold) {
+      make(int8_t(1), std::vector<int32_t>(list, list + len));
+      return;
+    }
+    for (int32_t i = 0; i < len; ++i) pos[list[i]] = i;
+    std::vector<int32_t> reach, dfs;
+    for (auto [troot, sg] : terms) {
+      ++stamp_counter;
+      reach.clear();
+      dfs.assign(1, troot);
+      stamp[troot] = stamp_counter;
+      while (!dfs.empty()) {
+        int32_t nd = dfs.back();
+        dfs.pop_back();
+        reach.push_back(nd);
+        for (int32_t ch : {tape.lhs[nd], tape.rhs[nd]}) {
+          if (ch >= 0 && stamp[ch] != stamp_counter) {
+            stamp[ch] = stamp_counter;
+            dfs.push_back(ch);
+          }
+        }
+      }
+      std::sort(reach.begin(), reach.end(),
+                [&](int32_t a, int32_t b) { return pos[a] < pos[b]; });
+      make(sg, reach);
+    }
+    for (int32_t i = 0; i < len; ++i) pos[list[i]] = -1;
+  }
+
+  /// Fills sr.flags and drops nodes that are neither active nor value-needed
+  /// (e.g. the −y_j term of a Lagrangian-gradient row: it feeds no output and
+  /// no partial, and would otherwise chain all time steps into one cluster).
+  void analyze_subrow(SubRow& sr) {
+    const int32_t len = static_cast<int32_t>(sr.nodes.size());
+    sr.flags.assign(len, 0);
+    if (sr.is_value) {
+      std::fill(sr.flags.begin(), sr.flags.end(), kValue);
+      return;
+    }
+    for (int32_t i = 0; i < len; ++i) pos[sr.nodes[i]] = i;
+    for (auto& [stage, nd] : sr.outs) sr.flags[pos[nd]] |= kActive;
+    for (int32_t i = len - 1; i >= 0; --i) {
+      const int32_t nd = sr.nodes[i];
+      if (!is_interior(nd)) continue;
+      const int32_t l = tape.lhs[nd], r = tape.rhs[nd];
+      if ((sr.flags[pos[l]] & kActive) ||
+          (r >= 0 && (sr.flags[pos[r]] & kActive))) {
+        sr.flags[i] |= kActive;
+      }
+    }
+    for (int32_t i = 0; i < len; ++i) {  // parent→child: one pass closes it
+      const int32_t nd = sr.nodes[i];
+      if (!is_interior(nd)) continue;
+      const int32_t l = tape.lhs[nd], r = tape.rhs[nd];
+      if (sr.flags[i] & kValue) {
+        sr.flags[pos[l]] |= kValue;
+        if (r >= 0) sr.flags[pos[r]] |= kValue;
+      }
+      if (sr.flags[i] & kActive) {
+        for (int side = 0; side < 2; ++side) {
+          const int32_t ch = side == 0 ? l : r;
+          if (ch < 0 || !(sr.flags[pos[ch]] & kActive)) continue;
+          const uint8_t needs = grad_value_needs(tape.op[nd], side);
+          if (needs & 1) sr.flags[pos[l]] |= kValue;
+          if ((needs & 2) && r >= 0) sr.flags[pos[r]] |= kValue;
+        }
+      }
+    }
+    for (int32_t i = 0; i < len; ++i) pos[sr.nodes[i]] = -1;
+    int32_t w = 0;
+    for (int32_t i = 0; i < len; ++i) {
+      if (sr.flags[i] == 0) continue;
+      sr.nodes[w] = sr.nodes[i];
+      sr.flags[w] = sr.flags[i];
+      ++w;
+    }
+    sr.nodes.resize(w);
+    sr.flags.resize(w);
+  }
+
+  /// Builds clusters + programs for `subs`.
+  bool build_programs(std::vector<SubRow>& subs, ProgramSet& ps) {
+    const int32_t ns = static_cast<int32_t>(subs.size());
+    // --- clusters: union-find over sub-rows that share an interior node ----
+    std::vector<int32_t> uf(ns);
+    std::iota(uf.begin(), uf.end(), 0);
+    auto find = [&](int32_t a) {
+      while (uf[a] != a) a = uf[a] = uf[uf[a]];
+      return a;
+    };
+    owner.assign(tape.n_nodes, -1);
+    for (int32_t s = 0; s < ns; ++s) analyze_subrow(subs[s]);
+    for (int32_t s = 0; s < ns; ++s) {
+      const SubRow& sr = subs[s];
+      for (size_t i = 0; i < sr.nodes.size(); ++i) {
+        const int32_t nd = sr.nodes[i];
+        if (!is_interior(nd) || !(sr.flags[i] & kValue)) continue;
+        if (owner[nd] < 0) {
+          owner[nd] = s;
+        } else {
+          int32_t a = find(owner[nd]), b = find(s);
+          if (a != b) uf[std::max(a, b)] = std::min(a, b);
+        }
+      }
+    }
+    std::vector<int32_t> cluster_of(ns);
+    std::vector<std::vector<int32_t>> members;
+    {
+      std::vector<int32_t> cid(ns, -1);
+      for (int32_t s = 0; s < ns; ++s) {
+        int32_t r = find(s);
+        if (cid[r] < 0) {
+          cid[r] = static_cast<int32_t>(members.size());
+          members.emplace_back();
+        }
+        cluster_of[s] = cid[r];
+        members[cid[r]].push_back(s);
+      }
+    }
+
+    std::unordered_map<uint64_t, std::vector<int32_t>> by_hash;
+    std::vector<uint32_t> prog;       // program being built
+    std::vector<int32_t> cl_nodes;    // nodes of the cluster, first-seen order
+    std::vector<int32_t> level;       // per local slot
+    std::vector<int32_t> sorted_ids;
+
+    std::fill(local.begin(), local.end(), -1);
+
+    for (const auto& mem : members) {
+      // --- local slots, first appearance order ----------------------------
+      cl_nodes.clear();
+      for (int32_t s : mem) {
+        const SubRow& sr = subs[s];
+        for (size_t i = 0; i < sr.nodes.size(); ++i) {
+          const int32_t nd = sr.nodes[i];
+          if ((sr.flags[i] & kValue) && local[nd] < 0) {
+            local[nd] = static_cast<int32_t>(cl_nodes.size());
+            cl_nodes.push_back(nd);
+          }
+        }
+      }
+      const int32_t n_slots = static_cast<int32_t>(cl_nodes.size());
+      if (n_slots > 65535) {
+        error = "an expression cluster has more than 65535 nodes; the block-"
+                "cooperative fallback for such graphs is not implemented";
+        return false;
+      }
+      // --- forward levels ----------------------------------------------------
+      sorted_ids.assign(cl_nodes.begin(), cl_nodes.end());
+      std::sort(sorted_ids.begin(), sorted_ids.end());
+      level.assign(n_slots, 0);
+      int32_t max_level = 0;
+      for (int32_t nd : sorted_ids) {
+        if (!is_interior(nd)) continue;
+        int32_t lv = level[local[tape.lhs[nd]]];
+        if (tape.rhs[nd] >= 0) lv = std::max(lv, level[local[tape.rhs[nd]]]);
+        level[local[nd]] = lv + 1;
+        max_level = std::max(max_level, lv + 1);
+      }
+      std::vector<std::vector<int32_t>> fwd_levels(max_level);  // local slots
+      std::vector<uint16_t> leaf_slots, const_slots;
+      std::vector<int32_t> leaf_index;
+      std::vector<double> const_vals;
+      for (int32_t slot = 0; slot < n_slots; ++slot) {
+        const int32_t nd = cl_nodes[slot];
+        if (is_interior(nd)) {
+          fwd_levels[level[slot] - 1].push_back(slot);
+        } else if (tape.op[nd] == SLPB_OP_VAR) {
+          if (tape.leaf_of_node[nd] < 0) {
+            error = "the tape contains a decision-variable node that is not a "
+                    "decision variable, y multiplier or z multiplier";
+            return false;
+          }
+          leaf_slots.push_back(static_cast<uint16_t>(slot));
+          leaf_index.push_back(tape.leaf_of_node[nd]);
+        } else {
+          const_slots.push_back(static_cast<uint16_t>(slot));
+          const_vals.push_back(tape.val[nd]);
+        }
+      }
+      // --- reverse visits -----------------------------------------------------
+      struct VisitTmp {
+        int32_t adj, rlevel, seed;
+        std::vector<Contrib> contribs;
+      };
+      std::vector<VisitTmp> visits;
+      std::vector<uint16_t> adj_out_slots, val_out_slots;
+      std::vector<int32_t> adj_out_stage, val_out_stage;
+      for (int32_t s : mem) {
+        SubRow& sr = subs[s];
+        if (sr.is_value) {
+          val_out_slots.push_back(static_cast<uint16_t>(local[sr.nodes[0]]));
+          val_out_stage.push_back(sr.value_stage);
+          continue;
+        }
+        const int32_t len = static_cast<int32_t>(sr.nodes.size());
+        // one visit per active node, in list order; pos[] = visit index
+        for (int32_t i = 0; i < len; ++i) {
+          const int32_t nd = sr.nodes[i];
+          if (!(sr.flags[i] & kActive)) continue;
+          pos[nd] = static_cast<int32_t>(visits.size());
+          visits.push_back({static_cast<int32_t>(visits.size()), 0, 0, {}});
+        }
+        if (pos[sr.nodes[0]] >= 0) visits[pos[sr.nodes[0]]].seed = sr.seed;
+        for (int32_t i = 0; i < len; ++i) {
+          const int32_t nd = sr.nodes[i];
+          if (pos[nd] < 0 || !is_interior(nd)) continue;
+          const int32_t l = tape.lhs[nd], r = tape.rhs[nd];
+          const VisitTmp& pv = visits[pos[nd]];
+          // operands a partial does not read may have no slot: point at 0
+          const uint16_t ls = static_cast<uint16_t>(std::max(local[l], 0));
+          const uint16_t rs =
+              r >= 0 ? static_cast<uint16_t>(std::max(local[r], 0)) : ls;
+          for (int side = 0; side < 2; ++side) {
+            const int32_t ch = side == 0 ? l : r;
+            if (ch < 0 || pos[ch] < 0) continue;
+            VisitTmp& cv = visits[pos[ch]];
+            cv.contribs.push_back({static_cast<uint16_t>(pv.adj), ls, rs,
+                                   tape.op[nd], static_cast<uint8_t>(side)});
+            cv.rlevel = std::max(cv.rlevel, pv.rlevel + 1);
+          }
+        }
+        for (auto& [stage, nd] : sr.outs) {
+          adj_out_slots.push_back(static_cast<uint16_t>(pos[nd]));
+          adj_out_stage.push_back(stage);
+        }
+        for (int32_t i = 0; i < len; ++i) pos[sr.nodes[i]] = -1;
+      }
+      const int32_t n_adj = static_cast<int32_t>(visits.size());
+      if (n_adj > 65535) {
+        error = "an expression cluster needs more than 65535 adjoint slots";
+        return false;
+      }
+      int32_t max_rlevel = -1;
+      for (auto& v : visits) max_rlevel = std::max(max_rlevel, v.rlevel);
+      std::vector<std::vector<int32_t>> rev_levels(max_rlevel + 1);
+      for (int32_t i = 0; i < n_adj; ++i) {
+        rev_levels[visits[i].rlevel].push_back(i);
+      }
+
+      // --- emit program ---------------------------------------------------------
+      prog.assign(kProgHeaderWords, 0);
+      auto align2 = [&] {
+        if (prog.size() & 1) prog.push_back(0);
+      };
+      auto push_u16s = [&](const std::vector<uint16_t>& v) {
+        const size_t off = prog.size();
+        prog.resize(off + (v.size() + 1) / 2, 0);
+        if (!v.empty()) {
+          std::memcpy(prog.data() + off, v.data(), v.size() * sizeof(uint16_t));
+        }
+        return static_cast<uint32_t>(off);
+      };
+      prog[0] = n_slots;
+      prog[1] = n_adj;
+      prog[2] = static_cast<uint32_t>(leaf_slots.size());
+      prog[3] = static_cast<uint32_t>(const_slots.size());
+      prog[4] = static_cast<uint32_t>(fwd_levels.size());
+      prog[5] = static_cast<uint32_t>(rev_levels.size());
+      prog[6] = static_cast<uint32_t>(val_out_slots.size());
+      prog[7] = static_cast<uint32_t>(adj_out_slots.size());
+      prog[8] = push_u16s(leaf_slots);
+      prog[9] = push_u16s(const_slots);
+      int32_t max_width = 1;
+      // forward
+      prog[10] = static_cast<uint32_t>(prog.size());
+      {
+        uint32_t run = 0;
+        prog.push_back(run);
+        for (auto& lv : fwd_levels) {
+          run += static_cast<uint32_t>(lv.size());
+          prog.push_back(run);
+          max_width = std::max<int32_t>(max_width, lv.size());
+        }
+      }
+      align2();
+      prog[11] = static_cast<uint32_t>(prog.size());
+      for (auto& lv : fwd_levels) {
+        for (int32_t slot : lv) {
+          const int32_t nd = cl_nodes[slot];
+          FwdInstr in{};
+          in.dst = static_cast<uint16_t>(slot);
+          in.a = static_cast<uint16_t>(local[tape.lhs[nd]]);
+          in.b = tape.rhs[nd] >= 0 ? static_cast<uint16_t>(local[tape.rhs[nd]])
+                                   : in.a;
+          in.op = tape.op[nd];
+          uint32_t w[2];
+          std::memcpy(w, &in, 8);
+          prog.push_back(w[0]);
+          prog.push_back(w[1]);
+          ++ps.n_instr;
+        }
+      }
+      // reverse
+      prog[12] = static_cast<uint32_t>(prog.size());
+      {
+        uint32_t run = 0;
+        prog.push_back(run);
+        for (auto& lv : rev_levels) {
+          run += static_cast<uint32_t>(lv.size());
+          prog.push_back(run);
+          max_width = std::max<int32_t>(max_width, lv.size());
+        }
+      }
+      align2();
+      prog[13] = static_cast<uint32_t>(prog.size());
+      {
+        uint32_t crun = 0;
+        for (auto& lv : rev_levels) {
+          for (int32_t vi : lv) {
+            const VisitTmp& v = visits[vi];
+            Visit rec{};
+            rec.adj = static_cast<uint16_t>(v.adj);
+            if (v.contribs.empty()) {
+              // a root (seeded) visit; an unseeded node without parents cannot
+              // occur because every non-root node of a list has a parent in it
+              rec.n_contrib = 0;
+              rec.seed = static_cast<int8_t>(v.seed);
+              rec.contrib_begin = 0;
+            } else {
+              if (v.contribs.size() > 254) {
+                error = "a node has more than 254 parents inside one row";
+                return false;
+              }
+              rec.n_contrib = static_cast<uint8_t>(v.contribs.size());
+              rec.seed = 0;
+              rec.contrib_begin = crun;
+              crun += static_cast<uint32_t>(v.contribs.size());
+            }
+            uint32_t w[2];
+            std::memcpy(w, &rec, 8);
+            prog.push_back(w[0]);
+            prog.push_back(w[1]);
+            ++ps.n_visits;
+          }
+        }
+      }
+      prog[14] = static_cast<uint32_t>(prog.size());
+      for (auto& lv : rev_levels) {
+        for (int32_t vi : lv) {
+          for (const Contrib& c : visits[vi].contribs) {
+            uint32_t w[2];
+            std::memcpy(w, &c, 8);
+            prog.push_back(w[0]);
+            prog.push_back(w[1]);
+            ++ps.n_contribs;
+          }
+        }
+      }
+      prog[15] = push_u16s(val_out_slots);
+      prog[16] = push_u16s(adj_out_slots);
+      prog[17] = static_cast<uint32_t>(max_width);
+      align2();
+
+      // --- de-duplicate --------------------------------------------------------
+      uint64_t h = 1469598103934665603ull;
+      for (uint32_t w : prog) {
+        h ^= w;
+        h *= 1099511628211ull;
+      }
+      int32_t pid = -1;
+      for (int32_t cand : by_hash[h]) {
+        const int64_t off = ps.prog_offset[cand];
+        const int64_t len = (cand + 1 < (int32_t)ps.prog_offset.size()
+                                 ? ps.prog_offset[cand + 1]
+                                 : (int64_t)ps.blob.size()) -
+                            off;
+        if (len == (int64_t)prog.size() &&
+            std::memcmp(ps.blob.data() + off, prog.data(),
+                        prog.size() * 4) == 0) {
+          pid = cand;
+          break;
+        }
+      }
+      if (pid < 0) {
+        pid = static_cast<int32_t>(ps.prog_offset.size());
+        ps.prog_offset.push_back(static_cast<int64_t>(ps.blob.size()));
+        ps.blob.insert(ps.blob.end(), prog.begin(), prog.end());
+        const int32_t smem = (n_slots + n_adj) * 8;
+        ps.prog_smem.push_back(smem);
+        ps.prog_width.push_back(max_width);
+        ps.max_smem = std::max(ps.max_smem, smem);
+        by_hash[h].push_back(pid);
+      }
+      // --- binding ---------------------------------------------------------------
+      if (ps.bindings.size() & 1) ps.bindings.push_back(0);
+      ps.cluster_prog.push_back(pid);
+      ps.cluster_bind.push_back(static_cast<int64_t>(ps.bindings.size()));
+      auto push_i32s = [&](const std::vector<int32_t>& v) {
+        const size_t off = ps.bindings.size();
+        ps.bindings.resize(off + v.size());
+        if (!v.empty()) std::memcpy(ps.bindings.data() + off, v.data(), v.size() * 4);
+      };
+      push_i32s(leaf_index);
+      if (ps.bindings.size() & 1) ps.bindings.push_back(0);
+      {
+        const size_t off = ps.bindings.size();
+        ps.bindings.resize(off + const_vals.size() * 2);
+        if (!const_vals.empty()) {
+          std::memcpy(ps.bindings.data() + off, const_vals.data(),
+                      const_vals.size() * 8);
+        }
+      }
+      push_i32s(val_out_stage);
+      push_i32s(adj_out_stage);
+
+      for (int32_t nd : cl_nodes) local[nd] = -1;
+    }
+    return true;
+  }
+};
+
+}  // namespace
+
+bool compile_autodiff(const Tape& tape, const RowSet rows[SLPB_OUT_COUNT],
+                      bool ignore_h_c, CompiledAD& out) {
+  out = CompiledAD{};
+  Compiler C{tape, out.error};
+  const int32_t n = tape.n_x, me = tape.n_y, mi = tape.n_z;
+
+  // ---- static patterns ---------------------------------------------------------
+  auto jac_pattern = [&](const RowSet& rs, int32_t nrows) {
+    std::vector<std::pair<int32_t, int32_t>> posv;
+    if (rs.present) {
+      for (size_t k = 0; k < rs.cached_row.size(); ++k) {
+        posv.emplace_back(rs.cached_col[k], rs.cached_row[k]);
+      }
+      for (int32_t r = 0; r < rs.n_rows; ++r) {
+        if (!rs.row_swept[r]) continue;
+        for (int32_t k = rs.out_ptr[r]; k < rs.out_ptr[r + 1]; ++k) {
+          posv.emplace_back(rs.out_col[k], r);
+        }
+      }
+    }
+    return pattern_from_positions(nrows, n, posv);
+  };
+  out.A_e = jac_pattern(rows[SLPB_OUT_A_E], me);
+  out.A_i = jac_pattern(rows[SLPB_OUT_A_I], mi);
+  {
+    std::vector<std::pair<int32_t, int32_t>> posv;
+    for (int which : {SLPB_OUT_H_F, SLPB_OUT_H_C}) {
+      const RowSet& rs = rows[which];
+      if (!rs.present || (which == SLPB_OUT_H_C && ignore_h_c)) continue;
+      for (size_t k = 0; k < rs.cached_row.size(); ++k) {
+        if (rs.cached_row[k] >= rs.cached_col[k]) {
+          posv.emplace_back(rs.cached_col[k], rs.cached_row[k]);
+        }
+      }
+      for (int32_t r = 0; r < rs.n_rows; ++r) {
+        if (!rs.row_swept[r]) continue;
+        for (int32_t k = rs.out_ptr[r]; k < rs.out_ptr[r + 1]; ++k) {
+          if (r >= rs.out_col[k]) posv.emplace_back(rs.out_col[k], r);
+        }
+      }
+    }
+    out.H = pattern_from_positions(n, n, posv);
+  }
+  out.off_g = 0;
+  out.off_ae = n;
+  out.off_ai = out.off_ae + out.A_e.nnz();
+  out.off_h = out.off_ai + out.A_i.nnz();
+  const int64_t n_deriv_entries = out.off_h + out.H.nnz();
+  GatherBuilder dgather{n_deriv_entries};
+  GatherBuilder vgather{1 + int64_t(me) + mi};
+
+  // scale references: −1 → 1, −2 → d_f, k ≥ 0 → [d_ce | d_ci][k]
+  auto scale_of = [&](int which, int32_t row) -> int32_t {
+    switch (which) {
+      case SLPB_OUT_F: case SLPB_OUT_G: case SLPB_OUT_H_F: return -2;
+      case SLPB_OUT_C_E: case SLPB_OUT_A_E: return row;
+      case SLPB_OUT_C_I: case SLPB_OUT_A_I: return me + row;
+      default: return -1;
+    }
+  };
+  auto deriv_entry = [&](int which, int32_t row, int32_t col) -> int64_t {
+    switch (which) {
+      case SLPB_OUT_G: return out.off_g + col;
+      case SLPB_OUT_A_E: return out.off_ae + out.A_e.find(row, col);
+      case SLPB_OUT_A_I: return out.off_ai + out.A_i.find(row, col);
+      default: return row >= col ? out.off_h + out.H.find(row, col) : -1;
+    }
+  };
+
+  // ---- derivative sub-rows -------------------------------------------------------
+  std::vector<SubRow> dsubs;
+  for (int which : {SLPB_OUT_G, SLPB_OUT_A_E, SLPB_OUT_A_I, SLPB_OUT_H_F,
+                    SLPB_OUT_H_C}) {
+    const RowSet& rs = rows[which];
+    if (!rs.present || (which == SLPB_OUT_H_C && ignore_h_c)) continue;
+    const bool hess = which == SLPB_OUT_H_F || which == SLPB_OUT_H_C;
+    // constants: cached triplets of LINEAR rows
+    for (size_t k = 0; k < rs.cached_row.size(); ++k) {
+      const int32_t r = rs.cached_row[k], c = rs.cached_col[k];
+      if (hess && r < c) continue;
+      const int32_t slot = static_cast<int32_t>(out.deriv_stage_init.size());
+      out.deriv_stage_init.push_back(rs.cached_val[k]);
+      dgather.add(deriv_entry(which, r, c), slot, scale_of(which, r));
+    }
+  }
+  const int32_t n_deriv_const = static_cast<int32_t>(out.deriv_stage_init.size());
+  int32_t next_stage = n_deriv_const;
+  for (int which : {SLPB_OUT_G, SLPB_OUT_A_E, SLPB_OUT_A_I, SLPB_OUT_H_F,
+                    SLPB_OUT_H_C}) {
+    const RowSet& rs = rows[which];
+    if (!rs.present || (which == SLPB_OUT_H_C && ignore_h_c)) continue;
+    const bool hess = which == SLPB_OUT_H_F || which == SLPB_OUT_H_C;
+    for (int32_t r = 0; r < rs.n_rows; ++r) {
+      if (!rs.row_swept[r]) continue;
+      const int32_t b = rs.row_ptr[r], e = rs.row_ptr[r + 1];
+      // outputs of the row that survive the triangle filter
+      int32_t n_outs = 0;
+      for (int32_t k = rs.out_ptr[r]; k < rs.out_ptr[r + 1]; ++k) {
+        if (hess && r < rs.out_col[k]) continue;
+        C.outcol[rs.out_node[k]] = rs.out_col[k];
+        ++n_outs;
+      }
+      if (n_outs > 0) {
+        C.split_row(rs.row_nodes.data() + b, e - b,
+                    [&](int8_t seed, std::vector<int32_t> nodes) {
+                      SubRow sr;
+                      sr.out = which;
+                      sr.row = r;
+                      sr.seed = seed;
+                      // outputs inside this sub-row, in list order (the order
+                      // of the reference's output lists, jacobian.hpp:65-72)
+                      for (int32_t nd : nodes) {
+                        const int32_t col = C.outcol[nd];
+                        if (col < 0) continue;
+                        sr.outs.emplace_back(next_stage, nd);
+                        dgather.add(deriv_entry(which, r, col), next_stage,
+                                    scale_of(which, r));
+                        ++next_stage;
+                      }
+                      if (sr.outs.empty()) return;
+                      sr.nodes = std::move(nodes);
+                      dsubs.push_back(std::move(sr));
+                    });
+      }
+      for (int32_t k = rs.out_ptr[r]; k < rs.out_ptr[r + 1]; ++k) {
+        C.outcol[rs.out_node[k]] = -1;
+      }
+    }
+  }
+  out.deriv_stage_size = next_stage;
+  out.deriv_stage_init.resize(next_stage, 0.0);
+  if (!C.build_programs(dsubs, out.derivs)) return false;
+  out.deriv_gather = dgather.finish();
+
+  // ---- value sub-rows ------------------------------------------------------------
+  std::vector<SubRow> vsubs;
+  int32_t next_vstage = 0;
+  auto value_entry = [&](int which, int32_t row) -> int64_t {
+    return which == SLPB_OUT_F ? 0
+           : which == SLPB_OUT_C_E ? 1 + row : 1 + int64_t(me) + row;
+  };
+  std::vector<double> vconst;
+  struct PendingConst { int64_t entry; int32_t scale; double v; };
+  std::vector<PendingConst> pend;
+  for (int which : {SLPB_OUT_F, SLPB_OUT_C_E, SLPB_OUT_C_I}) {
+    const RowSet& rs = rows[which];
+    if (!rs.present) continue;
+    for (int32_t r = 0; r < rs.n_rows; ++r) {
+      const int32_t b = rs.row_ptr[r], e = rs.row_ptr[r + 1];
+      if (e == b) {
+        pend.push_back({value_entry(which, r), scale_of(which, r),
+                        rs.const_val.empty() ? 0.0 : rs.const_val[r]});
+        continue;
+      }
+      C.split_row(rs.row_nodes.data() + b, e - b,
+                  [&](int8_t seed, std::vector<int32_t> nodes) {
+                    SubRow sr;
+                    sr.out = which;
+                    sr.row = r;
+                    sr.seed = seed;
+                    sr.is_value = true;
+                    sr.value_stage = next_vstage;
+                    vgather.add(value_entry(which, r), next_vstage,
+                                scale_of(which, r), seed < 0);
+                    ++next_vstage;
+                    sr.nodes = std::move(nodes);
+                    vsubs.push_back(std::move(sr));
+                  });
+    }
+  }
+  // constants go after the swept slots for the value stage
+  out.value_stage_init.assign(next_vstage, 0.0);
+  for (auto& p : pend) {
+    vgather.add(p.entry, static_cast<int32_t>(out.value_stage_init.size()),
+                p.scale);
+    out.value_stage_init.push_back(p.v);
+  }
+  out.value_stage_size = static_cast<int32_t>(out.value_stage_init.size());
+  if (!C.build_programs(vsubs, out.values)) return false;
+  out.value_gather = vgather.finish();
+  return true;
+}
+
+}  // namespace slpb

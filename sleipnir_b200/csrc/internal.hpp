@@ -1,0 +1,202 @@
+// Internal declarations shared by the translation units of libslpb.so.
+// Nothing here crosses the C ABI (include/slpb.h).
+#pragma once
+
+#include <cstdint>
+#include <string>
+#include <utility>
+#include <vector>
+
+#include "slpb.h"
+
+namespace slpb {
+
+// ---------------------------------------------------------------------------
+// Host copy of what the caller uploaded
+// ---------------------------------------------------------------------------
+
+struct Tape {
+  int32_t n_nodes = 0;
+  std::vector<uint8_t> op;
+  std::vector<int32_t> lhs, rhs;
+  std::vector<double> val;
+  int32_t n_x = 0, n_y = 0, n_z = 0;
+  /// node id → index into the concatenated leaf vector [x | d_ce⊙y | d_ci⊙z],
+  /// or −1 for a node that is not a leaf of the problem.
+  std::vector<int32_t> leaf_of_node;
+};
+
+struct RowSet {
+  bool present = false;
+  int32_t n_rows = 0, n_cols = 0;
+  std::vector<int32_t> row_ptr, row_nodes, out_ptr, out_col, out_node;
+  std::vector<uint8_t> row_swept;
+  std::vector<int32_t> cached_row, cached_col;
+  std::vector<double> cached_val;
+  std::vector<double> const_val;  // value rows with an empty list
+};
+
+/// Compressed sparse column pattern (Eigen ColMajor layout, 32-bit indices).
+struct Pattern {
+  int32_t rows = 0, cols = 0;
+  std::vector<int32_t> colptr, rowidx;
+  int64_t nnz() const { return static_cast<int64_t>(rowidx.size()); }
+  /// Index of entry (r, c), or −1.
+  int64_t find(int32_t r, int32_t c) const;
+};
+
+// ---------------------------------------------------------------------------
+// Compiled autodiff programs (built by compile.cpp, run by ad_kernels.cu)
+// ---------------------------------------------------------------------------
+//
+// A *cluster* is a connected set of rows that share interior nodes; it is
+// evaluated by one warp with its values and adjoints in shared memory. A
+// *program* is the position-independent code of a cluster (local slot
+// numbers only); clusters whose programs are byte-identical share one copy —
+// every time step of a direct transcription ends up on the same program, with
+// its own *binding* (global leaf indices, constants, output slots).
+//
+// Program blob, 32-bit words:
+//   [0] n_slots      value slots (leaves, constants, interior nodes)
+//   [1] n_adj        adjoint slots (one per (row, node) visit)
+//   [2] n_leaf       [3] n_const
+//   [4] n_fwd_levels [5] n_rev_levels
+//   [6] n_val_out    [7] n_adj_out
+//   [8] off_leaf_slot   u16[n_leaf]   (word offsets from blob start)
+//   [9] off_const_slot  u16[n_const]
+//   [10] off_fwd_lvl    u32[n_fwd_levels+1]  instruction ranges per level
+//   [11] off_fwd        FwdInstr[...]
+//   [12] off_rev_lvl    u32[n_rev_levels+1]  visit ranges per level
+//   [13] off_visit      Visit[...]
+//   [14] off_contrib    Contrib[...]
+//   [15] off_val_out    u16[n_val_out]  value slot of each value output
+//   [16] off_adj_out    u16[n_adj_out]  adjoint slot of each derivative output
+//   [17] max_width      widest level (forward or reverse)
+//   [18..23] reserved
+// Binding record of a cluster, 32-bit words:
+//   leaf_index  i32[n_leaf]      index into the leaf vector
+//   const_val   f64[n_const]     (8-byte aligned)
+//   val_out     i32[n_val_out]   stage slot of each value output
+//   adj_out     i32[n_adj_out]   stage slot of each derivative output
+
+constexpr int kProgHeaderWords = 24;
+
+struct FwdInstr {  // 8 bytes
+  uint16_t dst, a, b;
+  uint8_t op, pad;
+};
+struct Visit {  // 8 bytes
+  uint32_t contrib_begin;  // index into the program's Contrib array
+  uint16_t adj;            // adjoint slot written by this visit
+  uint8_t n_contrib;       // 255 = more than 254: count in next visit's begin
+  int8_t seed;             // root visits: adjoint = seed (±1); else 0
+};
+struct Contrib {  // 8 bytes
+  uint16_t parent_adj, l, r;
+  uint8_t op, side;  // side: 0 → ∂/∂lhs, 1 → ∂/∂rhs
+};
+
+struct ProgramSet {
+  // one entry per distinct program
+  std::vector<uint32_t> blob;          // all programs back to back
+  std::vector<int64_t> prog_offset;    // word offset of each program
+  std::vector<int32_t> prog_smem;      // bytes of shared memory per cluster
+  std::vector<int32_t> prog_width;     // widest level
+  // one entry per cluster
+  std::vector<int32_t> cluster_prog;
+  std::vector<int64_t> cluster_bind;   // word offset into `bindings`
+  std::vector<uint32_t> bindings;
+  int64_t n_instr = 0, n_visits = 0, n_contribs = 0;  // totals over clusters
+  int32_t max_smem = 0;
+};
+
+/// out[e] = Σ_k scale(k) · stage[src_idx[k]] over k ∈ [ptr[e], ptr[e+1]).
+struct Gather {
+  std::vector<int32_t> ptr;        // n_entries + 1
+  std::vector<int32_t> src_idx;    // stage slot
+  std::vector<int32_t> src_scale;  // −1: 1, −2: d_f, ≥0: index into [d_ce|d_ci]
+  int32_t n_entries() const { return static_cast<int32_t>(ptr.size()) - 1; }
+};
+
+struct CompiledAD {
+  // value programs (f, c_e, c_i) and derivative programs (g, A_e, A_i, H)
+  ProgramSet values, derivs;
+  // stage arrays: [constants | swept outputs]; constants are uploaded once
+  std::vector<double> value_stage_init, deriv_stage_init;
+  int32_t value_stage_size = 0, deriv_stage_size = 0;
+  // final entries, in this order: values: [f | c_e | c_i];
+  // derivatives: [g (n) | A_e.val | A_i.val | H.val]
+  Gather value_gather, deriv_gather;
+  Pattern A_e, A_i, H;  // H: lower triangle of d_f·H_f + H_c
+  int64_t off_g = 0, off_ae = 0, off_ai = 0, off_h = 0;  // into deriv entries
+  std::string error;
+};
+
+bool ingest_tape(Tape& t, int32_t n_nodes, const uint8_t* op,
+                 const int32_t* lhs, const int32_t* rhs, const double* val,
+                 int32_t n_x, const int32_t* leaf_x, int32_t n_y,
+                 const int32_t* leaf_y, int32_t n_z, const int32_t* leaf_z,
+                 std::string& error);
+bool ingest_rows(RowSet& r, const Tape& t, int which, const slpb_rowset* rows,
+                 const double* const_val, std::string& error);
+
+bool compile_autodiff(const Tape& tape, const RowSet rows[SLPB_OUT_COUNT],
+                      bool ignore_h_c, CompiledAD& out);
+
+// ---------------------------------------------------------------------------
+// Symbolic analysis of the reduced KKT system (symbolic.cpp)
+// ---------------------------------------------------------------------------
+
+/// How each lower-triangle entry of lhs = [H + tril(A_iᵀΣA_i); A_e] is
+/// computed from H.val, A_e.val, A_i.val and Σ.
+struct KktRecipe {
+  Pattern K;                       // lower triangle incl. full diagonal
+  std::vector<int32_t> h_idx;      // per K entry: index into H.val or −1
+  std::vector<int32_t> ae_idx;     // per K entry: index into A_e.val or −1
+  std::vector<int32_t> prod_ptr;   // per K entry: range of A_iᵀΣA_i terms
+  std::vector<int32_t> prod_a, prod_b, prod_row;  // A_i.val idx ×2, ineq row
+  std::vector<int32_t> diag_idx;   // per column: K entry of the diagonal
+};
+
+void build_kkt_recipe(int32_t n, int32_t me, const Pattern& H,
+                      const Pattern& A_e, const Pattern& A_i, KktRecipe& out);
+
+/// Supernodal multifrontal plan. Fronts are dense, column-major, of order
+/// `front_dim`, the first `n_piv` rows/cols being the supernode's own columns.
+struct Symbolic {
+  int32_t dim = 0;
+  std::vector<int32_t> perm, iperm;  // perm[k] = original index eliminated k-th
+  std::vector<int32_t> parent;       // column elimination tree (permuted)
+  int64_t nnz_l = 0;
+  int32_t etree_height = 0;
+
+  int32_t n_super = 0;
+  std::vector<int32_t> super_first;  // n_super+1: column ranges (permuted)
+  std::vector<int32_t> super_parent; // assembly tree
+  std::vector<int32_t> super_level;  // 0 = leaves
+  std::vector<int32_t> level_ptr, level_supers;  // supernodes grouped by level
+  std::vector<int32_t> front_dim;    // order of each front
+  std::vector<int64_t> rows_ptr;     // n_super+1 → front row indices (permuted)
+  std::vector<int32_t> rows_idx;
+  std::vector<int64_t> panel_ptr;    // n_super+1 → L panel storage (dim×n_piv)
+  std::vector<int64_t> update_ptr;   // n_super+1 → update matrix storage
+  std::vector<int64_t> child_ptr;    // n_super+1 → children lists
+  std::vector<int32_t> child_idx;
+  std::vector<int64_t> rel_ptr;      // per supernode: where its update rows
+  std::vector<int32_t> rel_idx;      //   land in the parent's front
+  // scatter of K values into fronts: per supernode a list of
+  // (K entry, position r + c·front_dim)
+  std::vector<int64_t> asm_ptr;
+  std::vector<int32_t> asm_src, asm_dst;
+  std::vector<uint8_t> col_is_primal;  // permuted column < n in original order
+  int32_t max_front = 0, n_levels = 0;
+  int64_t panel_size = 0, update_size = 0;
+};
+
+bool analyze_kkt(const Pattern& K, int32_t n_primal, int ordering,
+                 const int32_t* user_perm, Symbolic& out, std::string& error);
+
+std::vector<int32_t> order_nested_dissection(const Pattern& lowerK);
+std::vector<int32_t> order_amd(const Pattern& lowerK);
+
+}  // namespace slpb

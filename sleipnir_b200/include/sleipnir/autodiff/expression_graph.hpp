@@ -1,0 +1,98 @@
+// Host-side graph walks over the flat expression pool.
+//
+// Same ordering contract as the reference's expression_graph.hpp:
+// topological_sort (:28-78) yields the parent→child list whose order fixes the
+// accumulation order of every adjoint; update_values (:85-96) and
+// append_triplets (:106-153) are kept for the work the reference also does on
+// the host outside the Newton loop — Variable::value() queries, the one-time
+// evaluation of LINEAR rows (jacobian.hpp:84-89) and bound detection. The
+// per-iteration sweeps run on the device from the same lists.
+#pragma once
+
+#include <utility>
+#include <vector>
+
+#include "sleipnir/autodiff/expression.hpp"
+
+namespace slp::detail {
+
+/// Parent→child list of node ids.
+using ExpressionGraph = std::vector<ExprId>;
+
+struct Triplet {
+  int32_t row, col;
+  double value;
+};
+
+inline ExpressionGraph topological_sort(const Expr& root) {
+  ExpressionGraph list;
+  if (root == nullptr || root.type() == ExpressionType::CONSTANT) return list;
+
+  auto& P = pool();
+  auto& scratch = P.scratch;
+  std::vector<ExprId> stack;
+
+  // Pass 1: count incoming edges (offset by −1) by DFS from the root.
+  stack.push_back(root.id());
+  while (!stack.empty()) {
+    ExprId node = stack.back();
+    stack.pop_back();
+    for (ExprId arg : {P.lhs[node], P.rhs[node]}) {
+      if (arg != kNull && ++scratch[arg] == 0) stack.push_back(arg);
+    }
+  }
+  // Pass 2: emit a node once all of its parents have been emitted.
+  stack.push_back(root.id());
+  while (!stack.empty()) {
+    ExprId node = stack.back();
+    stack.pop_back();
+    list.push_back(node);
+    for (ExprId arg : {P.lhs[node], P.rhs[node]}) {
+      if (arg != kNull && --scratch[arg] == -1) stack.push_back(arg);
+    }
+  }
+  return list;
+}
+
+inline void update_values(const ExpressionGraph& list) {
+  auto& P = pool();
+  for (auto it = list.rbegin(); it != list.rend(); ++it) {
+    const ExprId node = *it;
+    const ExprId l = P.lhs[node], r = P.rhs[node];
+    if (l != kNull) {
+      P.val[node] = op_value(static_cast<Op>(P.op[node]), P.val[l],
+                             r != kNull ? P.val[r] : 0.0);
+    }
+  }
+}
+
+/// One reverse sweep. `adjoint` is caller-provided scratch indexed by node id
+/// (only entries of nodes in `top_list` are touched).
+inline void append_triplets(const ExpressionGraph& top_list,
+                            const std::vector<std::pair<int, ExprId>>& outputs,
+                            std::vector<double>& adjoint,
+                            std::vector<Triplet>& triplets, int row) {
+  if (top_list.empty()) return;
+  auto& P = pool();
+  if (adjoint.size() < P.size()) adjoint.resize(P.size());
+  adjoint[top_list[0]] = 1.0;
+  for (size_t i = 1; i < top_list.size(); ++i) adjoint[top_list[i]] = 0.0;
+  for (ExprId node : top_list) {
+    const ExprId l = P.lhs[node], r = P.rhs[node];
+    if (l == kNull) continue;
+    const Op op = static_cast<Op>(P.op[node]);
+    const double a = adjoint[node];
+    if (r != kNull) {
+      const double lv = P.val[l], rv = P.val[r];
+      adjoint[l] += op_grad_l(op, a, lv, rv);
+      adjoint[r] += op_grad_r(op, a, lv, rv);
+    } else {
+      adjoint[l] += op_grad_l(op, a, P.val[l], 0.0);
+    }
+  }
+  for (const auto& [col, node] : outputs) {
+    triplets.push_back({row, col, adjoint[node]});
+  }
+}
+
+}  // namespace slp::detail

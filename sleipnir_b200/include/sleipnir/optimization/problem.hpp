@@ -1,0 +1,426 @@
+// slp::Problem — the user-facing DSL and solver entry point.
+//
+// Same surface as the reference's include/sleipnir/optimization/problem.hpp:
+// decision_variable (:78-101), symmetric_decision_variable (:118-140),
+// minimize / maximize (:151-190), subject_to (:196-234), solve (:281),
+// add_callback ×2 / clear_callbacks / add_persistent_callback (:690-730).
+// solve() builds the same autodiff objects as the reference's IPM branch
+// (:517-560), detects conflicting bounds (:597-606), computes the problem
+// scaling (:615-616), then hands the flattened graphs to the device library
+// (include/slpb.h) and runs the interior-point loop there. The reference
+// dispatches problems without inequality constraints to its Newton / SQP
+// solvers (:335,403); those are outside this build, so every problem takes
+// the interior-point path (an empty inequality set is allowed).
+#pragma once
+
+#include <algorithm>
+#include <concepts>
+#include <functional>
+#include <limits>
+#include <memory>
+#include <optional>
+#include <span>
+#include <utility>
+#include <vector>
+
+#include "sleipnir/autodiff/gradient.hpp"
+#include "sleipnir/autodiff/hessian.hpp"
+#include "sleipnir/autodiff/jacobian.hpp"
+#include "sleipnir/autodiff/variable.hpp"
+#include "sleipnir/autodiff/variable_matrix.hpp"
+#include "sleipnir/optimization/solver/device_problem.hpp"
+#include "sleipnir/optimization/solver/exit_status.hpp"
+#include "sleipnir/optimization/solver/interior_point.hpp"
+#include "sleipnir/optimization/solver/iteration_info.hpp"
+#include "sleipnir/optimization/solver/options.hpp"
+#include "slpb.h"
+
+namespace slp {
+
+/// Device-side knobs that have no counterpart in the reference's Options.
+struct DeviceOptions {
+  int device = 0;                               ///< CUDA ordinal
+  int ordering = SLPB_ORDER_NESTED_DISSECTION;  ///< slpb_ordering
+  std::vector<int32_t> permutation;             ///< for SLPB_ORDER_CUSTOM
+  bool keep_iterates = false;                   ///< record x,s,y,z per iteration
+};
+
+/// RAII owner of a device handle.
+struct DeviceHandle {
+  slpb_solver* s = nullptr;
+  explicit DeviceHandle(int device) {
+    const int rc = slpb_create(device, &s);
+    if (rc != SLPB_OK) {
+      throw DeviceError(
+          "slpb_create failed (status " + std::to_string(rc) +
+          "): the interior-point path needs a CUDA device; there is no CPU "
+          "fallback");
+    }
+  }
+  DeviceHandle(const DeviceHandle&) = delete;
+  DeviceHandle& operator=(const DeviceHandle&) = delete;
+  ~DeviceHandle() { slpb_destroy(s); }
+};
+
+template <typename Scalar>
+class Problem {
+ public:
+  Problem() = default;
+
+  /// Creates a decision variable in the optimization problem.
+  [[nodiscard]] Variable<Scalar> decision_variable() {
+    m_decision_variables.emplace_back();
+    return m_decision_variables.back();
+  }
+  /// Creates a matrix of decision variables (appended row by row).
+  [[nodiscard]] VariableMatrix<Scalar> decision_variable(int rows,
+                                                         int cols = 1) {
+    m_decision_variables.reserve(m_decision_variables.size() + rows * cols);
+    VariableMatrix<Scalar> vars{detail::empty, rows, cols};
+    for (int row = 0; row < rows; ++row) {
+      for (int col = 0; col < cols; ++col) {
+        m_decision_variables.emplace_back();
+        vars(row, col) = m_decision_variables.back();
+      }
+    }
+    return vars;
+  }
+  /// Creates a symmetric matrix of decision variables (lower triangle stored).
+  [[nodiscard]] VariableMatrix<Scalar> symmetric_decision_variable(int rows) {
+    VariableMatrix<Scalar> vars{detail::empty, rows, rows};
+    for (int row = 0; row < rows; ++row) {
+      for (int col = 0; col <= row; ++col) {
+        m_decision_variables.emplace_back();
+        vars(row, col) = m_decision_variables.back();
+        vars(col, row) = m_decision_variables.back();
+      }
+    }
+    return vars;
+  }
+
+  void minimize(const Variable<Scalar>& cost) { m_f = cost; }
+  void maximize(const Variable<Scalar>& objective) { m_f = -objective; }
+
+  void subject_to(const EqualityConstraints<Scalar>& constraint) {
+    m_equality_constraints.insert(m_equality_constraints.end(),
+                                  constraint.constraints.begin(),
+                                  constraint.constraints.end());
+  }
+  void subject_to(const InequalityConstraints<Scalar>& constraint) {
+    m_inequality_constraints.insert(m_inequality_constraints.end(),
+                                    constraint.constraints.begin(),
+                                    constraint.constraints.end());
+  }
+
+  ExpressionType cost_function_type() const {
+    return m_f ? m_f->type() : ExpressionType::NONE;
+  }
+  ExpressionType equality_constraint_type() const {
+    return max_type(m_equality_constraints);
+  }
+  ExpressionType inequality_constraint_type() const {
+    return max_type(m_inequality_constraints);
+  }
+
+  /// Solves the optimization problem; the solution is stored in the original
+  /// variables. `spy` is accepted for source compatibility (sparsity-pattern
+  /// dumps are not part of this build).
+  ExitStatus solve(const Options& options = Options{},
+                   [[maybe_unused]] bool spy = false) {
+    return solve(options, DeviceOptions{});
+  }
+
+  ExitStatus solve(const Options& options, const DeviceOptions& dev_options) {
+    m_trace = SolveTrace{};
+    m_trace.keep_iterates = dev_options.keep_iterates;
+
+    const int n = static_cast<int>(m_decision_variables.size());
+    const int me = static_cast<int>(m_equality_constraints.size());
+    const int mi = static_cast<int>(m_inequality_constraints.size());
+
+    // Initial value column vector (:288-291)
+    std::vector<Scalar> x(n);
+    for (int i = 0; i < n; ++i) x[i] = m_decision_variables[i].value();
+
+    // Nothing to do for an empty or constant problem (:299-313)
+    if (cost_function_type() <= ExpressionType::CONSTANT &&
+        equality_constraint_type() <= ExpressionType::CONSTANT &&
+        inequality_constraint_type() <= ExpressionType::CONSTANT) {
+      return ExitStatus::SUCCESS;
+    }
+
+    std::vector<std::function<bool(const IterationInfo<Scalar>&)>> callbacks;
+    for (const auto& cb : m_iteration_callbacks) callbacks.push_back(cb);
+    for (const auto& cb : m_persistent_iteration_callbacks) {
+      callbacks.push_back(cb);
+    }
+
+    // Autodiff setup (:517-560)
+    auto graphs = build_graphs();
+
+    // Conflicting bounds (:597-606)
+    if (has_conflicting_bounds(*graphs->A_i)) {
+      return ExitStatus::GLOBALLY_INFEASIBLE;
+    }
+
+    // Hand the graphs to the device
+    detail::FlatProblem fp = graphs->flatten();
+
+    DeviceHandle handle{dev_options.device};
+    slpb_solver* dev = handle.s;
+    upload(dev, fp);
+
+    // Initial iterate: s = 1, y = 0, z = 1 (interior_point.hpp:74-80)
+    std::vector<Scalar> s(mi, Scalar(1)), y(me, Scalar(0)), z(mi, Scalar(1));
+    SLP_DEVICE_CALL(dev,
+                    slpb_set_iterate(dev, x.data(), s.data(), y.data(), z.data()));
+
+    // Problem scaling from g(x₀), A_e(x₀), A_i(x₀) (:615-616;
+    // problem_scaling.hpp:100-107)
+    DeviceProblemInfo info{n, me, mi, 1.0};
+    {
+      slpb_point_info pi{};
+      SLP_DEVICE_CALL(dev, slpb_eval_current(dev, 1, &pi));
+      std::vector<Scalar> gv(n);
+      SLP_DEVICE_CALL(dev, slpb_download(dev, SLPB_ARR_G, gv.data()));
+      Scalar g_inf(0);
+      for (Scalar v : gv) g_inf = std::max(g_inf, std::abs(v));
+      constexpr Scalar g_max(100);
+      info.scaling_f = std::min(Scalar(1), g_max / g_inf);
+      auto row_scales = [&](int which_pattern, int which_values, int rows) {
+        std::vector<Scalar> norms(rows, Scalar(0));
+        int32_t r = 0, c = 0;
+        int64_t nnz = 0;
+        SLP_DEVICE_CALL(dev, slpb_pattern(dev, which_pattern, &r, &c, &nnz,
+                                          nullptr, nullptr));
+        std::vector<int32_t> outer(c + 1), inner(nnz);
+        std::vector<Scalar> values(nnz);
+        SLP_DEVICE_CALL(dev, slpb_pattern(dev, which_pattern, &r, &c, &nnz,
+                                          outer.data(), inner.data()));
+        if (nnz > 0) {
+          SLP_DEVICE_CALL(dev, slpb_download(dev, which_values, values.data()));
+        }
+        for (int64_t k = 0; k < nnz; ++k) {
+          norms[inner[k]] = std::max(norms[inner[k]], std::abs(values[k]));
+        }
+        for (auto& v : norms) v = std::min(g_max / v, Scalar(1));
+        return norms;
+      };
+      std::vector<Scalar> d_ce =
+          row_scales(SLPB_OUT_A_E, SLPB_ARR_A_E_VAL, me);
+      std::vector<Scalar> d_ci =
+          row_scales(SLPB_OUT_A_I, SLPB_ARR_A_I_VAL, mi);
+      SLP_DEVICE_CALL(dev, slpb_set_scaling(dev, info.scaling_f, d_ce.data(),
+                                            d_ci.data()));
+    }
+
+    slpb_symbolic_stats sym{};
+    SLP_DEVICE_CALL(dev, slpb_analyze(dev, dev_options.ordering,
+                                      dev_options.permutation.empty()
+                                          ? nullptr
+                                          : dev_options.permutation.data(),
+                                      &sym));
+    m_symbolic = sym;
+
+    // Interior-point method (:663-668; overload 1, interior_point.hpp:74-86)
+    Scalar mu = Scalar(0.1) * info.scaling_f;
+    int iterations = 0;
+    ExitStatus status = interior_point<Scalar>(
+        dev, info, std::span{callbacks}, options, false, mu, iterations,
+        &m_trace);
+
+    // Write the solution back into the Variables (:676)
+    SLP_DEVICE_CALL(dev, slpb_get_iterate(dev, x.data(), s.data(), y.data(),
+                                          z.data()));
+    for (int i = 0; i < n; ++i) m_decision_variables[i].set_value(x[i]);
+    m_last_s = std::move(s);
+    m_last_y = std::move(y);
+    m_last_z = std::move(z);
+    slpb_get_counters(dev, &m_counters);
+    return status;
+  }
+
+  /// Adds a callback called at the beginning of each solver iteration; a
+  /// void-returning callback never stops the solve.
+  template <typename F>
+    requires requires(F callback, const IterationInfo<Scalar>& info) {
+      { callback(info) } -> std::same_as<void>;
+    }
+  void add_callback(F&& callback) {
+    m_iteration_callbacks.emplace_back(
+        [callback = std::forward<F>(callback)](
+            const IterationInfo<Scalar>& info) {
+          callback(info);
+          return false;
+        });
+  }
+  /// A bool-returning callback stops the solve by returning true.
+  template <typename F>
+    requires requires(F callback, const IterationInfo<Scalar>& info) {
+      { callback(info) } -> std::same_as<bool>;
+    }
+  void add_callback(F&& callback) {
+    m_iteration_callbacks.emplace_back(std::forward<F>(callback));
+  }
+  void clear_callbacks() { m_iteration_callbacks.clear(); }
+  /// Persistent callbacks survive clear_callbacks() and run last.
+  template <typename F>
+    requires requires(F callback, const IterationInfo<Scalar>& info) {
+      { callback(info) } -> std::same_as<bool>;
+    }
+  void add_persistent_callback(F&& callback) {
+    m_persistent_iteration_callbacks.emplace_back(std::forward<F>(callback));
+  }
+
+  // ---- introspection of the last solve (not in the reference) -------------
+  const SolveTrace& last_trace() const { return m_trace; }
+  const slpb_symbolic_stats& last_symbolic_stats() const { return m_symbolic; }
+  const slpb_counters& last_counters() const { return m_counters; }
+  const std::vector<Scalar>& last_s() const { return m_last_s; }
+  const std::vector<Scalar>& last_y() const { return m_last_y; }
+  const std::vector<Scalar>& last_z() const { return m_last_z; }
+  std::vector<Variable<Scalar>>& decision_variables() {
+    return m_decision_variables;
+  }
+  const std::vector<Variable<Scalar>>& equality_constraints() const {
+    return m_equality_constraints;
+  }
+  const std::vector<Variable<Scalar>>& inequality_constraints() const {
+    return m_inequality_constraints;
+  }
+  const std::optional<Variable<Scalar>>& cost() const { return m_f; }
+
+  /// The autodiff objects Problem::solve sets up for the interior-point
+  /// method, in the reference's construction order (problem.hpp:517-560).
+  struct Graphs {
+    VariableMatrix<Scalar> x_ad, c_e_ad, c_i_ad, y_ad, z_ad;
+    Variable<Scalar> f{nullptr};
+    std::unique_ptr<Gradient<Scalar>> g;
+    std::unique_ptr<Hessian<Scalar, Lower>> H_f, H_c;
+    std::unique_ptr<Jacobian<Scalar>> A_e, A_i;
+
+    detail::FlatProblem flatten() const {
+      detail::Flattener flat;
+      flat.set_leaves(x_ad, y_ad, z_ad);
+      flat.add_values(SLPB_OUT_F, VariableMatrix<Scalar>{f});
+      flat.add_jacobian(SLPB_OUT_G, g->jacobian());
+      flat.add_jacobian(SLPB_OUT_H_F, *H_f);
+      flat.add_jacobian(SLPB_OUT_H_C, *H_c);
+      flat.add_values(SLPB_OUT_C_E, c_e_ad);
+      flat.add_jacobian(SLPB_OUT_A_E, *A_e);
+      flat.add_values(SLPB_OUT_C_I, c_i_ad);
+      flat.add_jacobian(SLPB_OUT_A_I, *A_i);
+      return flat.finish();
+    }
+  };
+
+  std::unique_ptr<Graphs> build_graphs() {
+    const int me = static_cast<int>(m_equality_constraints.size());
+    const int mi = static_cast<int>(m_inequality_constraints.size());
+    auto G = std::make_unique<Graphs>();
+    G->x_ad = VariableMatrix<Scalar>{std::span<const Variable<Scalar>>{
+        m_decision_variables.data(), m_decision_variables.size()}};
+    G->f = m_f.value_or(Variable<Scalar>{Scalar(0)});
+    G->c_e_ad = VariableMatrix<Scalar>{std::span<const Variable<Scalar>>{
+        m_equality_constraints.data(), m_equality_constraints.size()}};
+    G->c_i_ad = VariableMatrix<Scalar>{std::span<const Variable<Scalar>>{
+        m_inequality_constraints.data(), m_inequality_constraints.size()}};
+    G->y_ad = VariableMatrix<Scalar>(me);
+    G->z_ad = VariableMatrix<Scalar>(mi);
+    G->g = std::make_unique<Gradient<Scalar>>(G->f, G->x_ad);
+    G->H_f = std::make_unique<Hessian<Scalar, Lower>>(G->f, G->x_ad);
+    // −yᵀc_e − zᵀc_i as 1x1 matrix products: left-deep chains (:547-548)
+    Variable<Scalar> lagrangian_c{VariableMatrix<Scalar>{
+        -G->y_ad.T() * G->c_e_ad - G->z_ad.T() * G->c_i_ad}};
+    G->H_c = std::make_unique<Hessian<Scalar, Lower>>(lagrangian_c, G->x_ad);
+    G->A_e = std::make_unique<Jacobian<Scalar>>(G->c_e_ad, G->x_ad);
+    G->A_i = std::make_unique<Jacobian<Scalar>>(G->c_i_ad, G->x_ad);
+    return G;
+  }
+
+  /// Uploads a flattened problem and compiles it on the device.
+  static void upload(slpb_solver* dev, const detail::FlatProblem& fp) {
+    SLP_DEVICE_CALL(
+        dev, slpb_upload_tape(dev, fp.n_nodes(), fp.op.data(), fp.lhs.data(),
+                              fp.rhs.data(), fp.val.data(),
+                              static_cast<int32_t>(fp.leaf_x.size()),
+                              fp.leaf_x.data(),
+                              static_cast<int32_t>(fp.leaf_y.size()),
+                              fp.leaf_y.data(),
+                              static_cast<int32_t>(fp.leaf_z.size()),
+                              fp.leaf_z.data()));
+    for (int which = 0; which < SLPB_OUT_COUNT; ++which) {
+      const slpb_rowset view = fp.rows[which].view();
+      SLP_DEVICE_CALL(dev, slpb_upload_rows(dev, which, &view,
+                                            fp.rows[which].const_val.data()));
+    }
+    SLP_DEVICE_CALL(dev, slpb_finalize(dev));
+  }
+
+ private:
+  static ExpressionType max_type(const std::vector<Variable<Scalar>>& v) {
+    ExpressionType t = ExpressionType::NONE;
+    for (const auto& e : v) t = std::max(t, e.type());
+    return t;
+  }
+
+  /// solver/util/bounds.hpp:54-179, reduced to what solve() consumes: whether
+  /// two bound constraints on one variable contradict each other. A bound is a
+  /// LINEAR inequality whose gradient has a single structural entry.
+  bool has_conflicting_bounds(const Jacobian<Scalar>& A_i) {
+    const int mi = static_cast<int>(m_inequality_constraints.size());
+    std::vector<int> count(mi, 0), col(mi, -1);
+    std::vector<Scalar> coeff(mi, Scalar(0));
+    for (const auto& t : A_i.cached_triplets()) {
+      ++count[t.row];
+      col[t.row] = t.col;
+      coeff[t.row] = t.value;
+    }
+    const size_t n = m_decision_variables.size();
+    std::vector<std::pair<Scalar, Scalar>> bnd(
+        n, {-std::numeric_limits<Scalar>::infinity(),
+            std::numeric_limits<Scalar>::infinity()});
+    bool conflict = false;
+    for (int ci = 0; ci < mi; ++ci) {
+      if (m_inequality_constraints[ci].type() != ExpressionType::LINEAR) {
+        continue;
+      }
+      if (count[ci] != 1) continue;
+      auto& var = m_decision_variables[col[ci]];
+      const Scalar var_value = var.value();
+      Scalar constant;
+      if (var_value != Scalar(0)) {
+        var.set_value(Scalar(0));
+        constant = m_inequality_constraints[ci].value();
+        var.set_value(var_value);
+      } else {
+        constant = m_inequality_constraints[ci].value();
+      }
+      auto& [lower, upper] = bnd[col[ci]];
+      const Scalar detected = -constant / coeff[ci];
+      if (coeff[ci] < Scalar(0) && detected < upper) {
+        upper = detected;
+      } else if (coeff[ci] > Scalar(0) && detected > lower) {
+        lower = detected;
+      }
+      if (lower > upper) conflict = true;
+    }
+    return conflict;
+  }
+
+  std::vector<Variable<Scalar>> m_decision_variables;
+  std::optional<Variable<Scalar>> m_f;
+  std::vector<Variable<Scalar>> m_equality_constraints;
+  std::vector<Variable<Scalar>> m_inequality_constraints;
+  std::vector<std::function<bool(const IterationInfo<Scalar>&)>>
+      m_iteration_callbacks;
+  std::vector<std::function<bool(const IterationInfo<Scalar>&)>>
+      m_persistent_iteration_callbacks;
+
+  SolveTrace m_trace;
+  slpb_symbolic_stats m_symbolic{};
+  slpb_counters m_counters{};
+  std::vector<Scalar> m_last_s, m_last_y, m_last_z;
+};
+
+}  // namespace slp

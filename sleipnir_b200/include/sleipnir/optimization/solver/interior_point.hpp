@@ -1,0 +1,606 @@
+// Host driver of the device-resident interior-point method.
+//
+// Control flow, constants and exit conditions follow the reference's
+// include/sleipnir/optimization/solver/interior_point.hpp:123-866 line by line
+// (citations inline); every vector/matrix operation of that loop is a call
+// into the C ABI (include/slpb.h) and runs on the GPU. Per call only a handful
+// of scalars return to the host, where the branchy logic lives: the
+// inertia-correcting δ/γ loop (solver/util/sparse_regularized_ldlt.hpp:64-152),
+// the filter (solver/util/filter.hpp:70-212), second-order corrections, the
+// barrier-parameter schedule and the exit statuses.
+#pragma once
+
+#include <algorithm>
+#include <chrono>
+#include <cmath>
+#include <functional>
+#include <limits>
+#include <span>
+#include <stdexcept>
+#include <string>
+#include <vector>
+
+#include "sleipnir/optimization/solver/exit_status.hpp"
+#include "sleipnir/optimization/solver/iteration_info.hpp"
+#include "sleipnir/optimization/solver/options.hpp"
+#include "sleipnir/util/linalg.hpp"
+#include "slpb.h"
+
+namespace slp {
+
+/// Thrown when the device library itself fails (no GPU, CUDA error, bad
+/// upload). Numerical outcomes are reported through ExitStatus, never thrown.
+class DeviceError : public std::runtime_error {
+ public:
+  using std::runtime_error::runtime_error;
+};
+
+namespace detail {
+inline void device_check(int rc, const slpb_solver* s, const char* what) {
+  if (rc != SLPB_OK) {
+    throw DeviceError(std::string{what} + ": " +
+                      (s ? slpb_last_error(s) : "no device handle") +
+                      " (status " + std::to_string(rc) + ")");
+  }
+}
+}  // namespace detail
+#define SLP_DEVICE_CALL(handle, call) \
+  ::slp::detail::device_check((call), (handle), #call)
+
+/// One row per Newton iteration (diagnostics and parity tests); mirrors the
+/// columns of the reference's iteration table
+/// (util/print_diagnostics.hpp:193-237).
+struct IterationRecord {
+  int iteration = 0;
+  int type = 0;  ///< 0 normal, 1 feasibility restoration
+  double error = 0, cost = 0, infeasibility = 0, complementarity = 0;
+  double mu = 0, delta = 0, gamma = 0, alpha = 0, alpha_max = 0, alpha_z = 0;
+  int factorizations = 0, solves = 0, trials = 0;
+  std::vector<double> x, s, y, z;  ///< filled when SolveTrace::keep_iterates
+};
+
+struct SolveTrace {
+  bool keep_iterates = false;
+  std::vector<IterationRecord> rows;
+  int64_t factorizations = 0, solves = 0, trials = 0;
+  double loop_seconds = 0.0;  ///< wall time inside the Newton loop
+};
+
+/// FilterEntry / Filter: solver/util/filter.hpp:20-212.
+template <typename Scalar>
+struct FilterEntry {
+  Scalar cost{0};
+  Scalar constraint_violation{0};
+  constexpr FilterEntry() = default;
+  constexpr FilterEntry(Scalar cost, Scalar constraint_violation)
+      : cost{cost}, constraint_violation{constraint_violation} {}
+  constexpr bool dominated_by(const FilterEntry& e) const {
+    return e.cost <= cost && e.constraint_violation <= constraint_violation;
+  }
+};
+
+template <typename Scalar>
+class Filter {
+ public:
+  Scalar min_constraint_violation;
+  Scalar max_constraint_violation;
+
+  explicit Filter(Scalar initial_constraint_violation = Scalar(0)) {
+    min_constraint_violation =
+        Scalar(1e-4) * std::max(Scalar(1), initial_constraint_violation);
+    max_constraint_violation =
+        Scalar(1e4) * std::max(Scalar(1), initial_constraint_violation);
+  }
+  void reset() {
+    m_filter.clear();
+    m_last_rejection_due_to_filter = false;
+  }
+  bool try_add(const FilterEntry<Scalar>& current,
+               const FilterEntry<Scalar>& trial, Scalar D_phi, Scalar alpha) {
+    using std::isfinite;
+    using std::pow;
+    if (!isfinite(trial.cost) ||
+        trial.constraint_violation > max_constraint_violation) {
+      return false;
+    }
+    constexpr Scalar s_phi(2.3), s_theta(1.1), eta_phi(1e-8);
+    const bool switching =
+        D_phi < Scalar(0) &&
+        alpha * pow(-D_phi, s_phi) > pow(current.constraint_violation, s_theta);
+    const bool armijo = trial.cost <= current.cost + eta_phi * alpha * D_phi;
+    const Scalar phi = pow(alpha, Scalar(1.5));
+    const bool sufficient_decrease =
+        trial.cost <=
+            current.cost - phi * kGammaCost * current.constraint_violation ||
+        trial.constraint_violation <=
+            (Scalar(1) - phi * kGammaConstraint) *
+                current.constraint_violation;
+    if (current.constraint_violation <= min_constraint_violation &&
+        switching) {
+      if (!armijo) {
+        m_last_rejection_due_to_filter = false;
+        return false;
+      }
+    } else if (!sufficient_decrease) {
+      m_last_rejection_due_to_filter = false;
+      return false;
+    }
+    if (std::any_of(m_filter.begin(), m_filter.end(),
+                    [&](const auto& e) { return trial.dominated_by(e); })) {
+      m_last_rejection_due_to_filter = true;
+      return false;
+    }
+    if (!switching || !armijo) {
+      const FilterEntry<Scalar> entry{
+          current.cost - phi * kGammaCost * current.constraint_violation,
+          (Scalar(1) - phi * kGammaConstraint) * current.constraint_violation};
+      std::erase_if(m_filter,
+                    [&](const auto& e) { return e.dominated_by(entry); });
+      m_filter.push_back(entry);
+    }
+    return true;
+  }
+  bool last_rejection_due_to_filter() const {
+    return m_last_rejection_due_to_filter;
+  }
+
+ private:
+  static constexpr Scalar kGammaCost{1e-8};
+  static constexpr Scalar kGammaConstraint{1e-5};
+  std::vector<FilterEntry<Scalar>> m_filter;
+  bool m_last_rejection_due_to_filter = false;
+};
+
+/// The inertia-correcting regularisation loop around the device factorisation
+/// (solver/util/sparse_regularized_ldlt.hpp:64-152). The matrix stays resident
+/// on the device: a retry only changes δ and γ.
+class DeviceRegularizedLDLT {
+ public:
+  DeviceRegularizedLDLT(slpb_solver* dev, int num_decision_variables,
+                        int num_equality_constraints, double gamma_min)
+      : m_dev{dev}, m_n{num_decision_variables},
+        m_me{num_equality_constraints}, m_gamma_min{gamma_min} {}
+
+  /// Returns false on NumericalIssue (δ or γ beyond 1e20).
+  bool compute() {
+    slpb_factor_info info{};
+    factor(0.0, 0.0, /*reassemble=*/1, info);
+    if (!info.zero_pivot && ideal(info) && info.min_abs_d >= 1e-4) {
+      m_prev_delta = 0.0;
+      m_prev_gamma = 0.0;
+      return true;
+    }
+    double delta = m_prev_delta == 0.0
+                       ? 1e-4
+                       : std::max(m_prev_delta / 2.0,
+                                  std::numeric_limits<double>::epsilon());
+    double gamma = m_gamma_min;
+    while (true) {
+      factor(delta, gamma, /*reassemble=*/0, info);
+      if (!info.zero_pivot) {
+        if (ideal(info)) {
+          m_prev_delta = delta;
+          m_prev_gamma = gamma;
+          return true;
+        } else if (info.n_zero > 0) {
+          if (gamma == 0.0) {
+            gamma = 1e-10;
+          } else {
+            delta *= 10.0;
+            gamma *= 10.0;
+          }
+        } else if (info.n_neg > m_me) {
+          delta *= 10.0;
+        } else if (info.n_pos > m_n) {
+          gamma = gamma == 0.0 ? 1e-10 : gamma * 10.0;
+        }
+      } else {
+        delta *= 10.0;
+        gamma = gamma == 0.0 ? 1e-10 : gamma * 10.0;
+      }
+      if (delta > 1e20 || gamma > 1e20) {
+        m_prev_delta = delta;
+        m_prev_gamma = gamma;
+        return false;
+      }
+    }
+  }
+
+  double hessian_regularization() const { return m_prev_delta; }
+  double constraint_jacobian_regularization() const { return m_prev_gamma; }
+  /// Test hook: seeds "previous δ" so a single step can be replayed.
+  void set_previous_regularization(double delta, double gamma) {
+    m_prev_delta = delta;
+    m_prev_gamma = gamma;
+  }
+  int factorizations = 0;
+
+ private:
+  bool ideal(const slpb_factor_info& i) const {
+    return i.n_pos == m_n && i.n_neg == m_me && i.n_zero == 0;
+  }
+  void factor(double delta, double gamma, int reassemble,
+              slpb_factor_info& info) {
+    ++factorizations;
+    SLP_DEVICE_CALL(m_dev, slpb_factor(m_dev, delta, gamma, reassemble, &info));
+  }
+
+  slpb_solver* m_dev;
+  int m_n, m_me;
+  double m_gamma_min;
+  double m_prev_delta = 0.0, m_prev_gamma = 0.0;
+};
+
+namespace detail {
+
+enum class KKTErrorType { INF_NORM_SCALED, ONE_NORM };
+
+/// kkt_error.hpp:92-146 from the reductions the device returned.
+inline double kkt_error_scaled(const slpb_kkt_stats& k, int me, int mi,
+                               double mu) {
+  constexpr double s_max = 100.0;
+  const double s_d =
+      std::max(s_max, (k.y_l1 + k.z_l1) / double(me + mi)) / s_max;
+  const double s_c = std::max(s_max, k.z_l1 / double(mi)) / s_max;
+  const double sz_inf =
+      std::max(std::abs(k.sz_max - mu), std::abs(k.sz_min - mu));
+  return std::max({k.r_inf / s_d, sz_inf / s_c, k.ce_inf, k.cis_inf});
+}
+/// kkt_error.hpp:216-251 (μ = 0, as the solver uses it for E_0).
+inline double kkt_error_unscaled_mu0(const slpb_kkt_stats& k, int me, int mi) {
+  constexpr double s_max = 100.0;
+  const double s_d =
+      std::max(s_max, (k.u_y_l1 + k.u_z_l1) / double(me + mi)) / s_max;
+  const double s_c = std::max(s_max, k.u_z_l1 / double(mi)) / s_max;
+  const double sz_inf = std::max(std::abs(k.u_sz_max), std::abs(k.u_sz_min));
+  return std::max({k.u_r_inf / s_d, sz_inf / s_c, k.u_ce_inf, k.u_cis_inf});
+}
+inline double kkt_error_one_norm(const slpb_kkt_stats& k) {
+  return k.r_l1 + k.sz_mu_l1 + k.ce_l1 + k.cis_l1;
+}
+
+}  // namespace detail
+
+/// Dimensions and scaling the driver needs besides the device handle.
+struct DeviceProblemInfo {
+  int num_decision_variables = 0;
+  int num_equality_constraints = 0;
+  int num_inequality_constraints = 0;
+  double scaling_f = 1.0;
+};
+
+/// Hook used by Problem::solve to run feasibility restoration on a second
+/// device problem; returns the restoration's ExitStatus
+/// (feasibility_restoration.hpp:346-628).
+using RestorationHook = std::function<ExitStatus(
+    double mu, int& iterations, const std::function<bool()>& accept_test)>;
+
+/// Finds the optimal solution to a nonlinear program with the interior-point
+/// method, with the iterate resident on the device (reference overload 2,
+/// interior_point.hpp:123-134).
+template <typename Scalar>
+ExitStatus interior_point(
+    slpb_solver* dev, const DeviceProblemInfo& problem,
+    std::span<std::function<bool(const IterationInfo<Scalar>& info)>>
+        iteration_callbacks,
+    const Options& options, bool in_feasibility_restoration, Scalar& mu,
+    int& iterations, SolveTrace* trace = nullptr,
+    const RestorationHook* restoration = nullptr,
+    double initial_delta = 0.0) {
+  using std::isfinite;
+  const auto solve_start_time = std::chrono::steady_clock::now();
+  const int n = problem.num_decision_variables;
+  const int me = problem.num_equality_constraints;
+  const int mi = problem.num_inequality_constraints;
+
+  // f, g, H, c_e, A_e, c_i, A_i at the initial iterate (:245-251)
+  slpb_point_info cur{};
+  SLP_DEVICE_CALL(dev, slpb_eval_current(dev, 1, &cur));
+
+  if (me > n) return ExitStatus::TOO_FEW_DOFS;  // :274-280
+
+  constexpr int kAllFinite = SLPB_FINITE_F | SLPB_FINITE_C_E |
+                             SLPB_FINITE_C_I | SLPB_FINITE_G |
+                             SLPB_FINITE_A_E | SLPB_FINITE_A_I | SLPB_FINITE_H;
+  if ((cur.finite & kAllFinite) != kAllFinite) {
+    return ExitStatus::NONFINITE_INITIAL_GUESS;  // :283-286
+  }
+
+  const Scalar mu_min = problem.scaling_f * Scalar(options.tolerance) / 10.0;
+  constexpr Scalar tau_min(0.99);
+  Scalar tau = tau_min;
+
+  Filter<Scalar> filter{cur.ce_l1 + cur.cis_l1};  // :303-304
+
+  auto update_barrier_parameter_and_reset_filter = [&] {  // :308-333
+    constexpr Scalar kappa_mu(0.2);
+    constexpr Scalar theta_mu(1.5);
+    mu = std::max(mu_min, std::min(kappa_mu * mu, std::pow(mu, theta_mu)));
+    tau = std::max(tau_min, Scalar(1) - mu);
+    filter.reset();
+  };
+
+  // The reference picks Eigen's dense LDLT when the lower triangle is ≥ 25 %
+  // full (:340-348); the device path always factors sparse.
+  DeviceRegularizedLDLT solver{dev, n, me,
+                               in_feasibility_restoration ? 0.0 : 1e-10};
+  solver.set_previous_regularization(initial_delta, 0.0);
+
+  constexpr Scalar alpha_reduction_factor(0.5);
+  constexpr Scalar alpha_min(1e-7);
+  int full_step_rejected_counter = 0;
+
+  slpb_kkt_stats kkt{};
+  SLP_DEVICE_CALL(dev, slpb_kkt_stats_current(dev, 0.0, &kkt));
+  Scalar E_0 = detail::kkt_error_unscaled_mu0(kkt, me, mi);  // :361-362
+
+  // Host mirrors for IterationInfo, filled lazily.
+  Vector<Scalar> hx, hs, hy, hz, hg;
+  SparseMatrix<Scalar> hH, hAe, hAi;
+  auto download_matrix = [&](int which_pattern, int which_values) {
+    int32_t rows = 0, cols = 0;
+    int64_t nnz = 0;
+    SLP_DEVICE_CALL(dev, slpb_pattern(dev, which_pattern, &rows, &cols, &nnz,
+                                      nullptr, nullptr));
+    std::vector<int32_t> outer(cols + 1), inner(nnz);
+    std::vector<Scalar> values(nnz);
+    SLP_DEVICE_CALL(dev, slpb_pattern(dev, which_pattern, &rows, &cols, &nnz,
+                                      outer.data(), inner.data()));
+    if (nnz > 0) {
+      SLP_DEVICE_CALL(dev, slpb_download(dev, which_values, values.data()));
+    }
+    return SparseMatrix<Scalar>{rows, cols, std::move(outer), std::move(inner),
+                                std::move(values)};
+  };
+  auto download_iterate = [&] {
+    hx.resize(n);
+    hs.resize(mi);
+    hy.resize(me);
+    hz.resize(mi);
+    SLP_DEVICE_CALL(dev, slpb_get_iterate(dev, hx.data(), hs.data(), hy.data(),
+                                          hz.data()));
+  };
+
+  const auto loop_start_time = std::chrono::steady_clock::now();
+  struct LoopTimer {
+    SolveTrace* t;
+    std::chrono::steady_clock::time_point t0;
+    ~LoopTimer() {
+      if (t) {
+        t->loop_seconds += std::chrono::duration<double>(
+                               std::chrono::steady_clock::now() - t0)
+                               .count();
+      }
+    }
+  } loop_timer{trace, loop_start_time};
+
+  while (E_0 > Scalar(options.tolerance)) {
+    int it_solves = 0, it_trials = 0;
+    const int fact_before = solver.factorizations;
+
+    // Local infeasibility (:387-402; is_locally_infeasible.hpp:17-60)
+    if (me > 0 && kkt.aetce_l2 < 1e-6 && kkt.ce_l2 > 1e-2) {
+      return ExitStatus::LOCALLY_INFEASIBLE;
+    }
+    if (mi > 0 && kkt.aitcip_l2 < 1e-6 && kkt.cip_l2 > 1e-6) {
+      return ExitStatus::LOCALLY_INFEASIBLE;
+    }
+    // Diverging iterates (:405-408)
+    if (kkt.x_inf > 1e10 || kkt.s_inf > 1e10 || !kkt.xs_finite) {
+      return ExitStatus::DIVERGING_ITERATES;
+    }
+
+    // Iteration callbacks (:414-418)
+    if (!iteration_callbacks.empty()) {
+      download_iterate();
+      hg.resize(n);
+      SLP_DEVICE_CALL(dev, slpb_download(dev, SLPB_ARR_G, hg.data()));
+      hH = download_matrix(SLPB_OUT_H_C, SLPB_ARR_H_VAL);
+      hAe = download_matrix(SLPB_OUT_A_E, SLPB_ARR_A_E_VAL);
+      hAi = download_matrix(SLPB_OUT_A_I, SLPB_ARR_A_I_VAL);
+      for (const auto& callback : iteration_callbacks) {
+        if (callback({iterations, hx, hs, hy, hz, hg, hH, hAe, hAi})) {
+          return ExitStatus::CALLBACK_REQUESTED_STOP;
+        }
+      }
+    }
+
+    Scalar alpha_max(1), alpha(1), alpha_z(1);
+    bool call_feasibility_restoration = false;
+
+    // lhs assembly + factorisation with inertia correction (:426-465)
+    if (!solver.compute()) return ExitStatus::FACTORIZATION_FAILED;
+
+    // rhs, solve, step recovery, fraction-to-the-boundary (:444-497)
+    slpb_step_info step{};
+    SLP_DEVICE_CALL(dev, slpb_solve(dev, mu, tau, &step));
+    ++it_solves;
+    alpha_max = step.alpha_max;
+    alpha = alpha_max;
+    if (alpha < alpha_min) call_feasibility_restoration = true;
+    alpha_z = step.alpha_z;
+
+    const FilterEntry<Scalar> current_entry{cur.f - mu * cur.log_s_sum,
+                                            cur.ce_l1 + cur.cis_l1};  // :499
+    const Scalar D_phi = step.g_dot_px - mu * step.sinv_dot_ps;       // :508
+
+    slpb_point_info trial{};
+    slpb_step_info accepted_step = step;
+    while (true) {  // :512-717
+      ++it_trials;
+      const int slack_from_ci =
+          options.feasible_ipm && cur.ci_all_positive ? 1 : 0;
+      SLP_DEVICE_CALL(dev,
+                      slpb_trial(dev, alpha, alpha_z, 0, slack_from_ci, &trial));
+
+      constexpr int kTrialFinite =
+          SLPB_FINITE_F | SLPB_FINITE_C_E | SLPB_FINITE_C_I;
+      if ((trial.finite & kTrialFinite) != kTrialFinite) {  // :532-542
+        alpha *= alpha_reduction_factor;
+        if (alpha < alpha_min) {
+          call_feasibility_restoration = true;
+          break;
+        }
+        continue;
+      }
+
+      const FilterEntry<Scalar> trial_entry{trial.f - mu * trial.log_s_sum,
+                                            trial.ce_l1 + trial.cis_l1};
+      if (filter.try_add(current_entry, trial_entry, D_phi, alpha)) break;
+
+      const Scalar prev_constraint_violation = cur.ce_l1 + cur.cis_l1;
+      Scalar next_constraint_violation = trial.ce_l1 + trial.cis_l1;
+
+      // Second-order corrections (:561-664)
+      if (alpha == alpha_max &&
+          next_constraint_violation >= prev_constraint_violation) {
+        Scalar alpha_soc = alpha;
+        Scalar alpha_z_soc = alpha_z;
+        Scalar soc_constraint_violation = next_constraint_violation;
+        bool step_acceptable = false;
+        SLP_DEVICE_CALL(dev, slpb_soc_begin(dev));
+        for (int soc_iteration = 0; soc_iteration < 5 && !step_acceptable;
+             ++soc_iteration) {
+          slpb_step_info soc_step{};
+          SLP_DEVICE_CALL(
+              dev, slpb_soc_iterate(dev, mu, tau, alpha_soc, &soc_step));
+          ++it_solves;
+          alpha_soc = soc_step.alpha_max;
+          alpha_z_soc = soc_step.alpha_z;
+          ++it_trials;
+          SLP_DEVICE_CALL(
+              dev, slpb_trial(dev, alpha_soc, alpha_z_soc, 1, 0, &trial));
+          const FilterEntry<Scalar> soc_entry{trial.f - mu * trial.log_s_sum,
+                                              trial.ce_l1 + trial.cis_l1};
+          // NB: the acceptance test uses the OUTER α (:637)
+          if (filter.try_add(current_entry, soc_entry, D_phi, alpha)) {
+            accepted_step = soc_step;
+            alpha = alpha_soc;
+            alpha_z = alpha_z_soc;
+            step_acceptable = true;
+            break;
+          }
+          constexpr Scalar kappa_soc(0.99);
+          next_constraint_violation = trial.ce_l1 + trial.cis_l1;
+          if (next_constraint_violation >
+              kappa_soc * soc_constraint_violation) {
+            break;
+          }
+          soc_constraint_violation = next_constraint_violation;
+        }
+        if (step_acceptable) break;
+      }
+
+      if (alpha == alpha_max) ++full_step_rejected_counter;  // :669-671
+
+      // Filter reset heuristic (:677-684)
+      if (full_step_rejected_counter >= 4 &&
+          filter.max_constraint_violation >
+              current_entry.constraint_violation / Scalar(10) &&
+          filter.last_rejection_due_to_filter()) {
+        filter.max_constraint_violation *= Scalar(0.1);
+        filter.reset();
+        continue;
+      }
+
+      alpha *= alpha_reduction_factor;
+
+      // Step size hit the minimum: accept anyway if the KKT error went down,
+      // else restore feasibility (:691-716)
+      if (alpha < alpha_min) {
+        slpb_kkt_stats ks{};
+        SLP_DEVICE_CALL(dev, slpb_kkt_stats_current(dev, mu, &ks));
+        const Scalar current_kkt_error = detail::kkt_error_one_norm(ks);
+        ++it_trials;
+        SLP_DEVICE_CALL(dev, slpb_trial(dev, alpha_max, alpha_z, 0, 0, &trial));
+        SLP_DEVICE_CALL(dev, slpb_kkt_stats_trial(dev, mu, &ks));
+        const Scalar next_kkt_error = detail::kkt_error_one_norm(ks);
+        if (next_kkt_error <= Scalar(0.999) * current_kkt_error) break;
+        call_feasibility_restoration = true;
+        break;
+      }
+    }
+
+    if (call_feasibility_restoration) {  // :721-771
+      if (in_feasibility_restoration || restoration == nullptr) {
+        return ExitStatus::FEASIBILITY_RESTORATION_FAILED;
+      }
+      // The trial-point KKT probe above may have overwritten the derivative
+      // arrays; bring them back to the current iterate for the hook.
+      SLP_DEVICE_CALL(dev, slpb_eval_current(dev, 2, &cur));
+      const FilterEntry<Scalar> initial_entry = current_entry;
+      (void)initial_entry;
+      ExitStatus status = (*restoration)(mu, iterations, [] { return false; });
+      if (status != ExitStatus::SUCCESS) return status;
+      SLP_DEVICE_CALL(dev, slpb_eval_current(dev, 0, &cur));
+    } else {
+      if (alpha == alpha_max) full_step_rejected_counter = 0;  // :774-776
+      // x, s, y, z, f, c_e, c_i ← trial; clamp z (:779-805)
+      SLP_DEVICE_CALL(dev, slpb_accept(dev, mu));
+      cur = trial;
+    }
+
+    // Re-linearise: A_e, A_i, g, H at the new iterate (:809-812)
+    {
+      slpb_point_info derivs{};
+      SLP_DEVICE_CALL(dev, slpb_eval_current(dev, 2, &derivs));
+      cur.finite = derivs.finite;
+    }
+
+    // E_0 and the barrier update (:815-832)
+    SLP_DEVICE_CALL(dev, slpb_kkt_stats_current(dev, mu, &kkt));
+    E_0 = detail::kkt_error_unscaled_mu0(kkt, me, mi);
+    if (E_0 > Scalar(options.tolerance)) {
+      constexpr Scalar kappa_eps(10);
+      Scalar E_mu = detail::kkt_error_scaled(kkt, me, mi, mu);
+      while (mu > mu_min && E_mu <= kappa_eps * mu) {
+        update_barrier_parameter_and_reset_filter();
+        E_mu = detail::kkt_error_scaled(kkt, me, mi, mu);
+      }
+    }
+
+    if (trace != nullptr) {
+      IterationRecord row;
+      row.iteration = iterations;
+      row.type = in_feasibility_restoration ? 1 : 0;
+      row.error = E_0;
+      row.cost = cur.f;
+      row.infeasibility = cur.ce_l1 + cur.cis_l1;
+      row.complementarity = 0.0;
+      row.mu = mu;
+      row.delta = solver.hessian_regularization();
+      row.gamma = solver.constraint_jacobian_regularization();
+      row.alpha = alpha;
+      row.alpha_max = alpha_max;
+      row.alpha_z = alpha_z;
+      row.factorizations = solver.factorizations - fact_before;
+      row.solves = it_solves;
+      row.trials = it_trials;
+      if (trace->keep_iterates) {
+        row.x.resize(n);
+        row.s.resize(mi);
+        row.y.resize(me);
+        row.z.resize(mi);
+        SLP_DEVICE_CALL(dev, slpb_get_iterate(dev, row.x.data(), row.s.data(),
+                                              row.y.data(), row.z.data()));
+      }
+      trace->factorizations += row.factorizations;
+      trace->solves += it_solves;
+      trace->trials += it_trials;
+      trace->rows.push_back(std::move(row));
+    }
+    (void)accepted_step;
+
+    ++iterations;
+    if (iterations >= options.max_iterations) {  // :855-857
+      return ExitStatus::MAX_ITERATIONS_EXCEEDED;
+    }
+    if (std::chrono::steady_clock::now() - solve_start_time >
+        options.timeout) {  // :860-862
+      return ExitStatus::TIMEOUT;
+    }
+  }
+  return ExitStatus::SUCCESS;
+}
+
+}  // namespace slp
