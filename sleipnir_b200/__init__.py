@@ -1,0 +1,434 @@
+"""B200-native interior-point Newton step with a Sleipnir-compatible front end.
+
+This Python package is only a thin ctypes loader used by tests/, bench.py and
+__graft_entry__.py. The product is native:
+
+* ``lib/libslpb.so``      CUDA kernels for sm_100a behind the C ABI declared in
+                          ``include/slpb.h``;
+* ``lib/libslpb_host.so`` the host side in C++ (``slp::Problem`` DSL, the IPM
+                          driver, the benchmark problem builders).
+
+There is no CPU fallback: without the built libraries import fails, and without
+a CUDA device every solve raises ``DeviceError``.
+"""
+from __future__ import annotations
+
+import ctypes as C
+import os
+from dataclasses import dataclass
+
+import numpy as np
+
+_HERE = os.path.dirname(os.path.abspath(__file__))
+LIB_DEVICE = os.path.join(_HERE, "lib", "libslpb.so")
+LIB_HOST = os.path.join(_HERE, "lib", "libslpb_host.so")
+
+EXIT_STATUS = {
+    0: "SUCCESS", 1: "CALLBACK_REQUESTED_STOP", -1: "TOO_FEW_DOFS",
+    -2: "LOCALLY_INFEASIBLE", -3: "GLOBALLY_INFEASIBLE",
+    -4: "FACTORIZATION_FAILED", -5: "LINE_SEARCH_FAILED",
+    -6: "FEASIBILITY_RESTORATION_FAILED", -7: "NONFINITE_INITIAL_GUESS",
+    -8: "DIVERGING_ITERATES", -9: "MAX_ITERATIONS_EXCEEDED", -10: "TIMEOUT",
+}
+
+ORDER_NESTED_DISSECTION, ORDER_AMD, ORDER_NATURAL, ORDER_CUSTOM = 0, 1, 2, 3
+
+# enum slpb_output / slpb_array (include/slpb.h)
+OUT_F, OUT_G, OUT_H_F, OUT_H_C, OUT_C_E, OUT_A_E, OUT_C_I, OUT_A_I = range(8)
+(ARR_X, ARR_S, ARR_Y, ARR_Z, ARR_G, ARR_C_E, ARR_C_I, ARR_A_E_VAL,
+ ARR_A_I_VAL, ARR_H_VAL, ARR_KKT_VAL, ARR_D, ARR_RHS, ARR_P_X, ARR_P_S,
+ ARR_P_Y, ARR_P_Z, ARR_TRIAL_X, ARR_TRIAL_S, ARR_TRIAL_Y, ARR_TRIAL_Z,
+ ARR_TRIAL_C_E, ARR_TRIAL_C_I) = range(23)
+
+
+class DeviceError(RuntimeError):
+    """The CUDA library failed (no device, CUDA error, unsupported graph)."""
+
+
+_dp = C.POINTER(C.c_double)
+_ip = C.POINTER(C.c_int32)
+_lp = C.POINTER(C.c_int64)
+
+
+def _d(a):
+    return None if a is None else a.ctypes.data_as(_dp)
+
+
+def _i(a):
+    return None if a is None else a.ctypes.data_as(_ip)
+
+
+class PointInfo(C.Structure):
+    _fields_ = [("f", C.c_double), ("ce_l1", C.c_double),
+                ("cis_l1", C.c_double), ("log_s_sum", C.c_double),
+                ("finite", C.c_int32), ("ci_all_positive", C.c_int32)]
+
+
+class KktStats(C.Structure):
+    _fields_ = [(k, C.c_double) for k in (
+        "r_inf", "r_l1", "y_l1", "z_l1", "sz_min", "sz_max", "sz_mu_l1",
+        "ce_inf", "ce_l1", "cis_inf", "cis_l1", "u_r_inf", "u_y_l1", "u_z_l1",
+        "u_sz_min", "u_sz_max", "u_ce_inf", "u_cis_inf", "aetce_l2", "ce_l2",
+        "aitcip_l2", "cip_l2", "x_inf", "s_inf")] + [
+        ("xs_finite", C.c_int32), ("pad", C.c_int32)]
+
+
+class FactorInfo(C.Structure):
+    _fields_ = [("n_pos", C.c_int32), ("n_neg", C.c_int32),
+                ("n_zero", C.c_int32), ("zero_pivot", C.c_int32),
+                ("min_abs_d", C.c_double)]
+
+
+class StepInfo(C.Structure):
+    _fields_ = [(k, C.c_double) for k in (
+        "alpha_max", "alpha_z", "g_dot_px", "sinv_dot_ps", "px_inf", "ps_inf",
+        "py_inf", "pz_inf")] + [("finite", C.c_int32), ("pad", C.c_int32)]
+
+
+class SymbolicStats(C.Structure):
+    _fields_ = [("dim", C.c_int32), ("nnz_kkt", C.c_int64),
+                ("nnz_l", C.c_int64), ("nnz_l_stored", C.c_int64),
+                ("n_supernodes", C.c_int32), ("n_levels", C.c_int32),
+                ("max_front", C.c_int32), ("etree_height", C.c_int32)]
+
+
+class Counters(C.Structure):
+    _fields_ = [(k, C.c_int64) for k in (
+        "kernel_launches", "factorizations", "solves", "evals_full",
+        "evals_values", "tape_nodes", "program_bytes", "n_clusters",
+        "n_program_classes", "h2d_bytes", "d2h_bytes")]
+
+
+# Every symbol include/slpb.h declares (tests check that the library exports
+# all of them).
+ABI_SYMBOLS = [
+    "slpb_create", "slpb_destroy", "slpb_last_error", "slpb_upload_tape",
+    "slpb_upload_rows", "slpb_finalize", "slpb_set_scaling",
+    "slpb_set_ignore_constraint_hessian", "slpb_analyze",
+    "slpb_get_permutation", "slpb_set_iterate", "slpb_get_iterate",
+    "slpb_eval_current", "slpb_kkt_stats_current", "slpb_kkt_stats_trial",
+    "slpb_factor", "slpb_solve", "slpb_soc_begin", "slpb_soc_iterate",
+    "slpb_trial", "slpb_accept", "slpb_array_size", "slpb_download",
+    "slpb_pattern", "slpb_get_counters", "slpb_last_device_ms", "slpb_stream",
+]
+
+_dev = None
+_host = None
+
+
+def device_lib() -> C.CDLL:
+    global _dev
+    if _dev is None:
+        if not os.path.exists(LIB_DEVICE):
+            raise ImportError(
+                f"{LIB_DEVICE} is missing: build it with `make -C sleipnir_b200`"
+                " (or `python -c 'import __graft_entry__ as g; g.build()'`)")
+        L = C.CDLL(LIB_DEVICE, mode=C.RTLD_GLOBAL)
+        vp = C.c_void_p
+        L.slpb_last_error.restype = C.c_char_p
+        L.slpb_last_error.argtypes = [vp]
+        L.slpb_set_scaling.argtypes = [vp, C.c_double, _dp, _dp]
+        L.slpb_analyze.argtypes = [vp, C.c_int, _ip, C.POINTER(SymbolicStats)]
+        L.slpb_get_permutation.argtypes = [vp, _ip]
+        L.slpb_set_iterate.argtypes = [vp, _dp, _dp, _dp, _dp]
+        L.slpb_get_iterate.argtypes = [vp, _dp, _dp, _dp, _dp]
+        L.slpb_eval_current.argtypes = [vp, C.c_int, C.POINTER(PointInfo)]
+        L.slpb_kkt_stats_current.argtypes = [vp, C.c_double, C.POINTER(KktStats)]
+        L.slpb_kkt_stats_trial.argtypes = [vp, C.c_double, C.POINTER(KktStats)]
+        L.slpb_factor.argtypes = [vp, C.c_double, C.c_double, C.c_int,
+                                  C.POINTER(FactorInfo)]
+        L.slpb_solve.argtypes = [vp, C.c_double, C.c_double, C.POINTER(StepInfo)]
+        L.slpb_soc_begin.argtypes = [vp]
+        L.slpb_soc_iterate.argtypes = [vp, C.c_double, C.c_double, C.c_double,
+                                       C.POINTER(StepInfo)]
+        L.slpb_trial.argtypes = [vp, C.c_double, C.c_double, C.c_int, C.c_int,
+                                 C.POINTER(PointInfo)]
+        L.slpb_accept.argtypes = [vp, C.c_double]
+        L.slpb_array_size.argtypes = [vp, C.c_int, _lp]
+        L.slpb_download.argtypes = [vp, C.c_int, _dp]
+        L.slpb_pattern.argtypes = [vp, C.c_int, _ip, _ip, _lp, _ip, _ip]
+        L.slpb_get_counters.argtypes = [vp, C.POINTER(Counters)]
+        L.slpb_last_device_ms.argtypes = [vp, C.c_int, C.POINTER(C.c_float)]
+        L.slpb_stream.restype = vp
+        L.slpb_stream.argtypes = [vp]
+        _dev = L
+    return _dev
+
+
+def host_lib() -> C.CDLL:
+    global _host
+    if _host is None:
+        device_lib()
+        if not os.path.exists(LIB_HOST):
+            raise ImportError(
+                f"{LIB_HOST} is missing: build it with `make -C sleipnir_b200`")
+        L = C.CDLL(LIB_HOST)
+        vp = C.c_void_p
+        L.slpbh_problem_create.restype = vp
+        L.slpbh_problem_create.argtypes = [C.c_char_p, C.c_int, C.c_double,
+                                           C.c_double]
+        L.slpbh_problem_destroy.argtypes = [vp]
+        L.slpbh_error.restype = C.c_char_p
+        L.slpbh_error.argtypes = [vp]
+        L.slpbh_dims.argtypes = [vp, _ip, _ip, _ip]
+        L.slpbh_types.argtypes = [vp, _ip, _ip, _ip]
+        L.slpbh_initial_guess.argtypes = [vp, _dp]
+        L.slpbh_set_guess.argtypes = [vp, _dp]
+        L.slpbh_solve.restype = C.c_int
+        L.slpbh_solve.argtypes = [vp, C.c_double, C.c_int, C.c_int, C.c_int,
+                                  C.c_int, _ip, C.c_int]
+        L.slpbh_trace_rows.restype = C.c_int
+        L.slpbh_trace_rows.argtypes = [vp]
+        L.slpbh_trace_get.argtypes = [vp, C.c_int, _dp, _dp, _dp, _dp, _dp]
+        L.slpbh_solution.argtypes = [vp, _dp, _dp, _dp, _dp]
+        L.slpbh_loop_seconds.restype = C.c_double
+        L.slpbh_loop_seconds.argtypes = [vp]
+        L.slpbh_symbolic_stats.argtypes = [vp, _lp]
+        L.slpbh_counters.argtypes = [vp, _lp]
+        L.slpbh_device_open.restype = vp
+        L.slpbh_device_open.argtypes = [vp, C.c_int]
+        L.slpbh_device_close.argtypes = [vp]
+        _host = L
+    return _host
+
+
+@dataclass
+class IterationRecord:
+    iteration: int
+    type: int
+    error: float
+    cost: float
+    infeasibility: float
+    complementarity: float
+    mu: float
+    delta: float
+    gamma: float
+    alpha: float
+    alpha_max: float
+    alpha_z: float
+    factorizations: int
+    solves: int
+    trials: int
+    x: np.ndarray | None = None
+    s: np.ndarray | None = None
+    y: np.ndarray | None = None
+    z: np.ndarray | None = None
+
+
+class DeviceSession:
+    """Direct access to the C ABI for a problem that was uploaded already."""
+
+    def __init__(self, raw, n, me, mi):
+        self.L = device_lib()
+        self.raw = C.c_void_p(raw)
+        self.n, self.me, self.mi = n, me, mi
+
+    def _check(self, rc, what):
+        if rc != 0:
+            raise DeviceError(
+                f"{what}: {self.L.slpb_last_error(self.raw).decode()} ({rc})")
+
+    def set_scaling(self, d_f, d_ce, d_ci):
+        d_ce = np.ascontiguousarray(d_ce, dtype=np.float64)
+        d_ci = np.ascontiguousarray(d_ci, dtype=np.float64)
+        self._check(self.L.slpb_set_scaling(self.raw, d_f, _d(d_ce), _d(d_ci)),
+                    "slpb_set_scaling")
+
+    def analyze(self, ordering=ORDER_NESTED_DISSECTION, perm=None):
+        st = SymbolicStats()
+        p = None if perm is None else np.ascontiguousarray(perm, dtype=np.int32)
+        self._check(self.L.slpb_analyze(self.raw, ordering, _i(p), C.byref(st)),
+                    "slpb_analyze")
+        return st
+
+    def permutation(self):
+        p = np.zeros(self.n + self.me, dtype=np.int32)
+        self._check(self.L.slpb_get_permutation(self.raw, _i(p)),
+                    "slpb_get_permutation")
+        return p
+
+    def set_iterate(self, x, s, y, z):
+        a = [np.ascontiguousarray(v, dtype=np.float64) for v in (x, s, y, z)]
+        self._check(self.L.slpb_set_iterate(self.raw, *[_d(v) for v in a]),
+                    "slpb_set_iterate")
+
+    def get_iterate(self):
+        x, s = np.zeros(self.n), np.zeros(self.mi)
+        y, z = np.zeros(self.me), np.zeros(self.mi)
+        self._check(self.L.slpb_get_iterate(self.raw, _d(x), _d(s), _d(y), _d(z)),
+                    "slpb_get_iterate")
+        return x, s, y, z
+
+    def eval_current(self, derivatives=1):
+        info = PointInfo()
+        self._check(self.L.slpb_eval_current(self.raw, derivatives,
+                                             C.byref(info)), "slpb_eval_current")
+        return info
+
+    def kkt_stats(self, mu, trial=False):
+        st = KktStats()
+        fn = self.L.slpb_kkt_stats_trial if trial else self.L.slpb_kkt_stats_current
+        self._check(fn(self.raw, mu, C.byref(st)), "slpb_kkt_stats")
+        return st
+
+    def factor(self, delta, gamma, reassemble=True):
+        info = FactorInfo()
+        self._check(self.L.slpb_factor(self.raw, delta, gamma, int(reassemble),
+                                       C.byref(info)), "slpb_factor")
+        return info
+
+    def solve(self, mu, tau):
+        info = StepInfo()
+        self._check(self.L.slpb_solve(self.raw, mu, tau, C.byref(info)),
+                    "slpb_solve")
+        return info
+
+    def soc_begin(self):
+        self._check(self.L.slpb_soc_begin(self.raw), "slpb_soc_begin")
+
+    def soc_iterate(self, mu, tau, alpha_soc):
+        info = StepInfo()
+        self._check(self.L.slpb_soc_iterate(self.raw, mu, tau, alpha_soc,
+                                            C.byref(info)), "slpb_soc_iterate")
+        return info
+
+    def trial(self, alpha, alpha_z, which_step=0, slack_from_ci=0):
+        info = PointInfo()
+        self._check(self.L.slpb_trial(self.raw, alpha, alpha_z, which_step,
+                                      slack_from_ci, C.byref(info)), "slpb_trial")
+        return info
+
+    def accept(self, mu):
+        self._check(self.L.slpb_accept(self.raw, mu), "slpb_accept")
+
+    def download(self, which):
+        cnt = C.c_int64()
+        self._check(self.L.slpb_array_size(self.raw, which, C.byref(cnt)),
+                    "slpb_array_size")
+        out = np.zeros(max(cnt.value, 1))
+        self._check(self.L.slpb_download(self.raw, which, _d(out)),
+                    "slpb_download")
+        return out[:cnt.value]
+
+    def pattern(self, which):
+        r, c, nnz = C.c_int32(), C.c_int32(), C.c_int64()
+        self._check(self.L.slpb_pattern(self.raw, which, C.byref(r), C.byref(c),
+                                        C.byref(nnz), None, None), "slpb_pattern")
+        colptr = np.zeros(c.value + 1, dtype=np.int32)
+        rowidx = np.zeros(max(nnz.value, 1), dtype=np.int32)
+        self._check(self.L.slpb_pattern(self.raw, which, C.byref(r), C.byref(c),
+                                        C.byref(nnz), _i(colptr), _i(rowidx)),
+                    "slpb_pattern")
+        return r.value, c.value, colptr, rowidx[:nnz.value]
+
+    def counters(self):
+        c = Counters()
+        self.L.slpb_get_counters(self.raw, C.byref(c))
+        return c
+
+    def last_device_ms(self, which):
+        ms = C.c_float()
+        self._check(self.L.slpb_last_device_ms(self.raw, which, C.byref(ms)),
+                    "slpb_last_device_ms")
+        return ms.value
+
+
+class Problem:
+    """A named benchmark / test problem built by the C++ host side."""
+
+    def __init__(self, name: str, N: int = 0, p0: float = 0.0, p1: float = 0.0):
+        self.H = host_lib()
+        self.h = self.H.slpbh_problem_create(name.encode(), N, p0, p1)
+        if not self.h:
+            raise ValueError(f"unknown problem {name!r}")
+        n, me, mi = C.c_int32(), C.c_int32(), C.c_int32()
+        self.H.slpbh_dims(self.h, C.byref(n), C.byref(me), C.byref(mi))
+        self.n, self.me, self.mi = n.value, me.value, mi.value
+        self._keep = False
+
+    def close(self):
+        if self.h:
+            self.H.slpbh_problem_destroy(self.h)
+            self.h = None
+
+    def __del__(self):
+        try:
+            self.close()
+        except Exception:
+            pass
+
+    def types(self):
+        f, ce, ci = C.c_int32(), C.c_int32(), C.c_int32()
+        self.H.slpbh_types(self.h, C.byref(f), C.byref(ce), C.byref(ci))
+        return f.value, ce.value, ci.value
+
+    def initial_guess(self):
+        x = np.zeros(self.n)
+        self.H.slpbh_initial_guess(self.h, _d(x))
+        return x
+
+    def set_guess(self, x):
+        x = np.ascontiguousarray(x, dtype=np.float64)
+        self.H.slpbh_set_guess(self.h, _d(x))
+
+    def solve(self, tolerance=1e-8, max_iterations=5000, feasible_ipm=False,
+              device=0, ordering=ORDER_NESTED_DISSECTION, perm=None,
+              keep_iterates=False) -> int:
+        p = None
+        if perm is not None:
+            p = np.ascontiguousarray(perm, dtype=np.int32)
+            ordering = ORDER_CUSTOM
+        self._keep = keep_iterates
+        st = self.H.slpbh_solve(self.h, tolerance, max_iterations,
+                                int(feasible_ipm), device, ordering, _i(p),
+                                int(keep_iterates))
+        if st == -100:
+            raise DeviceError(self.H.slpbh_error(self.h).decode())
+        return st
+
+    def trace(self):
+        rows = []
+        for r in range(self.H.slpbh_trace_rows(self.h)):
+            sc = np.zeros(16)
+            x = s = y = z = None
+            if self._keep:
+                x, s = np.zeros(self.n), np.zeros(max(self.mi, 1))
+                y, z = np.zeros(max(self.me, 1)), np.zeros(max(self.mi, 1))
+            self.H.slpbh_trace_get(self.h, r, _d(sc), _d(x), _d(s), _d(y), _d(z))
+            if self._keep:
+                s, y, z = s[:self.mi], y[:self.me], z[:self.mi]
+            rows.append(IterationRecord(int(sc[0]), int(sc[1]), *sc[2:12],
+                                        int(sc[12]), int(sc[13]), int(sc[14]),
+                                        x, s, y, z))
+        return rows
+
+    def solution(self):
+        x, s = np.zeros(self.n), np.zeros(max(self.mi, 1))
+        y, z = np.zeros(max(self.me, 1)), np.zeros(max(self.mi, 1))
+        self.H.slpbh_solution(self.h, _d(x), _d(s), _d(y), _d(z))
+        return x, s[:self.mi], y[:self.me], z[:self.mi]
+
+    def loop_seconds(self):
+        return self.H.slpbh_loop_seconds(self.h)
+
+    def symbolic_stats(self):
+        out = np.zeros(8, dtype=np.int64)
+        self.H.slpbh_symbolic_stats(self.h, out.ctypes.data_as(_lp))
+        keys = ("dim", "nnz_kkt", "nnz_l", "nnz_l_stored", "n_supernodes",
+                "n_levels", "max_front", "etree_height")
+        return dict(zip(keys, (int(v) for v in out)))
+
+    def counters(self):
+        out = np.zeros(11, dtype=np.int64)
+        self.H.slpbh_counters(self.h, out.ctypes.data_as(_lp))
+        keys = [k for k, _ in Counters._fields_]
+        return dict(zip(keys, (int(v) for v in out)))
+
+    def open_device(self, device=0) -> DeviceSession:
+        raw = self.H.slpbh_device_open(self.h, device)
+        if not raw:
+            raise DeviceError(self.H.slpbh_error(self.h).decode())
+        return DeviceSession(raw, self.n, self.me, self.mi)
+
+    def close_device(self):
+        self.H.slpbh_device_close(self.h)

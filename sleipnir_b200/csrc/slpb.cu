@@ -1,0 +1,1608 @@
+// libslpb.so — CUDA kernels (sm_100a) and the C ABI of include/slpb.h.
+//
+// Data layout in HBM (all FP64 unless noted), resident for a whole solve:
+//   iterate      x[n] s[mi] y[me] z[mi]      + trial copies
+//   leaves       [x | d_ce⊙y | d_ci⊙z]       what the tape's VAR nodes read
+//   programs     cluster programs + bindings (u32 words; see internal.hpp)
+//   stage        [constants | swept outputs] per program set
+//   values       [f | c_e | c_i]             current and trial
+//   derivatives  [g | A_e.val | A_i.val | H.val]   (CSC patterns are static)
+//   KKT          Kval[nnz(lhs)] in the reference's column-major lower order
+//   factor       supernodal panels, update matrices, D, in elimination order
+// Every kernel below is launched on the handle's stream; the host only reads
+// back small result structs through pinned memory.
+//
+// There is deliberately no CPU implementation behind this ABI: without a CUDA
+// device slpb_create fails with SLPB_ERR_NO_DEVICE.
+#include <cuda_runtime.h>
+
+#include <algorithm>
+#include <cmath>
+#include <cstdio>
+#include <cstring>
+#include <memory>
+#include <string>
+#include <vector>
+
+#include "ad_core.hpp"
+#include "internal.hpp"
+#include "kkt_core.hpp"
+#include "ldlt_core.hpp"
+#include "slpb.h"
+
+namespace slpb {
+
+// ---------------------------------------------------------------------------
+// small RAII helpers
+// ---------------------------------------------------------------------------
+
+template <typename T>
+struct DevBuf {
+  T* p = nullptr;
+  size_t n = 0;
+  DevBuf() = default;
+  DevBuf(const DevBuf&) = delete;
+  DevBuf& operator=(const DevBuf&) = delete;
+  ~DevBuf() { release(); }
+  void release() {
+    if (p) cudaFree(p);
+    p = nullptr;
+    n = 0;
+  }
+  cudaError_t alloc(size_t count) {
+    release();
+    n = count;
+    if (count == 0) return cudaSuccess;
+    return cudaMalloc(&p, count * sizeof(T));
+  }
+  cudaError_t upload(const std::vector<T>& v, cudaStream_t st) {
+    cudaError_t e = alloc(v.size());
+    if (e != cudaSuccess || v.empty()) return e;
+    return cudaMemcpyAsync(p, v.data(), v.size() * sizeof(T),
+                           cudaMemcpyHostToDevice, st);
+  }
+  cudaError_t zero(cudaStream_t st) {
+    if (!n) return cudaSuccess;
+    return cudaMemsetAsync(p, 0, n * sizeof(T), st);
+  }
+};
+
+struct DevProgramSet {
+  DevBuf<uint32_t> blob, bindings;
+  DevBuf<int64_t> prog_offset, cluster_bind;
+  DevBuf<int32_t> cluster_prog;
+  int n_clusters = 0, warps_per_block = 1, smem_per_warp = 0;
+};
+
+struct DevGather {
+  DevBuf<int32_t> ptr, src_idx, src_scale;
+  DevBuf<int32_t> long_entries;  // entries with many sources
+  int n_entries = 0, n_long = 0;
+};
+
+constexpr int kResultDoubles = 64;
+constexpr int kLongGather = 48;  // sources above which a block reduces an entry
+constexpr int kReduceThreads = 1024;
+
+}  // namespace slpb
+
+using namespace slpb;
+
+struct slpb_solver {
+  int device = 0;
+  cudaStream_t stream = nullptr;
+  std::string error = "";
+  // host side
+  Tape tape;
+  RowSet rows[SLPB_OUT_COUNT];
+  CompiledAD ad;
+  KktRecipe recipe;
+  Symbolic sym;
+  bool have_tape = false, finalized = false, analyzed = false;
+  bool ignore_h_c = false;
+  int n = 0, me = 0, mi = 0, dim = 0;
+  double d_f = 1.0;
+  slpb_counters counters{};
+  // device: programs
+  DevProgramSet pv, pd;
+  DevGather gv, gd;
+  DevBuf<double> vstage, dstage;
+  // device: state
+  DevBuf<double> leaf_cur, leaf_trial, d_c;
+  DevBuf<double> x, s, y, z, tx, ts, ty, tz;
+  DevBuf<double> vals_cur, vals_trial, dvals;
+  DevBuf<int32_t> ae_colptr, ae_rowidx, ai_colptr, ai_rowidx;
+  DevBuf<int32_t> ai_rowptr, ai_rcol, ai_ridx;  // A_i by rows
+  // device: KKT
+  DevBuf<int32_t> k_h_idx, k_ae_idx, k_prod_ptr, k_prod_a, k_prod_b, k_prod_row;
+  DevBuf<double> Kval, sigma, sinv, tvec, rhs, sol;
+  // device: symbolic + factor
+  DevBuf<int32_t> sy_super_first, sy_front_dim, sy_rows_idx, sy_child_idx,
+      sy_rel_idx, sy_asm_src, sy_asm_dst, sy_perm, sy_level_supers;
+  DevBuf<int64_t> sy_rows_ptr, sy_panel_ptr, sy_update_ptr, sy_child_ptr,
+      sy_rel_ptr, sy_asm_ptr;
+  DevBuf<uint8_t> sy_col_is_primal;
+  DevBuf<double> panels, updates, D, uvecs, xperm;
+  DevBuf<int32_t> fstats;  // FactorStats as 6 ints
+  SymbolicView sview{};
+  // device: steps
+  DevBuf<double> px, ps, py, pz, spx, sps, spy, spz, ce_soc, cis_soc;
+  // results
+  DevBuf<double> d_results;
+  double* h_results = nullptr;  // pinned
+  // timing
+  cudaEvent_t ev[10] = {};
+  float last_ms[5] = {0, 0, 0, 0, 0};
+};
+
+namespace slpb {
+
+#define CU(call)                                                          \
+  do {                                                                    \
+    cudaError_t e_ = (call);                                              \
+    if (e_ != cudaSuccess) {                                              \
+      S->error = std::string(#call) + ": " + cudaGetErrorString(e_);      \
+      return SLPB_ERR_CUDA;                                               \
+    }                                                                     \
+  } while (0)
+
+inline int fail(slpb_solver* S, int code, const std::string& msg) {
+  S->error = msg;
+  return code;
+}
+
+// ---------------------------------------------------------------------------
+// kernels: autodiff
+// ---------------------------------------------------------------------------
+
+struct WarpSync {
+  __device__ __forceinline__ void operator()() const { __syncwarp(); }
+};
+struct BlockSync {
+  __device__ __forceinline__ void operator()() const { __syncthreads(); }
+};
+
+/// One warp per cluster; values and adjoints of the cluster live in shared
+/// memory (smem_per_warp bytes each). Replaces update_values +
+/// append_triplets (expression_graph.hpp:85-153) for all rows of a cluster.
+__global__ void k_ad_sweep(const uint32_t* __restrict__ blob,
+                           const int64_t* __restrict__ prog_offset,
+                           const int32_t* __restrict__ cluster_prog,
+                           const int64_t* __restrict__ cluster_bind,
+                           const uint32_t* __restrict__ bindings,
+                           int n_clusters, int smem_doubles_per_warp,
+                           const double* __restrict__ leaf,
+                           double* __restrict__ stage) {
+  extern __shared__ double smem[];
+  const int warp = threadIdx.x >> 5;
+  const int lane = threadIdx.x & 31;
+  const int c = blockIdx.x * (blockDim.x >> 5) + warp;
+  if (c >= n_clusters) return;
+  const uint32_t* P = blob + prog_offset[cluster_prog[c]];
+  const uint32_t* B = bindings + cluster_bind[c];
+  double* scratch = smem + size_t(warp) * smem_doubles_per_warp;
+  ad_run_cluster<32>(lane, P, B, leaf, stage, scratch, WarpSync{});
+}
+
+__global__ void k_gather(const int32_t* __restrict__ ptr,
+                         const int32_t* __restrict__ src_idx,
+                         const int32_t* __restrict__ src_scale,
+                         const double* __restrict__ stage, double d_f,
+                         const double* __restrict__ d_c,
+                         double* __restrict__ out, int n_entries) {
+  const int e = blockIdx.x * blockDim.x + threadIdx.x;
+  if (e >= n_entries) return;
+  if (ptr[e + 1] - ptr[e] > kLongGather) return;  // k_gather_long does these
+  out[e] = gather_entry(e, ptr, src_idx, src_scale, stage, d_f, d_c);
+}
+
+/// One block per entry with a long source list (a split Σ_k cost): fixed-shape
+/// tree reduction, deterministic from run to run.
+__global__ void k_gather_long(const int32_t* __restrict__ entries,
+                              const int32_t* __restrict__ ptr,
+                              const int32_t* __restrict__ src_idx,
+                              const int32_t* __restrict__ src_scale,
+                              const double* __restrict__ stage, double d_f,
+                              const double* __restrict__ d_c,
+                              double* __restrict__ out) {
+  __shared__ double red[256];
+  const int e = entries[blockIdx.x];
+  const int b = ptr[e], en = ptr[e + 1];
+  double acc = 0.0;
+  for (int k = b + threadIdx.x; k < en; k += blockDim.x) {
+    const int32_t raw = src_idx[k];
+    double v = stage[raw & 0x7fffffff];
+    if (raw < 0) v = -v;
+    const int32_t sc = src_scale[k];
+    if (sc == -2) {
+      v = d_f * v;
+    } else if (sc >= 0) {
+      v = d_c[sc] * v;
+    }
+    acc += v;
+  }
+  red[threadIdx.x] = acc;
+  __syncthreads();
+  for (int w = blockDim.x / 2; w > 0; w >>= 1) {
+    if (threadIdx.x < w) red[threadIdx.x] += red[threadIdx.x + w];
+    __syncthreads();
+  }
+  if (threadIdx.x == 0) out[e] = red[0];
+}
+
+__global__ void k_prepare_leaves(const double* __restrict__ x,
+                                 const double* __restrict__ y,
+                                 const double* __restrict__ z,
+                                 const double* __restrict__ d_c, int n, int me,
+                                 int mi, double* __restrict__ leaf) {
+  const int i = blockIdx.x * blockDim.x + threadIdx.x;
+  if (i < n) {
+    leaf[i] = x[i];
+  } else if (i < n + me) {
+    leaf[i] = d_c[i - n] * y[i - n];
+  } else if (i < n + me + mi) {
+    leaf[i] = d_c[i - n] * z[i - n - me];
+  }
+}
+
+// ---------------------------------------------------------------------------
+// kernels: reductions (single block; sizes here are 1e4..1e5)
+// ---------------------------------------------------------------------------
+
+enum RedOp { RED_SUM = 0, RED_MAX = 1, RED_MIN = 2 };
+
+template <int NV>
+__device__ void block_reduce(double (&v)[NV], const int (&op)[NV],
+                             double* out) {
+  __shared__ double red[NV][kReduceThreads / 32];
+  const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+#pragma unroll
+  for (int q = 0; q < NV; ++q) {
+    double a = v[q];
+    for (int o = 16; o > 0; o >>= 1) {
+      const double b = __shfl_down_sync(0xffffffffu, a, o);
+      a = op[q] == RED_SUM ? a + b : (op[q] == RED_MAX ? fmax(a, b) : fmin(a, b));
+    }
+    if (lane == 0) red[q][warp] = a;
+  }
+  __syncthreads();
+  if (warp == 0) {
+    const int nw = blockDim.x >> 5;
+#pragma unroll
+    for (int q = 0; q < NV; ++q) {
+      double a = lane < nw ? red[q][lane]
+                           : (op[q] == RED_SUM ? 0.0
+                              : op[q] == RED_MAX ? -INFINITY : INFINITY);
+      for (int o = 16; o > 0; o >>= 1) {
+        const double b = __shfl_down_sync(0xffffffffu, a, o);
+        a = op[q] == RED_SUM ? a + b
+                             : (op[q] == RED_MAX ? fmax(a, b) : fmin(a, b));
+      }
+      if (lane == 0) out[q] = a;
+    }
+  }
+  __syncthreads();
+}
+
+/// slpb_point_info for a point: vals = [f | c_e | c_i], slack s.
+/// out: f, ce_l1, cis_l1, log_s_sum, finite bits (as double), ci_all_positive.
+__global__ void k_point_info(const double* __restrict__ vals,
+                             const double* __restrict__ s, int me, int mi,
+                             double* __restrict__ out) {
+  double v[5] = {0.0, 0.0, 0.0, 0.0, 0.0};
+  // v0 ce_l1, v1 cis_l1, v2 log sum, v3 nonfinite count c_e, v4 nonfinite c_i
+  double nonpos = 0.0;
+  const double* c_e = vals + 1;
+  const double* c_i = vals + 1 + me;
+  for (int i = threadIdx.x; i < me; i += blockDim.x) {
+    const double c = c_e[i];
+    v[0] += fabs(c);
+    if (!isfinite(c)) v[3] += 1.0;
+  }
+  for (int i = threadIdx.x; i < mi; i += blockDim.x) {
+    const double c = c_i[i];
+    v[1] += fabs(c - s[i]);
+    v[2] += log(s[i]);
+    if (!isfinite(c)) v[4] += 1.0;
+    if (!(c > 0.0)) nonpos += 1.0;
+  }
+  double w[6] = {v[0], v[1], v[2], v[3], v[4], nonpos};
+  const int op[6] = {RED_SUM, RED_SUM, RED_SUM, RED_SUM, RED_SUM, RED_SUM};
+  __shared__ double res[6];
+  block_reduce<6>(w, op, res);
+  if (threadIdx.x == 0) {
+    const double f = vals[0];
+    int bits = 0;
+    if (isfinite(f)) bits |= SLPB_FINITE_F;
+    if (res[3] == 0.0) bits |= SLPB_FINITE_C_E;
+    if (res[4] == 0.0) bits |= SLPB_FINITE_C_I;
+    out[0] = f;
+    out[1] = res[0];
+    out[2] = res[1];
+    out[3] = res[2];
+    out[4] = static_cast<double>(bits);
+    out[5] = res[5] == 0.0 ? 1.0 : 0.0;
+  }
+}
+
+/// Finite-ness of the derivative arrays: out[0] = OR of G/A_E/A_I/H bits.
+__global__ void k_deriv_finite(const double* __restrict__ dvals, int64_t off_ae,
+                               int64_t off_ai, int64_t off_h, int64_t total,
+                               double* __restrict__ out) {
+  double w[4] = {0.0, 0.0, 0.0, 0.0};
+  for (int64_t i = threadIdx.x; i < total; i += blockDim.x) {
+    if (!isfinite(dvals[i])) {
+      const int seg = i < off_ae ? 0 : (i < off_ai ? 1 : (i < off_h ? 2 : 3));
+      w[seg] += 1.0;
+    }
+  }
+  const int op[4] = {RED_SUM, RED_SUM, RED_SUM, RED_SUM};
+  __shared__ double res[4];
+  block_reduce<4>(w, op, res);
+  if (threadIdx.x == 0) {
+    int bits = 0;
+    if (res[0] == 0.0) bits |= SLPB_FINITE_G;
+    if (res[1] == 0.0) bits |= SLPB_FINITE_A_E;
+    if (res[2] == 0.0) bits |= SLPB_FINITE_A_I;
+    if (res[3] == 0.0) bits |= SLPB_FINITE_H;
+    out[0] = static_cast<double>(bits);
+  }
+}
+
+struct CscView {
+  const int32_t* colptr;
+  const int32_t* rowidx;
+  const double* val;
+};
+
+/// All reductions behind kkt_error / unscaled_kkt_error (kkt_error.hpp:92-251),
+/// is_locally_infeasible.hpp and the divergence guard, for one point.
+/// out layout = fields of slpb_kkt_stats in declaration order.
+__global__ void k_kkt_stats(CscView Ae, CscView Ai, const double* __restrict__ g,
+                            const double* __restrict__ c_e,
+                            const double* __restrict__ c_i,
+                            const double* __restrict__ x,
+                            const double* __restrict__ s,
+                            const double* __restrict__ y,
+                            const double* __restrict__ z,
+                            const double* __restrict__ d_c, double d_f,
+                            double mu, int n, int me, int mi,
+                            double* __restrict__ out) {
+  const double inv_d_f = 1.0 / d_f;
+  // 0 r_inf 1 r_l1 2 y_l1 3 z_l1 4 sz_min 5 sz_max 6 sz_mu_l1 7 ce_inf 8 ce_l1
+  // 9 cis_inf 10 cis_l1 11 u_r_inf 12 u_y_l1 13 u_z_l1 14 u_sz_min 15 u_sz_max
+  // 16 u_ce_inf 17 u_cis_inf 18 aetce_sq 19 ce_sq 20 aitcip_sq 21 cip_sq
+  // 22 x_inf 23 s_inf 24 nonfinite count
+  double v[25];
+  for (int q = 0; q < 25; ++q) v[q] = 0.0;
+  v[4] = INFINITY;
+  v[5] = -INFINITY;
+  v[14] = INFINITY;
+  v[15] = -INFINITY;
+  for (int c = threadIdx.x; c < n; c += blockDim.x) {
+    // scaled: g − A_eᵀy − A_iᵀz ; unscaled: g/d_f − (A_e/d_ce)ᵀ(d_ce y/d_f) − …
+    double aty = 0.0, atz = 0.0, u_aty = 0.0, u_atz = 0.0, atc = 0.0,
+           atcp = 0.0;
+    for (int k = Ae.colptr[c]; k < Ae.colptr[c + 1]; ++k) {
+      const int r = Ae.rowidx[k];
+      const double a = Ae.val[k];
+      aty += a * y[r];
+      const double dc = d_c[r];
+      u_aty += ((1.0 / dc) * a) * (dc * y[r] * inv_d_f);
+      atc += a * c_e[r];
+    }
+    for (int k = Ai.colptr[c]; k < Ai.colptr[c + 1]; ++k) {
+      const int r = Ai.rowidx[k];
+      const double a = Ai.val[k];
+      atz += a * z[r];
+      const double dc = d_c[me + r];
+      u_atz += ((1.0 / dc) * a) * (dc * z[r] * inv_d_f);
+      atcp += a * fmin(c_i[r], 0.0);
+    }
+    const double r = g[c] - aty - atz;
+    const double ur = inv_d_f * g[c] - u_aty - u_atz;
+    v[0] = fmax(v[0], fabs(r));
+    v[1] += fabs(r);
+    v[11] = fmax(v[11], fabs(ur));
+    v[18] += atc * atc;
+    v[20] += atcp * atcp;
+    const double xv = x[c];
+    v[22] = fmax(v[22], fabs(xv));
+    if (!isfinite(xv)) v[24] += 1.0;
+  }
+  for (int i = threadIdx.x; i < me; i += blockDim.x) {
+    const double c = c_e[i], yv = y[i], dc = d_c[i];
+    v[2] += fabs(yv);
+    v[7] = fmax(v[7], fabs(c));
+    v[8] += fabs(c);
+    v[12] += fabs(dc * yv * inv_d_f);
+    v[16] = fmax(v[16], fabs((1.0 / dc) * c));
+    v[19] += c * c;
+  }
+  for (int i = threadIdx.x; i < mi; i += blockDim.x) {
+    const double c = c_i[i], sv = s[i], zv = z[i], dc = d_c[me + i];
+    const double inv = 1.0 / dc;
+    v[3] += fabs(zv);
+    const double sz = sv * zv;
+    v[4] = fmin(v[4], sz);
+    v[5] = fmax(v[5], sz);
+    v[6] += fabs(sz - mu);
+    v[9] = fmax(v[9], fabs(c - sv));
+    v[10] += fabs(c - sv);
+    const double zu = dc * zv * inv_d_f;
+    v[13] += fabs(zu);
+    const double szu = (inv * sv) * zu;
+    v[14] = fmin(v[14], szu);
+    v[15] = fmax(v[15], szu);
+    v[17] = fmax(v[17], fabs(inv * c - inv * sv));
+    const double cp = fmin(c, 0.0);
+    v[21] += cp * cp;
+    v[23] = fmax(v[23], fabs(sv));
+    if (!isfinite(sv)) v[24] += 1.0;
+  }
+  const int op[25] = {RED_MAX, RED_SUM, RED_SUM, RED_SUM, RED_MIN, RED_MAX,
+                      RED_SUM, RED_MAX, RED_SUM, RED_MAX, RED_SUM, RED_MAX,
+                      RED_SUM, RED_SUM, RED_MIN, RED_MAX, RED_MAX, RED_MAX,
+                      RED_SUM, RED_SUM, RED_SUM, RED_SUM, RED_MAX, RED_MAX,
+                      RED_SUM};
+  __shared__ double res[25];
+  block_reduce<25>(v, op, res);
+  if (threadIdx.x == 0) {
+    for (int q = 0; q < 18; ++q) out[q] = res[q];
+    out[18] = sqrt(res[18]);
+    out[19] = sqrt(res[19]);
+    out[20] = sqrt(res[20]);
+    out[21] = sqrt(res[21]);
+    out[22] = res[22];
+    out[23] = res[23];
+    out[24] = res[24] == 0.0 ? 1.0 : 0.0;
+  }
+}
+
+// ---------------------------------------------------------------------------
+// kernels: KKT system
+// ---------------------------------------------------------------------------
+
+/// Σ = S⁻¹Z and the inequality part of the rhs (interior_point.hpp:426,447).
+/// mode 0: t = −Σc_i + μS⁻¹e + z ; mode 1 (SOC, :615): t = μS⁻¹e − Σ·cis_soc
+__global__ void k_sigma_t(const double* __restrict__ s,
+                          const double* __restrict__ z,
+                          const double* __restrict__ c_i,
+                          const double* __restrict__ cis_soc, double mu,
+                          int mode, int mi, double* __restrict__ sinv,
+                          double* __restrict__ sigma,
+                          double* __restrict__ t) {
+  const int i = blockIdx.x * blockDim.x + threadIdx.x;
+  if (i >= mi) return;
+  const double si = 1.0 / s[i];
+  const double sg = si * z[i];
+  sinv[i] = si;
+  sigma[i] = sg;
+  t[i] = mode == 0 ? (-sg * c_i[i] + mu * si + z[i])
+                   : (mu * si - sg * cis_soc[i]);
+}
+
+/// rhs = −[g − A_eᵀy − A_iᵀt ; c_e] (interior_point.hpp:444-448).
+__global__ void k_rhs(CscView Ae, CscView Ai, const double* __restrict__ g,
+                      const double* __restrict__ y,
+                      const double* __restrict__ t,
+                      const double* __restrict__ c_e, int n, int me,
+                      double* __restrict__ rhs) {
+  const int c = blockIdx.x * blockDim.x + threadIdx.x;
+  if (c < n) {
+    double aty = 0.0, att = 0.0;
+    for (int k = Ae.colptr[c]; k < Ae.colptr[c + 1]; ++k) {
+      aty += Ae.val[k] * y[Ae.rowidx[k]];
+    }
+    for (int k = Ai.colptr[c]; k < Ai.colptr[c + 1]; ++k) {
+      att += Ai.val[k] * t[Ai.rowidx[k]];
+    }
+    rhs[c] = -g[c] + aty + att;
+  } else if (c < n + me) {
+    rhs[c] = -c_e[c - n];
+  }
+}
+
+__global__ void k_kkt_assemble(const int32_t* __restrict__ h_idx,
+                               const int32_t* __restrict__ ae_idx,
+                               const int32_t* __restrict__ prod_ptr,
+                               const int32_t* __restrict__ prod_a,
+                               const int32_t* __restrict__ prod_b,
+                               const int32_t* __restrict__ prod_row,
+                               const double* __restrict__ Hv,
+                               const double* __restrict__ Aev,
+                               const double* __restrict__ Aiv,
+                               const double* __restrict__ sigma, int nnz,
+                               double* __restrict__ Kval) {
+  const int e = blockIdx.x * blockDim.x + threadIdx.x;
+  if (e >= nnz) return;
+  Kval[e] = kkt_entry(e, h_idx, ae_idx, prod_ptr, prod_a, prod_b, prod_row, Hv,
+                      Aev, Aiv, sigma);
+}
+
+// ---------------------------------------------------------------------------
+// kernels: multifrontal LDLᵀ, one thread block per front, one launch per
+// level of the assembly tree
+// ---------------------------------------------------------------------------
+
+constexpr int kFrontThreads = 128;
+
+__global__ void k_factor_level(SymbolicView S,
+                               const int32_t* __restrict__ level_supers,
+                               const double* __restrict__ Kval, double delta,
+                               double gamma, double* __restrict__ panels,
+                               double* __restrict__ updates,
+                               double* __restrict__ D,
+                               int32_t* __restrict__ stats) {
+  extern __shared__ double smem[];
+  __shared__ int ls[6];
+  const int s = level_supers[blockIdx.x];
+  const int F = S.front_dim[s];
+  double* W = smem;
+  double* lcol = smem + size_t(F) * F;
+  ldlt_factor_front<kFrontThreads>(threadIdx.x, s, S, Kval, delta, gamma,
+                                   panels, updates, D, W, lcol, ls,
+                                   BlockSync{});
+  if (threadIdx.x == 0) {
+    atomicAdd(&stats[0], ls[0]);
+    atomicAdd(&stats[1], ls[1]);
+    atomicAdd(&stats[2], ls[2]);
+    atomicOr(&stats[3], ls[3]);
+    const unsigned long long bits =
+        (unsigned long long)(unsigned)ls[4] |
+        ((unsigned long long)(unsigned)ls[5] << 32);
+    atomicMin(reinterpret_cast<unsigned long long*>(&stats[4]), bits);
+  }
+}
+
+__global__ void k_forward_level(SymbolicView S,
+                                const int32_t* __restrict__ level_supers,
+                                const double* __restrict__ panels,
+                                const double* __restrict__ rhs,
+                                double* __restrict__ xperm,
+                                double* __restrict__ uvecs) {
+  extern __shared__ double smem[];
+  const int s = level_supers[blockIdx.x];
+  ldlt_forward_front<kFrontThreads>(threadIdx.x, s, S, panels, rhs, xperm,
+                                    uvecs, smem, BlockSync{});
+}
+
+__global__ void k_backward_level(SymbolicView S,
+                                 const int32_t* __restrict__ level_supers,
+                                 const double* __restrict__ panels,
+                                 const double* __restrict__ D,
+                                 double* __restrict__ xperm) {
+  extern __shared__ double smem[];
+  const int s = level_supers[blockIdx.x];
+  ldlt_backward_front<kFrontThreads>(threadIdx.x, s, S, panels, D, xperm, smem,
+                                     BlockSync{});
+}
+
+__global__ void k_unpermute(const double* __restrict__ xperm,
+                            const int32_t* __restrict__ perm, int dim,
+                            double* __restrict__ sol) {
+  const int k = blockIdx.x * blockDim.x + threadIdx.x;
+  if (k < dim) sol[perm[k]] = xperm[k];
+}
+
+// ---------------------------------------------------------------------------
+// kernels: step recovery, line search
+// ---------------------------------------------------------------------------
+
+/// p_x, p_y = −p₂, p_s = cis + A_i p_x, p_z = μ/s − z − Σ p_s
+/// (interior_point.hpp:470-481). cis = c_i − s, or the SOC accumulator.
+__global__ void k_step_recover(const double* __restrict__ sol,
+                               const int32_t* __restrict__ ai_rowptr,
+                               const int32_t* __restrict__ ai_rcol,
+                               const int32_t* __restrict__ ai_ridx,
+                               const double* __restrict__ ai_val,
+                               const double* __restrict__ c_i,
+                               const double* __restrict__ s,
+                               const double* __restrict__ z,
+                               const double* __restrict__ cis_soc,
+                               const double* __restrict__ sinv,
+                               const double* __restrict__ sigma, double mu,
+                               int n, int me, int mi, double* __restrict__ px,
+                               double* __restrict__ py,
+                               double* __restrict__ ps,
+                               double* __restrict__ pz) {
+  const int i = blockIdx.x * blockDim.x + threadIdx.x;
+  if (i < n) px[i] = sol[i];
+  if (i < me) py[i] = -sol[n + i];
+  if (i < mi) {
+    double acc = 0.0;
+    for (int k = ai_rowptr[i]; k < ai_rowptr[i + 1]; ++k) {
+      acc += ai_val[ai_ridx[k]] * sol[ai_rcol[k]];
+    }
+    const double cis = cis_soc ? cis_soc[i] : (c_i[i] - s[i]);
+    const double p = cis + acc;
+    ps[i] = p;
+    pz[i] = mu * sinv[i] - z[i] - sigma[i] * p;
+  }
+}
+
+/// fraction-to-the-boundary rule on (s,p_s) and (z,p_z)
+/// (fraction_to_the_boundary_rule.hpp:19-43: α = min(1, min −τ/pᵢ·xᵢ over the
+/// blocking components), gᵀpˣ, (S⁻¹e)ᵀpˢ and step norms.
+__global__ void k_step_stats(const double* __restrict__ g,
+                             const double* __restrict__ s,
+                             const double* __restrict__ z,
+                             const double* __restrict__ sinv,
+                             const double* __restrict__ px,
+                             const double* __restrict__ ps,
+                             const double* __restrict__ py,
+                             const double* __restrict__ pz, double tau, int n,
+                             int me, int mi, double* __restrict__ out) {
+  // 0 alpha_max 1 alpha_z 2 g·px 3 sinv·ps 4..7 inf norms 8 nonfinite
+  double v[9] = {1.0, 1.0, 0.0, 0.0, 0.0, 0.0, 0.0, 0.0, 0.0};
+  for (int i = threadIdx.x; i < n; i += blockDim.x) {
+    const double p = px[i];
+    v[2] += g[i] * p;
+    v[4] = fmax(v[4], fabs(p));
+    if (!isfinite(p)) v[8] += 1.0;
+  }
+  for (int i = threadIdx.x; i < me; i += blockDim.x) {
+    v[6] = fmax(v[6], fabs(py[i]));
+  }
+  for (int i = threadIdx.x; i < mi; i += blockDim.x) {
+    const double p = ps[i], q = pz[i];
+    if (p < 0.0) {
+      const double cand = -tau / p * s[i];
+      if (cand < v[0]) v[0] = cand;
+    }
+    if (q < 0.0) {
+      const double cand = -tau / q * z[i];
+      if (cand < v[1]) v[1] = cand;
+    }
+    v[3] += sinv[i] * p;
+    v[5] = fmax(v[5], fabs(p));
+    v[7] = fmax(v[7], fabs(q));
+    if (!isfinite(p) || !isfinite(q)) v[8] += 1.0;
+  }
+  const int op[9] = {RED_MIN, RED_MIN, RED_SUM, RED_SUM, RED_MAX,
+                     RED_MAX, RED_MAX, RED_MAX, RED_SUM};
+  __shared__ double res[9];
+  block_reduce<9>(v, op, res);
+  if (threadIdx.x == 0) {
+    for (int q = 0; q < 8; ++q) out[q] = res[q];
+    out[8] = res[8] == 0.0 ? 1.0 : 0.0;
+  }
+}
+
+/// trial = iterate + α (p_x, p_s) and + α_z (p_y, p_z); writes trial x into
+/// the trial leaf vector as well.
+__global__ void k_trial_point(const double* __restrict__ x,
+                              const double* __restrict__ s,
+                              const double* __restrict__ y,
+                              const double* __restrict__ z,
+                              const double* __restrict__ px,
+                              const double* __restrict__ ps,
+                              const double* __restrict__ py,
+                              const double* __restrict__ pz, double alpha,
+                              double alpha_z, int n, int me, int mi,
+                              double* __restrict__ tx, double* __restrict__ ts,
+                              double* __restrict__ ty, double* __restrict__ tz,
+                              double* __restrict__ leaf_trial) {
+  const int i = blockIdx.x * blockDim.x + threadIdx.x;
+  if (i < n) {
+    const double v = x[i] + alpha * px[i];
+    tx[i] = v;
+    leaf_trial[i] = v;
+  }
+  if (i < mi) {
+    ts[i] = s[i] + alpha * ps[i];
+    tz[i] = z[i] + alpha_z * pz[i];
+  }
+  if (i < me) ty[i] = y[i] + alpha_z * py[i];
+}
+
+__global__ void k_copy(const double* __restrict__ src, double* __restrict__ dst,
+                       int n) {
+  const int i = blockIdx.x * blockDim.x + threadIdx.x;
+  if (i < n) dst[i] = src[i];
+}
+
+/// Commit: z ← clamp(z, μ/(κ s), κ μ / s), κ = 1e10 (interior_point.hpp:797-801).
+__global__ void k_clamp_z(const double* __restrict__ s, double mu, int mi,
+                          double* __restrict__ z) {
+  const int i = blockIdx.x * blockDim.x + threadIdx.x;
+  if (i >= mi) return;
+  const double kappa = 1e10;
+  const double lo = 1.0 / kappa * mu / s[i];
+  const double hi = kappa * mu / s[i];
+  const double v = z[i];
+  z[i] = v < lo ? lo : (hi < v ? hi : v);  // std::clamp
+}
+
+__global__ void k_soc_begin(const double* __restrict__ c_e,
+                            const double* __restrict__ c_i,
+                            const double* __restrict__ s, int me, int mi,
+                            double* __restrict__ ce_soc,
+                            double* __restrict__ cis_soc) {
+  const int i = blockIdx.x * blockDim.x + threadIdx.x;
+  if (i < me) ce_soc[i] = c_e[i];
+  if (i < mi) cis_soc[i] = c_i[i] - s[i];
+}
+
+/// c_e^soc ← α c_e^soc + trial c_e ; cis^soc ← α cis^soc + trial c_i − trial s
+/// (interior_point.hpp:611-612)
+__global__ void k_soc_accumulate(const double* __restrict__ tce,
+                                 const double* __restrict__ tci,
+                                 const double* __restrict__ ts, double alpha,
+                                 int me, int mi, double* __restrict__ ce_soc,
+                                 double* __restrict__ cis_soc) {
+  const int i = blockIdx.x * blockDim.x + threadIdx.x;
+  if (i < me) ce_soc[i] = alpha * ce_soc[i] + tce[i];
+  if (i < mi) cis_soc[i] = alpha * cis_soc[i] + tci[i] - ts[i];
+}
+
+// ---------------------------------------------------------------------------
+// host-side launch helpers
+// ---------------------------------------------------------------------------
+
+inline int blocks_for(int64_t n, int threads) {
+  return static_cast<int>((n + threads - 1) / threads);
+}
+
+int upload_program_set(slpb_solver* S, const ProgramSet& ps,
+                       DevProgramSet& d) {
+  d.n_clusters = static_cast<int>(ps.cluster_prog.size());
+  CU(d.blob.upload(ps.blob, S->stream));
+  CU(d.bindings.upload(ps.bindings, S->stream));
+  CU(d.prog_offset.upload(ps.prog_offset, S->stream));
+  CU(d.cluster_bind.upload(ps.cluster_bind, S->stream));
+  CU(d.cluster_prog.upload(ps.cluster_prog, S->stream));
+  d.smem_per_warp = std::max(8, ps.max_smem);
+  if (d.smem_per_warp > 200 * 1024) {
+    return fail(S, SLPB_ERR_UNSUPPORTED,
+                "an expression cluster needs more than 200 KB of shared "
+                "memory; the global-memory fallback is not implemented");
+  }
+  d.warps_per_block =
+      std::max(1, std::min(8, (64 * 1024) / d.smem_per_warp));
+  return SLPB_OK;
+}
+
+int upload_gather(slpb_solver* S, const Gather& g, DevGather& d) {
+  d.n_entries = g.n_entries();
+  CU(d.ptr.upload(g.ptr, S->stream));
+  CU(d.src_idx.upload(g.src_idx, S->stream));
+  CU(d.src_scale.upload(g.src_scale, S->stream));
+  std::vector<int32_t> longs;
+  for (int e = 0; e < d.n_entries; ++e) {
+    if (g.ptr[e + 1] - g.ptr[e] > kLongGather) longs.push_back(e);
+  }
+  d.n_long = static_cast<int>(longs.size());
+  CU(d.long_entries.upload(longs, S->stream));
+  return SLPB_OK;
+}
+
+int run_sweep(slpb_solver* S, const DevProgramSet& d, const double* leaf,
+              double* stage) {
+  if (d.n_clusters == 0) return SLPB_OK;
+  const int wpb = d.warps_per_block;
+  const int smem = wpb * d.smem_per_warp;
+  k_ad_sweep<<<blocks_for(d.n_clusters, wpb), wpb * 32, smem, S->stream>>>(
+      d.blob.p, d.prog_offset.p, d.cluster_prog.p, d.cluster_bind.p,
+      d.bindings.p, d.n_clusters, d.smem_per_warp / 8, leaf, stage);
+  ++S->counters.kernel_launches;
+  CU(cudaGetLastError());
+  return SLPB_OK;
+}
+
+int run_gather(slpb_solver* S, const DevGather& d, const double* stage,
+               double* out) {
+  if (d.n_entries == 0) return SLPB_OK;
+  k_gather<<<blocks_for(d.n_entries, 256), 256, 0, S->stream>>>(
+      d.ptr.p, d.src_idx.p, d.src_scale.p, stage, S->d_f, S->d_c.p, out,
+      d.n_entries);
+  ++S->counters.kernel_launches;
+  if (d.n_long > 0) {
+    k_gather_long<<<d.n_long, 256, 0, S->stream>>>(
+        d.long_entries.p, d.ptr.p, d.src_idx.p, d.src_scale.p, stage, S->d_f,
+        S->d_c.p, out);
+    ++S->counters.kernel_launches;
+  }
+  CU(cudaGetLastError());
+  return SLPB_OK;
+}
+
+/// Copies `count` doubles of the device result buffer to the pinned mirror and
+/// waits for the stream.
+int fetch_results(slpb_solver* S, int count) {
+  CU(cudaMemcpyAsync(S->h_results, S->d_results.p, count * sizeof(double),
+                     cudaMemcpyDeviceToHost, S->stream));
+  CU(cudaStreamSynchronize(S->stream));
+  S->counters.d2h_bytes += count * sizeof(double);
+  return SLPB_OK;
+}
+
+CscView ae_view(slpb_solver* S) {
+  return {S->ae_colptr.p, S->ae_rowidx.p, S->dvals.p + S->ad.off_ae};
+}
+CscView ai_view(slpb_solver* S) {
+  return {S->ai_colptr.p, S->ai_rowidx.p, S->dvals.p + S->ad.off_ai};
+}
+
+/// Values (f, c_e, c_i) of the point whose leaves are in `leaf`.
+int eval_values(slpb_solver* S, const double* leaf, double* vals) {
+  CU(cudaEventRecord(S->ev[2], S->stream));
+  int rc = run_sweep(S, S->pv, leaf, S->vstage.p);
+  if (rc) return rc;
+  rc = run_gather(S, S->gv, S->vstage.p, vals);
+  if (rc) return rc;
+  CU(cudaEventRecord(S->ev[3], S->stream));
+  ++S->counters.evals_values;
+  return SLPB_OK;
+}
+
+int eval_derivs(slpb_solver* S, const double* leaf) {
+  CU(cudaEventRecord(S->ev[0], S->stream));
+  int rc = run_sweep(S, S->pd, leaf, S->dstage.p);
+  if (rc) return rc;
+  rc = run_gather(S, S->gd, S->dstage.p, S->dvals.p);
+  if (rc) return rc;
+  CU(cudaEventRecord(S->ev[1], S->stream));
+  ++S->counters.evals_full;
+  return SLPB_OK;
+}
+
+int refresh_leaves(slpb_solver* S, const double* x, const double* y,
+                   const double* z, double* leaf) {
+  const int tot = S->n + S->me + S->mi;
+  if (tot == 0) return SLPB_OK;
+  k_prepare_leaves<<<blocks_for(tot, 256), 256, 0, S->stream>>>(
+      x, y, z, S->d_c.p, S->n, S->me, S->mi, leaf);
+  ++S->counters.kernel_launches;
+  CU(cudaGetLastError());
+  return SLPB_OK;
+}
+
+int point_info(slpb_solver* S, const double* vals, const double* s,
+               double* d_out) {
+  k_point_info<<<1, kReduceThreads, 0, S->stream>>>(vals, s, S->me, S->mi,
+                                                    d_out);
+  ++S->counters.kernel_launches;
+  CU(cudaGetLastError());
+  return SLPB_OK;
+}
+
+void fill_point_info(const double* r, slpb_point_info* info) {
+  info->f = r[0];
+  info->ce_l1 = r[1];
+  info->cis_l1 = r[2];
+  info->log_s_sum = r[3];
+  info->finite = static_cast<int32_t>(r[4]);
+  info->ci_all_positive = static_cast<int32_t>(r[5]);
+}
+
+int kkt_stats(slpb_solver* S, const double* c_e, const double* c_i,
+              const double* x, const double* s, const double* y,
+              const double* z, double mu, slpb_kkt_stats* out) {
+  k_kkt_stats<<<1, kReduceThreads, 0, S->stream>>>(
+      ae_view(S), ai_view(S), S->dvals.p + S->ad.off_g, c_e, c_i, x, s, y, z,
+      S->d_c.p, S->d_f, mu, S->n, S->me, S->mi, S->d_results.p);
+  ++S->counters.kernel_launches;
+  CU(cudaGetLastError());
+  int rc = fetch_results(S, 25);
+  if (rc) return rc;
+  const double* r = S->h_results;
+  out->r_inf = r[0];
+  out->r_l1 = r[1];
+  out->y_l1 = r[2];
+  out->z_l1 = r[3];
+  out->sz_min = r[4];
+  out->sz_max = r[5];
+  out->sz_mu_l1 = r[6];
+  out->ce_inf = r[7];
+  out->ce_l1 = r[8];
+  out->cis_inf = r[9];
+  out->cis_l1 = r[10];
+  out->u_r_inf = r[11];
+  out->u_y_l1 = r[12];
+  out->u_z_l1 = r[13];
+  out->u_sz_min = r[14];
+  out->u_sz_max = r[15];
+  out->u_ce_inf = r[16];
+  out->u_cis_inf = r[17];
+  out->aetce_l2 = r[18];
+  out->ce_l2 = r[19];
+  out->aitcip_l2 = r[20];
+  out->cip_l2 = r[21];
+  out->x_inf = r[22];
+  out->s_inf = r[23];
+  out->xs_finite = static_cast<int32_t>(r[24]);
+  out->pad = 0;
+  return SLPB_OK;
+}
+
+int launch_solve(slpb_solver* S) {
+  const Symbolic& Y = S->sym;
+  const int smem = Y.max_front * static_cast<int>(sizeof(double));
+  CU(cudaEventRecord(S->ev[8], S->stream));
+  for (int L = 0; L < Y.n_levels; ++L) {
+    const int cnt = Y.level_ptr[L + 1] - Y.level_ptr[L];
+    k_forward_level<<<cnt, kFrontThreads, smem, S->stream>>>(
+        S->sview, S->sy_level_supers.p + Y.level_ptr[L], S->panels.p, S->rhs.p,
+        S->xperm.p, S->uvecs.p);
+  }
+  for (int L = Y.n_levels - 1; L >= 0; --L) {
+    const int cnt = Y.level_ptr[L + 1] - Y.level_ptr[L];
+    k_backward_level<<<cnt, kFrontThreads, smem, S->stream>>>(
+        S->sview, S->sy_level_supers.p + Y.level_ptr[L], S->panels.p, S->D.p,
+        S->xperm.p);
+  }
+  k_unpermute<<<blocks_for(S->dim, 256), 256, 0, S->stream>>>(
+      S->xperm.p, S->sy_perm.p, S->dim, S->sol.p);
+  S->counters.kernel_launches += 2 * Y.n_levels + 1;
+  CU(cudaEventRecord(S->ev[9], S->stream));
+  CU(cudaGetLastError());
+  ++S->counters.solves;
+  return SLPB_OK;
+}
+
+/// rhs → solve → step recovery → step stats, into the given step arrays.
+int solve_into(slpb_solver* S, double mu, double tau, const double* cis_soc,
+               const double* ce_for_rhs, double* px, double* ps, double* py,
+               double* pz, slpb_step_info* info) {
+  const int n = S->n, me = S->me, mi = S->mi;
+  if (mi > 0) {
+    k_sigma_t<<<blocks_for(mi, 256), 256, 0, S->stream>>>(
+        S->s.p, S->z.p, S->vals_cur.p + 1 + me, cis_soc, mu,
+        cis_soc ? 1 : 0, mi, S->sinv.p, S->sigma.p, S->tvec.p);
+    ++S->counters.kernel_launches;
+  }
+  k_rhs<<<blocks_for(S->dim, 256), 256, 0, S->stream>>>(
+      ae_view(S), ai_view(S), S->dvals.p + S->ad.off_g, S->y.p, S->tvec.p,
+      ce_for_rhs, n, me, S->rhs.p);
+  ++S->counters.kernel_launches;
+  int rc = launch_solve(S);
+  if (rc) return rc;
+  const int m = std::max(n, std::max(me, mi));
+  k_step_recover<<<blocks_for(m, 256), 256, 0, S->stream>>>(
+      S->sol.p, S->ai_rowptr.p, S->ai_rcol.p, S->ai_ridx.p,
+      S->dvals.p + S->ad.off_ai, S->vals_cur.p + 1 + me, S->s.p, S->z.p,
+      cis_soc, S->sinv.p, S->sigma.p, mu, n, me, mi, px, py, ps, pz);
+  k_step_stats<<<1, kReduceThreads, 0, S->stream>>>(
+      S->dvals.p + S->ad.off_g, S->s.p, S->z.p, S->sinv.p, px, ps, py, pz, tau,
+      n, me, mi, S->d_results.p);
+  S->counters.kernel_launches += 2;
+  CU(cudaGetLastError());
+  rc = fetch_results(S, 9);
+  if (rc) return rc;
+  const double* r = S->h_results;
+  info->alpha_max = r[0];
+  info->alpha_z = r[1];
+  info->g_dot_px = r[2];
+  info->sinv_dot_ps = r[3];
+  info->px_inf = r[4];
+  info->ps_inf = r[5];
+  info->py_inf = r[6];
+  info->pz_inf = r[7];
+  info->finite = static_cast<int32_t>(r[8]);
+  info->pad = 0;
+  return SLPB_OK;
+}
+
+}  // namespace slpb
+
+// ===========================================================================
+// C ABI
+// ===========================================================================
+
+extern "C" {
+
+int slpb_create(int device, slpb_solver** out) {
+  if (!out) return SLPB_ERR_ARGUMENT;
+  *out = nullptr;
+  int count = 0;
+  if (cudaGetDeviceCount(&count) != cudaSuccess || count == 0) {
+    return SLPB_ERR_NO_DEVICE;
+  }
+  if (device < 0 || device >= count) return SLPB_ERR_ARGUMENT;
+  if (cudaSetDevice(device) != cudaSuccess) return SLPB_ERR_CUDA;
+  auto S = std::make_unique<slpb_solver>();
+  S->device = device;
+  if (cudaStreamCreateWithFlags(&S->stream, cudaStreamNonBlocking) !=
+      cudaSuccess) {
+    return SLPB_ERR_CUDA;
+  }
+  if (cudaMallocHost(&S->h_results, kResultDoubles * sizeof(double)) !=
+      cudaSuccess) {
+    return SLPB_ERR_CUDA;
+  }
+  if (S->d_results.alloc(kResultDoubles) != cudaSuccess) return SLPB_ERR_CUDA;
+  for (auto& e : S->ev) {
+    if (cudaEventCreate(&e) != cudaSuccess) return SLPB_ERR_CUDA;
+  }
+  *out = S.release();
+  return SLPB_OK;
+}
+
+void slpb_destroy(slpb_solver* S) {
+  if (!S) return;
+  cudaSetDevice(S->device);
+  if (S->stream) cudaStreamSynchronize(S->stream);
+  for (auto& e : S->ev) {
+    if (e) cudaEventDestroy(e);
+  }
+  if (S->h_results) cudaFreeHost(S->h_results);
+  cudaStream_t st = S->stream;
+  delete S;
+  if (st) cudaStreamDestroy(st);
+}
+
+const char* slpb_last_error(const slpb_solver* S) {
+  return S ? S->error.c_str() : "null handle";
+}
+
+int slpb_upload_tape(slpb_solver* S, int32_t n_nodes, const uint8_t* op,
+                     const int32_t* lhs, const int32_t* rhs, const double* val,
+                     int32_t n_x, const int32_t* leaf_x, int32_t n_y,
+                     const int32_t* leaf_y, int32_t n_z,
+                     const int32_t* leaf_z) {
+  if (!S) return SLPB_ERR_ARGUMENT;
+  if (!ingest_tape(S->tape, n_nodes, op, lhs, rhs, val, n_x, leaf_x, n_y,
+                   leaf_y, n_z, leaf_z, S->error)) {
+    return SLPB_ERR_ARGUMENT;
+  }
+  S->n = n_x;
+  S->me = n_y;
+  S->mi = n_z;
+  S->dim = n_x + n_y;
+  S->have_tape = true;
+  S->finalized = S->analyzed = false;
+  for (auto& r : S->rows) r = RowSet{};
+  S->counters.tape_nodes = n_nodes;
+  S->counters.h2d_bytes += int64_t(n_nodes) * 17;
+  return SLPB_OK;
+}
+
+int slpb_upload_rows(slpb_solver* S, int which, const slpb_rowset* rows,
+                     const double* const_val) {
+  if (!S || which < 0 || which >= SLPB_OUT_COUNT) return SLPB_ERR_ARGUMENT;
+  if (!S->have_tape) {
+    return fail(S, SLPB_ERR_STATE, "slpb_upload_rows before slpb_upload_tape");
+  }
+  if (!ingest_rows(S->rows[which], S->tape, which, rows, const_val, S->error)) {
+    return SLPB_ERR_ARGUMENT;
+  }
+  return SLPB_OK;
+}
+
+int slpb_set_ignore_constraint_hessian(slpb_solver* S, int ignore) {
+  if (!S) return SLPB_ERR_ARGUMENT;
+  if (S->finalized) {
+    return fail(S, SLPB_ERR_STATE,
+                "slpb_set_ignore_constraint_hessian must precede slpb_finalize");
+  }
+  S->ignore_h_c = ignore != 0;
+  return SLPB_OK;
+}
+
+int slpb_finalize(slpb_solver* S) {
+  if (!S) return SLPB_ERR_ARGUMENT;
+  if (!S->have_tape) {
+    return fail(S, SLPB_ERR_STATE, "slpb_finalize before slpb_upload_tape");
+  }
+  CU(cudaSetDevice(S->device));
+  if (!compile_autodiff(S->tape, S->rows, S->ignore_h_c, S->ad)) {
+    S->error = S->ad.error;
+    return SLPB_ERR_UNSUPPORTED;
+  }
+  const int n = S->n, me = S->me, mi = S->mi;
+  int rc;
+  if ((rc = upload_program_set(S, S->ad.values, S->pv))) return rc;
+  if ((rc = upload_program_set(S, S->ad.derivs, S->pd))) return rc;
+  if ((rc = upload_gather(S, S->ad.value_gather, S->gv))) return rc;
+  if ((rc = upload_gather(S, S->ad.deriv_gather, S->gd))) return rc;
+  CU(S->vstage.upload(S->ad.value_stage_init, S->stream));
+  CU(S->dstage.upload(S->ad.deriv_stage_init, S->stream));
+  const int max_wpb_smem =
+      std::max(S->pv.warps_per_block * S->pv.smem_per_warp,
+               S->pd.warps_per_block * S->pd.smem_per_warp);
+  CU(cudaFuncSetAttribute(k_ad_sweep,
+                          cudaFuncAttributeMaxDynamicSharedMemorySize,
+                          std::max(max_wpb_smem, 48 * 1024)));
+
+  CU(S->leaf_cur.alloc(n + me + mi));
+  CU(S->leaf_trial.alloc(n + me + mi));
+  CU(S->leaf_cur.zero(S->stream));
+  CU(S->leaf_trial.zero(S->stream));
+  std::vector<double> ones(me + mi, 1.0);
+  CU(S->d_c.upload(ones, S->stream));
+  S->d_f = 1.0;
+  for (auto* b : {&S->x, &S->tx, &S->px, &S->spx}) CU(b->alloc(n));
+  for (auto* b : {&S->y, &S->ty, &S->py, &S->spy, &S->ce_soc}) CU(b->alloc(me));
+  for (auto* b : {&S->s, &S->z, &S->ts, &S->tz, &S->ps, &S->pz, &S->sps,
+                  &S->spz, &S->cis_soc, &S->sigma, &S->sinv, &S->tvec}) {
+    CU(b->alloc(mi));
+  }
+  CU(S->vals_cur.alloc(1 + me + mi));
+  CU(S->vals_trial.alloc(1 + me + mi));
+  CU(S->vals_cur.zero(S->stream));
+  CU(S->vals_trial.zero(S->stream));
+  CU(S->dvals.alloc(S->ad.off_h + S->ad.H.nnz()));
+  CU(S->dvals.zero(S->stream));
+  CU(S->ae_colptr.upload(S->ad.A_e.colptr, S->stream));
+  CU(S->ae_rowidx.upload(S->ad.A_e.rowidx, S->stream));
+  CU(S->ai_colptr.upload(S->ad.A_i.colptr, S->stream));
+  CU(S->ai_rowidx.upload(S->ad.A_i.rowidx, S->stream));
+  {
+    const Pattern& A = S->ad.A_i;
+    std::vector<int32_t> rptr(mi + 1, 0), rcol(A.nnz()), ridx(A.nnz());
+    for (int32_t r : A.rowidx) ++rptr[r + 1];
+    for (int i = 0; i < mi; ++i) rptr[i + 1] += rptr[i];
+    std::vector<int32_t> nxt(rptr.begin(), rptr.end() - 1);
+    for (int32_t c = 0; c < A.cols; ++c) {
+      for (int32_t k = A.colptr[c]; k < A.colptr[c + 1]; ++k) {
+        const int32_t q = nxt[A.rowidx[k]]++;
+        rcol[q] = c;
+        ridx[q] = k;
+      }
+    }
+    CU(S->ai_rowptr.upload(rptr, S->stream));
+    CU(S->ai_rcol.upload(rcol, S->stream));
+    CU(S->ai_ridx.upload(ridx, S->stream));
+  }
+  // KKT recipe
+  build_kkt_recipe(n, me, S->ad.H, S->ad.A_e, S->ad.A_i, S->recipe);
+  CU(S->k_h_idx.upload(S->recipe.h_idx, S->stream));
+  CU(S->k_ae_idx.upload(S->recipe.ae_idx, S->stream));
+  CU(S->k_prod_ptr.upload(S->recipe.prod_ptr, S->stream));
+  CU(S->k_prod_a.upload(S->recipe.prod_a, S->stream));
+  CU(S->k_prod_b.upload(S->recipe.prod_b, S->stream));
+  CU(S->k_prod_row.upload(S->recipe.prod_row, S->stream));
+  CU(S->Kval.alloc(S->recipe.K.nnz()));
+  CU(S->rhs.alloc(S->dim));
+  CU(S->sol.alloc(S->dim));
+  CU(cudaStreamSynchronize(S->stream));
+  S->counters.program_bytes =
+      int64_t(S->ad.values.blob.size() + S->ad.derivs.blob.size() +
+              S->ad.values.bindings.size() + S->ad.derivs.bindings.size()) * 4;
+  S->counters.n_clusters = int64_t(S->ad.values.cluster_prog.size() +
+                                   S->ad.derivs.cluster_prog.size());
+  S->counters.n_program_classes = int64_t(S->ad.values.prog_offset.size() +
+                                          S->ad.derivs.prog_offset.size());
+  S->counters.h2d_bytes += S->counters.program_bytes;
+  S->finalized = true;
+  S->analyzed = false;
+  return SLPB_OK;
+}
+
+int slpb_set_scaling(slpb_solver* S, double d_f, const double* d_ce,
+                     const double* d_ci) {
+  if (!S || !S->finalized) return SLPB_ERR_STATE;
+  if ((S->me > 0 && !d_ce) || (S->mi > 0 && !d_ci)) return SLPB_ERR_ARGUMENT;
+  CU(cudaSetDevice(S->device));
+  S->d_f = d_f;
+  std::vector<double> d(S->me + S->mi);
+  std::copy(d_ce, d_ce + S->me, d.begin());
+  std::copy(d_ci, d_ci + S->mi, d.begin() + S->me);
+  if (!d.empty()) {
+    CU(cudaMemcpyAsync(S->d_c.p, d.data(), d.size() * sizeof(double),
+                       cudaMemcpyHostToDevice, S->stream));
+    CU(cudaStreamSynchronize(S->stream));
+  }
+  return SLPB_OK;
+}
+
+int slpb_analyze(slpb_solver* S, int ordering, const int32_t* perm,
+                 slpb_symbolic_stats* stats) {
+  if (!S || !S->finalized) return SLPB_ERR_STATE;
+  CU(cudaSetDevice(S->device));
+  if (!analyze_kkt(S->recipe.K, S->n, ordering, perm, S->sym, S->error)) {
+    return SLPB_ERR_ARGUMENT;
+  }
+  const Symbolic& Y = S->sym;
+  const size_t front_smem =
+      (size_t(Y.max_front) * Y.max_front + Y.max_front) * sizeof(double);
+  if (front_smem > 200 * 1024) {
+    return fail(S, SLPB_ERR_UNSUPPORTED,
+                "a frontal matrix exceeds 200 KB of shared memory (front order " +
+                    std::to_string(Y.max_front) + ")");
+  }
+  CU(cudaFuncSetAttribute(k_factor_level,
+                          cudaFuncAttributeMaxDynamicSharedMemorySize,
+                          std::max<int>(front_smem, 48 * 1024)));
+  CU(S->sy_super_first.upload(Y.super_first, S->stream));
+  CU(S->sy_front_dim.upload(Y.front_dim, S->stream));
+  CU(S->sy_rows_ptr.upload(Y.rows_ptr, S->stream));
+  CU(S->sy_rows_idx.upload(Y.rows_idx, S->stream));
+  CU(S->sy_panel_ptr.upload(Y.panel_ptr, S->stream));
+  CU(S->sy_update_ptr.upload(Y.update_ptr, S->stream));
+  CU(S->sy_child_ptr.upload(Y.child_ptr, S->stream));
+  CU(S->sy_child_idx.upload(Y.child_idx, S->stream));
+  CU(S->sy_rel_ptr.upload(Y.rel_ptr, S->stream));
+  CU(S->sy_rel_idx.upload(Y.rel_idx, S->stream));
+  CU(S->sy_asm_ptr.upload(Y.asm_ptr, S->stream));
+  CU(S->sy_asm_src.upload(Y.asm_src, S->stream));
+  CU(S->sy_asm_dst.upload(Y.asm_dst, S->stream));
+  CU(S->sy_col_is_primal.upload(Y.col_is_primal, S->stream));
+  CU(S->sy_perm.upload(Y.perm, S->stream));
+  CU(S->sy_level_supers.upload(Y.level_supers, S->stream));
+  CU(S->panels.alloc(Y.panel_size));
+  CU(S->updates.alloc(Y.update_size));
+  CU(S->D.alloc(Y.dim));
+  CU(S->uvecs.alloc(Y.rel_ptr.back()));
+  CU(S->xperm.alloc(Y.dim));
+  CU(S->fstats.alloc(8));
+  CU(cudaStreamSynchronize(S->stream));
+  SymbolicView& V = S->sview;
+  V.dim = Y.dim;
+  V.n_super = Y.n_super;
+  V.super_first = S->sy_super_first.p;
+  V.front_dim = S->sy_front_dim.p;
+  V.rows_ptr = S->sy_rows_ptr.p;
+  V.rows_idx = S->sy_rows_idx.p;
+  V.panel_ptr = S->sy_panel_ptr.p;
+  V.update_ptr = S->sy_update_ptr.p;
+  V.child_ptr = S->sy_child_ptr.p;
+  V.child_idx = S->sy_child_idx.p;
+  V.rel_ptr = S->sy_rel_ptr.p;
+  V.rel_idx = S->sy_rel_idx.p;
+  V.asm_ptr = S->sy_asm_ptr.p;
+  V.asm_src = S->sy_asm_src.p;
+  V.asm_dst = S->sy_asm_dst.p;
+  V.col_is_primal = S->sy_col_is_primal.p;
+  V.perm = S->sy_perm.p;
+  S->analyzed = true;
+  if (stats) {
+    stats->dim = Y.dim;
+    stats->nnz_kkt = S->recipe.K.nnz();
+    stats->nnz_l = Y.nnz_l;
+    stats->nnz_l_stored = Y.panel_size;
+    stats->n_supernodes = Y.n_super;
+    stats->n_levels = Y.n_levels;
+    stats->max_front = Y.max_front;
+    stats->etree_height = Y.etree_height;
+  }
+  return SLPB_OK;
+}
+
+int slpb_get_permutation(const slpb_solver* S, int32_t* perm) {
+  if (!S || !S->analyzed || !perm) return SLPB_ERR_STATE;
+  std::memcpy(perm, S->sym.perm.data(), S->sym.dim * sizeof(int32_t));
+  return SLPB_OK;
+}
+
+int slpb_set_iterate(slpb_solver* S, const double* x, const double* sl,
+                     const double* y, const double* z) {
+  if (!S || !S->finalized) return SLPB_ERR_STATE;
+  CU(cudaSetDevice(S->device));
+  auto put = [&](DevBuf<double>& b, const double* src) -> cudaError_t {
+    if (b.n == 0) return cudaSuccess;
+    if (!src) return cudaErrorInvalidValue;
+    S->counters.h2d_bytes += b.n * sizeof(double);
+    return cudaMemcpyAsync(b.p, src, b.n * sizeof(double),
+                           cudaMemcpyHostToDevice, S->stream);
+  };
+  CU(put(S->x, x));
+  CU(put(S->s, sl));
+  CU(put(S->y, y));
+  CU(put(S->z, z));
+  CU(cudaStreamSynchronize(S->stream));
+  return SLPB_OK;
+}
+
+int slpb_get_iterate(slpb_solver* S, double* x, double* sl, double* y,
+                     double* z) {
+  if (!S || !S->finalized) return SLPB_ERR_STATE;
+  CU(cudaSetDevice(S->device));
+  auto get = [&](DevBuf<double>& b, double* dst) -> cudaError_t {
+    if (b.n == 0 || !dst) return cudaSuccess;
+    S->counters.d2h_bytes += b.n * sizeof(double);
+    return cudaMemcpyAsync(dst, b.p, b.n * sizeof(double),
+                           cudaMemcpyDeviceToHost, S->stream);
+  };
+  CU(get(S->x, x));
+  CU(get(S->s, sl));
+  CU(get(S->y, y));
+  CU(get(S->z, z));
+  CU(cudaStreamSynchronize(S->stream));
+  return SLPB_OK;
+}
+
+int slpb_eval_current(slpb_solver* S, int derivatives,
+                      slpb_point_info* info) {
+  if (!S || !S->finalized || !info) return SLPB_ERR_STATE;
+  CU(cudaSetDevice(S->device));
+  int rc;
+  if ((rc = refresh_leaves(S, S->x.p, S->y.p, S->z.p, S->leaf_cur.p))) return rc;
+  if (derivatives != 2) {
+    if ((rc = eval_values(S, S->leaf_cur.p, S->vals_cur.p))) return rc;
+  }
+  if ((rc = point_info(S, S->vals_cur.p, S->s.p, S->d_results.p))) return rc;
+  int nres = 6;
+  if (derivatives != 0) {
+    if ((rc = eval_derivs(S, S->leaf_cur.p))) return rc;
+    k_deriv_finite<<<1, kReduceThreads, 0, S->stream>>>(
+        S->dvals.p, S->ad.off_ae, S->ad.off_ai, S->ad.off_h,
+        S->ad.off_h + S->ad.H.nnz(), S->d_results.p + 6);
+    ++S->counters.kernel_launches;
+    nres = 7;
+  }
+  if ((rc = fetch_results(S, nres))) return rc;
+  fill_point_info(S->h_results, info);
+  if (derivatives != 0) info->finite |= static_cast<int32_t>(S->h_results[6]);
+  return SLPB_OK;
+}
+
+int slpb_kkt_stats_current(slpb_solver* S, double mu, slpb_kkt_stats* out) {
+  if (!S || !S->finalized || !out) return SLPB_ERR_STATE;
+  CU(cudaSetDevice(S->device));
+  return kkt_stats(S, S->vals_cur.p + 1, S->vals_cur.p + 1 + S->me, S->x.p,
+                   S->s.p, S->y.p, S->z.p, mu, out);
+}
+
+int slpb_kkt_stats_trial(slpb_solver* S, double mu, slpb_kkt_stats* out) {
+  if (!S || !S->finalized || !out) return SLPB_ERR_STATE;
+  CU(cudaSetDevice(S->device));
+  // g, A_e, A_i at the trial point (interior_point.hpp:704-706). This
+  // overwrites the derivative arrays; the driver re-linearises afterwards.
+  int rc;
+  if ((rc = refresh_leaves(S, S->tx.p, S->ty.p, S->tz.p, S->leaf_trial.p))) {
+    return rc;
+  }
+  if ((rc = eval_derivs(S, S->leaf_trial.p))) return rc;
+  return kkt_stats(S, S->vals_trial.p + 1, S->vals_trial.p + 1 + S->me,
+                   S->tx.p, S->ts.p, S->ty.p, S->tz.p, mu, out);
+}
+
+int slpb_factor(slpb_solver* S, double delta, double gamma, int reassemble,
+                slpb_factor_info* info) {
+  if (!S || !S->analyzed || !info) return SLPB_ERR_STATE;
+  CU(cudaSetDevice(S->device));
+  const Symbolic& Y = S->sym;
+  if (reassemble) {
+    CU(cudaEventRecord(S->ev[4], S->stream));
+    if (S->mi > 0) {
+      k_sigma_t<<<blocks_for(S->mi, 256), 256, 0, S->stream>>>(
+          S->s.p, S->z.p, S->vals_cur.p + 1 + S->me, nullptr, 0.0, 0, S->mi,
+          S->sinv.p, S->sigma.p, S->tvec.p);
+      ++S->counters.kernel_launches;
+    }
+    const int nnz = static_cast<int>(S->recipe.K.nnz());
+    k_kkt_assemble<<<blocks_for(nnz, 256), 256, 0, S->stream>>>(
+        S->k_h_idx.p, S->k_ae_idx.p, S->k_prod_ptr.p, S->k_prod_a.p,
+        S->k_prod_b.p, S->k_prod_row.p, S->dvals.p + S->ad.off_h,
+        S->dvals.p + S->ad.off_ae, S->dvals.p + S->ad.off_ai, S->sigma.p, nnz,
+        S->Kval.p);
+    ++S->counters.kernel_launches;
+    CU(cudaEventRecord(S->ev[5], S->stream));
+  }
+  CU(cudaEventRecord(S->ev[6], S->stream));
+  // stats: n_pos n_neg n_zero zero_pivot | min|D| bits (+inf)
+  {
+    int32_t init[8] = {0, 0, 0, 0, 0, 0, 0, 0};
+    const double inf = INFINITY;
+    std::memcpy(&init[4], &inf, 8);
+    CU(cudaMemcpyAsync(S->fstats.p, init, sizeof(init), cudaMemcpyHostToDevice,
+                       S->stream));
+  }
+  const int smem = static_cast<int>(
+      (size_t(Y.max_front) * Y.max_front + Y.max_front) * sizeof(double));
+  for (int L = 0; L < Y.n_levels; ++L) {
+    const int cnt = Y.level_ptr[L + 1] - Y.level_ptr[L];
+    k_factor_level<<<cnt, kFrontThreads, smem, S->stream>>>(
+        S->sview, S->sy_level_supers.p + Y.level_ptr[L], S->Kval.p, delta,
+        gamma, S->panels.p, S->updates.p, S->D.p, S->fstats.p);
+  }
+  S->counters.kernel_launches += Y.n_levels;
+  CU(cudaEventRecord(S->ev[7], S->stream));
+  CU(cudaGetLastError());
+  int32_t host_stats[8];
+  CU(cudaMemcpyAsync(host_stats, S->fstats.p, sizeof(host_stats),
+                     cudaMemcpyDeviceToHost, S->stream));
+  CU(cudaStreamSynchronize(S->stream));
+  S->counters.d2h_bytes += sizeof(host_stats);
+  info->n_pos = host_stats[0];
+  info->n_neg = host_stats[1];
+  info->n_zero = host_stats[2];
+  info->zero_pivot = host_stats[3];
+  std::memcpy(&info->min_abs_d, &host_stats[4], 8);
+  ++S->counters.factorizations;
+  return SLPB_OK;
+}
+
+int slpb_solve(slpb_solver* S, double mu, double tau, slpb_step_info* info) {
+  if (!S || !S->analyzed || !info) return SLPB_ERR_STATE;
+  CU(cudaSetDevice(S->device));
+  return solve_into(S, mu, tau, nullptr, S->vals_cur.p + 1, S->px.p, S->ps.p,
+                    S->py.p, S->pz.p, info);
+}
+
+int slpb_soc_begin(slpb_solver* S) {
+  if (!S || !S->analyzed) return SLPB_ERR_STATE;
+  CU(cudaSetDevice(S->device));
+  const int m = std::max(S->me, S->mi);
+  if (m > 0) {
+    k_soc_begin<<<blocks_for(m, 256), 256, 0, S->stream>>>(
+        S->vals_cur.p + 1, S->vals_cur.p + 1 + S->me, S->s.p, S->me, S->mi,
+        S->ce_soc.p, S->cis_soc.p);
+    ++S->counters.kernel_launches;
+  }
+  CU(cudaGetLastError());
+  return SLPB_OK;
+}
+
+int slpb_soc_iterate(slpb_solver* S, double mu, double tau, double alpha_soc,
+                     slpb_step_info* info) {
+  if (!S || !S->analyzed || !info) return SLPB_ERR_STATE;
+  CU(cudaSetDevice(S->device));
+  const int m = std::max(S->me, S->mi);
+  if (m > 0) {
+    k_soc_accumulate<<<blocks_for(m, 256), 256, 0, S->stream>>>(
+        S->vals_trial.p + 1, S->vals_trial.p + 1 + S->me, S->ts.p, alpha_soc,
+        S->me, S->mi, S->ce_soc.p, S->cis_soc.p);
+    ++S->counters.kernel_launches;
+  }
+  return solve_into(S, mu, tau, S->cis_soc.p, S->ce_soc.p, S->spx.p, S->sps.p,
+                    S->spy.p, S->spz.p, info);
+}
+
+int slpb_trial(slpb_solver* S, double alpha, double alpha_z, int which_step,
+               int slack_from_ci, slpb_point_info* info) {
+  if (!S || !S->analyzed || !info) return SLPB_ERR_STATE;
+  CU(cudaSetDevice(S->device));
+  const int n = S->n, me = S->me, mi = S->mi;
+  const bool soc = which_step != 0;
+  const int m = std::max(n, std::max(me, mi));
+  k_trial_point<<<blocks_for(m, 256), 256, 0, S->stream>>>(
+      S->x.p, S->s.p, S->y.p, S->z.p, soc ? S->spx.p : S->px.p,
+      soc ? S->sps.p : S->ps.p, soc ? S->spy.p : S->py.p,
+      soc ? S->spz.p : S->pz.p, alpha, alpha_z, n, me, mi, S->tx.p, S->ts.p,
+      S->ty.p, S->tz.p, S->leaf_trial.p);
+  ++S->counters.kernel_launches;
+  int rc;
+  if ((rc = eval_values(S, S->leaf_trial.p, S->vals_trial.p))) return rc;
+  if (slack_from_ci && mi > 0) {
+    k_copy<<<blocks_for(mi, 256), 256, 0, S->stream>>>(
+        S->vals_trial.p + 1 + me, S->ts.p, mi);
+    ++S->counters.kernel_launches;
+  }
+  if ((rc = point_info(S, S->vals_trial.p, S->ts.p, S->d_results.p))) return rc;
+  if ((rc = fetch_results(S, 6))) return rc;
+  fill_point_info(S->h_results, info);
+  return SLPB_OK;
+}
+
+int slpb_accept(slpb_solver* S, double mu) {
+  if (!S || !S->analyzed) return SLPB_ERR_STATE;
+  CU(cudaSetDevice(S->device));
+  auto cp = [&](DevBuf<double>& dst, DevBuf<double>& src) -> cudaError_t {
+    if (dst.n == 0) return cudaSuccess;
+    return cudaMemcpyAsync(dst.p, src.p, dst.n * sizeof(double),
+                           cudaMemcpyDeviceToDevice, S->stream);
+  };
+  CU(cp(S->x, S->tx));
+  CU(cp(S->s, S->ts));
+  CU(cp(S->y, S->ty));
+  CU(cp(S->z, S->tz));
+  CU(cp(S->vals_cur, S->vals_trial));
+  if (S->mi > 0) {
+    k_clamp_z<<<blocks_for(S->mi, 256), 256, 0, S->stream>>>(S->s.p, mu, S->mi,
+                                                            S->z.p);
+    ++S->counters.kernel_launches;
+  }
+  CU(cudaGetLastError());
+  return SLPB_OK;
+}
+
+int slpb_array_size(const slpb_solver* S, int which, int64_t* count) {
+  if (!S || !S->finalized || !count) return SLPB_ERR_STATE;
+  switch (which) {
+    case SLPB_ARR_X: case SLPB_ARR_G: case SLPB_ARR_P_X: case SLPB_ARR_TRIAL_X:
+      *count = S->n;
+      break;
+    case SLPB_ARR_S: case SLPB_ARR_Z: case SLPB_ARR_C_I: case SLPB_ARR_P_S:
+    case SLPB_ARR_P_Z: case SLPB_ARR_TRIAL_S: case SLPB_ARR_TRIAL_Z:
+    case SLPB_ARR_TRIAL_C_I:
+      *count = S->mi;
+      break;
+    case SLPB_ARR_Y: case SLPB_ARR_C_E: case SLPB_ARR_P_Y:
+    case SLPB_ARR_TRIAL_Y: case SLPB_ARR_TRIAL_C_E:
+      *count = S->me;
+      break;
+    case SLPB_ARR_A_E_VAL: *count = S->ad.A_e.nnz(); break;
+    case SLPB_ARR_A_I_VAL: *count = S->ad.A_i.nnz(); break;
+    case SLPB_ARR_H_VAL: *count = S->ad.H.nnz(); break;
+    case SLPB_ARR_KKT_VAL: *count = S->recipe.K.nnz(); break;
+    case SLPB_ARR_D: case SLPB_ARR_RHS: *count = S->dim; break;
+    default: return SLPB_ERR_ARGUMENT;
+  }
+  return SLPB_OK;
+}
+
+int slpb_download(slpb_solver* S, int which, double* dst) {
+  if (!S || !S->finalized || !dst) return SLPB_ERR_STATE;
+  CU(cudaSetDevice(S->device));
+  int64_t count = 0;
+  int rc = slpb_array_size(S, which, &count);
+  if (rc) return rc;
+  const double* src = nullptr;
+  const int me = S->me;
+  switch (which) {
+    case SLPB_ARR_X: src = S->x.p; break;
+    case SLPB_ARR_S: src = S->s.p; break;
+    case SLPB_ARR_Y: src = S->y.p; break;
+    case SLPB_ARR_Z: src = S->z.p; break;
+    case SLPB_ARR_G: src = S->dvals.p + S->ad.off_g; break;
+    case SLPB_ARR_C_E: src = S->vals_cur.p + 1; break;
+    case SLPB_ARR_C_I: src = S->vals_cur.p + 1 + me; break;
+    case SLPB_ARR_A_E_VAL: src = S->dvals.p + S->ad.off_ae; break;
+    case SLPB_ARR_A_I_VAL: src = S->dvals.p + S->ad.off_ai; break;
+    case SLPB_ARR_H_VAL: src = S->dvals.p + S->ad.off_h; break;
+    case SLPB_ARR_KKT_VAL: src = S->Kval.p; break;
+    case SLPB_ARR_D: src = S->D.p; break;
+    case SLPB_ARR_RHS: src = S->rhs.p; break;
+    case SLPB_ARR_P_X: src = S->px.p; break;
+    case SLPB_ARR_P_S: src = S->ps.p; break;
+    case SLPB_ARR_P_Y: src = S->py.p; break;
+    case SLPB_ARR_P_Z: src = S->pz.p; break;
+    case SLPB_ARR_TRIAL_X: src = S->tx.p; break;
+    case SLPB_ARR_TRIAL_S: src = S->ts.p; break;
+    case SLPB_ARR_TRIAL_Y: src = S->ty.p; break;
+    case SLPB_ARR_TRIAL_Z: src = S->tz.p; break;
+    case SLPB_ARR_TRIAL_C_E: src = S->vals_trial.p + 1; break;
+    case SLPB_ARR_TRIAL_C_I: src = S->vals_trial.p + 1 + me; break;
+    default: return SLPB_ERR_ARGUMENT;
+  }
+  if (count > 0) {
+    if (!src) return fail(S, SLPB_ERR_STATE, "array not available yet");
+    CU(cudaMemcpyAsync(dst, src, count * sizeof(double),
+                       cudaMemcpyDeviceToHost, S->stream));
+    CU(cudaStreamSynchronize(S->stream));
+    S->counters.d2h_bytes += count * sizeof(double);
+  }
+  return SLPB_OK;
+}
+
+int slpb_pattern(const slpb_solver* S, int which, int32_t* rows, int32_t* cols,
+                 int64_t* nnz, int32_t* colptr, int32_t* rowidx) {
+  if (!S || !S->finalized) return SLPB_ERR_STATE;
+  const Pattern* p = nullptr;
+  switch (which) {
+    case SLPB_OUT_A_E: p = &S->ad.A_e; break;
+    case SLPB_OUT_A_I: p = &S->ad.A_i; break;
+    case SLPB_OUT_H_C: case SLPB_OUT_H_F: p = &S->ad.H; break;
+    case -1: p = &S->recipe.K; break;
+    default: return SLPB_ERR_ARGUMENT;
+  }
+  if (rows) *rows = p->rows;
+  if (cols) *cols = p->cols;
+  if (nnz) *nnz = p->nnz();
+  if (colptr) {
+    std::memcpy(colptr, p->colptr.data(), p->colptr.size() * sizeof(int32_t));
+  }
+  if (rowidx && p->nnz() > 0) {
+    std::memcpy(rowidx, p->rowidx.data(), p->nnz() * sizeof(int32_t));
+  }
+  return SLPB_OK;
+}
+
+int slpb_get_counters(const slpb_solver* S, slpb_counters* out) {
+  if (!S || !out) return SLPB_ERR_ARGUMENT;
+  *out = S->counters;
+  return SLPB_OK;
+}
+
+int slpb_last_device_ms(slpb_solver* S, int which, float* ms) {
+  if (!S || !ms || which < 0 || which > 4) return SLPB_ERR_ARGUMENT;
+  CU(cudaSetDevice(S->device));
+  CU(cudaStreamSynchronize(S->stream));
+  *ms = 0.0f;
+  const int a = 2 * which, b = 2 * which + 1;
+  if (cudaEventQuery(S->ev[a]) == cudaSuccess &&
+      cudaEventQuery(S->ev[b]) == cudaSuccess) {
+    if (cudaEventElapsedTime(ms, S->ev[a], S->ev[b]) != cudaSuccess) {
+      *ms = 0.0f;
+      cudaGetLastError();
+    }
+  }
+  return SLPB_OK;
+}
+
+void* slpb_stream(slpb_solver* S) { return S ? S->stream : nullptr; }
+
+}  // extern "C"

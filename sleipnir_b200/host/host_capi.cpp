@@ -1,0 +1,177 @@
+// libslpb_host.so — C API over the host side (slp::Problem DSL + IPM driver +
+// the benchmark/parity problem builders) so that Python (tests/, bench.py,
+// __graft_entry__.py) can drive it with ctypes. The host side is C++ because
+// the reference's is; everything numerical below it goes through the C ABI of
+// include/slpb.h into the CUDA library.
+#include <cstring>
+#include <memory>
+#include <string>
+#include <vector>
+
+#include "problems/problems.hpp"
+
+namespace {
+
+struct Handle {
+  std::unique_ptr<slp::Problem<double>> problem;
+  std::unique_ptr<slp::Problem<double>::Graphs> graphs;
+  std::unique_ptr<slp::DeviceHandle> device;
+  std::string error;
+  std::vector<double> x;
+  int last_status = 0;
+};
+
+Handle* H(void* h) { return static_cast<Handle*>(h); }
+
+}  // namespace
+
+extern "C" {
+
+void* slpbh_problem_create(const char* name, int N, double p0, double p1) {
+  try {
+    auto h = std::make_unique<Handle>();
+    h->problem = slpb_problems::make_problem(name, N, p0, p1);
+    return h.release();
+  } catch (...) {
+    return nullptr;
+  }
+}
+
+void slpbh_problem_destroy(void* h) { delete H(h); }
+
+const char* slpbh_error(void* h) { return H(h)->error.c_str(); }
+
+void slpbh_dims(void* h, int* n, int* me, int* mi) {
+  *n = static_cast<int>(H(h)->problem->decision_variables().size());
+  *me = static_cast<int>(H(h)->problem->equality_constraints().size());
+  *mi = static_cast<int>(H(h)->problem->inequality_constraints().size());
+}
+
+void slpbh_types(void* h, int* f, int* ce, int* ci) {
+  *f = static_cast<int>(H(h)->problem->cost_function_type());
+  *ce = static_cast<int>(H(h)->problem->equality_constraint_type());
+  *ci = static_cast<int>(H(h)->problem->inequality_constraint_type());
+}
+
+void slpbh_initial_guess(void* h, double* x) {
+  auto& vars = H(h)->problem->decision_variables();
+  for (size_t i = 0; i < vars.size(); ++i) x[i] = vars[i].value();
+}
+
+void slpbh_set_guess(void* h, const double* x) {
+  auto& vars = H(h)->problem->decision_variables();
+  for (size_t i = 0; i < vars.size(); ++i) vars[i].set_value(x[i]);
+}
+
+/// Problem::solve. Returns the ExitStatus value, or −100 when the device
+/// library failed (slpbh_error has the text).
+int slpbh_solve(void* h, double tolerance, int max_iterations, int feasible_ipm,
+                int device, int ordering, const int* perm, int keep_iterates) {
+  Handle* hd = H(h);
+  slp::Options opt;
+  opt.tolerance = tolerance;
+  opt.max_iterations = max_iterations;
+  opt.feasible_ipm = feasible_ipm != 0;
+  slp::DeviceOptions dopt;
+  dopt.device = device;
+  dopt.ordering = ordering;
+  dopt.keep_iterates = keep_iterates != 0;
+  if (perm) {
+    const size_t dim = hd->problem->decision_variables().size() +
+                       hd->problem->equality_constraints().size();
+    dopt.permutation.assign(perm, perm + dim);
+  }
+  try {
+    hd->last_status = static_cast<int>(hd->problem->solve(opt, dopt));
+  } catch (const std::exception& e) {
+    hd->error = e.what();
+    return -100;
+  }
+  return hd->last_status;
+}
+
+int slpbh_trace_rows(void* h) {
+  return static_cast<int>(H(h)->problem->last_trace().rows.size());
+}
+
+/// scalars[16]: same layout as the oracle's orc_trace_get.
+void slpbh_trace_get(void* h, int row, double* scalars, double* x, double* s,
+                     double* y, double* z) {
+  const auto& r = H(h)->problem->last_trace().rows[row];
+  double sc[16] = {double(r.iteration), double(r.type), r.error, r.cost,
+                   r.infeasibility, r.complementarity, r.mu, r.delta, r.gamma,
+                   r.alpha, r.alpha_max, r.alpha_z, double(r.factorizations),
+                   double(r.solves), double(r.trials), 0.0};
+  std::memcpy(scalars, sc, sizeof(sc));
+  auto cp = [](double* dst, const std::vector<double>& v) {
+    if (dst && !v.empty()) std::memcpy(dst, v.data(), v.size() * 8);
+  };
+  cp(x, r.x);
+  cp(s, r.s);
+  cp(y, r.y);
+  cp(z, r.z);
+}
+
+void slpbh_solution(void* h, double* x, double* s, double* y, double* z) {
+  Handle* hd = H(h);
+  auto& vars = hd->problem->decision_variables();
+  if (x) {
+    for (size_t i = 0; i < vars.size(); ++i) x[i] = vars[i].value();
+  }
+  auto cp = [](double* dst, const std::vector<double>& v) {
+    if (dst && !v.empty()) std::memcpy(dst, v.data(), v.size() * 8);
+  };
+  cp(s, hd->problem->last_s());
+  cp(y, hd->problem->last_y());
+  cp(z, hd->problem->last_z());
+}
+
+double slpbh_loop_seconds(void* h) {
+  return H(h)->problem->last_trace().loop_seconds;
+}
+
+/// out[8]: dim, nnz_kkt, nnz_l, nnz_l_stored, n_supernodes, n_levels,
+/// max_front, etree_height
+void slpbh_symbolic_stats(void* h, int64_t* out) {
+  const auto& s = H(h)->problem->last_symbolic_stats();
+  out[0] = s.dim;
+  out[1] = s.nnz_kkt;
+  out[2] = s.nnz_l;
+  out[3] = s.nnz_l_stored;
+  out[4] = s.n_supernodes;
+  out[5] = s.n_levels;
+  out[6] = s.max_front;
+  out[7] = s.etree_height;
+}
+
+/// out[11]: the fields of slpb_counters in declaration order.
+void slpbh_counters(void* h, int64_t* out) {
+  const auto& c = H(h)->problem->last_counters();
+  const int64_t v[11] = {c.kernel_launches, c.factorizations, c.solves,
+                         c.evals_full, c.evals_values, c.tape_nodes,
+                         c.program_bytes, c.n_clusters, c.n_program_classes,
+                         c.h2d_bytes, c.d2h_bytes};
+  std::memcpy(out, v, sizeof(v));
+}
+
+/// Builds the autodiff graphs, opens a device handle, uploads and finalises.
+/// Returns the raw slpb_solver* (owned by this handle) so a test can drive the
+/// C ABI of include/slpb.h directly, or NULL on failure.
+void* slpbh_device_open(void* h, int device) {
+  Handle* hd = H(h);
+  try {
+    hd->graphs = hd->problem->build_graphs();
+    slp::detail::FlatProblem fp = hd->graphs->flatten();
+    hd->device = std::make_unique<slp::DeviceHandle>(device);
+    slp::Problem<double>::upload(hd->device->s, fp);
+    return hd->device->s;
+  } catch (const std::exception& e) {
+    hd->error = e.what();
+    hd->device.reset();
+    return nullptr;
+  }
+}
+
+void slpbh_device_close(void* h) { H(h)->device.reset(); }
+
+}  // extern "C"

@@ -17,6 +17,8 @@
 
 #include "ad_core.hpp"
 #include "internal.hpp"
+#include "kkt_core.hpp"
+#include "ldlt_core.hpp"
 #include "problems/problems.hpp"
 
 namespace {
@@ -32,7 +34,33 @@ struct Emu {
   int n = 0, me = 0, mi = 0;
   // last evaluation
   std::vector<double> values, derivs;
+  // linear algebra
+  slpb::KktRecipe recipe;
+  slpb::Symbolic sym;
+  std::vector<double> Kval, panels, updates, D, uvecs, xperm;
 };
+
+slpb::SymbolicView view_of(const slpb::Symbolic& S) {
+  slpb::SymbolicView v{};
+  v.dim = S.dim;
+  v.n_super = S.n_super;
+  v.super_first = S.super_first.data();
+  v.front_dim = S.front_dim.data();
+  v.rows_ptr = S.rows_ptr.data();
+  v.rows_idx = S.rows_idx.data();
+  v.panel_ptr = S.panel_ptr.data();
+  v.update_ptr = S.update_ptr.data();
+  v.child_ptr = S.child_ptr.data();
+  v.child_idx = S.child_idx.data();
+  v.rel_ptr = S.rel_ptr.data();
+  v.rel_idx = S.rel_idx.data();
+  v.asm_ptr = S.asm_ptr.data();
+  v.asm_src = S.asm_src.data();
+  v.asm_dst = S.asm_dst.data();
+  v.col_is_primal = S.col_is_primal.data();
+  v.perm = S.perm.data();
+  return v;
+}
 
 void run_programs(const slpb::ProgramSet& ps, const double* leaf,
                   double* stage) {
@@ -175,6 +203,118 @@ void emu_eval(void* h, const double* x, const double* y, const double* z,
   if (a.A_e.nnz()) std::memcpy(ae, e->derivs.data() + a.off_ae, a.A_e.nnz() * 8);
   if (a.A_i.nnz()) std::memcpy(ai, e->derivs.data() + a.off_ai, a.A_i.nnz() * 8);
   if (a.H.nnz()) std::memcpy(hv, e->derivs.data() + a.off_h, a.H.nnz() * 8);
+}
+
+
+// ---- KKT assembly + multifrontal LDLT --------------------------------------
+
+/// Builds the KKT recipe; returns nnz of the lower triangle.
+int64_t emu_kkt_build(void* h) {
+  auto* e = static_cast<Emu*>(h);
+  slpb::build_kkt_recipe(e->n, e->me, e->ad.H, e->ad.A_e, e->ad.A_i, e->recipe);
+  return e->recipe.K.nnz();
+}
+
+void emu_kkt_pattern(void* h, int* colptr, int* rowidx) {
+  auto* e = static_cast<Emu*>(h);
+  const auto& K = e->recipe.K;
+  std::memcpy(colptr, K.colptr.data(), K.colptr.size() * sizeof(int));
+  std::memcpy(rowidx, K.rowidx.data(), K.nnz() * sizeof(int));
+}
+
+/// Assembles lhs values (no δ/γ) from the last emu_eval and Σ = z/s.
+void emu_kkt_assemble(void* h, const double* sigma, double* kval_out) {
+  auto* e = static_cast<Emu*>(h);
+  const auto& R = e->recipe;
+  const auto& a = e->ad;
+  e->Kval.resize(R.K.nnz());
+  for (int64_t k = 0; k < R.K.nnz(); ++k) {
+    e->Kval[k] = slpb::kkt_entry(
+        static_cast<int>(k), R.h_idx.data(), R.ae_idx.data(), R.prod_ptr.data(),
+        R.prod_a.data(), R.prod_b.data(), R.prod_row.data(),
+        e->derivs.data() + a.off_h, e->derivs.data() + a.off_ae,
+        e->derivs.data() + a.off_ai, sigma);
+  }
+  if (kval_out) std::memcpy(kval_out, e->Kval.data(), e->Kval.size() * 8);
+}
+
+/// out: dim, nnz_l, n_super, n_levels, max_front, etree_height, panel doubles,
+/// update doubles. Returns 0 on success.
+int emu_analyze(void* h, int ordering, const int* perm, int64_t* out) {
+  auto* e = static_cast<Emu*>(h);
+  if (!slpb::analyze_kkt(e->recipe.K, e->n, ordering, perm, e->sym, e->error)) {
+    return -1;
+  }
+  const auto& S = e->sym;
+  out[0] = S.dim;
+  out[1] = S.nnz_l;
+  out[2] = S.n_super;
+  out[3] = S.n_levels;
+  out[4] = S.max_front;
+  out[5] = S.etree_height;
+  out[6] = S.panel_size;
+  out[7] = S.update_size;
+  e->panels.assign(S.panel_size, 0.0);
+  e->updates.assign(S.update_size, 0.0);
+  e->D.assign(S.dim, 0.0);
+  e->uvecs.assign(S.rel_ptr.back(), 0.0);
+  e->xperm.assign(S.dim, 0.0);
+  return 0;
+}
+
+void emu_get_perm(void* h, int* perm) {
+  auto* e = static_cast<Emu*>(h);
+  std::memcpy(perm, e->sym.perm.data(), e->sym.dim * sizeof(int));
+}
+
+/// info: n_pos, n_neg, n_zero, zero_pivot; returns min |D|.
+double emu_factor(void* h, double delta, double gamma, int* info, double* D) {
+  auto* e = static_cast<Emu*>(h);
+  const auto& S = e->sym;
+  slpb::SymbolicView V = view_of(S);
+  std::vector<double> W(size_t(S.max_front) * S.max_front), lcol(S.max_front);
+  int tot[4] = {0, 0, 0, 0};
+  double min_abs = INFINITY;
+  for (int L = 0; L < S.n_levels; ++L) {
+    for (int k = S.level_ptr[L]; k < S.level_ptr[L + 1]; ++k) {
+      int ls[6];
+      slpb::ldlt_factor_front<1>(0, S.level_supers[k], V, e->Kval.data(), delta,
+                                 gamma, e->panels.data(), e->updates.data(),
+                                 e->D.data(), W.data(), lcol.data(), ls,
+                                 slpb::NoSync{});
+      for (int i = 0; i < 4; ++i) tot[i] += ls[i];
+      unsigned long long bits = (unsigned long long)(unsigned)ls[4] |
+                                ((unsigned long long)(unsigned)ls[5] << 32);
+      double a;
+      std::memcpy(&a, &bits, 8);
+      min_abs = std::fmin(min_abs, a);
+    }
+  }
+  std::memcpy(info, tot, sizeof(tot));
+  if (D) std::memcpy(D, e->D.data(), S.dim * 8);
+  return min_abs;
+}
+
+void emu_solve(void* h, const double* rhs, double* x) {
+  auto* e = static_cast<Emu*>(h);
+  const auto& S = e->sym;
+  slpb::SymbolicView V = view_of(S);
+  std::vector<double> w(S.max_front);
+  for (int L = 0; L < S.n_levels; ++L) {
+    for (int k = S.level_ptr[L]; k < S.level_ptr[L + 1]; ++k) {
+      slpb::ldlt_forward_front<1>(0, S.level_supers[k], V, e->panels.data(),
+                                  rhs, e->xperm.data(), e->uvecs.data(),
+                                  w.data(), slpb::NoSync{});
+    }
+  }
+  for (int L = S.n_levels - 1; L >= 0; --L) {
+    for (int k = S.level_ptr[L]; k < S.level_ptr[L + 1]; ++k) {
+      slpb::ldlt_backward_front<1>(0, S.level_supers[k], V, e->panels.data(),
+                                   e->D.data(), e->xperm.data(), w.data(),
+                                   slpb::NoSync{});
+    }
+  }
+  for (int k = 0; k < S.dim; ++k) x[S.perm[k]] = e->xperm[k];
 }
 
 }  // extern "C"
