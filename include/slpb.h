@@ -317,6 +317,16 @@ typedef struct slpb_counters {
 } slpb_counters;
 int slpb_get_counters(const slpb_solver* s, slpb_counters* out);
 
+/* Device time accumulated per phase since the handle was created, measured
+ * with CUDA events on the handle's stream (milliseconds) and the number of
+ * times each phase ran: [0] eval(full) [1] eval(values) [2] assemble
+ * [3] factor [4] solve. */
+typedef struct slpb_timers {
+  double total_ms[5];
+  int64_t count[5];
+} slpb_timers;
+int slpb_get_timers(slpb_solver* s, slpb_timers* out);
+
 /* Device time of the most recent factor / solve / eval, measured with CUDA
  * events on the handle's stream (milliseconds; 0 if not yet run). which:
  * 0 eval(full), 1 eval(values), 2 assemble, 3 factor, 4 solve. */

@@ -136,7 +136,7 @@ void orc_trace_get(void* h, int row, double* scalars, double* x, double* s,
   double sc[16] = {double(r.iteration), double(r.type), r.error, r.cost,
                    r.infeasibility, r.complementarity, r.mu, r.delta, r.gamma,
                    r.alpha, r.alpha_max, r.alpha_z, double(r.factorizations),
-                   double(r.solves), double(r.trials), 0.0};
+                   double(r.solves), double(r.trials), r.t_end};
   std::memcpy(scalars, sc, sizeof(sc));
   auto cp = [](double* dst, const orc::Vec& v) {
     if (dst && !v.empty()) std::memcpy(dst, v.data(), v.size() * sizeof(double));

@@ -111,6 +111,7 @@ struct TraceRow {
   double error, cost, infeasibility, complementarity, mu, delta, gamma;
   double alpha, alpha_max, alpha_z;
   int factorizations, solves, trials;
+  double t_end = 0.0;  // seconds since interior_point() was entered
   Vec x, s, y, z;
 };
 struct Trace {
@@ -1012,6 +1013,9 @@ inline ExitStatus interior_point(const IpmCallbacks& matrices,
       row.factorizations = solver.factorizations - fact_before;
       row.solves = it_solves;
       row.trials = it_trials;
+      row.t_end = std::chrono::duration<double>(
+                      std::chrono::steady_clock::now() - solve_start)
+                      .count();
       if (trace->keep_iterates) {
         row.x = x;
         row.s = s;

@@ -124,6 +124,7 @@ class TraceRow:
     factorizations: int
     solves: int
     trials: int
+    t_end: float = 0.0
     x: np.ndarray | None = None
     s: np.ndarray | None = None
     y: np.ndarray | None = None
@@ -203,7 +204,7 @@ class OracleProblem:
                 x, s, z = x[:self.n], s[:self.mi], z[:self.mi]
             rows.append(TraceRow(int(sc[0]), int(sc[1]), *sc[2:12],
                                  int(sc[12]), int(sc[13]), int(sc[14]),
-                                 x, s, y, z))
+                                 float(sc[15]), x, s, y, z))
         return rows
 
     def solution(self):

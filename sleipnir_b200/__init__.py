@@ -109,7 +109,8 @@ ABI_SYMBOLS = [
     "slpb_eval_current", "slpb_kkt_stats_current", "slpb_kkt_stats_trial",
     "slpb_factor", "slpb_solve", "slpb_soc_begin", "slpb_soc_iterate",
     "slpb_trial", "slpb_accept", "slpb_array_size", "slpb_download",
-    "slpb_pattern", "slpb_get_counters", "slpb_last_device_ms", "slpb_stream",
+    "slpb_pattern", "slpb_get_counters", "slpb_get_timers",
+    "slpb_last_device_ms", "slpb_stream",
 ]
 
 _dev = None
@@ -185,6 +186,7 @@ def host_lib() -> C.CDLL:
         L.slpbh_loop_seconds.argtypes = [vp]
         L.slpbh_symbolic_stats.argtypes = [vp, _lp]
         L.slpbh_counters.argtypes = [vp, _lp]
+        L.slpbh_timers.argtypes = [vp, _dp]
         L.slpbh_device_open.restype = vp
         L.slpbh_device_open.argtypes = [vp, C.c_int]
         L.slpbh_device_close.argtypes = [vp]
@@ -209,6 +211,7 @@ class IterationRecord:
     factorizations: int
     solves: int
     trials: int
+    t_end: float = 0.0
     x: np.ndarray | None = None
     s: np.ndarray | None = None
     y: np.ndarray | None = None
@@ -399,7 +402,7 @@ class Problem:
                 s, y, z = s[:self.mi], y[:self.me], z[:self.mi]
             rows.append(IterationRecord(int(sc[0]), int(sc[1]), *sc[2:12],
                                         int(sc[12]), int(sc[13]), int(sc[14]),
-                                        x, s, y, z))
+                                        float(sc[15]), x, s, y, z))
         return rows
 
     def solution(self):
@@ -423,6 +426,13 @@ class Problem:
         self.H.slpbh_counters(self.h, out.ctypes.data_as(_lp))
         keys = [k for k, _ in Counters._fields_]
         return dict(zip(keys, (int(v) for v in out)))
+
+    def timers(self):
+        out = np.zeros(10)
+        self.H.slpbh_timers(self.h, _d(out))
+        names = ("eval_full", "eval_values", "assemble", "factor", "solve")
+        return {k: {"total_ms": float(out[i]), "count": int(out[5 + i])}
+                for i, k in enumerate(names)}
 
     def open_device(self, device=0) -> DeviceSession:
         raw = self.H.slpbh_device_open(self.h, device)

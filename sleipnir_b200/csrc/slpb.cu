@@ -82,7 +82,7 @@ struct DevGather {
 
 constexpr int kResultDoubles = 64;
 constexpr int kLongGather = 48;  // sources above which a block reduces an entry
-constexpr int kReduceThreads = 1024;
+constexpr int kReduceThreads = 512;
 
 }  // namespace slpb
 
@@ -133,6 +133,8 @@ struct slpb_solver {
   // timing
   cudaEvent_t ev[10] = {};
   float last_ms[5] = {0, 0, 0, 0, 0};
+  slpb_timers timers{};
+  bool pending[5] = {false, false, false, false, false};
 };
 
 namespace slpb {
@@ -286,7 +288,7 @@ __device__ void block_reduce(double (&v)[NV], const int (&op)[NV],
 
 /// slpb_point_info for a point: vals = [f | c_e | c_i], slack s.
 /// out: f, ce_l1, cis_l1, log_s_sum, finite bits (as double), ci_all_positive.
-__global__ void k_point_info(const double* __restrict__ vals,
+__global__ void __launch_bounds__(kReduceThreads) k_point_info(const double* __restrict__ vals,
                              const double* __restrict__ s, int me, int mi,
                              double* __restrict__ out) {
   double v[5] = {0.0, 0.0, 0.0, 0.0, 0.0};
@@ -326,7 +328,7 @@ __global__ void k_point_info(const double* __restrict__ vals,
 }
 
 /// Finite-ness of the derivative arrays: out[0] = OR of G/A_E/A_I/H bits.
-__global__ void k_deriv_finite(const double* __restrict__ dvals, int64_t off_ae,
+__global__ void __launch_bounds__(kReduceThreads) k_deriv_finite(const double* __restrict__ dvals, int64_t off_ae,
                                int64_t off_ai, int64_t off_h, int64_t total,
                                double* __restrict__ out) {
   double w[4] = {0.0, 0.0, 0.0, 0.0};
@@ -358,7 +360,7 @@ struct CscView {
 /// All reductions behind kkt_error / unscaled_kkt_error (kkt_error.hpp:92-251),
 /// is_locally_infeasible.hpp and the divergence guard, for one point.
 /// out layout = fields of slpb_kkt_stats in declaration order.
-__global__ void k_kkt_stats(CscView Ae, CscView Ai, const double* __restrict__ g,
+__global__ void __launch_bounds__(kReduceThreads) k_kkt_stats(CscView Ae, CscView Ai, const double* __restrict__ g,
                             const double* __restrict__ c_e,
                             const double* __restrict__ c_i,
                             const double* __restrict__ x,
@@ -624,7 +626,7 @@ __global__ void k_step_recover(const double* __restrict__ sol,
 /// fraction-to-the-boundary rule on (s,p_s) and (z,p_z)
 /// (fraction_to_the_boundary_rule.hpp:19-43: α = min(1, min −τ/pᵢ·xᵢ over the
 /// blocking components), gᵀpˣ, (S⁻¹e)ᵀpˢ and step norms.
-__global__ void k_step_stats(const double* __restrict__ g,
+__global__ void __launch_bounds__(kReduceThreads) k_step_stats(const double* __restrict__ g,
                              const double* __restrict__ s,
                              const double* __restrict__ z,
                              const double* __restrict__ sinv,
@@ -807,12 +809,31 @@ int run_gather(slpb_solver* S, const DevGather& d, const double* stage,
   return SLPB_OK;
 }
 
+/// After a stream synchronisation: folds the event pairs that were recorded
+/// since the last harvest into the per-phase timers.
+void harvest_timers(slpb_solver* S) {
+  for (int w = 0; w < 5; ++w) {
+    if (!S->pending[w]) continue;
+    float ms = 0.0f;
+    if (cudaEventElapsedTime(&ms, S->ev[2 * w], S->ev[2 * w + 1]) ==
+        cudaSuccess) {
+      S->last_ms[w] = ms;
+      S->timers.total_ms[w] += ms;
+      ++S->timers.count[w];
+    } else {
+      cudaGetLastError();
+    }
+    S->pending[w] = false;
+  }
+}
+
 /// Copies `count` doubles of the device result buffer to the pinned mirror and
 /// waits for the stream.
 int fetch_results(slpb_solver* S, int count) {
   CU(cudaMemcpyAsync(S->h_results, S->d_results.p, count * sizeof(double),
                      cudaMemcpyDeviceToHost, S->stream));
   CU(cudaStreamSynchronize(S->stream));
+  harvest_timers(S);
   S->counters.d2h_bytes += count * sizeof(double);
   return SLPB_OK;
 }
@@ -832,6 +853,7 @@ int eval_values(slpb_solver* S, const double* leaf, double* vals) {
   rc = run_gather(S, S->gv, S->vstage.p, vals);
   if (rc) return rc;
   CU(cudaEventRecord(S->ev[3], S->stream));
+  S->pending[1] = true;
   ++S->counters.evals_values;
   return SLPB_OK;
 }
@@ -843,6 +865,7 @@ int eval_derivs(slpb_solver* S, const double* leaf) {
   rc = run_gather(S, S->gd, S->dstage.p, S->dvals.p);
   if (rc) return rc;
   CU(cudaEventRecord(S->ev[1], S->stream));
+  S->pending[0] = true;
   ++S->counters.evals_full;
   return SLPB_OK;
 }
@@ -936,6 +959,7 @@ int launch_solve(slpb_solver* S) {
       S->xperm.p, S->sy_perm.p, S->dim, S->sol.p);
   S->counters.kernel_launches += 2 * Y.n_levels + 1;
   CU(cudaEventRecord(S->ev[9], S->stream));
+  S->pending[4] = true;
   CU(cudaGetLastError());
   ++S->counters.solves;
   return SLPB_OK;
@@ -1370,6 +1394,7 @@ int slpb_factor(slpb_solver* S, double delta, double gamma, int reassemble,
         S->Kval.p);
     ++S->counters.kernel_launches;
     CU(cudaEventRecord(S->ev[5], S->stream));
+    S->pending[2] = true;
   }
   CU(cudaEventRecord(S->ev[6], S->stream));
   // stats: n_pos n_neg n_zero zero_pivot | min|D| bits (+inf)
@@ -1390,11 +1415,13 @@ int slpb_factor(slpb_solver* S, double delta, double gamma, int reassemble,
   }
   S->counters.kernel_launches += Y.n_levels;
   CU(cudaEventRecord(S->ev[7], S->stream));
+  S->pending[3] = true;
   CU(cudaGetLastError());
   int32_t host_stats[8];
   CU(cudaMemcpyAsync(host_stats, S->fstats.p, sizeof(host_stats),
                      cudaMemcpyDeviceToHost, S->stream));
   CU(cudaStreamSynchronize(S->stream));
+  harvest_timers(S);
   S->counters.d2h_bytes += sizeof(host_stats);
   info->n_pos = host_stats[0];
   info->n_neg = host_stats[1];
@@ -1591,15 +1618,17 @@ int slpb_last_device_ms(slpb_solver* S, int which, float* ms) {
   if (!S || !ms || which < 0 || which > 4) return SLPB_ERR_ARGUMENT;
   CU(cudaSetDevice(S->device));
   CU(cudaStreamSynchronize(S->stream));
-  *ms = 0.0f;
-  const int a = 2 * which, b = 2 * which + 1;
-  if (cudaEventQuery(S->ev[a]) == cudaSuccess &&
-      cudaEventQuery(S->ev[b]) == cudaSuccess) {
-    if (cudaEventElapsedTime(ms, S->ev[a], S->ev[b]) != cudaSuccess) {
-      *ms = 0.0f;
-      cudaGetLastError();
-    }
-  }
+  harvest_timers(S);
+  *ms = S->last_ms[which];
+  return SLPB_OK;
+}
+
+int slpb_get_timers(slpb_solver* S, slpb_timers* out) {
+  if (!S || !out) return SLPB_ERR_ARGUMENT;
+  CU(cudaSetDevice(S->device));
+  CU(cudaStreamSynchronize(S->stream));
+  harvest_timers(S);
+  *out = S->timers;
   return SLPB_OK;
 }
 

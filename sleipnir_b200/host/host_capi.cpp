@@ -101,7 +101,7 @@ void slpbh_trace_get(void* h, int row, double* scalars, double* x, double* s,
   double sc[16] = {double(r.iteration), double(r.type), r.error, r.cost,
                    r.infeasibility, r.complementarity, r.mu, r.delta, r.gamma,
                    r.alpha, r.alpha_max, r.alpha_z, double(r.factorizations),
-                   double(r.solves), double(r.trials), 0.0};
+                   double(r.solves), double(r.trials), r.t_end};
   std::memcpy(scalars, sc, sizeof(sc));
   auto cp = [](double* dst, const std::vector<double>& v) {
     if (dst && !v.empty()) std::memcpy(dst, v.data(), v.size() * 8);
@@ -152,6 +152,15 @@ void slpbh_counters(void* h, int64_t* out) {
                          c.program_bytes, c.n_clusters, c.n_program_classes,
                          c.h2d_bytes, c.d2h_bytes};
   std::memcpy(out, v, sizeof(v));
+}
+
+/// out[10]: total_ms[5] then count[5] of slpb_timers.
+void slpbh_timers(void* h, double* out) {
+  const auto& t = H(h)->problem->last_timers();
+  for (int i = 0; i < 5; ++i) {
+    out[i] = t.total_ms[i];
+    out[5 + i] = static_cast<double>(t.count[i]);
+  }
 }
 
 /// Builds the autodiff graphs, opens a device handle, uploads and finalises.

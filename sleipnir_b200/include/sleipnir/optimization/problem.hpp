@@ -237,6 +237,7 @@ class Problem {
     m_last_y = std::move(y);
     m_last_z = std::move(z);
     slpb_get_counters(dev, &m_counters);
+    slpb_get_timers(dev, &m_timers);
     return status;
   }
 
@@ -276,6 +277,7 @@ class Problem {
   const SolveTrace& last_trace() const { return m_trace; }
   const slpb_symbolic_stats& last_symbolic_stats() const { return m_symbolic; }
   const slpb_counters& last_counters() const { return m_counters; }
+  const slpb_timers& last_timers() const { return m_timers; }
   const std::vector<Scalar>& last_s() const { return m_last_s; }
   const std::vector<Scalar>& last_y() const { return m_last_y; }
   const std::vector<Scalar>& last_z() const { return m_last_z; }
@@ -420,6 +422,7 @@ class Problem {
   SolveTrace m_trace;
   slpb_symbolic_stats m_symbolic{};
   slpb_counters m_counters{};
+  slpb_timers m_timers{};
   std::vector<Scalar> m_last_s, m_last_y, m_last_z;
 };
 

@@ -56,6 +56,7 @@ struct IterationRecord {
   double error = 0, cost = 0, infeasibility = 0, complementarity = 0;
   double mu = 0, delta = 0, gamma = 0, alpha = 0, alpha_max = 0, alpha_z = 0;
   int factorizations = 0, solves = 0, trials = 0;
+  double t_end = 0.0;  ///< seconds since the solve entered the solver
   std::vector<double> x, s, y, z;  ///< filled when SolveTrace::keep_iterates
 };
 
@@ -576,6 +577,9 @@ ExitStatus interior_point(
       row.factorizations = solver.factorizations - fact_before;
       row.solves = it_solves;
       row.trials = it_trials;
+      row.t_end = std::chrono::duration<double>(
+                      std::chrono::steady_clock::now() - solve_start_time)
+                      .count();
       if (trace->keep_iterates) {
         row.x.resize(n);
         row.s.resize(mi);

@@ -1,0 +1,81 @@
+"""The C-ABI libraries load, export every symbol include/slpb.h declares, and
+refuse to run without a GPU (no compute calls here)."""
+import ctypes as C
+import os
+import re
+
+import pytest
+
+import sleipnir_b200 as sb
+
+ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+
+
+def _declared_symbols():
+    text = open(os.path.join(ROOT, "include", "slpb.h")).read()
+    text = re.sub(r"/\*.*?\*/", "", text, flags=re.S)
+    return sorted(set(re.findall(r"\b(slpb_[a-z_]+)\s*\(", text)))
+
+
+def test_header_and_python_symbol_lists_agree():
+    assert _declared_symbols() == sorted(sb.ABI_SYMBOLS)
+
+
+def test_library_exports_every_declared_symbol():
+    lib = sb.device_lib()
+    for name in _declared_symbols():
+        assert hasattr(lib, name), f"libslpb.so does not export {name}"
+
+
+def test_host_library_loads():
+    H = sb.host_lib()
+    for name in ("slpbh_problem_create", "slpbh_solve", "slpbh_device_open",
+                 "slpbh_trace_get", "slpbh_solution"):
+        assert hasattr(H, name)
+
+
+def test_problem_dimensions_match_the_survey_table():
+    # cart-pole n = 5N+4, m_e = 4N+8, m_i = 4N+2; flywheel 2N+1, N+1, 2N
+    P = sb.Problem("cart_pole", 100)
+    assert (P.n, P.me, P.mi) == (504, 408, 402)
+    assert P.types() == (3, 4, 2)
+    P.close()
+    P = sb.Problem("flywheel", 50)
+    assert (P.n, P.me, P.mi) == (101, 51, 100)
+    P.close()
+
+
+def _no_gpu():
+    try:
+        import torch
+        return not torch.cuda.is_available()
+    except Exception:
+        return True
+
+
+@pytest.mark.skipif(not _no_gpu(), reason="only meaningful without a GPU")
+def test_fails_loudly_without_a_device():
+    lib = sb.device_lib()
+    h = C.c_void_p()
+    rc = lib.slpb_create(0, C.byref(h))
+    assert rc == -5  # SLPB_ERR_NO_DEVICE
+    P = sb.Problem("quartic")
+    with pytest.raises(sb.DeviceError, match="no CPU fallback"):
+        P.solve()
+    P.close()
+
+
+def test_product_does_not_reference_the_oracle():
+    """Nothing under sleipnir_b200/ (nor include/) may include, import or link
+    anything under oracle/."""
+    bad = []
+    for base in ("sleipnir_b200", "include"):
+        for dp, _, files in os.walk(os.path.join(ROOT, base)):
+            for f in files:
+                if not f.endswith((".hpp", ".h", ".cpp", ".cu", ".py", "Makefile")):
+                    continue
+                text = open(os.path.join(dp, f), errors="ignore").read()
+                if re.search(r'#include\s+[<"].*oracle|from oracle|import oracle|'
+                             r'liboracle|pyoracle', text):
+                    bad.append(os.path.join(dp, f))
+    assert not bad, bad

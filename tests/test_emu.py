@@ -1,0 +1,162 @@
+"""CPU-tier checks of the product's host logic and of the kernels' bodies run
+on the host by tests/emu (one lane instead of a warp / thread block):
+host DSL → tape → cluster programs → interpreter; KKT recipe; symbolic
+analysis; multifrontal LDLT — each against the oracle and the golden vectors."""
+import glob
+import os
+
+import numpy as np
+import pytest
+import scipy.sparse as sp
+
+from emu import Emu
+from oracle.pyoracle import OracleProblem, ldlt
+
+GOLDEN = os.path.join(os.path.dirname(__file__), "golden")
+PARAMS = {"rosenbrock_cubic_line": (0.3, 0.7), "rosenbrock_disk": (-0.5, 1.2)}
+
+
+@pytest.mark.parametrize("path", sorted(glob.glob(os.path.join(GOLDEN, "eval_*.npz"))))
+def test_interpreter_matches_reference_core_bit_for_bit(path):
+    """Same libm on both sides here, so the product's DSL + compiler +
+    interpreter must reproduce the reference core's numbers exactly."""
+    g = np.load(path)
+    name, N = os.path.basename(path)[5:-4].rsplit("_", 1)
+    p0, p1 = PARAMS.get(name, (0, 0))
+    E = Emu(name, int(N), p0, p1)
+    out = E.eval(g["x"], g["y"], g["z"], float(g["d_f"]), g["d_ce"], g["d_ci"])
+    assert out["f"] == g["f"]
+    np.testing.assert_array_equal(out["c_e"], g["c_e"])
+    np.testing.assert_array_equal(out["c_i"], g["c_i"])
+    np.testing.assert_array_equal(out["g"], g["g"])
+    for nm, which in (("A_e", 5), ("A_i", 7), ("H", 3)):
+        _, _, cp, ri = E.pattern(which)
+        np.testing.assert_array_equal(cp, g[nm + "_colptr"])
+        np.testing.assert_array_equal(ri, g[nm + "_rowidx"])
+        np.testing.assert_array_equal(out[nm], g[nm + "_val"])
+    E.close()
+
+
+def test_time_steps_share_one_program():
+    """Every stage of a transcription compiles to the same position-independent
+    program: the blob must not grow with the horizon."""
+    a, b = Emu("cart_pole", 20), Emu("cart_pole", 40)  # both above the split threshold
+    sa, sb_ = a.stats(), b.stats()
+    assert sa["deriv_programs"] == sb_["deriv_programs"] <= 4
+    assert sa["deriv_words"] == sb_["deriv_words"]
+    assert sb_["deriv_clusters"] == 2 * 40  # dynamics + u_k² term per stage
+    assert sb_["max_smem"] < 48 * 1024
+    a.close(); b.close()
+
+
+def test_long_cost_sum_is_split():
+    """Σ_k (r − x_k)² with 301 terms: the row is split into independent terms
+    and summed by the gather; values agree with the oracle to rounding."""
+    N = 300
+    E, O = Emu("flywheel", N), OracleProblem("flywheel", N)
+    O.eval_setup()
+    d_f, d_ce, d_ci = O.scaling()
+    rng = np.random.default_rng(5)
+    x = rng.standard_normal(E.n)
+    y, z = rng.standard_normal(E.me), np.abs(rng.standard_normal(E.mi))
+    out = E.eval(x, y, z, d_f, d_ce, d_ci)
+    assert abs(out["f"] - O.f(x)) <= 1e-13 * abs(O.f(x))
+    np.testing.assert_allclose(out["g"], O.g(x), rtol=1e-14, atol=0)
+    np.testing.assert_array_equal(out["A_e"], O.A_e(x).val)
+    np.testing.assert_array_equal(out["H"], O.H(x, y, z).val)
+    assert E.stats()["value_clusters"] > N  # one cluster per term
+    E.close(); O.close()
+
+
+@pytest.mark.parametrize("name,N", [("cart_pole", 30), ("flywheel", 40),
+                                    ("wachter_biegler", 0)])
+def test_kkt_assembly(name, N):
+    E, O = Emu(name, N), OracleProblem(name, N)
+    O.eval_setup()
+    d_f, d_ce, d_ci = O.scaling()
+    rng = np.random.default_rng(9)
+    x = O.initial_guess() + 0.01 * rng.standard_normal(E.n)
+    y = 0.1 * rng.standard_normal(E.me)
+    z = 0.1 + np.abs(rng.standard_normal(E.mi))
+    s = 0.1 + np.abs(rng.standard_normal(E.mi))
+    E.eval(x, y, z, d_f, d_ce, d_ci)
+    cp, ri, kv = E.kkt(z / s)
+    n, me, mi = E.n, E.me, E.mi
+    H, Ae, Ai = O.H(x, y, z), O.A_e(x), O.A_i(x)
+    Hs = sp.csc_matrix((H.val, H.rowidx, H.colptr), shape=(n, n))
+    Aes = sp.csc_matrix((Ae.val, Ae.rowidx, Ae.colptr), shape=(me, n))
+    Ais = sp.csc_matrix((Ai.val, Ai.rowidx, Ai.colptr), shape=(mi, n))
+    TL = Hs + sp.tril(Ais.T @ sp.diags(z / s) @ Ais)
+    K = sp.bmat([[TL, None], [Aes, sp.csc_matrix((me, me))]], format="csc")
+    Kemu = sp.csc_matrix((kv, ri, cp), shape=(n + me, n + me))
+    assert abs(Kemu - K).max() <= 1e-12 * max(1.0, abs(K).max())
+    # every diagonal entry is structurally present (pattern stability,
+    # sparse_regularized_ldlt.hpp:65-67)
+    for c in range(n + me):
+        assert c in ri[cp[c]:cp[c + 1]]
+    E.close(); O.close()
+
+
+@pytest.mark.parametrize("ordering", [0, 2])
+def test_multifrontal_ldlt_matches_oracle(ordering):
+    E, O = Emu("cart_pole", 60), OracleProblem("cart_pole", 60)
+    O.eval_setup()
+    d_f, d_ce, d_ci = O.scaling()
+    rng = np.random.default_rng(4)
+    x = O.initial_guess() + 0.01 * rng.standard_normal(E.n)
+    y = 0.1 * rng.standard_normal(E.me)
+    z = 0.5 + np.abs(rng.standard_normal(E.mi))
+    s = 0.5 + np.abs(rng.standard_normal(E.mi))
+    E.eval(x, y, z, d_f, d_ce, d_ci)
+    cp, ri, kv = E.kkt(z / s)
+    st = E.analyze(ordering)
+    perm = E.perm()
+    assert sorted(perm) == list(range(E.n + E.me))
+    dim = E.n + E.me
+    delta, gamma = 1.0, 1e-6
+    info, mn, D = E.factor(delta, gamma)
+    assert info[:3] == (E.n, E.me, 0) and info[3] == 0
+    kvr = kv.copy()
+    for c in range(dim):
+        k = cp[c] + np.searchsorted(ri[cp[c]:cp[c + 1]], c)
+        kvr[k] += delta if c < E.n else -gamma
+    rhs = rng.standard_normal(dim)
+    nnzL, Do, xo, _ = ldlt(dim, cp, ri, kvr, rhs, perm)
+    assert nnzL == st["nnz_l"]
+    np.testing.assert_allclose(D, Do, rtol=1e-9)
+    assert mn == pytest.approx(np.abs(Do).min(), rel=1e-9)
+    xs = E.solve(rhs)
+    np.testing.assert_allclose(xs, xo, rtol=0, atol=1e-9 * np.abs(xo).max())
+    full = sp.csc_matrix((kvr, ri, cp), shape=(dim, dim))
+    full = full + sp.tril(full, -1).T
+    assert np.abs(full @ xs - rhs).max() < 1e-8
+    E.close(); O.close()
+
+
+def test_nested_dissection_gives_a_shallow_tree():
+    """The assembly tree's depth grows like log N (the reference's AMD order
+    has an O(N) chain)."""
+    depth = {}
+    for N in (50, 400):
+        E = Emu("cart_pole", N)
+        E.eval(np.zeros(E.n), np.zeros(E.me), np.ones(E.mi), 1.0,
+               np.ones(E.me), np.ones(E.mi))
+        E.kkt(np.ones(E.mi))
+        st = E.analyze(0)
+        depth[N] = st["n_levels"]
+        assert st["max_front"] <= 40
+        E.close()
+    assert depth[400] <= depth[50] + 4
+
+
+def test_zero_pivot_flag():
+    """δ = γ = 0 on the initial cart-pole KKT hits a structurally zero pivot
+    (states without curvature): the factor must flag it, not crash."""
+    E = Emu("cart_pole", 10)
+    E.eval(np.zeros(E.n), np.zeros(E.me), np.ones(E.mi), 1.0, np.ones(E.me),
+           np.ones(E.mi))
+    E.kkt(np.ones(E.mi))
+    E.analyze(2)
+    info, mn, D = E.factor(0.0, 0.0)
+    assert info[3] == 1 or info[2] > 0 or info[:2] != (E.n, E.me)
+    E.close()

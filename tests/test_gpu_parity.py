@@ -1,0 +1,338 @@
+"""Parity tests proper: the CUDA path, called through the C ABI
+(include/slpb.h), against the CPU oracle and the golden vectors.
+
+Tolerances (FP64):
+ * autodiff outputs: 1e-13 relative. The device arithmetic is the reference's
+   op for op and unfused; only libdevice sin/cos/… differ from glibc (≤ 2 ulp).
+ * KKT assembly: 1e-13.
+ * LDLᵀ: D and the solution are compared for a well-conditioned regularisation
+   (δ = 1, γ = 1e-6) at 1e-9; for the reference's own γ = 1e-10 the factor has
+   1e10 element growth (a −γ pivot) on BOTH sides, so only the residual is
+   checked there.
+ * iterates: a Newton step replayed from the same state agrees to 1e-6
+   relative on cart-pole (conditioning above) and 1e-12 on flywheel; full
+   trajectories are compared only while the reference algorithm itself is not
+   chaotic (flywheel: all iterations, 1e-10).
+"""
+import glob
+import os
+
+import numpy as np
+import pytest
+import scipy.sparse as sp
+
+import sleipnir_b200 as sb
+from oracle.pyoracle import EXIT_STATUS, OracleProblem, ldlt
+
+pytestmark = pytest.mark.gpu
+GOLDEN = os.path.join(os.path.dirname(__file__), "golden")
+PARAMS = {"rosenbrock_cubic_line": (0.3, 0.7), "rosenbrock_disk": (-0.5, 1.2)}
+
+
+def rel(a, b):
+    a, b = np.asarray(a, float), np.asarray(b, float)
+    if a.size == 0:
+        return 0.0
+    return np.abs(a - b).max() / max(np.abs(b).max(), 1e-300)
+
+
+@pytest.mark.parametrize("path", sorted(glob.glob(os.path.join(GOLDEN, "eval_*.npz"))))
+def test_autodiff_kernels_vs_golden(path):
+    g = np.load(path)
+    name, N = os.path.basename(path)[5:-4].rsplit("_", 1)
+    p0, p1 = PARAMS.get(name, (0, 0))
+    P = sb.Problem(name, int(N), p0, p1)
+    D = P.open_device()
+    D.set_scaling(float(g["d_f"]), g["d_ce"], g["d_ci"])
+    s = np.ones(P.mi)
+    D.set_iterate(g["x"], s, g["y"], g["z"])
+    info = D.eval_current(1)
+    assert rel([info.f], [g["f"]]) < 1e-13
+    assert rel(D.download(sb.ARR_C_E), g["c_e"]) < 1e-13
+    assert rel(D.download(sb.ARR_C_I), g["c_i"]) < 1e-13
+    assert rel(D.download(sb.ARR_G), g["g"]) < 1e-13
+    for nm, arr, pat in (("A_e", sb.ARR_A_E_VAL, sb.OUT_A_E),
+                         ("A_i", sb.ARR_A_I_VAL, sb.OUT_A_I),
+                         ("H", sb.ARR_H_VAL, sb.OUT_H_C)):
+        _, _, cp, ri = D.pattern(pat)
+        np.testing.assert_array_equal(cp, g[nm + "_colptr"])
+        np.testing.assert_array_equal(ri, g[nm + "_rowidx"])
+        assert rel(D.download(arr), g[nm + "_val"]) < 1e-13
+    assert info.finite == 127
+    assert abs(info.ce_l1 - np.abs(g["c_e"]).sum()) <= 1e-12 * max(1, np.abs(g["c_e"]).sum())
+    assert abs(info.cis_l1 - np.abs(g["c_i"] - s).sum()) <= 1e-12 * max(1, np.abs(g["c_i"]).sum())
+    P.close_device(); P.close()
+
+
+def _state(P, O, seed, dx=0.01):
+    rng = np.random.default_rng(seed)
+    x = O.initial_guess() + dx * rng.standard_normal(P.n)
+    y = 0.1 * rng.standard_normal(P.me)
+    z = 0.5 + np.abs(rng.standard_normal(P.mi))
+    s = 0.5 + np.abs(rng.standard_normal(P.mi))
+    return x, s, y, z
+
+
+@pytest.mark.parametrize("name,N", [("cart_pole", 100), ("flywheel", 200)])
+def test_newton_step_vs_oracle(name, N):
+    """KKT assembly, factorisation (same permutation on both sides), solve,
+    step recovery and fraction-to-the-boundary against the oracle's linear
+    algebra."""
+    P, O = sb.Problem(name, N), OracleProblem(name, N)
+    O.eval_setup()
+    d_f, d_ce, d_ci = O.scaling()
+    D = P.open_device()
+    D.set_scaling(d_f, d_ce, d_ci)
+    x, s, y, z = _state(P, O, 21)
+    D.set_iterate(x, s, y, z)
+    D.eval_current(1)
+    st = D.analyze(sb.ORDER_NESTED_DISSECTION)
+    perm = D.permutation()
+    n, me, mi, dim = P.n, P.me, P.mi, P.n + P.me
+    assert st.dim == dim and sorted(perm) == list(range(dim))
+
+    # assembled lhs vs scipy on the oracle's matrices
+    _, _, cp, ri = D.pattern(-1)
+    H, Ae, Ai = O.H(x, y, z), O.A_e(x), O.A_i(x)
+    Hs = sp.csc_matrix((H.val, H.rowidx, H.colptr), shape=(n, n))
+    Aes = sp.csc_matrix((Ae.val, Ae.rowidx, Ae.colptr), shape=(me, n))
+    Ais = sp.csc_matrix((Ai.val, Ai.rowidx, Ai.colptr), shape=(mi, n))
+    sigma = z / s
+    TL = Hs + sp.tril(Ais.T @ sp.diags(sigma) @ Ais)
+    Kref = sp.bmat([[TL, None], [Aes, sp.csc_matrix((me, me))]], format="csc")
+
+    mu, tau = 0.1 * d_f, 0.99
+    for delta, gamma, tight in ((1.0, 1e-6, True), (1e-4, 1e-10, False)):
+        fi = D.factor(delta, gamma, True)
+        kv = D.download(sb.ARR_KKT_VAL)
+        Kgpu = sp.csc_matrix((kv, ri, cp), shape=(dim, dim))
+        assert abs(Kgpu - Kref).max() <= 1e-13 * max(1.0, abs(Kref).max())
+        assert (fi.n_pos, fi.n_neg, fi.n_zero, fi.zero_pivot) == (n, me, 0, 0)
+        si = D.solve(mu, tau)
+        rhs = D.download(sb.ARR_RHS)
+        # rhs per interior_point.hpp:444-448 from oracle pieces
+        g, ce, ci = O.g(x), O.c_e(x), O.c_i(x)
+        t = -sigma * ci + mu / s + z
+        rhs_ref = np.concatenate([-g + Aes.T @ y + Ais.T @ t, -ce])
+        assert rel(rhs, rhs_ref) < 1e-12
+        kvr = kv.copy()
+        for c in range(dim):
+            k = cp[c] + np.searchsorted(ri[cp[c]:cp[c + 1]], c)
+            kvr[k] += delta if c < n else -gamma
+        nnzL, Do, xo, _ = ldlt(dim, cp, ri, kvr, rhs, perm)
+        assert nnzL == st.nnz_l
+        px, ps = D.download(sb.ARR_P_X), D.download(sb.ARR_P_S)
+        py, pz = D.download(sb.ARR_P_Y), D.download(sb.ARR_P_Z)
+        sol = np.concatenate([px, -py])
+        full = sp.csc_matrix((kvr, ri, cp), shape=(dim, dim))
+        full = full + sp.tril(full, -1).T
+        res_gpu = np.abs(full @ sol - rhs).max()
+        res_cpu = np.abs(full @ xo - rhs).max()
+        assert res_gpu <= 10 * res_cpu + 1e-9 * np.abs(rhs).max()
+        if tight:
+            assert rel(D.download(sb.ARR_D), Do) < 1e-9
+            assert abs(fi.min_abs_d - np.abs(Do).min()) <= 1e-9 * np.abs(Do).min()
+            assert rel(sol, xo) < 1e-9
+        # step recovery (interior_point.hpp:470-481) from the device's own p_x
+        ps_ref = (ci - s) + Ais @ px
+        pz_ref = mu / s - z - sigma * ps_ref
+        assert rel(ps, ps_ref) < 1e-12 and rel(pz, pz_ref) < 1e-11
+        # fraction-to-the-boundary (fraction_to_the_boundary_rule.hpp:19-43)
+        def ftb(v, p):
+            a = 1.0
+            for vi, pi in zip(v, p):
+                if a * pi < -tau * vi:
+                    a = -tau / pi * vi
+            return a
+        assert si.alpha_max == pytest.approx(ftb(s, ps), rel=1e-14)
+        assert si.alpha_z == pytest.approx(ftb(z, pz), rel=1e-14)
+        assert si.g_dot_px == pytest.approx(g @ px, rel=1e-10, abs=1e-12)
+        assert si.sinv_dot_ps == pytest.approx((ps / s).sum(), rel=1e-10)
+    P.close_device(); P.close(); O.close()
+
+
+def test_trial_point_and_accept():
+    name, N = "cart_pole", 60
+    P, O = sb.Problem(name, N), OracleProblem(name, N)
+    O.eval_setup()
+    d_f, d_ce, d_ci = O.scaling()
+    D = P.open_device()
+    D.set_scaling(d_f, d_ce, d_ci)
+    x, s, y, z = _state(P, O, 33)
+    D.set_iterate(x, s, y, z)
+    D.eval_current(1)
+    D.analyze()
+    D.factor(1.0, 1e-6, True)
+    mu = 0.05
+    si = D.solve(mu, 0.99)
+    px, ps = D.download(sb.ARR_P_X), D.download(sb.ARR_P_S)
+    py, pz = D.download(sb.ARR_P_Y), D.download(sb.ARR_P_Z)
+    a, az = si.alpha_max, si.alpha_z
+    ti = D.trial(a, az)
+    tx = x + a * px
+    assert rel(D.download(sb.ARR_TRIAL_X), tx) == 0.0
+    assert rel(D.download(sb.ARR_TRIAL_S), s + a * ps) == 0.0
+    assert rel(D.download(sb.ARR_TRIAL_Y), y + az * py) == 0.0
+    assert rel(D.download(sb.ARR_TRIAL_Z), z + az * pz) == 0.0
+    assert rel([ti.f], [O.f(tx)]) < 1e-13
+    assert rel(D.download(sb.ARR_TRIAL_C_E), O.c_e(tx)) < 1e-13
+    assert rel(D.download(sb.ARR_TRIAL_C_I), O.c_i(tx)) < 1e-13
+    ts = s + a * ps
+    assert ti.log_s_sum == pytest.approx(np.log(ts).sum(), rel=1e-13)
+    assert ti.cis_l1 == pytest.approx(np.abs(O.c_i(tx) - ts).sum(), rel=1e-12)
+    D.accept(mu)
+    x2, s2, y2, z2 = D.get_iterate()
+    np.testing.assert_array_equal(x2, tx)
+    zc = np.clip(z + az * pz, 1e-10 * mu / s2, 1e10 * mu / s2)
+    np.testing.assert_allclose(z2, zc, rtol=1e-15)
+    # KKT error pieces after re-linearisation (kkt_error.hpp:92-146)
+    D.eval_current(2)
+    ks = D.kkt_stats(mu)
+    g, Ae, Ai = O.g(x2), O.A_e(x2), O.A_i(x2)
+    Aes = sp.csc_matrix((Ae.val, Ae.rowidx, Ae.colptr), shape=(P.me, P.n))
+    Ais = sp.csc_matrix((Ai.val, Ai.rowidx, Ai.colptr), shape=(P.mi, P.n))
+    r = g - Aes.T @ y2 - Ais.T @ z2
+    assert ks.r_inf == pytest.approx(np.abs(r).max(), rel=1e-9)
+    assert ks.sz_max == pytest.approx((s2 * z2).max(), rel=1e-14)
+    assert ks.ce_inf == pytest.approx(np.abs(O.c_e(x2)).max(), rel=1e-12)
+    assert ks.cis_inf == pytest.approx(np.abs(O.c_i(x2) - s2).max(), rel=1e-12)
+    P.close_device(); P.close(); O.close()
+
+
+KNOWN = [("lp_maximize", "SUCCESS", (375, 250), 1e-6),
+         ("quartic", "SUCCESS", (1,), 1e-6),
+         ("wachter_biegler", "SUCCESS", (1, 0, 0.5), 1e-6),
+         ("qp_inequality_2d", "SUCCESS", (3 + 1 / 3, 1 + 2 / 3), 1e-6),
+         ("rosenbrock_disk", "SUCCESS", (1, 1), 1e-3),
+         ("conflicting_bounds", "GLOBALLY_INFEASIBLE", None, 0),
+         ("locally_infeasible_ineq", "LOCALLY_INFEASIBLE", None, 0),
+         ("nonfinite_ineq", "NONFINITE_INITIAL_GUESS", None, 0),
+         ("nonfinite_ineq_jacobian", "NONFINITE_INITIAL_GUESS", None, 0)]
+
+
+@pytest.mark.parametrize("name,status,expect,tol", KNOWN)
+def test_reference_known_answers_on_gpu(name, status, expect, tol):
+    """The reference's own solution-level tests (test/src/optimization/*),
+    through slp::Problem::solve on the device."""
+    P = sb.Problem(name, 0, -0.5, 1.2)
+    st = P.solve()
+    assert sb.EXIT_STATUS[st] == status
+    if expect is not None:
+        np.testing.assert_allclose(P.solution()[0], expect, atol=tol)
+    P.close()
+
+
+def test_flywheel_trajectory_matches_oracle():
+    """Well-conditioned problem: same decisions and iterates to 1e-10 along the
+    whole solve (same permutation on both sides)."""
+    N = 50
+    P = sb.Problem("flywheel", N)
+    st = P.solve(keep_iterates=True)
+    tr = P.trace()
+    D = P.open_device(); D.analyze(); perm = D.permutation(); P.close_device()
+    O = OracleProblem("flywheel", N)
+    so = O.solve(perm=perm, force_sparse=1)
+    to = O.trace()
+    assert sb.EXIT_STATUS[st] == EXIT_STATUS[so] == "SUCCESS"
+    assert len(tr) == len(to)
+    for a, b in zip(tr, to):
+        assert a.factorizations == b.factorizations and a.trials == b.trials
+        assert a.delta == b.delta and a.mu == b.mu
+        assert rel(a.x, b.x) < 1e-10 and rel(a.z, b.z) < 1e-10
+        assert rel(a.y, b.y) < 1e-10
+    g = np.load(os.path.join(GOLDEN, "solve_flywheel_50.npz"))
+    np.testing.assert_allclose(P.solution()[0], g["x"], atol=1e-7)
+    P.close(); O.close()
+
+
+def test_cart_pole_first_iterations_match_oracle():
+    """Cart-pole: identical regularisation / line-search decisions and
+    iterates within 1e-5 over the first 12 iterations. (Beyond that the
+    reference algorithm amplifies rounding differences of ANY two
+    implementations — DESIGN.md, 'Parity'.)"""
+    N = 100
+    P = sb.Problem("cart_pole", N)
+    P.solve(max_iterations=12, keep_iterates=True)
+    tr = P.trace()
+    D = P.open_device(); D.analyze(); perm = D.permutation(); P.close_device()
+    O = OracleProblem("cart_pole", N)
+    O.solve(max_iterations=12, perm=perm, force_sparse=1)
+    to = O.trace()
+    assert len(tr) == len(to) == 12
+    for a, b in zip(tr, to):
+        assert a.factorizations == b.factorizations and a.trials == b.trials
+        assert a.delta == b.delta
+        assert a.alpha == pytest.approx(b.alpha, rel=1e-3)
+        assert rel(a.x, b.x) < 1e-5 and rel(a.y, b.y) < 1e-4
+    assert rel(tr[0].x, to[0].x) < 1e-6
+    P.close(); O.close()
+
+
+def test_cart_pole_solves_to_the_reference_test_bar():
+    """cart_pole_problem_test.cpp:87-124 through the device path (N = 60)."""
+    N, T = 60, 5.0
+    P = sb.Problem("cart_pole", N)
+    assert sb.EXIT_STATUS[P.solve()] == "SUCCESS"
+    x, *_ = P.solution()
+    X = x[:4 * (N + 1)].reshape(4, N + 1)
+    U = x[4 * (N + 1):]
+    np.testing.assert_allclose(X[:, 0], 0, atol=1e-8)
+    np.testing.assert_allclose(X[:, N], (1, np.pi, 0, 0), atol=1e-8)
+    assert (X[0] >= -1e-9).all() and (X[0] <= 2 + 1e-9).all()
+    assert (np.abs(U) <= 20 + 1e-9).all()
+
+    def f(s, u):
+        m_c, m_p, l, g = 5.0, 0.5, 0.5, 9.806
+        th, xd, thd = s[1], s[2], s[3]
+        M = np.array([[m_c + m_p, m_p * l * np.cos(th)],
+                      [m_p * l * np.cos(th), m_p * l * l]])
+        rhs = np.array([m_p * l * thd * thd * np.sin(th) + u,
+                        -m_p * g * l * np.sin(th)])
+        return np.concatenate([[xd, thd], np.linalg.solve(M, rhs)])
+
+    h = T / N
+    for k in range(N):
+        s, u = X[:, k], U[k]
+        k1 = f(s, u); k2 = f(s + h / 2 * k1, u)
+        k3 = f(s + h / 2 * k2, u); k4 = f(s + h * k3, u)
+        np.testing.assert_allclose(X[:, k + 1], s + h / 6 * (k1 + 2 * k2 + 2 * k3 + k4),
+                                   atol=1e-8)
+    P.close()
+
+
+def test_full_size_properties_n5000():
+    """BASELINE.json's full size (cart-pole N = 5000): size-independent
+    properties — the Newton system the device solved has a small residual, the
+    inertia is (n, m_e, 0), and the step satisfies the linearised constraints."""
+    N = 5000
+    P = sb.Problem("cart_pole", N)
+    D = P.open_device()
+    n, me, mi, dim = P.n, P.me, P.mi, P.n + P.me
+    assert (n, me, mi) == (25004, 20008, 20002)
+    rng = np.random.default_rng(0)
+    x = P.initial_guess() + 0.01 * rng.standard_normal(n)
+    s = 0.5 + np.abs(rng.standard_normal(mi)); z = 0.5 + np.abs(rng.standard_normal(mi))
+    y = 0.1 * rng.standard_normal(me)
+    D.set_iterate(x, s, y, z)
+    info = D.eval_current(1)
+    assert info.finite == 127
+    st = D.analyze()
+    assert st.n_levels <= 20 and st.max_front <= 40
+    fi = D.factor(1.0, 1e-6, True)
+    assert (fi.n_pos, fi.n_neg, fi.n_zero, fi.zero_pivot) == (n, me, 0, 0)
+    D.solve(0.1, 0.99)
+    _, _, cp, ri = D.pattern(-1)
+    kv = D.download(sb.ARR_KKT_VAL)
+    K = sp.csc_matrix((kv, ri, cp), shape=(dim, dim))
+    K = K + sp.tril(K, -1).T + sp.diags(np.concatenate([np.ones(n), -1e-6 * np.ones(me)]))
+    sol = np.concatenate([D.download(sb.ARR_P_X), -D.download(sb.ARR_P_Y)])
+    rhs = D.download(sb.ARR_RHS)
+    assert np.abs(K @ sol - rhs).max() <= 1e-7 * np.abs(rhs).max()
+    # linearised equality constraints: A_e p_x + γ p_y-ish ≈ −c_e
+    _, _, acp, ari = D.pattern(sb.OUT_A_E)
+    Ae = sp.csc_matrix((D.download(sb.ARR_A_E_VAL), ari, acp), shape=(me, n))
+    lin = Ae @ sol[:n] - 1e-6 * sol[n:] + D.download(sb.ARR_C_E)
+    assert np.abs(lin).max() <= 1e-7 * max(1.0, np.abs(rhs).max())
+    c = D.counters()
+    assert c.kernel_launches > 0 and c.n_program_classes <= 12
+    P.close_device(); P.close()
