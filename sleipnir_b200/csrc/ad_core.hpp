@@ -26,6 +26,14 @@
 #define SLPB_HD inline
 #endif
 
+// Load that bypasses the (non-coherent) L1: for data another SM wrote earlier
+// in the SAME kernel launch (dependency-driven tree kernels).
+#if defined(__CUDA_ARCH__)
+#define SLPB_LDCG(ptr) __ldcg(ptr)
+#else
+#define SLPB_LDCG(ptr) (*(ptr))
+#endif
+
 namespace slpb {
 
 SLPB_HD double ad_op_value(uint8_t op, double l, double r) {

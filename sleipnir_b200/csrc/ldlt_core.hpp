@@ -78,9 +78,9 @@ SLPB_HD void ldlt_factor_front(int tid, int s, const SymbolicView& S,
     const int mc = S.front_dim[c] - (S.super_first[c + 1] - S.super_first[c]);
     const double* U = updates + S.update_ptr[c];
     const int32_t* rel = S.rel_idx + S.rel_ptr[c];
-    for (int e = tid; e < mc * mc; e += NT) {
-      const int i = e % mc, j = e / mc;
-      if (i >= j) W[rel[i] + rel[j] * F] += U[i + j * mc];
+    for (int j = 0; j < mc; ++j) {
+      const int cj = rel[j] * F;
+      for (int i = j + tid; i < mc; i += NT) W[rel[i] + cj] += SLPB_LDCG(U + i + j * mc);
     }
     sync();
   }
@@ -105,10 +105,9 @@ SLPB_HD void ldlt_factor_front(int tid, int s, const SymbolicView& S,
     for (int i = k + 1 + tid; i < F; i += NT) lcol[i] = W[i + k * F] / d;
     sync();
     // W(i,j) −= l_ik · (d·l_jk) for k < j ≤ i, with d·l_jk still in column k
-    const int rem = F - k - 1;
-    for (int e = tid; e < rem * rem; e += NT) {
-      const int i = k + 1 + e % rem, j = k + 1 + e / rem;
-      if (i >= j) W[i + j * F] -= lcol[i] * W[j + k * F];
+    for (int j = k + 1; j < F; ++j) {
+      const double wjk = W[j + k * F];
+      for (int i = j + tid; i < F; i += NT) W[i + j * F] -= lcol[i] * wjk;
     }
     sync();
     for (int i = k + 1 + tid; i < F; i += NT) W[i + k * F] = lcol[i];
@@ -118,9 +117,10 @@ SLPB_HD void ldlt_factor_front(int tid, int s, const SymbolicView& S,
   double* P = panels + S.panel_ptr[s];
   for (int e = tid; e < F * np; e += NT) P[e] = W[e];
   double* U = updates + S.update_ptr[s];
-  for (int e = tid; e < m * m; e += NT) {
-    const int i = e % m, j = e / m;
-    U[e] = i >= j ? W[(np + i) + (np + j) * F] : 0.0;
+  for (int j = 0; j < m; ++j) {
+    for (int i = j + tid; i < m; i += NT) {
+      U[i + j * m] = W[(np + i) + (np + j) * F];
+    }
   }
   if (tid == 0) {
     local_stats[0] = pos;
@@ -157,7 +157,7 @@ SLPB_HD void ldlt_forward_front(int tid, int s, const SymbolicView& S,
     const int mc = S.front_dim[c] - (S.super_first[c + 1] - S.super_first[c]);
     const double* u = uvecs + S.rel_ptr[c];
     const int32_t* rel = S.rel_idx + S.rel_ptr[c];
-    for (int i = tid; i < mc; i += NT) w[rel[i]] += u[i];
+    for (int i = tid; i < mc; i += NT) w[rel[i]] += SLPB_LDCG(u + i);
     sync();
   }
   const double* P = panels + S.panel_ptr[s];
@@ -188,17 +188,22 @@ SLPB_HD void ldlt_backward_front(int tid, int s, const SymbolicView& S,
   const int np = S.super_first[s + 1] - c0;
   const int32_t* rows = S.rows_idx + S.rows_ptr[s];
   for (int i = tid; i < F; i += NT) {
-    w[i] = i < np ? x_perm[c0 + i] / D[c0 + i] : x_perm[rows[i]];
+    w[i] = i < np ? SLPB_LDCG(x_perm + c0 + i) / D[c0 + i]
+                  : SLPB_LDCG(x_perm + rows[i]);
   }
   sync();
   const double* P = panels + S.panel_ptr[s];
-  for (int k = np - 1; k >= 0; --k) {
-    // w[k] −= Σ_{i>k} L(i,k) w[i]; a serial dot keeps the order fixed
-    if (tid == 0) {
-      double acc = w[k];
-      for (int i = k + 1; i < F; ++i) acc -= P[i + k * F] * w[i];
-      w[k] = acc;
-    }
+  // t = z − L21ᵀ x_below: one own column per thread
+  for (int k = tid; k < np; k += NT) {
+    double acc = w[k];
+    for (int i = np; i < F; ++i) acc -= P[i + k * F] * w[i];
+    w[k] = acc;
+  }
+  sync();
+  // L11ᵀ x = t, column-oriented: once x_i is final, every k < i takes its term
+  for (int i = np - 1; i >= 1; --i) {
+    const double xi = w[i];
+    for (int k = tid; k < i; k += NT) w[k] -= P[i + k * F] * xi;
     sync();
   }
   for (int i = tid; i < np; i += NT) x_perm[c0 + i] = w[i];

@@ -1,0 +1,335 @@
+// Warp-specialised front kernels for fronts of order ≤ 32 (device only).
+//
+// Same assembly and the same per-entry arithmetic as the generic bodies in
+// ldlt_core.hpp — W(i,j) −= l_ik · w_jk for k ascending, l_ik = w_ik / d_k — so
+// both produce identical bits. What changes is the mapping: the trailing
+// triangle of every pivot is spread over all 32 lanes element by element (a
+// fixed table turns a packed index into (row, col)), the pivot column is staged
+// once per pivot in shared memory, global loads are batched ahead of the
+// shared-memory read-modify-writes, and all per-front metadata comes from one
+// packed record instead of a chain of dependent index loads.
+#pragma once
+
+#include "ldlt_core.hpp"
+
+namespace slpb {
+
+/// Everything a warp needs to know about a front, in one 64-byte record.
+struct alignas(16) FrontMeta {
+  int32_t F, np, c0, n_child;
+  int32_t child_begin, asm_begin, asm_end, rel_off;
+  int64_t panel_off, update_off;
+  int64_t rows_off;
+  int32_t parent, pad;
+};
+static_assert(sizeof(FrontMeta) == 64, "FrontMeta must stay one 64-byte line");
+
+__device__ __forceinline__ FrontMeta load_front_meta(const FrontMeta* p) {
+  // four independent 16-byte loads
+  FrontMeta m;
+  const int4* src = reinterpret_cast<const int4*>(p);
+  int4* dst = reinterpret_cast<int4*>(&m);
+  dst[0] = __ldg(src + 0);
+  dst[1] = __ldg(src + 1);
+  dst[2] = __ldg(src + 2);
+  dst[3] = __ldg(src + 3);
+  return m;
+}
+
+/// (row, col) of packed lower-triangle index e, row-major: e = a(a+1)/2 + b.
+/// The enumeration is the same for every triangle size (prefix property), so
+/// one table of 528 entries serves every pivot of every front of order ≤ 32.
+constexpr int kTriEntries = 33 * 32 / 2;
+
+__device__ __forceinline__ void init_tri_table(uchar2* tri) {
+  for (int e = threadIdx.x; e < kTriEntries; e += blockDim.x) {
+    int a = static_cast<int>((sqrtf(8.0f * e + 1.0f) - 1.0f) * 0.5f);
+    while ((a + 1) * (a + 2) / 2 <= e) ++a;
+    while (a * (a + 1) / 2 > e) --a;
+    tri[e] = make_uchar2(static_cast<unsigned char>(a),
+                         static_cast<unsigned char>(e - a * (a + 1) / 2));
+  }
+}
+
+/// What a parent front pre-loads about one child before it starts waiting.
+struct ChildPre {
+  int mc;            // order of the child's update matrix
+  int ri;            // target row/col of this lane's row (lane < mc)
+  int rel_off;       // child's slice of the update-vector storage
+  const double* U;   // child's update matrix
+};
+
+__device__ __forceinline__ ChildPre preload_child(
+    int lane, int c, const FrontMeta* __restrict__ metas,
+    const int32_t* __restrict__ rel_idx, const double* updates) {
+  const FrontMeta cm = load_front_meta(metas + c);
+  ChildPre p;
+  p.mc = cm.F - cm.np;
+  p.ri = lane < p.mc ? rel_idx[cm.rel_off + lane] : 0;
+  p.rel_off = cm.rel_off;
+  p.U = updates + cm.update_off;
+  return p;
+}
+
+constexpr int kPreChildren = 4;  // children whose metadata is pre-loaded
+
+/// Spins (relaxed polls, no L1 invalidation per poll) until *p ≥ need, then
+/// acquires once.
+__device__ __forceinline__ void wait_children(const int* p, int need) {
+  if (need > 0) {
+    int v;
+    unsigned ns = 32;
+    for (;;) {
+      asm volatile("ld.relaxed.gpu.global.s32 %0, [%1];" : "=r"(v) : "l"(p) : "memory");
+      if (v >= need) break;
+      __nanosleep(ns);
+      if (ns < 256) ns <<= 1;
+    }
+  }
+  __threadfence();
+}
+
+/// W: F×F column-major in shared memory; col: 64 doubles of shared scratch
+/// (scaled pivot column in [0,32), unscaled in [32,64)). `dep` is polled by
+/// lane 0 AFTER everything that does not depend on the children is done.
+__device__ __forceinline__ void ldlt_factor_front_warp(
+    int lane, const FrontMeta& fm, const FrontMeta* __restrict__ metas,
+    const int32_t* __restrict__ child_idx, const int32_t* __restrict__ rel_idx,
+    const int32_t* __restrict__ asm_src, const int32_t* __restrict__ asm_dst,
+    const uint8_t* __restrict__ col_is_primal,
+    const double* __restrict__ Kval, double delta, double gamma,
+    double* __restrict__ panels, double* updates, double* __restrict__ D,
+    double* __restrict__ W, double* __restrict__ col,
+    const uchar2* __restrict__ tri, const int* dep, int* local_stats,
+    unsigned long long* stamp = nullptr) {
+  const int F = fm.F, np = fm.np, c0 = fm.c0, m = F - np;
+
+  // ---- child-independent part: own KKT entries, δ/γ, child metadata ---------
+  for (int i = lane; i < F * F; i += 32) W[i] = 0.0;
+  __syncwarp();
+  for (int k = fm.asm_begin + lane; k < fm.asm_end; k += 32) {
+    W[asm_dst[k]] = Kval[asm_src[k]];
+  }
+  ChildPre pre[kPreChildren];
+#pragma unroll
+  for (int q = 0; q < kPreChildren; ++q) {
+    if (q < fm.n_child) {
+      pre[q] = preload_child(lane, child_idx[fm.child_begin + q], metas,
+                             rel_idx, updates);
+    }
+  }
+  __syncwarp();
+  if (lane < np) W[lane + lane * F] += col_is_primal[c0 + lane] ? delta : -gamma;
+
+  // ---- wait for the children, then extend-add their update matrices ---------
+  if (lane == 0) {
+    wait_children(dep, fm.n_child);
+    if (stamp) {
+      unsigned long long t;
+      asm volatile("mov.u64 %0, %globaltimer;" : "=l"(t));
+      *stamp = t;
+    }
+  }
+  __syncwarp();
+  for (int ck = 0; ck < fm.n_child; ++ck) {
+    ChildPre cp;
+    if (ck < kPreChildren) {
+      // static indexing keeps pre[] in registers
+      cp = pre[0];
+#pragma unroll
+      for (int q = 1; q < kPreChildren; ++q) {
+        if (ck == q) cp = pre[q];
+      }
+    } else {
+      cp = preload_child(lane, child_idx[fm.child_begin + ck], metas, rel_idx,
+                         updates);
+    }
+    const int mc = cp.mc, ri = cp.ri;
+    const double* U = cp.U;
+    for (int j0 = 0; j0 < mc; j0 += 8) {
+      double u[8];
+#pragma unroll
+      for (int q = 0; q < 8; ++q) {
+        const int j = j0 + q;
+        u[q] = (j < mc && j <= lane && lane < mc) ? __ldcg(U + lane + j * mc)
+                                                  : 0.0;
+      }
+#pragma unroll
+      for (int q = 0; q < 8; ++q) {
+        const int j = j0 + q;
+        const int rj = __shfl_sync(0xffffffffu, ri, j & 31);
+        if (j < mc && j <= lane && lane < mc) W[ri + rj * F] += u[q];
+      }
+    }
+    __syncwarp();
+  }
+
+  // ---- elimination of the own columns ----------------------------------------
+  int pos = 0, neg = 0, zero = 0, zpiv = 0;
+  double min_abs = INFINITY;
+  double* lcol = col;        // l_ik
+  double* wcol = col + 32;   // d·l_ik (unscaled column)
+  for (int k = 0; k < np; ++k) {
+    const double d = W[k + k * F];
+    if (lane == 0) {
+      const double eps = 2.220446049250313e-16;
+      if (d > eps) {
+        ++pos;
+      } else if (d < -eps) {
+        ++neg;
+      } else {
+        ++zero;
+      }
+      if (d == 0.0) zpiv = 1;
+      min_abs = fmin(min_abs, fabs(d));
+      D[c0 + k] = d;
+    }
+    if (lane > k && lane < F) {
+      const double w = W[lane + k * F];
+      wcol[lane] = w;
+      lcol[lane] = w / d;
+    }
+    __syncwarp();
+    // trailing triangle of order r, spread element-wise over the lanes
+    const int r = F - k - 1;
+    const int T = r * (r + 1) / 2;
+    const int o = k + 1;
+    for (int e0 = lane; e0 < T; e0 += 128) {
+      int idx[4];
+      double wv[4], lv[4], cv[4];
+#pragma unroll
+      for (int q = 0; q < 4; ++q) {
+        const int e = e0 + 32 * q;
+        const bool on = e < T;
+        const uchar2 ab = tri[on ? e : 0];
+        const int i = o + ab.x, j = o + ab.y;
+        idx[q] = on ? i + j * F : -1;
+        lv[q] = lcol[i];
+        cv[q] = wcol[j];
+        wv[q] = on ? W[i + j * F] : 0.0;
+      }
+#pragma unroll
+      for (int q = 0; q < 4; ++q) {
+        if (idx[q] >= 0) W[idx[q]] = wv[q] - lv[q] * cv[q];
+      }
+    }
+    __syncwarp();
+    if (lane > k && lane < F) W[lane + k * F] = lcol[lane];
+  }
+  __syncwarp();
+
+  // ---- L panel (F × np) and update matrix (m × m, lower) ----------------------
+  double* P = panels + fm.panel_off;
+  for (int e = lane; e < F * np; e += 32) P[e] = W[e];
+  double* U = updates + fm.update_off;
+  for (int j = 0; j < m; ++j) {
+    const int i = j + lane;
+    if (i < m) U[i + j * m] = W[(np + i) + (np + j) * F];
+  }
+  if (lane == 0) {
+    local_stats[0] = pos;
+    local_stats[1] = neg;
+    local_stats[2] = zero;
+    local_stats[3] = zpiv;
+    const unsigned long long bits = __double_as_longlong(min_abs);
+    local_stats[4] = static_cast<int>(bits & 0xffffffffull);
+    local_stats[5] = static_cast<int>(bits >> 32);
+  }
+}
+
+/// Forward substitution on a front (same arithmetic as ldlt_forward_front).
+/// Lane i keeps w_i and its row of L in registers; everything that does not
+/// depend on the children is loaded before the wait.
+__device__ __forceinline__ void ldlt_forward_front_warp(
+    int lane, const FrontMeta& fm, const FrontMeta* __restrict__ metas,
+    const int32_t* __restrict__ child_idx, const int32_t* __restrict__ rel_idx,
+    const int32_t* __restrict__ perm, const double* __restrict__ panels,
+    const double* __restrict__ rhs, double* x_perm, double* uvecs,
+    double* __restrict__ w, const int* dep) {
+  const int F = fm.F, np = fm.np, c0 = fm.c0;
+  const double* P = panels + fm.panel_off;
+  double Lrow[32];  // L(lane, k), k < lane
+#pragma unroll
+  for (int k = 0; k < 32; ++k) {
+    Lrow[k] = (k < np && lane > k && lane < F) ? P[lane + k * F] : 0.0;
+  }
+  if (lane < F) w[lane] = lane < np ? rhs[perm[c0 + lane]] : 0.0;
+  ChildPre pre[kPreChildren];
+#pragma unroll
+  for (int q = 0; q < kPreChildren; ++q) {
+    if (q < fm.n_child) {
+      pre[q] = preload_child(lane, child_idx[fm.child_begin + q], metas,
+                             rel_idx, nullptr);
+    }
+  }
+  if (lane == 0) wait_children(dep, fm.n_child);
+  __syncwarp();
+  for (int ck = 0; ck < fm.n_child; ++ck) {
+    ChildPre cp;
+    if (ck < kPreChildren) {
+      cp = pre[0];
+#pragma unroll
+      for (int q = 1; q < kPreChildren; ++q) {
+        if (ck == q) cp = pre[q];
+      }
+    } else {
+      cp = preload_child(lane, child_idx[fm.child_begin + ck], metas, rel_idx,
+                         nullptr);
+    }
+    if (lane < cp.mc) w[cp.ri] += __ldcg(uvecs + cp.rel_off + lane);
+    __syncwarp();
+  }
+  double wi = lane < F ? w[lane] : 0.0;
+#pragma unroll
+  for (int k = 0; k < 32; ++k) {
+    if (k >= np) break;
+    const double yk = __shfl_sync(0xffffffffu, wi, k);
+    if (lane > k) wi -= Lrow[k] * yk;
+  }
+  if (lane < np) {
+    x_perm[c0 + lane] = wi;
+  } else if (lane < F) {
+    uvecs[fm.rel_off + (lane - np)] = wi;
+  }
+}
+
+/// Backward substitution on a front (same arithmetic as ldlt_backward_front).
+/// Lane k keeps column k of L in registers, loaded before the wait.
+__device__ __forceinline__ void ldlt_backward_front_warp(
+    int lane, const FrontMeta& fm, const int32_t* __restrict__ rows_idx,
+    const double* __restrict__ panels, const double* __restrict__ D,
+    double* x_perm, const int* dep) {
+  const int F = fm.F, np = fm.np, c0 = fm.c0;
+  const double* P = panels + fm.panel_off;
+  double Lcol[32];  // L(i, lane), i > lane
+#pragma unroll
+  for (int i = 0; i < 32; ++i) {
+    Lcol[i] = (lane < np && i > lane && i < F) ? P[i + lane * F] : 0.0;
+  }
+  const double dinv_src = lane < np ? D[c0 + lane] : 1.0;
+  const int row = (lane >= np && lane < F) ? rows_idx[fm.rows_off + lane] : 0;
+  if (lane == 0) wait_children(dep, 1);
+  __syncwarp();
+  double wi = 0.0;
+  if (lane < np) {
+    wi = __ldcg(x_perm + c0 + lane) / dinv_src;
+  } else if (lane < F) {
+    wi = __ldcg(x_perm + row);
+  }
+  // t_k = z_k − Σ_{i ≥ np} L(i,k) x_i  (ascending i), then L11ᵀ x = t
+#pragma unroll
+  for (int i = 0; i < 32; ++i) {
+    if (i >= F) break;
+    const double xi = __shfl_sync(0xffffffffu, wi, i);
+    if (i >= np && lane < np) wi -= Lcol[i] * xi;
+  }
+#pragma unroll
+  for (int i = 31; i >= 1; --i) {
+    if (i >= np) continue;
+    const double xi = __shfl_sync(0xffffffffu, wi, i);
+    if (lane < i) wi -= Lcol[i] * xi;
+  }
+  if (lane < np) x_perm[c0 + lane] = wi;
+}
+
+}  // namespace slpb

@@ -19,6 +19,7 @@
 #include <algorithm>
 #include <cmath>
 #include <cstdio>
+#include <cstdlib>
 #include <cstring>
 #include <memory>
 #include <string>
@@ -28,6 +29,7 @@
 #include "internal.hpp"
 #include "kkt_core.hpp"
 #include "ldlt_core.hpp"
+#include "ldlt_warp.cuh"
 #include "slpb.h"
 
 namespace slpb {
@@ -71,7 +73,11 @@ struct DevProgramSet {
   DevBuf<uint32_t> blob, bindings;
   DevBuf<int64_t> prog_offset, cluster_bind;
   DevBuf<int32_t> cluster_prog;
-  int n_clusters = 0, warps_per_block = 1, smem_per_warp = 0;
+  // Warp tasks: every warp evaluates up to 32/G clusters of ONE program in
+  // lockstep, G lanes per cluster. task = {first, count, G, scratch doubles}
+  DevBuf<int32_t> task;           // 4 ints per warp
+  DevBuf<int32_t> cluster_order;  // clusters sorted by program
+  int n_clusters = 0, n_tasks = 0, warps_per_block = 1, smem_per_warp = 0;
 };
 
 struct DevGather {
@@ -82,7 +88,8 @@ struct DevGather {
 
 constexpr int kResultDoubles = 64;
 constexpr int kLongGather = 48;  // sources above which a block reduces an entry
-constexpr int kReduceThreads = 512;
+constexpr int kReduceThreads = 256;
+constexpr int kReduceBlocks = 148;  // one per SM
 
 }  // namespace slpb
 
@@ -124,10 +131,17 @@ struct slpb_solver {
   DevBuf<uint8_t> sy_col_is_primal;
   DevBuf<double> panels, updates, D, uvecs, xperm;
   DevBuf<int32_t> fstats;  // FactorStats as 6 ints
+  DevBuf<int32_t> sy_super_parent, sy_nchild, tree_sync;
+  DevBuf<FrontMeta> sy_metas;
+  DevBuf<unsigned long long> tree_debug;
+  bool use_tree = false;
+  int tree_blocks = 0, tree_smem_doubles = 0;
   SymbolicView sview{};
   // device: steps
   DevBuf<double> px, ps, py, pz, spx, sps, spy, spz, ce_soc, cis_soc;
   // results
+  DevBuf<double> red_partials;
+  DevBuf<unsigned int> red_counter;
   DevBuf<double> d_results;
   double* h_results = nullptr;  // pinned
   // timing
@@ -164,26 +178,47 @@ struct BlockSync {
   __device__ __forceinline__ void operator()() const { __syncthreads(); }
 };
 
-/// One warp per cluster; values and adjoints of the cluster live in shared
-/// memory (smem_per_warp bytes each). Replaces update_values +
-/// append_triplets (expression_graph.hpp:85-153) for all rows of a cluster.
+struct WarpSyncMask {
+  unsigned mask;
+  __device__ __forceinline__ void operator()() const { __syncwarp(mask); }
+};
+
+/// Each warp evaluates up to 32/G clusters of one program in lockstep, G lanes
+/// per cluster; values and adjoints of every cluster live in shared memory.
+/// Replaces update_values + append_triplets (expression_graph.hpp:85-153) for
+/// all rows of a cluster.
 __global__ void k_ad_sweep(const uint32_t* __restrict__ blob,
                            const int64_t* __restrict__ prog_offset,
                            const int32_t* __restrict__ cluster_prog,
                            const int64_t* __restrict__ cluster_bind,
                            const uint32_t* __restrict__ bindings,
-                           int n_clusters, int smem_doubles_per_warp,
+                           const int32_t* __restrict__ task,
+                           const int32_t* __restrict__ cluster_order,
+                           int n_tasks, int smem_doubles_per_warp,
                            const double* __restrict__ leaf,
                            double* __restrict__ stage) {
   extern __shared__ double smem[];
   const int warp = threadIdx.x >> 5;
   const int lane = threadIdx.x & 31;
-  const int c = blockIdx.x * (blockDim.x >> 5) + warp;
-  if (c >= n_clusters) return;
+  const int w = blockIdx.x * (blockDim.x >> 5) + warp;
+  if (w >= n_tasks) return;
+  const int first = task[4 * w + 0], count = task[4 * w + 1];
+  const int G = task[4 * w + 2], per_cluster = task[4 * w + 3];
+  const int group = lane / G, sub = lane % G;
+  const unsigned mask = __ballot_sync(0xffffffffu, group < count);
+  if (group >= count) return;
+  const int c = cluster_order[first + group];
   const uint32_t* P = blob + prog_offset[cluster_prog[c]];
   const uint32_t* B = bindings + cluster_bind[c];
-  double* scratch = smem + size_t(warp) * smem_doubles_per_warp;
-  ad_run_cluster<32>(lane, P, B, leaf, stage, scratch, WarpSync{});
+  double* scratch =
+      smem + size_t(warp) * smem_doubles_per_warp + size_t(group) * per_cluster;
+  const WarpSyncMask sync{mask};
+  switch (G) {
+    case 4: ad_run_cluster<4>(sub, P, B, leaf, stage, scratch, sync); break;
+    case 8: ad_run_cluster<8>(sub, P, B, leaf, stage, scratch, sync); break;
+    case 16: ad_run_cluster<16>(sub, P, B, leaf, stage, scratch, sync); break;
+    default: ad_run_cluster<32>(sub, P, B, leaf, stage, scratch, sync); break;
+  }
 }
 
 __global__ void k_gather(const int32_t* __restrict__ ptr,
@@ -248,10 +283,20 @@ __global__ void k_prepare_leaves(const double* __restrict__ x,
 }
 
 // ---------------------------------------------------------------------------
-// kernels: reductions (single block; sizes here are 1e4..1e5)
+// kernels: reductions. Grid-wide, two-phase and deterministic: every block
+// reduces its grid-stride slice in a fixed tree, writes one partial per
+// quantity, and the block that takes the last ticket combines the partials in
+// a fixed order and finalises the result (no floating-point atomics anywhere).
 // ---------------------------------------------------------------------------
 
 enum RedOp { RED_SUM = 0, RED_MAX = 1, RED_MIN = 2 };
+
+__device__ __forceinline__ double red_combine(int op, double a, double b) {
+  return op == RED_SUM ? a + b : (op == RED_MAX ? fmax(a, b) : fmin(a, b));
+}
+__device__ __forceinline__ double red_identity(int op) {
+  return op == RED_SUM ? 0.0 : (op == RED_MAX ? -INFINITY : INFINITY);
+}
 
 template <int NV>
 __device__ void block_reduce(double (&v)[NV], const int (&op)[NV],
@@ -262,8 +307,7 @@ __device__ void block_reduce(double (&v)[NV], const int (&op)[NV],
   for (int q = 0; q < NV; ++q) {
     double a = v[q];
     for (int o = 16; o > 0; o >>= 1) {
-      const double b = __shfl_down_sync(0xffffffffu, a, o);
-      a = op[q] == RED_SUM ? a + b : (op[q] == RED_MAX ? fmax(a, b) : fmin(a, b));
+      a = red_combine(op[q], a, __shfl_down_sync(0xffffffffu, a, o));
     }
     if (lane == 0) red[q][warp] = a;
   }
@@ -272,13 +316,9 @@ __device__ void block_reduce(double (&v)[NV], const int (&op)[NV],
     const int nw = blockDim.x >> 5;
 #pragma unroll
     for (int q = 0; q < NV; ++q) {
-      double a = lane < nw ? red[q][lane]
-                           : (op[q] == RED_SUM ? 0.0
-                              : op[q] == RED_MAX ? -INFINITY : INFINITY);
+      double a = lane < nw ? red[q][lane] : red_identity(op[q]);
       for (int o = 16; o > 0; o >>= 1) {
-        const double b = __shfl_down_sync(0xffffffffu, a, o);
-        a = op[q] == RED_SUM ? a + b
-                             : (op[q] == RED_MAX ? fmax(a, b) : fmin(a, b));
+        a = red_combine(op[q], a, __shfl_down_sync(0xffffffffu, a, o));
       }
       if (lane == 0) out[q] = a;
     }
@@ -286,32 +326,68 @@ __device__ void block_reduce(double (&v)[NV], const int (&op)[NV],
   __syncthreads();
 }
 
+/// Returns true in the (single) block that holds the grid-wide result in res.
+template <int NV>
+__device__ bool grid_reduce(double (&v)[NV], const int (&op)[NV],
+                            double* __restrict__ partials,
+                            unsigned int* __restrict__ counter, double* res) {
+  __shared__ bool is_last;
+  block_reduce<NV>(v, op, res);
+  if (gridDim.x == 1) return true;
+  if (threadIdx.x == 0) {
+    for (int q = 0; q < NV; ++q) partials[blockIdx.x * NV + q] = res[q];
+    __threadfence();
+    // atomicInc wraps to 0 at gridDim.x − 1: the counter resets itself
+    const unsigned int t = atomicInc(counter, gridDim.x - 1);
+    is_last = (t == gridDim.x - 1);
+  }
+  __syncthreads();
+  if (!is_last) return false;
+  __threadfence();
+  double w[NV];
+#pragma unroll
+  for (int q = 0; q < NV; ++q) w[q] = red_identity(op[q]);
+  for (int b = threadIdx.x; b < gridDim.x; b += blockDim.x) {
+#pragma unroll
+    for (int q = 0; q < NV; ++q) {
+      w[q] = red_combine(op[q], w[q], __ldcg(&partials[b * NV + q]));
+    }
+  }
+  block_reduce<NV>(w, op, res);
+  return true;
+}
+
+struct RedBuf {
+  double* partials;
+  unsigned int* counter;
+};
+
 /// slpb_point_info for a point: vals = [f | c_e | c_i], slack s.
 /// out: f, ce_l1, cis_l1, log_s_sum, finite bits (as double), ci_all_positive.
-__global__ void __launch_bounds__(kReduceThreads) k_point_info(const double* __restrict__ vals,
-                             const double* __restrict__ s, int me, int mi,
-                             double* __restrict__ out) {
-  double v[5] = {0.0, 0.0, 0.0, 0.0, 0.0};
-  // v0 ce_l1, v1 cis_l1, v2 log sum, v3 nonfinite count c_e, v4 nonfinite c_i
-  double nonpos = 0.0;
+__global__ void __launch_bounds__(kReduceThreads)
+k_point_info(const double* __restrict__ vals, const double* __restrict__ s,
+             int me, int mi, RedBuf rb, double* __restrict__ out) {
+  // 0 ce_l1, 1 cis_l1, 2 log sum, 3 nonfinite c_e, 4 nonfinite c_i, 5 c_i ≤ 0
+  double w[6] = {0.0, 0.0, 0.0, 0.0, 0.0, 0.0};
   const double* c_e = vals + 1;
   const double* c_i = vals + 1 + me;
-  for (int i = threadIdx.x; i < me; i += blockDim.x) {
+  const int stride = gridDim.x * blockDim.x;
+  const int t0 = blockIdx.x * blockDim.x + threadIdx.x;
+  for (int i = t0; i < me; i += stride) {
     const double c = c_e[i];
-    v[0] += fabs(c);
-    if (!isfinite(c)) v[3] += 1.0;
+    w[0] += fabs(c);
+    if (!isfinite(c)) w[3] += 1.0;
   }
-  for (int i = threadIdx.x; i < mi; i += blockDim.x) {
+  for (int i = t0; i < mi; i += stride) {
     const double c = c_i[i];
-    v[1] += fabs(c - s[i]);
-    v[2] += log(s[i]);
-    if (!isfinite(c)) v[4] += 1.0;
-    if (!(c > 0.0)) nonpos += 1.0;
+    w[1] += fabs(c - s[i]);
+    w[2] += log(s[i]);
+    if (!isfinite(c)) w[4] += 1.0;
+    if (!(c > 0.0)) w[5] += 1.0;
   }
-  double w[6] = {v[0], v[1], v[2], v[3], v[4], nonpos};
   const int op[6] = {RED_SUM, RED_SUM, RED_SUM, RED_SUM, RED_SUM, RED_SUM};
   __shared__ double res[6];
-  block_reduce<6>(w, op, res);
+  if (!grid_reduce<6>(w, op, rb.partials, rb.counter, res)) return;
   if (threadIdx.x == 0) {
     const double f = vals[0];
     int bits = 0;
@@ -328,11 +404,14 @@ __global__ void __launch_bounds__(kReduceThreads) k_point_info(const double* __r
 }
 
 /// Finite-ness of the derivative arrays: out[0] = OR of G/A_E/A_I/H bits.
-__global__ void __launch_bounds__(kReduceThreads) k_deriv_finite(const double* __restrict__ dvals, int64_t off_ae,
-                               int64_t off_ai, int64_t off_h, int64_t total,
-                               double* __restrict__ out) {
+__global__ void __launch_bounds__(kReduceThreads)
+k_deriv_finite(const double* __restrict__ dvals, int64_t off_ae, int64_t off_ai,
+               int64_t off_h, int64_t total, RedBuf rb,
+               double* __restrict__ out) {
   double w[4] = {0.0, 0.0, 0.0, 0.0};
-  for (int64_t i = threadIdx.x; i < total; i += blockDim.x) {
+  const int64_t stride = int64_t(gridDim.x) * blockDim.x;
+  for (int64_t i = int64_t(blockIdx.x) * blockDim.x + threadIdx.x; i < total;
+       i += stride) {
     if (!isfinite(dvals[i])) {
       const int seg = i < off_ae ? 0 : (i < off_ai ? 1 : (i < off_h ? 2 : 3));
       w[seg] += 1.0;
@@ -340,7 +419,7 @@ __global__ void __launch_bounds__(kReduceThreads) k_deriv_finite(const double* _
   }
   const int op[4] = {RED_SUM, RED_SUM, RED_SUM, RED_SUM};
   __shared__ double res[4];
-  block_reduce<4>(w, op, res);
+  if (!grid_reduce<4>(w, op, rb.partials, rb.counter, res)) return;
   if (threadIdx.x == 0) {
     int bits = 0;
     if (res[0] == 0.0) bits |= SLPB_FINITE_G;
@@ -360,16 +439,13 @@ struct CscView {
 /// All reductions behind kkt_error / unscaled_kkt_error (kkt_error.hpp:92-251),
 /// is_locally_infeasible.hpp and the divergence guard, for one point.
 /// out layout = fields of slpb_kkt_stats in declaration order.
-__global__ void __launch_bounds__(kReduceThreads) k_kkt_stats(CscView Ae, CscView Ai, const double* __restrict__ g,
-                            const double* __restrict__ c_e,
-                            const double* __restrict__ c_i,
-                            const double* __restrict__ x,
-                            const double* __restrict__ s,
-                            const double* __restrict__ y,
-                            const double* __restrict__ z,
-                            const double* __restrict__ d_c, double d_f,
-                            double mu, int n, int me, int mi,
-                            double* __restrict__ out) {
+__global__ void __launch_bounds__(kReduceThreads)
+k_kkt_stats(CscView Ae, CscView Ai, const double* __restrict__ g,
+            const double* __restrict__ c_e, const double* __restrict__ c_i,
+            const double* __restrict__ x, const double* __restrict__ s,
+            const double* __restrict__ y, const double* __restrict__ z,
+            const double* __restrict__ d_c, double d_f, double mu, int n,
+            int me, int mi, RedBuf rb, double* __restrict__ out) {
   const double inv_d_f = 1.0 / d_f;
   // 0 r_inf 1 r_l1 2 y_l1 3 z_l1 4 sz_min 5 sz_max 6 sz_mu_l1 7 ce_inf 8 ce_l1
   // 9 cis_inf 10 cis_l1 11 u_r_inf 12 u_y_l1 13 u_z_l1 14 u_sz_min 15 u_sz_max
@@ -381,7 +457,9 @@ __global__ void __launch_bounds__(kReduceThreads) k_kkt_stats(CscView Ae, CscVie
   v[5] = -INFINITY;
   v[14] = INFINITY;
   v[15] = -INFINITY;
-  for (int c = threadIdx.x; c < n; c += blockDim.x) {
+  const int stride = gridDim.x * blockDim.x;
+  const int t0 = blockIdx.x * blockDim.x + threadIdx.x;
+  for (int c = t0; c < n; c += stride) {
     // scaled: g − A_eᵀy − A_iᵀz ; unscaled: g/d_f − (A_e/d_ce)ᵀ(d_ce y/d_f) − …
     double aty = 0.0, atz = 0.0, u_aty = 0.0, u_atz = 0.0, atc = 0.0,
            atcp = 0.0;
@@ -412,7 +490,7 @@ __global__ void __launch_bounds__(kReduceThreads) k_kkt_stats(CscView Ae, CscVie
     v[22] = fmax(v[22], fabs(xv));
     if (!isfinite(xv)) v[24] += 1.0;
   }
-  for (int i = threadIdx.x; i < me; i += blockDim.x) {
+  for (int i = t0; i < me; i += stride) {
     const double c = c_e[i], yv = y[i], dc = d_c[i];
     v[2] += fabs(yv);
     v[7] = fmax(v[7], fabs(c));
@@ -421,7 +499,7 @@ __global__ void __launch_bounds__(kReduceThreads) k_kkt_stats(CscView Ae, CscVie
     v[16] = fmax(v[16], fabs((1.0 / dc) * c));
     v[19] += c * c;
   }
-  for (int i = threadIdx.x; i < mi; i += blockDim.x) {
+  for (int i = t0; i < mi; i += stride) {
     const double c = c_i[i], sv = s[i], zv = z[i], dc = d_c[me + i];
     const double inv = 1.0 / dc;
     v[3] += fabs(zv);
@@ -448,7 +526,7 @@ __global__ void __launch_bounds__(kReduceThreads) k_kkt_stats(CscView Ae, CscVie
                       RED_SUM, RED_SUM, RED_SUM, RED_SUM, RED_MAX, RED_MAX,
                       RED_SUM};
   __shared__ double res[25];
-  block_reduce<25>(v, op, res);
+  if (!grid_reduce<25>(v, op, rb.partials, rb.counter, res)) return;
   if (threadIdx.x == 0) {
     for (int q = 0; q < 18; ++q) out[q] = res[q];
     out[18] = sqrt(res[18]);
@@ -588,6 +666,142 @@ __global__ void k_unpermute(const double* __restrict__ xperm,
 }
 
 // ---------------------------------------------------------------------------
+// kernels: multifrontal LDLᵀ as ONE dependency-driven launch (fronts ≤ 32).
+// One warp per front, front in shared memory, warp-level syncs only. Warps
+// draw fronts from an atomic ticket counter in level order (children always
+// hold smaller tickets, so whatever a warp waits for is already running or
+// done: no deadlock, no grid-wide barrier) and signal their parent through a
+// per-front counter in global memory.
+// ---------------------------------------------------------------------------
+
+constexpr int kTreeWarps = 8;
+
+__device__ __forceinline__ int ld_acquire_gpu(const int* p) {
+  int v;
+  asm volatile("ld.acquire.gpu.global.s32 %0, [%1];" : "=r"(v) : "l"(p) : "memory");
+  return v;
+}
+
+/// Spins until *p ≥ need, backing off so that idle warps do not flood the L2.
+__device__ __forceinline__ void wait_at_least(const int* p, int need) {
+  unsigned ns = 64;
+  while (ld_acquire_gpu(p) < need) {
+    __nanosleep(ns);
+    if (ns < 1024) ns <<= 1;
+  }
+}
+
+struct TreeView {
+  const int32_t* order;      // fronts by ascending level
+  const FrontMeta* metas;    // one packed record per front
+  const int32_t* child_idx;
+  const int32_t* rel_idx;
+  const int32_t* rows_idx;
+  const int32_t* asm_src;
+  const int32_t* asm_dst;
+  const uint8_t* col_is_primal;
+  const int32_t* perm;
+  int32_t* sync;             // [0] ticket | fcount[ns] | fflag[ns] | bflag[ns]
+  int32_t n_super;
+  unsigned long long* debug; // optional: 3 globaltimer stamps per front
+};
+
+__device__ __forceinline__ unsigned long long global_ns() {
+  unsigned long long t;
+  asm volatile("mov.u64 %0, %globaltimer;" : "=l"(t));
+  return t;
+}
+
+__global__ void __launch_bounds__(kTreeWarps * 32)
+k_factor_tree(TreeView T, const double* __restrict__ Kval, double delta,
+              double gamma, double* __restrict__ panels, double* updates,
+              double* __restrict__ D, int32_t* __restrict__ stats,
+              int smem_doubles_per_warp) {
+  extern __shared__ double smem[];
+  __shared__ int ls[kTreeWarps][6];
+  __shared__ uchar2 tri[kTriEntries];
+  init_tri_table(tri);
+  __syncthreads();
+  const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+  double* W = smem + size_t(warp) * smem_doubles_per_warp;
+  double* col = W + (smem_doubles_per_warp - 64);
+  int32_t* fcount = T.sync + 1;
+  for (;;) {
+    int t = 0;
+    if (lane == 0) t = atomicAdd(&T.sync[0], 1);
+    t = __shfl_sync(0xffffffffu, t, 0);
+    if (t >= T.n_super) break;
+    const int s = T.order[t];
+    const FrontMeta fm = load_front_meta(T.metas + s);
+    if (T.debug && lane == 0) T.debug[3 * s] = global_ns();
+    ldlt_factor_front_warp(lane, fm, T.metas, T.child_idx, T.rel_idx, T.asm_src,
+                           T.asm_dst, T.col_is_primal, Kval, delta, gamma,
+                           panels, updates, D, W, col, tri, &fcount[s],
+                           ls[warp], T.debug ? T.debug + 3 * s + 1 : nullptr);
+    __syncwarp();
+    if (T.debug && lane == 0) T.debug[3 * s + 2] = global_ns();
+    if (lane == 0) {
+      atomicAdd(&stats[0], ls[warp][0]);
+      atomicAdd(&stats[1], ls[warp][1]);
+      atomicAdd(&stats[2], ls[warp][2]);
+      atomicOr(&stats[3], ls[warp][3]);
+      const unsigned long long bits =
+          (unsigned long long)(unsigned)ls[warp][4] |
+          ((unsigned long long)(unsigned)ls[warp][5] << 32);
+      atomicMin(reinterpret_cast<unsigned long long*>(&stats[4]), bits);
+      __threadfence();
+      if (fm.parent >= 0) atomicAdd(&fcount[fm.parent], 1);
+    }
+  }
+}
+
+/// Forward (leaves→roots) then backward (roots→leaves) substitution in one
+/// launch; tickets [0, ns) are forward fronts, [ns, 2ns) backward fronts. The
+/// backward pass writes the un-permuted solution directly.
+__global__ void __launch_bounds__(kTreeWarps * 32)
+k_solve_tree(TreeView T, const double* __restrict__ panels,
+             const double* __restrict__ D, const double* __restrict__ rhs,
+             double* xperm, double* uvecs, double* __restrict__ sol) {
+  __shared__ double wbuf[kTreeWarps][32];
+  const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+  double* w = wbuf[warp];
+  const int ns = T.n_super;
+  int32_t* fcount = T.sync + 1;
+  int32_t* fflag = fcount + ns;
+  int32_t* bflag = fflag + ns;
+  for (;;) {
+    int t = 0;
+    if (lane == 0) t = atomicAdd(&T.sync[0], 1);
+    t = __shfl_sync(0xffffffffu, t, 0);
+    if (t >= 2 * ns) break;
+    if (t < ns) {
+      const int s = T.order[t];
+      const FrontMeta fm = load_front_meta(T.metas + s);
+      ldlt_forward_front_warp(lane, fm, T.metas, T.child_idx, T.rel_idx, T.perm,
+                              panels, rhs, xperm, uvecs, w, &fcount[s]);
+      __syncwarp();
+      if (lane == 0) {
+        __threadfence();
+        atomicExch(&fflag[s], 1);
+        if (fm.parent >= 0) atomicAdd(&fcount[fm.parent], 1);
+      }
+    } else {
+      const int s = T.order[2 * ns - 1 - t];
+      const FrontMeta fm = load_front_meta(T.metas + s);
+      ldlt_backward_front_warp(lane, fm, T.rows_idx, panels, D, xperm,
+                               fm.parent >= 0 ? &bflag[fm.parent] : &fflag[s]);
+      __syncwarp();
+      if (lane < fm.np) sol[T.perm[fm.c0 + lane]] = xperm[fm.c0 + lane];
+      __syncwarp();
+      if (lane == 0) {
+        __threadfence();
+        atomicExch(&bflag[s], 1);
+      }
+    }
+  }
+}
+
+// ---------------------------------------------------------------------------
 // kernels: step recovery, line search
 // ---------------------------------------------------------------------------
 
@@ -626,27 +840,25 @@ __global__ void k_step_recover(const double* __restrict__ sol,
 /// fraction-to-the-boundary rule on (s,p_s) and (z,p_z)
 /// (fraction_to_the_boundary_rule.hpp:19-43: α = min(1, min −τ/pᵢ·xᵢ over the
 /// blocking components), gᵀpˣ, (S⁻¹e)ᵀpˢ and step norms.
-__global__ void __launch_bounds__(kReduceThreads) k_step_stats(const double* __restrict__ g,
-                             const double* __restrict__ s,
-                             const double* __restrict__ z,
-                             const double* __restrict__ sinv,
-                             const double* __restrict__ px,
-                             const double* __restrict__ ps,
-                             const double* __restrict__ py,
-                             const double* __restrict__ pz, double tau, int n,
-                             int me, int mi, double* __restrict__ out) {
+__global__ void __launch_bounds__(kReduceThreads)
+k_step_stats(const double* __restrict__ g, const double* __restrict__ s,
+             const double* __restrict__ z, const double* __restrict__ sinv,
+             const double* __restrict__ px, const double* __restrict__ ps,
+             const double* __restrict__ py, const double* __restrict__ pz,
+             double tau, int n, int me, int mi, RedBuf rb,
+             double* __restrict__ out) {
   // 0 alpha_max 1 alpha_z 2 g·px 3 sinv·ps 4..7 inf norms 8 nonfinite
   double v[9] = {1.0, 1.0, 0.0, 0.0, 0.0, 0.0, 0.0, 0.0, 0.0};
-  for (int i = threadIdx.x; i < n; i += blockDim.x) {
+  const int stride = gridDim.x * blockDim.x;
+  const int t0 = blockIdx.x * blockDim.x + threadIdx.x;
+  for (int i = t0; i < n; i += stride) {
     const double p = px[i];
     v[2] += g[i] * p;
     v[4] = fmax(v[4], fabs(p));
     if (!isfinite(p)) v[8] += 1.0;
   }
-  for (int i = threadIdx.x; i < me; i += blockDim.x) {
-    v[6] = fmax(v[6], fabs(py[i]));
-  }
-  for (int i = threadIdx.x; i < mi; i += blockDim.x) {
+  for (int i = t0; i < me; i += stride) v[6] = fmax(v[6], fabs(py[i]));
+  for (int i = t0; i < mi; i += stride) {
     const double p = ps[i], q = pz[i];
     if (p < 0.0) {
       const double cand = -tau / p * s[i];
@@ -664,7 +876,7 @@ __global__ void __launch_bounds__(kReduceThreads) k_step_stats(const double* __r
   const int op[9] = {RED_MIN, RED_MIN, RED_SUM, RED_SUM, RED_MAX,
                      RED_MAX, RED_MAX, RED_MAX, RED_SUM};
   __shared__ double res[9];
-  block_reduce<9>(v, op, res);
+  if (!grid_reduce<9>(v, op, rb.partials, rb.counter, res)) return;
   if (threadIdx.x == 0) {
     for (int q = 0; q < 8; ++q) out[q] = res[q];
     out[8] = res[8] == 0.0 ? 1.0 : 0.0;
@@ -746,6 +958,16 @@ inline int blocks_for(int64_t n, int threads) {
   return static_cast<int>((n + threads - 1) / threads);
 }
 
+/// Grid of a reduction kernel: enough blocks for ~4 elements per thread, at
+/// most one block per SM.
+inline int red_blocks(int64_t n) {
+  return std::max(1, std::min<int>(kReduceBlocks,
+                                   blocks_for(n, 4 * kReduceThreads)));
+}
+inline RedBuf red_buf(slpb_solver* S) {
+  return {S->red_partials.p, S->red_counter.p};
+}
+
 int upload_program_set(slpb_solver* S, const ProgramSet& ps,
                        DevProgramSet& d) {
   d.n_clusters = static_cast<int>(ps.cluster_prog.size());
@@ -754,14 +976,64 @@ int upload_program_set(slpb_solver* S, const ProgramSet& ps,
   CU(d.prog_offset.upload(ps.prog_offset, S->stream));
   CU(d.cluster_bind.upload(ps.cluster_bind, S->stream));
   CU(d.cluster_prog.upload(ps.cluster_prog, S->stream));
-  d.smem_per_warp = std::max(8, ps.max_smem);
+  // lanes per cluster: the average level width of the program, rounded down
+  // to a power of two in [4, 32] (SLPB_AD_GROUP overrides, for experiments)
+  const int n_prog = static_cast<int>(ps.prog_offset.size());
+  int forced = 0;
+  if (const char* e = std::getenv("SLPB_AD_GROUP")) forced = std::atoi(e);
+  std::vector<int> group(n_prog, 32);
+  for (int p = 0; p < n_prog; ++p) {
+    const uint32_t* P = ps.blob.data() + ps.prog_offset[p];
+    const uint32_t levels = std::max<uint32_t>(1, P[4] + P[5]);
+    const uint32_t n_fwd = (P + P[10])[P[4]];
+    const uint32_t n_vis = (P + P[12])[P[5]];
+    const double avg = double(n_fwd + n_vis) / levels;
+    int G = 4;
+    while (G < 32 && 2 * G <= avg) G *= 2;
+    if (forced == 4 || forced == 8 || forced == 16 || forced == 32) G = forced;
+    // keep a warp's scratch within what one SM can hold
+    while (G < 32 && (32 / G) * std::max(8, ps.prog_smem[p]) > 200 * 1024) G *= 2;
+    group[p] = G;
+  }
+  std::vector<int32_t> order(d.n_clusters);
+  for (int c = 0; c < d.n_clusters; ++c) order[c] = c;
+  std::stable_sort(order.begin(), order.end(), [&](int a, int b) {
+    return ps.cluster_prog[a] < ps.cluster_prog[b];
+  });
+  // heavy programs first so the tail of the launch is made of cheap warps
+  std::vector<int> prog_rank(n_prog);
+  for (int p = 0; p < n_prog; ++p) prog_rank[p] = p;
+  std::sort(prog_rank.begin(), prog_rank.end(), [&](int a, int b) {
+    return ps.prog_smem[a] > ps.prog_smem[b];
+  });
+  std::vector<std::vector<int32_t>> by_prog(n_prog);
+  for (int c : order) by_prog[ps.cluster_prog[c]].push_back(c);
+  std::vector<int32_t> tasks, sorted;
+  d.smem_per_warp = 8;
+  for (int p : prog_rank) {
+    const int G = group[p], per = 32 / G;
+    const int per_cluster = std::max(8, ps.prog_smem[p]) / 8;
+    d.smem_per_warp = std::max(d.smem_per_warp, per * per_cluster * 8);
+    const auto& list = by_prog[p];
+    for (size_t k = 0; k < list.size(); k += per) {
+      const int cnt = static_cast<int>(std::min<size_t>(per, list.size() - k));
+      tasks.push_back(static_cast<int32_t>(sorted.size()));
+      tasks.push_back(cnt);
+      tasks.push_back(G);
+      tasks.push_back(per_cluster);
+      for (int q = 0; q < cnt; ++q) sorted.push_back(list[k + q]);
+    }
+  }
+  d.n_tasks = static_cast<int>(tasks.size() / 4);
+  CU(d.task.upload(tasks, S->stream));
+  CU(d.cluster_order.upload(sorted, S->stream));
   if (d.smem_per_warp > 200 * 1024) {
     return fail(S, SLPB_ERR_UNSUPPORTED,
                 "an expression cluster needs more than 200 KB of shared "
                 "memory; the global-memory fallback is not implemented");
   }
   d.warps_per_block =
-      std::max(1, std::min(8, (64 * 1024) / d.smem_per_warp));
+      std::max(1, std::min(8, (96 * 1024) / d.smem_per_warp));
   return SLPB_OK;
 }
 
@@ -781,12 +1053,13 @@ int upload_gather(slpb_solver* S, const Gather& g, DevGather& d) {
 
 int run_sweep(slpb_solver* S, const DevProgramSet& d, const double* leaf,
               double* stage) {
-  if (d.n_clusters == 0) return SLPB_OK;
+  if (d.n_tasks == 0) return SLPB_OK;
   const int wpb = d.warps_per_block;
   const int smem = wpb * d.smem_per_warp;
-  k_ad_sweep<<<blocks_for(d.n_clusters, wpb), wpb * 32, smem, S->stream>>>(
+  k_ad_sweep<<<blocks_for(d.n_tasks, wpb), wpb * 32, smem, S->stream>>>(
       d.blob.p, d.prog_offset.p, d.cluster_prog.p, d.cluster_bind.p,
-      d.bindings.p, d.n_clusters, d.smem_per_warp / 8, leaf, stage);
+      d.bindings.p, d.task.p, d.cluster_order.p, d.n_tasks,
+      d.smem_per_warp / 8, leaf, stage);
   ++S->counters.kernel_launches;
   CU(cudaGetLastError());
   return SLPB_OK;
@@ -883,8 +1156,8 @@ int refresh_leaves(slpb_solver* S, const double* x, const double* y,
 
 int point_info(slpb_solver* S, const double* vals, const double* s,
                double* d_out) {
-  k_point_info<<<1, kReduceThreads, 0, S->stream>>>(vals, s, S->me, S->mi,
-                                                    d_out);
+  k_point_info<<<red_blocks(S->me + S->mi), kReduceThreads, 0, S->stream>>>(
+      vals, s, S->me, S->mi, red_buf(S), d_out);
   ++S->counters.kernel_launches;
   CU(cudaGetLastError());
   return SLPB_OK;
@@ -902,9 +1175,9 @@ void fill_point_info(const double* r, slpb_point_info* info) {
 int kkt_stats(slpb_solver* S, const double* c_e, const double* c_i,
               const double* x, const double* s, const double* y,
               const double* z, double mu, slpb_kkt_stats* out) {
-  k_kkt_stats<<<1, kReduceThreads, 0, S->stream>>>(
+  k_kkt_stats<<<red_blocks(S->n + S->mi), kReduceThreads, 0, S->stream>>>(
       ae_view(S), ai_view(S), S->dvals.p + S->ad.off_g, c_e, c_i, x, s, y, z,
-      S->d_c.p, S->d_f, mu, S->n, S->me, S->mi, S->d_results.p);
+      S->d_c.p, S->d_f, mu, S->n, S->me, S->mi, red_buf(S), S->d_results.p);
   ++S->counters.kernel_launches;
   CU(cudaGetLastError());
   int rc = fetch_results(S, 25);
@@ -939,25 +1212,51 @@ int kkt_stats(slpb_solver* S, const double* c_e, const double* c_i,
   return SLPB_OK;
 }
 
+TreeView tree_view(slpb_solver* S) {
+  TreeView T{};
+  T.order = S->sy_level_supers.p;
+  T.metas = S->sy_metas.p;
+  T.child_idx = S->sy_child_idx.p;
+  T.rel_idx = S->sy_rel_idx.p;
+  T.rows_idx = S->sy_rows_idx.p;
+  T.asm_src = S->sy_asm_src.p;
+  T.asm_dst = S->sy_asm_dst.p;
+  T.col_is_primal = S->sy_col_is_primal.p;
+  T.perm = S->sy_perm.p;
+  T.sync = S->tree_sync.p;
+  T.n_super = S->sym.n_super;
+  T.debug = S->tree_debug.p;
+  return T;
+}
+
 int launch_solve(slpb_solver* S) {
   const Symbolic& Y = S->sym;
-  const int smem = Y.max_front * static_cast<int>(sizeof(double));
   CU(cudaEventRecord(S->ev[8], S->stream));
-  for (int L = 0; L < Y.n_levels; ++L) {
-    const int cnt = Y.level_ptr[L + 1] - Y.level_ptr[L];
-    k_forward_level<<<cnt, kFrontThreads, smem, S->stream>>>(
-        S->sview, S->sy_level_supers.p + Y.level_ptr[L], S->panels.p, S->rhs.p,
-        S->xperm.p, S->uvecs.p);
+  if (S->use_tree) {
+    CU(cudaMemsetAsync(S->tree_sync.p, 0, (1 + 3 * size_t(Y.n_super)) * 4,
+                       S->stream));
+    const TreeView T = tree_view(S);
+    k_solve_tree<<<S->tree_blocks, kTreeWarps * 32, 0, S->stream>>>(
+        T, S->panels.p, S->D.p, S->rhs.p, S->xperm.p, S->uvecs.p, S->sol.p);
+    ++S->counters.kernel_launches;
+  } else {
+    const int smem = Y.max_front * static_cast<int>(sizeof(double));
+    for (int L = 0; L < Y.n_levels; ++L) {
+      const int cnt = Y.level_ptr[L + 1] - Y.level_ptr[L];
+      k_forward_level<<<cnt, kFrontThreads, smem, S->stream>>>(
+          S->sview, S->sy_level_supers.p + Y.level_ptr[L], S->panels.p,
+          S->rhs.p, S->xperm.p, S->uvecs.p);
+    }
+    for (int L = Y.n_levels - 1; L >= 0; --L) {
+      const int cnt = Y.level_ptr[L + 1] - Y.level_ptr[L];
+      k_backward_level<<<cnt, kFrontThreads, smem, S->stream>>>(
+          S->sview, S->sy_level_supers.p + Y.level_ptr[L], S->panels.p, S->D.p,
+          S->xperm.p);
+    }
+    k_unpermute<<<blocks_for(S->dim, 256), 256, 0, S->stream>>>(
+        S->xperm.p, S->sy_perm.p, S->dim, S->sol.p);
+    S->counters.kernel_launches += 2 * Y.n_levels + 1;
   }
-  for (int L = Y.n_levels - 1; L >= 0; --L) {
-    const int cnt = Y.level_ptr[L + 1] - Y.level_ptr[L];
-    k_backward_level<<<cnt, kFrontThreads, smem, S->stream>>>(
-        S->sview, S->sy_level_supers.p + Y.level_ptr[L], S->panels.p, S->D.p,
-        S->xperm.p);
-  }
-  k_unpermute<<<blocks_for(S->dim, 256), 256, 0, S->stream>>>(
-      S->xperm.p, S->sy_perm.p, S->dim, S->sol.p);
-  S->counters.kernel_launches += 2 * Y.n_levels + 1;
   CU(cudaEventRecord(S->ev[9], S->stream));
   S->pending[4] = true;
   CU(cudaGetLastError());
@@ -987,9 +1286,9 @@ int solve_into(slpb_solver* S, double mu, double tau, const double* cis_soc,
       S->sol.p, S->ai_rowptr.p, S->ai_rcol.p, S->ai_ridx.p,
       S->dvals.p + S->ad.off_ai, S->vals_cur.p + 1 + me, S->s.p, S->z.p,
       cis_soc, S->sinv.p, S->sigma.p, mu, n, me, mi, px, py, ps, pz);
-  k_step_stats<<<1, kReduceThreads, 0, S->stream>>>(
+  k_step_stats<<<red_blocks(n + mi), kReduceThreads, 0, S->stream>>>(
       S->dvals.p + S->ad.off_g, S->s.p, S->z.p, S->sinv.p, px, ps, py, pz, tau,
-      n, me, mi, S->d_results.p);
+      n, me, mi, red_buf(S), S->d_results.p);
   S->counters.kernel_launches += 2;
   CU(cudaGetLastError());
   rc = fetch_results(S, 9);
@@ -1036,6 +1335,11 @@ int slpb_create(int device, slpb_solver** out) {
     return SLPB_ERR_CUDA;
   }
   if (S->d_results.alloc(kResultDoubles) != cudaSuccess) return SLPB_ERR_CUDA;
+  if (S->red_partials.alloc(kReduceBlocks * 32) != cudaSuccess ||
+      S->red_counter.alloc(1) != cudaSuccess ||
+      S->red_counter.zero(S->stream) != cudaSuccess) {
+    return SLPB_ERR_CUDA;
+  }
   for (auto& e : S->ev) {
     if (cudaEventCreate(&e) != cudaSuccess) return SLPB_ERR_CUDA;
   }
@@ -1251,6 +1555,51 @@ int slpb_analyze(slpb_solver* S, int ordering, const int32_t* perm,
   CU(S->uvecs.alloc(Y.rel_ptr.back()));
   CU(S->xperm.alloc(Y.dim));
   CU(S->fstats.alloc(8));
+  {
+    std::vector<int32_t> nchild(Y.n_super);
+    for (int32_t q = 0; q < Y.n_super; ++q) {
+      nchild[q] = static_cast<int32_t>(Y.child_ptr[q + 1] - Y.child_ptr[q]);
+    }
+    CU(S->sy_super_parent.upload(Y.super_parent, S->stream));
+    CU(S->sy_nchild.upload(nchild, S->stream));
+    std::vector<FrontMeta> metas(Y.n_super);
+    for (int32_t q = 0; q < Y.n_super; ++q) {
+      FrontMeta& fm = metas[q];
+      fm.F = Y.front_dim[q];
+      fm.c0 = Y.super_first[q];
+      fm.np = Y.super_first[q + 1] - Y.super_first[q];
+      fm.n_child = nchild[q];
+      fm.child_begin = static_cast<int32_t>(Y.child_ptr[q]);
+      fm.asm_begin = static_cast<int32_t>(Y.asm_ptr[q]);
+      fm.asm_end = static_cast<int32_t>(Y.asm_ptr[q + 1]);
+      fm.rel_off = static_cast<int32_t>(Y.rel_ptr[q]);
+      fm.panel_off = Y.panel_ptr[q];
+      fm.update_off = Y.update_ptr[q];
+      fm.rows_off = Y.rows_ptr[q];
+      fm.parent = Y.super_parent[q];
+      fm.pad = 0;
+    }
+    CU(S->sy_metas.upload(metas, S->stream));
+    if (std::getenv("SLPB_TREE_DEBUG")) {
+      CU(S->tree_debug.alloc(3 * size_t(Y.n_super)));
+      CU(S->tree_debug.zero(S->stream));
+    }
+    CU(S->tree_sync.alloc(1 + 3 * size_t(Y.n_super)));
+  }
+  // fronts of order ≤ 32: one warp per front, one launch per factorisation
+  S->use_tree = Y.max_front <= 32;
+  S->tree_smem_doubles = Y.max_front * Y.max_front + 64;
+  // about two blocks of warps per SM: enough to cover the widest level in a
+  // couple of passes without parking thousands of warps on a spin-wait
+  S->tree_blocks = std::max(
+      1, std::min(blocks_for(Y.n_super, kTreeWarps), 148 * 2));
+  {
+    const int tree_smem =
+        kTreeWarps * S->tree_smem_doubles * static_cast<int>(sizeof(double));
+    CU(cudaFuncSetAttribute(k_factor_tree,
+                            cudaFuncAttributeMaxDynamicSharedMemorySize,
+                            std::max(tree_smem, 48 * 1024)));
+  }
   CU(cudaStreamSynchronize(S->stream));
   SymbolicView& V = S->sview;
   V.dim = Y.dim;
@@ -1340,9 +1689,10 @@ int slpb_eval_current(slpb_solver* S, int derivatives,
   int nres = 6;
   if (derivatives != 0) {
     if ((rc = eval_derivs(S, S->leaf_cur.p))) return rc;
-    k_deriv_finite<<<1, kReduceThreads, 0, S->stream>>>(
+    k_deriv_finite<<<red_blocks(S->ad.off_h + S->ad.H.nnz()), kReduceThreads,
+                     0, S->stream>>>(
         S->dvals.p, S->ad.off_ae, S->ad.off_ai, S->ad.off_h,
-        S->ad.off_h + S->ad.H.nnz(), S->d_results.p + 6);
+        S->ad.off_h + S->ad.H.nnz(), red_buf(S), S->d_results.p + 6);
     ++S->counters.kernel_launches;
     nres = 7;
   }
@@ -1405,15 +1755,27 @@ int slpb_factor(slpb_solver* S, double delta, double gamma, int reassemble,
     CU(cudaMemcpyAsync(S->fstats.p, init, sizeof(init), cudaMemcpyHostToDevice,
                        S->stream));
   }
-  const int smem = static_cast<int>(
-      (size_t(Y.max_front) * Y.max_front + Y.max_front) * sizeof(double));
-  for (int L = 0; L < Y.n_levels; ++L) {
-    const int cnt = Y.level_ptr[L + 1] - Y.level_ptr[L];
-    k_factor_level<<<cnt, kFrontThreads, smem, S->stream>>>(
-        S->sview, S->sy_level_supers.p + Y.level_ptr[L], S->Kval.p, delta,
-        gamma, S->panels.p, S->updates.p, S->D.p, S->fstats.p);
+  if (S->use_tree) {
+    CU(cudaMemsetAsync(S->tree_sync.p, 0, (1 + size_t(Y.n_super)) * 4,
+                       S->stream));
+    const TreeView T = tree_view(S);
+    const int smem =
+        kTreeWarps * S->tree_smem_doubles * static_cast<int>(sizeof(double));
+    k_factor_tree<<<S->tree_blocks, kTreeWarps * 32, smem, S->stream>>>(
+        T, S->Kval.p, delta, gamma, S->panels.p, S->updates.p, S->D.p,
+        S->fstats.p, S->tree_smem_doubles);
+    ++S->counters.kernel_launches;
+  } else {
+    const int smem = static_cast<int>(
+        (size_t(Y.max_front) * Y.max_front + Y.max_front) * sizeof(double));
+    for (int L = 0; L < Y.n_levels; ++L) {
+      const int cnt = Y.level_ptr[L + 1] - Y.level_ptr[L];
+      k_factor_level<<<cnt, kFrontThreads, smem, S->stream>>>(
+          S->sview, S->sy_level_supers.p + Y.level_ptr[L], S->Kval.p, delta,
+          gamma, S->panels.p, S->updates.p, S->D.p, S->fstats.p);
+    }
+    S->counters.kernel_launches += Y.n_levels;
   }
-  S->counters.kernel_launches += Y.n_levels;
   CU(cudaEventRecord(S->ev[7], S->stream));
   S->pending[3] = true;
   CU(cudaGetLastError());
@@ -1605,6 +1967,21 @@ int slpb_pattern(const slpb_solver* S, int which, int32_t* rows, int32_t* cols,
   if (rowidx && p->nnz() > 0) {
     std::memcpy(rowidx, p->rowidx.data(), p->nnz() * sizeof(int32_t));
   }
+  return SLPB_OK;
+}
+
+/* Undocumented debugging aid (SLPB_TREE_DEBUG=1): per front, globaltimer ns at
+ * ticket, after the children wait, and at completion of the last
+ * factorisation; level of each front. Not part of include/slpb.h. */
+int slpb_debug_tree(slpb_solver* S, unsigned long long* stamps, int32_t* level,
+                    int32_t* parent) {
+  if (!S || !S->analyzed || !S->tree_debug.p) return SLPB_ERR_STATE;
+  CU(cudaSetDevice(S->device));
+  CU(cudaStreamSynchronize(S->stream));
+  CU(cudaMemcpy(stamps, S->tree_debug.p, S->tree_debug.n * 8,
+                cudaMemcpyDeviceToHost));
+  std::memcpy(level, S->sym.super_level.data(), S->sym.n_super * 4);
+  std::memcpy(parent, S->sym.super_parent.data(), S->sym.n_super * 4);
   return SLPB_OK;
 }
 

@@ -155,6 +155,18 @@ void emu_stats(void* h, int64_t* out) {
   out[11] = a.deriv_stage_size;
 }
 
+/// Header words of program `prog` of the value (set 0) or derivative (set 1)
+/// program set; returns the number of programs in the set.
+int emu_program_header(void* h, int set, int prog, uint32_t* out24) {
+  auto* e = static_cast<Emu*>(h);
+  const slpb::ProgramSet& ps = set == 0 ? e->ad.values : e->ad.derivs;
+  const int n = static_cast<int>(ps.prog_offset.size());
+  if (prog >= 0 && prog < n) {
+    std::memcpy(out24, ps.blob.data() + ps.prog_offset[prog], 24 * 4);
+  }
+  return n;
+}
+
 /// which: SLPB_OUT_A_E, SLPB_OUT_A_I, SLPB_OUT_H_C (pattern of H).
 void emu_pattern(void* h, int which, int* rows, int* cols, int64_t* nnz,
                  int* colptr, int* rowidx) {
