@@ -8,10 +8,11 @@
 // contraction, so that it rounds like the reference's x86-64 build; only the
 // transcendental functions can differ (CUDA libdevice vs glibc, ≤ 1-2 ulp).
 //
-// The body is written once as a function of (lane, NLANES): the kernels run it
-// with one warp per cluster (NLANES = 32, levels separated by __syncwarp),
-// and tests/emu runs the very same code on the host with NLANES = 1 to check
-// the program encoding without a GPU. It is not a CPU path of the product:
+// The body is written once as a function of (tid, nthreads, LC): the kernel
+// runs it with one thread block per task of up to LC = 32 clusters that share a
+// program (lane = cluster, levels separated by __syncthreads), and tests/emu
+// runs the very same code on the host, lane after lane, to check the program
+// encoding and the task plan without a GPU. It is not a CPU path of the product:
 // nothing in libslpb.so calls it on the host.
 #pragma once
 
@@ -126,39 +127,54 @@ struct NoSync {
   SLPB_HD void operator()() const {}
 };
 
-/// Runs one cluster. `scratch` holds n_slots values followed by n_adj
-/// adjoints. `stage` receives value outputs and derivative outputs.
-template <int NLANES, typename Sync>
-SLPB_HD void ad_run_cluster(int lane, const uint32_t* __restrict__ P,
-                            const uint32_t* __restrict__ B,
-                            const double* __restrict__ leaf,
-                            double* __restrict__ stage, double* scratch,
-                            Sync sync) {
-  const int n_slots = static_cast<int>(P[0]);
+/// Runs one TASK: up to LC clusters that share ONE program, side by side.
+/// Thread `tid` of `nthreads` (a multiple of LC) works for cluster c = tid % LC
+/// on the items q, q+R, … of every level (q = tid / LC, R = nthreads / LC). On
+/// the device LC = 32 makes every warp run one instruction for 32 clusters
+/// (time steps) at once: the opcode is warp-uniform, the scratch of slot s and
+/// lane c sits at scratch[s·LC + c] (conflict-free in shared memory), and the
+/// block synchronises between levels. tests/emu runs the same code with
+/// nthreads = LC, one lane after the other.
+///
+/// `scratch` holds P[0]·LC doubles; values and adjoints share it (the compiler
+/// assigns physical slots by liveness). `B` is the task's binding block,
+/// transposed so that lanes read consecutive words:
+///   leaf_index i32[n_leaf][LC] | pad | const_val f64[n_const][LC]
+///   | val_out i32[n_val_out][LC] | adj_out i32[n_adj_out][LC]
+/// Lanes ≥ count carry a copy of lane 0's bindings and skip their stores.
+template <int LC, typename Sync>
+SLPB_HD void ad_run_group(int tid, int nthreads, int count,
+                          const uint32_t* __restrict__ P,
+                          const uint32_t* __restrict__ B,
+                          const double* __restrict__ leaf,
+                          double* __restrict__ stage, double* scratch,
+                          Sync sync) {
+  const int c = tid % LC;
+  const int q = tid / LC;
+  const int R = nthreads / LC;
+  const bool active = c < count;
   const int n_leaf = static_cast<int>(P[2]);
   const int n_const = static_cast<int>(P[3]);
   const int n_fwd_levels = static_cast<int>(P[4]);
   const int n_rev_levels = static_cast<int>(P[5]);
   const int n_val_out = static_cast<int>(P[6]);
   const int n_adj_out = static_cast<int>(P[7]);
-  double* vals = scratch;
-  double* adj = scratch + n_slots;
+  double* S = scratch + c;  // slot s of this lane: S[s * LC]
 
-  // binding layout: leaf_index | pad | const_val | val_out | adj_out
   const int32_t* leaf_index = reinterpret_cast<const int32_t*>(B);
-  const int const_off = (n_leaf + 1) & ~1;
+  const int const_off = (n_leaf * LC + 1) & ~1;
   const double* const_val = reinterpret_cast<const double*>(B + const_off);
   const int32_t* val_out_stage =
-      reinterpret_cast<const int32_t*>(B + const_off + 2 * n_const);
-  const int32_t* adj_out_stage = val_out_stage + n_val_out;
+      reinterpret_cast<const int32_t*>(B + const_off + 2 * n_const * LC);
+  const int32_t* adj_out_stage = val_out_stage + n_val_out * LC;
 
   const uint16_t* leaf_slot = reinterpret_cast<const uint16_t*>(P + P[8]);
   const uint16_t* const_slot = reinterpret_cast<const uint16_t*>(P + P[9]);
-  for (int i = lane; i < n_leaf; i += NLANES) {
-    vals[leaf_slot[i]] = leaf[leaf_index[i]];
+  for (int i = q; i < n_leaf; i += R) {
+    S[leaf_slot[i] * LC] = leaf[leaf_index[i * LC + c]];
   }
-  for (int i = lane; i < n_const; i += NLANES) {
-    vals[const_slot[i]] = const_val[i];
+  for (int i = q; i < n_const; i += R) {
+    S[const_slot[i] * LC] = const_val[i * LC + c];
   }
   sync();
 
@@ -168,15 +184,20 @@ SLPB_HD void ad_run_cluster(int lane, const uint32_t* __restrict__ P,
   for (int L = 0; L < n_fwd_levels; ++L) {
     const int b = static_cast<int>(fwd_lvl[L]);
     const int e = static_cast<int>(fwd_lvl[L + 1]);
-    for (int i = b + lane; i < e; i += NLANES) {
+    for (int i = b + q; i < e; i += R) {
       const FwdInstr in = fwd[i];
-      vals[in.dst] = ad_op_value(in.op, vals[in.a], vals[in.b]);
+      S[in.dst * LC] = ad_op_value(in.op, S[in.a * LC], S[in.b * LC]);
     }
     sync();
   }
-  const uint16_t* val_out_slot = reinterpret_cast<const uint16_t*>(P + P[15]);
-  for (int i = lane; i < n_val_out; i += NLANES) {
-    stage[val_out_stage[i]] = vals[val_out_slot[i]];
+  if (n_val_out > 0) {
+    const uint16_t* val_out_slot =
+        reinterpret_cast<const uint16_t*>(P + P[15]);
+    for (int i = q; i < n_val_out; i += R) {
+      if (active) stage[val_out_stage[i * LC + c]] = S[val_out_slot[i] * LC];
+    }
+    // slots read here may be recycled by the first reverse level
+    if (n_rev_levels > 0) sync();
   }
 
   // ---- reverse sweeps: each visit pulls from its parents' adjoints ----------
@@ -186,7 +207,7 @@ SLPB_HD void ad_run_cluster(int lane, const uint32_t* __restrict__ P,
   for (int L = 0; L < n_rev_levels; ++L) {
     const int b = static_cast<int>(rev_lvl[L]);
     const int e = static_cast<int>(rev_lvl[L + 1]);
-    for (int i = b + lane; i < e; i += NLANES) {
+    for (int i = b + q; i < e; i += R) {
       const Visit v = visit[i];
       double a;
       if (v.n_contrib == 0) {
@@ -194,20 +215,20 @@ SLPB_HD void ad_run_cluster(int lane, const uint32_t* __restrict__ P,
       } else {
         // adjoint starts at 0 and accumulates in the row's parent order
         a = 0.0;
-        const Contrib* c = contrib + v.contrib_begin;
+        const Contrib* ct = contrib + v.contrib_begin;
         for (int k = 0; k < v.n_contrib; ++k) {
-          const Contrib ck = c[k];
-          a += ad_op_grad(ck.op, ck.side, adj[ck.parent_adj], vals[ck.l],
-                          vals[ck.r]);
+          const Contrib ck = ct[k];
+          a += ad_op_grad(ck.op, ck.side, S[ck.parent_adj * LC], S[ck.l * LC],
+                          S[ck.r * LC]);
         }
       }
-      adj[v.adj] = a;
+      S[v.adj * LC] = a;
     }
     sync();
   }
   const uint16_t* adj_out_slot = reinterpret_cast<const uint16_t*>(P + P[16]);
-  for (int i = lane; i < n_adj_out; i += NLANES) {
-    stage[adj_out_stage[i]] = adj[adj_out_slot[i]];
+  for (int i = q; i < n_adj_out; i += R) {
+    if (active) stage[adj_out_stage[i * LC + c]] = S[adj_out_slot[i] * LC];
   }
 }
 

@@ -243,6 +243,306 @@ struct Compiler {
     sr.flags.resize(w);
   }
 
+  /// Emits the position-independent program of one cluster into `prog`.
+  /// local[] must hold the cluster's logical value slots (cl_nodes order).
+  ///
+  /// Scratch slots are PHYSICAL: values and adjoints share one array and a
+  /// slot is recycled once its last reader has run (liveness over the level
+  /// schedule: load → forward levels → value outputs → reverse levels → adjoint
+  /// outputs). That keeps a cart-pole stage at a few hundred doubles instead of
+  /// 1 700, so that 32 stages fit in one CTA's shared memory side by side.
+  bool emit_program(std::vector<SubRow>& subs, const std::vector<int32_t>& mem,
+                    const std::vector<int32_t>& cl_nodes,
+                    std::vector<int32_t>& level,
+                    std::vector<int32_t>& sorted_ids,
+                    std::vector<uint32_t>& prog, ProgramSet& ps) {
+    (void)ps;
+    const int32_t n_slots = static_cast<int32_t>(cl_nodes.size());
+    // --- forward levels ------------------------------------------------------
+    sorted_ids.assign(cl_nodes.begin(), cl_nodes.end());
+    std::sort(sorted_ids.begin(), sorted_ids.end());
+    level.assign(n_slots, 0);
+    int32_t max_level = 0;
+    for (int32_t nd : sorted_ids) {
+      if (!is_interior(nd)) continue;
+      int32_t lv = level[local[tape.lhs[nd]]];
+      if (tape.rhs[nd] >= 0) lv = std::max(lv, level[local[tape.rhs[nd]]]);
+      level[local[nd]] = lv + 1;
+      max_level = std::max(max_level, lv + 1);
+    }
+    std::vector<std::vector<int32_t>> fwd_levels(max_level);  // logical slots
+    std::vector<int32_t> leaf_slots, const_slots;             // logical slots
+    for (int32_t slot = 0; slot < n_slots; ++slot) {
+      const int32_t nd = cl_nodes[slot];
+      if (is_interior(nd)) {
+        fwd_levels[level[slot] - 1].push_back(slot);
+      } else if (tape.op[nd] == SLPB_OP_VAR) {
+        leaf_slots.push_back(slot);
+      } else {
+        const_slots.push_back(slot);
+      }
+    }
+    // --- reverse visits ------------------------------------------------------
+    struct ContribTmp {
+      int32_t parent_visit, l, r;  // l, r: logical value slots or −1
+      uint8_t op, side;
+    };
+    struct VisitTmp {
+      int32_t rlevel, seed;
+      std::vector<ContribTmp> contribs;
+    };
+    std::vector<VisitTmp> visits;
+    std::vector<int32_t> adj_out_visit, val_out_slots;
+    for (int32_t s : mem) {
+      SubRow& sr = subs[s];
+      if (sr.is_value) {
+        val_out_slots.push_back(local[sr.nodes[0]]);
+        continue;
+      }
+      const int32_t len = static_cast<int32_t>(sr.nodes.size());
+      // one visit per active node, in list order; pos[] = visit index
+      for (int32_t i = 0; i < len; ++i) {
+        const int32_t nd = sr.nodes[i];
+        if (!(sr.flags[i] & kActive)) continue;
+        pos[nd] = static_cast<int32_t>(visits.size());
+        visits.push_back({0, 0, {}});
+      }
+      if (pos[sr.nodes[0]] >= 0) visits[pos[sr.nodes[0]]].seed = sr.seed;
+      for (int32_t i = 0; i < len; ++i) {
+        const int32_t nd = sr.nodes[i];
+        if (pos[nd] < 0 || !is_interior(nd)) continue;
+        const int32_t l = tape.lhs[nd], r = tape.rhs[nd];
+        const int32_t pv = pos[nd];
+        for (int side = 0; side < 2; ++side) {
+          const int32_t ch = side == 0 ? l : r;
+          if (ch < 0 || pos[ch] < 0) continue;
+          VisitTmp& cv = visits[pos[ch]];
+          const uint8_t needs = grad_value_needs(tape.op[nd], side);
+          ContribTmp c{};
+          c.parent_visit = pv;
+          c.l = (needs & 1) ? local[l] : -1;
+          c.r = (needs & 2) ? (r >= 0 ? local[r] : local[l]) : -1;
+          c.op = tape.op[nd];
+          c.side = static_cast<uint8_t>(side);
+          cv.contribs.push_back(c);
+          cv.rlevel = std::max(cv.rlevel, visits[pv].rlevel + 1);
+        }
+      }
+      for (auto& [stage, nd] : sr.outs) adj_out_visit.push_back(pos[nd]);
+      for (int32_t i = 0; i < len; ++i) pos[sr.nodes[i]] = -1;
+    }
+    const int32_t n_visits = static_cast<int32_t>(visits.size());
+    int32_t max_rlevel = -1;
+    for (auto& v : visits) max_rlevel = std::max(max_rlevel, v.rlevel);
+    std::vector<std::vector<int32_t>> rev_levels(max_rlevel + 1);
+    for (int32_t i = 0; i < n_visits; ++i) {
+      rev_levels[visits[i].rlevel].push_back(i);
+    }
+
+    // --- physical slot allocation (liveness over the level schedule) ---------
+    // time 0: leaf/constant load; 1..Lf: forward levels; Lf+1: value outputs;
+    // Lf+2+r: reverse level r; t_end: adjoint outputs.
+    const int32_t Lf = max_level;
+    const int32_t t_valout = Lf + 1;
+    const int32_t t_end = Lf + 2 + (max_rlevel + 1);
+    auto t_rev = [&](int32_t rl) { return Lf + 2 + rl; };
+    std::vector<int32_t> v_last(n_slots), a_last(n_visits);
+    for (int32_t slot = 0; slot < n_slots; ++slot) v_last[slot] = level[slot];
+    for (int32_t slot = 0; slot < n_slots; ++slot) {
+      const int32_t nd = cl_nodes[slot];
+      if (!is_interior(nd)) continue;
+      const int32_t a = local[tape.lhs[nd]];
+      v_last[a] = std::max(v_last[a], level[slot]);
+      if (tape.rhs[nd] >= 0) {
+        const int32_t b = local[tape.rhs[nd]];
+        v_last[b] = std::max(v_last[b], level[slot]);
+      }
+    }
+    for (int32_t slot : val_out_slots) {
+      v_last[slot] = std::max(v_last[slot], t_valout);
+    }
+    for (int32_t i = 0; i < n_visits; ++i) {
+      const int32_t t = t_rev(visits[i].rlevel);
+      a_last[i] = t;
+    }
+    for (int32_t i = 0; i < n_visits; ++i) {
+      const int32_t t = t_rev(visits[i].rlevel);
+      for (const ContribTmp& c : visits[i].contribs) {
+        a_last[c.parent_visit] = std::max(a_last[c.parent_visit], t);
+        if (c.l >= 0) v_last[c.l] = std::max(v_last[c.l], t);
+        if (c.r >= 0) v_last[c.r] = std::max(v_last[c.r], t);
+      }
+    }
+    for (int32_t vi : adj_out_visit) a_last[vi] = t_end;
+    // items defined at each time, in a fixed order (values by slot, adjoints by
+    // visit index); items released after each time
+    std::vector<std::vector<int32_t>> defs(t_end + 1), frees(t_end + 1);
+    // item id: value slot s → s ; visit i → n_slots + i
+    for (int32_t slot = 0; slot < n_slots; ++slot) {
+      defs[level[slot]].push_back(slot);
+      frees[v_last[slot]].push_back(slot);
+    }
+    for (int32_t i = 0; i < n_visits; ++i) {
+      defs[t_rev(visits[i].rlevel)].push_back(n_slots + i);
+      frees[a_last[i]].push_back(n_slots + i);
+    }
+    std::vector<int32_t> phys(n_slots + n_visits, -1);
+    std::vector<int32_t> free_list;  // min-heap
+    int32_t n_scratch = 0;
+    auto heap_cmp = std::greater<int32_t>{};
+    for (int32_t t = 0; t <= t_end; ++t) {
+      for (int32_t item : defs[t]) {
+        if (free_list.empty()) {
+          phys[item] = n_scratch++;
+        } else {
+          std::pop_heap(free_list.begin(), free_list.end(), heap_cmp);
+          phys[item] = free_list.back();
+          free_list.pop_back();
+        }
+      }
+      // a slot whose last reader runs at time t is reusable from t+1 on (other
+      // lanes may still be reading it during t)
+      for (int32_t item : frees[t]) {
+        free_list.push_back(phys[item]);
+        std::push_heap(free_list.begin(), free_list.end(), heap_cmp);
+      }
+    }
+    if (n_scratch > 65535) {
+      error = "an expression cluster needs more than 65535 scratch slots; the "
+              "block-cooperative fallback for such graphs is not implemented";
+      return false;
+    }
+    if (n_scratch == 0) n_scratch = 1;
+    auto vp = [&](int32_t slot) {
+      return static_cast<uint16_t>(slot >= 0 ? phys[slot] : 0);
+    };
+    auto ap = [&](int32_t visit) {
+      return static_cast<uint16_t>(phys[n_slots + visit]);
+    };
+
+    // --- emit ----------------------------------------------------------------
+    prog.assign(kProgHeaderWords, 0);
+    auto align2 = [&] {
+      if (prog.size() & 1) prog.push_back(0);
+    };
+    auto push_u16s = [&](const std::vector<uint16_t>& v) {
+      const size_t off = prog.size();
+      prog.resize(off + (v.size() + 1) / 2, 0);
+      if (!v.empty()) {
+        std::memcpy(prog.data() + off, v.data(), v.size() * sizeof(uint16_t));
+      }
+      return static_cast<uint32_t>(off);
+    };
+    auto phys_list = [&](const std::vector<int32_t>& logical, bool adjoint) {
+      std::vector<uint16_t> out;
+      out.reserve(logical.size());
+      for (int32_t x : logical) out.push_back(adjoint ? ap(x) : vp(x));
+      return out;
+    };
+    prog[0] = static_cast<uint32_t>(n_scratch);
+    prog[1] = static_cast<uint32_t>(n_slots + n_visits);  // logical, for stats
+    prog[2] = static_cast<uint32_t>(leaf_slots.size());
+    prog[3] = static_cast<uint32_t>(const_slots.size());
+    prog[4] = static_cast<uint32_t>(fwd_levels.size());
+    prog[5] = static_cast<uint32_t>(rev_levels.size());
+    prog[6] = static_cast<uint32_t>(val_out_slots.size());
+    prog[7] = static_cast<uint32_t>(adj_out_visit.size());
+    prog[8] = push_u16s(phys_list(leaf_slots, false));
+    prog[9] = push_u16s(phys_list(const_slots, false));
+    int32_t max_width = 1;
+    // forward
+    prog[10] = static_cast<uint32_t>(prog.size());
+    {
+      uint32_t run = 0;
+      prog.push_back(run);
+      for (auto& lv : fwd_levels) {
+        run += static_cast<uint32_t>(lv.size());
+        prog.push_back(run);
+        max_width = std::max<int32_t>(max_width, lv.size());
+      }
+    }
+    align2();
+    prog[11] = static_cast<uint32_t>(prog.size());
+    for (auto& lv : fwd_levels) {
+      for (int32_t slot : lv) {
+        const int32_t nd = cl_nodes[slot];
+        FwdInstr in{};
+        in.dst = vp(slot);
+        in.a = vp(local[tape.lhs[nd]]);
+        in.b = tape.rhs[nd] >= 0 ? vp(local[tape.rhs[nd]]) : in.a;
+        in.op = tape.op[nd];
+        uint32_t w[2];
+        std::memcpy(w, &in, 8);
+        prog.push_back(w[0]);
+        prog.push_back(w[1]);
+      }
+    }
+    // reverse
+    prog[12] = static_cast<uint32_t>(prog.size());
+    {
+      uint32_t run = 0;
+      prog.push_back(run);
+      for (auto& lv : rev_levels) {
+        run += static_cast<uint32_t>(lv.size());
+        prog.push_back(run);
+        max_width = std::max<int32_t>(max_width, lv.size());
+      }
+    }
+    align2();
+    prog[13] = static_cast<uint32_t>(prog.size());
+    uint32_t crun = 0;
+    for (auto& lv : rev_levels) {
+      for (int32_t vi : lv) {
+        const VisitTmp& v = visits[vi];
+        Visit rec{};
+        rec.adj = ap(vi);
+        if (v.contribs.empty()) {
+          // a root (seeded) visit; an unseeded node without parents cannot
+          // occur because every non-root node of a list has a parent in it
+          rec.n_contrib = 0;
+          rec.seed = static_cast<int8_t>(v.seed);
+          rec.contrib_begin = 0;
+        } else {
+          if (v.contribs.size() > 254) {
+            error = "a node has more than 254 parents inside one row";
+            return false;
+          }
+          rec.n_contrib = static_cast<uint8_t>(v.contribs.size());
+          rec.seed = 0;
+          rec.contrib_begin = crun;
+          crun += static_cast<uint32_t>(v.contribs.size());
+        }
+        uint32_t w[2];
+        std::memcpy(w, &rec, 8);
+        prog.push_back(w[0]);
+        prog.push_back(w[1]);
+      }
+    }
+    prog[14] = static_cast<uint32_t>(prog.size());
+    for (auto& lv : rev_levels) {
+      for (int32_t vi : lv) {
+        for (const ContribTmp& c : visits[vi].contribs) {
+          Contrib rec{};
+          rec.parent_adj = ap(c.parent_visit);
+          rec.l = vp(c.l);
+          rec.r = vp(c.r);
+          rec.op = c.op;
+          rec.side = c.side;
+          uint32_t w[2];
+          std::memcpy(w, &rec, 8);
+          prog.push_back(w[0]);
+          prog.push_back(w[1]);
+        }
+      }
+    }
+    prog[15] = push_u16s(phys_list(val_out_slots, false));
+    prog[16] = push_u16s(phys_list(adj_out_visit, true));
+    prog[17] = static_cast<uint32_t>(max_width);
+    prog[18] = crun;  // contributions
+    align2();
+    return true;
+  }
+
   /// Builds clusters + programs for `subs`.
   bool build_programs(std::vector<SubRow>& subs, ProgramSet& ps) {
     const int32_t ns = static_cast<int32_t>(subs.size());
@@ -284,7 +584,9 @@ struct Compiler {
     }
 
     std::unordered_map<uint64_t, std::vector<int32_t>> by_hash;
+    std::vector<std::vector<uint32_t>> prog_sig;  // signature of each program
     std::vector<uint32_t> prog;       // program being built
+    std::vector<uint32_t> sig;        // structural signature of the cluster
     std::vector<int32_t> cl_nodes;    // nodes of the cluster, first-seen order
     std::vector<int32_t> level;       // per local slot
     std::vector<int32_t> sorted_ids;
@@ -310,242 +612,93 @@ struct Compiler {
                 "cooperative fallback for such graphs is not implemented";
         return false;
       }
-      // --- forward levels ----------------------------------------------------
-      sorted_ids.assign(cl_nodes.begin(), cl_nodes.end());
-      std::sort(sorted_ids.begin(), sorted_ids.end());
-      level.assign(n_slots, 0);
-      int32_t max_level = 0;
-      for (int32_t nd : sorted_ids) {
-        if (!is_interior(nd)) continue;
-        int32_t lv = level[local[tape.lhs[nd]]];
-        if (tape.rhs[nd] >= 0) lv = std::max(lv, level[local[tape.rhs[nd]]]);
-        level[local[nd]] = lv + 1;
-        max_level = std::max(max_level, lv + 1);
-      }
-      std::vector<std::vector<int32_t>> fwd_levels(max_level);  // local slots
-      std::vector<uint16_t> leaf_slots, const_slots;
-      std::vector<int32_t> leaf_index;
+      // --- binding data (cheap; needed whether or not the program is new) ----
+      std::vector<int32_t> leaf_index, val_out_stage, adj_out_stage;
       std::vector<double> const_vals;
       for (int32_t slot = 0; slot < n_slots; ++slot) {
         const int32_t nd = cl_nodes[slot];
-        if (is_interior(nd)) {
-          fwd_levels[level[slot] - 1].push_back(slot);
-        } else if (tape.op[nd] == SLPB_OP_VAR) {
+        if (is_interior(nd)) continue;
+        if (tape.op[nd] == SLPB_OP_VAR) {
           if (tape.leaf_of_node[nd] < 0) {
             error = "the tape contains a decision-variable node that is not a "
                     "decision variable, y multiplier or z multiplier";
             return false;
           }
-          leaf_slots.push_back(static_cast<uint16_t>(slot));
           leaf_index.push_back(tape.leaf_of_node[nd]);
         } else {
-          const_slots.push_back(static_cast<uint16_t>(slot));
           const_vals.push_back(tape.val[nd]);
         }
       }
-      // --- reverse visits -----------------------------------------------------
-      struct VisitTmp {
-        int32_t adj, rlevel, seed;
-        std::vector<Contrib> contribs;
-      };
-      std::vector<VisitTmp> visits;
-      std::vector<uint16_t> adj_out_slots, val_out_slots;
-      std::vector<int32_t> adj_out_stage, val_out_stage;
       for (int32_t s : mem) {
-        SubRow& sr = subs[s];
+        const SubRow& sr = subs[s];
         if (sr.is_value) {
-          val_out_slots.push_back(static_cast<uint16_t>(local[sr.nodes[0]]));
           val_out_stage.push_back(sr.value_stage);
-          continue;
+        } else {
+          for (auto& [stage, nd] : sr.outs) adj_out_stage.push_back(stage);
         }
+      }
+      // --- structural signature: everything the program depends on, expressed
+      // in cluster-local terms (slot numbers, positions inside each sub-row).
+      // Two clusters with equal signatures get byte-identical programs, so the
+      // program of every time step after the first is found here without
+      // being rebuilt.
+      sig.clear();
+      sig.push_back(static_cast<uint32_t>(mem.size()));
+      sig.push_back(static_cast<uint32_t>(n_slots));
+      for (int32_t s : mem) {
+        const SubRow& sr = subs[s];
         const int32_t len = static_cast<int32_t>(sr.nodes.size());
-        // one visit per active node, in list order; pos[] = visit index
+        sig.push_back(sr.is_value ? 1u : 0u);
+        sig.push_back(static_cast<uint32_t>(static_cast<int32_t>(sr.seed)));
+        sig.push_back(static_cast<uint32_t>(len));
+        sig.push_back(static_cast<uint32_t>(sr.outs.size()));
+        for (int32_t i = 0; i < len; ++i) pos[sr.nodes[i]] = i;
         for (int32_t i = 0; i < len; ++i) {
           const int32_t nd = sr.nodes[i];
-          if (!(sr.flags[i] & kActive)) continue;
-          pos[nd] = static_cast<int32_t>(visits.size());
-          visits.push_back({static_cast<int32_t>(visits.size()), 0, 0, {}});
-        }
-        if (pos[sr.nodes[0]] >= 0) visits[pos[sr.nodes[0]]].seed = sr.seed;
-        for (int32_t i = 0; i < len; ++i) {
-          const int32_t nd = sr.nodes[i];
-          if (pos[nd] < 0 || !is_interior(nd)) continue;
           const int32_t l = tape.lhs[nd], r = tape.rhs[nd];
-          const VisitTmp& pv = visits[pos[nd]];
-          // operands a partial does not read may have no slot: point at 0
-          const uint16_t ls = static_cast<uint16_t>(std::max(local[l], 0));
-          const uint16_t rs =
-              r >= 0 ? static_cast<uint16_t>(std::max(local[r], 0)) : ls;
-          for (int side = 0; side < 2; ++side) {
-            const int32_t ch = side == 0 ? l : r;
-            if (ch < 0 || pos[ch] < 0) continue;
-            VisitTmp& cv = visits[pos[ch]];
-            cv.contribs.push_back({static_cast<uint16_t>(pv.adj), ls, rs,
-                                   tape.op[nd], static_cast<uint8_t>(side)});
-            cv.rlevel = std::max(cv.rlevel, pv.rlevel + 1);
-          }
+          sig.push_back(uint32_t(tape.op[nd]) | (uint32_t(sr.flags[i]) << 8));
+          sig.push_back(static_cast<uint32_t>(local[nd]));
+          sig.push_back(static_cast<uint32_t>(l >= 0 ? pos[l] : -2));
+          sig.push_back(static_cast<uint32_t>(r >= 0 ? pos[r] : -2));
         }
         for (auto& [stage, nd] : sr.outs) {
-          adj_out_slots.push_back(static_cast<uint16_t>(pos[nd]));
-          adj_out_stage.push_back(stage);
+          sig.push_back(static_cast<uint32_t>(pos[nd]));
         }
         for (int32_t i = 0; i < len; ++i) pos[sr.nodes[i]] = -1;
       }
-      const int32_t n_adj = static_cast<int32_t>(visits.size());
-      if (n_adj > 65535) {
-        error = "an expression cluster needs more than 65535 adjoint slots";
-        return false;
-      }
-      int32_t max_rlevel = -1;
-      for (auto& v : visits) max_rlevel = std::max(max_rlevel, v.rlevel);
-      std::vector<std::vector<int32_t>> rev_levels(max_rlevel + 1);
-      for (int32_t i = 0; i < n_adj; ++i) {
-        rev_levels[visits[i].rlevel].push_back(i);
-      }
-
-      // --- emit program ---------------------------------------------------------
-      prog.assign(kProgHeaderWords, 0);
-      auto align2 = [&] {
-        if (prog.size() & 1) prog.push_back(0);
-      };
-      auto push_u16s = [&](const std::vector<uint16_t>& v) {
-        const size_t off = prog.size();
-        prog.resize(off + (v.size() + 1) / 2, 0);
-        if (!v.empty()) {
-          std::memcpy(prog.data() + off, v.data(), v.size() * sizeof(uint16_t));
-        }
-        return static_cast<uint32_t>(off);
-      };
-      prog[0] = n_slots;
-      prog[1] = n_adj;
-      prog[2] = static_cast<uint32_t>(leaf_slots.size());
-      prog[3] = static_cast<uint32_t>(const_slots.size());
-      prog[4] = static_cast<uint32_t>(fwd_levels.size());
-      prog[5] = static_cast<uint32_t>(rev_levels.size());
-      prog[6] = static_cast<uint32_t>(val_out_slots.size());
-      prog[7] = static_cast<uint32_t>(adj_out_slots.size());
-      prog[8] = push_u16s(leaf_slots);
-      prog[9] = push_u16s(const_slots);
-      int32_t max_width = 1;
-      // forward
-      prog[10] = static_cast<uint32_t>(prog.size());
-      {
-        uint32_t run = 0;
-        prog.push_back(run);
-        for (auto& lv : fwd_levels) {
-          run += static_cast<uint32_t>(lv.size());
-          prog.push_back(run);
-          max_width = std::max<int32_t>(max_width, lv.size());
-        }
-      }
-      align2();
-      prog[11] = static_cast<uint32_t>(prog.size());
-      for (auto& lv : fwd_levels) {
-        for (int32_t slot : lv) {
-          const int32_t nd = cl_nodes[slot];
-          FwdInstr in{};
-          in.dst = static_cast<uint16_t>(slot);
-          in.a = static_cast<uint16_t>(local[tape.lhs[nd]]);
-          in.b = tape.rhs[nd] >= 0 ? static_cast<uint16_t>(local[tape.rhs[nd]])
-                                   : in.a;
-          in.op = tape.op[nd];
-          uint32_t w[2];
-          std::memcpy(w, &in, 8);
-          prog.push_back(w[0]);
-          prog.push_back(w[1]);
-          ++ps.n_instr;
-        }
-      }
-      // reverse
-      prog[12] = static_cast<uint32_t>(prog.size());
-      {
-        uint32_t run = 0;
-        prog.push_back(run);
-        for (auto& lv : rev_levels) {
-          run += static_cast<uint32_t>(lv.size());
-          prog.push_back(run);
-          max_width = std::max<int32_t>(max_width, lv.size());
-        }
-      }
-      align2();
-      prog[13] = static_cast<uint32_t>(prog.size());
-      {
-        uint32_t crun = 0;
-        for (auto& lv : rev_levels) {
-          for (int32_t vi : lv) {
-            const VisitTmp& v = visits[vi];
-            Visit rec{};
-            rec.adj = static_cast<uint16_t>(v.adj);
-            if (v.contribs.empty()) {
-              // a root (seeded) visit; an unseeded node without parents cannot
-              // occur because every non-root node of a list has a parent in it
-              rec.n_contrib = 0;
-              rec.seed = static_cast<int8_t>(v.seed);
-              rec.contrib_begin = 0;
-            } else {
-              if (v.contribs.size() > 254) {
-                error = "a node has more than 254 parents inside one row";
-                return false;
-              }
-              rec.n_contrib = static_cast<uint8_t>(v.contribs.size());
-              rec.seed = 0;
-              rec.contrib_begin = crun;
-              crun += static_cast<uint32_t>(v.contribs.size());
-            }
-            uint32_t w[2];
-            std::memcpy(w, &rec, 8);
-            prog.push_back(w[0]);
-            prog.push_back(w[1]);
-            ++ps.n_visits;
-          }
-        }
-      }
-      prog[14] = static_cast<uint32_t>(prog.size());
-      for (auto& lv : rev_levels) {
-        for (int32_t vi : lv) {
-          for (const Contrib& c : visits[vi].contribs) {
-            uint32_t w[2];
-            std::memcpy(w, &c, 8);
-            prog.push_back(w[0]);
-            prog.push_back(w[1]);
-            ++ps.n_contribs;
-          }
-        }
-      }
-      prog[15] = push_u16s(val_out_slots);
-      prog[16] = push_u16s(adj_out_slots);
-      prog[17] = static_cast<uint32_t>(max_width);
-      align2();
-
-      // --- de-duplicate --------------------------------------------------------
       uint64_t h = 1469598103934665603ull;
-      for (uint32_t w : prog) {
+      for (uint32_t w : sig) {
         h ^= w;
         h *= 1099511628211ull;
       }
       int32_t pid = -1;
       for (int32_t cand : by_hash[h]) {
-        const int64_t off = ps.prog_offset[cand];
-        const int64_t len = (cand + 1 < (int32_t)ps.prog_offset.size()
-                                 ? ps.prog_offset[cand + 1]
-                                 : (int64_t)ps.blob.size()) -
-                            off;
-        if (len == (int64_t)prog.size() &&
-            std::memcmp(ps.blob.data() + off, prog.data(),
-                        prog.size() * 4) == 0) {
+        if (prog_sig[cand] == sig) {
           pid = cand;
           break;
         }
       }
       if (pid < 0) {
+        if (!emit_program(subs, mem, cl_nodes, level, sorted_ids, prog, ps)) {
+          return false;
+        }
         pid = static_cast<int32_t>(ps.prog_offset.size());
         ps.prog_offset.push_back(static_cast<int64_t>(ps.blob.size()));
         ps.blob.insert(ps.blob.end(), prog.begin(), prog.end());
-        const int32_t smem = (n_slots + n_adj) * 8;
+        const int32_t smem = static_cast<int32_t>(prog[0]) * 8;
         ps.prog_smem.push_back(smem);
-        ps.prog_width.push_back(max_width);
+        ps.prog_width.push_back(static_cast<int32_t>(prog[17]));
         ps.max_smem = std::max(ps.max_smem, smem);
         by_hash[h].push_back(pid);
+        prog_sig.push_back(sig);
+      }
+      {
+        const uint32_t* P = ps.blob.data() + ps.prog_offset[pid];
+        const uint32_t* fl = P + P[10];
+        const uint32_t* rl = P + P[12];
+        ps.n_instr += fl[P[4]];
+        ps.n_visits += rl[P[5]];
+        ps.n_contribs += P[18];
       }
       // --- binding ---------------------------------------------------------------
       if (ps.bindings.size() & 1) ps.bindings.push_back(0);
@@ -576,6 +729,103 @@ struct Compiler {
 };
 
 }  // namespace
+
+bool build_task_plan(ProgramSet& ps, int32_t smem_budget, std::string& error) {
+  const int32_t n_prog = static_cast<int32_t>(ps.prog_offset.size());
+  const int32_t n_clusters = static_cast<int32_t>(ps.cluster_prog.size());
+  ps.task_prog.clear();
+  ps.task_count.clear();
+  ps.task_lanes.clear();
+  ps.task_bind.clear();
+  ps.task_bindings.clear();
+  ps.launches.clear();
+  std::vector<std::vector<int32_t>> by_prog(n_prog);
+  for (int32_t c = 0; c < n_clusters; ++c) {
+    by_prog[ps.cluster_prog[c]].push_back(c);
+  }
+  // lanes and block size of each program
+  std::vector<int32_t> lanes(n_prog), threads(n_prog);
+  for (int32_t p = 0; p < n_prog; ++p) {
+    const int32_t bytes = std::max(8, ps.prog_smem[p]);
+    if (bytes > smem_budget) {
+      error = "an expression cluster needs " + std::to_string(bytes) +
+              " bytes of scratch, more than one thread block's shared memory; "
+              "the global-memory fallback is not implemented";
+      return false;
+    }
+    int32_t L = 32;
+    while (L > 1 && int64_t(bytes) * L > smem_budget) L >>= 1;
+    // no wider than the clusters available
+    while (L > 1 && L / 2 >= static_cast<int32_t>(by_prog[p].size())) L >>= 1;
+    lanes[p] = L;
+    // enough threads for the widest level, between one warp and 16
+    const int64_t want = int64_t(ps.prog_width[p]) * L;
+    int32_t T = 32;
+    while (T < 512 && T < want) T <<= 1;
+    threads[p] = T;
+  }
+  // launches: one per block size, biggest first; inside, heavy programs first
+  std::vector<int32_t> order(n_prog);
+  std::iota(order.begin(), order.end(), 0);
+  std::stable_sort(order.begin(), order.end(), [&](int32_t a, int32_t b) {
+    if (threads[a] != threads[b]) return threads[a] > threads[b];
+    return ps.prog_smem[a] > ps.prog_smem[b];
+  });
+  for (int32_t p : order) {
+    const uint32_t* P = ps.blob.data() + ps.prog_offset[p];
+    const int32_t n_leaf = static_cast<int32_t>(P[2]);
+    const int32_t n_const = static_cast<int32_t>(P[3]);
+    const int32_t n_val_out = static_cast<int32_t>(P[6]);
+    const int32_t n_adj_out = static_cast<int32_t>(P[7]);
+    const int32_t L = lanes[p];
+    const auto& list = by_prog[p];
+    if (list.empty()) continue;
+    if (ps.launches.empty() || ps.launches.back().threads != threads[p]) {
+      ps.launches.push_back(
+          {static_cast<int32_t>(ps.task_prog.size()), 0, threads[p], 0});
+    }
+    ProgramSet::Launch& launch = ps.launches.back();
+    launch.smem_bytes =
+        std::max(launch.smem_bytes, std::max(8, ps.prog_smem[p]) * L);
+    for (size_t k = 0; k < list.size(); k += L) {
+      const int32_t cnt =
+          static_cast<int32_t>(std::min<size_t>(L, list.size() - k));
+      if (ps.task_bindings.size() & 1) ps.task_bindings.push_back(0);
+      ps.task_prog.push_back(p);
+      ps.task_count.push_back(cnt);
+      ps.task_lanes.push_back(L);
+      ps.task_bind.push_back(static_cast<int64_t>(ps.task_bindings.size()));
+      ++launch.n_tasks;
+      // per-cluster binding layout: leaf_index | pad | const_val | val_out |
+      // adj_out  →  transposed per task
+      const int32_t const_off_c = (n_leaf + 1) & ~1;
+      auto cluster_words = [&](int32_t lane) {
+        const int32_t c = list[k + (lane < cnt ? lane : 0)];
+        return ps.bindings.data() + ps.cluster_bind[c];
+      };
+      const size_t base = ps.task_bindings.size();
+      const int32_t const_off_t = (n_leaf * L + 1) & ~1;
+      const size_t total = size_t(const_off_t) + size_t(2) * n_const * L +
+                           size_t(n_val_out + n_adj_out) * L;
+      ps.task_bindings.resize(base + total, 0);
+      uint32_t* T = ps.task_bindings.data() + base;
+      for (int32_t lane = 0; lane < L; ++lane) {
+        const uint32_t* B = cluster_words(lane);
+        for (int32_t i = 0; i < n_leaf; ++i) T[i * L + lane] = B[i];
+        for (int32_t i = 0; i < n_const; ++i) {
+          T[const_off_t + 2 * (i * L + lane)] = B[const_off_c + 2 * i];
+          T[const_off_t + 2 * (i * L + lane) + 1] = B[const_off_c + 2 * i + 1];
+        }
+        const uint32_t* Bo = B + const_off_c + 2 * n_const;
+        uint32_t* To = T + const_off_t + 2 * n_const * L;
+        for (int32_t i = 0; i < n_val_out + n_adj_out; ++i) {
+          To[i * L + lane] = Bo[i];
+        }
+      }
+    }
+  }
+  return true;
+}
 
 bool compile_autodiff(const Tape& tape, const RowSet rows[SLPB_OUT_COUNT],
                       bool ignore_h_c, CompiledAD& out) {

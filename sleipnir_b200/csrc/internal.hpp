@@ -49,16 +49,20 @@ struct Pattern {
 // Compiled autodiff programs (built by compile.cpp, run by ad_kernels.cu)
 // ---------------------------------------------------------------------------
 //
-// A *cluster* is a connected set of rows that share interior nodes; it is
-// evaluated by one warp with its values and adjoints in shared memory. A
-// *program* is the position-independent code of a cluster (local slot
-// numbers only); clusters whose programs are byte-identical share one copy —
-// every time step of a direct transcription ends up on the same program, with
-// its own *binding* (global leaf indices, constants, output slots).
+// A *cluster* is a connected set of rows that share interior nodes. A
+// *program* is the position-independent code of a cluster (local slot numbers
+// only); clusters whose programs are identical share one copy — every time
+// step of a direct transcription ends up on the same program, with its own
+// *binding* (global leaf indices, constants, output slots). A *task* is up to
+// 32 clusters of one program evaluated side by side by one thread block: lane =
+// cluster, so every warp instruction applies one node of the graph to 32 time
+// steps, and the scratch values/adjoints of the 32 clusters are interleaved in
+// shared memory.
 //
 // Program blob, 32-bit words:
-//   [0] n_slots      value slots (leaves, constants, interior nodes)
-//   [1] n_adj        adjoint slots (one per (row, node) visit)
+//   [0] n_scratch    physical scratch slots per cluster (values and adjoints
+//                    share them; assigned by liveness over the level schedule)
+//   [1] n_logical    value slots + adjoint visits before slot sharing (stats)
 //   [2] n_leaf       [3] n_const
 //   [4] n_fwd_levels [5] n_rev_levels
 //   [6] n_val_out    [7] n_adj_out
@@ -69,15 +73,17 @@ struct Pattern {
 //   [12] off_rev_lvl    u32[n_rev_levels+1]  visit ranges per level
 //   [13] off_visit      Visit[...]
 //   [14] off_contrib    Contrib[...]
-//   [15] off_val_out    u16[n_val_out]  value slot of each value output
-//   [16] off_adj_out    u16[n_adj_out]  adjoint slot of each derivative output
+//   [15] off_val_out    u16[n_val_out]  scratch slot of each value output
+//   [16] off_adj_out    u16[n_adj_out]  scratch slot of each derivative output
 //   [17] max_width      widest level (forward or reverse)
-//   [18..23] reserved
+//   [18] n_contrib      [19..23] reserved
 // Binding record of a cluster, 32-bit words:
 //   leaf_index  i32[n_leaf]      index into the leaf vector
 //   const_val   f64[n_const]     (8-byte aligned)
 //   val_out     i32[n_val_out]   stage slot of each value output
 //   adj_out     i32[n_adj_out]   stage slot of each derivative output
+// Binding block of a task: the same four arrays, each transposed to
+// [entry][lanes] so that the lanes of a warp read consecutive words.
 
 constexpr int kProgHeaderWords = 24;
 
@@ -107,8 +113,22 @@ struct ProgramSet {
   std::vector<int64_t> cluster_bind;   // word offset into `bindings`
   std::vector<uint32_t> bindings;
   int64_t n_instr = 0, n_visits = 0, n_contribs = 0;  // totals over clusters
-  int32_t max_smem = 0;
+  int32_t max_smem = 0;                // largest per-cluster scratch, bytes
+
+  // ---- task plan (build_task_plan) ----
+  std::vector<int32_t> task_prog, task_count, task_lanes;
+  std::vector<int64_t> task_bind;      // word offset into task_bindings
+  std::vector<uint32_t> task_bindings;
+  struct Launch {
+    int32_t first_task, n_tasks, threads, smem_bytes;
+  };
+  std::vector<Launch> launches;        // tasks are sorted by launch
 };
+
+/// Groups the clusters of `ps` into tasks and launches. smem_budget: bytes of
+/// shared memory one task may use. Returns false (error set) when a single
+/// cluster does not fit.
+bool build_task_plan(ProgramSet& ps, int32_t smem_budget, std::string& error);
 
 /// out[e] = Σ_k scale(k) · stage[src_idx[k]] over k ∈ [ptr[e], ptr[e+1]).
 struct Gather {

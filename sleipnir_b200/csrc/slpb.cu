@@ -70,14 +70,11 @@ struct DevBuf {
 };
 
 struct DevProgramSet {
-  DevBuf<uint32_t> blob, bindings;
-  DevBuf<int64_t> prog_offset, cluster_bind;
-  DevBuf<int32_t> cluster_prog;
-  // Warp tasks: every warp evaluates up to 32/G clusters of ONE program in
-  // lockstep, G lanes per cluster. task = {first, count, G, scratch doubles}
-  DevBuf<int32_t> task;           // 4 ints per warp
-  DevBuf<int32_t> cluster_order;  // clusters sorted by program
-  int n_clusters = 0, n_tasks = 0, warps_per_block = 1, smem_per_warp = 0;
+  DevBuf<uint32_t> blob, task_bindings;
+  DevBuf<int64_t> prog_offset, task_bind;
+  DevBuf<int32_t> task_prog, task_count, task_lanes;
+  std::vector<ProgramSet::Launch> launches;
+  int n_tasks = 0, max_smem = 0;
 };
 
 struct DevGather {
@@ -183,41 +180,40 @@ struct WarpSyncMask {
   __device__ __forceinline__ void operator()() const { __syncwarp(mask); }
 };
 
-/// Each warp evaluates up to 32/G clusters of one program in lockstep, G lanes
-/// per cluster; values and adjoints of every cluster live in shared memory.
-/// Replaces update_values + append_triplets (expression_graph.hpp:85-153) for
-/// all rows of a cluster.
-__global__ void k_ad_sweep(const uint32_t* __restrict__ blob,
-                           const int64_t* __restrict__ prog_offset,
-                           const int32_t* __restrict__ cluster_prog,
-                           const int64_t* __restrict__ cluster_bind,
-                           const uint32_t* __restrict__ bindings,
-                           const int32_t* __restrict__ task,
-                           const int32_t* __restrict__ cluster_order,
-                           int n_tasks, int smem_doubles_per_warp,
-                           const double* __restrict__ leaf,
-                           double* __restrict__ stage) {
+struct AdTasks {
+  const uint32_t* blob;
+  const int64_t* prog_offset;
+  const int32_t* task_prog;
+  const int32_t* task_count;
+  const int32_t* task_lanes;
+  const int64_t* task_bind;
+  const uint32_t* task_bindings;
+};
+
+/// One thread block per task = up to 32 clusters (time steps) that share one
+/// program. Lane = cluster: a warp applies ONE graph node to 32 time steps, so
+/// the opcode is warp-uniform and the interleaved scratch (values and adjoints
+/// of all 32 clusters) in shared memory is read without bank conflicts; the
+/// warps of the block take the nodes of a level in turn and the block
+/// synchronises between levels. Replaces update_values + append_triplets
+/// (expression_graph.hpp:85-153) for all rows of the clusters.
+__global__ void __launch_bounds__(512)
+k_ad_sweep(AdTasks A, int first_task, const double* __restrict__ leaf,
+           double* __restrict__ stage) {
   extern __shared__ double smem[];
-  const int warp = threadIdx.x >> 5;
-  const int lane = threadIdx.x & 31;
-  const int w = blockIdx.x * (blockDim.x >> 5) + warp;
-  if (w >= n_tasks) return;
-  const int first = task[4 * w + 0], count = task[4 * w + 1];
-  const int G = task[4 * w + 2], per_cluster = task[4 * w + 3];
-  const int group = lane / G, sub = lane % G;
-  const unsigned mask = __ballot_sync(0xffffffffu, group < count);
-  if (group >= count) return;
-  const int c = cluster_order[first + group];
-  const uint32_t* P = blob + prog_offset[cluster_prog[c]];
-  const uint32_t* B = bindings + cluster_bind[c];
-  double* scratch =
-      smem + size_t(warp) * smem_doubles_per_warp + size_t(group) * per_cluster;
-  const WarpSyncMask sync{mask};
-  switch (G) {
-    case 4: ad_run_cluster<4>(sub, P, B, leaf, stage, scratch, sync); break;
-    case 8: ad_run_cluster<8>(sub, P, B, leaf, stage, scratch, sync); break;
-    case 16: ad_run_cluster<16>(sub, P, B, leaf, stage, scratch, sync); break;
-    default: ad_run_cluster<32>(sub, P, B, leaf, stage, scratch, sync); break;
+  const int t = first_task + blockIdx.x;
+  const uint32_t* P = A.blob + A.prog_offset[A.task_prog[t]];
+  const uint32_t* B = A.task_bindings + A.task_bind[t];
+  const int count = A.task_count[t];
+  const int tid = threadIdx.x, nt = blockDim.x;
+  const BlockSync sync{};
+  switch (A.task_lanes[t]) {
+    case 32: ad_run_group<32>(tid, nt, count, P, B, leaf, stage, smem, sync); break;
+    case 16: ad_run_group<16>(tid, nt, count, P, B, leaf, stage, smem, sync); break;
+    case 8: ad_run_group<8>(tid, nt, count, P, B, leaf, stage, smem, sync); break;
+    case 4: ad_run_group<4>(tid, nt, count, P, B, leaf, stage, smem, sync); break;
+    case 2: ad_run_group<2>(tid, nt, count, P, B, leaf, stage, smem, sync); break;
+    default: ad_run_group<1>(tid, nt, count, P, B, leaf, stage, smem, sync); break;
   }
 }
 
@@ -968,72 +964,27 @@ inline RedBuf red_buf(slpb_solver* S) {
   return {S->red_partials.p, S->red_counter.p};
 }
 
-int upload_program_set(slpb_solver* S, const ProgramSet& ps,
-                       DevProgramSet& d) {
-  d.n_clusters = static_cast<int>(ps.cluster_prog.size());
+/// Shared memory one task may use: two tasks of the largest class stay
+/// co-resident on an SM (228 KB per SM, 1 KB reserved per block).
+constexpr int kAdSmemBudget = 112 * 1024;
+constexpr int kAdSmemMax = 224 * 1024;
+
+int upload_program_set(slpb_solver* S, ProgramSet& ps, DevProgramSet& d) {
+  int budget = kAdSmemBudget;
+  if (ps.max_smem > budget) budget = kAdSmemMax;  // one cluster per block
+  if (const char* e = std::getenv("SLPB_AD_SMEM_BUDGET")) budget = std::atoi(e);
+  if (!build_task_plan(ps, budget, S->error)) return SLPB_ERR_UNSUPPORTED;
+  d.n_tasks = static_cast<int>(ps.task_prog.size());
+  d.launches = ps.launches;
+  d.max_smem = 0;
+  for (const auto& L : d.launches) d.max_smem = std::max(d.max_smem, L.smem_bytes);
   CU(d.blob.upload(ps.blob, S->stream));
-  CU(d.bindings.upload(ps.bindings, S->stream));
   CU(d.prog_offset.upload(ps.prog_offset, S->stream));
-  CU(d.cluster_bind.upload(ps.cluster_bind, S->stream));
-  CU(d.cluster_prog.upload(ps.cluster_prog, S->stream));
-  // lanes per cluster: the average level width of the program, rounded down
-  // to a power of two in [4, 32] (SLPB_AD_GROUP overrides, for experiments)
-  const int n_prog = static_cast<int>(ps.prog_offset.size());
-  int forced = 0;
-  if (const char* e = std::getenv("SLPB_AD_GROUP")) forced = std::atoi(e);
-  std::vector<int> group(n_prog, 32);
-  for (int p = 0; p < n_prog; ++p) {
-    const uint32_t* P = ps.blob.data() + ps.prog_offset[p];
-    const uint32_t levels = std::max<uint32_t>(1, P[4] + P[5]);
-    const uint32_t n_fwd = (P + P[10])[P[4]];
-    const uint32_t n_vis = (P + P[12])[P[5]];
-    const double avg = double(n_fwd + n_vis) / levels;
-    int G = 4;
-    while (G < 32 && 2 * G <= avg) G *= 2;
-    if (forced == 4 || forced == 8 || forced == 16 || forced == 32) G = forced;
-    // keep a warp's scratch within what one SM can hold
-    while (G < 32 && (32 / G) * std::max(8, ps.prog_smem[p]) > 200 * 1024) G *= 2;
-    group[p] = G;
-  }
-  std::vector<int32_t> order(d.n_clusters);
-  for (int c = 0; c < d.n_clusters; ++c) order[c] = c;
-  std::stable_sort(order.begin(), order.end(), [&](int a, int b) {
-    return ps.cluster_prog[a] < ps.cluster_prog[b];
-  });
-  // heavy programs first so the tail of the launch is made of cheap warps
-  std::vector<int> prog_rank(n_prog);
-  for (int p = 0; p < n_prog; ++p) prog_rank[p] = p;
-  std::sort(prog_rank.begin(), prog_rank.end(), [&](int a, int b) {
-    return ps.prog_smem[a] > ps.prog_smem[b];
-  });
-  std::vector<std::vector<int32_t>> by_prog(n_prog);
-  for (int c : order) by_prog[ps.cluster_prog[c]].push_back(c);
-  std::vector<int32_t> tasks, sorted;
-  d.smem_per_warp = 8;
-  for (int p : prog_rank) {
-    const int G = group[p], per = 32 / G;
-    const int per_cluster = std::max(8, ps.prog_smem[p]) / 8;
-    d.smem_per_warp = std::max(d.smem_per_warp, per * per_cluster * 8);
-    const auto& list = by_prog[p];
-    for (size_t k = 0; k < list.size(); k += per) {
-      const int cnt = static_cast<int>(std::min<size_t>(per, list.size() - k));
-      tasks.push_back(static_cast<int32_t>(sorted.size()));
-      tasks.push_back(cnt);
-      tasks.push_back(G);
-      tasks.push_back(per_cluster);
-      for (int q = 0; q < cnt; ++q) sorted.push_back(list[k + q]);
-    }
-  }
-  d.n_tasks = static_cast<int>(tasks.size() / 4);
-  CU(d.task.upload(tasks, S->stream));
-  CU(d.cluster_order.upload(sorted, S->stream));
-  if (d.smem_per_warp > 200 * 1024) {
-    return fail(S, SLPB_ERR_UNSUPPORTED,
-                "an expression cluster needs more than 200 KB of shared "
-                "memory; the global-memory fallback is not implemented");
-  }
-  d.warps_per_block =
-      std::max(1, std::min(8, (96 * 1024) / d.smem_per_warp));
+  CU(d.task_prog.upload(ps.task_prog, S->stream));
+  CU(d.task_count.upload(ps.task_count, S->stream));
+  CU(d.task_lanes.upload(ps.task_lanes, S->stream));
+  CU(d.task_bind.upload(ps.task_bind, S->stream));
+  CU(d.task_bindings.upload(ps.task_bindings, S->stream));
   return SLPB_OK;
 }
 
@@ -1054,13 +1005,14 @@ int upload_gather(slpb_solver* S, const Gather& g, DevGather& d) {
 int run_sweep(slpb_solver* S, const DevProgramSet& d, const double* leaf,
               double* stage) {
   if (d.n_tasks == 0) return SLPB_OK;
-  const int wpb = d.warps_per_block;
-  const int smem = wpb * d.smem_per_warp;
-  k_ad_sweep<<<blocks_for(d.n_tasks, wpb), wpb * 32, smem, S->stream>>>(
-      d.blob.p, d.prog_offset.p, d.cluster_prog.p, d.cluster_bind.p,
-      d.bindings.p, d.task.p, d.cluster_order.p, d.n_tasks,
-      d.smem_per_warp / 8, leaf, stage);
-  ++S->counters.kernel_launches;
+  const AdTasks A{d.blob.p,      d.prog_offset.p, d.task_prog.p,
+                  d.task_count.p, d.task_lanes.p, d.task_bind.p,
+                  d.task_bindings.p};
+  for (const auto& L : d.launches) {
+    k_ad_sweep<<<L.n_tasks, L.threads, L.smem_bytes, S->stream>>>(
+        A, L.first_task, leaf, stage);
+    ++S->counters.kernel_launches;
+  }
   CU(cudaGetLastError());
   return SLPB_OK;
 }
@@ -1426,12 +1378,9 @@ int slpb_finalize(slpb_solver* S) {
   if ((rc = upload_gather(S, S->ad.deriv_gather, S->gd))) return rc;
   CU(S->vstage.upload(S->ad.value_stage_init, S->stream));
   CU(S->dstage.upload(S->ad.deriv_stage_init, S->stream));
-  const int max_wpb_smem =
-      std::max(S->pv.warps_per_block * S->pv.smem_per_warp,
-               S->pd.warps_per_block * S->pd.smem_per_warp);
-  CU(cudaFuncSetAttribute(k_ad_sweep,
-                          cudaFuncAttributeMaxDynamicSharedMemorySize,
-                          std::max(max_wpb_smem, 48 * 1024)));
+  CU(cudaFuncSetAttribute(
+      k_ad_sweep, cudaFuncAttributeMaxDynamicSharedMemorySize,
+      std::max(std::max(S->pv.max_smem, S->pd.max_smem), 48 * 1024)));
 
   CU(S->leaf_cur.alloc(n + me + mi));
   CU(S->leaf_trial.alloc(n + me + mi));
@@ -1487,7 +1436,8 @@ int slpb_finalize(slpb_solver* S) {
   CU(cudaStreamSynchronize(S->stream));
   S->counters.program_bytes =
       int64_t(S->ad.values.blob.size() + S->ad.derivs.blob.size() +
-              S->ad.values.bindings.size() + S->ad.derivs.bindings.size()) * 4;
+              S->ad.values.task_bindings.size() +
+              S->ad.derivs.task_bindings.size()) * 4;
   S->counters.n_clusters = int64_t(S->ad.values.cluster_prog.size() +
                                    S->ad.derivs.cluster_prog.size());
   S->counters.n_program_classes = int64_t(S->ad.values.prog_offset.size() +

@@ -10,6 +10,7 @@
 // never linked into, loaded by or reachable from the product
 // (sleipnir_b200/): the product library has no CPU path and returns
 // SLPB_ERR_NO_DEVICE without a GPU.
+#include <cstdlib>
 #include <cstring>
 #include <memory>
 #include <string>
@@ -62,14 +63,34 @@ slpb::SymbolicView view_of(const slpb::Symbolic& S) {
   return v;
 }
 
+template <int LC>
+void run_task(const slpb::ProgramSet& ps, int t, const double* leaf,
+              double* stage, double* scratch) {
+  const uint32_t* P = ps.blob.data() + ps.prog_offset[ps.task_prog[t]];
+  const uint32_t* B = ps.task_bindings.data() + ps.task_bind[t];
+  // nthreads = LC: every lane owns all items of its own cluster, so the lanes
+  // are independent and may run one after the other
+  for (int tid = 0; tid < LC; ++tid) {
+    slpb::ad_run_group<LC>(tid, LC, ps.task_count[t], P, B, leaf, stage,
+                           scratch, slpb::NoSync{});
+  }
+}
+
+/// Runs the task plan the device would run (same tasks, same transposed
+/// bindings, same lane count per task).
 void run_programs(const slpb::ProgramSet& ps, const double* leaf,
                   double* stage) {
-  std::vector<double> scratch(ps.max_smem / 8 + 1);
-  for (size_t c = 0; c < ps.cluster_prog.size(); ++c) {
-    const uint32_t* P = ps.blob.data() + ps.prog_offset[ps.cluster_prog[c]];
-    const uint32_t* B = ps.bindings.data() + ps.cluster_bind[c];
-    slpb::ad_run_cluster<1>(0, P, B, leaf, stage, scratch.data(),
-                            slpb::NoSync{});
+  std::vector<double> scratch(size_t(ps.max_smem / 8 + 1) * 32);
+  for (size_t t = 0; t < ps.task_prog.size(); ++t) {
+    const int ti = static_cast<int>(t);
+    switch (ps.task_lanes[t]) {
+      case 1: run_task<1>(ps, ti, leaf, stage, scratch.data()); break;
+      case 2: run_task<2>(ps, ti, leaf, stage, scratch.data()); break;
+      case 4: run_task<4>(ps, ti, leaf, stage, scratch.data()); break;
+      case 8: run_task<8>(ps, ti, leaf, stage, scratch.data()); break;
+      case 16: run_task<16>(ps, ti, leaf, stage, scratch.data()); break;
+      default: run_task<32>(ps, ti, leaf, stage, scratch.data()); break;
+    }
   }
 }
 
@@ -115,6 +136,15 @@ void* emu_create(const char* name, int N, double p0, double p1) {
   }
   if (!slpb::compile_autodiff(e->tape, e->rows, false, e->ad)) {
     e->error = e->ad.error;
+    return e.release();
+  }
+  // the device's plan, with a deliberately small budget when asked (so that
+  // tests also cover tasks of fewer than 32 lanes)
+  int32_t budget = 200 * 1024;
+  if (const char* env = std::getenv("SLPB_EMU_SMEM_BUDGET")) budget = std::atoi(env);
+  if (!slpb::build_task_plan(e->ad.values, budget, e->error) ||
+      !slpb::build_task_plan(e->ad.derivs, budget, e->error)) {
+    return e.release();
   }
   return e.release();
 }
