@@ -127,6 +127,14 @@ struct NoSync {
   SLPB_HD void operator()() const {}
 };
 
+/// Instruction stream read straight from the program blob (host emulation,
+/// and the reference point for the device's TMA-staged ring in slpb.cu).
+struct DirectStream {
+  const uint32_t* P;
+  SLPB_HD const uint32_t* acquire(int b) const { return P + (P + P[10])[b]; }
+  SLPB_HD void release(int) const {}
+};
+
 /// Runs one TASK: up to LC clusters that share ONE program, side by side.
 /// Thread `tid` of `nthreads` (a multiple of LC) works for cluster c = tid % LC
 /// on the items q, q+R, … of every level (q = tid / LC, R = nthreads / LC). On
@@ -136,15 +144,17 @@ struct NoSync {
 /// block synchronises between levels. tests/emu runs the same code with
 /// nthreads = LC, one lane after the other.
 ///
-/// `scratch` holds P[0]·LC doubles; values and adjoints share it (the compiler
-/// assigns physical slots by liveness). `B` is the task's binding block,
-/// transposed so that lanes read consecutive words:
+/// `H` is the program's header + tables (P[5] words; in shared memory on the
+/// device); `stream` hands out the level blocks in order (acquire → process →
+/// barrier → release). `scratch` holds H[0]·LC doubles; values and adjoints
+/// share it (the compiler assigns physical slots by liveness). `B` is the
+/// task's binding block, transposed so that lanes read consecutive words:
 ///   leaf_index i32[n_leaf][LC] | pad | const_val f64[n_const][LC]
 ///   | val_out i32[n_val_out][LC] | adj_out i32[n_adj_out][LC]
 /// Lanes ≥ count carry a copy of lane 0's bindings and skip their stores.
-template <int LC, typename Sync>
+template <int LC, typename Stream, typename Sync>
 SLPB_HD void ad_run_group(int tid, int nthreads, int count,
-                          const uint32_t* __restrict__ P,
+                          const uint32_t* __restrict__ H, Stream& stream,
                           const uint32_t* __restrict__ B,
                           const double* __restrict__ leaf,
                           double* __restrict__ stage, double* scratch,
@@ -153,12 +163,11 @@ SLPB_HD void ad_run_group(int tid, int nthreads, int count,
   const int q = tid / LC;
   const int R = nthreads / LC;
   const bool active = c < count;
-  const int n_leaf = static_cast<int>(P[2]);
-  const int n_const = static_cast<int>(P[3]);
-  const int n_fwd_levels = static_cast<int>(P[4]);
-  const int n_rev_levels = static_cast<int>(P[5]);
-  const int n_val_out = static_cast<int>(P[6]);
-  const int n_adj_out = static_cast<int>(P[7]);
+  const int n_leaf = static_cast<int>(H[2]);
+  const int n_const = static_cast<int>(H[3]);
+  const int n_blocks = static_cast<int>(H[4]);
+  const int n_val_out = static_cast<int>(H[6]);
+  const int n_adj_out = static_cast<int>(H[7]);
   double* S = scratch + c;  // slot s of this lane: S[s * LC]
 
   const int32_t* leaf_index = reinterpret_cast<const int32_t*>(B);
@@ -168,8 +177,8 @@ SLPB_HD void ad_run_group(int tid, int nthreads, int count,
       reinterpret_cast<const int32_t*>(B + const_off + 2 * n_const * LC);
   const int32_t* adj_out_stage = val_out_stage + n_val_out * LC;
 
-  const uint16_t* leaf_slot = reinterpret_cast<const uint16_t*>(P + P[8]);
-  const uint16_t* const_slot = reinterpret_cast<const uint16_t*>(P + P[9]);
+  const uint16_t* leaf_slot = reinterpret_cast<const uint16_t*>(H + H[8]);
+  const uint16_t* const_slot = reinterpret_cast<const uint16_t*>(H + H[9]);
   for (int i = q; i < n_leaf; i += R) {
     S[leaf_slot[i] * LC] = leaf[leaf_index[i * LC + c]];
   }
@@ -178,55 +187,51 @@ SLPB_HD void ad_run_group(int tid, int nthreads, int count,
   }
   sync();
 
-  // ---- forward sweep, level by level ----------------------------------------
-  const uint32_t* fwd_lvl = P + P[10];
-  const FwdInstr* fwd = reinterpret_cast<const FwdInstr*>(P + P[11]);
-  for (int L = 0; L < n_fwd_levels; ++L) {
-    const int b = static_cast<int>(fwd_lvl[L]);
-    const int e = static_cast<int>(fwd_lvl[L + 1]);
-    for (int i = b + q; i < e; i += R) {
-      const FwdInstr in = fwd[i];
-      S[in.dst * LC] = ad_op_value(in.op, S[in.a * LC], S[in.b * LC]);
-    }
-    sync();
-  }
-  if (n_val_out > 0) {
-    const uint16_t* val_out_slot =
-        reinterpret_cast<const uint16_t*>(P + P[15]);
-    for (int i = q; i < n_val_out; i += R) {
-      if (active) stage[val_out_stage[i * LC + c]] = S[val_out_slot[i] * LC];
-    }
-    // slots read here may be recycled by the first reverse level
-    if (n_rev_levels > 0) sync();
-  }
-
-  // ---- reverse sweeps: each visit pulls from its parents' adjoints ----------
-  const uint32_t* rev_lvl = P + P[12];
-  const Visit* visit = reinterpret_cast<const Visit*>(P + P[13]);
-  const Contrib* contrib = reinterpret_cast<const Contrib*>(P + P[14]);
-  for (int L = 0; L < n_rev_levels; ++L) {
-    const int b = static_cast<int>(rev_lvl[L]);
-    const int e = static_cast<int>(rev_lvl[L + 1]);
-    for (int i = b + q; i < e; i += R) {
-      const Visit v = visit[i];
-      double a;
-      if (v.n_contrib == 0) {
-        a = static_cast<double>(v.seed);
-      } else {
-        // adjoint starts at 0 and accumulates in the row's parent order
-        a = 0.0;
-        const Contrib* ct = contrib + v.contrib_begin;
-        for (int k = 0; k < v.n_contrib; ++k) {
-          const Contrib ck = ct[k];
-          a += ad_op_grad(ck.op, ck.side, S[ck.parent_adj * LC], S[ck.l * LC],
-                          S[ck.r * LC]);
-        }
+  for (int blk = 0; blk < n_blocks; ++blk) {
+    const uint32_t* Bk = stream.acquire(blk);
+    const uint32_t kind = Bk[0];
+    const int n_items = static_cast<int>(Bk[1]);
+    if (kind == kBlockForward) {
+      // ---- one level of the forward value sweep ------------------------------
+      const FwdInstr* fwd = reinterpret_cast<const FwdInstr*>(Bk + 4);
+      for (int i = q; i < n_items; i += R) {
+        const FwdInstr in = fwd[i];
+        S[in.dst * LC] = ad_op_value(in.op, S[in.a * LC], S[in.b * LC]);
       }
-      S[v.adj * LC] = a;
+    } else if (kind == kBlockReverse) {
+      // ---- one level of the reverse sweeps: each visit pulls from its
+      // parents' adjoints, in the row's parent order --------------------------
+      const Visit* visit = reinterpret_cast<const Visit*>(Bk + 4);
+      const Contrib* contrib =
+          reinterpret_cast<const Contrib*>(Bk + 4 + 2 * n_items);
+      for (int i = q; i < n_items; i += R) {
+        const Visit v = visit[i];
+        double a;
+        if (v.n_contrib == 0) {
+          a = static_cast<double>(v.seed);
+        } else {
+          a = 0.0;
+          const Contrib* ct = contrib + v.contrib_begin;
+          for (int k = 0; k < v.n_contrib; ++k) {
+            const Contrib ck = ct[k];
+            a += ad_op_grad(ck.op, ck.side, S[ck.parent_adj * LC],
+                            S[ck.l * LC], S[ck.r * LC]);
+          }
+        }
+        S[v.adj * LC] = a;
+      }
+    } else {
+      // ---- value outputs (slots read here may be recycled afterwards) --------
+      const uint16_t* val_out_slot =
+          reinterpret_cast<const uint16_t*>(H + H[15]);
+      for (int i = q; i < n_val_out; i += R) {
+        if (active) stage[val_out_stage[i * LC + c]] = S[val_out_slot[i] * LC];
+      }
     }
     sync();
+    stream.release(blk);
   }
-  const uint16_t* adj_out_slot = reinterpret_cast<const uint16_t*>(P + P[16]);
+  const uint16_t* adj_out_slot = reinterpret_cast<const uint16_t*>(H + H[16]);
   for (int i = q; i < n_adj_out; i += R) {
     if (active) stage[adj_out_stage[i * LC + c]] = S[adj_out_slot[i] * LC];
   }

@@ -422,8 +422,8 @@ struct Compiler {
 
     // --- emit ----------------------------------------------------------------
     prog.assign(kProgHeaderWords, 0);
-    auto align2 = [&] {
-      if (prog.size() & 1) prog.push_back(0);
+    auto align4 = [&] {
+      while (prog.size() & 3) prog.push_back(0);
     };
     auto push_u16s = [&](const std::vector<uint16_t>& v) {
       const size_t off = prog.size();
@@ -439,31 +439,54 @@ struct Compiler {
       for (int32_t x : logical) out.push_back(adjoint ? ap(x) : vp(x));
       return out;
     };
+    auto push_record = [&](const void* rec) {
+      uint32_t w[2];
+      std::memcpy(w, rec, 8);
+      prog.push_back(w[0]);
+      prog.push_back(w[1]);
+    };
+    const bool has_valout = !val_out_slots.empty();
+    const int32_t n_blocks = static_cast<int32_t>(fwd_levels.size()) +
+                             (has_valout ? 1 : 0) +
+                             static_cast<int32_t>(rev_levels.size());
     prog[0] = static_cast<uint32_t>(n_scratch);
     prog[1] = static_cast<uint32_t>(n_slots + n_visits);  // logical, for stats
     prog[2] = static_cast<uint32_t>(leaf_slots.size());
     prog[3] = static_cast<uint32_t>(const_slots.size());
-    prog[4] = static_cast<uint32_t>(fwd_levels.size());
-    prog[5] = static_cast<uint32_t>(rev_levels.size());
+    prog[4] = static_cast<uint32_t>(n_blocks);
     prog[6] = static_cast<uint32_t>(val_out_slots.size());
     prog[7] = static_cast<uint32_t>(adj_out_visit.size());
+    // tables (copied to shared memory together with the header)
     prog[8] = push_u16s(phys_list(leaf_slots, false));
     prog[9] = push_u16s(phys_list(const_slots, false));
-    int32_t max_width = 1;
-    // forward
+    prog[15] = push_u16s(phys_list(val_out_slots, false));
+    prog[16] = push_u16s(phys_list(adj_out_visit, true));
     prog[10] = static_cast<uint32_t>(prog.size());
-    {
-      uint32_t run = 0;
-      prog.push_back(run);
-      for (auto& lv : fwd_levels) {
-        run += static_cast<uint32_t>(lv.size());
-        prog.push_back(run);
-        max_width = std::max<int32_t>(max_width, lv.size());
-      }
-    }
-    align2();
-    prog[11] = static_cast<uint32_t>(prog.size());
+    const size_t table_at = prog.size();
+    prog.resize(prog.size() + n_blocks + 1, 0);
+    align4();
+    prog[5] = static_cast<uint32_t>(prog.size());  // prologue words
+    // level blocks, each 16-byte aligned: {kind, n_items, n_contrib, 0} + payload
+    int32_t max_width = 1, blk = 0;
+    uint32_t max_block_words = 4, n_instr = 0, n_contrib_total = 0;
+    auto begin_block = [&](uint32_t kind, uint32_t items, uint32_t contribs) {
+      align4();
+      prog[table_at + blk] = static_cast<uint32_t>(prog.size());
+      prog.push_back(kind);
+      prog.push_back(items);
+      prog.push_back(contribs);
+      prog.push_back(0);
+    };
+    auto end_block = [&] {
+      align4();
+      max_block_words = std::max<uint32_t>(
+          max_block_words,
+          static_cast<uint32_t>(prog.size()) - prog[table_at + blk]);
+      ++blk;
+    };
     for (auto& lv : fwd_levels) {
+      begin_block(kBlockForward, static_cast<uint32_t>(lv.size()), 0);
+      max_width = std::max<int32_t>(max_width, lv.size());
       for (int32_t slot : lv) {
         const int32_t nd = cl_nodes[slot];
         FwdInstr in{};
@@ -471,27 +494,21 @@ struct Compiler {
         in.a = vp(local[tape.lhs[nd]]);
         in.b = tape.rhs[nd] >= 0 ? vp(local[tape.rhs[nd]]) : in.a;
         in.op = tape.op[nd];
-        uint32_t w[2];
-        std::memcpy(w, &in, 8);
-        prog.push_back(w[0]);
-        prog.push_back(w[1]);
+        push_record(&in);
+        ++n_instr;
       }
+      end_block();
     }
-    // reverse
-    prog[12] = static_cast<uint32_t>(prog.size());
-    {
-      uint32_t run = 0;
-      prog.push_back(run);
-      for (auto& lv : rev_levels) {
-        run += static_cast<uint32_t>(lv.size());
-        prog.push_back(run);
-        max_width = std::max<int32_t>(max_width, lv.size());
-      }
+    if (has_valout) {
+      begin_block(kBlockValueOut, 0, 0);
+      end_block();
     }
-    align2();
-    prog[13] = static_cast<uint32_t>(prog.size());
-    uint32_t crun = 0;
     for (auto& lv : rev_levels) {
+      uint32_t nc = 0;
+      for (int32_t vi : lv) nc += static_cast<uint32_t>(visits[vi].contribs.size());
+      begin_block(kBlockReverse, static_cast<uint32_t>(lv.size()), nc);
+      max_width = std::max<int32_t>(max_width, lv.size());
+      uint32_t crun = 0;
       for (int32_t vi : lv) {
         const VisitTmp& v = visits[vi];
         Visit rec{};
@@ -509,17 +526,11 @@ struct Compiler {
           }
           rec.n_contrib = static_cast<uint8_t>(v.contribs.size());
           rec.seed = 0;
-          rec.contrib_begin = crun;
+          rec.contrib_begin = crun;  // relative to the block's contributions
           crun += static_cast<uint32_t>(v.contribs.size());
         }
-        uint32_t w[2];
-        std::memcpy(w, &rec, 8);
-        prog.push_back(w[0]);
-        prog.push_back(w[1]);
+        push_record(&rec);
       }
-    }
-    prog[14] = static_cast<uint32_t>(prog.size());
-    for (auto& lv : rev_levels) {
       for (int32_t vi : lv) {
         for (const ContribTmp& c : visits[vi].contribs) {
           Contrib rec{};
@@ -528,18 +539,21 @@ struct Compiler {
           rec.r = vp(c.r);
           rec.op = c.op;
           rec.side = c.side;
-          uint32_t w[2];
-          std::memcpy(w, &rec, 8);
-          prog.push_back(w[0]);
-          prog.push_back(w[1]);
+          push_record(&rec);
         }
       }
+      n_contrib_total += nc;
+      end_block();
     }
-    prog[15] = push_u16s(phys_list(val_out_slots, false));
-    prog[16] = push_u16s(phys_list(adj_out_visit, true));
+    align4();
+    prog[table_at + n_blocks] = static_cast<uint32_t>(prog.size());
+    prog[11] = max_block_words;
+    prog[12] = static_cast<uint32_t>(fwd_levels.size());
+    prog[13] = static_cast<uint32_t>(rev_levels.size());
+    prog[14] = n_instr;
     prog[17] = static_cast<uint32_t>(max_width);
-    prog[18] = crun;  // contributions
-    align2();
+    prog[18] = n_contrib_total;
+    prog[19] = static_cast<uint32_t>(n_visits);
     return true;
   }
 
@@ -694,10 +708,8 @@ struct Compiler {
       }
       {
         const uint32_t* P = ps.blob.data() + ps.prog_offset[pid];
-        const uint32_t* fl = P + P[10];
-        const uint32_t* rl = P + P[12];
-        ps.n_instr += fl[P[4]];
-        ps.n_visits += rl[P[5]];
+        ps.n_instr += P[14];
+        ps.n_visits += P[19];
         ps.n_contribs += P[18];
       }
       // --- binding ---------------------------------------------------------------
@@ -745,16 +757,19 @@ bool build_task_plan(ProgramSet& ps, int32_t smem_budget, std::string& error) {
   }
   // lanes and block size of each program
   std::vector<int32_t> lanes(n_prog), threads(n_prog);
+  auto task_bytes = [&](int32_t p, int32_t L) {
+    const uint32_t* P = ps.blob.data() + ps.prog_offset[p];
+    return ad_smem_layout(P[0], P[5], P[11], L).total;
+  };
   for (int32_t p = 0; p < n_prog; ++p) {
-    const int32_t bytes = std::max(8, ps.prog_smem[p]);
-    if (bytes > smem_budget) {
-      error = "an expression cluster needs " + std::to_string(bytes) +
-              " bytes of scratch, more than one thread block's shared memory; "
+    if (task_bytes(p, 1) > smem_budget) {
+      error = "an expression cluster needs " + std::to_string(task_bytes(p, 1)) +
+              " bytes of shared memory, more than one thread block has; "
               "the global-memory fallback is not implemented";
       return false;
     }
     int32_t L = 32;
-    while (L > 1 && int64_t(bytes) * L > smem_budget) L >>= 1;
+    while (L > 1 && task_bytes(p, L) > smem_budget) L >>= 1;
     // no wider than the clusters available
     while (L > 1 && L / 2 >= static_cast<int32_t>(by_prog[p].size())) L >>= 1;
     lanes[p] = L;
@@ -785,8 +800,7 @@ bool build_task_plan(ProgramSet& ps, int32_t smem_budget, std::string& error) {
           {static_cast<int32_t>(ps.task_prog.size()), 0, threads[p], 0});
     }
     ProgramSet::Launch& launch = ps.launches.back();
-    launch.smem_bytes =
-        std::max(launch.smem_bytes, std::max(8, ps.prog_smem[p]) * L);
+    launch.smem_bytes = std::max(launch.smem_bytes, task_bytes(p, L));
     for (size_t k = 0; k < list.size(); k += L) {
       const int32_t cnt =
           static_cast<int32_t>(std::min<size_t>(L, list.size() - k));

@@ -59,24 +59,30 @@ struct Pattern {
 // steps, and the scratch values/adjoints of the 32 clusters are interleaved in
 // shared memory.
 //
-// Program blob, 32-bit words:
+// Program blob, 32-bit words (every program starts 16-byte aligned):
 //   [0] n_scratch    physical scratch slots per cluster (values and adjoints
 //                    share them; assigned by liveness over the level schedule)
 //   [1] n_logical    value slots + adjoint visits before slot sharing (stats)
 //   [2] n_leaf       [3] n_const
-//   [4] n_fwd_levels [5] n_rev_levels
+//   [4] n_blocks     level blocks in the instruction stream
+//   [5] prologue_words  header + tables: what a thread block keeps resident
 //   [6] n_val_out    [7] n_adj_out
 //   [8] off_leaf_slot   u16[n_leaf]   (word offsets from blob start)
 //   [9] off_const_slot  u16[n_const]
-//   [10] off_fwd_lvl    u32[n_fwd_levels+1]  instruction ranges per level
-//   [11] off_fwd        FwdInstr[...]
-//   [12] off_rev_lvl    u32[n_rev_levels+1]  visit ranges per level
-//   [13] off_visit      Visit[...]
-//   [14] off_contrib    Contrib[...]
+//   [10] off_block_table u32[n_blocks+1]  word offset of each level block
+//   [11] max_block_words  largest level block (ring-buffer stage size)
+//   [12] n_fwd_levels [13] n_rev_levels [14] n_instr   (stats)
 //   [15] off_val_out    u16[n_val_out]  scratch slot of each value output
 //   [16] off_adj_out    u16[n_adj_out]  scratch slot of each derivative output
 //   [17] max_width      widest level (forward or reverse)
-//   [18] n_contrib      [19..23] reserved
+//   [18] n_contrib [19] n_visits (stats)  [20..23] reserved
+//   tables …, then the INSTRUCTION STREAM: one 16-byte-aligned block per level,
+//   in execution order, {kind, n_items, n_contrib, 0} followed by
+//     kBlockForward:  FwdInstr[n_items]
+//     kBlockValueOut: nothing (value outputs are stored at this point)
+//     kBlockReverse:  Visit[n_items], Contrib[n_contrib]
+//   The device streams these blocks through a shared-memory ring with TMA bulk
+//   copies (cp.async.bulk + mbarrier) a few levels ahead of their use.
 // Binding record of a cluster, 32-bit words:
 //   leaf_index  i32[n_leaf]      index into the leaf vector
 //   const_val   f64[n_const]     (8-byte aligned)
@@ -86,6 +92,28 @@ struct Pattern {
 // [entry][lanes] so that the lanes of a warp read consecutive words.
 
 constexpr int kProgHeaderWords = 24;
+constexpr uint32_t kBlockForward = 0, kBlockReverse = 1, kBlockValueOut = 2;
+constexpr int kAdStages = 4;  // ring-buffer stages of the instruction stream
+
+/// Shared-memory layout of one task (bytes from the start of dynamic shared
+/// memory): scratch | header+tables | instruction ring | mbarriers.
+struct AdSmemLayout {
+  int32_t off_prologue, off_ring, off_bars, total;
+};
+#if defined(__CUDACC__)
+__host__ __device__
+#endif
+inline AdSmemLayout ad_smem_layout(uint32_t n_scratch, uint32_t prologue_words,
+                                   uint32_t max_block_words, int lanes) {
+  AdSmemLayout L;
+  const uint32_t scratch = (n_scratch * uint32_t(lanes) * 8u + 15u) & ~15u;
+  L.off_prologue = static_cast<int32_t>(scratch);
+  L.off_ring =
+      static_cast<int32_t>((scratch + prologue_words * 4u + 15u) & ~15u);
+  L.off_bars = L.off_ring + kAdStages * static_cast<int32_t>(max_block_words) * 4;
+  L.total = L.off_bars + kAdStages * 8;
+  return L;
+}
 
 struct FwdInstr {  // 8 bytes
   uint16_t dst, a, b;

@@ -190,30 +190,121 @@ struct AdTasks {
   const uint32_t* task_bindings;
 };
 
+// ---- TMA-staged instruction stream ------------------------------------------
+__device__ __forceinline__ uint32_t smem_u32(const void* p) {
+  return static_cast<uint32_t>(__cvta_generic_to_shared(p));
+}
+__device__ __forceinline__ void mbar_init(uint64_t* bar, uint32_t count) {
+  asm volatile("mbarrier.init.shared::cta.b64 [%0], %1;" ::"r"(smem_u32(bar)),
+               "r"(count)
+               : "memory");
+}
+__device__ __forceinline__ void mbar_expect_tx(uint64_t* bar, uint32_t bytes) {
+  asm volatile("mbarrier.arrive.expect_tx.shared::cta.b64 _, [%0], %1;" ::"r"(
+                   smem_u32(bar)),
+               "r"(bytes)
+               : "memory");
+}
+__device__ __forceinline__ void mbar_wait(uint64_t* bar, uint32_t parity) {
+  asm volatile(
+      "{\n"
+      ".reg .pred p;\n"
+      "WAIT_%=:\n"
+      "mbarrier.try_wait.parity.shared::cta.b64 p, [%0], %1;\n"
+      "@p bra DONE_%=;\n"
+      "bra WAIT_%=;\n"
+      "DONE_%=:\n"
+      "}\n" ::"r"(smem_u32(bar)),
+      "r"(parity)
+      : "memory");
+}
+/// 1-D TMA bulk copy global → shared, completion counted on an mbarrier.
+__device__ __forceinline__ void tma_bulk_g2s(void* dst, const void* src,
+                                             uint32_t bytes, uint64_t* bar) {
+  asm volatile(
+      "cp.async.bulk.shared::cluster.global.mbarrier::complete_tx::bytes "
+      "[%0], [%1], %2, [%3];" ::"r"(smem_u32(dst)),
+      "l"(src), "r"(bytes), "r"(smem_u32(bar))
+      : "memory");
+}
+
+/// The level blocks of a program travel global → shared memory through a ring
+/// of kAdStages buffers, kAdStages − 1 levels ahead of their use: thread 0
+/// issues one TMA bulk copy per block, every thread waits on the stage's
+/// mbarrier before decoding it, and the block's level barrier frees the stage.
+struct TmaStream {
+  const uint32_t* Pg;      // program in global memory
+  const uint32_t* table;   // block table (shared memory copy)
+  uint32_t* ring;
+  uint64_t* bars;
+  int n_blocks, stage_words;
+  bool issuer;
+  __device__ __forceinline__ void issue(int b) const {
+    const int st = b % kAdStages;
+    const uint32_t bytes = (table[b + 1] - table[b]) * 4u;
+    mbar_expect_tx(&bars[st], bytes);
+    tma_bulk_g2s(ring + st * stage_words, Pg + table[b], bytes, &bars[st]);
+  }
+  __device__ __forceinline__ const uint32_t* acquire(int b) const {
+    const int st = b % kAdStages;
+    mbar_wait(&bars[st], (b / kAdStages) & 1);
+    return ring + st * stage_words;
+  }
+  /// Called by every thread after the level barrier of block b.
+  __device__ __forceinline__ void release(int b) const {
+    if (issuer && b + kAdStages < n_blocks) issue(b + kAdStages);
+  }
+};
+
 /// One thread block per task = up to 32 clusters (time steps) that share one
 /// program. Lane = cluster: a warp applies ONE graph node to 32 time steps, so
 /// the opcode is warp-uniform and the interleaved scratch (values and adjoints
 /// of all 32 clusters) in shared memory is read without bank conflicts; the
 /// warps of the block take the nodes of a level in turn and the block
-/// synchronises between levels. Replaces update_values + append_triplets
+/// synchronises between levels. The program itself is streamed through shared
+/// memory by TMA (TmaStream). Replaces update_values + append_triplets
 /// (expression_graph.hpp:85-153) for all rows of the clusters.
 __global__ void __launch_bounds__(512)
 k_ad_sweep(AdTasks A, int first_task, const double* __restrict__ leaf,
            double* __restrict__ stage) {
-  extern __shared__ double smem[];
+  extern __shared__ __align__(16) unsigned char smem_raw[];
   const int t = first_task + blockIdx.x;
   const uint32_t* P = A.blob + A.prog_offset[A.task_prog[t]];
   const uint32_t* B = A.task_bindings + A.task_bind[t];
   const int count = A.task_count[t];
+  const int lanes = A.task_lanes[t];
   const int tid = threadIdx.x, nt = blockDim.x;
+  const uint32_t n_scratch = __ldg(P + 0), pro_words = __ldg(P + 5);
+  const uint32_t stage_words = __ldg(P + 11);
+  const AdSmemLayout lay = ad_smem_layout(n_scratch, pro_words, stage_words, lanes);
+  double* scratch = reinterpret_cast<double*>(smem_raw);
+  uint32_t* H = reinterpret_cast<uint32_t*>(smem_raw + lay.off_prologue);
+  uint32_t* ring = reinterpret_cast<uint32_t*>(smem_raw + lay.off_ring);
+  uint64_t* bars = reinterpret_cast<uint64_t*>(smem_raw + lay.off_bars);
+  // header + tables → shared memory (16-byte vectors)
+  {
+    const uint4* src = reinterpret_cast<const uint4*>(P);
+    uint4* dst = reinterpret_cast<uint4*>(H);
+    for (uint32_t i = tid; i < pro_words / 4; i += nt) dst[i] = __ldg(src + i);
+  }
+  if (tid == 0) {
+    for (int s = 0; s < kAdStages; ++s) mbar_init(&bars[s], 1);
+    asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
+  }
+  __syncthreads();
+  TmaStream stream{P, H + H[10], ring, bars, static_cast<int>(H[4]),
+                   static_cast<int>(stage_words), tid == 0};
+  if (tid == 0) {
+    for (int b = 0; b < kAdStages && b < stream.n_blocks; ++b) stream.issue(b);
+  }
   const BlockSync sync{};
-  switch (A.task_lanes[t]) {
-    case 32: ad_run_group<32>(tid, nt, count, P, B, leaf, stage, smem, sync); break;
-    case 16: ad_run_group<16>(tid, nt, count, P, B, leaf, stage, smem, sync); break;
-    case 8: ad_run_group<8>(tid, nt, count, P, B, leaf, stage, smem, sync); break;
-    case 4: ad_run_group<4>(tid, nt, count, P, B, leaf, stage, smem, sync); break;
-    case 2: ad_run_group<2>(tid, nt, count, P, B, leaf, stage, smem, sync); break;
-    default: ad_run_group<1>(tid, nt, count, P, B, leaf, stage, smem, sync); break;
+  switch (lanes) {
+    case 32: ad_run_group<32>(tid, nt, count, H, stream, B, leaf, stage, scratch, sync); break;
+    case 16: ad_run_group<16>(tid, nt, count, H, stream, B, leaf, stage, scratch, sync); break;
+    case 8: ad_run_group<8>(tid, nt, count, H, stream, B, leaf, stage, scratch, sync); break;
+    case 4: ad_run_group<4>(tid, nt, count, H, stream, B, leaf, stage, scratch, sync); break;
+    case 2: ad_run_group<2>(tid, nt, count, H, stream, B, leaf, stage, scratch, sync); break;
+    default: ad_run_group<1>(tid, nt, count, H, stream, B, leaf, stage, scratch, sync); break;
   }
 }
 

@@ -70,9 +70,10 @@ void run_task(const slpb::ProgramSet& ps, int t, const double* leaf,
   const uint32_t* B = ps.task_bindings.data() + ps.task_bind[t];
   // nthreads = LC: every lane owns all items of its own cluster, so the lanes
   // are independent and may run one after the other
+  slpb::DirectStream stream{P};
   for (int tid = 0; tid < LC; ++tid) {
-    slpb::ad_run_group<LC>(tid, LC, ps.task_count[t], P, B, leaf, stage,
-                           scratch, slpb::NoSync{});
+    slpb::ad_run_group<LC>(tid, LC, ps.task_count[t], P, stream, B, leaf,
+                           stage, scratch, slpb::NoSync{});
   }
 }
 
