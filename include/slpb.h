@@ -252,6 +252,20 @@ typedef struct slpb_factor_info {
 int slpb_factor(slpb_solver* s, double delta, double gamma, int reassemble,
                 slpb_factor_info* info);
 
+/* Speculative pair: factors lhs + diag(δ₀, −γ₀) and lhs + diag(δ₁, −γ₁) in ONE
+ * launch (two independent numeric factorisations over the same symbolic
+ * structure). The reference's retry loop (sparse_regularized_ldlt.hpp:64-104)
+ * always tries (0, 0) first and knows its second candidate (δ, γ_min) before
+ * the first attempt returns, so both can run side by side; the host then keeps
+ * the one the sequential algorithm would have kept (slpb_select_factor) and the
+ * decision sequence is unchanged. info[v] describes variant v. */
+int slpb_factor_pair(slpb_solver* s, const double delta[2],
+                     const double gamma[2], int reassemble,
+                     slpb_factor_info info[2]);
+/* Chooses which variant (0 or 1) of the last factorisation slpb_solve /
+ * slpb_soc_iterate / SLPB_ARR_D use. slpb_factor always selects 0. */
+int slpb_select_factor(slpb_solver* s, int which);
+
 typedef struct slpb_step_info {
   double alpha_max;  /* fraction-to-the-boundary on (s, p_s)            */
   double alpha_z;    /* fraction-to-the-boundary on (z, p_z)            */

@@ -107,7 +107,8 @@ ABI_SYMBOLS = [
     "slpb_set_ignore_constraint_hessian", "slpb_analyze",
     "slpb_get_permutation", "slpb_set_iterate", "slpb_get_iterate",
     "slpb_eval_current", "slpb_kkt_stats_current", "slpb_kkt_stats_trial",
-    "slpb_factor", "slpb_solve", "slpb_soc_begin", "slpb_soc_iterate",
+    "slpb_factor", "slpb_factor_pair", "slpb_select_factor", "slpb_solve",
+    "slpb_soc_begin", "slpb_soc_iterate",
     "slpb_trial", "slpb_accept", "slpb_array_size", "slpb_download",
     "slpb_pattern", "slpb_get_counters", "slpb_get_timers",
     "slpb_last_device_ms", "slpb_stream",
@@ -138,6 +139,9 @@ def device_lib() -> C.CDLL:
         L.slpb_kkt_stats_trial.argtypes = [vp, C.c_double, C.POINTER(KktStats)]
         L.slpb_factor.argtypes = [vp, C.c_double, C.c_double, C.c_int,
                                   C.POINTER(FactorInfo)]
+        L.slpb_factor_pair.argtypes = [vp, _dp, _dp, C.c_int,
+                                       C.POINTER(FactorInfo)]
+        L.slpb_select_factor.argtypes = [vp, C.c_int]
         L.slpb_solve.argtypes = [vp, C.c_double, C.c_double, C.POINTER(StepInfo)]
         L.slpb_soc_begin.argtypes = [vp]
         L.slpb_soc_iterate.argtypes = [vp, C.c_double, C.c_double, C.c_double,
@@ -279,6 +283,20 @@ class DeviceSession:
         self._check(self.L.slpb_factor(self.raw, delta, gamma, int(reassemble),
                                        C.byref(info)), "slpb_factor")
         return info
+
+    def factor_pair(self, delta, gamma, reassemble=True):
+        """Two regularisations factored side by side; returns (info0, info1)."""
+        info = (FactorInfo * 2)()
+        d = np.ascontiguousarray(delta, dtype=np.float64)
+        g = np.ascontiguousarray(gamma, dtype=np.float64)
+        self._check(self.L.slpb_factor_pair(self.raw, _d(d), _d(g),
+                                            int(reassemble), info),
+                    "slpb_factor_pair")
+        return info[0], info[1]
+
+    def select_factor(self, which):
+        self._check(self.L.slpb_select_factor(self.raw, which),
+                    "slpb_select_factor")
 
     def solve(self, mu, tau):
         info = StepInfo()

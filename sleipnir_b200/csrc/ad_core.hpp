@@ -196,7 +196,16 @@ SLPB_HD void ad_run_group(int tid, int nthreads, int count,
       const FwdInstr* fwd = reinterpret_cast<const FwdInstr*>(Bk + 4);
       for (int i = q; i < n_items; i += R) {
         const FwdInstr in = fwd[i];
-        S[in.dst * LC] = ad_op_value(in.op, S[in.a * LC], S[in.b * LC]);
+        const double l = S[in.a * LC], r = S[in.b * LC];
+        double v;
+        if (in.op == SLPB_OP_MUL) {  // the common ops first
+          v = l * r;
+        } else if (in.op == SLPB_OP_ADD) {
+          v = l + r;
+        } else {
+          v = ad_op_value(in.op, l, r);
+        }
+        S[in.dst * LC] = v;
       }
     } else if (kind == kBlockReverse) {
       // ---- one level of the reverse sweeps: each visit pulls from its
@@ -214,8 +223,12 @@ SLPB_HD void ad_run_group(int tid, int nthreads, int count,
           const Contrib* ct = contrib + v.contrib_begin;
           for (int k = 0; k < v.n_contrib; ++k) {
             const Contrib ck = ct[k];
-            a += ad_op_grad(ck.op, ck.side, S[ck.parent_adj * LC],
-                            S[ck.l * LC], S[ck.r * LC]);
+            const double pa = S[ck.parent_adj * LC], lv = S[ck.l * LC];
+            if (ck.op == kOpLinear) {
+              a += pa * lv;  // adjoint × (±1 or the other factor): no decode
+            } else {
+              a += ad_op_grad(ck.op, ck.side, pa, lv, S[ck.r * LC]);
+            }
           }
         }
         S[v.adj * LC] = a;

@@ -287,6 +287,13 @@ struct Compiler {
       int32_t parent_visit, l, r;  // l, r: logical value slots or −1
       uint8_t op, side;
     };
+    // Partials of +, −, unary − and × are "adjoint × multiplier" with the
+    // multiplier +1, −1 or an operand value: a·(±1) is exact, so those
+    // contributions are emitted as kOpLinear records (multiplier slot in `l`)
+    // that the kernel evaluates without decoding an opcode. ±1 live in two
+    // synthetic constant slots (logical ids n_slots, n_slots + 1).
+    bool uses_unit_consts = false;
+    const int32_t slot_plus1 = n_slots, slot_minus1 = n_slots + 1;
     struct VisitTmp {
       int32_t rlevel, seed;
       std::vector<ContribTmp> contribs;
@@ -324,6 +331,25 @@ struct Compiler {
           c.r = (needs & 2) ? (r >= 0 ? local[r] : local[l]) : -1;
           c.op = tape.op[nd];
           c.side = static_cast<uint8_t>(side);
+          switch (tape.op[nd]) {
+            case SLPB_OP_ADD:
+              c.op = kOpLinear, c.l = slot_plus1, c.r = -1;
+              break;
+            case SLPB_OP_SUB:
+              c.op = kOpLinear, c.l = side == 0 ? slot_plus1 : slot_minus1;
+              c.r = -1;
+              break;
+            case SLPB_OP_NEG:
+              c.op = kOpLinear, c.l = slot_minus1, c.r = -1;
+              break;
+            case SLPB_OP_MUL:
+              c.op = kOpLinear, c.l = side == 0 ? local[r] : local[l];
+              c.r = -1;
+              break;
+            default:
+              break;
+          }
+          if (c.op == kOpLinear && c.l >= n_slots) uses_unit_consts = true;
           cv.contribs.push_back(c);
           cv.rlevel = std::max(cv.rlevel, visits[pv].rlevel + 1);
         }
@@ -346,8 +372,11 @@ struct Compiler {
     const int32_t t_valout = Lf + 1;
     const int32_t t_end = Lf + 2 + (max_rlevel + 1);
     auto t_rev = [&](int32_t rl) { return Lf + 2 + rl; };
-    std::vector<int32_t> v_last(n_slots), a_last(n_visits);
-    for (int32_t slot = 0; slot < n_slots; ++slot) v_last[slot] = level[slot];
+    const int32_t n_synth = uses_unit_consts ? 2 : 0;
+    const int32_t n_val = n_slots + n_synth;  // value-like items
+    std::vector<int32_t> v_last(n_val), a_last(n_visits);
+    level.resize(n_val, 0);  // synthetic constants are loaded at time 0
+    for (int32_t slot = 0; slot < n_val; ++slot) v_last[slot] = level[slot];
     for (int32_t slot = 0; slot < n_slots; ++slot) {
       const int32_t nd = cl_nodes[slot];
       if (!is_interior(nd)) continue;
@@ -378,15 +407,15 @@ struct Compiler {
     // visit index); items released after each time
     std::vector<std::vector<int32_t>> defs(t_end + 1), frees(t_end + 1);
     // item id: value slot s → s ; visit i → n_slots + i
-    for (int32_t slot = 0; slot < n_slots; ++slot) {
+    for (int32_t slot = 0; slot < n_val; ++slot) {
       defs[level[slot]].push_back(slot);
       frees[v_last[slot]].push_back(slot);
     }
     for (int32_t i = 0; i < n_visits; ++i) {
-      defs[t_rev(visits[i].rlevel)].push_back(n_slots + i);
-      frees[a_last[i]].push_back(n_slots + i);
+      defs[t_rev(visits[i].rlevel)].push_back(n_val + i);
+      frees[a_last[i]].push_back(n_val + i);
     }
-    std::vector<int32_t> phys(n_slots + n_visits, -1);
+    std::vector<int32_t> phys(n_val + n_visits, -1);
     std::vector<int32_t> free_list;  // min-heap
     int32_t n_scratch = 0;
     auto heap_cmp = std::greater<int32_t>{};
@@ -417,8 +446,9 @@ struct Compiler {
       return static_cast<uint16_t>(slot >= 0 ? phys[slot] : 0);
     };
     auto ap = [&](int32_t visit) {
-      return static_cast<uint16_t>(phys[n_slots + visit]);
+      return static_cast<uint16_t>(phys[n_val + visit]);
     };
+    for (int32_t k = 0; k < n_synth; ++k) const_slots.push_back(n_slots + k);
 
     // --- emit ----------------------------------------------------------------
     prog.assign(kProgHeaderWords, 0);
@@ -554,6 +584,7 @@ struct Compiler {
     prog[17] = static_cast<uint32_t>(max_width);
     prog[18] = n_contrib_total;
     prog[19] = static_cast<uint32_t>(n_visits);
+    prog[20] = static_cast<uint32_t>(n_synth);  // trailing ±1 constants
     return true;
   }
 
@@ -705,6 +736,10 @@ struct Compiler {
         ps.max_smem = std::max(ps.max_smem, smem);
         by_hash[h].push_back(pid);
         prog_sig.push_back(sig);
+      }
+      if ((ps.blob.data() + ps.prog_offset[pid])[20] == 2) {
+        const_vals.push_back(1.0);
+        const_vals.push_back(-1.0);
       }
       {
         const uint32_t* P = ps.blob.data() + ps.prog_offset[pid];

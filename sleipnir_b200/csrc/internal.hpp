@@ -75,7 +75,9 @@ struct Pattern {
 //   [15] off_val_out    u16[n_val_out]  scratch slot of each value output
 //   [16] off_adj_out    u16[n_adj_out]  scratch slot of each derivative output
 //   [17] max_width      widest level (forward or reverse)
-//   [18] n_contrib [19] n_visits (stats)  [20..23] reserved
+//   [18] n_contrib [19] n_visits (stats)
+//   [20] n_synth     trailing constants +1, −1 appended by the compiler
+//   [21..23] reserved
 //   tables …, then the INSTRUCTION STREAM: one 16-byte-aligned block per level,
 //   in execution order, {kind, n_items, n_contrib, 0} followed by
 //     kBlockForward:  FwdInstr[n_items]
@@ -93,6 +95,9 @@ struct Pattern {
 
 constexpr int kProgHeaderWords = 24;
 constexpr uint32_t kBlockForward = 0, kBlockReverse = 1, kBlockValueOut = 2;
+/// Contrib.op of a contribution that is adjoint × (value in slot l): the
+/// partials of +, −, unary − (multiplier ±1) and × (the other operand).
+constexpr uint8_t kOpLinear = 255;
 constexpr int kAdStages = 4;  // ring-buffer stages of the instruction stream
 
 /// Shared-memory layout of one task (bytes from the start of dynamic shared

@@ -89,6 +89,92 @@ __device__ __forceinline__ void wait_children(const int* p, int need) {
   __threadfence();
 }
 
+/// Elimination of the own columns of a front of order F ≤ 32 with the rows in
+/// registers, then the write-out of the L panel and the update matrix.
+/// Lane i keeps row i, shifted so that w[0] is always the current pivot column
+/// (w[jj] = W(i, k + jj)): one compact loop body serves every pivot (a fully
+/// unrolled 32 × 32 elimination does not fit the instruction cache). Pivot k:
+/// lane k broadcasts d, every lane i > k forms l_ik = w_ik / d, the unscaled
+/// w_jk travels from lane j by shuffle and W(i,j) −= l_ik · w_jk — the same
+/// products in the same order as ldlt_factor_front, with no shared-memory
+/// round trip and no warp barrier per pivot. Inertia counters are meaningful
+/// in lane 0 only.
+__device__ __noinline__ void ldlt_eliminate_rows(
+    int lane, int F, int np, int m, const double* __restrict__ W,
+    double* __restrict__ Dk, double* __restrict__ P, double* __restrict__ U,
+    int* __restrict__ local_stats) {
+  double w[32];
+#pragma unroll
+  for (int j = 0; j < 32; ++j) {
+    w[j] = (lane < F && j <= lane) ? W[lane + j * F] : 0.0;
+  }
+  int pos = 0, neg = 0, zero = 0, zpiv = 0;
+  double min_abs = INFINITY;
+#pragma unroll 1
+  for (int k = 0; k < np; ++k) {
+    const double d = __shfl_sync(0xffffffffu, w[0], k);
+    {
+      // inertia bookkeeping (every lane computes it; lane 0 reports it)
+      const double eps = 2.220446049250313e-16;
+      pos += d > eps ? 1 : 0;
+      neg += d < -eps ? 1 : 0;
+      zero += (d > eps || d < -eps) ? 0 : 1;
+      zpiv |= d == 0.0 ? 1 : 0;
+      min_abs = fmin(min_abs, fabs(d));
+    }
+    if (lane == 0) Dk[k] = d;
+    const double wk = w[0];
+    // 0 / d: div.rn.f64 sends a zero dividend through its ~90-instruction
+    // special-case subroutine, and every lane outside the column (and every
+    // structural zero inside it) would drag the warp through it on every
+    // pivot. The quotient is a signed zero: form it directly (same bits).
+    double l;
+    if (wk == 0.0 && d == d && d != 0.0) {
+      l = (signbit(wk) != signbit(d)) ? -0.0 : 0.0;
+    } else {
+      l = wk / d;
+    }
+    // column k of the L panel (the diagonal slot keeps d, as in the generic body)
+    if (lane < F) P[lane + k * F] = lane > k ? l : wk;
+    // trailing update in branch-free groups of 8 columns, so that the eight
+    // shuffles and multiply-subtracts of a group overlap
+#pragma unroll
+    for (int g = 0; g < 4; ++g) {
+      if (k + 1 + 8 * g < F) {
+#pragma unroll
+        for (int q = 0; q < 8; ++q) {
+          const int jj = 1 + 8 * g + q;
+          if (jj < 32) {
+            const int j = k + jj;
+            const double wjk = __shfl_sync(0xffffffffu, wk, j & 31);
+            const double upd = w[jj] - l * wjk;
+            w[jj] = (j < F && lane >= j) ? upd : w[jj];
+          }
+        }
+      }
+    }
+#pragma unroll
+    for (int jj = 0; jj < 31; ++jj) w[jj] = w[jj + 1];
+    w[31] = 0.0;
+  }
+  // update matrix (m × m, lower): w[jj] now holds column np + jj
+#pragma unroll
+  for (int jj = 0; jj < 32; ++jj) {
+    if (jj < m && lane >= np + jj && lane < F) {
+      U[(lane - np) + jj * m] = w[jj];
+    }
+  }
+  if (lane == 0) {
+    local_stats[0] = pos;
+    local_stats[1] = neg;
+    local_stats[2] = zero;
+    local_stats[3] = zpiv;
+    const unsigned long long bits = __double_as_longlong(min_abs);
+    local_stats[4] = static_cast<int>(bits & 0xffffffffull);
+    local_stats[5] = static_cast<int>(bits >> 32);
+  }
+}
+
 /// W: F×F column-major in shared memory; col: 64 doubles of shared scratch
 /// (scaled pivot column in [0,32), unscaled in [32,64)). `dep` is polled by
 /// lane 0 AFTER everything that does not depend on the children is done.
@@ -164,77 +250,12 @@ __device__ __forceinline__ void ldlt_factor_front_warp(
     __syncwarp();
   }
 
-  // ---- elimination of the own columns ----------------------------------------
-  int pos = 0, neg = 0, zero = 0, zpiv = 0;
-  double min_abs = INFINITY;
-  double* lcol = col;        // l_ik
-  double* wcol = col + 32;   // d·l_ik (unscaled column)
-  for (int k = 0; k < np; ++k) {
-    const double d = W[k + k * F];
-    if (lane == 0) {
-      const double eps = 2.220446049250313e-16;
-      if (d > eps) {
-        ++pos;
-      } else if (d < -eps) {
-        ++neg;
-      } else {
-        ++zero;
-      }
-      if (d == 0.0) zpiv = 1;
-      min_abs = fmin(min_abs, fabs(d));
-      D[c0 + k] = d;
-    }
-    if (lane > k && lane < F) {
-      const double w = W[lane + k * F];
-      wcol[lane] = w;
-      lcol[lane] = w / d;
-    }
-    __syncwarp();
-    // trailing triangle of order r, spread element-wise over the lanes
-    const int r = F - k - 1;
-    const int T = r * (r + 1) / 2;
-    const int o = k + 1;
-    for (int e0 = lane; e0 < T; e0 += 128) {
-      int idx[4];
-      double wv[4], lv[4], cv[4];
-#pragma unroll
-      for (int q = 0; q < 4; ++q) {
-        const int e = e0 + 32 * q;
-        const bool on = e < T;
-        const uchar2 ab = tri[on ? e : 0];
-        const int i = o + ab.x, j = o + ab.y;
-        idx[q] = on ? i + j * F : -1;
-        lv[q] = lcol[i];
-        cv[q] = wcol[j];
-        wv[q] = on ? W[i + j * F] : 0.0;
-      }
-#pragma unroll
-      for (int q = 0; q < 4; ++q) {
-        if (idx[q] >= 0) W[idx[q]] = wv[q] - lv[q] * cv[q];
-      }
-    }
-    __syncwarp();
-    if (lane > k && lane < F) W[lane + k * F] = lcol[lane];
-  }
-  __syncwarp();
-
-  // ---- L panel (F × np) and update matrix (m × m, lower) ----------------------
-  double* P = panels + fm.panel_off;
-  for (int e = lane; e < F * np; e += 32) P[e] = W[e];
-  double* U = updates + fm.update_off;
-  for (int j = 0; j < m; ++j) {
-    const int i = j + lane;
-    if (i < m) U[i + j * m] = W[(np + i) + (np + j) * F];
-  }
-  if (lane == 0) {
-    local_stats[0] = pos;
-    local_stats[1] = neg;
-    local_stats[2] = zero;
-    local_stats[3] = zpiv;
-    const unsigned long long bits = __double_as_longlong(min_abs);
-    local_stats[4] = static_cast<int>(bits & 0xffffffffull);
-    local_stats[5] = static_cast<int>(bits >> 32);
-  }
+  // ---- elimination of the own columns + write-out (separate function so that
+  // the 32-double row stays in registers) --------------------------------------
+  (void)col;
+  (void)tri;
+  ldlt_eliminate_rows(lane, F, np, m, W, D + c0, panels + fm.panel_off,
+                      updates + fm.update_off, local_stats);
 }
 
 /// Forward substitution on a front (same arithmetic as ldlt_forward_front).

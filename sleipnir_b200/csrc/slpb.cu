@@ -133,6 +133,7 @@ struct slpb_solver {
   DevBuf<unsigned long long> tree_debug;
   bool use_tree = false;
   int tree_blocks = 0, tree_smem_doubles = 0;
+  int factor_sel = 0;  // which variant of the last factorisation the solves use
   SymbolicView sview{};
   // device: steps
   DevBuf<double> px, ps, py, pz, spx, sps, spy, spz, ce_soc, cis_soc;
@@ -799,11 +800,21 @@ __device__ __forceinline__ unsigned long long global_ns() {
   return t;
 }
 
+/// Second regularisation of a speculative pair (slpb_factor_pair) and where its
+/// results go: variant v of the factorisation writes panels + v·panel_stride,
+/// updates + v·update_stride, D + v·dim and stats + 8·v.
+struct FactorPair {
+  int n_variants;
+  double delta1, gamma1;
+  int64_t panel_stride, update_stride;
+  int32_t dim;
+};
+
 __global__ void __launch_bounds__(kTreeWarps * 32)
 k_factor_tree(TreeView T, const double* __restrict__ Kval, double delta,
-              double gamma, double* __restrict__ panels, double* updates,
-              double* __restrict__ D, int32_t* __restrict__ stats,
-              int smem_doubles_per_warp) {
+              double gamma, FactorPair pair, double* __restrict__ panels,
+              double* updates, double* __restrict__ D,
+              int32_t* __restrict__ stats, int smem_doubles_per_warp) {
   extern __shared__ double smem[];
   __shared__ int ls[kTreeWarps][6];
   __shared__ uchar2 tri[kTriEntries];
@@ -812,30 +823,38 @@ k_factor_tree(TreeView T, const double* __restrict__ Kval, double delta,
   const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
   double* W = smem + size_t(warp) * smem_doubles_per_warp;
   double* col = W + (smem_doubles_per_warp - 64);
-  int32_t* fcount = T.sync + 1;
+  const int nv = pair.n_variants;
   for (;;) {
     int t = 0;
     if (lane == 0) t = atomicAdd(&T.sync[0], 1);
     t = __shfl_sync(0xffffffffu, t, 0);
-    if (t >= T.n_super) break;
-    const int s = T.order[t];
+    if (t >= nv * T.n_super) break;
+    // both variants of a front hold neighbouring tickets: children (of either
+    // variant) always hold smaller tickets than their parents
+    const int v = nv == 2 ? (t & 1) : 0;
+    const int s = T.order[nv == 2 ? (t >> 1) : t];
     const FrontMeta fm = load_front_meta(T.metas + s);
-    if (T.debug && lane == 0) T.debug[3 * s] = global_ns();
-    ldlt_factor_front_warp(lane, fm, T.metas, T.child_idx, T.rel_idx, T.asm_src,
-                           T.asm_dst, T.col_is_primal, Kval, delta, gamma,
-                           panels, updates, D, W, col, tri, &fcount[s],
-                           ls[warp], T.debug ? T.debug + 3 * s + 1 : nullptr);
+    int32_t* fcount = T.sync + 1 + v * T.n_super;
+    int32_t* vstats = stats + 8 * v;
+    if (T.debug && lane == 0 && v == 0) T.debug[3 * s] = global_ns();
+    ldlt_factor_front_warp(
+        lane, fm, T.metas, T.child_idx, T.rel_idx, T.asm_src, T.asm_dst,
+        T.col_is_primal, Kval, v ? pair.delta1 : delta,
+        v ? pair.gamma1 : gamma, panels + v * pair.panel_stride,
+        updates + v * pair.update_stride, D + v * pair.dim, W, col, tri,
+        &fcount[s], ls[warp],
+        (T.debug && v == 0) ? T.debug + 3 * s + 1 : nullptr);
     __syncwarp();
-    if (T.debug && lane == 0) T.debug[3 * s + 2] = global_ns();
+    if (T.debug && lane == 0 && v == 0) T.debug[3 * s + 2] = global_ns();
     if (lane == 0) {
-      atomicAdd(&stats[0], ls[warp][0]);
-      atomicAdd(&stats[1], ls[warp][1]);
-      atomicAdd(&stats[2], ls[warp][2]);
-      atomicOr(&stats[3], ls[warp][3]);
+      atomicAdd(&vstats[0], ls[warp][0]);
+      atomicAdd(&vstats[1], ls[warp][1]);
+      atomicAdd(&vstats[2], ls[warp][2]);
+      atomicOr(&vstats[3], ls[warp][3]);
       const unsigned long long bits =
           (unsigned long long)(unsigned)ls[warp][4] |
           ((unsigned long long)(unsigned)ls[warp][5] << 32);
-      atomicMin(reinterpret_cast<unsigned long long*>(&stats[4]), bits);
+      atomicMin(reinterpret_cast<unsigned long long*>(&vstats[4]), bits);
       __threadfence();
       if (fm.parent >= 0) atomicAdd(&fcount[fm.parent], 1);
     }
@@ -1280,7 +1299,9 @@ int launch_solve(slpb_solver* S) {
                        S->stream));
     const TreeView T = tree_view(S);
     k_solve_tree<<<S->tree_blocks, kTreeWarps * 32, 0, S->stream>>>(
-        T, S->panels.p, S->D.p, S->rhs.p, S->xperm.p, S->uvecs.p, S->sol.p);
+        T, S->panels.p + S->factor_sel * Y.panel_size,
+        S->D.p + size_t(S->factor_sel) * Y.dim, S->rhs.p, S->xperm.p,
+        S->uvecs.p, S->sol.p);
     ++S->counters.kernel_launches;
   } else {
     const int smem = Y.max_front * static_cast<int>(sizeof(double));
@@ -1590,12 +1611,13 @@ int slpb_analyze(slpb_solver* S, int ordering, const int32_t* perm,
   CU(S->sy_col_is_primal.upload(Y.col_is_primal, S->stream));
   CU(S->sy_perm.upload(Y.perm, S->stream));
   CU(S->sy_level_supers.upload(Y.level_supers, S->stream));
-  CU(S->panels.alloc(Y.panel_size));
-  CU(S->updates.alloc(Y.update_size));
-  CU(S->D.alloc(Y.dim));
+  // two variants: slpb_factor_pair factors two regularisations side by side
+  CU(S->panels.alloc(2 * Y.panel_size));
+  CU(S->updates.alloc(2 * Y.update_size));
+  CU(S->D.alloc(2 * size_t(Y.dim)));
   CU(S->uvecs.alloc(Y.rel_ptr.back()));
   CU(S->xperm.alloc(Y.dim));
-  CU(S->fstats.alloc(8));
+  CU(S->fstats.alloc(16));
   {
     std::vector<int32_t> nchild(Y.n_super);
     for (int32_t q = 0; q < Y.n_super; ++q) {
@@ -1633,7 +1655,7 @@ int slpb_analyze(slpb_solver* S, int ordering, const int32_t* perm,
   // about two blocks of warps per SM: enough to cover the widest level in a
   // couple of passes without parking thousands of warps on a spin-wait
   S->tree_blocks = std::max(
-      1, std::min(blocks_for(Y.n_super, kTreeWarps), 148 * 2));
+      1, std::min(blocks_for(2 * Y.n_super, kTreeWarps), 148 * 2));
   {
     const int tree_smem =
         kTreeWarps * S->tree_smem_doubles * static_cast<int>(sizeof(double));
@@ -1764,9 +1786,12 @@ int slpb_kkt_stats_trial(slpb_solver* S, double mu, slpb_kkt_stats* out) {
                    S->tx.p, S->ts.p, S->ty.p, S->tz.p, mu, out);
 }
 
-int slpb_factor(slpb_solver* S, double delta, double gamma, int reassemble,
-                slpb_factor_info* info) {
-  if (!S || !S->analyzed || !info) return SLPB_ERR_STATE;
+namespace {
+
+/// Assembles (optionally) and factors one or two regularisations of the KKT
+/// matrix in one dependency-driven launch.
+int factor_impl(slpb_solver* S, int n_variants, const double* delta,
+                const double* gamma, int reassemble, slpb_factor_info* info) {
   CU(cudaSetDevice(S->device));
   const Symbolic& Y = S->sym;
   if (reassemble) {
@@ -1788,50 +1813,86 @@ int slpb_factor(slpb_solver* S, double delta, double gamma, int reassemble,
     S->pending[2] = true;
   }
   CU(cudaEventRecord(S->ev[6], S->stream));
-  // stats: n_pos n_neg n_zero zero_pivot | min|D| bits (+inf)
+  // stats per variant: n_pos n_neg n_zero zero_pivot | min|D| bits (+inf)
   {
-    int32_t init[8] = {0, 0, 0, 0, 0, 0, 0, 0};
+    int32_t init[16] = {};
     const double inf = INFINITY;
     std::memcpy(&init[4], &inf, 8);
+    std::memcpy(&init[12], &inf, 8);
     CU(cudaMemcpyAsync(S->fstats.p, init, sizeof(init), cudaMemcpyHostToDevice,
                        S->stream));
   }
   if (S->use_tree) {
-    CU(cudaMemsetAsync(S->tree_sync.p, 0, (1 + size_t(Y.n_super)) * 4,
+    CU(cudaMemsetAsync(S->tree_sync.p, 0, (1 + 2 * size_t(Y.n_super)) * 4,
                        S->stream));
     const TreeView T = tree_view(S);
     const int smem =
         kTreeWarps * S->tree_smem_doubles * static_cast<int>(sizeof(double));
+    const FactorPair pair{n_variants,
+                          n_variants == 2 ? delta[1] : 0.0,
+                          n_variants == 2 ? gamma[1] : 0.0,
+                          Y.panel_size,
+                          Y.update_size,
+                          Y.dim};
     k_factor_tree<<<S->tree_blocks, kTreeWarps * 32, smem, S->stream>>>(
-        T, S->Kval.p, delta, gamma, S->panels.p, S->updates.p, S->D.p,
-        S->fstats.p, S->tree_smem_doubles);
+        T, S->Kval.p, delta[0], gamma[0], pair, S->panels.p, S->updates.p,
+        S->D.p, S->fstats.p, S->tree_smem_doubles);
     ++S->counters.kernel_launches;
   } else {
     const int smem = static_cast<int>(
         (size_t(Y.max_front) * Y.max_front + Y.max_front) * sizeof(double));
-    for (int L = 0; L < Y.n_levels; ++L) {
-      const int cnt = Y.level_ptr[L + 1] - Y.level_ptr[L];
-      k_factor_level<<<cnt, kFrontThreads, smem, S->stream>>>(
-          S->sview, S->sy_level_supers.p + Y.level_ptr[L], S->Kval.p, delta,
-          gamma, S->panels.p, S->updates.p, S->D.p, S->fstats.p);
+    for (int v = 0; v < n_variants; ++v) {
+      for (int L = 0; L < Y.n_levels; ++L) {
+        const int cnt = Y.level_ptr[L + 1] - Y.level_ptr[L];
+        k_factor_level<<<cnt, kFrontThreads, smem, S->stream>>>(
+            S->sview, S->sy_level_supers.p + Y.level_ptr[L], S->Kval.p,
+            delta[v], gamma[v], S->panels.p + v * Y.panel_size,
+            S->updates.p + v * Y.update_size, S->D.p + size_t(v) * Y.dim,
+            S->fstats.p + 8 * v);
+      }
+      S->counters.kernel_launches += Y.n_levels;
     }
-    S->counters.kernel_launches += Y.n_levels;
   }
   CU(cudaEventRecord(S->ev[7], S->stream));
   S->pending[3] = true;
   CU(cudaGetLastError());
-  int32_t host_stats[8];
+  int32_t host_stats[16];
   CU(cudaMemcpyAsync(host_stats, S->fstats.p, sizeof(host_stats),
                      cudaMemcpyDeviceToHost, S->stream));
   CU(cudaStreamSynchronize(S->stream));
   harvest_timers(S);
   S->counters.d2h_bytes += sizeof(host_stats);
-  info->n_pos = host_stats[0];
-  info->n_neg = host_stats[1];
-  info->n_zero = host_stats[2];
-  info->zero_pivot = host_stats[3];
-  std::memcpy(&info->min_abs_d, &host_stats[4], 8);
-  ++S->counters.factorizations;
+  for (int v = 0; v < n_variants; ++v) {
+    info[v].n_pos = host_stats[8 * v + 0];
+    info[v].n_neg = host_stats[8 * v + 1];
+    info[v].n_zero = host_stats[8 * v + 2];
+    info[v].zero_pivot = host_stats[8 * v + 3];
+    std::memcpy(&info[v].min_abs_d, &host_stats[8 * v + 4], 8);
+  }
+  S->counters.factorizations += n_variants;
+  S->factor_sel = 0;
+  return SLPB_OK;
+}
+
+}  // namespace
+
+int slpb_factor(slpb_solver* S, double delta, double gamma, int reassemble,
+                slpb_factor_info* info) {
+  if (!S || !S->analyzed || !info) return SLPB_ERR_STATE;
+  return factor_impl(S, 1, &delta, &gamma, reassemble, info);
+}
+
+int slpb_factor_pair(slpb_solver* S, const double delta[2],
+                     const double gamma[2], int reassemble,
+                     slpb_factor_info info[2]) {
+  if (!S || !S->analyzed || !info || !delta || !gamma) return SLPB_ERR_STATE;
+  return factor_impl(S, 2, delta, gamma, reassemble, info);
+}
+
+int slpb_select_factor(slpb_solver* S, int which) {
+  if (!S || !S->analyzed) return SLPB_ERR_STATE;
+  if (which != 0 && which != 1) return SLPB_ERR_ARGUMENT;
+  S->factor_sel = which;
   return SLPB_OK;
 }
 
@@ -1964,7 +2025,7 @@ int slpb_download(slpb_solver* S, int which, double* dst) {
     case SLPB_ARR_A_I_VAL: src = S->dvals.p + S->ad.off_ai; break;
     case SLPB_ARR_H_VAL: src = S->dvals.p + S->ad.off_h; break;
     case SLPB_ARR_KKT_VAL: src = S->Kval.p; break;
-    case SLPB_ARR_D: src = S->D.p; break;
+    case SLPB_ARR_D: src = S->D.p + size_t(S->factor_sel) * S->dim; break;
     case SLPB_ARR_RHS: src = S->rhs.p; break;
     case SLPB_ARR_P_X: src = S->px.p; break;
     case SLPB_ARR_P_S: src = S->ps.p; break;

@@ -163,21 +163,48 @@ class DeviceRegularizedLDLT {
         m_me{num_equality_constraints}, m_gamma_min{gamma_min} {}
 
   /// Returns false on NumericalIssue (δ or γ beyond 1e20).
+  ///
+  /// The decision sequence is the reference's: try (0, 0); then (δ, γ_min) with
+  /// δ from the previous solve; then grow δ/γ by the inertia seen. The second
+  /// candidate is known before the first attempt returns, so when the previous
+  /// iteration needed regularisation both are factored side by side in one
+  /// launch (slpb_factor_pair) and the one the sequential loop would have kept
+  /// is selected. `factorizations` counts the attempts of the sequential
+  /// algorithm (what the reference would have run).
   bool compute() {
     slpb_factor_info info{};
-    factor(0.0, 0.0, /*reassemble=*/1, info);
-    if (!info.zero_pivot && ideal(info) && info.min_abs_d >= 1e-4) {
-      m_prev_delta = 0.0;
-      m_prev_gamma = 0.0;
-      return true;
-    }
     double delta = m_prev_delta == 0.0
                        ? 1e-4
                        : std::max(m_prev_delta / 2.0,
                                   std::numeric_limits<double>::epsilon());
     double gamma = m_gamma_min;
+    bool have_second = false;
+    slpb_factor_info second{};
+    if (m_speculate && m_prev_delta != 0.0) {
+      const double d2[2] = {0.0, delta}, g2[2] = {0.0, gamma};
+      slpb_factor_info pair[2]{};
+      ++factorizations;
+      SLP_DEVICE_CALL(m_dev, slpb_factor_pair(m_dev, d2, g2, 1, pair));
+      info = pair[0];
+      second = pair[1];
+      have_second = true;
+    } else {
+      factor(0.0, 0.0, /*reassemble=*/1, info);
+    }
+    if (!info.zero_pivot && ideal(info) && info.min_abs_d >= 1e-4) {
+      m_prev_delta = 0.0;
+      m_prev_gamma = 0.0;
+      return true;
+    }
     while (true) {
-      factor(delta, gamma, /*reassemble=*/0, info);
+      if (have_second) {
+        have_second = false;
+        ++factorizations;
+        info = second;
+        SLP_DEVICE_CALL(m_dev, slpb_select_factor(m_dev, 1));
+      } else {
+        factor(delta, gamma, /*reassemble=*/0, info);
+      }
       if (!info.zero_pivot) {
         if (ideal(info)) {
           m_prev_delta = delta;
@@ -215,6 +242,8 @@ class DeviceRegularizedLDLT {
     m_prev_gamma = gamma;
   }
   int factorizations = 0;
+  /// Enables the side-by-side factorisation of the first two candidates.
+  void set_speculation(bool on) { m_speculate = on; }
 
  private:
   bool ideal(const slpb_factor_info& i) const {
@@ -230,6 +259,7 @@ class DeviceRegularizedLDLT {
   int m_n, m_me;
   double m_gamma_min;
   double m_prev_delta = 0.0, m_prev_gamma = 0.0;
+  bool m_speculate = true;
 };
 
 namespace detail {

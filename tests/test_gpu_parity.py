@@ -151,6 +151,40 @@ def test_newton_step_vs_oracle(name, N):
     P.close_device(); P.close(); O.close()
 
 
+def test_factor_pair_matches_two_single_factorisations():
+    """slpb_factor_pair (two regularisations in one launch) gives, variant by
+    variant, the bits of two separate slpb_factor calls, and slpb_select_factor
+    makes the solve use the chosen one."""
+    name, N = "cart_pole", 80
+    P, O = sb.Problem(name, N), OracleProblem(name, N)
+    O.eval_setup()
+    d_f, d_ce, d_ci = O.scaling()
+    D = P.open_device()
+    D.set_scaling(d_f, d_ce, d_ci)
+    x, s, y, z = _state(P, O, 5)
+    D.set_iterate(x, s, y, z)
+    D.eval_current(1)
+    D.analyze()
+    regs = [(0.0, 0.0), (1e-2, 1e-8)]
+    single = []
+    for delta, gamma in regs:
+        fi = D.factor(delta, gamma, True)
+        si = D.solve(0.05, 0.99)
+        single.append((fi, D.download(sb.ARR_D), D.download(sb.ARR_P_X), si.alpha_max))
+    f0, f1 = D.factor_pair([r[0] for r in regs], [r[1] for r in regs], True)
+    for v, fi in enumerate((f0, f1)):
+        ref = single[v][0]
+        assert (fi.n_pos, fi.n_neg, fi.n_zero, fi.zero_pivot) == (
+            ref.n_pos, ref.n_neg, ref.n_zero, ref.zero_pivot)
+        assert fi.min_abs_d == ref.min_abs_d
+        D.select_factor(v)
+        np.testing.assert_array_equal(D.download(sb.ARR_D), single[v][1])
+        si = D.solve(0.05, 0.99)
+        np.testing.assert_array_equal(D.download(sb.ARR_P_X), single[v][2])
+        assert si.alpha_max == single[v][3]
+    P.close_device(); P.close(); O.close()
+
+
 def test_trial_point_and_accept():
     name, N = "cart_pole", 60
     P, O = sb.Problem(name, N), OracleProblem(name, N)
