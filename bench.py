@@ -9,9 +9,11 @@ A *step* is one Newton iteration of the interior-point loop
 the cart-pole direct-transcription problem of the reference's scalability
 benchmark (benchmarks/scalability/cart_pole/sleipnir.cpp, T = 5 s, dt = T/N),
 N = 5000 by default, started from the benchmark's initial guess. W warm-up
-iterations are followed by exactly K timed ones inside one solve; every
+iterations are followed by exactly K timed ones inside one solve (K = 200 by
+default: a cart-pole solve of this size runs for hundreds of iterations); every
 iteration ends with a device→host read of its scalars, so the host timestamps
-taken at iteration boundaries are device-complete.
+taken at iteration boundaries are device-complete. The L2 is evicted before
+every timed iteration (excluded from the timestamps).
 
 Prints ONE JSON line (see README/DESIGN for the field meanings).
 """
@@ -126,7 +128,7 @@ def run_cpu(horizon, steps, warmup):
 def main():
     ap = argparse.ArgumentParser()
     ap.add_argument("--gpus", type=int, default=1)
-    ap.add_argument("--steps", type=int, default=60)
+    ap.add_argument("--steps", type=int, default=200)
     ap.add_argument("--warmup", type=int, default=5)
     ap.add_argument("--impl", default="b200", choices=["b200", "reference"])
     ap.add_argument("--horizon", type=int, default=5000)
@@ -147,8 +149,8 @@ def main():
     if args.impl == "reference":
         if rank != 0:
             return
-        # bounded sample: at most ~25 iterations of the same workload
-        k = min(args.steps, 20)
+        # bounded sample: at most 60 iterations (≈10 s) of the same workload
+        k = min(args.steps, 60)
         w = min(args.warmup, 3)
         r = run_cpu(N, k, w)
         line = {
@@ -186,41 +188,68 @@ def main():
     peaks, peak_kind = measured_peaks()
 
     P = sb.Problem("cart_pole", N)
-    # untimed: build + compile + first solve to warm caches / clocks
+    # untimed: build + compile + first solve to warm the context / clocks
     P.solve(max_iterations=args.warmup, device=local_rank)
     P.close()
 
-    P = sb.Problem("cart_pole", N)
-    if world > 1:
-        dist.barrier()
-    torch.cuda.synchronize()
-    with ClockSampler(local_rank) as clk:
-        t0 = time.perf_counter()
-        P.solve(max_iterations=args.warmup + args.steps, device=local_rank)
+    def one_solve(flush):
+        Q = sb.Problem("cart_pole", N)
+        Q.set_flush_l2(flush)
+        if world > 1:
+            dist.barrier()
         torch.cuda.synchronize()
-        total_s = time.perf_counter() - t0
-    tr = P.trace()
-    k, dt = steady_rate(tr, args.warmup, args.steps)
-    if world > 1:
-        t = torch.tensor([dt], device="cuda", dtype=torch.float64)
-        dist.all_reduce(t, op=dist.ReduceOp.MAX)
-        dt = float(t.item())
-        tt = torch.tensor([total_s], device="cuda", dtype=torch.float64)
-        dist.all_reduce(tt, op=dist.ReduceOp.MAX)
-        total_s = float(tt.item())
-    rate = world * k / dt
-    cnt, tim, sym = P.counters(), P.timers(), P.symbolic_stats()
-    iters = len(tr)
+        t0 = time.perf_counter()
+        Q.solve(max_iterations=args.warmup + args.steps, device=local_rank)
+        torch.cuda.synchronize()
+        return Q, time.perf_counter() - t0
 
-    # roofline of the LDLᵀ factorisation (the kernel BASELINE.json names):
-    # algorithmic bytes per factorisation = 12·nnz(K) + 12·nnz(L) + 8·dim
-    # (SURVEY §8d), duration = CUDA-event time of one factorisation on the
-    # solver's stream, averaged over the solve.
+    def max_over_ranks(v):
+        if world == 1:
+            return v
+        t = torch.tensor([v], device="cuda", dtype=torch.float64)
+        dist.all_reduce(t, op=dist.ReduceOp.MAX)
+        return float(t.item())
+
+    with ClockSampler(local_rank) as clk:
+        # (1) headline `value`: L2 evicted before every iteration (256 MiB
+        #     memset, excluded from the iteration timestamps)
+        P, _ = one_solve(True)
+        tr = P.trace()
+        k, dt = steady_rate(tr, args.warmup, args.steps)
+        dt = max_over_ranks(dt)
+        cnt, tim, sym = P.counters(), P.timers(), P.symbolic_stats()
+        iters = len(tr)
+        # (2) the same solve as a user runs it (no flushes): warm-L2 rate and the
+        #     end-to-end number through Problem::solve with host buffers
+        P2, total_s = one_solve(False)
+        tr2 = P2.trace()
+        k2, dt2 = steady_rate(tr2, args.warmup, args.steps)
+        dt2 = max_over_ranks(dt2)
+        total_s = max_over_ranks(total_s)
+        cnt2, phases = P2.counters(), P2.phase_seconds()
+    rate = world * k / dt
+
+    # roofline of the dominant kernel, k_factor_tree (supernodal LDLT; also the
+    # kernel BASELINE.json's metric names). Algorithmic bytes per numeric
+    # factorisation = 12·nnz(K) + 12·nnz(L) + 8·dim;
+    # a launch factors one matrix, or two when the regularisation pair is
+    # speculated, so bytes per launch = bytes × factorisations ÷ launches.
     fac_bytes = 12 * sym["nnz_kkt"] + 12 * sym["nnz_l"] + 8 * sym["dim"]
-    fac_ms = tim["factor"]["total_ms"] / max(tim["factor"]["count"], 1)
-    achieved = fac_bytes / (fac_ms * 1e-3) / 1e9 if fac_ms > 0 else 0.0
+    n_launch = max(tim["factor"]["count"], 1)
+    fac_ms = tim["factor"]["total_ms"] / n_launch
+    fac_per_launch = cnt["factorizations"] / n_launch
+    achieved = (fac_bytes * fac_per_launch) / (fac_ms * 1e-3) / 1e9 if fac_ms > 0 else 0.0
     peak = float(peaks["hbm_gbs"])
     phase_ms = {k_: (v["total_ms"] / max(v["count"], 1)) for k_, v in tim.items()}
+    per_step_ms = {k_: v["total_ms"] / iters for k_, v in tim.items()}
+    traffic = None
+    tpath = os.path.join(ROOT, "profiles", "traffic.json")
+    if os.path.exists(tpath):
+        with open(tpath) as f:
+            traffic = json.load(f).get("k_factor_tree_dram_bytes_per_launch")
+    # autodiff sweep (second kernel of the step): algorithmic bytes of one full
+    # re-linearisation = program stream + bindings + leaves + outputs
+    ad_bytes = cnt["program_bytes"] + 8 * (5 * N + 4 + 8 * N + 10) + 8 * sym["nnz_kkt"]
 
     line = {
         "metric": METRIC, "value": rate, "unit": UNIT, "n_gpus": world,
@@ -230,33 +259,51 @@ def main():
         "config": {
             "workload": workload,
             "parallelism": ("single GPU" if world == 1 else
-                            f"{world} independent replicas, one per GPU"),
-            "l2_policy": ("working set (tape bindings + KKT + factor ≈ "
-                          f"{(cnt['program_bytes'] + 20 * sym['nnz_l_stored']) / 1e6:.0f} MB) "
-                          "is re-streamed by every phase; no explicit L2 flush — "
-                          "the step is latency-bound, see DESIGN.md"),
+                            f"{world} independent replicas of the solve, one per "
+                            "GPU, no data-path collective (DESIGN.md, Multi-GPU)"),
+            "l2_policy": ("L2 flushed before every timed iteration (256 MiB "
+                          "device memset > 126 MB L2, excluded from the iteration "
+                          "timestamps); value_warm_l2 is the same solve without "
+                          "flushes"),
+            "value_warm_l2": world * k2 / dt2,
             "ordering": "nested dissection (level-set bisection)",
             "symbolic": sym,
             "per_step": {
                 "factorizations": sum(r.factorizations for r in tr) / iters,
+                "factor_launches": tim["factor"]["count"] / iters,
                 "solves": sum(r.solves for r in tr) / iters,
                 "trial_points": sum(r.trials for r in tr) / iters},
-            "device_ms_per_call": phase_ms,
+            "device_ms_per_launch_group": phase_ms,
+            "device_ms_per_step": per_step_ms,
+            "solve_call_phases_s": phases,
         },
         "roofline": {
-            "bound": "hbm", "kernel": "k_factor_level (supernodal LDLT, all levels of one factorisation)",
+            "bound": "hbm",
+            "kernel": "k_factor_tree (dependency-driven supernodal LDLT, one "
+                      "launch per factorisation or speculated pair)",
             "achieved": achieved, "peak": peak, "unit": "GB/s",
-            "frac": achieved / peak if peak else None, "traffic": None,
-            "peak_kind": peak_kind,
+            "frac": achieved / peak if peak else None, "traffic": traffic,
+            "peak_kind": peak_kind + " (MEASURED_PEAKS.json hbm_gbs, burst copy)",
             "algorithmic_bytes_per_factorization": fac_bytes,
-            "ms_per_factorization": fac_ms},
+            "factorizations_per_launch": fac_per_launch,
+            "ms_per_launch": fac_ms,
+            "share_of_step_device_time": per_step_ms["factor"] / max(sum(per_step_ms.values()), 1e-12),
+            "note": "latency-bound: the factor (≈7 MB) is L2-sized and the "
+                    "assembly tree has 13 dependent levels; see DESIGN.md",
+            "ad_sweep": {
+                "kernel": "k_ad_sweep (full re-linearisation)",
+                "algorithmic_bytes": ad_bytes,
+                "ms": phase_ms["eval_full"],
+                "achieved_gbs": ad_bytes / (phase_ms["eval_full"] * 1e-3) / 1e9 if phase_ms["eval_full"] > 0 else None},
+        },
         "e2e": {
-            "value": world * iters / total_s, "unit": UNIT,
-            "what": "slp::Problem::solve() wall time incl. autodiff setup, tape "
-                    "upload, symbolic analysis, the Newton loop and the "
-                    "solution read-back, divided by the iterations it ran",
-            "h2d_bytes_per_step": cnt["h2d_bytes"] / iters,
-            "d2h_bytes_per_step": cnt["d2h_bytes"] / iters,
+            "value": world * len(tr2) / total_s, "unit": UNIT,
+            "what": "slp::Problem::solve() wall time with HOST buffers: autodiff "
+                    "setup, tape upload, compilation, symbolic analysis, the "
+                    "Newton loop and the solution read-back, divided by the "
+                    "iterations it ran",
+            "h2d_bytes_per_step": cnt2["h2d_bytes"] / len(tr2),
+            "d2h_bytes_per_step": cnt2["d2h_bytes"] / len(tr2),
             "solve_call_s": total_s},
         "gpu_launches": int(cnt["kernel_launches"] * k / iters),
         "clocks": clk.summary(),

@@ -345,6 +345,10 @@ int slpb_get_timers(slpb_solver* s, slpb_timers* out);
  * events on the handle's stream (milliseconds; 0 if not yet run). which:
  * 0 eval(full), 1 eval(values), 2 assemble, 3 factor, 4 solve. */
 int slpb_last_device_ms(slpb_solver* s, int which, float* ms);
+/* Benchmark hygiene: overwrites a 256 MiB scratch buffer (larger than the
+ * 126 MB L2) on the handle's stream and waits, so that the next phase starts
+ * with a cold L2. Not used by the solver itself. */
+int slpb_flush_l2(slpb_solver* s);
 /* The handle's CUDA stream (cudaStream_t as void*), for external timing. */
 void* slpb_stream(slpb_solver* s);
 

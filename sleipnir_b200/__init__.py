@@ -111,7 +111,7 @@ ABI_SYMBOLS = [
     "slpb_soc_begin", "slpb_soc_iterate",
     "slpb_trial", "slpb_accept", "slpb_array_size", "slpb_download",
     "slpb_pattern", "slpb_get_counters", "slpb_get_timers",
-    "slpb_last_device_ms", "slpb_stream",
+    "slpb_last_device_ms", "slpb_flush_l2", "slpb_stream",
 ]
 
 _dev = None
@@ -188,6 +188,10 @@ def host_lib() -> C.CDLL:
         L.slpbh_solution.argtypes = [vp, _dp, _dp, _dp, _dp]
         L.slpbh_loop_seconds.restype = C.c_double
         L.slpbh_loop_seconds.argtypes = [vp]
+        L.slpbh_set_flush_l2.argtypes = [vp, C.c_int]
+        L.slpbh_flush_seconds.restype = C.c_double
+        L.slpbh_flush_seconds.argtypes = [vp]
+        L.slpbh_phase_seconds.argtypes = [vp, _dp]
         L.slpbh_symbolic_stats.argtypes = [vp, _lp]
         L.slpbh_counters.argtypes = [vp, _lp]
         L.slpbh_timers.argtypes = [vp, _dp]
@@ -431,6 +435,22 @@ class Problem:
 
     def loop_seconds(self):
         return self.H.slpbh_loop_seconds(self.h)
+
+    def set_flush_l2(self, on=True):
+        """Benchmark hygiene: evict the device L2 before every iteration of the
+        following solves; the flushes are excluded from the iteration times."""
+        self.H.slpbh_set_flush_l2(self.h, int(on))
+
+    def flush_seconds(self):
+        return self.H.slpbh_flush_seconds(self.h)
+
+    def phase_seconds(self):
+        """Host wall time of the phases of the last solve() call."""
+        out = np.zeros(8)
+        self.H.slpbh_phase_seconds(self.h, _d(out))
+        keys = ("build_graphs", "flatten", "device_create", "upload_compile",
+                "scaling", "analyze", "newton_loop", "write_back")
+        return dict(zip(keys, (float(v) for v in out)))
 
     def symbolic_stats(self):
         out = np.zeros(8, dtype=np.int64)

@@ -141,6 +141,7 @@ struct slpb_solver {
   DevBuf<double> red_partials;
   DevBuf<unsigned int> red_counter;
   DevBuf<double> d_results;
+  DevBuf<unsigned char> l2_flush;
   double* h_results = nullptr;  // pinned
   // timing
   cudaEvent_t ev[10] = {};
@@ -2108,6 +2109,16 @@ int slpb_get_timers(slpb_solver* S, slpb_timers* out) {
   CU(cudaStreamSynchronize(S->stream));
   harvest_timers(S);
   *out = S->timers;
+  return SLPB_OK;
+}
+
+int slpb_flush_l2(slpb_solver* S) {
+  if (!S) return SLPB_ERR_ARGUMENT;
+  CU(cudaSetDevice(S->device));
+  constexpr size_t kBytes = size_t(256) << 20;
+  if (S->l2_flush.n != kBytes) CU(S->l2_flush.alloc(kBytes));
+  CU(cudaMemsetAsync(S->l2_flush.p, 0xA5, kBytes, S->stream));
+  CU(cudaStreamSynchronize(S->stream));
   return SLPB_OK;
 }
 

@@ -19,6 +19,7 @@ struct Handle {
   std::string error;
   std::vector<double> x;
   int last_status = 0;
+  bool flush_l2 = false;
 };
 
 Handle* H(void* h) { return static_cast<Handle*>(h); }
@@ -76,6 +77,7 @@ int slpbh_solve(void* h, double tolerance, int max_iterations, int feasible_ipm,
   dopt.device = device;
   dopt.ordering = ordering;
   dopt.keep_iterates = keep_iterates != 0;
+  dopt.flush_l2 = hd->flush_l2;
   if (perm) {
     const size_t dim = hd->problem->decision_variables().size() +
                        hd->problem->equality_constraints().size();
@@ -88,6 +90,20 @@ int slpbh_solve(void* h, double tolerance, int max_iterations, int feasible_ipm,
     return -100;
   }
   return hd->last_status;
+}
+
+/// Benchmark hygiene: evict the device L2 before every iteration of the next
+/// solves (excluded from the iteration timestamps).
+void slpbh_set_flush_l2(void* h, int on) { H(h)->flush_l2 = on != 0; }
+double slpbh_flush_seconds(void* h) {
+  return H(h)->problem->last_trace().flush_seconds;
+}
+
+/// out[8]: build_graphs, flatten, device_create, upload+compile, scaling,
+/// analyze, newton loop, write-back — host seconds of the last solve().
+void slpbh_phase_seconds(void* h, double* out) {
+  const auto& p = H(h)->problem->last_phase_seconds();
+  for (int i = 0; i < 8; ++i) out[i] = p[i];
 }
 
 int slpbh_trace_rows(void* h) {

@@ -9,6 +9,8 @@
 // per-iteration sweeps run on the device from the same lists.
 #pragma once
 
+#include <algorithm>
+#include <thread>
 #include <utility>
 #include <vector>
 
@@ -24,16 +26,16 @@ struct Triplet {
   double value;
 };
 
-inline ExpressionGraph topological_sort(const Expr& root) {
+/// Sorts with caller-provided scratch (all −1 on entry and on exit) and stack,
+/// so that independent rows can be sorted by different threads: the graph is
+/// only read.
+inline ExpressionGraph topological_sort(const ExpressionPool& P, ExprId root_id,
+                                        std::vector<int32_t>& scratch,
+                                        std::vector<ExprId>& stack) {
   ExpressionGraph list;
-  if (root == nullptr || root.type() == ExpressionType::CONSTANT) return list;
-
-  auto& P = pool();
-  auto& scratch = P.scratch;
-  std::vector<ExprId> stack;
-
+  stack.clear();
   // Pass 1: count incoming edges (offset by −1) by DFS from the root.
-  stack.push_back(root.id());
+  stack.push_back(root_id);
   while (!stack.empty()) {
     ExprId node = stack.back();
     stack.pop_back();
@@ -42,7 +44,7 @@ inline ExpressionGraph topological_sort(const Expr& root) {
     }
   }
   // Pass 2: emit a node once all of its parents have been emitted.
-  stack.push_back(root.id());
+  stack.push_back(root_id);
   while (!stack.empty()) {
     ExprId node = stack.back();
     stack.pop_back();
@@ -52,6 +54,58 @@ inline ExpressionGraph topological_sort(const Expr& root) {
     }
   }
   return list;
+}
+
+inline ExpressionGraph topological_sort(const Expr& root) {
+  if (root == nullptr || root.type() == ExpressionType::CONSTANT) return {};
+  std::vector<ExprId> stack;
+  return topological_sort(pool(), root.id(), pool().scratch, stack);
+}
+
+/// Row-wise topological sorts (jacobian.hpp:55-57 of the reference does them
+/// one after the other). The rows are independent and the graph is read-only
+/// here, so large row sets are sorted by several host threads, each with its
+/// own in-degree scratch; every list is identical to the sequential one.
+template <typename RootOf>
+std::vector<ExpressionGraph> topological_sort_rows(int n_rows, RootOf&& root_of) {
+  std::vector<ExpressionGraph> lists(n_rows);
+  // the pool is thread_local (like the reference's, src/util/pool.cpp:5-8):
+  // resolve everything that needs it on this thread and hand the workers a
+  // pointer to it
+  ExpressionPool& P = pool();
+  std::vector<ExprId> roots(n_rows, kNull);
+  for (int row = 0; row < n_rows; ++row) {
+    const Expr& root = root_of(row);
+    if (root == nullptr || root.type() == ExpressionType::CONSTANT) continue;
+    roots[row] = root.id();
+  }
+  const unsigned hw = std::thread::hardware_concurrency();
+  const int n_threads =
+      n_rows < 2048 ? 1 : static_cast<int>(std::min(8u, std::max(1u, hw)));
+  auto work = [&](int t, std::vector<int32_t>& scratch) {
+    std::vector<ExprId> stack;
+    const int b = static_cast<int>(int64_t(n_rows) * t / n_threads);
+    const int e = static_cast<int>(int64_t(n_rows) * (t + 1) / n_threads);
+    for (int row = b; row < e; ++row) {
+      if (roots[row] == kNull) continue;
+      lists[row] = topological_sort(P, roots[row], scratch, stack);
+    }
+  };
+  if (n_threads == 1) {
+    work(0, P.scratch);
+    return lists;
+  }
+  const size_t pool_size = P.size();
+  std::vector<std::thread> threads;
+  for (int t = 1; t < n_threads; ++t) {
+    threads.emplace_back([&, t] {
+      std::vector<int32_t> scratch(pool_size, -1);
+      work(t, scratch);
+    });
+  }
+  work(0, P.scratch);
+  for (auto& th : threads) th.join();
+  return lists;
 }
 
 inline void update_values(const ExpressionGraph& list) {

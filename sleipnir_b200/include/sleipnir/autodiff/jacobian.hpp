@@ -58,10 +58,9 @@ class Jacobian {
 
   void init() {
     auto& scratch = detail::pool().scratch;
-    m_top_lists.reserve(m_variables.size());
-    for (auto& v : m_variables) {
-      m_top_lists.emplace_back(detail::topological_sort(v.expr));
-    }
+    m_top_lists = detail::topological_sort_rows(
+        m_variables.size(),
+        [&](int row) -> const detail::Expr& { return m_variables(row).expr; });
     for (int col = 0; col < m_wrt.size(); ++col) {
       scratch[m_wrt(col).expr.id()] = col;
     }

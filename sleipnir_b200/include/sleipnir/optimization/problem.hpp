@@ -15,6 +15,8 @@
 
 #include <algorithm>
 #include <concepts>
+#include <array>
+#include <chrono>
 #include <functional>
 #include <limits>
 #include <memory>
@@ -43,6 +45,7 @@ struct DeviceOptions {
   int ordering = SLPB_ORDER_NESTED_DISSECTION;  ///< slpb_ordering
   std::vector<int32_t> permutation;             ///< for SLPB_ORDER_CUSTOM
   bool keep_iterates = false;                   ///< record x,s,y,z per iteration
+  bool flush_l2 = false;  ///< evict L2 before every iteration (benchmarks)
 };
 
 /// RAII owner of a device handle.
@@ -133,6 +136,7 @@ class Problem {
   ExitStatus solve(const Options& options, const DeviceOptions& dev_options) {
     m_trace = SolveTrace{};
     m_trace.keep_iterates = dev_options.keep_iterates;
+    m_trace.flush_l2 = dev_options.flush_l2;
 
     const int n = static_cast<int>(m_decision_variables.size());
     const int me = static_cast<int>(m_equality_constraints.size());
@@ -155,8 +159,17 @@ class Problem {
       callbacks.push_back(cb);
     }
 
+    m_phase.fill(0.0);
+    auto tick = std::chrono::steady_clock::now();
+    auto lap = [&](int which) {
+      const auto now = std::chrono::steady_clock::now();
+      m_phase[which] += std::chrono::duration<double>(now - tick).count();
+      tick = now;
+    };
+
     // Autodiff setup (:517-560)
     auto graphs = build_graphs();
+    lap(0);
 
     // Conflicting bounds (:597-606)
     if (has_conflicting_bounds(*graphs->A_i)) {
@@ -165,10 +178,13 @@ class Problem {
 
     // Hand the graphs to the device
     detail::FlatProblem fp = graphs->flatten();
+    lap(1);
 
     DeviceHandle handle{dev_options.device};
     slpb_solver* dev = handle.s;
+    lap(2);
     upload(dev, fp);
+    lap(3);
 
     // Initial iterate: s = 1, y = 0, z = 1 (interior_point.hpp:74-80)
     std::vector<Scalar> s(mi, Scalar(1)), y(me, Scalar(0)), z(mi, Scalar(1));
@@ -214,6 +230,7 @@ class Problem {
                                             d_ci.data()));
     }
 
+    lap(4);
     slpb_symbolic_stats sym{};
     SLP_DEVICE_CALL(dev, slpb_analyze(dev, dev_options.ordering,
                                       dev_options.permutation.empty()
@@ -221,6 +238,7 @@ class Problem {
                                           : dev_options.permutation.data(),
                                       &sym));
     m_symbolic = sym;
+    lap(5);
 
     // Interior-point method (:663-668; overload 1, interior_point.hpp:74-86)
     Scalar mu = Scalar(0.1) * info.scaling_f;
@@ -229,6 +247,7 @@ class Problem {
         dev, info, std::span{callbacks}, options, false, mu, iterations,
         &m_trace);
 
+    lap(6);
     // Write the solution back into the Variables (:676)
     SLP_DEVICE_CALL(dev, slpb_get_iterate(dev, x.data(), s.data(), y.data(),
                                           z.data()));
@@ -238,6 +257,7 @@ class Problem {
     m_last_z = std::move(z);
     slpb_get_counters(dev, &m_counters);
     slpb_get_timers(dev, &m_timers);
+    lap(7);
     return status;
   }
 
@@ -278,6 +298,9 @@ class Problem {
   const slpb_symbolic_stats& last_symbolic_stats() const { return m_symbolic; }
   const slpb_counters& last_counters() const { return m_counters; }
   const slpb_timers& last_timers() const { return m_timers; }
+  /// Host seconds of the phases of the last solve(): build_graphs, flatten,
+  /// device_create, upload+compile, scaling, analyze, newton loop, write-back.
+  const std::array<double, 8>& last_phase_seconds() const { return m_phase; }
   const std::vector<Scalar>& last_s() const { return m_last_s; }
   const std::vector<Scalar>& last_y() const { return m_last_y; }
   const std::vector<Scalar>& last_z() const { return m_last_z; }
@@ -423,6 +446,7 @@ class Problem {
   slpb_symbolic_stats m_symbolic{};
   slpb_counters m_counters{};
   slpb_timers m_timers{};
+  std::array<double, 8> m_phase{};
   std::vector<Scalar> m_last_s, m_last_y, m_last_z;
 };
 

@@ -62,6 +62,11 @@ struct IterationRecord {
 
 struct SolveTrace {
   bool keep_iterates = false;
+  /// Benchmark hygiene: evict the device L2 (slpb_flush_l2) at the start of
+  /// every iteration; the time spent flushing is excluded from t_end and
+  /// loop_seconds.
+  bool flush_l2 = false;
+  double flush_seconds = 0.0;
   std::vector<IterationRecord> rows;
   int64_t factorizations = 0, solves = 0, trials = 0;
   double loop_seconds = 0.0;  ///< wall time inside the Newton loop
@@ -400,12 +405,20 @@ ExitStatus interior_point(
       if (t) {
         t->loop_seconds += std::chrono::duration<double>(
                                std::chrono::steady_clock::now() - t0)
-                               .count();
+                               .count() -
+                           t->flush_seconds;
       }
     }
   } loop_timer{trace, loop_start_time};
 
   while (E_0 > Scalar(options.tolerance)) {
+    if (trace && trace->flush_l2) {
+      const auto f0 = std::chrono::steady_clock::now();
+      SLP_DEVICE_CALL(dev, slpb_flush_l2(dev));
+      trace->flush_seconds += std::chrono::duration<double>(
+                                  std::chrono::steady_clock::now() - f0)
+                                  .count();
+    }
     int it_solves = 0, it_trials = 0;
     const int fact_before = solver.factorizations;
 
@@ -609,7 +622,8 @@ ExitStatus interior_point(
       row.trials = it_trials;
       row.t_end = std::chrono::duration<double>(
                       std::chrono::steady_clock::now() - solve_start_time)
-                      .count();
+                      .count() -
+                  trace->flush_seconds;
       if (trace->keep_iterates) {
         row.x.resize(n);
         row.s.resize(mi);

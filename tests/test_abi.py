@@ -14,7 +14,7 @@ ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
 def _declared_symbols():
     text = open(os.path.join(ROOT, "include", "slpb.h")).read()
     text = re.sub(r"/\*.*?\*/", "", text, flags=re.S)
-    return sorted(set(re.findall(r"\b(slpb_[a-z_]+)\s*\(", text)))
+    return sorted(set(re.findall(r"\b(slpb_[a-z0-9_]+)\s*\(", text)))
 
 
 def test_header_and_python_symbol_lists_agree():

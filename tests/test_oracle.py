@@ -217,3 +217,38 @@ def test_zero_pivot_is_reported():
     nnzL, D, x, h = ldlt(2, indptr, indices, data, np.ones(2),
                          np.arange(2, dtype=np.int32))
     assert nnzL == -1
+
+
+def test_cart_pole_sensitivity_floor():
+    """How far two CORRECT runs of the reference algorithm drift apart: the
+    oracle against itself with two elimination orders (its own AMD vs the
+    nested-dissection order the device uses). Same decisions, but the iterates
+    differ by ~1e-8 after ONE cart-pole step and by ~1e-5 after ten — the
+    regularised KKT system (γ = 1e-10, unpivoted factor) amplifies rounding by
+    ≳ 1e8. This is the floor any implementation's iterate parity sits on, and
+    why tests/test_gpu_parity.py compares cart-pole trajectories at 1e-5 and
+    single steps from a common state at 1e-6."""
+    import emu
+    name, N = "cart_pole", 100
+    E = emu.Emu(name, N)
+    E.L.emu_kkt_build(E.h)
+    E.analyze(0)
+    nd = E.perm()
+    E.close()
+    traces = []
+    for perm in (nd, None):
+        O = OracleProblem(name, N)
+        O.solve(max_iterations=10, perm=perm, force_sparse=1)
+        traces.append(O.trace())
+        O.close()
+
+    def rel(a, b):
+        return np.abs(a - b).max() / np.abs(b).max()
+
+    drift = [rel(a.x, b.x) for a, b in zip(*traces)]
+    for a, b in zip(*traces):
+        assert a.delta == b.delta and a.factorizations == b.factorizations
+        assert a.trials == b.trials
+    assert 1e-10 < drift[0] < 1e-6      # one step: already ~1e-8
+    assert max(drift) > 1e-7            # and it grows along the trajectory
+    assert max(drift) < 1e-3
