@@ -4,11 +4,13 @@
 //   cart-pole   benchmarks/scalability/cart_pole/sleipnir.cpp:16-129,
 //               benchmarks/rk4.hpp:14-23
 //   flywheel    benchmarks/scalability/flywheel/sleipnir.cpp:12-43
+//   g-fold      examples/g-fold/src/main.cpp:145-386 (dt rescaled to T_f/N)
 //   small NLPs  test/src/optimization/{linear,quadratic,nonlinear}_problem_test.cpp
 // Operand order is preserved everywhere: it decides grad_l vs grad_r and hence
 // floating-point rounding.
 #pragma once
 
+#include <algorithm>
 #include <cmath>
 #include <memory>
 #include <numbers>
@@ -204,11 +206,190 @@ std::unique_ptr<Problem<B>> small_problem(const std::string& name, double p0,
   return P;
 }
 
+
+/// exp([A B; 0 0]·dt) by scaling and squaring of a Taylor series — the same
+/// routine as the product's builder (sleipnir_b200/problems/problems.hpp), so
+/// both sides transcribe the same constants. (The reference uses Eigen's
+/// matrix exponential, examples/g-fold/src/main.cpp:39-57; Eigen is absent.)
+inline void discretize_ab(const std::vector<double>& A,
+                          const std::vector<double>& B, int ns, int ni,
+                          double dt, std::vector<double>& A_d,
+                          std::vector<double>& B_d) {
+  const int n = ns + ni;
+  std::vector<double> M(size_t(n) * n, 0.0), E(size_t(n) * n, 0.0),
+      T(size_t(n) * n, 0.0), tmp(size_t(n) * n, 0.0);
+  for (int r = 0; r < ns; ++r) {
+    for (int c = 0; c < ns; ++c) M[r * n + c] = A[r * ns + c] * dt;
+    for (int c = 0; c < ni; ++c) M[r * n + ns + c] = B[r * ni + c] * dt;
+  }
+  double norm = 0.0;
+  for (double v : M) norm = std::max(norm, std::abs(v));
+  int squarings = 0;
+  while (norm * n > 0.5) {
+    norm *= 0.5;
+    ++squarings;
+  }
+  const double scale = std::ldexp(1.0, -squarings);
+  for (double& v : M) v *= scale;
+  auto matmul = [&](const std::vector<double>& X, const std::vector<double>& Y,
+                    std::vector<double>& Zm) {
+    for (int r = 0; r < n; ++r) {
+      for (int c = 0; c < n; ++c) {
+        double acc = 0.0;
+        for (int k = 0; k < n; ++k) acc += X[r * n + k] * Y[k * n + c];
+        Zm[r * n + c] = acc;
+      }
+    }
+  };
+  for (int i = 0; i < n; ++i) E[i * n + i] = T[i * n + i] = 1.0;
+  for (int term = 1; term <= 20; ++term) {
+    matmul(T, M, tmp);
+    for (size_t i = 0; i < tmp.size(); ++i) T[i] = tmp[i] / term;
+    for (size_t i = 0; i < E.size(); ++i) E[i] += T[i];
+  }
+  for (int q = 0; q < squarings; ++q) {
+    matmul(E, E, tmp);
+    E = tmp;
+  }
+  A_d.assign(size_t(ns) * ns, 0.0);
+  B_d.assign(size_t(ns) * ni, 0.0);
+  for (int r = 0; r < ns; ++r) {
+    for (int c = 0; c < ns; ++c) A_d[r * ns + c] = E[r * n + c];
+    for (int c = 0; c < ni; ++c) B_d[r * ni + c] = E[r * n + ns + c];
+  }
+}
+
+/// G-FOLD powered-descent guidance, examples/g-fold/src/main.cpp:145-386, with
+/// dt = T_f/N (SURVEY.md §7 hard part 8).
+template <class B>
+std::unique_ptr<Problem<B>> gfold_problem(int N, double T_f = 48.0) {
+  using M = Mat<B>;
+  using V = Var<B>;
+  constexpr double m_wet = 2000.0;
+  constexpr double T_max = 24000;
+  constexpr double rho_1 = 0.2 * T_max;
+  constexpr double rho_2 = 0.8 * T_max;
+  constexpr double alpha = 5e-4;
+  const std::vector<double> q_0{2400.0, 450.0, -330.0};
+  const std::vector<double> v_0{-10.0, -40.0, 10.0};
+  const std::vector<double> q_f{0.0, 0.0, 0.0};
+  const std::vector<double> v_f{0.0, 0.0, 0.0};
+  const std::vector<double> gv{-3.71, 0.0, 0.0};
+  constexpr double w1 = 2.53e-5, w2 = 0.0, w3 = 6.62e-5;
+  const double theta = 90.0 * std::numbers::pi / 180.0;
+  const double gamma_gs = 30.0 * std::numbers::pi / 180.0;
+  constexpr double v_max = 90.0;
+  const double dt = T_f / N;
+  constexpr bool END_STRAIGHT = true;
+
+  const double S[3][3] = {{0.0, -w3, w2}, {w3, 0.0, -w1}, {-w2, w1, 0.0}};
+  std::vector<double> A(36, 0.0), Bc(18, 0.0), A_d, B_d;
+  for (int i = 0; i < 3; ++i) {
+    A[i * 6 + 3 + i] = 1.0;
+    Bc[(3 + i) * 3 + i] = 1.0;
+    for (int j = 0; j < 3; ++j) {
+      double ss = 0.0;
+      for (int k = 0; k < 3; ++k) ss += S[i][k] * S[k][j];
+      A[(3 + i) * 6 + j] = -ss;
+      A[(3 + i) * 6 + 3 + j] = -2 * S[i][j];
+    }
+  }
+  discretize_ab(A, Bc, 6, 3, dt, A_d, B_d);
+  const M Ad = M::constants(6, 6, A_d);
+  const M Bd = M::constants(6, 3, B_d);
+  const M g = M::constants(3, 1, gv);
+
+  auto problem = std::make_unique<Problem<B>>();
+  M X = problem->decision_variable(6, N + 1);
+  M Z = problem->decision_variable(1, N + 1);
+  M U = problem->decision_variable(3, N);
+  M sigma = problem->decision_variable(1, N);
+
+  M q = X.block(0, 0, 3, N + 1);
+  M v = X.block(3, 0, 3, N + 1);
+
+  problem->subject_to_eq(eq(q.col(0), M::constants(3, 1, q_0)));
+  problem->subject_to_eq(eq(v.col(0), M::constants(3, 1, v_0)));
+  problem->subject_to_eq(eq(M{Z(0, 0)}, V{std::log(m_wet)}));
+  problem->subject_to_eq(eq(q.col(N), M::constants(3, 1, q_f)));
+  problem->subject_to_eq(eq(v.col(N), M::constants(3, 1, v_f)));
+
+  for (int k = 0; k < N + 1; ++k) {
+    for (int i = 0; i < 3; ++i) {
+      q(i, k).set_value(std::lerp(q_0[i], q_f[i], static_cast<double>(k) / N));
+      v(i, k).set_value(std::lerp(v_0[i], v_f[i], static_cast<double>(k) / N));
+    }
+  }
+
+  for (int k = 0; k < N + 1; ++k) {
+    const double t = k * dt;
+    M x_k = X.col(k);
+    M q_k = X.block(0, k, 3, 1);
+    M v_k = X.block(3, k, 3, 1);
+    M z_k = Z.col(k);
+
+    problem->subject_to_ineq(le(v_k.T() * v_k, V{v_max * v_max}));
+
+    const double z_min = std::log(m_wet - alpha * rho_2 * t);
+    const double z_max = std::log(m_wet - alpha * rho_1 * t);
+    const double z_estimate = (z_min + z_max) / 2;
+    z_k[0].set_value(z_estimate);
+
+    if (k < N) {
+      M x_k1 = X.col(k + 1);
+      M z_k1 = Z.col(k + 1);
+      M u_k = U.col(k);
+      M sigma_k = sigma.col(k);
+
+      const double u_min = rho_1 / std::exp(z_estimate);
+      const double u_max = rho_2 / std::exp(z_estimate);
+      u_k.set_value(std::vector<double>{(u_min + u_max) / 2, 0.0, 0.0});
+
+      {
+        V lhs = pow(q_k[0] - V{q_f[0]}, 2.0);
+        V rhs = V{std::tan(gamma_gs) * std::tan(gamma_gs)} *
+                (pow(q_k[1] - V{q_f[1]}, 2.0) + pow(q_k[2] - V{q_f[2]}, 2.0));
+        problem->subject_to_ineq(std::vector<V>{lhs - rhs});
+      }
+
+      problem->subject_to_ineq(ge(sigma_k, V{0}));
+
+      if (k == N - 1 && END_STRAIGHT) {
+        problem->subject_to_eq(eq(M{u_k(0, 0)}, sigma_k));
+        problem->subject_to_eq(eq(M{u_k(1, 0)}, V{0}));
+        problem->subject_to_eq(eq(M{u_k(2, 0)}, V{0}));
+      } else {
+        // u_kᵀu_k ≤ σ_k·σ_k  →  rhs − lhs
+        problem->subject_to_ineq(ge(sigma_k * sigma_k, u_k.T() * u_k));
+        problem->subject_to_ineq(ge(u_k[0], std::cos(theta) * sigma_k));
+      }
+
+      const double z_0 = std::log(m_wet - alpha * rho_2 * t);
+      const double mu_1 = rho_1 * std::exp(-z_0);
+      const double mu_2 = rho_2 * std::exp(-z_0);
+      V sigma_min = V{mu_1} * (V{1} - (z_k[0] - V{z_0}) +
+                               V{0.5} * pow(z_k[0] - V{z_0}, 2.0));
+      V sigma_max = V{mu_2} * (V{1} - (z_k[0] - V{z_0}));
+      problem->subject_to_ineq(bounds(sigma_min, sigma_k, sigma_max));
+      sigma_k[0].set_value((sigma_min.value() + sigma_max.value()) / 2);
+
+      problem->subject_to_eq(eq(x_k1, Ad * x_k + Bd * (g + u_k)));
+      problem->subject_to_eq(eq(z_k1, z_k - alpha * dt * sigma_k));
+    }
+  }
+
+  V J{0.0};
+  for (int k = 0; k < N; ++k) J = J + sigma(0, k);
+  problem->minimize(J);
+  return problem;
+}
+
 template <class B>
 std::unique_ptr<Problem<B>> make_problem(const std::string& name, int N,
                                          double p0, double p1) {
   if (name == "cart_pole") return cart_pole_problem<B>(N, p0 > 0 ? p0 : 5.0);
   if (name == "flywheel") return flywheel_problem<B>(N, p0 > 0 ? p0 : 5.0);
+  if (name == "gfold") return gfold_problem<B>(N, p0 > 0 ? p0 : 48.0);
   return small_problem<B>(name, p0, p1);
 }
 

@@ -2,6 +2,7 @@
 // the slp:: DSL exactly as a user of the reference would write them:
 //   cart-pole  benchmarks/scalability/cart_pole/sleipnir.cpp:16-129 (+ rk4.hpp)
 //   flywheel   benchmarks/scalability/flywheel/sleipnir.cpp:12-43
+//   g-fold     examples/g-fold/src/main.cpp:145-386 (dt rescaled to T_f/N)
 //   small NLPs test/src/optimization/{linear,quadratic,nonlinear}_problem_test.cpp,
 //              test/src/optimization/solver/exit_status_test.cpp
 #pragma once
@@ -12,6 +13,7 @@
 #include <numbers>
 #include <stdexcept>
 #include <string>
+#include <vector>
 
 #include <sleipnir/autodiff/variable.hpp>
 #include <sleipnir/autodiff/variable_matrix.hpp>
@@ -118,6 +120,177 @@ inline std::unique_ptr<slp::Problem<double>> flywheel(int N, double T = 5.0) {
   return problem;
 }
 
+
+/// Zero-order-hold discretisation [A_d B_d; 0 I] = exp([A B; 0 0]·dt) by scaling
+/// and squaring of a Taylor series (the reference uses Eigen's matrix
+/// exponential, examples/g-fold/src/main.cpp:39-57; Eigen is not in the image).
+inline void discretize_ab(const slp::Matrix<double>& A,
+                          const slp::Matrix<double>& B, double dt,
+                          slp::Matrix<double>& A_d, slp::Matrix<double>& B_d) {
+  const int ns = A.rows(), ni = B.cols(), n = ns + ni;
+  std::vector<double> M(size_t(n) * n, 0.0), E(size_t(n) * n, 0.0),
+      T(size_t(n) * n, 0.0), tmp(size_t(n) * n, 0.0);
+  for (int r = 0; r < ns; ++r) {
+    for (int c = 0; c < ns; ++c) M[r * n + c] = A(r, c) * dt;
+    for (int c = 0; c < ni; ++c) M[r * n + ns + c] = B(r, c) * dt;
+  }
+  double norm = 0.0;
+  for (double v : M) norm = std::max(norm, std::abs(v));
+  int squarings = 0;
+  while (norm * n > 0.5) {
+    norm *= 0.5;
+    ++squarings;
+  }
+  const double scale = std::ldexp(1.0, -squarings);
+  for (double& v : M) v *= scale;
+  auto matmul = [&](const std::vector<double>& X, const std::vector<double>& Y,
+                    std::vector<double>& Z) {
+    for (int r = 0; r < n; ++r) {
+      for (int c = 0; c < n; ++c) {
+        double acc = 0.0;
+        for (int k = 0; k < n; ++k) acc += X[r * n + k] * Y[k * n + c];
+        Z[r * n + c] = acc;
+      }
+    }
+  };
+  for (int i = 0; i < n; ++i) E[i * n + i] = T[i * n + i] = 1.0;
+  for (int term = 1; term <= 20; ++term) {
+    matmul(T, M, tmp);
+    for (size_t i = 0; i < tmp.size(); ++i) T[i] = tmp[i] / term;
+    for (size_t i = 0; i < E.size(); ++i) E[i] += T[i];
+  }
+  for (int q = 0; q < squarings; ++q) {
+    matmul(E, E, tmp);
+    E = tmp;
+  }
+  A_d = slp::Matrix<double>(ns, ns);
+  B_d = slp::Matrix<double>(ns, ni);
+  for (int r = 0; r < ns; ++r) {
+    for (int c = 0; c < ns; ++c) A_d(r, c) = E[r * n + c];
+    for (int c = 0; c < ni; ++c) B_d(r, c) = E[r * n + ns + c];
+  }
+}
+
+/// Powered-descent guidance (G-FOLD), examples/g-fold/src/main.cpp:145-386 with
+/// the time step rescaled to dt = T_f/N (the example hard-codes dt = 0.5 s,
+/// which is only meaningful for N ≤ 250; SURVEY.md §7 hard part 8).
+inline std::unique_ptr<slp::Problem<double>> gfold(int N, double T_f = 48.0) {
+  using slp::Matrix;
+  constexpr double m_wet = 2000.0;
+  constexpr double T_max = 24000;
+  constexpr double rho_1 = 0.2 * T_max;
+  constexpr double rho_2 = 0.8 * T_max;
+  constexpr double alpha = 5e-4;
+  const Matrix<double> q_0{{2400.0}, {450.0}, {-330.0}};
+  const Matrix<double> v_0{{-10.0}, {-40.0}, {10.0}};
+  const Matrix<double> q_f{{0.0}, {0.0}, {0.0}};
+  const Matrix<double> v_f{{0.0}, {0.0}, {0.0}};
+  const Matrix<double> g{{-3.71}, {0.0}, {0.0}};
+  constexpr double w1 = 2.53e-5, w2 = 0.0, w3 = 6.62e-5;
+  const double theta = 90.0 * std::numbers::pi / 180.0;
+  const double gamma_gs = 30.0 * std::numbers::pi / 180.0;
+  constexpr double v_max = 90.0;
+  const double dt = T_f / N;
+  constexpr bool END_STRAIGHT = true;
+
+  const double S[3][3] = {{0.0, -w3, w2}, {w3, 0.0, -w1}, {-w2, w1, 0.0}};
+  Matrix<double> A(6, 6), B(6, 3);
+  for (int i = 0; i < 3; ++i) {
+    A(i, 3 + i) = 1.0;
+    B(3 + i, i) = 1.0;
+    for (int j = 0; j < 3; ++j) {
+      double ss = 0.0;
+      for (int k = 0; k < 3; ++k) ss += S[i][k] * S[k][j];
+      A(3 + i, j) = -ss;
+      A(3 + i, 3 + j) = -2 * S[i][j];
+    }
+  }
+  Matrix<double> A_d, B_d;
+  discretize_ab(A, B, dt, A_d, B_d);
+
+  auto P = std::make_unique<slp::Problem<double>>();
+  auto& problem = *P;
+  auto X = problem.decision_variable(6, N + 1);
+  auto Z = problem.decision_variable(1, N + 1);
+  auto U = problem.decision_variable(3, N);
+  auto sigma = problem.decision_variable(1, N);
+
+  auto q = X.block(0, 0, 3, N + 1);
+  auto v = X.block(3, 0, 3, N + 1);
+
+  problem.subject_to(q.col(0) == q_0);
+  problem.subject_to(v.col(0) == v_0);
+  problem.subject_to(Z[0, 0] == std::log(m_wet));
+  problem.subject_to(q.col(N) == q_f);
+  problem.subject_to(v.col(N) == v_f);
+
+  for (int k = 0; k < N + 1; ++k) {
+    for (int i = 0; i < 3; ++i) {
+      q[i, k].set_value(std::lerp(q_0(i, 0), q_f(i, 0), static_cast<double>(k) / N));
+      v[i, k].set_value(std::lerp(v_0(i, 0), v_f(i, 0), static_cast<double>(k) / N));
+    }
+  }
+
+  for (int k = 0; k < N + 1; ++k) {
+    const double t = k * dt;
+    auto x_k = X.col(k);
+    auto q_k = X.block(0, k, 3, 1);
+    auto v_k = X.block(3, k, 3, 1);
+    auto z_k = Z.col(k);
+
+    problem.subject_to(v_k.T() * v_k <= v_max * v_max);
+
+    const double z_min = std::log(m_wet - alpha * rho_2 * t);
+    const double z_max = std::log(m_wet - alpha * rho_1 * t);
+    const double z_estimate = (z_min + z_max) / 2;
+    z_k.set_value(z_estimate);
+
+    if (k < N) {
+      auto x_k1 = X.col(k + 1);
+      auto z_k1 = Z.col(k + 1);
+      auto u_k = U.col(k);
+      auto sigma_k = sigma.col(k);
+
+      const double u_min = rho_1 / std::exp(z_estimate);
+      const double u_max = rho_2 / std::exp(z_estimate);
+      u_k.set_value(Matrix<double>{{(u_min + u_max) / 2}, {0.0}, {0.0}});
+
+      problem.subject_to(
+          slp::pow(q_k[0] - q_f(0, 0), 2) >=
+          std::tan(gamma_gs) * std::tan(gamma_gs) *
+              (slp::pow(q_k[1] - q_f(1, 0), 2) + slp::pow(q_k[2] - q_f(2, 0), 2)));
+
+      problem.subject_to(sigma_k >= 0);
+
+      if (k == N - 1 && END_STRAIGHT) {
+        problem.subject_to(u_k[0, 0] == sigma_k);
+        problem.subject_to(u_k[1, 0] == 0);
+        problem.subject_to(u_k[2, 0] == 0);
+      } else {
+        problem.subject_to(u_k.T() * u_k <= sigma_k * sigma_k);
+        problem.subject_to(u_k[0] >= std::cos(theta) * sigma_k);
+      }
+
+      const double z_0 = std::log(m_wet - alpha * rho_2 * t);
+      const double mu_1 = rho_1 * std::exp(-z_0);
+      const double mu_2 = rho_2 * std::exp(-z_0);
+      auto sigma_min =
+          mu_1 * (1 - (z_k[0] - z_0) + 0.5 * slp::pow(z_k[0] - z_0, 2));
+      auto sigma_max = mu_2 * (1 - (z_k[0] - z_0));
+      problem.subject_to(slp::bounds(sigma_min, sigma_k, sigma_max));
+      sigma_k.set_value((sigma_min.value() + sigma_max.value()) / 2);
+
+      problem.subject_to(x_k1 == A_d * x_k + B_d * (g + u_k));
+      problem.subject_to(z_k1 == z_k - alpha * dt * sigma_k);
+    }
+  }
+
+  slp::Variable<double> J{0.0};
+  for (int k = 0; k < N; ++k) J = J + sigma[0, k];
+  problem.minimize(J);
+  return P;
+}
+
 inline std::unique_ptr<slp::Problem<double>> small_problem(
     const std::string& name, double p0, double p1) {
   using T = double;
@@ -203,6 +376,7 @@ inline std::unique_ptr<slp::Problem<double>> make_problem(
     const std::string& name, int N, double p0, double p1) {
   if (name == "cart_pole") return cart_pole(N, p0 > 0 ? p0 : 5.0);
   if (name == "flywheel") return flywheel(N, p0 > 0 ? p0 : 5.0);
+  if (name == "gfold") return gfold(N, p0 > 0 ? p0 : 48.0);
   return small_problem(name, p0, p1);
 }
 

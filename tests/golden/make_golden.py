@@ -22,13 +22,15 @@ assert have_reference(), "build oracle/_ref first: make -C oracle ref"
 
 EVAL_CASES = [("cart_pole", 8, 0.0, 0.0), ("cart_pole", 40, 0.0, 0.0),
               ("flywheel", 50, 0.0, 0.0), ("rosenbrock_cubic_line", 0, 0.3, 0.7),
-              ("rosenbrock_disk", 0, -0.5, 1.2), ("wachter_biegler", 0, 0.0, 0.0)]
+              ("rosenbrock_disk", 0, -0.5, 1.2), ("wachter_biegler", 0, 0.0, 0.0),
+              ("gfold", 12, 0.0, 0.0)]
 SOLVE_CASES = [("flywheel", 50, 0.0, 0.0), ("cart_pole", 50, 0.0, 0.0),
                ("lp_maximize", 0, 0.0, 0.0), ("quartic", 0, 0.0, 0.0),
                ("qp_inequality_2d", 0, 0.0, 0.0),
                ("wachter_biegler", 0, 0.0, 0.0),
                ("rosenbrock_disk", 0, -0.5, 1.2),
-               ("rosenbrock_cubic_line", 0, 0.3, 0.7)]
+               ("rosenbrock_cubic_line", 0, 0.3, 0.7),
+               ("gfold", 20, 0.0, 0.0)]
 
 
 def eval_case(name, N, p0, p1):
@@ -66,6 +68,10 @@ def solve_case(name, N, p0, p1):
 
 
 if __name__ == "__main__":
+    only = set(sys.argv[1:])  # optional: regenerate only these problems
+    if only:
+        EVAL_CASES = [c for c in EVAL_CASES if c[0] in only]
+        SOLVE_CASES = [c for c in SOLVE_CASES if c[0] in only]
     for c in EVAL_CASES:
         np.savez_compressed(os.path.join(HERE, f"eval_{c[0]}_{c[1]}.npz"),
                             **eval_case(*c))

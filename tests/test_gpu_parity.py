@@ -73,7 +73,8 @@ def _state(P, O, seed, dx=0.01):
     return x, s, y, z
 
 
-@pytest.mark.parametrize("name,N", [("cart_pole", 100), ("flywheel", 200)])
+@pytest.mark.parametrize("name,N", [("cart_pole", 100), ("flywheel", 200),
+                                    ("gfold", 40)])
 def test_newton_step_vs_oracle(name, N):
     """KKT assembly, factorisation (same permutation on both sides), solve,
     step recovery and fraction-to-the-boundary against the oracle's linear
@@ -332,6 +333,53 @@ def test_cart_pole_solves_to_the_reference_test_bar():
         np.testing.assert_allclose(X[:, k + 1], s + h / 6 * (k1 + 2 * k2 + 2 * k3 + k4),
                                    atol=1e-8)
     P.close()
+
+
+def test_gfold_solves_like_the_oracle():
+    """g-fold rocket landing (examples/g-fold/src/main.cpp, nonlinear
+    inequality constraints), N = 20: the device solve reaches SUCCESS at the
+    optimum the reference-core oracle found (golden vector)."""
+    g = np.load(os.path.join(GOLDEN, "solve_gfold_20.npz"))
+    assert EXIT_STATUS[int(g["status"])] == "SUCCESS"
+    P = sb.Problem("gfold", 20)
+    assert sb.EXIT_STATUS[P.solve()] == "SUCCESS"
+    x, s, y, z = P.solution()
+    N = 20
+    fuel_gpu, fuel_ref = x[-N:].sum(), g["x"][-N:].sum()
+    assert fuel_gpu == pytest.approx(fuel_ref, rel=1e-6)
+    np.testing.assert_allclose(x, g["x"], atol=2e-4 * np.abs(g["x"]).max())
+    P.close()
+
+
+def test_full_size_properties_gfold_n2000():
+    """BASELINE.json config 5 (g-fold N = 2000) at full size: dimensions of the
+    survey table, finite evaluation, correct inertia and a small Newton
+    residual."""
+    N = 2000
+    P = sb.Problem("gfold", N)
+    D = P.open_device()
+    n, me, mi, dim = P.n, P.me, P.mi, P.n + P.me
+    assert (n, me, mi) == (11 * N + 7, 7 * N + 16, 7 * N - 1)
+    rng = np.random.default_rng(2)
+    x = P.initial_guess() * (1 + 1e-3 * rng.standard_normal(n))
+    s = 0.5 + np.abs(rng.standard_normal(mi)); z = 0.5 + np.abs(rng.standard_normal(mi))
+    y = 0.1 * rng.standard_normal(me)
+    D.set_iterate(x, s, y, z)
+    info = D.eval_current(1)
+    assert info.finite == 127
+    st = D.analyze()
+    assert st.dim == dim and st.n_levels <= 24
+    fi = D.factor(1.0, 1e-6, True)
+    assert (fi.n_pos, fi.n_neg, fi.n_zero, fi.zero_pivot) == (n, me, 0, 0)
+    D.solve(0.1, 0.99)
+    _, _, cp, ri = D.pattern(-1)
+    kv = D.download(sb.ARR_KKT_VAL)
+    K = sp.csc_matrix((kv, ri, cp), shape=(dim, dim))
+    K = K + sp.tril(K, -1).T + sp.diags(np.concatenate([np.ones(n), -1e-6 * np.ones(me)]))
+    sol = np.concatenate([D.download(sb.ARR_P_X), -D.download(sb.ARR_P_Y)])
+    rhs = D.download(sb.ARR_RHS)
+    assert np.abs(K @ sol - rhs).max() <= 1e-7 * np.abs(rhs).max()
+    P.close_device(); P.close()
 
 
 def test_full_size_properties_n5000():
