@@ -276,6 +276,15 @@ typedef struct slpb_step_info {
   int32_t pad;
 } slpb_step_info;
 
+/* Optional: announces the barrier parameter of the next slpb_solve BEFORE the
+ * factorisation. The right-hand side (interior_point.hpp:444-448) does not
+ * depend on δ, γ, so it is built now and the following slpb_factor /
+ * slpb_factor_pair carries its forward substitution through the elimination
+ * (one extra column per front); slpb_solve(mu, …) with the same μ then only runs
+ * the backward pass. Same arithmetic, same bits as the separate forward pass.
+ * Any call that changes the iterate or the derivatives cancels it. */
+int slpb_prepare_rhs(slpb_solver* s, double mu);
+
 /* rhs (interior_point.hpp:444-448), p = lhs⁻¹ rhs, step recovery (:470-481),
  * both fraction-to-the-boundary rules (:488,497) and the pieces of D_ϕ (:508). */
 int slpb_solve(slpb_solver* s, double mu, double tau, slpb_step_info* info);

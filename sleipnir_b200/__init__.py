@@ -107,7 +107,8 @@ ABI_SYMBOLS = [
     "slpb_set_ignore_constraint_hessian", "slpb_analyze",
     "slpb_get_permutation", "slpb_set_iterate", "slpb_get_iterate",
     "slpb_eval_current", "slpb_kkt_stats_current", "slpb_kkt_stats_trial",
-    "slpb_factor", "slpb_factor_pair", "slpb_select_factor", "slpb_solve",
+    "slpb_factor", "slpb_factor_pair", "slpb_select_factor",
+    "slpb_prepare_rhs", "slpb_solve",
     "slpb_soc_begin", "slpb_soc_iterate",
     "slpb_trial", "slpb_accept", "slpb_array_size", "slpb_download",
     "slpb_pattern", "slpb_get_counters", "slpb_get_timers",
@@ -142,6 +143,7 @@ def device_lib() -> C.CDLL:
         L.slpb_factor_pair.argtypes = [vp, _dp, _dp, C.c_int,
                                        C.POINTER(FactorInfo)]
         L.slpb_select_factor.argtypes = [vp, C.c_int]
+        L.slpb_prepare_rhs.argtypes = [vp, C.c_double]
         L.slpb_solve.argtypes = [vp, C.c_double, C.c_double, C.POINTER(StepInfo)]
         L.slpb_soc_begin.argtypes = [vp]
         L.slpb_soc_iterate.argtypes = [vp, C.c_double, C.c_double, C.c_double,
@@ -297,6 +299,10 @@ class DeviceSession:
                                             int(reassemble), info),
                     "slpb_factor_pair")
         return info[0], info[1]
+
+    def prepare_rhs(self, mu):
+        """Lets the next factorisation carry the forward substitution."""
+        self._check(self.L.slpb_prepare_rhs(self.raw, mu), "slpb_prepare_rhs")
 
     def select_factor(self, which):
         self._check(self.L.slpb_select_factor(self.raw, which),

@@ -73,20 +73,17 @@ __device__ __forceinline__ ChildPre preload_child(
 
 constexpr int kPreChildren = 4;  // children whose metadata is pre-loaded
 
-/// Spins (relaxed polls, no L1 invalidation per poll) until *p ≥ need, then
-/// acquires once.
+/// Spins with acquire loads until *p ≥ need (short back-off: the dependency is
+/// usually a few hundred nanoseconds away and sits on the critical path).
 __device__ __forceinline__ void wait_children(const int* p, int need) {
-  if (need > 0) {
-    int v;
-    unsigned ns = 32;
-    for (;;) {
-      asm volatile("ld.relaxed.gpu.global.s32 %0, [%1];" : "=r"(v) : "l"(p) : "memory");
-      if (v >= need) break;
-      __nanosleep(ns);
-      if (ns < 256) ns <<= 1;
-    }
+  if (need <= 0) return;
+  int v;
+  unsigned spins = 0;
+  for (;;) {
+    asm volatile("ld.acquire.gpu.global.s32 %0, [%1];" : "=r"(v) : "l"(p) : "memory");
+    if (v >= need) break;
+    if (++spins > 16) __nanosleep(spins > 256 ? 200 : 40);
   }
-  __threadfence();
 }
 
 /// Elimination of the own columns of a front of order F ≤ 32 with the rows in
@@ -102,7 +99,12 @@ __device__ __forceinline__ void wait_children(const int* p, int need) {
 __device__ __noinline__ void ldlt_eliminate_rows(
     int lane, int F, int np, int m, const double* __restrict__ W,
     double* __restrict__ Dk, double* __restrict__ P, double* __restrict__ U,
-    int* __restrict__ local_stats) {
+    int* __restrict__ local_stats, double& rhs_i) {
+  // rhs_i: this lane's entry of the front's right-hand side; it takes part in
+  // the elimination (forward substitution carried along: r_i −= l_ik · r_k,
+  // the arithmetic of ldlt_forward_front) and returns y (lanes < np) and the
+  // update vector (lanes ≥ np).
+  double r = rhs_i;
   double w[32];
 #pragma unroll
   for (int j = 0; j < 32; ++j) {
@@ -136,6 +138,11 @@ __device__ __noinline__ void ldlt_eliminate_rows(
     }
     // column k of the L panel (the diagonal slot keeps d, as in the generic body)
     if (lane < F) P[lane + k * F] = lane > k ? l : wk;
+    {
+      const double rk = __shfl_sync(0xffffffffu, r, k);
+      const double upd = r - l * rk;
+      r = (lane > k && lane < F) ? upd : r;
+    }
     // trailing update in branch-free groups of 8 columns, so that the eight
     // shuffles and multiply-subtracts of a group overlap
 #pragma unroll
@@ -164,6 +171,7 @@ __device__ __noinline__ void ldlt_eliminate_rows(
       U[(lane - np) + jj * m] = w[jj];
     }
   }
+  rhs_i = r;
   if (lane == 0) {
     local_stats[0] = pos;
     local_stats[1] = neg;
@@ -174,6 +182,15 @@ __device__ __noinline__ void ldlt_eliminate_rows(
     local_stats[5] = static_cast<int>(bits >> 32);
   }
 }
+
+/// Right-hand side carried through the factorisation (forward substitution
+/// fused into the factor launch); rhs == nullptr switches it off.
+struct FusedRhs {
+  const double* rhs;      // un-permuted right-hand side
+  const int32_t* perm;
+  double* xperm;          // y of the own columns, elimination order
+  double* uvecs;          // update vectors, indexed like rel_idx
+};
 
 /// W: F×F column-major in shared memory; col: 64 doubles of shared scratch
 /// (scaled pivot column in [0,32), unscaled in [32,64)). `dep` is polled by
@@ -187,8 +204,12 @@ __device__ __forceinline__ void ldlt_factor_front_warp(
     double* __restrict__ panels, double* updates, double* __restrict__ D,
     double* __restrict__ W, double* __restrict__ col,
     const uchar2* __restrict__ tri, const int* dep, int* local_stats,
-    unsigned long long* stamp = nullptr) {
+    const FusedRhs& fr, unsigned long long* stamp = nullptr) {
   const int F = fm.F, np = fm.np, c0 = fm.c0, m = F - np;
+  // own part of the right-hand side (col[] doubles as the rhs work vector)
+  if (fr.rhs != nullptr && lane < F) {
+    col[lane] = lane < np ? fr.rhs[fr.perm[c0 + lane]] : 0.0;
+  }
 
   // ---- child-independent part: own KKT entries, δ/γ, child metadata ---------
   for (int i = lane; i < F * F; i += 32) W[i] = 0.0;
@@ -232,6 +253,9 @@ __device__ __forceinline__ void ldlt_factor_front_warp(
     }
     const int mc = cp.mc, ri = cp.ri;
     const double* U = cp.U;
+    if (fr.rhs != nullptr && lane < mc) {
+      col[ri] += __ldcg(fr.uvecs + cp.rel_off + lane);
+    }
     for (int j0 = 0; j0 < mc; j0 += 8) {
       double u[8];
 #pragma unroll
@@ -252,10 +276,17 @@ __device__ __forceinline__ void ldlt_factor_front_warp(
 
   // ---- elimination of the own columns + write-out (separate function so that
   // the 32-double row stays in registers) --------------------------------------
-  (void)col;
   (void)tri;
+  double rhs_i = (fr.rhs != nullptr && lane < F) ? col[lane] : 0.0;
   ldlt_eliminate_rows(lane, F, np, m, W, D + c0, panels + fm.panel_off,
-                      updates + fm.update_off, local_stats);
+                      updates + fm.update_off, local_stats, rhs_i);
+  if (fr.rhs != nullptr) {
+    if (lane < np) {
+      fr.xperm[c0 + lane] = rhs_i;
+    } else if (lane < F) {
+      fr.uvecs[fm.rel_off + (lane - np)] = rhs_i;
+    }
+  }
 }
 
 /// Forward substitution on a front (same arithmetic as ldlt_forward_front).

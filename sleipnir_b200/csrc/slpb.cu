@@ -86,7 +86,7 @@ struct DevGather {
 constexpr int kResultDoubles = 64;
 constexpr int kLongGather = 48;  // sources above which a block reduces an entry
 constexpr int kReduceThreads = 256;
-constexpr int kReduceBlocks = 148;  // one per SM
+constexpr int kReduceBlocks = 296;  // two per SM
 
 }  // namespace slpb
 
@@ -134,6 +134,10 @@ struct slpb_solver {
   bool use_tree = false;
   int tree_blocks = 0, tree_smem_doubles = 0;
   int factor_sel = 0;  // which variant of the last factorisation the solves use
+  // forward substitution fused into the factorisation (slpb_prepare_rhs)
+  bool rhs_ready = false;
+  double rhs_mu = 0.0;
+  bool fwd_valid[2] = {false, false};
   SymbolicView sview{};
   // device: steps
   DevBuf<double> px, ps, py, pz, spx, sps, spy, spz, ce_soc, cis_soc;
@@ -324,18 +328,17 @@ __global__ void k_gather(const int32_t* __restrict__ ptr,
 
 /// One block per entry with a long source list (a split Σ_k cost): fixed-shape
 /// tree reduction, deterministic from run to run.
-__global__ void k_gather_long(const int32_t* __restrict__ entries,
-                              const int32_t* __restrict__ ptr,
-                              const int32_t* __restrict__ src_idx,
-                              const int32_t* __restrict__ src_scale,
-                              const double* __restrict__ stage, double d_f,
-                              const double* __restrict__ d_c,
-                              double* __restrict__ out) {
-  __shared__ double red[256];
+__global__ void __launch_bounds__(1024)
+k_gather_long(const int32_t* __restrict__ entries,
+              const int32_t* __restrict__ ptr,
+              const int32_t* __restrict__ src_idx,
+              const int32_t* __restrict__ src_scale,
+              const double* __restrict__ stage, double d_f,
+              const double* __restrict__ d_c, double* __restrict__ out) {
+  __shared__ double red[1024];
   const int e = entries[blockIdx.x];
   const int b = ptr[e], en = ptr[e + 1];
-  double acc = 0.0;
-  for (int k = b + threadIdx.x; k < en; k += blockDim.x) {
+  auto term = [&](int k) -> double {
     const int32_t raw = src_idx[k];
     double v = stage[raw & 0x7fffffff];
     if (raw < 0) v = -v;
@@ -345,8 +348,11 @@ __global__ void k_gather_long(const int32_t* __restrict__ entries,
     } else if (sc >= 0) {
       v = d_c[sc] * v;
     }
-    acc += v;
-  }
+    return v;
+  };
+  // fixed assignment k ≡ tid (mod blockDim): deterministic from run to run
+  double acc = 0.0;
+  for (int k = b + threadIdx.x; k < en; k += blockDim.x) acc += term(k);
   red[threadIdx.x] = acc;
   __syncthreads();
   for (int w = blockDim.x / 2; w > 0; w >>= 1) {
@@ -780,6 +786,18 @@ __device__ __forceinline__ void wait_at_least(const int* p, int need) {
   }
 }
 
+/// Publishes everything this warp wrote (the lanes were joined by __syncwarp
+/// before) and bumps a dependency counter: one release-RMW instead of a full
+/// fence followed by an atomic.
+__device__ __forceinline__ void red_release_add(int* p, int v) {
+  asm volatile("red.release.gpu.global.add.s32 [%0], %1;" ::"l"(p), "r"(v)
+               : "memory");
+}
+__device__ __forceinline__ void st_release(int* p, int v) {
+  asm volatile("st.release.gpu.global.s32 [%0], %1;" ::"l"(p), "r"(v)
+               : "memory");
+}
+
 struct TreeView {
   const int32_t* order;      // fronts by ascending level
   const FrontMeta* metas;    // one packed record per front
@@ -807,8 +825,11 @@ __device__ __forceinline__ unsigned long long global_ns() {
 struct FactorPair {
   int n_variants;
   double delta1, gamma1;
-  int64_t panel_stride, update_stride;
+  int64_t panel_stride, update_stride, uvec_stride;
   int32_t dim;
+  const double* rhs;  // non-null: carry the forward substitution of this rhs
+  double* xperm;      // variant v: xperm + v·dim
+  double* uvecs;      // variant v: uvecs + v·uvec_stride
 };
 
 __global__ void __launch_bounds__(kTreeWarps * 32)
@@ -825,6 +846,10 @@ k_factor_tree(TreeView T, const double* __restrict__ Kval, double delta,
   double* W = smem + size_t(warp) * smem_doubles_per_warp;
   double* col = W + (smem_doubles_per_warp - 64);
   const int nv = pair.n_variants;
+  int acc_pos[2] = {0, 0}, acc_neg[2] = {0, 0}, acc_zero[2] = {0, 0};
+  int acc_zpiv[2] = {0, 0};
+  unsigned long long acc_min[2] = {0x7ff0000000000000ull,
+                                   0x7ff0000000000000ull};  // +inf
   for (;;) {
     int t = 0;
     if (lane == 0) t = atomicAdd(&T.sync[0], 1);
@@ -838,27 +863,55 @@ k_factor_tree(TreeView T, const double* __restrict__ Kval, double delta,
     int32_t* fcount = T.sync + 1 + v * T.n_super;
     int32_t* vstats = stats + 8 * v;
     if (T.debug && lane == 0 && v == 0) T.debug[3 * s] = global_ns();
+    const FusedRhs fr{pair.rhs, T.perm, pair.xperm + size_t(v) * pair.dim,
+                      pair.uvecs + v * pair.uvec_stride};
     ldlt_factor_front_warp(
         lane, fm, T.metas, T.child_idx, T.rel_idx, T.asm_src, T.asm_dst,
         T.col_is_primal, Kval, v ? pair.delta1 : delta,
         v ? pair.gamma1 : gamma, panels + v * pair.panel_stride,
         updates + v * pair.update_stride, D + v * pair.dim, W, col, tri,
-        &fcount[s], ls[warp],
+        &fcount[s], ls[warp], fr,
         (T.debug && v == 0) ? T.debug + 3 * s + 1 : nullptr);
     __syncwarp();
     if (T.debug && lane == 0 && v == 0) T.debug[3 * s + 2] = global_ns();
     if (lane == 0) {
-      atomicAdd(&vstats[0], ls[warp][0]);
-      atomicAdd(&vstats[1], ls[warp][1]);
-      atomicAdd(&vstats[2], ls[warp][2]);
-      atomicOr(&vstats[3], ls[warp][3]);
+      // hand over to the parent first; the inertia bookkeeping stays in
+      // registers until the warp runs out of fronts
+      if (fm.parent >= 0) red_release_add(&fcount[fm.parent], 1);
+      acc_pos[v] += ls[warp][0];
+      acc_neg[v] += ls[warp][1];
+      acc_zero[v] += ls[warp][2];
+      acc_zpiv[v] |= ls[warp][3];
       const unsigned long long bits =
           (unsigned long long)(unsigned)ls[warp][4] |
           ((unsigned long long)(unsigned)ls[warp][5] << 32);
-      atomicMin(reinterpret_cast<unsigned long long*>(&vstats[4]), bits);
-      __threadfence();
-      if (fm.parent >= 0) atomicAdd(&fcount[fm.parent], 1);
+      acc_min[v] = bits < acc_min[v] ? bits : acc_min[v];
     }
+    (void)vstats;
+  }
+  if (lane == 0) {
+    for (int v = 0; v < nv; ++v) {
+      int32_t* vstats = stats + 8 * v;
+      if (acc_pos[v]) atomicAdd(&vstats[0], acc_pos[v]);
+      if (acc_neg[v]) atomicAdd(&vstats[1], acc_neg[v]);
+      if (acc_zero[v]) atomicAdd(&vstats[2], acc_zero[v]);
+      if (acc_zpiv[v]) atomicOr(&vstats[3], acc_zpiv[v]);
+      atomicMin(reinterpret_cast<unsigned long long*>(&vstats[4]), acc_min[v]);
+    }
+  }
+}
+
+/// Prepares the ticket/flag words of k_solve_tree. With skip_forward the
+/// forward substitution was carried by the factorisation: tickets start at ns
+/// and every "forward done" flag is already set.
+__global__ void k_init_solve_sync(int32_t* __restrict__ sync, int ns,
+                                  int skip_forward) {
+  const int i = blockIdx.x * blockDim.x + threadIdx.x;
+  if (i == 0) sync[0] = skip_forward ? ns : 0;
+  if (i < ns) {
+    sync[1 + i] = 0;                          // fcount
+    sync[1 + ns + i] = skip_forward ? 1 : 0;  // fflag
+    sync[1 + 2 * ns + i] = 0;                 // bflag
   }
 }
 
@@ -888,9 +941,10 @@ k_solve_tree(TreeView T, const double* __restrict__ panels,
                               panels, rhs, xperm, uvecs, w, &fcount[s]);
       __syncwarp();
       if (lane == 0) {
-        __threadfence();
-        atomicExch(&fflag[s], 1);
-        if (fm.parent >= 0) atomicAdd(&fcount[fm.parent], 1);
+        if (fm.parent >= 0) {
+          red_release_add(&fcount[fm.parent], 1);
+        }
+        st_release(&fflag[s], 1);
       }
     } else {
       const int s = T.order[2 * ns - 1 - t];
@@ -900,10 +954,7 @@ k_solve_tree(TreeView T, const double* __restrict__ panels,
       __syncwarp();
       if (lane < fm.np) sol[T.perm[fm.c0 + lane]] = xperm[fm.c0 + lane];
       __syncwarp();
-      if (lane == 0) {
-        __threadfence();
-        atomicExch(&bflag[s], 1);
-      }
+      if (lane == 0) st_release(&bflag[s], 1);
     }
   }
 }
@@ -1065,11 +1116,12 @@ inline int blocks_for(int64_t n, int threads) {
   return static_cast<int>((n + threads - 1) / threads);
 }
 
-/// Grid of a reduction kernel: enough blocks for ~4 elements per thread, at
-/// most one block per SM.
+/// Grid of a reduction kernel: about one element per thread (the reductions
+/// are latency-bound: short per-thread loops matter more than few blocks), at
+/// most two blocks per SM.
 inline int red_blocks(int64_t n) {
   return std::max(1, std::min<int>(kReduceBlocks,
-                                   blocks_for(n, 4 * kReduceThreads)));
+                                   blocks_for(n, kReduceThreads)));
 }
 inline RedBuf red_buf(slpb_solver* S) {
   return {S->red_partials.p, S->red_counter.p};
@@ -1136,7 +1188,7 @@ int run_gather(slpb_solver* S, const DevGather& d, const double* stage,
       d.n_entries);
   ++S->counters.kernel_launches;
   if (d.n_long > 0) {
-    k_gather_long<<<d.n_long, 256, 0, S->stream>>>(
+    k_gather_long<<<d.n_long, 1024, 0, S->stream>>>(
         d.long_entries.p, d.ptr.p, d.src_idx.p, d.src_scale.p, stage, S->d_f,
         S->d_c.p, out);
     ++S->counters.kernel_launches;
@@ -1292,18 +1344,38 @@ TreeView tree_view(slpb_solver* S) {
   return T;
 }
 
-int launch_solve(slpb_solver* S) {
+/// Σ, S⁻¹, t and rhs = −[g − A_eᵀy − A_iᵀt ; c_e] (interior_point.hpp:444-448;
+/// with the SOC accumulators, :611-616).
+int build_rhs(slpb_solver* S, double mu, const double* cis_soc,
+              const double* ce_for_rhs) {
+  const int n = S->n, me = S->me, mi = S->mi;
+  if (mi > 0) {
+    k_sigma_t<<<blocks_for(mi, 256), 256, 0, S->stream>>>(
+        S->s.p, S->z.p, S->vals_cur.p + 1 + me, cis_soc, mu,
+        cis_soc ? 1 : 0, mi, S->sinv.p, S->sigma.p, S->tvec.p);
+    ++S->counters.kernel_launches;
+  }
+  k_rhs<<<blocks_for(S->dim, 256), 256, 0, S->stream>>>(
+      ae_view(S), ai_view(S), S->dvals.p + S->ad.off_g, S->y.p, S->tvec.p,
+      ce_for_rhs, n, me, S->rhs.p);
+  ++S->counters.kernel_launches;
+  CU(cudaGetLastError());
+  return SLPB_OK;
+}
+
+int launch_solve(slpb_solver* S, bool skip_forward) {
   const Symbolic& Y = S->sym;
   CU(cudaEventRecord(S->ev[8], S->stream));
   if (S->use_tree) {
-    CU(cudaMemsetAsync(S->tree_sync.p, 0, (1 + 3 * size_t(Y.n_super)) * 4,
-                       S->stream));
+    const int sel = S->factor_sel;
+    k_init_solve_sync<<<blocks_for(Y.n_super, 256), 256, 0, S->stream>>>(
+        S->tree_sync.p, Y.n_super, skip_forward ? 1 : 0);
     const TreeView T = tree_view(S);
     k_solve_tree<<<S->tree_blocks, kTreeWarps * 32, 0, S->stream>>>(
-        T, S->panels.p + S->factor_sel * Y.panel_size,
-        S->D.p + size_t(S->factor_sel) * Y.dim, S->rhs.p, S->xperm.p,
-        S->uvecs.p, S->sol.p);
-    ++S->counters.kernel_launches;
+        T, S->panels.p + sel * Y.panel_size, S->D.p + size_t(sel) * Y.dim,
+        S->rhs.p, S->xperm.p + size_t(sel) * Y.dim,
+        S->uvecs.p + size_t(sel) * Y.rel_ptr.back(), S->sol.p);
+    S->counters.kernel_launches += 2;
   } else {
     const int smem = Y.max_front * static_cast<int>(sizeof(double));
     for (int L = 0; L < Y.n_levels; ++L) {
@@ -1334,17 +1406,17 @@ int solve_into(slpb_solver* S, double mu, double tau, const double* cis_soc,
                const double* ce_for_rhs, double* px, double* ps, double* py,
                double* pz, slpb_step_info* info) {
   const int n = S->n, me = S->me, mi = S->mi;
-  if (mi > 0) {
-    k_sigma_t<<<blocks_for(mi, 256), 256, 0, S->stream>>>(
-        S->s.p, S->z.p, S->vals_cur.p + 1 + me, cis_soc, mu,
-        cis_soc ? 1 : 0, mi, S->sinv.p, S->sigma.p, S->tvec.p);
-    ++S->counters.kernel_launches;
+  // the factorisation already carried this right-hand side forward?
+  const bool fused = cis_soc == nullptr && S->use_tree && S->rhs_ready &&
+                     S->rhs_mu == mu && S->fwd_valid[S->factor_sel];
+  if (!fused) {
+    int rc0 = build_rhs(S, mu, cis_soc, ce_for_rhs);
+    if (rc0) return rc0;
+    // a different right-hand side now sits in rhs/xperm/uvecs
+    S->rhs_ready = false;
+    S->fwd_valid[0] = S->fwd_valid[1] = false;
   }
-  k_rhs<<<blocks_for(S->dim, 256), 256, 0, S->stream>>>(
-      ae_view(S), ai_view(S), S->dvals.p + S->ad.off_g, S->y.p, S->tvec.p,
-      ce_for_rhs, n, me, S->rhs.p);
-  ++S->counters.kernel_launches;
-  int rc = launch_solve(S);
+  int rc = launch_solve(S, fused);
   if (rc) return rc;
   const int m = std::max(n, std::max(me, mi));
   k_step_recover<<<blocks_for(m, 256), 256, 0, S->stream>>>(
@@ -1616,8 +1688,8 @@ int slpb_analyze(slpb_solver* S, int ordering, const int32_t* perm,
   CU(S->panels.alloc(2 * Y.panel_size));
   CU(S->updates.alloc(2 * Y.update_size));
   CU(S->D.alloc(2 * size_t(Y.dim)));
-  CU(S->uvecs.alloc(Y.rel_ptr.back()));
-  CU(S->xperm.alloc(Y.dim));
+  CU(S->uvecs.alloc(2 * size_t(Y.rel_ptr.back())));
+  CU(S->xperm.alloc(2 * size_t(Y.dim)));
   CU(S->fstats.alloc(16));
   {
     std::vector<int32_t> nchild(Y.n_super);
@@ -1707,6 +1779,7 @@ int slpb_set_iterate(slpb_solver* S, const double* x, const double* sl,
                      const double* y, const double* z) {
   if (!S || !S->finalized) return SLPB_ERR_STATE;
   CU(cudaSetDevice(S->device));
+  S->rhs_ready = false;
   auto put = [&](DevBuf<double>& b, const double* src) -> cudaError_t {
     if (b.n == 0) return cudaSuccess;
     if (!src) return cudaErrorInvalidValue;
@@ -1744,6 +1817,7 @@ int slpb_eval_current(slpb_solver* S, int derivatives,
                       slpb_point_info* info) {
   if (!S || !S->finalized || !info) return SLPB_ERR_STATE;
   CU(cudaSetDevice(S->device));
+  S->rhs_ready = false;
   int rc;
   if ((rc = refresh_leaves(S, S->x.p, S->y.p, S->z.p, S->leaf_cur.p))) return rc;
   if (derivatives != 2) {
@@ -1778,6 +1852,7 @@ int slpb_kkt_stats_trial(slpb_solver* S, double mu, slpb_kkt_stats* out) {
   CU(cudaSetDevice(S->device));
   // g, A_e, A_i at the trial point (interior_point.hpp:704-706). This
   // overwrites the derivative arrays; the driver re-linearises afterwards.
+  S->rhs_ready = false;
   int rc;
   if ((rc = refresh_leaves(S, S->tx.p, S->ty.p, S->tz.p, S->leaf_trial.p))) {
     return rc;
@@ -1834,12 +1909,18 @@ int factor_impl(slpb_solver* S, int n_variants, const double* delta,
                           n_variants == 2 ? gamma[1] : 0.0,
                           Y.panel_size,
                           Y.update_size,
-                          Y.dim};
+                          static_cast<int64_t>(Y.rel_ptr.back()),
+                          Y.dim,
+                          S->rhs_ready ? S->rhs.p : nullptr,
+                          S->xperm.p,
+                          S->uvecs.p};
+    for (int v = 0; v < 2; ++v) S->fwd_valid[v] = S->rhs_ready && v < n_variants;
     k_factor_tree<<<S->tree_blocks, kTreeWarps * 32, smem, S->stream>>>(
         T, S->Kval.p, delta[0], gamma[0], pair, S->panels.p, S->updates.p,
         S->D.p, S->fstats.p, S->tree_smem_doubles);
     ++S->counters.kernel_launches;
   } else {
+    S->fwd_valid[0] = S->fwd_valid[1] = false;
     const int smem = static_cast<int>(
         (size_t(Y.max_front) * Y.max_front + Y.max_front) * sizeof(double));
     for (int v = 0; v < n_variants; ++v) {
@@ -1894,6 +1975,17 @@ int slpb_select_factor(slpb_solver* S, int which) {
   if (!S || !S->analyzed) return SLPB_ERR_STATE;
   if (which != 0 && which != 1) return SLPB_ERR_ARGUMENT;
   S->factor_sel = which;
+  return SLPB_OK;
+}
+
+int slpb_prepare_rhs(slpb_solver* S, double mu) {
+  if (!S || !S->analyzed) return SLPB_ERR_STATE;
+  CU(cudaSetDevice(S->device));
+  int rc = build_rhs(S, mu, nullptr, S->vals_cur.p + 1);
+  if (rc) return rc;
+  S->rhs_ready = true;
+  S->rhs_mu = mu;
+  S->fwd_valid[0] = S->fwd_valid[1] = false;
   return SLPB_OK;
 }
 
@@ -1961,6 +2053,7 @@ int slpb_trial(slpb_solver* S, double alpha, double alpha_z, int which_step,
 
 int slpb_accept(slpb_solver* S, double mu) {
   if (!S || !S->analyzed) return SLPB_ERR_STATE;
+  S->rhs_ready = false;
   CU(cudaSetDevice(S->device));
   auto cp = [&](DevBuf<double>& dst, DevBuf<double>& src) -> cudaError_t {
     if (dst.n == 0) return cudaSuccess;

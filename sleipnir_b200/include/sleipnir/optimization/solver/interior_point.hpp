@@ -453,6 +453,9 @@ ExitStatus interior_point(
     bool call_feasibility_restoration = false;
 
     // lhs assembly + factorisation with inertia correction (:426-465)
+    // The right-hand side does not depend on δ/γ: build it first so that the
+    // factorisation carries its forward substitution (slpb_prepare_rhs).
+    SLP_DEVICE_CALL(dev, slpb_prepare_rhs(dev, mu));
     if (!solver.compute()) return ExitStatus::FACTORIZATION_FAILED;
 
     // rhs, solve, step recovery, fraction-to-the-boundary (:444-497)

@@ -186,6 +186,47 @@ def test_factor_pair_matches_two_single_factorisations():
     P.close_device(); P.close(); O.close()
 
 
+def test_fused_forward_substitution_matches_separate_solve():
+    """slpb_prepare_rhs makes the factorisation carry the forward substitution;
+    the step must have the bits of the factor-then-full-solve path."""
+    name, N = "cart_pole", 80
+    P, O = sb.Problem(name, N), OracleProblem(name, N)
+    O.eval_setup()
+    d_f, d_ce, d_ci = O.scaling()
+    D = P.open_device()
+    D.set_scaling(d_f, d_ce, d_ci)
+    x, s, y, z = _state(P, O, 9)
+    D.set_iterate(x, s, y, z)
+    D.eval_current(1)
+    D.analyze()
+    mu = 0.07
+    D.factor(1e-2, 1e-8, True)
+    si0 = D.solve(mu, 0.99)
+    ref = [D.download(a) for a in (sb.ARR_P_X, sb.ARR_P_Y, sb.ARR_P_S, sb.ARR_P_Z)]
+    c0 = D.counters().kernel_launches
+    D.prepare_rhs(mu)
+    D.factor(1e-2, 1e-8, True)
+    si1 = D.solve(mu, 0.99)
+    for a, r in zip((sb.ARR_P_X, sb.ARR_P_Y, sb.ARR_P_S, sb.ARR_P_Z), ref):
+        np.testing.assert_array_equal(D.download(a), r)
+    assert (si1.alpha_max, si1.alpha_z) == (si0.alpha_max, si0.alpha_z)
+    # pair + selection of the second variant
+    D.prepare_rhs(mu)
+    D.factor_pair([0.0, 1e-2], [0.0, 1e-8], True)
+    D.select_factor(1)
+    D.solve(mu, 0.99)
+    np.testing.assert_array_equal(D.download(sb.ARR_P_X), ref[0])
+    # a different mu falls back to the full solve and still agrees with itself
+    D.prepare_rhs(mu)
+    D.factor(1e-2, 1e-8, True)
+    si2 = D.solve(0.5 * mu, 0.99)
+    D.factor(1e-2, 1e-8, True)
+    si3 = D.solve(0.5 * mu, 0.99)
+    assert si2.alpha_max == si3.alpha_max and si2.g_dot_px == si3.g_dot_px
+    assert c0 > 0
+    P.close_device(); P.close(); O.close()
+
+
 def test_trial_point_and_accept():
     name, N = "cart_pole", 60
     P, O = sb.Problem(name, N), OracleProblem(name, N)
