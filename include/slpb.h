@@ -303,6 +303,22 @@ int slpb_soc_iterate(slpb_solver* s, double mu, double tau, double alpha_soc,
 int slpb_trial(slpb_solver* s, double alpha, double alpha_z, int which_step,
                int slack_from_ci, slpb_point_info* info);
 
+/* Evaluates f, c_e, c_i at a HOST-supplied point (x, s) without touching the
+ * current iterate (it lands in the trial buffers): the acceptance test of
+ * feasibility restoration (interior_point.hpp:738-756) probes the original
+ * problem at the restoration iterate this way. */
+int slpb_probe_point(slpb_solver* s, const double* x, const double* sl,
+                     slpb_point_info* info);
+
+/* Least-squares multiplier estimate at the current iterate
+ * (lagrange_multiplier_estimate.hpp:55-131): y, z ← argmin ‖Âᵀ[y; z] − [∇f; −μe]‖,
+ * Â = [A_e 0; A_i −S], z clamped to [μ/(κs), κμ/s]. Needs g, A_e, A_i of the
+ * current iterate (slpb_eval_current with derivatives) and slpb_analyze. Solved
+ * as the equivalent system with the Newton matrix's pattern (H → I, Σ → S⁻²),
+ * so it reuses the symbolic factorisation; overwrites the assembled lhs and
+ * the factor. info reports the inertia of that factorisation. */
+int slpb_multiplier_estimate(slpb_solver* s, double mu, slpb_factor_info* info);
+
 /* Commits the trial point: x,s,y,z,f,c_e,c_i ← trial, clamps z to
  * [μ/(κs), κμ/s], κ = 1e10 (interior_point.hpp:779-805). */
 int slpb_accept(slpb_solver* s, double mu);

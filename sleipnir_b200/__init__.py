@@ -110,7 +110,7 @@ ABI_SYMBOLS = [
     "slpb_factor", "slpb_factor_pair", "slpb_select_factor",
     "slpb_prepare_rhs", "slpb_solve",
     "slpb_soc_begin", "slpb_soc_iterate",
-    "slpb_trial", "slpb_accept", "slpb_array_size", "slpb_download",
+    "slpb_trial", "slpb_probe_point", "slpb_multiplier_estimate", "slpb_accept", "slpb_array_size", "slpb_download",
     "slpb_pattern", "slpb_get_counters", "slpb_get_timers",
     "slpb_last_device_ms", "slpb_flush_l2", "slpb_stream",
 ]
@@ -151,6 +151,9 @@ def device_lib() -> C.CDLL:
         L.slpb_trial.argtypes = [vp, C.c_double, C.c_double, C.c_int, C.c_int,
                                  C.POINTER(PointInfo)]
         L.slpb_accept.argtypes = [vp, C.c_double]
+        L.slpb_probe_point.argtypes = [vp, _dp, _dp, C.POINTER(PointInfo)]
+        L.slpb_multiplier_estimate.argtypes = [vp, C.c_double,
+                                               C.POINTER(FactorInfo)]
         L.slpb_array_size.argtypes = [vp, C.c_int, _lp]
         L.slpb_download.argtypes = [vp, C.c_int, _dp]
         L.slpb_pattern.argtypes = [vp, C.c_int, _ip, _ip, _lp, _ip, _ip]
@@ -194,6 +197,11 @@ def host_lib() -> C.CDLL:
         L.slpbh_flush_seconds.restype = C.c_double
         L.slpbh_flush_seconds.argtypes = [vp]
         L.slpbh_phase_seconds.argtypes = [vp, _dp]
+        L.slpbh_set_timeout.argtypes = [vp, C.c_double]
+        L.slpbh_add_recording_callback.argtypes = [vp, C.c_int, C.c_int]
+        L.slpbh_clear_callbacks.argtypes = [vp]
+        L.slpbh_callback_log.restype = C.c_int
+        L.slpbh_callback_log.argtypes = [vp, _dp, C.c_int, _dp]
         L.slpbh_symbolic_stats.argtypes = [vp, _lp]
         L.slpbh_counters.argtypes = [vp, _lp]
         L.slpbh_timers.argtypes = [vp, _dp]
@@ -329,6 +337,20 @@ class DeviceSession:
                                       slack_from_ci, C.byref(info)), "slpb_trial")
         return info
 
+    def probe_point(self, x, s):
+        info = PointInfo()
+        x = np.ascontiguousarray(x, dtype=np.float64)
+        s = np.ascontiguousarray(s if self.mi else np.zeros(1), dtype=np.float64)
+        self._check(self.L.slpb_probe_point(self.raw, _d(x), _d(s),
+                                            C.byref(info)), "slpb_probe_point")
+        return info
+
+    def multiplier_estimate(self, mu):
+        info = FactorInfo()
+        self._check(self.L.slpb_multiplier_estimate(self.raw, mu, C.byref(info)),
+                    "slpb_multiplier_estimate")
+        return info
+
     def accept(self, mu):
         self._check(self.L.slpb_accept(self.raw, mu), "slpb_accept")
 
@@ -423,11 +445,17 @@ class Problem:
             sc = np.zeros(16)
             x = s = y = z = None
             if self._keep:
-                x, s = np.zeros(self.n), np.zeros(max(self.mi, 1))
-                y, z = np.zeros(max(self.me, 1)), np.zeros(max(self.mi, 1))
+                # restoration rows (type 1) carry the enlarged problem's vectors
+                extra = 2 * self.me + 2 * self.mi
+                x, s = np.zeros(self.n + extra), np.zeros(self.mi + extra + 1)
+                y, z = np.zeros(max(self.me, 1)), np.zeros(self.mi + extra + 1)
             self.H.slpbh_trace_get(self.h, r, _d(sc), _d(x), _d(s), _d(y), _d(z))
             if self._keep:
-                s, y, z = s[:self.mi], y[:self.me], z[:self.mi]
+                if int(sc[1]) == 0:
+                    x, s, z = x[:self.n], s[:self.mi], z[:self.mi]
+                else:
+                    s, z = s[:self.mi + extra], z[:self.mi + extra]
+                y = y[:self.me]
             rows.append(IterationRecord(int(sc[0]), int(sc[1]), *sc[2:12],
                                         int(sc[12]), int(sc[13]), int(sc[14]),
                                         float(sc[15]), x, s, y, z))
@@ -441,6 +469,27 @@ class Problem:
 
     def loop_seconds(self):
         return self.H.slpbh_loop_seconds(self.h)
+
+    def set_timeout(self, seconds):
+        """Options::timeout of the following solves (negative: none)."""
+        self.H.slpbh_set_timeout(self.h, float(seconds))
+
+    def add_callback(self, stop_at=-1, persistent=False):
+        """Registers an iteration callback (Problem::add_callback /
+        add_persistent_callback) that records the IterationInfo it receives and
+        returns true once iteration `stop_at` is reached."""
+        self.H.slpbh_add_recording_callback(self.h, int(stop_at), int(persistent))
+
+    def clear_callbacks(self):
+        self.H.slpbh_clear_callbacks(self.h)
+
+    def callback_log(self):
+        """(records, last_x): one row per callback invocation — iteration, n,
+        ‖x‖∞, |s|, |y|, |z|, nnz(H)+nnz(A_e)+nnz(A_i), |g|."""
+        out = np.zeros(8 * 4096)
+        last_x = np.zeros(max(self.n, 1))
+        k = self.H.slpbh_callback_log(self.h, _d(out), 4096, _d(last_x))
+        return out[:8 * min(k, 4096)].reshape(-1, 8), last_x[:self.n]
 
     def set_flush_l2(self, on=True):
         """Benchmark hygiene: evict the device L2 before every iteration of the

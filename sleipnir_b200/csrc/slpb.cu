@@ -21,7 +21,9 @@
 #include <cstdio>
 #include <cstdlib>
 #include <cstring>
+#include <map>
 #include <memory>
+#include <mutex>
 #include <string>
 #include <vector>
 
@@ -119,6 +121,7 @@ struct slpb_solver {
   DevBuf<int32_t> ai_rowptr, ai_rcol, ai_ridx;  // A_i by rows
   // device: KKT
   DevBuf<int32_t> k_h_idx, k_ae_idx, k_prod_ptr, k_prod_a, k_prod_b, k_prod_row;
+  DevBuf<uint8_t> k_diag_flag;  // KKT entry is a primal diagonal entry
   DevBuf<double> Kval, sigma, sinv, tvec, rhs, sol;
   // device: symbolic + factor
   DevBuf<int32_t> sy_super_first, sy_front_dim, sy_rows_idx, sy_child_idx,
@@ -695,6 +698,83 @@ __global__ void k_kkt_assemble(const int32_t* __restrict__ h_idx,
                       Aev, Aiv, sigma);
 }
 
+// ---- Lagrange multiplier estimate (lagrange_multiplier_estimate.hpp:55-131) ---
+// The reference solves the normal equations (ÂÂᵀ)[y; z] = Â[∇f; −μe] with
+// Â = [A_e 0; A_i −S]. Eliminating the slack block of the equivalent augmented
+// system [I Âᵀ; Â 0] gives a system with the pattern of the Newton matrix:
+//   [I + A_iᵀS⁻²A_i  A_eᵀ; A_e  0] [r; y] = [∇f − μA_iᵀS⁻¹e; 0],
+//   z = S⁻²(A_i r + μs),
+// so the estimate reuses the assembly recipe, the symbolic factorisation and the
+// tree kernels (H → I, Σ → S⁻²).
+
+/// lhs entry e with H replaced by the identity; sigma holds S⁻².
+__global__ void k_kkt_assemble_identity(
+    const uint8_t* __restrict__ diag_flag, const int32_t* __restrict__ ae_idx,
+    const int32_t* __restrict__ prod_ptr, const int32_t* __restrict__ prod_a,
+    const int32_t* __restrict__ prod_b, const int32_t* __restrict__ prod_row,
+    const double* __restrict__ Aev, const double* __restrict__ Aiv,
+    const double* __restrict__ sigma, int nnz, double* __restrict__ Kval) {
+  const int e = blockIdx.x * blockDim.x + threadIdx.x;
+  if (e >= nnz) return;
+  const int ae = ae_idx[e];
+  if (ae >= 0) {
+    Kval[e] = Aev[ae];
+    return;
+  }
+  double v = diag_flag[e] ? 1.0 : 0.0;
+  for (int k = prod_ptr[e]; k < prod_ptr[e + 1]; ++k) {
+    v += (Aiv[prod_a[k]] * sigma[prod_row[k]]) * Aiv[prod_b[k]];
+  }
+  Kval[e] = v;
+}
+
+__global__ void k_inv_square(const double* __restrict__ s, int mi,
+                             double* __restrict__ out) {
+  const int i = blockIdx.x * blockDim.x + threadIdx.x;
+  if (i < mi) out[i] = 1.0 / (s[i] * s[i]);
+}
+
+/// rhs = [∇f − μ A_iᵀ S⁻¹ e ; 0]
+__global__ void k_rhs_estimate(CscView Ai, const double* __restrict__ g,
+                               const double* __restrict__ s, double mu, int n,
+                               int me, double* __restrict__ rhs) {
+  const int c = blockIdx.x * blockDim.x + threadIdx.x;
+  if (c < n) {
+    double acc = 0.0;
+    for (int k = Ai.colptr[c]; k < Ai.colptr[c + 1]; ++k) {
+      acc += Ai.val[k] * (1.0 / s[Ai.rowidx[k]]);
+    }
+    rhs[c] = g[c] - mu * acc;
+  } else if (c < n + me) {
+    rhs[c] = 0.0;
+  }
+}
+
+/// y = sol₂ ; z = clamp(S⁻²(A_i r + μs), μ/(κs), κμ/s), κ = 1e10.
+__global__ void k_estimate_finish(const double* __restrict__ sol,
+                                  const int32_t* __restrict__ ai_rowptr,
+                                  const int32_t* __restrict__ ai_rcol,
+                                  const int32_t* __restrict__ ai_ridx,
+                                  const double* __restrict__ ai_val,
+                                  const double* __restrict__ s, double mu, int n,
+                                  int me, int mi, double* __restrict__ y,
+                                  double* __restrict__ z) {
+  const int i = blockIdx.x * blockDim.x + threadIdx.x;
+  if (i < me) y[i] = sol[n + i];
+  if (i < mi) {
+    double acc = 0.0;
+    for (int k = ai_rowptr[i]; k < ai_rowptr[i + 1]; ++k) {
+      acc += ai_val[ai_ridx[k]] * sol[ai_rcol[k]];
+    }
+    const double si = s[i];
+    const double v = (acc + mu * si) / (si * si);
+    const double kappa = 1e10;
+    const double lo = 1.0 / kappa * mu / si;
+    const double hi = kappa * mu / si;
+    z[i] = v < lo ? lo : (hi < v ? hi : v);
+  }
+}
+
 // ---------------------------------------------------------------------------
 // kernels: multifrontal LDLᵀ, one thread block per front, one launch per
 // level of the assembly tree
@@ -1151,6 +1231,22 @@ int upload_program_set(slpb_solver* S, ProgramSet& ps, DevProgramSet& d) {
   return SLPB_OK;
 }
 
+/// Raises (never lowers) a kernel's dynamic shared-memory limit.
+template <typename Kernel>
+cudaError_t raise_dynamic_smem(Kernel kernel, int bytes) {
+  static std::mutex mu;
+  static std::map<const void*, int> current;
+  std::lock_guard<std::mutex> lock{mu};
+  const void* key = reinterpret_cast<const void*>(kernel);
+  int& have = current[key];
+  const int want = std::max(bytes, 48 * 1024);
+  if (want <= have) return cudaSuccess;
+  const cudaError_t e = cudaFuncSetAttribute(
+      kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, want);
+  if (e == cudaSuccess) have = want;
+  return e;
+}
+
 int upload_gather(slpb_solver* S, const Gather& g, DevGather& d) {
   d.n_entries = g.n_entries();
   CU(d.ptr.upload(g.ptr, S->stream));
@@ -1378,16 +1474,18 @@ int launch_solve(slpb_solver* S, bool skip_forward) {
     S->counters.kernel_launches += 2;
   } else {
     const int smem = Y.max_front * static_cast<int>(sizeof(double));
+    const double* panels = S->panels.p + S->factor_sel * Y.panel_size;
+    const double* Dsel = S->D.p + size_t(S->factor_sel) * Y.dim;
     for (int L = 0; L < Y.n_levels; ++L) {
       const int cnt = Y.level_ptr[L + 1] - Y.level_ptr[L];
       k_forward_level<<<cnt, kFrontThreads, smem, S->stream>>>(
-          S->sview, S->sy_level_supers.p + Y.level_ptr[L], S->panels.p,
-          S->rhs.p, S->xperm.p, S->uvecs.p);
+          S->sview, S->sy_level_supers.p + Y.level_ptr[L], panels, S->rhs.p,
+          S->xperm.p, S->uvecs.p);
     }
     for (int L = Y.n_levels - 1; L >= 0; --L) {
       const int cnt = Y.level_ptr[L + 1] - Y.level_ptr[L];
       k_backward_level<<<cnt, kFrontThreads, smem, S->stream>>>(
-          S->sview, S->sy_level_supers.p + Y.level_ptr[L], S->panels.p, S->D.p,
+          S->sview, S->sy_level_supers.p + Y.level_ptr[L], panels, Dsel,
           S->xperm.p);
     }
     k_unpermute<<<blocks_for(S->dim, 256), 256, 0, S->stream>>>(
@@ -1563,9 +1661,10 @@ int slpb_finalize(slpb_solver* S) {
   if ((rc = upload_gather(S, S->ad.deriv_gather, S->gd))) return rc;
   CU(S->vstage.upload(S->ad.value_stage_init, S->stream));
   CU(S->dstage.upload(S->ad.deriv_stage_init, S->stream));
-  CU(cudaFuncSetAttribute(
-      k_ad_sweep, cudaFuncAttributeMaxDynamicSharedMemorySize,
-      std::max(std::max(S->pv.max_smem, S->pd.max_smem), 48 * 1024)));
+  // Function attributes are per process, not per handle: only ever raise them
+  // (a second handle — feasibility restoration, multistart — must not lower
+  // what a live handle relies on).
+  CU(raise_dynamic_smem(k_ad_sweep, std::max(S->pv.max_smem, S->pd.max_smem)));
 
   CU(S->leaf_cur.alloc(n + me + mi));
   CU(S->leaf_trial.alloc(n + me + mi));
@@ -1615,6 +1714,11 @@ int slpb_finalize(slpb_solver* S) {
   CU(S->k_prod_a.upload(S->recipe.prod_a, S->stream));
   CU(S->k_prod_b.upload(S->recipe.prod_b, S->stream));
   CU(S->k_prod_row.upload(S->recipe.prod_row, S->stream));
+  {
+    std::vector<uint8_t> flag(S->recipe.K.nnz(), 0);
+    for (int c = 0; c < n; ++c) flag[S->recipe.diag_idx[c]] = 1;
+    CU(S->k_diag_flag.upload(flag, S->stream));
+  }
   CU(S->Kval.alloc(S->recipe.K.nnz()));
   CU(S->rhs.alloc(S->dim));
   CU(S->sol.alloc(S->dim));
@@ -1665,9 +1769,7 @@ int slpb_analyze(slpb_solver* S, int ordering, const int32_t* perm,
                 "a frontal matrix exceeds 200 KB of shared memory (front order " +
                     std::to_string(Y.max_front) + ")");
   }
-  CU(cudaFuncSetAttribute(k_factor_level,
-                          cudaFuncAttributeMaxDynamicSharedMemorySize,
-                          std::max<int>(front_smem, 48 * 1024)));
+  CU(raise_dynamic_smem(k_factor_level, static_cast<int>(front_smem)));
   CU(S->sy_super_first.upload(Y.super_first, S->stream));
   CU(S->sy_front_dim.upload(Y.front_dim, S->stream));
   CU(S->sy_rows_ptr.upload(Y.rows_ptr, S->stream));
@@ -1732,9 +1834,7 @@ int slpb_analyze(slpb_solver* S, int ordering, const int32_t* perm,
   {
     const int tree_smem =
         kTreeWarps * S->tree_smem_doubles * static_cast<int>(sizeof(double));
-    CU(cudaFuncSetAttribute(k_factor_tree,
-                            cudaFuncAttributeMaxDynamicSharedMemorySize,
-                            std::max(tree_smem, 48 * 1024)));
+    if (S->use_tree) CU(raise_dynamic_smem(k_factor_tree, tree_smem));
   }
   CU(cudaStreamSynchronize(S->stream));
   SymbolicView& V = S->sview;
@@ -2048,6 +2148,75 @@ int slpb_trial(slpb_solver* S, double alpha, double alpha_z, int which_step,
   if ((rc = point_info(S, S->vals_trial.p, S->ts.p, S->d_results.p))) return rc;
   if ((rc = fetch_results(S, 6))) return rc;
   fill_point_info(S->h_results, info);
+  return SLPB_OK;
+}
+
+int slpb_probe_point(slpb_solver* S, const double* x, const double* sl,
+                     slpb_point_info* info) {
+  if (!S || !S->finalized || !info || !x) return SLPB_ERR_STATE;
+  CU(cudaSetDevice(S->device));
+  const int n = S->n, me = S->me, mi = S->mi;
+  if (mi > 0 && !sl) return SLPB_ERR_ARGUMENT;
+  CU(cudaMemcpyAsync(S->tx.p, x, n * sizeof(double), cudaMemcpyHostToDevice,
+                     S->stream));
+  if (mi > 0) {
+    CU(cudaMemcpyAsync(S->ts.p, sl, mi * sizeof(double),
+                       cudaMemcpyHostToDevice, S->stream));
+    CU(cudaMemcpyAsync(S->tz.p, S->z.p, mi * sizeof(double),
+                       cudaMemcpyDeviceToDevice, S->stream));
+  }
+  if (me > 0) {
+    CU(cudaMemcpyAsync(S->ty.p, S->y.p, me * sizeof(double),
+                       cudaMemcpyDeviceToDevice, S->stream));
+  }
+  S->counters.h2d_bytes += (n + mi) * sizeof(double);
+  int rc;
+  if ((rc = refresh_leaves(S, S->tx.p, S->ty.p, S->tz.p, S->leaf_trial.p))) {
+    return rc;
+  }
+  if ((rc = eval_values(S, S->leaf_trial.p, S->vals_trial.p))) return rc;
+  if ((rc = point_info(S, S->vals_trial.p, S->ts.p, S->d_results.p))) return rc;
+  if ((rc = fetch_results(S, 6))) return rc;
+  fill_point_info(S->h_results, info);
+  return SLPB_OK;
+}
+
+int slpb_multiplier_estimate(slpb_solver* S, double mu, slpb_factor_info* info) {
+  if (!S || !S->analyzed || !info) return SLPB_ERR_STATE;
+  CU(cudaSetDevice(S->device));
+  const int n = S->n, me = S->me, mi = S->mi;
+  S->rhs_ready = false;
+  if (mi > 0) {
+    k_inv_square<<<blocks_for(mi, 256), 256, 0, S->stream>>>(S->s.p, mi,
+                                                            S->sigma.p);
+    ++S->counters.kernel_launches;
+  }
+  const int nnz = static_cast<int>(S->recipe.K.nnz());
+  k_kkt_assemble_identity<<<blocks_for(nnz, 256), 256, 0, S->stream>>>(
+      S->k_diag_flag.p, S->k_ae_idx.p, S->k_prod_ptr.p, S->k_prod_a.p,
+      S->k_prod_b.p, S->k_prod_row.p, S->dvals.p + S->ad.off_ae,
+      S->dvals.p + S->ad.off_ai, S->sigma.p, nnz, S->Kval.p);
+  k_rhs_estimate<<<blocks_for(S->dim, 256), 256, 0, S->stream>>>(
+      ai_view(S), S->dvals.p + S->ad.off_g, S->s.p, mu, n, me, S->rhs.p);
+  S->counters.kernel_launches += 2;
+  CU(cudaGetLastError());
+  // the (2,2) block is zero: a tiny γ keeps multipliers of degree-1 rows (which
+  // the ordering may eliminate first) from meeting an exactly zero pivot
+  const double delta = 0.0, gamma = 1e-10;
+  int rc = factor_impl(S, 1, &delta, &gamma, /*reassemble=*/0, info);
+  if (rc) return rc;
+  S->fwd_valid[0] = S->fwd_valid[1] = false;
+  if ((rc = launch_solve(S, false))) return rc;
+  const int m = std::max(me, mi);
+  if (m > 0) {
+    k_estimate_finish<<<blocks_for(m, 256), 256, 0, S->stream>>>(
+        S->sol.p, S->ai_rowptr.p, S->ai_rcol.p, S->ai_ridx.p,
+        S->dvals.p + S->ad.off_ai, S->s.p, mu, n, me, mi, S->y.p, S->z.p);
+    ++S->counters.kernel_launches;
+  }
+  CU(cudaGetLastError());
+  CU(cudaStreamSynchronize(S->stream));
+  harvest_timers(S);
   return SLPB_OK;
 }
 

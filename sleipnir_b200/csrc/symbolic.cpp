@@ -288,6 +288,76 @@ std::vector<int32_t> order_nested_dissection(const Pattern& lowerK) {
   return nd.order;
 }
 
+/// Moves every multiplier (index ≥ n_primal) that would be eliminated before
+/// ALL of its neighbours to just behind its first neighbour. Without pivoting a
+/// multiplier that comes first meets the pivot −γ (exactly 0 for γ = 0, and
+/// element growth 1/γ otherwise); after one neighbour it meets
+/// −γ − aᵀ(H + δ)⁻¹a. Minimum-degree orderings have this property on
+/// relaxed problems by themselves (the degree-1 slack columns go first);
+/// a dissection order needs the nudge.
+std::vector<int32_t> defer_leading_multipliers(const Pattern& lowerK,
+                                               int32_t n_primal,
+                                               const std::vector<int32_t>& perm) {
+  const int32_t dim = lowerK.cols;
+  std::vector<int32_t> ptr, idx;
+  symmetric_adjacency(lowerK, ptr, idx);
+  // (1) Primal columns whose only neighbour is one multiplier (the p/n slack
+  // columns of a relaxed problem, entry ±1) go first, as a minimum-degree
+  // order would put them: no fill, and their multiplier gets a non-zero
+  // diagonal whatever the values of its other entries are.
+  std::vector<uint8_t> stripped(dim, 0);
+  std::vector<int32_t> out;
+  out.reserve(dim);
+  for (int32_t k = 0; k < dim; ++k) {
+    const int32_t v = perm[k];
+    if (v >= n_primal) continue;
+    int32_t deg = 0, nb = -1;
+    for (int32_t q = ptr[v]; q < ptr[v + 1]; ++q) {
+      if (idx[q] != v) {
+        ++deg;
+        nb = idx[q];
+      }
+    }
+    if (deg == 1 && nb >= n_primal) {
+      stripped[v] = 1;
+      out.push_back(v);
+    }
+  }
+  // (2) Every remaining multiplier that would still come before all of its
+  // neighbours moves to just behind the first of them.
+  std::vector<int32_t> pos(dim);
+  for (int32_t k = 0; k < dim; ++k) pos[perm[k]] = stripped[perm[k]] ? -1 : k;
+  std::vector<int32_t> anchor(dim, -1);
+  std::vector<int32_t> wait_head(dim, -1), wait_next(dim, -1), wait_tail(dim, -1);
+  for (int32_t k = 0; k < dim; ++k) {
+    const int32_t d = perm[k];
+    if (d < n_primal) continue;
+    int32_t first = -1;
+    for (int32_t q = ptr[d]; q < ptr[d + 1]; ++q) {
+      const int32_t u = idx[q];
+      if (u == d) continue;
+      if (first < 0 || pos[u] < pos[first]) first = u;
+    }
+    if (first >= 0 && pos[first] > k) {
+      anchor[d] = first;
+      // keep the original relative order among the waiters of one anchor
+      if (wait_head[first] < 0) {
+        wait_head[first] = wait_tail[first] = d;
+      } else {
+        wait_next[wait_tail[first]] = d;
+        wait_tail[first] = d;
+      }
+    }
+  }
+  for (int32_t k = 0; k < dim; ++k) {
+    const int32_t v = perm[k];
+    if (stripped[v] || anchor[v] >= 0) continue;  // already placed / waits
+    out.push_back(v);
+    for (int32_t d = wait_head[v]; d >= 0; d = wait_next[d]) out.push_back(d);
+  }
+  return out;
+}
+
 bool analyze_kkt(const Pattern& K, int32_t n_primal, int ordering,
                  const int32_t* user_perm, Symbolic& S, std::string& error) {
   S = Symbolic{};
@@ -296,7 +366,7 @@ bool analyze_kkt(const Pattern& K, int32_t n_primal, int ordering,
   std::vector<int32_t> perm;
   switch (ordering) {
     case SLPB_ORDER_NESTED_DISSECTION:
-      perm = order_nested_dissection(K);
+      perm = defer_leading_multipliers(K, n_primal, order_nested_dissection(K));
       break;
     case SLPB_ORDER_NATURAL:
       perm.resize(dim);

@@ -3,6 +3,9 @@
 // __graft_entry__.py) can drive it with ctypes. The host side is C++ because
 // the reference's is; everything numerical below it goes through the C ABI of
 // include/slpb.h into the CUDA library.
+#include <algorithm>
+#include <chrono>
+#include <cmath>
 #include <cstring>
 #include <memory>
 #include <string>
@@ -20,6 +23,11 @@ struct Handle {
   std::vector<double> x;
   int last_status = 0;
   bool flush_l2 = false;
+  double timeout_s = -1.0;  // < 0: Options default (no timeout)
+  // what the recording callback saw, 8 doubles per call: iteration, n, ‖x‖∞,
+  // s.size, y.size, z.size, nnz(H) + nnz(A_e) + nnz(A_i), g.size
+  std::vector<double> callback_log;
+  std::vector<double> callback_last_x;
 };
 
 Handle* H(void* h) { return static_cast<Handle*>(h); }
@@ -73,6 +81,9 @@ int slpbh_solve(void* h, double tolerance, int max_iterations, int feasible_ipm,
   opt.tolerance = tolerance;
   opt.max_iterations = max_iterations;
   opt.feasible_ipm = feasible_ipm != 0;
+  if (hd->timeout_s >= 0.0) {
+    opt.timeout = std::chrono::duration<double>(hd->timeout_s);
+  }
   slp::DeviceOptions dopt;
   dopt.device = device;
   dopt.ordering = ordering;
@@ -104,6 +115,50 @@ double slpbh_flush_seconds(void* h) {
 void slpbh_phase_seconds(void* h, double* out) {
   const auto& p = H(h)->problem->last_phase_seconds();
   for (int i = 0; i < 8; ++i) out[i] = p[i];
+}
+
+/// Options::timeout for the next solves (seconds; negative = none).
+void slpbh_set_timeout(void* h, double seconds) { H(h)->timeout_s = seconds; }
+
+/// Registers an iteration callback (Problem::add_callback, or
+/// add_persistent_callback) that records what IterationInfo hands it and asks
+/// the solver to stop once `stop_at` iterations have been seen (stop_at < 0:
+/// never).
+void slpbh_add_recording_callback(void* h, int stop_at, int persistent) {
+  Handle* hd = H(h);
+  auto cb = [hd, stop_at](const slp::IterationInfo<double>& info) -> bool {
+    double xinf = 0.0;
+    for (size_t i = 0; i < info.x.size(); ++i) {
+      xinf = std::max(xinf, std::abs(info.x[i]));
+    }
+    const double rec[8] = {double(info.iteration), double(info.x.size()), xinf,
+                           double(info.s.size()), double(info.y.size()),
+                           double(info.z.size()),
+                           double(info.H.nonZeros() + info.A_e.nonZeros() +
+                                  info.A_i.nonZeros()),
+                           double(info.g.size())};
+    hd->callback_log.insert(hd->callback_log.end(), rec, rec + 8);
+    hd->callback_last_x.assign(info.x.data(), info.x.data() + info.x.size());
+    return stop_at >= 0 && info.iteration >= stop_at;
+  };
+  if (persistent) {
+    hd->problem->add_persistent_callback(cb);
+  } else {
+    hd->problem->add_callback(cb);
+  }
+}
+void slpbh_clear_callbacks(void* h) { H(h)->problem->clear_callbacks(); }
+int slpbh_callback_log(void* h, double* out, int max_records, double* last_x) {
+  Handle* hd = H(h);
+  const int n = static_cast<int>(hd->callback_log.size() / 8);
+  for (int i = 0; i < std::min(n, max_records) * 8; ++i) {
+    out[i] = hd->callback_log[i];
+  }
+  if (last_x && !hd->callback_last_x.empty()) {
+    std::memcpy(last_x, hd->callback_last_x.data(),
+                hd->callback_last_x.size() * 8);
+  }
+  return n;
 }
 
 int slpbh_trace_rows(void* h) {

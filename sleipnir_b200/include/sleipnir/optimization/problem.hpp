@@ -194,6 +194,7 @@ class Problem {
     // Problem scaling from g(x₀), A_e(x₀), A_i(x₀) (:615-616;
     // problem_scaling.hpp:100-107)
     DeviceProblemInfo info{n, me, mi, 1.0};
+    std::vector<Scalar> d_ce, d_ci;
     {
       slpb_point_info pi{};
       SLP_DEVICE_CALL(dev, slpb_eval_current(dev, 1, &pi));
@@ -222,10 +223,8 @@ class Problem {
         for (auto& v : norms) v = std::min(g_max / v, Scalar(1));
         return norms;
       };
-      std::vector<Scalar> d_ce =
-          row_scales(SLPB_OUT_A_E, SLPB_ARR_A_E_VAL, me);
-      std::vector<Scalar> d_ci =
-          row_scales(SLPB_OUT_A_I, SLPB_ARR_A_I_VAL, mi);
+      d_ce = row_scales(SLPB_OUT_A_E, SLPB_ARR_A_E_VAL, me);
+      d_ci = row_scales(SLPB_OUT_A_I, SLPB_ARR_A_I_VAL, mi);
       SLP_DEVICE_CALL(dev, slpb_set_scaling(dev, info.scaling_f, d_ce.data(),
                                             d_ci.data()));
     }
@@ -243,9 +242,15 @@ class Problem {
     // Interior-point method (:663-668; overload 1, interior_point.hpp:74-86)
     Scalar mu = Scalar(0.1) * info.scaling_f;
     int iterations = 0;
+    const RestorationHook restoration =
+        [&](double mu_outer, int& iters,
+            const RestorationAcceptTest& accept) -> ExitStatus {
+      return feasibility_restoration(dev, info, d_ce, d_ci, options, callbacks,
+                                     mu_outer, iters, accept, dev_options);
+    };
     ExitStatus status = interior_point<Scalar>(
         dev, info, std::span{callbacks}, options, false, mu, iterations,
-        &m_trace);
+        &m_trace, &restoration);
 
     lap(6);
     // Write the solution back into the Variables (:676)
@@ -340,16 +345,28 @@ class Problem {
   };
 
   std::unique_ptr<Graphs> build_graphs() {
-    const int me = static_cast<int>(m_equality_constraints.size());
-    const int mi = static_cast<int>(m_inequality_constraints.size());
+    return build_graphs_from(m_decision_variables,
+                             m_f.value_or(Variable<Scalar>{Scalar(0)}),
+                             m_equality_constraints, m_inequality_constraints);
+  }
+
+  /// The same construction over explicit lists (the feasibility-restoration
+  /// problem reuses the original constraint expressions over an enlarged
+  /// variable vector).
+  static std::unique_ptr<Graphs> build_graphs_from(
+      const std::vector<Variable<Scalar>>& xs, const Variable<Scalar>& f,
+      const std::vector<Variable<Scalar>>& c_e,
+      const std::vector<Variable<Scalar>>& c_i) {
+    const int me = static_cast<int>(c_e.size());
+    const int mi = static_cast<int>(c_i.size());
     auto G = std::make_unique<Graphs>();
-    G->x_ad = VariableMatrix<Scalar>{std::span<const Variable<Scalar>>{
-        m_decision_variables.data(), m_decision_variables.size()}};
-    G->f = m_f.value_or(Variable<Scalar>{Scalar(0)});
-    G->c_e_ad = VariableMatrix<Scalar>{std::span<const Variable<Scalar>>{
-        m_equality_constraints.data(), m_equality_constraints.size()}};
-    G->c_i_ad = VariableMatrix<Scalar>{std::span<const Variable<Scalar>>{
-        m_inequality_constraints.data(), m_inequality_constraints.size()}};
+    G->x_ad = VariableMatrix<Scalar>{
+        std::span<const Variable<Scalar>>{xs.data(), xs.size()}};
+    G->f = f;
+    G->c_e_ad = VariableMatrix<Scalar>{
+        std::span<const Variable<Scalar>>{c_e.data(), c_e.size()}};
+    G->c_i_ad = VariableMatrix<Scalar>{
+        std::span<const Variable<Scalar>>{c_i.data(), c_i.size()}};
     G->y_ad = VariableMatrix<Scalar>(me);
     G->z_ad = VariableMatrix<Scalar>(mi);
     G->g = std::make_unique<Gradient<Scalar>>(G->f, G->x_ad);
@@ -383,6 +400,168 @@ class Problem {
   }
 
  private:
+  /// Feasibility restoration for the interior-point method
+  /// (solver/util/feasibility_restoration.hpp:346-628). The reference wraps the
+  /// matrix callbacks into an enlarged problem over x̃ = [x, p_e, n_e, p_i, n_i]:
+  ///
+  ///   min ρΣ(p + n) + ζ/2 (x − x_r)ᵀD_r(x − x_r)
+  ///   s.t. c_e(x) − p_e + n_e = 0,  c_i(x) − p_i + n_i ≥ 0,  p, n ≥ 0
+  ///
+  /// and re-enters interior_point on it. Here the enlarged problem is written
+  /// with the DSL over the ORIGINAL constraint expressions, compiled for a
+  /// second device handle (Hessian of the constraints ignored, as the
+  /// reference's H callback effectively does, :485-495) and solved by the same
+  /// device loop with in_feasibility_restoration = true.
+  ExitStatus feasibility_restoration(
+      slpb_solver* dev, const DeviceProblemInfo& info,
+      const std::vector<Scalar>& d_ce, const std::vector<Scalar>& d_ci,
+      const Options& options,
+      std::vector<std::function<bool(const IterationInfo<Scalar>&)>>& callbacks,
+      Scalar mu, int& iterations, const RestorationAcceptTest& accept,
+      const DeviceOptions& dev_options) {
+    const int n = info.num_decision_variables;
+    const int me = info.num_equality_constraints;
+    const int mi = info.num_inequality_constraints;
+    constexpr Scalar rho(1e3);
+
+    std::vector<Scalar> x(n), s(mi), y(me), z(mi), c_e(me), c_i(mi);
+    SLP_DEVICE_CALL(dev, slpb_get_iterate(dev, x.data(), s.data(), y.data(),
+                                          z.data()));
+    if (me > 0) SLP_DEVICE_CALL(dev, slpb_download(dev, SLPB_ARR_C_E, c_e.data()));
+    if (mi > 0) SLP_DEVICE_CALL(dev, slpb_download(dev, SLPB_ARR_C_I, c_i.data()));
+
+    Scalar fr_mu = mu;
+    for (Scalar v : c_e) fr_mu = std::max(fr_mu, std::abs(v));
+    std::vector<Scalar> cis(mi);
+    for (int i = 0; i < mi; ++i) {
+      cis[i] = c_i[i] - s[i];
+      fr_mu = std::max(fr_mu, std::abs(cis[i]));
+    }
+    const Scalar zeta = std::sqrt(fr_mu);
+
+    // closed-form initial p, n (:49-100)
+    auto compute_p_n = [&](const std::vector<Scalar>& c, std::vector<Scalar>& p,
+                           std::vector<Scalar>& nn) {
+      p.resize(c.size());
+      nn.resize(c.size());
+      for (size_t r = 0; r < c.size(); ++r) {
+        const Scalar a = rho;
+        const Scalar b = rho * c[r] - fr_mu;
+        const Scalar cc = -fr_mu * c[r] / Scalar(2);
+        nn[r] = (-b + std::sqrt(b * b - Scalar(4) * a * cc)) / (Scalar(2) * a);
+        p[r] = c[r] + nn[r];
+      }
+    };
+    std::vector<Scalar> p_e_0, n_e_0, p_i_0, n_i_0;
+    compute_p_n(c_e, p_e_0, n_e_0);
+    compute_p_n(cis, p_i_0, n_i_0);
+
+    // ---- the enlarged problem, over the original constraint expressions ----
+    const int extra = 2 * me + 2 * mi;
+    std::vector<Variable<Scalar>> xs = m_decision_variables;
+    std::vector<Variable<Scalar>> p_e(me), n_e(me), p_i(mi), n_i(mi);
+    for (auto* blk : {&p_e, &n_e, &p_i, &n_i}) {
+      xs.insert(xs.end(), blk->begin(), blk->end());
+    }
+    // cost = ρΣ(p + n) + ζ/2 (x − x_r)ᵀD_r(x − x_r), written as ONE flat sum of
+    // small terms (the factors ρ and ζ/2 inside each term) so that the device
+    // compiler can split the row into independent clusters instead of one
+    // 10⁵-node chain.
+    Variable<Scalar> cost{Scalar(0)};
+    for (int i = n; i < n + extra; ++i) cost = cost + rho * xs[i];
+    for (int i = 0; i < n; ++i) {
+      const Scalar D_r = std::min(Scalar(1) / (x[i] * x[i]), Scalar(1));
+      Variable<Scalar> d = xs[i] - x[i];
+      cost = cost + (zeta / Scalar(2)) * (d * (D_r * d));
+    }
+
+    // rows are scaled as a whole on the device (d_c ⊙ row); the reference adds
+    // −p + n to the already scaled d_c ⊙ c(x), so p and n enter divided by d_c
+    auto relax = [](const Variable<Scalar>& c, const Variable<Scalar>& p,
+                    const Variable<Scalar>& nn, Scalar d) {
+      if (d == Scalar(1)) return c - p + nn;
+      return c - p / d + nn / d;
+    };
+    std::vector<Variable<Scalar>> ce_fr, ci_fr;
+    ce_fr.reserve(me);
+    ci_fr.reserve(mi + extra);
+    for (int j = 0; j < me; ++j) {
+      ce_fr.push_back(relax(m_equality_constraints[j], p_e[j], n_e[j], d_ce[j]));
+    }
+    for (int i = 0; i < mi; ++i) {
+      ci_fr.push_back(
+          relax(m_inequality_constraints[i], p_i[i], n_i[i], d_ci[i]));
+    }
+    for (int i = n; i < n + extra; ++i) ci_fr.push_back(xs[i]);
+
+    auto graphs = build_graphs_from(xs, cost, ce_fr, ci_fr);
+    detail::FlatProblem fp = graphs->flatten();
+
+    DeviceHandle inner{dev_options.device};
+    SLP_DEVICE_CALL(inner.s, slpb_set_ignore_constraint_hessian(inner.s, 1));
+    upload(inner.s, fp);
+
+    // initial iterate (:408-424): perfect complementarity with the slacks
+    std::vector<Scalar> fr_x(x), fr_s(s), fr_y(me, Scalar(0)), fr_z;
+    fr_s.resize(mi + extra, Scalar(1));
+    fr_z.reserve(mi + extra);
+    for (const auto* v : {&p_e_0, &n_e_0, &p_i_0, &n_i_0}) {
+      fr_x.insert(fr_x.end(), v->begin(), v->end());
+    }
+    for (const auto* v : {&s, &p_e_0, &n_e_0, &p_i_0, &n_i_0}) {
+      for (Scalar e : *v) fr_z.push_back(fr_mu * (Scalar(1) / e));
+    }
+    SLP_DEVICE_CALL(inner.s, slpb_set_iterate(inner.s, fr_x.data(), fr_s.data(),
+                                              fr_y.data(), fr_z.data()));
+    std::vector<Scalar> fr_d_ci(d_ci);
+    fr_d_ci.resize(mi + extra, Scalar(1));
+    SLP_DEVICE_CALL(inner.s, slpb_set_scaling(inner.s, 1.0, d_ce.data(),
+                                              fr_d_ci.data()));
+    slpb_symbolic_stats sym{};
+    SLP_DEVICE_CALL(inner.s, slpb_analyze(inner.s, SLPB_ORDER_NESTED_DISSECTION,
+                                          nullptr, &sym));
+
+    // user callbacks + the acceptance test (interior_point.hpp:733-756)
+    std::vector<std::function<bool(const IterationInfo<Scalar>&)>> fr_callbacks{
+        callbacks.begin(), callbacks.end()};
+    fr_callbacks.emplace_back([&](const IterationInfo<Scalar>& it) {
+      std::vector<double> trial_x(it.x.data(), it.x.data() + n);
+      std::vector<double> trial_s(it.s.data(), it.s.data() + mi);
+      return accept(trial_x, trial_s);
+    });
+
+    const DeviceProblemInfo fr_info{n + extra, me, mi + extra, 1.0};
+    Scalar fr_mu_io = fr_mu;
+    const ExitStatus status = interior_point<Scalar>(
+        inner.s, fr_info, std::span{fr_callbacks}, options, true, fr_mu_io,
+        iterations, &m_trace);
+
+    SLP_DEVICE_CALL(inner.s, slpb_get_iterate(inner.s, fr_x.data(), fr_s.data(),
+                                              nullptr, nullptr));
+    std::copy(fr_x.begin(), fr_x.begin() + n, x.begin());
+    std::copy(fr_s.begin(), fr_s.begin() + mi, s.begin());
+    SLP_DEVICE_CALL(dev,
+                    slpb_set_iterate(dev, x.data(), s.data(), y.data(), z.data()));
+    {
+      slpb_counters c{};
+      slpb_get_counters(inner.s, &c);
+      m_restoration_launches += c.kernel_launches;
+    }
+
+    if (status == ExitStatus::CALLBACK_REQUESTED_STOP) {
+      // y, z by least squares at the restored point (:612-622)
+      slpb_point_info pi{};
+      SLP_DEVICE_CALL(dev, slpb_eval_current(dev, 1, &pi));
+      slpb_factor_info fi{};
+      SLP_DEVICE_CALL(dev, slpb_multiplier_estimate(dev, mu, &fi));
+      if (fi.zero_pivot) return ExitStatus::FEASIBILITY_RESTORATION_FAILED;
+      return ExitStatus::SUCCESS;
+    } else if (status == ExitStatus::SUCCESS) {
+      return ExitStatus::LOCALLY_INFEASIBLE;  // :623-624
+    }
+    return ExitStatus::FEASIBILITY_RESTORATION_FAILED;
+  }
+
   static ExpressionType max_type(const std::vector<Variable<Scalar>>& v) {
     ExpressionType t = ExpressionType::NONE;
     for (const auto& e : v) t = std::max(t, e.type());
@@ -447,6 +626,7 @@ class Problem {
   slpb_counters m_counters{};
   slpb_timers m_timers{};
   std::array<double, 8> m_phase{};
+  int64_t m_restoration_launches = 0;
   std::vector<Scalar> m_last_s, m_last_y, m_last_z;
 };
 

@@ -12,6 +12,7 @@
 
 #include <algorithm>
 #include <chrono>
+#include <cstdlib>
 #include <cmath>
 #include <functional>
 #include <limits>
@@ -308,8 +309,14 @@ struct DeviceProblemInfo {
 /// Hook used by Problem::solve to run feasibility restoration on a second
 /// device problem; returns the restoration's ExitStatus
 /// (feasibility_restoration.hpp:346-628).
+/// accept_test(trial_x, trial_s): the stopping rule of the restoration phase
+/// (interior_point.hpp:738-756) evaluated on the ORIGINAL problem — the trial
+/// reduces the violation to < 0.9× its value at entry and the outer filter
+/// accepts it.
+using RestorationAcceptTest = std::function<bool(
+    const std::vector<double>& trial_x, const std::vector<double>& trial_s)>;
 using RestorationHook = std::function<ExitStatus(
-    double mu, int& iterations, const std::function<bool()>& accept_test)>;
+    double mu, int& iterations, const RestorationAcceptTest& accept_test)>;
 
 /// Finds the optimal solution to a nonlinear program with the interior-point
 /// method, with the iterate resident on the device (reference overload 2,
@@ -358,9 +365,14 @@ ExitStatus interior_point(
 
   // The reference picks Eigen's dense LDLT when the lower triangle is ≥ 25 %
   // full (:340-348); the device path always factors sparse.
+  // γ_min = 0 inside feasibility restoration (:352). (The device ordering keeps
+  // every multiplier behind one of its neighbours — symbolic.cpp,
+  // defer_leading_multipliers — so γ = 0 does not meet structurally zero
+  // pivots on the relaxed problem.)
   DeviceRegularizedLDLT solver{dev, n, me,
                                in_feasibility_restoration ? 0.0 : 1e-10};
   solver.set_previous_regularization(initial_delta, 0.0);
+  if (std::getenv("SLPB_NO_SPECULATION")) solver.set_speculation(false);
 
   constexpr Scalar alpha_reduction_factor(0.5);
   constexpr Scalar alpha_min(1e-7);
@@ -455,7 +467,9 @@ ExitStatus interior_point(
     // lhs assembly + factorisation with inertia correction (:426-465)
     // The right-hand side does not depend on δ/γ: build it first so that the
     // factorisation carries its forward substitution (slpb_prepare_rhs).
-    SLP_DEVICE_CALL(dev, slpb_prepare_rhs(dev, mu));
+    if (!std::getenv("SLPB_NO_FUSED_FORWARD")) {
+      SLP_DEVICE_CALL(dev, slpb_prepare_rhs(dev, mu));
+    }
     if (!solver.compute()) return ExitStatus::FACTORIZATION_FAILED;
 
     // rhs, solve, step recovery, fraction-to-the-boundary (:444-497)
@@ -576,8 +590,31 @@ ExitStatus interior_point(
       // arrays; bring them back to the current iterate for the hook.
       SLP_DEVICE_CALL(dev, slpb_eval_current(dev, 2, &cur));
       const FilterEntry<Scalar> initial_entry = current_entry;
-      (void)initial_entry;
-      ExitStatus status = (*restoration)(mu, iterations, [] { return false; });
+      // outer iterate and gradient at entry, for D_ϕ of the acceptance test
+      std::vector<double> x0(n), s0(mi), g0(n);
+      SLP_DEVICE_CALL(dev, slpb_get_iterate(dev, x0.data(), s0.data(), nullptr,
+                                            nullptr));
+      SLP_DEVICE_CALL(dev, slpb_download(dev, SLPB_ARR_G, g0.data()));
+      const RestorationAcceptTest accept_test =
+          [&](const std::vector<double>& trial_x,
+              const std::vector<double>& trial_s) -> bool {
+        slpb_point_info probe{};
+        SLP_DEVICE_CALL(dev, slpb_probe_point(dev, trial_x.data(),
+                                              trial_s.data(), &probe));
+        const FilterEntry<Scalar> trial_entry{
+            probe.f - mu * probe.log_s_sum, probe.ce_l1 + probe.cis_l1};
+        Scalar gdx(0), sds(0);
+        for (int i = 0; i < n; ++i) gdx += g0[i] * (trial_x[i] - x0[i]);
+        for (int i = 0; i < mi; ++i) {
+          sds += (Scalar(1) / s0[i]) * (trial_s[i] - s0[i]);
+        }
+        const Scalar D_phi_restoration = gdx - mu * sds;
+        return trial_entry.constraint_violation <
+                   Scalar(0.9) * initial_entry.constraint_violation &&
+               filter.try_add(initial_entry, trial_entry, D_phi_restoration,
+                              alpha);
+      };
+      ExitStatus status = (*restoration)(mu, iterations, accept_test);
       if (status != ExitStatus::SUCCESS) return status;
       SLP_DEVICE_CALL(dev, slpb_eval_current(dev, 0, &cur));
     } else {

@@ -152,11 +152,12 @@ def test_newton_step_vs_oracle(name, N):
     P.close_device(); P.close(); O.close()
 
 
-def test_factor_pair_matches_two_single_factorisations():
+@pytest.mark.parametrize("name,N", [("cart_pole", 80), ("gfold", 20)])
+def test_factor_pair_matches_two_single_factorisations(name, N):
     """slpb_factor_pair (two regularisations in one launch) gives, variant by
     variant, the bits of two separate slpb_factor calls, and slpb_select_factor
-    makes the solve use the chosen one."""
-    name, N = "cart_pole", 80
+    makes the solve use the chosen one. cart-pole runs the one-warp-per-front
+    tree kernels, g-fold (fronts of order > 32) the block-per-front ones."""
     P, O = sb.Problem(name, N), OracleProblem(name, N)
     O.eval_setup()
     d_f, d_ce, d_ci = O.scaling()
@@ -296,6 +297,47 @@ def test_reference_known_answers_on_gpu(name, status, expect, tol):
     if expect is not None:
         np.testing.assert_allclose(P.solution()[0], expect, atol=tol)
     P.close()
+
+
+def test_iteration_callbacks_and_off_nominal_exits():
+    """Problem::add_callback / clear_callbacks / add_persistent_callback with
+    host mirrors of the device iterate (interior_point.hpp:414-418), and the
+    off-nominal exits of the loop (:852-862), on the interior-point branch
+    (the reference's exit_status_test.cpp exercises them on its Newton/SQP
+    siblings)."""
+    N = 30
+    P = sb.Problem("cart_pole", N)
+    P.add_callback(stop_at=-1)                      # never asks to stop
+    assert sb.EXIT_STATUS[P.solve(max_iterations=4, keep_iterates=True)] == \
+        "MAX_ITERATIONS_EXCEEDED"
+    log, last_x = P.callback_log()
+    tr = P.trace()
+    assert len(tr) == 4 and [int(r[0]) for r in log] == [0, 1, 2, 3]
+    assert all(int(r[1]) == P.n and int(r[3]) == P.mi and int(r[4]) == P.me
+               and int(r[5]) == P.mi and int(r[7]) == P.n for r in log)
+    D = P.open_device()
+    nnz = sum(len(D.pattern(w)[3]) for w in (sb.OUT_H_C, sb.OUT_A_E, sb.OUT_A_I))
+    P.close_device()
+    assert all(int(r[6]) == nnz for r in log)
+    # the callback of iteration 3 saw the iterate accepted at the end of iteration 2
+    np.testing.assert_array_equal(last_x, tr[2].x)
+    assert log[3][2] == np.abs(tr[2].x).max()
+
+    P.add_callback(stop_at=2)                       # second callback stops the solve
+    assert sb.EXIT_STATUS[P.solve(max_iterations=50)] == "CALLBACK_REQUESTED_STOP"
+    assert len(P.trace()) == 2
+    P.clear_callbacks()
+    assert sb.EXIT_STATUS[P.solve(max_iterations=3)] == "MAX_ITERATIONS_EXCEEDED"
+    P.add_callback(stop_at=1, persistent=True)      # survives clear_callbacks()
+    P.clear_callbacks()
+    assert sb.EXIT_STATUS[P.solve(max_iterations=50)] == "CALLBACK_REQUESTED_STOP"
+    P.close()
+
+    Q = sb.Problem("cart_pole", N)
+    Q.set_timeout(0.0)
+    assert sb.EXIT_STATUS[Q.solve()] == "TIMEOUT"
+    assert len(Q.trace()) == 1
+    Q.close()
 
 
 def test_flywheel_trajectory_matches_oracle():
