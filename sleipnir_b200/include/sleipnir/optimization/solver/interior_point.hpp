@@ -421,7 +421,8 @@ ExitStatus interior_point(
                            t->flush_seconds;
       }
     }
-  } loop_timer{trace, loop_start_time};
+    // the restoration sub-solve runs inside the outer loop's time
+  } loop_timer{in_feasibility_restoration ? nullptr : trace, loop_start_time};
 
   while (E_0 > Scalar(options.tolerance)) {
     if (trace && trace->flush_l2) {

@@ -299,6 +299,71 @@ def test_reference_known_answers_on_gpu(name, status, expect, tol):
     P.close()
 
 
+def test_multiplier_estimate_and_probe_point():
+    """slpb_multiplier_estimate against a dense least-squares solve of
+    Âᵀ[y; z] ≈ [∇f; −μe], Â = [A_e 0; A_i −S]
+    (lagrange_multiplier_estimate.hpp:55-131), and slpb_probe_point against the
+    oracle's f, c_e, c_i."""
+    name, N = "cart_pole", 12
+    P, O = sb.Problem(name, N), OracleProblem(name, N)
+    O.eval_setup()
+    d_f, d_ce, d_ci = O.scaling()
+    D = P.open_device()
+    D.set_scaling(d_f, d_ce, d_ci)
+    x, s, y, z = _state(P, O, 17)
+    D.set_iterate(x, s, y, z)
+    D.eval_current(1)
+    D.analyze()
+    n, me, mi = P.n, P.me, P.mi
+    mu = 0.03
+    fi = D.multiplier_estimate(mu)
+    assert fi.zero_pivot == 0
+    _, _, y_est, z_est = D.get_iterate()
+    Ae, Ai, g = O.A_e(x), O.A_i(x), O.g(x)
+    Aes = sp.csc_matrix((Ae.val, Ae.rowidx, Ae.colptr), shape=(me, n)).toarray()
+    Ais = sp.csc_matrix((Ai.val, Ai.rowidx, Ai.colptr), shape=(mi, n)).toarray()
+    A_hat = np.block([[Aes, np.zeros((me, mi))], [Ais, -np.diag(s)]])
+    b = np.concatenate([g, -mu * np.ones(mi)])
+    lam = np.linalg.lstsq(A_hat.T, b, rcond=None)[0]
+    y_ref = lam[:me]
+    z_ref = np.clip(lam[me:], 1e-10 * mu / s, 1e10 * mu / s)
+    # the device solve carries γ = 1e-10 on the multiplier block (see slpb.cu)
+    assert rel(y_est, y_ref) < 1e-4 and rel(z_est, z_ref) < 1e-4
+    # probe: values of the original problem at a host-supplied point
+    rng = np.random.default_rng(3)
+    xp = x + 0.01 * rng.standard_normal(n)
+    sp_ = s * (1 + 0.1 * rng.random(mi))
+    info = D.probe_point(xp, sp_)
+    assert info.f == pytest.approx(O.f(xp), rel=1e-13)
+    assert info.ce_l1 == pytest.approx(np.abs(O.c_e(xp)).sum(), rel=1e-12)
+    assert info.cis_l1 == pytest.approx(np.abs(O.c_i(xp) - sp_).sum(), rel=1e-12)
+    assert info.log_s_sum == pytest.approx(np.log(sp_).sum(), rel=1e-12)
+    x2, s2, _, _ = D.get_iterate()
+    np.testing.assert_array_equal(x2, x)   # the iterate itself is untouched
+    np.testing.assert_array_equal(s2, s)
+    P.close_device(); P.close(); O.close()
+
+
+def test_feasibility_restoration_reaches_the_reference_solution():
+    """cart-pole N = 50 only converges THROUGH feasibility restoration
+    (feasibility_restoration.hpp:346-628): the reference-core oracle spends 132
+    of its 378 iterations there (golden vector). The device path must enter
+    restoration, come back, and end at the same optimum; N = 20 must end
+    LOCALLY_INFEASIBLE like the oracle."""
+    g = np.load(os.path.join(GOLDEN, "solve_cart_pole_50.npz"))
+    assert EXIT_STATUS[int(g["status"])] == "SUCCESS"
+    P = sb.Problem("cart_pole", 50)
+    assert sb.EXIT_STATUS[P.solve()] == "SUCCESS"
+    tr = P.trace()
+    assert sum(r.type == 1 for r in tr) > 0
+    np.testing.assert_allclose(P.solution()[0], g["x"], atol=1e-5)
+    P.close()
+    Q = sb.Problem("cart_pole", 20)
+    assert sb.EXIT_STATUS[Q.solve()] == "LOCALLY_INFEASIBLE"
+    assert sum(r.type == 1 for r in Q.trace()) > 0
+    Q.close()
+
+
 def test_iteration_callbacks_and_off_nominal_exits():
     """Problem::add_callback / clear_callbacks / add_persistent_callback with
     host mirrors of the device iterate (interior_point.hpp:414-418), and the
