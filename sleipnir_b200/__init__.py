@@ -501,10 +501,10 @@ class Problem:
 
     def phase_seconds(self):
         """Host wall time of the phases of the last solve() call."""
-        out = np.zeros(8)
+        out = np.zeros(9)
         self.H.slpbh_phase_seconds(self.h, _d(out))
         keys = ("build_graphs", "flatten", "device_create", "upload_compile",
-                "scaling", "analyze", "newton_loop", "write_back")
+                "scaling", "analyze", "newton_loop", "write_back", "teardown")
         return dict(zip(keys, (float(v) for v in out)))
 
     def symbolic_stats(self):

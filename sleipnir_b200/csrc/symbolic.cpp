@@ -17,6 +17,7 @@
 // reference (min |D_ii| ≥ 1e-4, exact-zero pivots) are ordering-dependent.
 #include <algorithm>
 #include <cmath>
+#include <cstdlib>
 #include <numeric>
 #include <queue>
 
@@ -269,6 +270,42 @@ struct NestedDissection {
                                bfs_out.begin() + lvl[best_lv + 1]);
         std::vector<int32_t> Bv(bfs_out.begin() + lvl[best_lv + 1],
                                 bfs_out.end());
+        // Trim the separator: a level-set vertex always touches the previous
+        // level (side A); one that does not touch side B separates nothing and
+        // joins A. On a time-banded KKT graph this turns a separator of a whole
+        // stage (states, input and multipliers) into the 4-5 vertices that
+        // actually couple the two halves: shorter pivot chains on the critical
+        // path of the factorisation, smaller fronts, less fill.
+        {
+          // mark[v]: 1 = A, 2 = S, 3 = B (within this component)
+          for (int32_t v : A) dist[v] = 1;
+          for (int32_t v : S) dist[v] = 2;
+          for (int32_t v : Bv) dist[v] = 3;
+          std::vector<int32_t> keep;
+          for (int32_t v : S) {
+            bool touches_b = false;
+            for (int32_t k = ptr[v]; k < ptr[v + 1] && !touches_b; ++k) {
+              const int32_t w = idx[k];
+              touches_b = part[w] == cid && dist[w] == 3;
+            }
+            if (touches_b) {
+              keep.push_back(v);
+            } else {
+              dist[v] = 1;
+              A.push_back(v);
+            }
+          }
+          for (int32_t v : bfs_out) dist[v] = -1;
+          if (!keep.empty()) S.swap(keep);
+          // (an empty trimmed separator means A and B were not connected
+          // through S at all; keep the untrimmed one in that odd case)
+          else {
+            for (int32_t v : S) {
+              auto it = std::find(A.begin(), A.end(), v);
+              if (it != A.end()) A.erase(it);
+            }
+          }
+        }
         // emitted order: A…, B…, S  ⇒ push S first (stack is LIFO)
         stack.push_back({std::move(S), true});
         stack.push_back({std::move(Bv), false});
@@ -283,7 +320,9 @@ struct NestedDissection {
 std::vector<int32_t> order_nested_dissection(const Pattern& lowerK) {
   std::vector<int32_t> ptr, idx;
   symmetric_adjacency(lowerK, ptr, idx);
-  NestedDissection nd{ptr, idx, /*leaf_size=*/20};
+  int32_t leaf = 20;
+  if (const char* e = std::getenv("SLPB_ND_LEAF")) leaf = std::max(2, std::atoi(e));
+  NestedDissection nd{ptr, idx, leaf};
   nd.run();
   return nd.order;
 }

@@ -110,11 +110,12 @@ double slpbh_flush_seconds(void* h) {
   return H(h)->problem->last_trace().flush_seconds;
 }
 
-/// out[8]: build_graphs, flatten, device_create, upload+compile, scaling,
-/// analyze, newton loop, write-back — host seconds of the last solve().
+/// out[9]: build_graphs, flatten, device_create, upload+compile, scaling,
+/// analyze, newton loop, write-back, teardown — host seconds of the last
+/// solve().
 void slpbh_phase_seconds(void* h, double* out) {
   const auto& p = H(h)->problem->last_phase_seconds();
-  for (int i = 0; i < 8; ++i) out[i] = p[i];
+  for (int i = 0; i < 9; ++i) out[i] = p[i];
 }
 
 /// Options::timeout for the next solves (seconds; negative = none).

@@ -134,6 +134,22 @@ class Problem {
   }
 
   ExitStatus solve(const Options& options, const DeviceOptions& dev_options) {
+    const auto t0 = std::chrono::steady_clock::now();
+    const ExitStatus status = solve_impl(options, dev_options);
+    // everything solve_impl owned (graphs, flattened tape, device handle) has
+    // been released by now: the remainder is teardown
+    double accounted = 0.0;
+    for (int i = 0; i < 8; ++i) accounted += m_phase[i];
+    m_phase[8] = std::chrono::duration<double>(
+                     std::chrono::steady_clock::now() - t0)
+                     .count() -
+                 accounted;
+    return status;
+  }
+
+ private:
+  ExitStatus solve_impl(const Options& options,
+                        const DeviceOptions& dev_options) {
     m_trace = SolveTrace{};
     m_trace.keep_iterates = dev_options.keep_iterates;
     m_trace.flush_l2 = dev_options.flush_l2;
@@ -266,6 +282,8 @@ class Problem {
     return status;
   }
 
+ public:
+
   /// Adds a callback called at the beginning of each solver iteration; a
   /// void-returning callback never stops the solve.
   template <typename F>
@@ -304,8 +322,9 @@ class Problem {
   const slpb_counters& last_counters() const { return m_counters; }
   const slpb_timers& last_timers() const { return m_timers; }
   /// Host seconds of the phases of the last solve(): build_graphs, flatten,
-  /// device_create, upload+compile, scaling, analyze, newton loop, write-back.
-  const std::array<double, 8>& last_phase_seconds() const { return m_phase; }
+  /// device_create, upload+compile, scaling, analyze, newton loop, write-back,
+  /// teardown (release of graphs, tape and device handle).
+  const std::array<double, 9>& last_phase_seconds() const { return m_phase; }
   const std::vector<Scalar>& last_s() const { return m_last_s; }
   const std::vector<Scalar>& last_y() const { return m_last_y; }
   const std::vector<Scalar>& last_z() const { return m_last_z; }
@@ -625,7 +644,7 @@ class Problem {
   slpb_symbolic_stats m_symbolic{};
   slpb_counters m_counters{};
   slpb_timers m_timers{};
-  std::array<double, 8> m_phase{};
+  std::array<double, 9> m_phase{};
   int64_t m_restoration_launches = 0;
   std::vector<Scalar> m_last_s, m_last_y, m_last_z;
 };
