@@ -133,6 +133,11 @@ def main():
     ap.add_argument("--impl", default="b200", choices=["b200", "reference"])
     ap.add_argument("--horizon", type=int, default=5000)
     ap.add_argument("--no-cpu-baseline", action="store_true")
+    ap.add_argument("--shard", action="store_true",
+                    help="N > 1: ONE solve sharded over the GPUs (derivative "
+                         "sweep split over the ranks, one NCCL all-gather per "
+                         "Newton iteration; strong scaling) instead of N "
+                         "independent replicas")
     args = ap.parse_args()
     args.warmup = max(args.warmup, 3)
 
@@ -208,9 +213,18 @@ def main():
     P.solve(max_iterations=args.warmup, device=local_rank)
     P.close()
 
+    shard = args.shard and world > 1
+    comm_id = None
+    if shard:
+        box = [sb.comm_unique_id() if rank == 0 else None]
+        dist.broadcast_object_list(box, src=0)
+        comm_id = box[0]
+
     def one_solve(flush, max_iterations):
         Q = sb.Problem("cart_pole", N)
         Q.set_flush_l2(flush)
+        if shard:
+            Q.set_comm(rank, world, comm_id)
         if world > 1:
             dist.barrier()
         torch.cuda.synchronize()
@@ -245,7 +259,8 @@ def main():
         dt2 = max_over_ranks(dt2)
         total_s = max_over_ranks(total_s)
         cnt2, phases = P2.counters(), P2.phase_seconds()
-    rate = world * k / dt
+    replicas = 1 if shard else world   # independent solves running side by side
+    rate = replicas * k / dt
 
     # roofline of the dominant kernel, k_factor_tree (supernodal LDLT; also the
     # kernel BASELINE.json's metric names). Algorithmic bytes per numeric
@@ -272,18 +287,23 @@ def main():
     line = {
         "metric": METRIC, "value": rate, "unit": UNIT, "n_gpus": world,
         "steps": k, "warmup": args.warmup, "ms_per_step": 1e3 * dt / k,
-        "higher_is_better": True, "scaling": "weak", "vs_baseline": None,
+        "higher_is_better": True, "scaling": "strong" if shard else "weak",
+        "vs_baseline": None,
         "dtype": "f64", "data": "synthetic",
         "config": {
             "workload": workload,
             "parallelism": ("single GPU" if world == 1 else
+                            f"ONE solve on {world} GPUs: derivative sweep sharded "
+                            "over the ranks, one NCCL all-gather per Newton "
+                            "iteration, factorisation and solve replicated"
+                            if shard else
                             f"{world} independent replicas of the solve, one per "
                             "GPU, no data-path collective (DESIGN.md, Multi-GPU)"),
             "l2_policy": ("L2 flushed before every timed iteration (256 MiB "
                           "device memset > 126 MB L2, excluded from the iteration "
                           "timestamps); value_warm_l2 is the same solve without "
                           "flushes"),
-            "value_warm_l2": world * k2 / dt2,
+            "value_warm_l2": replicas * k2 / dt2,
             "ordering": "nested dissection (level-set bisection)",
             "symbolic": sym,
             "per_step": {
@@ -315,7 +335,7 @@ def main():
                 "achieved_gbs": ad_bytes / (phase_ms["eval_full"] * 1e-3) / 1e9 if phase_ms["eval_full"] > 0 else None},
         },
         "e2e": {
-            "value": world * len(tr2) / total_s, "unit": UNIT,
+            "value": replicas * len(tr2) / total_s, "unit": UNIT,
             "what": "slp::Problem::solve() with default Options, run to its exit "
                     "status from HOST buffers: autodiff setup, tape upload, "
                     "compilation, symbolic analysis, every Newton iteration "

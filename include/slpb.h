@@ -106,6 +106,21 @@ void slpb_destroy(slpb_solver* s);
 /* Human-readable text of the last error on this handle (never NULL). */
 const char* slpb_last_error(const slpb_solver* s);
 
+/* ---- multi-GPU (optional) -------------------------------------------------
+ * One process per GPU. The re-linearisation sweep (slpb_eval_current with
+ * derivatives: g, A_e, A_i, H) is sharded over the time steps: every rank
+ * evaluates its share of the tasks and ONE ncclAllGather per Newton iteration
+ * exchanges the rows the ranks produced; assembly, factorisation and solve then
+ * run redundantly (and bit-identically) on every rank, so all ranks take the
+ * same decisions without further communication. Every rank must make the same
+ * sequence of calls. NCCL is loaded at run time (libnccl.so.2).
+ *   slpb_comm_unique_id: rank 0 creates the 128-byte ncclUniqueId, the caller
+ *                        distributes it (MPI, torch.distributed, a file …);
+ *   slpb_comm_init:      between slpb_create and slpb_finalize. */
+int slpb_comm_unique_id(void* id_out_128_bytes);
+int slpb_comm_init(slpb_solver* s, int rank, int world,
+                   const void* id_128_bytes);
+
 /* ---- problem upload (once per solve) ------------------------------------ */
 
 /* Flattened, de-duplicated node list in child-before-parent order: the union

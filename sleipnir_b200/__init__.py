@@ -102,7 +102,8 @@ class Counters(C.Structure):
 # Every symbol include/slpb.h declares (tests check that the library exports
 # all of them).
 ABI_SYMBOLS = [
-    "slpb_create", "slpb_destroy", "slpb_last_error", "slpb_upload_tape",
+    "slpb_create", "slpb_destroy", "slpb_last_error", "slpb_comm_unique_id",
+    "slpb_comm_init", "slpb_upload_tape",
     "slpb_upload_rows", "slpb_finalize", "slpb_set_scaling",
     "slpb_set_ignore_constraint_hessian", "slpb_analyze",
     "slpb_get_permutation", "slpb_set_iterate", "slpb_get_iterate",
@@ -165,6 +166,15 @@ def device_lib() -> C.CDLL:
     return _dev
 
 
+def comm_unique_id() -> bytes:
+    """A fresh ncclUniqueId (rank 0 creates it and sends it to the others)."""
+    buf = C.create_string_buffer(128)
+    rc = device_lib().slpb_comm_unique_id(buf)
+    if rc != 0:
+        raise DeviceError(f"slpb_comm_unique_id failed (status {rc})")
+    return buf.raw
+
+
 def host_lib() -> C.CDLL:
     global _host
     if _host is None:
@@ -198,6 +208,7 @@ def host_lib() -> C.CDLL:
         L.slpbh_flush_seconds.argtypes = [vp]
         L.slpbh_phase_seconds.argtypes = [vp, _dp]
         L.slpbh_set_timeout.argtypes = [vp, C.c_double]
+        L.slpbh_set_comm.argtypes = [vp, C.c_int, C.c_int, C.c_char_p]
         L.slpbh_add_recording_callback.argtypes = [vp, C.c_int, C.c_int]
         L.slpbh_clear_callbacks.argtypes = [vp]
         L.slpbh_callback_log.restype = C.c_int
@@ -469,6 +480,13 @@ class Problem:
 
     def loop_seconds(self):
         return self.H.slpbh_loop_seconds(self.h)
+
+    def set_comm(self, rank, world, unique_id: bytes):
+        """Multi-GPU sharded solve: this process is `rank` of `world`; every
+        rank solves the same problem in lockstep. unique_id: the 128 bytes of
+        comm_unique_id() from rank 0."""
+        assert world == 1 or len(unique_id) == 128
+        self.H.slpbh_set_comm(self.h, int(rank), int(world), unique_id)
 
     def set_timeout(self, seconds):
         """Options::timeout of the following solves (negative: none)."""

@@ -876,6 +876,45 @@ bool build_task_plan(ProgramSet& ps, int32_t smem_budget, std::string& error) {
   return true;
 }
 
+void build_shard_plan(const ProgramSet& ps, int32_t world, ShardPlan& out) {
+  out = ShardPlan{};
+  out.world = world;
+  std::vector<std::vector<int32_t>> slots(world);
+  for (const auto& L : ps.launches) {
+    for (int32_t r = 0; r < world; ++r) {
+      const int32_t b = static_cast<int32_t>(int64_t(L.n_tasks) * r / world);
+      const int32_t e = static_cast<int32_t>(int64_t(L.n_tasks) * (r + 1) / world);
+      out.first_task.push_back(L.first_task + b);
+      out.n_tasks.push_back(e - b);
+      for (int32_t t = L.first_task + b; t < L.first_task + e; ++t) {
+        const uint32_t* P = ps.blob.data() + ps.prog_offset[ps.task_prog[t]];
+        const int32_t n_leaf = static_cast<int32_t>(P[2]);
+        const int32_t n_const = static_cast<int32_t>(P[3]);
+        const int32_t n_out = static_cast<int32_t>(P[6] + P[7]);
+        const int32_t lanes = ps.task_lanes[t], cnt = ps.task_count[t];
+        const uint32_t* B = ps.task_bindings.data() + ps.task_bind[t];
+        const int32_t const_off = (n_leaf * lanes + 1) & ~1;
+        const uint32_t* outs = B + const_off + 2 * n_const * lanes;
+        for (int32_t i = 0; i < n_out; ++i) {
+          for (int32_t c = 0; c < cnt; ++c) {
+            slots[r].push_back(static_cast<int32_t>(outs[i * lanes + c]));
+          }
+        }
+      }
+    }
+  }
+  out.len.resize(world);
+  for (int32_t r = 0; r < world; ++r) {
+    out.len[r] = static_cast<int32_t>(slots[r].size());
+    out.max_len = std::max(out.max_len, out.len[r]);
+  }
+  out.slots.assign(size_t(world) * out.max_len, -1);
+  for (int32_t r = 0; r < world; ++r) {
+    std::copy(slots[r].begin(), slots[r].end(),
+              out.slots.begin() + size_t(r) * out.max_len);
+  }
+}
+
 bool compile_autodiff(const Tape& tape, const RowSet rows[SLPB_OUT_COUNT],
                       bool ignore_h_c, CompiledAD& out) {
   out = CompiledAD{};

@@ -158,6 +158,20 @@ struct ProgramSet {
   std::vector<Launch> launches;        // tasks are sorted by launch
 };
 
+/// Multi-GPU sharding of one program set: every launch's tasks are split into
+/// `world` contiguous ranges; rank r evaluates range r and the ranks exchange
+/// the stage slots they produced (one all-gather of `max_len` doubles per rank).
+struct ShardPlan {
+  int32_t world = 1;
+  /// per launch and rank: first task and task count (launch-major)
+  std::vector<int32_t> first_task, n_tasks;
+  /// per rank: the stage slots its tasks write, padded with −1 to max_len
+  std::vector<int32_t> slots;  // world × max_len
+  std::vector<int32_t> len;    // world
+  int32_t max_len = 0;
+};
+void build_shard_plan(const ProgramSet& ps, int32_t world, ShardPlan& out);
+
 /// Groups the clusters of `ps` into tasks and launches. smem_budget: bytes of
 /// shared memory one task may use. Returns false (error set) when a single
 /// cluster does not fit.

@@ -15,6 +15,7 @@
 // There is deliberately no CPU implementation behind this ABI: without a CUDA
 // device slpb_create fails with SLPB_ERR_NO_DEVICE.
 #include <cuda_runtime.h>
+#include <dlfcn.h>
 
 #include <algorithm>
 #include <cmath>
@@ -35,6 +36,48 @@
 #include "slpb.h"
 
 namespace slpb {
+
+// ---------------------------------------------------------------------------
+// NCCL, resolved at run time (dlopen): only the multi-GPU sharded sweep needs
+// it, and a process that already carries an NCCL (torch) shares that copy.
+// Minimal declarations of the stable NCCL 2 C API.
+// ---------------------------------------------------------------------------
+struct NcclUniqueId {
+  char internal[128];
+};
+using NcclComm = void*;
+struct NcclApi {
+  int (*GetUniqueId)(NcclUniqueId*) = nullptr;
+  int (*CommInitRank)(NcclComm*, int, NcclUniqueId, int) = nullptr;
+  int (*AllGather)(const void*, void*, size_t, int, NcclComm, cudaStream_t) =
+      nullptr;
+  int (*CommDestroy)(NcclComm) = nullptr;
+  const char* (*GetErrorString)(int) = nullptr;
+  bool ok = false;
+};
+constexpr int kNcclFloat64 = 8;  // ncclDouble
+
+inline const NcclApi& nccl_api() {
+  static const NcclApi api = [] {
+    NcclApi a;
+    void* h = dlopen("libnccl.so.2", RTLD_NOW | RTLD_GLOBAL);
+    if (!h) h = dlopen("libnccl.so", RTLD_NOW | RTLD_GLOBAL);
+    if (!h) return a;
+    a.GetUniqueId = reinterpret_cast<decltype(a.GetUniqueId)>(
+        dlsym(h, "ncclGetUniqueId"));
+    a.CommInitRank = reinterpret_cast<decltype(a.CommInitRank)>(
+        dlsym(h, "ncclCommInitRank"));
+    a.AllGather =
+        reinterpret_cast<decltype(a.AllGather)>(dlsym(h, "ncclAllGather"));
+    a.CommDestroy =
+        reinterpret_cast<decltype(a.CommDestroy)>(dlsym(h, "ncclCommDestroy"));
+    a.GetErrorString = reinterpret_cast<decltype(a.GetErrorString)>(
+        dlsym(h, "ncclGetErrorString"));
+    a.ok = a.GetUniqueId && a.CommInitRank && a.AllGather && a.CommDestroy;
+    return a;
+  }();
+  return api;
+}
 
 // ---------------------------------------------------------------------------
 // small RAII helpers
@@ -150,6 +193,12 @@ struct slpb_solver {
   DevBuf<double> d_results;
   DevBuf<unsigned char> l2_flush;
   double* h_results = nullptr;  // pinned
+  // multi-GPU sharded re-linearisation
+  int rank = 0, world = 1;
+  NcclComm comm = nullptr;
+  ShardPlan shard;
+  DevBuf<int32_t> shard_slots;
+  DevBuf<double> shard_buf;
   // timing
   cudaEvent_t ev[10] = {};
   float last_ms[5] = {0, 0, 0, 0, 0};
@@ -363,6 +412,24 @@ k_gather_long(const int32_t* __restrict__ entries,
     __syncthreads();
   }
   if (threadIdx.x == 0) out[e] = red[0];
+}
+
+/// Sharded sweep: buf[i] = stage[slots[i]] for the slots this rank produced.
+__global__ void k_shard_pack(const double* __restrict__ stage,
+                             const int32_t* __restrict__ slots, int len,
+                             double* __restrict__ buf) {
+  const int i = blockIdx.x * blockDim.x + threadIdx.x;
+  if (i < len) buf[i] = stage[slots[i]];
+}
+/// After the all-gather: stage[slots[r][i]] = buf[r][i] for every other rank.
+__global__ void k_shard_unpack(const double* __restrict__ buf,
+                               const int32_t* __restrict__ slots, int max_len,
+                               int world, int rank, double* __restrict__ stage) {
+  const int64_t i = int64_t(blockIdx.x) * blockDim.x + threadIdx.x;
+  if (i >= int64_t(world) * max_len) return;
+  if (i / max_len == rank) return;
+  const int32_t slot = slots[i];
+  if (slot >= 0) stage[slot] = buf[i];
 }
 
 __global__ void k_prepare_leaves(const double* __restrict__ x,
@@ -1276,6 +1343,48 @@ int run_sweep(slpb_solver* S, const DevProgramSet& d, const double* leaf,
   return SLPB_OK;
 }
 
+/// The derivative sweep on `world` GPUs: this rank evaluates its share of the
+/// tasks, then ONE NCCL all-gather over NVLink exchanges the stage slots every
+/// rank produced (a few MB per Newton iteration), issued on the solver's stream
+/// right behind the producing kernel.
+int run_sweep_sharded(slpb_solver* S, const DevProgramSet& d, const double* leaf,
+                      double* stage) {
+  const ShardPlan& plan = S->shard;
+  const int W = plan.world, r = S->rank;
+  const AdTasks A{d.blob.p,      d.prog_offset.p, d.task_prog.p,
+                  d.task_count.p, d.task_lanes.p, d.task_bind.p,
+                  d.task_bindings.p};
+  for (size_t L = 0; L < d.launches.size(); ++L) {
+    const int cnt = plan.n_tasks[L * W + r];
+    if (cnt == 0) continue;
+    k_ad_sweep<<<cnt, d.launches[L].threads, d.launches[L].smem_bytes,
+                 S->stream>>>(A, plan.first_task[L * W + r], leaf, stage);
+    ++S->counters.kernel_launches;
+  }
+  CU(cudaGetLastError());
+  if (plan.max_len == 0) return SLPB_OK;
+  double* mine = S->shard_buf.p + size_t(r) * plan.max_len;
+  if (plan.len[r] > 0) {
+    k_shard_pack<<<blocks_for(plan.len[r], 256), 256, 0, S->stream>>>(
+        stage, S->shard_slots.p + size_t(r) * plan.max_len, plan.len[r], mine);
+    ++S->counters.kernel_launches;
+  }
+  const int rc = nccl_api().AllGather(mine, S->shard_buf.p, plan.max_len,
+                                      kNcclFloat64, S->comm, S->stream);
+  if (rc != 0) {
+    return fail(S, SLPB_ERR_NCCL,
+                std::string("ncclAllGather: ") +
+                    (nccl_api().GetErrorString ? nccl_api().GetErrorString(rc)
+                                               : "error"));
+  }
+  k_shard_unpack<<<blocks_for(int64_t(W) * plan.max_len, 256), 256, 0,
+                   S->stream>>>(S->shard_buf.p, S->shard_slots.p, plan.max_len,
+                                W, r, stage);
+  ++S->counters.kernel_launches;
+  CU(cudaGetLastError());
+  return SLPB_OK;
+}
+
 int run_gather(slpb_solver* S, const DevGather& d, const double* stage,
                double* out) {
   if (d.n_entries == 0) return SLPB_OK;
@@ -1344,7 +1453,8 @@ int eval_values(slpb_solver* S, const double* leaf, double* vals) {
 
 int eval_derivs(slpb_solver* S, const double* leaf) {
   CU(cudaEventRecord(S->ev[0], S->stream));
-  int rc = run_sweep(S, S->pd, leaf, S->dstage.p);
+  int rc = S->world > 1 ? run_sweep_sharded(S, S->pd, leaf, S->dstage.p)
+                        : run_sweep(S, S->pd, leaf, S->dstage.p);
   if (rc) return rc;
   rc = run_gather(S, S->gd, S->dstage.p, S->dvals.p);
   if (rc) return rc;
@@ -1589,10 +1699,46 @@ void slpb_destroy(slpb_solver* S) {
   for (auto& e : S->ev) {
     if (e) cudaEventDestroy(e);
   }
+  if (S->comm && nccl_api().ok) nccl_api().CommDestroy(S->comm);
   if (S->h_results) cudaFreeHost(S->h_results);
   cudaStream_t st = S->stream;
   delete S;
   if (st) cudaStreamDestroy(st);
+}
+
+int slpb_comm_unique_id(void* id_out) {
+  if (!id_out) return SLPB_ERR_ARGUMENT;
+  if (!nccl_api().ok) return SLPB_ERR_NCCL;
+  NcclUniqueId id;
+  if (nccl_api().GetUniqueId(&id) != 0) return SLPB_ERR_NCCL;
+  std::memcpy(id_out, &id, sizeof(id));
+  return SLPB_OK;
+}
+
+int slpb_comm_init(slpb_solver* S, int rank, int world, const void* id) {
+  if (!S || !id || world < 1 || rank < 0 || rank >= world) {
+    return SLPB_ERR_ARGUMENT;
+  }
+  if (S->finalized) {
+    return fail(S, SLPB_ERR_STATE, "slpb_comm_init must precede slpb_finalize");
+  }
+  if (world == 1) return SLPB_OK;
+  if (!nccl_api().ok) {
+    return fail(S, SLPB_ERR_NCCL, "libnccl.so.2 could not be loaded");
+  }
+  CU(cudaSetDevice(S->device));
+  NcclUniqueId uid;
+  std::memcpy(&uid, id, sizeof(uid));
+  const int rc = nccl_api().CommInitRank(&S->comm, world, uid, rank);
+  if (rc != 0) {
+    return fail(S, SLPB_ERR_NCCL,
+                std::string("ncclCommInitRank: ") +
+                    (nccl_api().GetErrorString ? nccl_api().GetErrorString(rc)
+                                               : "error"));
+  }
+  S->rank = rank;
+  S->world = world;
+  return SLPB_OK;
 }
 
 const char* slpb_last_error(const slpb_solver* S) {
@@ -1661,6 +1807,11 @@ int slpb_finalize(slpb_solver* S) {
   if ((rc = upload_gather(S, S->ad.deriv_gather, S->gd))) return rc;
   CU(S->vstage.upload(S->ad.value_stage_init, S->stream));
   CU(S->dstage.upload(S->ad.deriv_stage_init, S->stream));
+  if (S->world > 1) {
+    build_shard_plan(S->ad.derivs, S->world, S->shard);
+    CU(S->shard_slots.upload(S->shard.slots, S->stream));
+    CU(S->shard_buf.alloc(std::max<size_t>(1, S->shard.slots.size())));
+  }
   // Function attributes are per process, not per handle: only ever raise them
   // (a second handle — feasibility restoration, multistart — must not lower
   // what a live handle relies on).

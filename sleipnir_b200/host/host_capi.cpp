@@ -4,6 +4,7 @@
 // the reference's is; everything numerical below it goes through the C ABI of
 // include/slpb.h into the CUDA library.
 #include <algorithm>
+#include <array>
 #include <chrono>
 #include <cmath>
 #include <cstring>
@@ -24,6 +25,8 @@ struct Handle {
   int last_status = 0;
   bool flush_l2 = false;
   double timeout_s = -1.0;  // < 0: Options default (no timeout)
+  int rank = 0, world = 1;
+  std::array<char, 128> nccl_id{};
   // what the recording callback saw, 8 doubles per call: iteration, n, ‖x‖∞,
   // s.size, y.size, z.size, nnz(H) + nnz(A_e) + nnz(A_i), g.size
   std::vector<double> callback_log;
@@ -89,6 +92,9 @@ int slpbh_solve(void* h, double tolerance, int max_iterations, int feasible_ipm,
   dopt.ordering = ordering;
   dopt.keep_iterates = keep_iterates != 0;
   dopt.flush_l2 = hd->flush_l2;
+  dopt.rank = hd->rank;
+  dopt.world = hd->world;
+  dopt.nccl_unique_id = hd->nccl_id;
   if (perm) {
     const size_t dim = hd->problem->decision_variables().size() +
                        hd->problem->equality_constraints().size();
@@ -116,6 +122,15 @@ double slpbh_flush_seconds(void* h) {
 void slpbh_phase_seconds(void* h, double* out) {
   const auto& p = H(h)->problem->last_phase_seconds();
   for (int i = 0; i < 9; ++i) out[i] = p[i];
+}
+
+/// Multi-GPU sharded solves: this process is `rank` of `world`, id = the
+/// 128-byte ncclUniqueId of slpb_comm_unique_id distributed by the caller.
+void slpbh_set_comm(void* h, int rank, int world, const void* id) {
+  Handle* hd = H(h);
+  hd->rank = rank;
+  hd->world = world;
+  if (id) std::memcpy(hd->nccl_id.data(), id, 128);
 }
 
 /// Options::timeout for the next solves (seconds; negative = none).

@@ -46,6 +46,11 @@ struct DeviceOptions {
   std::vector<int32_t> permutation;             ///< for SLPB_ORDER_CUSTOM
   bool keep_iterates = false;                   ///< record x,s,y,z per iteration
   bool flush_l2 = false;  ///< evict L2 before every iteration (benchmarks)
+  /// Multi-GPU: one process per GPU, all solving the SAME problem in lockstep;
+  /// the re-linearisation sweep is sharded and exchanged with one NCCL
+  /// all-gather per iteration (slpb_comm_init). world == 1: single GPU.
+  int rank = 0, world = 1;
+  std::array<char, 128> nccl_unique_id{};
 };
 
 /// RAII owner of a device handle.
@@ -198,6 +203,11 @@ class Problem {
 
     DeviceHandle handle{dev_options.device};
     slpb_solver* dev = handle.s;
+    if (dev_options.world > 1) {
+      SLP_DEVICE_CALL(dev, slpb_comm_init(dev, dev_options.rank,
+                                          dev_options.world,
+                                          dev_options.nccl_unique_id.data()));
+    }
     lap(2);
     upload(dev, fp);
     lap(3);

@@ -20,6 +20,7 @@ def lib():
         L.emu_create.restype = vp
         L.emu_create.argtypes = [C.c_char_p, C.c_int, C.c_double, C.c_double]
         L.emu_destroy.argtypes = [vp]
+        L.emu_set_shard_world.argtypes = [vp, C.c_int]
         L.emu_error.restype = C.c_char_p
         L.emu_error.argtypes = [vp]
         L.emu_dims.argtypes = [vp, _ip, _ip, _ip]
@@ -64,6 +65,10 @@ class Emu:
         if self.h:
             self.L.emu_destroy(self.h)
             self.h = None
+
+    def set_shard_world(self, world):
+        """Emulate the derivative sweep as `world` ranks would run it."""
+        self.L.emu_set_shard_world(self.h, world)
 
     def stats(self):
         out = (C.c_int64 * 12)()

@@ -39,6 +39,7 @@ struct Emu {
   slpb::KktRecipe recipe;
   slpb::Symbolic sym;
   std::vector<double> Kval, panels, updates, D, uvecs, xperm;
+  int shard_world = 1;  // > 1: emulate the multi-GPU sharded sweep
 };
 
 slpb::SymbolicView view_of(const slpb::Symbolic& S) {
@@ -91,6 +92,53 @@ void run_programs(const slpb::ProgramSet& ps, const double* leaf,
       case 8: run_task<8>(ps, ti, leaf, stage, scratch.data()); break;
       case 16: run_task<16>(ps, ti, leaf, stage, scratch.data()); break;
       default: run_task<32>(ps, ti, leaf, stage, scratch.data()); break;
+    }
+  }
+}
+
+void run_one_task(const slpb::ProgramSet& ps, int ti, const double* leaf,
+                  double* stage, double* scratch) {
+  switch (ps.task_lanes[ti]) {
+    case 1: run_task<1>(ps, ti, leaf, stage, scratch); break;
+    case 2: run_task<2>(ps, ti, leaf, stage, scratch); break;
+    case 4: run_task<4>(ps, ti, leaf, stage, scratch); break;
+    case 8: run_task<8>(ps, ti, leaf, stage, scratch); break;
+    case 16: run_task<16>(ps, ti, leaf, stage, scratch); break;
+    default: run_task<32>(ps, ti, leaf, stage, scratch); break;
+  }
+}
+
+/// What `world` ranks would do with a ShardPlan: every rank sweeps only its
+/// task ranges into its OWN copy of the stage, packs the slots it produced,
+/// the packed buffers are concatenated (the all-gather) and unpacked into
+/// rank 0's stage, which is returned in `stage`.
+void run_programs_sharded(const slpb::ProgramSet& ps, int world,
+                          const double* leaf, std::vector<double>& stage) {
+  slpb::ShardPlan plan;
+  slpb::build_shard_plan(ps, world, plan);
+  std::vector<double> scratch(size_t(ps.max_smem / 8 + 1) * 32);
+  std::vector<double> gathered(size_t(world) * plan.max_len, 0.0);
+  const std::vector<double> init = stage;
+  const size_t n_launch = ps.launches.size();
+  for (int r = 0; r < world; ++r) {
+    std::vector<double> mine = init;
+    for (size_t L = 0; L < n_launch; ++L) {
+      const int first = plan.first_task[L * world + r];
+      const int cnt = plan.n_tasks[L * world + r];
+      for (int t = first; t < first + cnt; ++t) {
+        run_one_task(ps, t, leaf, mine.data(), scratch.data());
+      }
+    }
+    for (int i = 0; i < plan.len[r]; ++i) {
+      gathered[size_t(r) * plan.max_len + i] =
+          mine[plan.slots[size_t(r) * plan.max_len + i]];
+    }
+    if (r == 0) stage = mine;
+  }
+  for (int r = 1; r < world; ++r) {
+    for (int i = 0; i < plan.len[r]; ++i) {
+      stage[plan.slots[size_t(r) * plan.max_len + i]] =
+          gathered[size_t(r) * plan.max_len + i];
     }
   }
 }
@@ -151,6 +199,10 @@ void* emu_create(const char* name, int N, double p0, double p1) {
 }
 
 void emu_destroy(void* h) { delete static_cast<Emu*>(h); }
+/// Emulates the derivative sweep as `world` ranks would run it (ShardPlan).
+void emu_set_shard_world(void* h, int world) {
+  static_cast<Emu*>(h)->shard_world = world;
+}
 const char* emu_error(void* h) { return static_cast<Emu*>(h)->error.c_str(); }
 
 void emu_dims(void* h, int* n, int* me, int* mi) {
@@ -237,7 +289,11 @@ void emu_eval(void* h, const double* x, const double* y, const double* z,
   run_programs(a.values, leaf.data(), vstage.data());
   run_gather(a.value_gather, vstage.data(), d_f, d_c.data(), e->values);
   std::vector<double> dstage = a.deriv_stage_init;
-  run_programs(a.derivs, leaf.data(), dstage.data());
+  if (e->shard_world > 1) {
+    run_programs_sharded(a.derivs, e->shard_world, leaf.data(), dstage);
+  } else {
+    run_programs(a.derivs, leaf.data(), dstage.data());
+  }
   run_gather(a.deriv_gather, dstage.data(), d_f, d_c.data(), e->derivs);
   *f = e->values[0];
   std::memcpy(c_e, e->values.data() + 1, me * 8);

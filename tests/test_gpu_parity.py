@@ -571,3 +571,27 @@ def test_full_size_properties_n5000():
     c = D.counters()
     assert c.kernel_launches > 0 and c.n_program_classes <= 12
     P.close_device(); P.close()
+
+
+def test_sharded_two_gpu():
+    """Multi-GPU path (slpb_comm_init): two processes, one per GPU, solve the
+    same problem with the derivative sweep sharded over the ranks and one NCCL
+    all-gather per Newton iteration; iterates must be bit-identical to the
+    single-GPU solve (tests/shard_worker.py). Skipped on a one-GPU box."""
+    import socket
+    import subprocess
+    import sys
+    import torch
+    if torch.cuda.device_count() < 2:
+        pytest.skip("needs two GPUs")
+    root = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+    with socket.socket() as sk:
+        sk.bind(("127.0.0.1", 0))
+        port = sk.getsockname()[1]
+    res = subprocess.run(
+        [sys.executable, "-m", "torch.distributed.run", "--nnodes=1",
+         "--nproc-per-node=2", "--master-addr", "127.0.0.1", "--master-port",
+         str(port), os.path.join(root, "tests", "shard_worker.py"), "300", "25"],
+        capture_output=True, text=True, timeout=600, cwd=root)
+    assert res.returncode == 0, res.stdout[-3000:] + res.stderr[-3000:]
+    assert "SHARDED_OK" in res.stdout
