@@ -214,17 +214,15 @@ def main():
     P.close()
 
     shard = args.shard and world > 1
-    comm_id = None
-    if shard:
-        box = [sb.comm_unique_id() if rank == 0 else None]
-        dist.broadcast_object_list(box, src=0)
-        comm_id = box[0]
 
     def one_solve(flush, max_iterations):
         Q = sb.Problem("cart_pole", N)
         Q.set_flush_l2(flush)
         if shard:
-            Q.set_comm(rank, world, comm_id)
+            # a ncclUniqueId serves ONE communicator: a fresh one per solve
+            box = [sb.comm_unique_id() if rank == 0 else None]
+            dist.broadcast_object_list(box, src=0)
+            Q.set_comm(rank, world, box[0])
         if world > 1:
             dist.barrier()
         torch.cuda.synchronize()
