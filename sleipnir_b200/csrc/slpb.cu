@@ -1009,6 +1009,15 @@ k_factor_tree(TreeView T, const double* __restrict__ Kval, double delta,
     const FrontMeta fm = load_front_meta(T.metas + s);
     int32_t* fcount = T.sync + 1 + v * T.n_super;
     int32_t* vstats = stats + 8 * v;
+    // A variant that met an exactly zero pivot has failed whatever follows
+    // (SimplicialLDLT reports NumericalIssue; the host only looks at the flag):
+    // its remaining fronts just hand the dependency on. For the speculated
+    // pair this makes the doomed (0, 0) attempt nearly free.
+    int32_t* dead = T.sync + 1 + 3 * T.n_super + v;
+    if (ld_acquire_gpu(dead) != 0) {
+      if (lane == 0 && fm.parent >= 0) red_release_add(&fcount[fm.parent], 1);
+      continue;
+    }
     if (T.debug && lane == 0 && v == 0) T.debug[3 * s] = global_ns();
     const FusedRhs fr{pair.rhs, T.perm, pair.xperm + size_t(v) * pair.dim,
                       pair.uvecs + v * pair.uvec_stride};
@@ -1029,6 +1038,10 @@ k_factor_tree(TreeView T, const double* __restrict__ Kval, double delta,
       acc_neg[v] += ls[warp][1];
       acc_zero[v] += ls[warp][2];
       acc_zpiv[v] |= ls[warp][3];
+      if (ls[warp][3]) {
+        atomicExch(dead, 1);
+        atomicOr(&vstats[3], 1);  // reported even if this warp is preempted
+      }
       const unsigned long long bits =
           (unsigned long long)(unsigned)ls[warp][4] |
           ((unsigned long long)(unsigned)ls[warp][5] << 32);
@@ -1973,7 +1986,9 @@ int slpb_analyze(slpb_solver* S, int ordering, const int32_t* perm,
       CU(S->tree_debug.alloc(3 * size_t(Y.n_super)));
       CU(S->tree_debug.zero(S->stream));
     }
-    CU(S->tree_sync.alloc(1 + 3 * size_t(Y.n_super)));
+    // [0] ticket | 3 × n_super dependency words | [1 + 3 n_super + v] "variant v
+    // met an exactly zero pivot" flags of the factor launch
+    CU(S->tree_sync.alloc(3 + 3 * size_t(Y.n_super)));
   }
   // fronts of order ≤ 32: one warp per front, one launch per factorisation
   S->use_tree = Y.max_front <= 32;
@@ -2152,6 +2167,8 @@ int factor_impl(slpb_solver* S, int n_variants, const double* delta,
   if (S->use_tree) {
     CU(cudaMemsetAsync(S->tree_sync.p, 0, (1 + 2 * size_t(Y.n_super)) * 4,
                        S->stream));
+    CU(cudaMemsetAsync(S->tree_sync.p + 1 + 3 * size_t(Y.n_super), 0, 2 * 4,
+                       S->stream));
     const TreeView T = tree_view(S);
     const int smem =
         kTreeWarps * S->tree_smem_doubles * static_cast<int>(sizeof(double));
@@ -2201,6 +2218,7 @@ int factor_impl(slpb_solver* S, int n_variants, const double* delta,
     info[v].n_zero = host_stats[8 * v + 2];
     info[v].zero_pivot = host_stats[8 * v + 3];
     std::memcpy(&info[v].min_abs_d, &host_stats[8 * v + 4], 8);
+    if (info[v].zero_pivot) S->fwd_valid[v] = false;  // factor was abandoned
   }
   S->counters.factorizations += n_variants;
   S->factor_sel = 0;
