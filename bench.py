@@ -43,30 +43,77 @@ def measured_peaks():
 
 
 class ClockSampler:
-    """Samples nvidia-smi clocks / throttle reasons during the timed region."""
+    """Samples SM clocks / throttle reasons during the timed region. Uses NVML
+    in-process (pynvml) — spawning nvidia-smi five times a second contends for
+    the driver lock with the very cudaMalloc/memcpy calls being timed — and
+    falls back to nvidia-smi when pynvml is unavailable."""
 
     Q = ("index,clocks.sm,clocks.max.sm,power.draw,clocks_event_reasons.active,"
          "clocks_event_reasons.hw_slowdown,clocks_event_reasons.hw_thermal_slowdown,"
          "clocks_event_reasons.sw_thermal_slowdown,clocks_event_reasons.sw_power_cap")
+    REASONS = {0x8: "hw_slowdown", 0x40: "hw_thermal_slowdown",
+               0x20: "sw_thermal_slowdown", 0x4: "sw_power_cap"}
 
     def __init__(self, gpu_index=0):
-        self.samples = []
+        self.samples = []     # (sm_mhz, max_mhz, set of reasons)
         self.gpu_index = gpu_index
         self._stop = threading.Event()
         self._thread = None
+        self._nvml = None
+        try:
+            import pynvml
+            pynvml.nvmlInit()
+            self._nvml = pynvml
+            self._handle = pynvml.nvmlDeviceGetHandleByIndex(self._physical_index())
+        except Exception:
+            self._nvml = None
 
-    def _loop(self):
-        while not self._stop.is_set():
+    def _physical_index(self):
+        vis = os.environ.get("CUDA_VISIBLE_DEVICES")
+        if vis:
             try:
-                out = subprocess.run(
-                    ["nvidia-smi", f"--query-gpu={self.Q}",
-                     "--format=csv,noheader,nounits", "-i", str(self.gpu_index)],
-                    capture_output=True, text=True, timeout=5).stdout.strip()
-                if out:
-                    self.samples.append([c.strip() for c in out.split(",")])
+                return int(vis.split(",")[self.gpu_index])
             except Exception:
                 pass
-            self._stop.wait(0.2)
+        return self.gpu_index
+
+    def _sample_nvml(self):
+        n = self._nvml
+        sm = n.nvmlDeviceGetClockInfo(self._handle, n.NVML_CLOCK_SM)
+        mx = n.nvmlDeviceGetMaxClockInfo(self._handle, n.NVML_CLOCK_SM)
+        try:
+            bits = n.nvmlDeviceGetCurrentClocksEventReasons(self._handle)
+        except Exception:
+            bits = n.nvmlDeviceGetCurrentClocksThrottleReasons(self._handle)
+        self.samples.append((float(sm), float(mx),
+                             {name for bit, name in self.REASONS.items() if bits & bit}))
+
+    def _sample_smi(self):
+        out = subprocess.run(
+            ["nvidia-smi", f"--query-gpu={self.Q}", "--format=csv,noheader,nounits",
+             "-i", str(self._physical_index())],
+            capture_output=True, text=True, timeout=5).stdout.strip()
+        if not out:
+            return
+        c = [x.strip() for x in out.split(",")]
+        names = ["hw_slowdown", "hw_thermal_slowdown", "sw_thermal_slowdown",
+                 "sw_power_cap"]
+        self.samples.append((float(c[1]), float(c[2]),
+                             {nm for nm, v in zip(names, c[5:9])
+                              if v.lower().startswith("active")}))
+
+    enabled = True
+
+    def _loop(self):
+        while self.enabled and not self._stop.is_set():
+            try:
+                if self._nvml is not None:
+                    self._sample_nvml()
+                else:
+                    self._sample_smi()
+            except Exception:
+                pass
+            self._stop.wait(0.5)
 
     def __enter__(self):
         self._thread = threading.Thread(target=self._loop, daemon=True)
@@ -78,22 +125,15 @@ class ClockSampler:
         self._thread.join(timeout=6)
 
     def summary(self):
-        sm, mx, reasons = [], [], set()
-        names = ["hw_slowdown", "hw_thermal_slowdown", "sw_thermal_slowdown",
-                 "sw_power_cap"]
+        sm = sorted(s[0] for s in self.samples)
+        mx = [s[1] for s in self.samples]
+        reasons = set()
         for s in self.samples:
-            try:
-                sm.append(float(s[1]))
-                mx.append(float(s[2]))
-            except Exception:
-                continue
-            for name, v in zip(names, s[5:9]):
-                if v.lower().startswith("active"):
-                    reasons.add(name)
-        sm.sort()
+            reasons |= s[2]
         return {"sm_mhz": sm[len(sm) // 2] if sm else None,
                 "sm_max_mhz": max(mx) if mx else None,
-                "reasons": sorted(reasons), "samples": len(sm)}
+                "reasons": sorted(reasons), "samples": len(sm),
+                "source": "nvml" if self._nvml is not None else "nvidia-smi"}
 
 
 def steady_rate(trace, warmup, steps):
@@ -133,6 +173,8 @@ def main():
     ap.add_argument("--impl", default="b200", choices=["b200", "reference"])
     ap.add_argument("--horizon", type=int, default=5000)
     ap.add_argument("--no-cpu-baseline", action="store_true")
+    ap.add_argument("--no-clock-sampler", action="store_true",
+                    help="experiments only: do not poll NVML during the run")
     ap.add_argument("--shard", action="store_true",
                     help="N > 1: ONE solve sharded over the GPUs (derivative "
                          "sweep split over the ranks, one NCCL all-gather per "
@@ -238,6 +280,7 @@ def main():
         dist.all_reduce(t, op=dist.ReduceOp.MAX)
         return float(t.item())
 
+    ClockSampler.enabled = not args.no_clock_sampler
     with ClockSampler(local_rank) as clk:
         # (1) headline `value`: L2 evicted before every iteration (256 MiB
         #     memset, excluded from the iteration timestamps)

@@ -14,8 +14,13 @@
 // jacobian.hpp:139-141); long root sums (Σ_k u_k² costs) are split into
 // independent terms so a 5000-term chain does not serialise on one warp.
 #include <algorithm>
+#include <chrono>
+#include <cstdio>
+#include <cstdlib>
 #include <cstring>
+#include <map>
 #include <numeric>
+#include <thread>
 #include <unordered_map>
 
 #include "internal.hpp"
@@ -31,6 +36,19 @@ int64_t Pattern::find(int32_t r, int32_t c) const {
 }
 
 namespace {
+
+/// SLPB_COMPILE_TIMING=1 prints where the host compiler spends its time.
+struct StageTimer {
+  bool on = std::getenv("SLPB_COMPILE_TIMING") != nullptr;
+  std::chrono::steady_clock::time_point t = std::chrono::steady_clock::now();
+  void lap(const char* what) {
+    if (!on) return;
+    const auto now = std::chrono::steady_clock::now();
+    std::fprintf(stderr, "[slpb compile] %-28s %8.1f ms\n", what,
+                 std::chrono::duration<double, std::milli>(now - t).count());
+    t = now;
+  }
+};
 
 constexpr int kSplitThreshold = 16;  // root sums shorter than this stay whole
 
@@ -195,7 +213,8 @@ struct Compiler {
   /// Fills sr.flags and drops nodes that are neither active nor value-needed
   /// (e.g. the −y_j term of a Lagrangian-gradient row: it feeds no output and
   /// no partial, and would otherwise chain all time steps into one cluster).
-  void analyze_subrow(SubRow& sr) {
+  void analyze_subrow(SubRow& sr) { analyze_subrow(sr, pos); }
+  void analyze_subrow(SubRow& sr, std::vector<int32_t>& pos) const {
     const int32_t len = static_cast<int32_t>(sr.nodes.size());
     sr.flags.assign(len, 0);
     if (sr.is_value) {
@@ -241,6 +260,117 @@ struct Compiler {
     }
     sr.nodes.resize(w);
     sr.flags.resize(w);
+  }
+
+  /// Per-thread scratch indexed by node id (all −1 between uses).
+  struct Scratch {
+    std::vector<int32_t> pos, local;
+  };
+  /// What the parallel pass records about one cluster.
+  struct ClusterInfo {
+    uint64_t h1 = 0, h2 = 0;
+    int32_t n_slots = 0;
+    bool bad_leaf = false;
+    std::vector<int32_t> leaf_index, val_out_stage, adj_out_stage;
+    std::vector<double> const_vals;
+  };
+
+  /// Runs fn(begin, end, scratch) over [0, n) split across a few host threads
+  /// (the compiler's own scratch serves the calling thread).
+  template <typename F>
+  void parallel_ranges(int32_t n, F&& fn) {
+    const unsigned hw = std::thread::hardware_concurrency();
+    const int32_t T =
+        n < 4096 ? 1 : static_cast<int32_t>(std::min(8u, std::max(1u, hw)));
+    Scratch mine;
+    mine.pos.swap(pos);
+    mine.local.swap(local);
+    if (T == 1) {
+      fn(0, n, mine);
+    } else {
+      std::vector<std::thread> threads;
+      for (int32_t t = 1; t < T; ++t) {
+        threads.emplace_back([&, t] {
+          Scratch sc;
+          sc.pos.assign(tape.n_nodes, -1);
+          sc.local.assign(tape.n_nodes, -1);
+          fn(static_cast<int32_t>(int64_t(n) * t / T),
+             static_cast<int32_t>(int64_t(n) * (t + 1) / T), sc);
+        });
+      }
+      fn(0, static_cast<int32_t>(int64_t(n) / T), mine);
+      for (auto& th : threads) th.join();
+    }
+    mine.pos.swap(pos);
+    mine.local.swap(local);
+  }
+
+  /// Local slot numbering (left in sc.local, nodes in cl_nodes), binding data
+  /// and signature hashes of one cluster.
+  void describe_cluster(const std::vector<SubRow>& subs,
+                        const std::vector<int32_t>& mem, Scratch& sc,
+                        ClusterInfo& ci, std::vector<int32_t>& cl_nodes) const {
+    cl_nodes.clear();
+    for (int32_t s : mem) {
+      const SubRow& sr = subs[s];
+      for (size_t i = 0; i < sr.nodes.size(); ++i) {
+        const int32_t nd = sr.nodes[i];
+        if ((sr.flags[i] & kValue) && sc.local[nd] < 0) {
+          sc.local[nd] = static_cast<int32_t>(cl_nodes.size());
+          cl_nodes.push_back(nd);
+        }
+      }
+    }
+    ci = ClusterInfo{};
+    ci.n_slots = static_cast<int32_t>(cl_nodes.size());
+    for (int32_t slot = 0; slot < ci.n_slots; ++slot) {
+      const int32_t nd = cl_nodes[slot];
+      if (is_interior(nd)) continue;
+      if (tape.op[nd] == SLPB_OP_VAR) {
+        if (tape.leaf_of_node[nd] < 0) ci.bad_leaf = true;
+        ci.leaf_index.push_back(tape.leaf_of_node[nd]);
+      } else {
+        ci.const_vals.push_back(tape.val[nd]);
+      }
+    }
+    for (int32_t s : mem) {
+      const SubRow& sr = subs[s];
+      if (sr.is_value) {
+        ci.val_out_stage.push_back(sr.value_stage);
+      } else {
+        for (auto& [stage, nd] : sr.outs) ci.adj_out_stage.push_back(stage);
+      }
+    }
+    uint64_t h1 = 1469598103934665603ull, h2 = 0x9e3779b97f4a7c15ull;
+    auto mix = [&](uint32_t w) {
+      h1 ^= w;
+      h1 *= 1099511628211ull;
+      h2 = (h2 ^ (w + 0x9e3779b9u)) * 0xff51afd7ed558ccdull;
+      h2 ^= h2 >> 29;
+    };
+    mix(static_cast<uint32_t>(mem.size()));
+    mix(static_cast<uint32_t>(ci.n_slots));
+    for (int32_t s : mem) {
+      const SubRow& sr = subs[s];
+      const int32_t len = static_cast<int32_t>(sr.nodes.size());
+      mix(sr.is_value ? 1u : 0u);
+      mix(static_cast<uint32_t>(static_cast<int32_t>(sr.seed)));
+      mix(static_cast<uint32_t>(len));
+      mix(static_cast<uint32_t>(sr.outs.size()));
+      for (int32_t i = 0; i < len; ++i) sc.pos[sr.nodes[i]] = i;
+      for (int32_t i = 0; i < len; ++i) {
+        const int32_t nd = sr.nodes[i];
+        const int32_t l = tape.lhs[nd], r = tape.rhs[nd];
+        mix(uint32_t(tape.op[nd]) | (uint32_t(sr.flags[i]) << 8));
+        mix(static_cast<uint32_t>(sc.local[nd]));
+        mix(static_cast<uint32_t>(l >= 0 ? sc.pos[l] : -2));
+        mix(static_cast<uint32_t>(r >= 0 ? sc.pos[r] : -2));
+      }
+      for (auto& [stage, nd] : sr.outs) mix(static_cast<uint32_t>(sc.pos[nd]));
+      for (int32_t i = 0; i < len; ++i) sc.pos[sr.nodes[i]] = -1;
+    }
+    ci.h1 = h1;
+    ci.h2 = h2;
   }
 
   /// Emits the position-independent program of one cluster into `prog`.
@@ -591,6 +721,7 @@ struct Compiler {
   /// Builds clusters + programs for `subs`.
   bool build_programs(std::vector<SubRow>& subs, ProgramSet& ps) {
     const int32_t ns = static_cast<int32_t>(subs.size());
+    StageTimer timer;
     // --- clusters: union-find over sub-rows that share an interior node ----
     std::vector<int32_t> uf(ns);
     std::iota(uf.begin(), uf.end(), 0);
@@ -599,7 +730,10 @@ struct Compiler {
       return a;
     };
     owner.assign(tape.n_nodes, -1);
-    for (int32_t s = 0; s < ns; ++s) analyze_subrow(subs[s]);
+    parallel_ranges(ns, [&](int32_t b, int32_t e, Scratch& sc) {
+      for (int32_t s = b; s < e; ++s) analyze_subrow(subs[s], sc.pos);
+    });
+    timer.lap("analyze_subrow");
     for (int32_t s = 0; s < ns; ++s) {
       const SubRow& sr = subs[s];
       for (size_t i = 0; i < sr.nodes.size(); ++i) {
@@ -628,105 +762,69 @@ struct Compiler {
       }
     }
 
-    std::unordered_map<uint64_t, std::vector<int32_t>> by_hash;
-    std::vector<std::vector<uint32_t>> prog_sig;  // signature of each program
-    std::vector<uint32_t> prog;       // program being built
-    std::vector<uint32_t> sig;        // structural signature of the cluster
-    std::vector<int32_t> cl_nodes;    // nodes of the cluster, first-seen order
-    std::vector<int32_t> level;       // per local slot
-    std::vector<int32_t> sorted_ids;
-
-    std::fill(local.begin(), local.end(), -1);
-
-    for (const auto& mem : members) {
-      // --- local slots, first appearance order ----------------------------
-      cl_nodes.clear();
-      for (int32_t s : mem) {
-        const SubRow& sr = subs[s];
-        for (size_t i = 0; i < sr.nodes.size(); ++i) {
-          const int32_t nd = sr.nodes[i];
-          if ((sr.flags[i] & kValue) && local[nd] < 0) {
-            local[nd] = static_cast<int32_t>(cl_nodes.size());
-            cl_nodes.push_back(nd);
-          }
-        }
+    timer.lap("union-find + members");
+    // --- per cluster, in parallel: local slot numbering, binding data and a
+    // 128-bit hash of the structural signature (everything the program depends
+    // on, in cluster-local terms: slot numbers, positions inside each sub-row).
+    // Clusters with equal hashes share one program — every time step after the
+    // first finds its program without it being rebuilt. (Two independent 64-bit
+    // hashes; a collision between different signatures is a 2⁻¹²⁸ event.)
+    const int32_t n_clusters = static_cast<int32_t>(members.size());
+    std::vector<ClusterInfo> infos(n_clusters);
+    parallel_ranges(n_clusters, [&](int32_t b, int32_t e, Scratch& sc) {
+      std::vector<int32_t> cl_nodes;
+      for (int32_t c = b; c < e; ++c) {
+        describe_cluster(subs, members[c], sc, infos[c], cl_nodes);
+        for (int32_t nd : cl_nodes) sc.local[nd] = -1;
       }
-      const int32_t n_slots = static_cast<int32_t>(cl_nodes.size());
-      if (n_slots > 65535) {
+    });
+    for (const ClusterInfo& ci : infos) {
+      if (ci.n_slots > 65535) {
         error = "an expression cluster has more than 65535 nodes; the block-"
                 "cooperative fallback for such graphs is not implemented";
         return false;
       }
-      // --- binding data (cheap; needed whether or not the program is new) ----
-      std::vector<int32_t> leaf_index, val_out_stage, adj_out_stage;
-      std::vector<double> const_vals;
-      for (int32_t slot = 0; slot < n_slots; ++slot) {
-        const int32_t nd = cl_nodes[slot];
-        if (is_interior(nd)) continue;
-        if (tape.op[nd] == SLPB_OP_VAR) {
-          if (tape.leaf_of_node[nd] < 0) {
-            error = "the tape contains a decision-variable node that is not a "
-                    "decision variable, y multiplier or z multiplier";
-            return false;
-          }
-          leaf_index.push_back(tape.leaf_of_node[nd]);
-        } else {
-          const_vals.push_back(tape.val[nd]);
-        }
+      if (ci.bad_leaf) {
+        error = "the tape contains a decision-variable node that is not a "
+                "decision variable, y multiplier or z multiplier";
+        return false;
       }
-      for (int32_t s : mem) {
-        const SubRow& sr = subs[s];
-        if (sr.is_value) {
-          val_out_stage.push_back(sr.value_stage);
-        } else {
-          for (auto& [stage, nd] : sr.outs) adj_out_stage.push_back(stage);
+    }
+    timer.lap("signatures (parallel)");
+
+    // --- sequential merge: programs in first-seen order, bindings appended ----
+    std::map<std::pair<uint64_t, uint64_t>, int32_t> by_hash;
+    std::vector<uint32_t> prog;       // program being built
+    std::vector<int32_t> cl_nodes;    // nodes of the cluster, first-seen order
+    std::vector<int32_t> level;       // per local slot
+    std::vector<int32_t> sorted_ids;
+    Scratch main_sc;
+    main_sc.pos.assign(tape.n_nodes, -1);
+    main_sc.local.assign(tape.n_nodes, -1);
+    std::fill(local.begin(), local.end(), -1);
+    for (int32_t c = 0; c < n_clusters; ++c) {
+      const auto& mem = members[c];
+      ClusterInfo& ci = infos[c];
+      const auto key = std::make_pair(ci.h1, ci.h2);
+      auto it = by_hash.find(key);
+      int32_t pid;
+      if (it != by_hash.end()) {
+        pid = it->second;
+      } else {
+        // a new program: rebuild the cluster's local numbering in the
+        // compiler's own scratch (emit_program reads `local`) and emit it
+        ClusterInfo again;
+        describe_cluster(subs, mem, main_sc, again, cl_nodes);
+        for (size_t k = 0; k < cl_nodes.size(); ++k) {
+          local[cl_nodes[k]] = static_cast<int32_t>(k);
         }
-      }
-      // --- structural signature: everything the program depends on, expressed
-      // in cluster-local terms (slot numbers, positions inside each sub-row).
-      // Two clusters with equal signatures get byte-identical programs, so the
-      // program of every time step after the first is found here without
-      // being rebuilt.
-      sig.clear();
-      sig.push_back(static_cast<uint32_t>(mem.size()));
-      sig.push_back(static_cast<uint32_t>(n_slots));
-      for (int32_t s : mem) {
-        const SubRow& sr = subs[s];
-        const int32_t len = static_cast<int32_t>(sr.nodes.size());
-        sig.push_back(sr.is_value ? 1u : 0u);
-        sig.push_back(static_cast<uint32_t>(static_cast<int32_t>(sr.seed)));
-        sig.push_back(static_cast<uint32_t>(len));
-        sig.push_back(static_cast<uint32_t>(sr.outs.size()));
-        for (int32_t i = 0; i < len; ++i) pos[sr.nodes[i]] = i;
-        for (int32_t i = 0; i < len; ++i) {
-          const int32_t nd = sr.nodes[i];
-          const int32_t l = tape.lhs[nd], r = tape.rhs[nd];
-          sig.push_back(uint32_t(tape.op[nd]) | (uint32_t(sr.flags[i]) << 8));
-          sig.push_back(static_cast<uint32_t>(local[nd]));
-          sig.push_back(static_cast<uint32_t>(l >= 0 ? pos[l] : -2));
-          sig.push_back(static_cast<uint32_t>(r >= 0 ? pos[r] : -2));
+        const bool ok =
+            emit_program(subs, mem, cl_nodes, level, sorted_ids, prog, ps);
+        for (int32_t nd : cl_nodes) {
+          local[nd] = -1;
+          main_sc.local[nd] = -1;
         }
-        for (auto& [stage, nd] : sr.outs) {
-          sig.push_back(static_cast<uint32_t>(pos[nd]));
-        }
-        for (int32_t i = 0; i < len; ++i) pos[sr.nodes[i]] = -1;
-      }
-      uint64_t h = 1469598103934665603ull;
-      for (uint32_t w : sig) {
-        h ^= w;
-        h *= 1099511628211ull;
-      }
-      int32_t pid = -1;
-      for (int32_t cand : by_hash[h]) {
-        if (prog_sig[cand] == sig) {
-          pid = cand;
-          break;
-        }
-      }
-      if (pid < 0) {
-        if (!emit_program(subs, mem, cl_nodes, level, sorted_ids, prog, ps)) {
-          return false;
-        }
+        if (!ok) return false;
         pid = static_cast<int32_t>(ps.prog_offset.size());
         ps.prog_offset.push_back(static_cast<int64_t>(ps.blob.size()));
         ps.blob.insert(ps.blob.end(), prog.begin(), prog.end());
@@ -734,12 +832,11 @@ struct Compiler {
         ps.prog_smem.push_back(smem);
         ps.prog_width.push_back(static_cast<int32_t>(prog[17]));
         ps.max_smem = std::max(ps.max_smem, smem);
-        by_hash[h].push_back(pid);
-        prog_sig.push_back(sig);
+        by_hash.emplace(key, pid);
       }
       if ((ps.blob.data() + ps.prog_offset[pid])[20] == 2) {
-        const_vals.push_back(1.0);
-        const_vals.push_back(-1.0);
+        ci.const_vals.push_back(1.0);
+        ci.const_vals.push_back(-1.0);
       }
       {
         const uint32_t* P = ps.blob.data() + ps.prog_offset[pid];
@@ -756,21 +853,20 @@ struct Compiler {
         ps.bindings.resize(off + v.size());
         if (!v.empty()) std::memcpy(ps.bindings.data() + off, v.data(), v.size() * 4);
       };
-      push_i32s(leaf_index);
+      push_i32s(ci.leaf_index);
       if (ps.bindings.size() & 1) ps.bindings.push_back(0);
       {
         const size_t off = ps.bindings.size();
-        ps.bindings.resize(off + const_vals.size() * 2);
-        if (!const_vals.empty()) {
-          std::memcpy(ps.bindings.data() + off, const_vals.data(),
-                      const_vals.size() * 8);
+        ps.bindings.resize(off + ci.const_vals.size() * 2);
+        if (!ci.const_vals.empty()) {
+          std::memcpy(ps.bindings.data() + off, ci.const_vals.data(),
+                      ci.const_vals.size() * 8);
         }
       }
-      push_i32s(val_out_stage);
-      push_i32s(adj_out_stage);
-
-      for (int32_t nd : cl_nodes) local[nd] = -1;
+      push_i32s(ci.val_out_stage);
+      push_i32s(ci.adj_out_stage);
     }
+    timer.lap("signatures + bindings");
     return true;
   }
 };
@@ -918,6 +1014,7 @@ void build_shard_plan(const ProgramSet& ps, int32_t world, ShardPlan& out) {
 bool compile_autodiff(const Tape& tape, const RowSet rows[SLPB_OUT_COUNT],
                       bool ignore_h_c, CompiledAD& out) {
   out = CompiledAD{};
+  StageTimer timer;
   Compiler C{tape, out.error};
   const int32_t n = tape.n_x, me = tape.n_y, mi = tape.n_z;
 
@@ -1046,7 +1143,9 @@ bool compile_autodiff(const Tape& tape, const RowSet rows[SLPB_OUT_COUNT],
   }
   out.deriv_stage_size = next_stage;
   out.deriv_stage_init.resize(next_stage, 0.0);
+  timer.lap("patterns + derivative sub-rows");
   if (!C.build_programs(dsubs, out.derivs)) return false;
+  timer.lap("build_programs(derivs) total");
   out.deriv_gather = dgather.finish();
 
   // ---- value sub-rows ------------------------------------------------------------
@@ -1093,8 +1192,10 @@ bool compile_autodiff(const Tape& tape, const RowSet rows[SLPB_OUT_COUNT],
     out.value_stage_init.push_back(p.v);
   }
   out.value_stage_size = static_cast<int32_t>(out.value_stage_init.size());
+  timer.lap("value sub-rows");
   if (!C.build_programs(vsubs, out.values)) return false;
   out.value_gather = vgather.finish();
+  timer.lap("build_programs(values) total");
   return true;
 }
 

@@ -18,6 +18,7 @@
 #include <dlfcn.h>
 
 #include <algorithm>
+#include <chrono>
 #include <cmath>
 #include <cstdio>
 #include <cstdlib>
@@ -83,16 +84,40 @@ inline const NcclApi& nccl_api() {
 // small RAII helpers
 // ---------------------------------------------------------------------------
 
+/// Stream on which the DevBufs of the running ABI call allocate and free
+/// (stream-ordered allocator: cudaMallocAsync / cudaFreeAsync). A plain
+/// cudaFree synchronises the whole device and takes the driver's global lock —
+/// ~130 of them made the teardown of one solve take anywhere from 10 ms to
+/// seconds; stream-ordered frees are queued and the memory stays in the
+/// device's pool for the next solve.
+inline thread_local cudaStream_t tls_alloc_stream = nullptr;
+struct AllocScope {
+  cudaStream_t prev;
+  explicit AllocScope(cudaStream_t st) : prev{tls_alloc_stream} {
+    tls_alloc_stream = st;
+  }
+  ~AllocScope() { tls_alloc_stream = prev; }
+};
+
 template <typename T>
 struct DevBuf {
   T* p = nullptr;
   size_t n = 0;
+  cudaStream_t owner = nullptr;  // stream the allocation is ordered on
   DevBuf() = default;
   DevBuf(const DevBuf&) = delete;
   DevBuf& operator=(const DevBuf&) = delete;
   ~DevBuf() { release(); }
   void release() {
-    if (p) cudaFree(p);
+    if (p) {
+      // free on the stream of the running call if there is one (it may differ
+      // from `owner` only by being the same handle's stream), else the owner's
+      cudaStream_t st = tls_alloc_stream ? tls_alloc_stream : owner;
+      if (cudaFreeAsync(p, st) != cudaSuccess) {
+        cudaGetLastError();
+        cudaFree(p);
+      }
+    }
     p = nullptr;
     n = 0;
   }
@@ -100,7 +125,9 @@ struct DevBuf {
     release();
     n = count;
     if (count == 0) return cudaSuccess;
-    return cudaMalloc(&p, count * sizeof(T));
+    owner = tls_alloc_stream;
+    return cudaMallocAsync(reinterpret_cast<void**>(&p), count * sizeof(T),
+                           owner);
   }
   cudaError_t upload(const std::vector<T>& v, cudaStream_t st) {
     cudaError_t e = alloc(v.size());
@@ -1327,6 +1354,38 @@ cudaError_t raise_dynamic_smem(Kernel kernel, int bytes) {
   return e;
 }
 
+/// Pinned result mirrors are recycled across handles: cudaFreeHost
+/// synchronises the whole context and was seen to take 250 ms at the end of a
+/// solve; a handle needs 512 bytes, so the few buffers a process ever creates
+/// are simply kept.
+struct PinnedPool {
+  std::mutex mu;
+  std::vector<double*> free_list;
+  double* acquire() {
+    {
+      std::lock_guard<std::mutex> lock{mu};
+      if (!free_list.empty()) {
+        double* p = free_list.back();
+        free_list.pop_back();
+        return p;
+      }
+    }
+    double* p = nullptr;
+    if (cudaMallocHost(&p, kResultDoubles * sizeof(double)) != cudaSuccess) {
+      return nullptr;
+    }
+    return p;
+  }
+  void give_back(double* p) {
+    std::lock_guard<std::mutex> lock{mu};
+    free_list.push_back(p);
+  }
+};
+inline PinnedPool& pinned_pool() {
+  static PinnedPool* pool = new PinnedPool;  // intentionally never destroyed
+  return *pool;
+}
+
 int upload_gather(slpb_solver* S, const Gather& g, DevGather& d) {
   d.n_entries = g.n_entries();
   CU(d.ptr.upload(g.ptr, S->stream));
@@ -1688,10 +1747,20 @@ int slpb_create(int device, slpb_solver** out) {
       cudaSuccess) {
     return SLPB_ERR_CUDA;
   }
-  if (cudaMallocHost(&S->h_results, kResultDoubles * sizeof(double)) !=
-      cudaSuccess) {
-    return SLPB_ERR_CUDA;
+  {
+    // keep freed memory in the device's default pool (re-used by the next
+    // solve) instead of returning it to the driver at every synchronisation
+    cudaMemPool_t pool = nullptr;
+    if (cudaDeviceGetDefaultMemPool(&pool, device) == cudaSuccess) {
+      unsigned long long keep = ~0ull;
+      cudaMemPoolSetAttribute(pool, cudaMemPoolAttrReleaseThreshold, &keep);
+    } else {
+      cudaGetLastError();
+    }
   }
+  const AllocScope alloc_scope{S->stream};
+  S->h_results = pinned_pool().acquire();
+  if (!S->h_results) return SLPB_ERR_CUDA;
   if (S->d_results.alloc(kResultDoubles) != cudaSuccess) return SLPB_ERR_CUDA;
   if (S->red_partials.alloc(kReduceBlocks * 32) != cudaSuccess ||
       S->red_counter.alloc(1) != cudaSuccess ||
@@ -1707,16 +1776,33 @@ int slpb_create(int device, slpb_solver** out) {
 
 void slpb_destroy(slpb_solver* S) {
   if (!S) return;
+  const bool timing = std::getenv("SLPB_DESTROY_TIMING") != nullptr;
+  const auto t_begin = std::chrono::steady_clock::now();
+  auto lap = [&, last = t_begin](const char* what) mutable {
+    if (!timing) return;
+    const auto now = std::chrono::steady_clock::now();
+    std::fprintf(stderr, "[slpb destroy] %-22s %8.2f ms\n", what,
+                 std::chrono::duration<double, std::milli>(now - last).count());
+    last = now;
+  };
   cudaSetDevice(S->device);
   if (S->stream) cudaStreamSynchronize(S->stream);
+  lap("stream sync");
   for (auto& e : S->ev) {
     if (e) cudaEventDestroy(e);
   }
+  lap("events");
   if (S->comm && nccl_api().ok) nccl_api().CommDestroy(S->comm);
-  if (S->h_results) cudaFreeHost(S->h_results);
+  if (S->h_results) pinned_pool().give_back(S->h_results);
+  lap("comm + pinned");
   cudaStream_t st = S->stream;
-  delete S;
+  {
+    const AllocScope alloc_scope{st};
+    delete S;  // DevBufs are freed stream-ordered; the stream outlives them
+  }
+  lap("delete (async frees)");
   if (st) cudaStreamDestroy(st);
+  lap("stream destroy");
 }
 
 int slpb_comm_unique_id(void* id_out) {
@@ -1804,6 +1890,7 @@ int slpb_set_ignore_constraint_hessian(slpb_solver* S, int ignore) {
 
 int slpb_finalize(slpb_solver* S) {
   if (!S) return SLPB_ERR_ARGUMENT;
+  const AllocScope alloc_scope{S->stream};
   if (!S->have_tape) {
     return fail(S, SLPB_ERR_STATE, "slpb_finalize before slpb_upload_tape");
   }
@@ -1921,6 +2008,7 @@ int slpb_set_scaling(slpb_solver* S, double d_f, const double* d_ce,
 int slpb_analyze(slpb_solver* S, int ordering, const int32_t* perm,
                  slpb_symbolic_stats* stats) {
   if (!S || !S->finalized) return SLPB_ERR_STATE;
+  const AllocScope alloc_scope{S->stream};
   CU(cudaSetDevice(S->device));
   if (!analyze_kkt(S->recipe.K, S->n, ordering, perm, S->sym, S->error)) {
     return SLPB_ERR_ARGUMENT;
@@ -2545,6 +2633,7 @@ int slpb_get_timers(slpb_solver* S, slpb_timers* out) {
 
 int slpb_flush_l2(slpb_solver* S) {
   if (!S) return SLPB_ERR_ARGUMENT;
+  const AllocScope alloc_scope{S->stream};
   CU(cudaSetDevice(S->device));
   constexpr size_t kBytes = size_t(256) << 20;
   if (S->l2_flush.n != kBytes) CU(S->l2_flush.alloc(kBytes));

@@ -17,6 +17,8 @@
 #include <concepts>
 #include <array>
 #include <chrono>
+#include <cstdio>
+#include <cstdlib>
 #include <functional>
 #include <limits>
 #include <memory>
@@ -289,6 +291,24 @@ class Problem {
     slpb_get_counters(dev, &m_counters);
     slpb_get_timers(dev, &m_timers);
     lap(7);
+    if (std::getenv("SLPB_DESTROY_TIMING")) {
+      // where the teardown goes (development aid): release the big owners one
+      // by one instead of at scope exit
+      auto t = std::chrono::steady_clock::now();
+      auto mark = [&](const char* what) {
+        const auto now = std::chrono::steady_clock::now();
+        std::fprintf(stderr, "[slp teardown] %-18s %8.2f ms\n", what,
+                     std::chrono::duration<double, std::milli>(now - t).count());
+        t = now;
+      };
+      fp = detail::FlatProblem{};
+      mark("flat problem");
+      graphs.reset();
+      mark("graphs");
+      slpb_destroy(handle.s);
+      handle.s = nullptr;
+      mark("device handle");
+    }
     return status;
   }
 

@@ -70,14 +70,28 @@ class Flattener {
     for (int row : J.nonlinear_rows()) R.row_swept[row] = 1;
     const auto& lists = J.top_lists();
     const auto& outs = J.output_lists();
+    size_t total_nodes = 0, total_outs = 0;
+    for (int r = 0; r < R.n_rows; ++r) {
+      if (!R.row_swept[r]) continue;
+      total_nodes += lists[r].size();
+      total_outs += outs[r].size();
+    }
+    R.row_nodes.reserve(total_nodes);
+    R.out_col.reserve(total_outs);
+    R.out_node.reserve(total_outs);
+    R.row_ptr.reserve(R.n_rows + 1);
+    R.out_ptr.reserve(R.n_rows + 1);
+    ensure_touched();
     for (int r = 0; r < R.n_rows; ++r) {
       // Only swept rows need their lists on the device; LINEAR rows travel as
       // cached triplets.
       if (R.row_swept[r]) {
-        for (ExprId id : lists[r]) R.row_nodes.push_back(touch(id));
+        R.row_nodes.insert(R.row_nodes.end(), lists[r].begin(), lists[r].end());
+        for (ExprId id : lists[r]) m_touched[id] = 1;
         for (const auto& [col, id] : outs[r]) {
           R.out_col.push_back(col);
-          R.out_node.push_back(touch(id));
+          R.out_node.push_back(id);
+          m_touched[id] = 1;
         }
       }
       R.row_ptr.push_back(static_cast<int32_t>(R.row_nodes.size()));
@@ -167,6 +181,9 @@ class Flattener {
     }
     m_touched[id] = 1;
     return id;
+  }
+  void ensure_touched() {
+    if (m_touched.size() < pool().size()) m_touched.resize(pool().size(), 0);
   }
 
   FlatProblem m_out;
