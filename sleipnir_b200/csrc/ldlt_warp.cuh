@@ -2,12 +2,13 @@
 //
 // Same assembly and the same per-entry arithmetic as the generic bodies in
 // ldlt_core.hpp — W(i,j) −= l_ik · w_jk for k ascending, l_ik = w_ik / d_k — so
-// both produce identical bits. What changes is the mapping: the trailing
-// triangle of every pivot is spread over all 32 lanes element by element (a
-// fixed table turns a packed index into (row, col)), the pivot column is staged
-// once per pivot in shared memory, global loads are batched ahead of the
-// shared-memory read-modify-writes, and all per-front metadata comes from one
-// packed record instead of a chain of dependent index loads.
+// both produce identical bits. What changes is the mapping: a front is assembled
+// in shared memory, then lane i takes row i into registers and the pivots are
+// eliminated with warp shuffles (no shared-memory round trip, no barrier per
+// pivot); the right-hand side rides along (forward substitution fused into the
+// factorisation); global loads are batched ahead of the shared-memory
+// read-modify-writes, and all per-front metadata comes from one packed record
+// instead of a chain of dependent index loads.
 #pragma once
 
 #include "ldlt_core.hpp"
@@ -34,21 +35,6 @@ __device__ __forceinline__ FrontMeta load_front_meta(const FrontMeta* p) {
   dst[2] = __ldg(src + 2);
   dst[3] = __ldg(src + 3);
   return m;
-}
-
-/// (row, col) of packed lower-triangle index e, row-major: e = a(a+1)/2 + b.
-/// The enumeration is the same for every triangle size (prefix property), so
-/// one table of 528 entries serves every pivot of every front of order ≤ 32.
-constexpr int kTriEntries = 33 * 32 / 2;
-
-__device__ __forceinline__ void init_tri_table(uchar2* tri) {
-  for (int e = threadIdx.x; e < kTriEntries; e += blockDim.x) {
-    int a = static_cast<int>((sqrtf(8.0f * e + 1.0f) - 1.0f) * 0.5f);
-    while ((a + 1) * (a + 2) / 2 <= e) ++a;
-    while (a * (a + 1) / 2 > e) --a;
-    tri[e] = make_uchar2(static_cast<unsigned char>(a),
-                         static_cast<unsigned char>(e - a * (a + 1) / 2));
-  }
 }
 
 /// What a parent front pre-loads about one child before it starts waiting.
@@ -192,9 +178,9 @@ struct FusedRhs {
   double* uvecs;          // update vectors, indexed like rel_idx
 };
 
-/// W: F×F column-major in shared memory; col: 64 doubles of shared scratch
-/// (scaled pivot column in [0,32), unscaled in [32,64)). `dep` is polled by
-/// lane 0 AFTER everything that does not depend on the children is done.
+/// W: F×F column-major in shared memory; col: 64 doubles of shared scratch (the
+/// front's right-hand side while it is assembled). `dep` is polled by lane 0
+/// AFTER everything that does not depend on the children is done.
 __device__ __forceinline__ void ldlt_factor_front_warp(
     int lane, const FrontMeta& fm, const FrontMeta* __restrict__ metas,
     const int32_t* __restrict__ child_idx, const int32_t* __restrict__ rel_idx,
@@ -203,8 +189,8 @@ __device__ __forceinline__ void ldlt_factor_front_warp(
     const double* __restrict__ Kval, double delta, double gamma,
     double* __restrict__ panels, double* updates, double* __restrict__ D,
     double* __restrict__ W, double* __restrict__ col,
-    const uchar2* __restrict__ tri, const int* dep, int* local_stats,
-    const FusedRhs& fr, unsigned long long* stamp = nullptr) {
+    const int* dep, int* local_stats, const FusedRhs& fr,
+    unsigned long long* stamp = nullptr) {
   const int F = fm.F, np = fm.np, c0 = fm.c0, m = F - np;
   // own part of the right-hand side (col[] doubles as the rhs work vector)
   if (fr.rhs != nullptr && lane < F) {
@@ -276,7 +262,6 @@ __device__ __forceinline__ void ldlt_factor_front_warp(
 
   // ---- elimination of the own columns + write-out (separate function so that
   // the 32-double row stays in registers) --------------------------------------
-  (void)tri;
   double rhs_i = (fr.rhs != nullptr && lane < F) ? col[lane] : 0.0;
   ldlt_eliminate_rows(lane, F, np, m, W, D + c0, panels + fm.panel_off,
                       updates + fm.update_off, local_stats, rhs_i);

@@ -1013,9 +1013,6 @@ k_factor_tree(TreeView T, const double* __restrict__ Kval, double delta,
               int32_t* __restrict__ stats, int smem_doubles_per_warp) {
   extern __shared__ double smem[];
   __shared__ int ls[kTreeWarps][6];
-  __shared__ uchar2 tri[kTriEntries];
-  init_tri_table(tri);
-  __syncthreads();
   const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
   double* W = smem + size_t(warp) * smem_doubles_per_warp;
   double* col = W + (smem_doubles_per_warp - 64);
@@ -1052,7 +1049,7 @@ k_factor_tree(TreeView T, const double* __restrict__ Kval, double delta,
         lane, fm, T.metas, T.child_idx, T.rel_idx, T.asm_src, T.asm_dst,
         T.col_is_primal, Kval, v ? pair.delta1 : delta,
         v ? pair.gamma1 : gamma, panels + v * pair.panel_stride,
-        updates + v * pair.update_stride, D + v * pair.dim, W, col, tri,
+        updates + v * pair.update_stride, D + v * pair.dim, W, col,
         &fcount[s], ls[warp], fr,
         (T.debug && v == 0) ? T.debug + 3 * s + 1 : nullptr);
     __syncwarp();

@@ -9,7 +9,11 @@ import numpy as np
 import pytest
 import scipy.sparse as sp
 
+import ctypes
+
 from emu import Emu
+
+emu_ip = ctypes.POINTER(ctypes.c_int)
 from oracle.pyoracle import OracleProblem, ldlt
 
 GOLDEN = os.path.join(os.path.dirname(__file__), "golden")
@@ -176,4 +180,35 @@ def test_sharded_sweep_equals_the_single_rank_sweep(world):
     for k in ("g", "A_e", "A_i", "H", "c_e", "c_i"):
         np.testing.assert_array_equal(out[k], ref[k])
     assert out["f"] == ref["f"]
+    E.close()
+
+
+@pytest.mark.parametrize("name,N", [("cart_pole", 40), ("gfold", 12), ("flywheel", 30)])
+def test_ordering_keeps_every_multiplier_behind_a_neighbour(name, N):
+    """csrc/symbolic.cpp, defer_leading_multipliers: in the elimination order no
+    multiplier (index ≥ n) precedes all of its neighbours — an unpivoted LDLᵀ
+    would meet the bare −γ there (an exactly zero pivot for γ = 0). The order
+    must still be a permutation."""
+    E = Emu(name, N)
+    n, me = E.n, E.me
+    E.L.emu_kkt_build(E.h)
+    E.analyze(0)
+    perm = E.perm()
+    dim = n + me
+    assert sorted(perm) == list(range(dim))
+    nnz = E.L.emu_kkt_build(E.h)
+    cp = np.zeros(dim + 1, dtype=np.int32)
+    ri = np.zeros(nnz, dtype=np.int32)
+    E.L.emu_kkt_pattern(E.h, cp.ctypes.data_as(emu_ip), ri.ctypes.data_as(emu_ip))
+    pos = np.empty(dim, dtype=np.int64)
+    pos[perm] = np.arange(dim)
+    nbrs = [[] for _ in range(dim)]
+    for c in range(dim):
+        for r in ri[cp[c]:cp[c + 1]]:
+            if r != c:
+                nbrs[r].append(c)
+                nbrs[c].append(r)
+    for d in range(n, dim):
+        assert nbrs[d], "a multiplier without neighbours"
+        assert min(pos[u] for u in nbrs[d]) < pos[d]
     E.close()
