@@ -344,6 +344,13 @@ inline double fraction_to_the_boundary_rule(const Vec& x, const Vec& p,
 
 enum class KKTErrorType { INF_NORM_SCALED, ONE_NORM };
 
+/// Which of the reference's three Newton-type drivers the loop below restates.
+/// They share one structure (optimization/solver/{interior_point,sqp,newton}.hpp);
+/// SQP is the loop without slacks, barrier and fraction-to-the-boundary rule
+/// (sqp.hpp:91-596), Newton additionally drops the constraints, the
+/// second-order correction and feasibility restoration (newton.hpp:50-290).
+enum class SolverKind { IPM, SQP, NEWTON };
+
 /// kkt_error.hpp:92-146.
 inline double kkt_error(KKTErrorType T, const Vec& g, const Csc& A_e,
                         const Vec& c_e, const Csc& A_i, const Vec& c_i,
@@ -425,7 +432,8 @@ inline ExitStatus interior_point(const IpmCallbacks& matrices,
                                  bool in_feasibility_restoration, Vec& x,
                                  Vec& s, Vec& y, Vec& z, double& mu,
                                  int& iterations, Trace* trace,
-                                 const LinearSolverConfig& lin);
+                                 const LinearSolverConfig& lin,
+                                 SolverKind kind = SolverKind::IPM);
 
 /// lagrange_multiplier_estimate.hpp:55-131.
 inline std::pair<Vec, Vec> lagrange_multiplier_estimate(const Vec& g,
@@ -671,7 +679,8 @@ inline ExitStatus interior_point(const IpmCallbacks& matrices,
                                  bool in_feasibility_restoration, Vec& x,
                                  Vec& s, Vec& y, Vec& z, double& mu,
                                  int& iterations, Trace* trace,
-                                 const LinearSolverConfig& lin) {
+                                 const LinearSolverConfig& lin,
+                                 SolverKind kind) {
   struct Step {
     Vec p_x, p_s, p_y, p_z;
   };
@@ -785,7 +794,9 @@ inline ExitStatus interior_point(const IpmCallbacks& matrices,
     double alpha_max = 1.0, alpha = 1.0, alpha_z = 1.0;
     bool call_feasibility_restoration = false;
 
-    if (!solver.compute(lhs)) return ExitStatus::FACTORIZATION_FAILED;
+    if (!solver.compute(lhs) && kind != SolverKind::NEWTON) {
+      return ExitStatus::FACTORIZATION_FAILED;  // newton.hpp:183 ignores it
+    }
 
     auto compute_step = [&](Step& st, const Vec& c_i_minus_s) {  // :470-481
       ++it_solves;
@@ -822,7 +833,7 @@ inline ExitStatus interior_point(const IpmCallbacks& matrices,
       } else {
         trial_s = axpy(s, alpha, step.p_s);
       }
-      trial_y = axpy(y, alpha_z, step.p_y);
+      trial_y = axpy(y, kind == SolverKind::IPM ? alpha_z : alpha, step.p_y);
       trial_z = axpy(z, alpha_z, step.p_z);
 
       trial_f = matrices.f(trial_x);
@@ -832,6 +843,9 @@ inline ExitStatus interior_point(const IpmCallbacks& matrices,
           !all_finite(trial_c_i)) {
         alpha *= alpha_reduction_factor;
         if (alpha < alpha_min) {
+          if (kind == SolverKind::NEWTON) {
+            return ExitStatus::LINE_SEARCH_FAILED;  // newton.hpp:213
+          }
           call_feasibility_restoration = true;
           break;
         }
@@ -846,7 +860,8 @@ inline ExitStatus interior_point(const IpmCallbacks& matrices,
           norm1(trial_c_e) + norm1(sub(trial_c_i, trial_s));
 
       // Second-order corrections (:561-664)
-      if (alpha == alpha_max && next_violation >= prev_violation) {
+      if (kind != SolverKind::NEWTON && alpha == alpha_max &&
+          next_violation >= prev_violation) {
         Step soc_step = step;
         double alpha_soc = alpha;
         double alpha_z_soc = alpha_z;
@@ -878,7 +893,8 @@ inline ExitStatus interior_point(const IpmCallbacks& matrices,
 
           trial_x = axpy(x, alpha_soc, soc_step.p_x);
           trial_s = axpy(s, alpha_soc, soc_step.p_s);
-          trial_y = axpy(y, alpha_z_soc, soc_step.p_y);
+          trial_y = axpy(y, kind == SolverKind::IPM ? alpha_z_soc : alpha_soc,
+                         soc_step.p_y);
           trial_z = axpy(z, alpha_z_soc, soc_step.p_z);
 
           ++it_trials;
@@ -904,7 +920,7 @@ inline ExitStatus interior_point(const IpmCallbacks& matrices,
 
       if (alpha == alpha_max) ++full_step_rejected_counter;
 
-      if (full_step_rejected_counter >= 4 &&
+      if (kind != SolverKind::NEWTON && full_step_rejected_counter >= 4 &&
           filter.max_constraint_violation >
               current_entry.constraint_violation / 10.0 &&
           filter.last_rejection_due_to_filter()) {
@@ -920,7 +936,8 @@ inline ExitStatus interior_point(const IpmCallbacks& matrices,
                                              c_e, A_i, c_i, s, y, z, mu);
         trial_x = axpy(x, alpha_max, step.p_x);
         trial_s = axpy(s, alpha_max, step.p_s);
-        trial_y = axpy(y, alpha_z, step.p_y);
+        trial_y = axpy(y, kind == SolverKind::IPM ? alpha_z : alpha_max,
+                       step.p_y);
         trial_z = axpy(z, alpha_z, step.p_z);
         trial_f = matrices.f(trial_x);
         trial_c_e = matrices.c_e(trial_x);
@@ -930,6 +947,9 @@ inline ExitStatus interior_point(const IpmCallbacks& matrices,
             trial_c_e, matrices.A_i(trial_x), trial_c_i, trial_s, trial_y,
             trial_z, mu);
         if (next_kkt_error <= 0.999 * current_kkt_error) break;
+        if (kind == SolverKind::NEWTON) {
+          return ExitStatus::LINE_SEARCH_FAILED;  // newton.hpp:245
+        }
         call_feasibility_restoration = true;
         break;
       }
@@ -954,9 +974,12 @@ inline ExitStatus interior_point(const IpmCallbacks& matrices,
                    0.9 * initial_entry.constraint_violation &&
                filter.try_add(initial_entry, te, D_phi_r, alpha);
       });
-      ExitStatus status =
-          feasibility_restoration(matrices, fr_callbacks, options, x, s, y, z,
-                                  mu, iterations, trace, lin);
+      // the SQP variant enters with μ = tolerance/10
+      // (feasibility_restoration.hpp:121)
+      ExitStatus status = feasibility_restoration(
+          matrices, fr_callbacks, options, x, s, y, z,
+          kind == SolverKind::IPM ? mu : options.tolerance / 10.0, iterations,
+          trace, lin);
       if (status != ExitStatus::SUCCESS) return status;
       f = matrices.f(x);
       c_e = matrices.c_e(x);
@@ -985,7 +1008,7 @@ inline ExitStatus interior_point(const IpmCallbacks& matrices,
     E_0 = unscaled_kkt_error(KKTErrorType::INF_NORM_SCALED, matrices.scaling,
                              g, A_e, c_e, A_i, c_i, s, y, z, 0.0);
 
-    if (E_0 > options.tolerance) {  // :819-832
+    if (kind == SolverKind::IPM && E_0 > options.tolerance) {  // :819-832
       constexpr double kappa_eps = 10.0;
       double E_mu = kkt_error(KKTErrorType::INF_NORM_SCALED, g, A_e, c_e, A_i,
                               c_i, s, y, z, mu);
@@ -1048,14 +1071,15 @@ inline ExitStatus interior_point(const IpmCallbacks& matrices,
                                  Trace* trace = nullptr,
                                  const LinearSolverConfig& lin = {},
                                  Vec* s_out = nullptr, Vec* y_out = nullptr,
-                                 Vec* z_out = nullptr) {
+                                 Vec* z_out = nullptr,
+                                 SolverKind kind = SolverKind::IPM) {
   Vec s(matrices.num_inequality_constraints, 1.0);
   Vec y(matrices.num_equality_constraints, 0.0);
   Vec z(matrices.num_inequality_constraints, 1.0);
   double mu = 0.1 * matrices.scaling.f;
   int iterations = 0;
   ExitStatus st = interior_point(matrices, callbacks, options, false, x, s, y,
-                                 z, mu, iterations, trace, lin);
+                                 z, mu, iterations, trace, lin, kind);
   if (s_out) *s_out = s;
   if (y_out) *y_out = y;
   if (z_out) *z_out = z;

@@ -204,8 +204,17 @@ class Problem {
       return ExitStatus::GLOBALLY_INFEASIBLE;
     }
     std::vector<IterationCallback> cbs = m_callbacks;
+    // problem.hpp:335 (Newton), :403 (SQP), :512 (IPM). The three drivers
+    // share one setup here: with no inequality (equality) constraints the
+    // z (y) blocks are empty and H_c's missing terms are exact zeros.
+    SolverKind kind = SolverKind::IPM;
+    if (m_eq.empty() && m_ineq.empty()) {
+      kind = SolverKind::NEWTON;
+    } else if (m_ineq.empty()) {
+      kind = SolverKind::SQP;
+    }
     ExitStatus status = interior_point(setup->callbacks, cbs, options, x, trace,
-                                       lin, s_out, y_out, z_out);
+                                       lin, s_out, y_out, z_out, kind);
     M{m_decision_variables}.set_value(x);
     return status;
   }

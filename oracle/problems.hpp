@@ -58,7 +58,8 @@ Mat<B> rk4(F&& f, const Mat<B>& x, const Mat<B>& u, double h) {
 }
 
 template <class B>
-std::unique_ptr<Problem<B>> cart_pole_problem(int N, double T = 5.0) {
+std::unique_ptr<Problem<B>> cart_pole_problem(int N, double T = 5.0,
+                                              bool bounded = true) {
   using M = Mat<B>;
   using V = Var<B>;
   const double dt = T / N;
@@ -79,8 +80,10 @@ std::unique_ptr<Problem<B>> cart_pole_problem(int N, double T = 5.0) {
 
   problem->subject_to_eq(eq(X.col(0), M::constants(4, 1, x_initial)));
   problem->subject_to_eq(eq(X.col(N), M::constants(4, 1, x_final)));
-  problem->subject_to_ineq(bounds(V{0.0}, X.row(0), V{d_max}));
-  problem->subject_to_ineq(bounds(V{-u_max}, U, V{u_max}));
+  if (bounded) {  // without the bounds the reference takes its SQP branch
+    problem->subject_to_ineq(bounds(V{0.0}, X.row(0), V{d_max}));
+    problem->subject_to_ineq(bounds(V{-u_max}, U, V{u_max}));
+  }
   for (int k = 0; k < N; ++k) {
     problem->subject_to_eq(
         eq(X.col(k + 1),
@@ -96,7 +99,8 @@ std::unique_ptr<Problem<B>> cart_pole_problem(int N, double T = 5.0) {
 }
 
 template <class B>
-std::unique_ptr<Problem<B>> flywheel_problem(int N, double T = 5.0) {
+std::unique_ptr<Problem<B>> flywheel_problem(int N, double T = 5.0,
+                                             bool bounded = true) {
   using M = Mat<B>;
   using V = Var<B>;
   const double dt = T / N;
@@ -110,12 +114,32 @@ std::unique_ptr<Problem<B>> flywheel_problem(int N, double T = 5.0) {
     problem->subject_to_eq(eq(X.col(k + 1), A * X.col(k) + Bm * U.col(k)));
   }
   problem->subject_to_eq(eq(X.col(0), V{0.0}));
-  problem->subject_to_ineq(bounds(V{-12}, U, V{12}));
+  if (bounded) problem->subject_to_ineq(bounds(V{-12}, U, V{12}));
   M r = M::constants(1, 1, {10.0});
   V J{0.0};
   for (int k = 0; k < N + 1; ++k) {
     M e = (r - X.col(k)).T() * (r - X.col(k));
     J += e(0, 0);
+  }
+  problem->minimize(J);
+  return problem;
+}
+
+/// Σ 100(xᵢ₊₁ − xᵢ²)² + (1 − xᵢ)² from the classic (−1.2, 1, −1.2, …) start:
+/// an unconstrained problem of any size for the Newton branch
+/// (problem.hpp:335).
+template <class B>
+std::unique_ptr<Problem<B>> chained_rosenbrock_problem(int N) {
+  using M = Mat<B>;
+  using V = Var<B>;
+  auto problem = std::make_unique<Problem<B>>();
+  M X = problem->decision_variable(N + 1, 1);
+  for (int k = 0; k < N + 1; ++k) X(k, 0).set_value(k % 2 == 0 ? -1.2 : 1.0);
+  V J{0.0};
+  for (int k = 0; k < N; ++k) {
+    V x = X(k, 0);
+    V y = X(k + 1, 0);
+    J += V{100} * pow(y - pow(x, 2.0), 2.0) + pow(V{1} - x, 2.0);
   }
   problem->minimize(J);
   return problem;
@@ -200,6 +224,69 @@ std::unique_ptr<Problem<B>> small_problem(const std::string& name, double p0,
   } else if (name == "nonfinite_ineq_jacobian") {  // :169-175
     V x = P->decision_variable();
     P->subject_to_ineq(ge1(sqrt(x), V{1}));
+  } else if (name == "unconstrained_1d") {  // quadratic_problem_test.cpp:15-34
+    V x = P->decision_variable();
+    x.set_value(2);
+    P->minimize(x * x - V{6} * x);
+  } else if (name == "unconstrained_2d") {  // :36-58
+    V x = P->decision_variable();
+    V y = P->decision_variable();
+    x.set_value(1);
+    y.set_value(2);
+    P->minimize(x * x + y * y);
+  } else if (name == "eq_maximize_xy") {  // :80-141
+    V x = P->decision_variable();
+    V y = P->decision_variable();
+    P->maximize(x * y);
+    P->subject_to_eq({x + V{3} * y - V{36}});
+  } else if (name == "eq_pin_2d") {  // :143-161
+    M x = P->decision_variable(2, 1);
+    x(0, 0).set_value(1);
+    x(1, 0).set_value(2);
+    M xx = x.T() * x;
+    P->minimize(xx(0, 0));
+    P->subject_to_eq(eq(x, M::constants(2, 1, {3.0, 3.0})));
+  } else if (name == "min_distance_line") {  // nonlinear_problem_test.cpp:120-143
+    V x = P->decision_variable();
+    V y = P->decision_variable();
+    x.set_value(20);
+    y.set_value(50);
+    P->minimize(sqrt(x * x + y * y));
+    P->subject_to_eq({y - (-x + V{5})});
+  } else if (name == "too_few_dofs") {  // exit_status_test.cpp:52-72
+    V x = P->decision_variable();
+    V y = P->decision_variable();
+    V z = P->decision_variable();
+    P->subject_to_eq({x - V{1}});
+    P->subject_to_eq({x - V{2}});
+    P->subject_to_eq({y - V{1}});
+    P->subject_to_eq({z - V{1}});
+  } else if (name == "locally_infeasible_eq") {  // :78-95
+    V x = P->decision_variable();
+    V y = P->decision_variable();
+    V z = P->decision_variable();
+    P->subject_to_eq({x - (y + V{1})});
+    P->subject_to_eq({y - (z + V{1})});
+    P->subject_to_eq({z - (x + V{1})});
+  } else if (name == "nonfinite_cost") {  // :124-130
+    V x = P->decision_variable();
+    P->minimize(V{1} / x);
+  } else if (name == "nonfinite_gradient") {  // :133-139
+    V x = P->decision_variable();
+    P->minimize(sqrt(x));
+  } else if (name == "nonfinite_eq") {  // :142-148
+    V x = P->decision_variable();
+    P->subject_to_eq({V{1} / x - V{1}});
+  } else if (name == "nonfinite_eq_jacobian") {  // :151-157
+    V x = P->decision_variable();
+    P->subject_to_eq({sqrt(x) - V{1}});
+  } else if (name == "diverging") {  // :178-194
+    V x = P->decision_variable();
+    P->minimize(x);
+  } else if (name == "min_x_squared") {  // :17-50, :196-234
+    V x = P->decision_variable();
+    x.set_value(1);
+    P->minimize(x * x);
   } else {
     throw std::invalid_argument("unknown oracle problem: " + name);
   }
@@ -390,6 +477,13 @@ std::unique_ptr<Problem<B>> make_problem(const std::string& name, int N,
   if (name == "cart_pole") return cart_pole_problem<B>(N, p0 > 0 ? p0 : 5.0);
   if (name == "flywheel") return flywheel_problem<B>(N, p0 > 0 ? p0 : 5.0);
   if (name == "gfold") return gfold_problem<B>(N, p0 > 0 ? p0 : 48.0);
+  if (name == "cart_pole_eq") {
+    return cart_pole_problem<B>(N, p0 > 0 ? p0 : 5.0, false);
+  }
+  if (name == "flywheel_eq") {
+    return flywheel_problem<B>(N, p0 > 0 ? p0 : 5.0, false);
+  }
+  if (name == "chained_rosenbrock") return chained_rosenbrock_problem<B>(N);
   return small_problem<B>(name, p0, p1);
 }
 

@@ -203,6 +203,8 @@ def host_lib() -> C.CDLL:
         L.slpbh_solution.argtypes = [vp, _dp, _dp, _dp, _dp]
         L.slpbh_loop_seconds.restype = C.c_double
         L.slpbh_loop_seconds.argtypes = [vp]
+        L.slpbh_solver_kind.restype = C.c_int
+        L.slpbh_solver_kind.argtypes = [vp]
         L.slpbh_set_flush_l2.argtypes = [vp, C.c_int]
         L.slpbh_flush_seconds.restype = C.c_double
         L.slpbh_flush_seconds.argtypes = [vp]
@@ -480,6 +482,11 @@ class Problem:
 
     def loop_seconds(self):
         return self.H.slpbh_loop_seconds(self.h)
+
+    def solver_kind(self):
+        """Branch of the last solve(): "IPM", "SQP" or "NEWTON"
+        (reference problem.hpp:512, :403, :335)."""
+        return ("IPM", "SQP", "NEWTON")[self.H.slpbh_solver_kind(self.h)]
 
     def set_comm(self, rank, world, unique_id: bytes):
         """Multi-GPU sharded solve: this process is `rank` of `world`; every

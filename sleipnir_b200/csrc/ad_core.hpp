@@ -256,19 +256,29 @@ SLPB_HD double gather_entry(int e, const int32_t* __restrict__ ptr,
                             const int32_t* __restrict__ src_scale,
                             const double* __restrict__ stage, double d_f,
                             const double* __restrict__ d_c) {
+  // Sources come in runs of one scale (the d_f·H_f run and the H_c run of a
+  // Hessian entry; one run otherwise). A run is summed first and scaled once,
+  // as the reference scales whole matrices after evaluating them
+  // (problem.hpp:622-660: scaling.f * H_f.value() + H_c.value()).
   double acc = 0.0;
   const int b = ptr[e], en = ptr[e + 1];
-  for (int k = b; k < en; ++k) {
-    const int32_t raw = src_idx[k];
-    double v = stage[raw & 0x7fffffff];
-    if (raw < 0) v = -v;
+  int k = b;
+  while (k < en) {
     const int32_t sc = src_scale[k];
-    if (sc == -2) {
-      v = d_f * v;
-    } else if (sc >= 0) {
-      v = d_c[sc] * v;
+    double run = 0.0;
+    const int k0 = k;
+    for (; k < en && src_scale[k] == sc; ++k) {
+      const int32_t raw = src_idx[k];
+      double v = stage[raw & 0x7fffffff];
+      if (raw < 0) v = -v;
+      run = (k == k0) ? v : run + v;
     }
-    acc = (k == b) ? v : acc + v;
+    if (sc == -2) {
+      run = d_f * run;
+    } else if (sc >= 0) {
+      run = d_c[sc] * run;
+    }
+    acc = (k0 == b) ? run : acc + run;
   }
   return acc;
 }

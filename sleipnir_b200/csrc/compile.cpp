@@ -160,20 +160,56 @@ struct Compiler {
       if (tape.lhs[nd] >= 0) ++cnt[tape.lhs[nd]];
       if (tape.rhs[nd] >= 0) ++cnt[tape.rhs[nd]];
     }
+    // How many terms each expandable sum node would flatten into.
+    auto expandable = [&](int32_t nd) {
+      return is_sum_op(tape.op[nd]) && (nd == root || cnt[nd] == 1);
+    };
+    std::unordered_map<int32_t, int32_t> n_terms;
+    {
+      std::vector<int32_t> order, st{root};
+      while (!st.empty()) {
+        const int32_t nd = st.back();
+        st.pop_back();
+        if (!expandable(nd)) continue;
+        order.push_back(nd);
+        st.push_back(tape.lhs[nd]);
+        if (tape.op[nd] != SLPB_OP_NEG) st.push_back(tape.rhs[nd]);
+      }
+      for (auto it = order.rbegin(); it != order.rend(); ++it) {
+        auto count = [&](int32_t ch) {
+          auto f = n_terms.find(ch);
+          return f == n_terms.end() ? 1 : f->second;
+        };
+        int32_t c = count(tape.lhs[*it]);
+        if (tape.op[*it] != SLPB_OP_NEG) c += count(tape.rhs[*it]);
+        n_terms[*it] = c;
+      }
+    }
+    // The left spine is flattened: ((t0 + t1) + t2) + … summed term by term
+    // in that order is the chain itself, so values and the term-major adjoint
+    // order of the reference's sweep survive. A right operand stays one term
+    // (x + (a + b) is not (x + a) + b) unless it is itself a long sum, which
+    // must be cut to keep clusters small; that reassociates it (a few ulp).
     std::vector<std::pair<int32_t, int8_t>> terms;
     std::vector<std::pair<int32_t, int8_t>> stack{{root, int8_t(1)}};
+    std::vector<uint8_t> on_spine{1};
     while (!stack.empty()) {
       auto [nd, sg] = stack.back();
+      const bool spine = on_spine.back() != 0;
       stack.pop_back();
+      on_spine.pop_back();
       const uint8_t op = tape.op[nd];
-      if (is_sum_op(op) && (nd == root || cnt[nd] == 1)) {
+      if (expandable(nd) && (spine || n_terms[nd] >= kSplitThreshold)) {
         if (op == SLPB_OP_NEG) {
           stack.emplace_back(tape.lhs[nd], int8_t(-sg));
+          on_spine.push_back(spine);
         } else {
           // push rhs first so that lhs is expanded first (left-to-right terms)
           stack.emplace_back(tape.rhs[nd],
                              op == SLPB_OP_SUB ? int8_t(-sg) : sg);
+          on_spine.push_back(0);
           stack.emplace_back(tape.lhs[nd], sg);
+          on_spine.push_back(spine);
         }
       } else {
         terms.emplace_back(nd, sg);

@@ -417,10 +417,15 @@ k_gather_long(const int32_t* __restrict__ entries,
   __shared__ double red[1024];
   const int e = entries[blockIdx.x];
   const int b = ptr[e], en = ptr[e + 1];
+  // one scale for the whole entry (the usual case: a split Σ_k cost) is
+  // applied once to the sum, as gather_entry does per run
+  const int32_t sc0 = src_scale[b];
+  const bool uniform = src_scale[en - 1] == sc0;
   auto term = [&](int k) -> double {
     const int32_t raw = src_idx[k];
     double v = stage[raw & 0x7fffffff];
     if (raw < 0) v = -v;
+    if (uniform) return v;
     const int32_t sc = src_scale[k];
     if (sc == -2) {
       v = d_f * v;
@@ -437,6 +442,13 @@ k_gather_long(const int32_t* __restrict__ entries,
   for (int w = blockDim.x / 2; w > 0; w >>= 1) {
     if (threadIdx.x < w) red[threadIdx.x] += red[threadIdx.x + w];
     __syncthreads();
+  }
+  if (threadIdx.x == 0 && uniform) {
+    if (sc0 == -2) {
+      red[0] = d_f * red[0];
+    } else if (sc0 >= 0) {
+      red[0] = d_c[sc0] * red[0];
+    }
   }
   if (threadIdx.x == 0) out[e] = red[0];
 }
@@ -1679,12 +1691,14 @@ int launch_solve(slpb_solver* S, bool skip_forward) {
 }
 
 /// rhs → solve → step recovery → step stats, into the given step arrays.
-int solve_into(slpb_solver* S, double mu, double tau, const double* cis_soc,
-               const double* ce_for_rhs, double* px, double* ps, double* py,
-               double* pz, slpb_step_info* info) {
+int solve_into(slpb_solver* S, double mu, double tau, bool soc,
+               const double* cis_soc, const double* ce_for_rhs, double* px,
+               double* ps, double* py, double* pz, slpb_step_info* info) {
   const int n = S->n, me = S->me, mi = S->mi;
   // the factorisation already carried this right-hand side forward?
-  const bool fused = cis_soc == nullptr && S->use_tree && S->rhs_ready &&
+  // (`soc` and not `cis_soc != nullptr`: without inequality constraints the
+  // corrected c_i − s array is empty and its pointer null)
+  const bool fused = !soc && S->use_tree && S->rhs_ready &&
                      S->rhs_mu == mu && S->fwd_valid[S->factor_sel];
   if (!fused) {
     int rc0 = build_rhs(S, mu, cis_soc, ce_for_rhs);
@@ -2346,8 +2360,8 @@ int slpb_prepare_rhs(slpb_solver* S, double mu) {
 int slpb_solve(slpb_solver* S, double mu, double tau, slpb_step_info* info) {
   if (!S || !S->analyzed || !info) return SLPB_ERR_STATE;
   CU(cudaSetDevice(S->device));
-  return solve_into(S, mu, tau, nullptr, S->vals_cur.p + 1, S->px.p, S->ps.p,
-                    S->py.p, S->pz.p, info);
+  return solve_into(S, mu, tau, false, nullptr, S->vals_cur.p + 1, S->px.p,
+                    S->ps.p, S->py.p, S->pz.p, info);
 }
 
 int slpb_soc_begin(slpb_solver* S) {
@@ -2375,8 +2389,8 @@ int slpb_soc_iterate(slpb_solver* S, double mu, double tau, double alpha_soc,
         S->me, S->mi, S->ce_soc.p, S->cis_soc.p);
     ++S->counters.kernel_launches;
   }
-  return solve_into(S, mu, tau, S->cis_soc.p, S->ce_soc.p, S->spx.p, S->sps.p,
-                    S->spy.p, S->spz.p, info);
+  return solve_into(S, mu, tau, true, S->cis_soc.p, S->ce_soc.p, S->spx.p,
+                    S->sps.p, S->spy.p, S->spz.p, info);
 }
 
 int slpb_trial(slpb_solver* S, double alpha, double alpha_z, int which_step,

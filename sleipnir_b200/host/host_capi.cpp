@@ -213,6 +213,11 @@ void slpbh_solution(void* h, double* x, double* s, double* y, double* z) {
   cp(z, hd->problem->last_z());
 }
 
+/// 0 interior-point, 1 SQP, 2 Newton: the branch the last solve() took.
+int slpbh_solver_kind(void* h) {
+  return static_cast<int>(H(h)->problem->last_solver_kind());
+}
+
 double slpbh_loop_seconds(void* h) {
   return H(h)->problem->last_trace().loop_seconds;
 }

@@ -276,9 +276,18 @@ class Problem {
       return feasibility_restoration(dev, info, d_ce, d_ci, options, callbacks,
                                      mu_outer, iters, accept, dev_options);
     };
+    // Newton without constraints (:335), SQP with equality constraints only
+    // (:403), else the interior-point method (:512): one loop, three modes.
+    SolverKind kind = SolverKind::IPM;
+    if (me == 0 && mi == 0) {
+      kind = SolverKind::NEWTON;
+    } else if (mi == 0) {
+      kind = SolverKind::SQP;
+    }
+    m_solver_kind = kind;
     ExitStatus status = interior_point<Scalar>(
         dev, info, std::span{callbacks}, options, false, mu, iterations,
-        &m_trace, &restoration);
+        &m_trace, &restoration, 0.0, kind);
 
     lap(6);
     // Write the solution back into the Variables (:676)
@@ -349,6 +358,8 @@ class Problem {
   // ---- introspection of the last solve (not in the reference) -------------
   const SolveTrace& last_trace() const { return m_trace; }
   const slpb_symbolic_stats& last_symbolic_stats() const { return m_symbolic; }
+  /// Which driver the last solve() took (Newton / SQP / IPM).
+  SolverKind last_solver_kind() const { return m_solver_kind; }
   const slpb_counters& last_counters() const { return m_counters; }
   const slpb_timers& last_timers() const { return m_timers; }
   /// Host seconds of the phases of the last solve(): build_graphs, flatten,
@@ -672,6 +683,7 @@ class Problem {
 
   SolveTrace m_trace;
   slpb_symbolic_stats m_symbolic{};
+  SolverKind m_solver_kind = SolverKind::IPM;
   slpb_counters m_counters{};
   slpb_timers m_timers{};
   std::array<double, 9> m_phase{};

@@ -279,8 +279,10 @@ inline double kkt_error_scaled(const slpb_kkt_stats& k, int me, int mi,
   const double s_d =
       std::max(s_max, (k.y_l1 + k.z_l1) / double(me + mi)) / s_max;
   const double s_c = std::max(s_max, k.z_l1 / double(mi)) / s_max;
+  // the device reports ±∞ extrema for an empty s∘z
   const double sz_inf =
-      std::max(std::abs(k.sz_max - mu), std::abs(k.sz_min - mu));
+      mi == 0 ? 0.0
+              : std::max(std::abs(k.sz_max - mu), std::abs(k.sz_min - mu));
   return std::max({k.r_inf / s_d, sz_inf / s_c, k.ce_inf, k.cis_inf});
 }
 /// kkt_error.hpp:216-251 (μ = 0, as the solver uses it for E_0).
@@ -289,7 +291,8 @@ inline double kkt_error_unscaled_mu0(const slpb_kkt_stats& k, int me, int mi) {
   const double s_d =
       std::max(s_max, (k.u_y_l1 + k.u_z_l1) / double(me + mi)) / s_max;
   const double s_c = std::max(s_max, k.u_z_l1 / double(mi)) / s_max;
-  const double sz_inf = std::max(std::abs(k.u_sz_max), std::abs(k.u_sz_min));
+  const double sz_inf =
+      mi == 0 ? 0.0 : std::max(std::abs(k.u_sz_max), std::abs(k.u_sz_min));
   return std::max({k.u_r_inf / s_d, sz_inf / s_c, k.u_ce_inf, k.u_cis_inf});
 }
 inline double kkt_error_one_norm(const slpb_kkt_stats& k) {
@@ -297,6 +300,14 @@ inline double kkt_error_one_norm(const slpb_kkt_stats& k) {
 }
 
 }  // namespace detail
+
+/// The reference has three Newton-type drivers of one shape: interior_point.hpp,
+/// sqp.hpp (no slacks, no barrier, one step length for x and y, restoration
+/// entered with μ = tolerance/10) and newton.hpp (no constraints, no
+/// second-order correction, no restoration, factorisation failures ignored).
+/// Problem::solve picks one by the constraint counts (problem.hpp:335, :403,
+/// :512); here they are one loop over the same device kernels.
+enum class SolverKind { IPM, SQP, NEWTON };
 
 /// Dimensions and scaling the driver needs besides the device handle.
 struct DeviceProblemInfo {
@@ -329,7 +340,7 @@ ExitStatus interior_point(
     const Options& options, bool in_feasibility_restoration, Scalar& mu,
     int& iterations, SolveTrace* trace = nullptr,
     const RestorationHook* restoration = nullptr,
-    double initial_delta = 0.0) {
+    double initial_delta = 0.0, SolverKind kind = SolverKind::IPM) {
   using std::isfinite;
   const auto solve_start_time = std::chrono::steady_clock::now();
   const int n = problem.num_decision_variables;
@@ -471,7 +482,9 @@ ExitStatus interior_point(
     if (!std::getenv("SLPB_NO_FUSED_FORWARD")) {
       SLP_DEVICE_CALL(dev, slpb_prepare_rhs(dev, mu));
     }
-    if (!solver.compute()) return ExitStatus::FACTORIZATION_FAILED;
+    if (!solver.compute() && kind != SolverKind::NEWTON) {
+      return ExitStatus::FACTORIZATION_FAILED;  // newton.hpp:183 carries on
+    }
 
     // rhs, solve, step recovery, fraction-to-the-boundary (:444-497)
     slpb_step_info step{};
@@ -480,7 +493,8 @@ ExitStatus interior_point(
     alpha_max = step.alpha_max;
     alpha = alpha_max;
     if (alpha < alpha_min) call_feasibility_restoration = true;
-    alpha_z = step.alpha_z;
+    // sqp.hpp:346 moves y by the primal step length
+    alpha_z = kind == SolverKind::IPM ? step.alpha_z : alpha;
 
     const FilterEntry<Scalar> current_entry{cur.f - mu * cur.log_s_sum,
                                             cur.ce_l1 + cur.cis_l1};  // :499
@@ -492,6 +506,7 @@ ExitStatus interior_point(
       ++it_trials;
       const int slack_from_ci =
           options.feasible_ipm && cur.ci_all_positive ? 1 : 0;
+      if (kind != SolverKind::IPM) alpha_z = alpha;
       SLP_DEVICE_CALL(dev,
                       slpb_trial(dev, alpha, alpha_z, 0, slack_from_ci, &trial));
 
@@ -500,6 +515,9 @@ ExitStatus interior_point(
       if ((trial.finite & kTrialFinite) != kTrialFinite) {  // :532-542
         alpha *= alpha_reduction_factor;
         if (alpha < alpha_min) {
+          if (kind == SolverKind::NEWTON) {
+            return ExitStatus::LINE_SEARCH_FAILED;  // newton.hpp:213
+          }
           call_feasibility_restoration = true;
           break;
         }
@@ -514,7 +532,7 @@ ExitStatus interior_point(
       Scalar next_constraint_violation = trial.ce_l1 + trial.cis_l1;
 
       // Second-order corrections (:561-664)
-      if (alpha == alpha_max &&
+      if (kind != SolverKind::NEWTON && alpha == alpha_max &&
           next_constraint_violation >= prev_constraint_violation) {
         Scalar alpha_soc = alpha;
         Scalar alpha_z_soc = alpha_z;
@@ -528,7 +546,8 @@ ExitStatus interior_point(
               dev, slpb_soc_iterate(dev, mu, tau, alpha_soc, &soc_step));
           ++it_solves;
           alpha_soc = soc_step.alpha_max;
-          alpha_z_soc = soc_step.alpha_z;
+          alpha_z_soc =
+              kind == SolverKind::IPM ? soc_step.alpha_z : alpha_soc;
           ++it_trials;
           SLP_DEVICE_CALL(
               dev, slpb_trial(dev, alpha_soc, alpha_z_soc, 1, 0, &trial));
@@ -556,7 +575,7 @@ ExitStatus interior_point(
       if (alpha == alpha_max) ++full_step_rejected_counter;  // :669-671
 
       // Filter reset heuristic (:677-684)
-      if (full_step_rejected_counter >= 4 &&
+      if (kind != SolverKind::NEWTON && full_step_rejected_counter >= 4 &&
           filter.max_constraint_violation >
               current_entry.constraint_violation / Scalar(10) &&
           filter.last_rejection_due_to_filter()) {
@@ -574,10 +593,14 @@ ExitStatus interior_point(
         SLP_DEVICE_CALL(dev, slpb_kkt_stats_current(dev, mu, &ks));
         const Scalar current_kkt_error = detail::kkt_error_one_norm(ks);
         ++it_trials;
+        if (kind != SolverKind::IPM) alpha_z = alpha_max;
         SLP_DEVICE_CALL(dev, slpb_trial(dev, alpha_max, alpha_z, 0, 0, &trial));
         SLP_DEVICE_CALL(dev, slpb_kkt_stats_trial(dev, mu, &ks));
         const Scalar next_kkt_error = detail::kkt_error_one_norm(ks);
         if (next_kkt_error <= Scalar(0.999) * current_kkt_error) break;
+        if (kind == SolverKind::NEWTON) {
+          return ExitStatus::LINE_SEARCH_FAILED;  // newton.hpp:245
+        }
         call_feasibility_restoration = true;
         break;
       }
@@ -615,7 +638,11 @@ ExitStatus interior_point(
                filter.try_add(initial_entry, trial_entry, D_phi_restoration,
                               alpha);
       };
-      ExitStatus status = (*restoration)(mu, iterations, accept_test);
+      // the SQP variant enters with μ = tolerance/10
+      // (feasibility_restoration.hpp:121)
+      ExitStatus status = (*restoration)(
+          kind == SolverKind::IPM ? mu : Scalar(options.tolerance) / 10.0,
+          iterations, accept_test);
       if (status != ExitStatus::SUCCESS) return status;
       SLP_DEVICE_CALL(dev, slpb_eval_current(dev, 0, &cur));
     } else {
@@ -635,7 +662,7 @@ ExitStatus interior_point(
     // E_0 and the barrier update (:815-832)
     SLP_DEVICE_CALL(dev, slpb_kkt_stats_current(dev, mu, &kkt));
     E_0 = detail::kkt_error_unscaled_mu0(kkt, me, mi);
-    if (E_0 > Scalar(options.tolerance)) {
+    if (kind == SolverKind::IPM && E_0 > Scalar(options.tolerance)) {
       constexpr Scalar kappa_eps(10);
       Scalar E_mu = detail::kkt_error_scaled(kkt, me, mi, mu);
       while (mu > mu_min && E_mu <= kappa_eps * mu) {

@@ -58,7 +58,8 @@ inline slp::VariableMatrix<double> cart_pole_dynamics(
   return qddot;
 }
 
-inline std::unique_ptr<slp::Problem<double>> cart_pole(int N, double T = 5.0) {
+inline std::unique_ptr<slp::Problem<double>> cart_pole(int N, double T = 5.0,
+                                                       bool bounded = true) {
   const std::chrono::duration<double> dt{T / N};
   constexpr double u_max = 20.0;  // N
   constexpr double d_max = 2.0;   // m
@@ -80,8 +81,10 @@ inline std::unique_ptr<slp::Problem<double>> cart_pole(int N, double T = 5.0) {
 
   problem->subject_to(X.col(0) == x_initial);
   problem->subject_to(X.col(N) == x_final);
-  problem->subject_to(slp::bounds(0.0, X.row(0), d_max));
-  problem->subject_to(slp::bounds(-u_max, U, u_max));
+  if (bounded) {  // without the bounds solve() takes the SQP branch
+    problem->subject_to(slp::bounds(0.0, X.row(0), d_max));
+    problem->subject_to(slp::bounds(-u_max, U, u_max));
+  }
   for (int k = 0; k < N; ++k) {
     problem->subject_to(
         X.col(k + 1) ==
@@ -97,7 +100,8 @@ inline std::unique_ptr<slp::Problem<double>> cart_pole(int N, double T = 5.0) {
   return problem;
 }
 
-inline std::unique_ptr<slp::Problem<double>> flywheel(int N, double T = 5.0) {
+inline std::unique_ptr<slp::Problem<double>> flywheel(int N, double T = 5.0,
+                                                      bool bounded = true) {
   const double dt = T / N;
   slp::Matrix<double> A{{std::exp(-dt)}};
   slp::Matrix<double> B{{1.0 - std::exp(-dt)}};
@@ -109,7 +113,7 @@ inline std::unique_ptr<slp::Problem<double>> flywheel(int N, double T = 5.0) {
     problem->subject_to(X.col(k + 1) == A * X.col(k) + B * U.col(k));
   }
   problem->subject_to(X.col(0) == 0.0);
-  problem->subject_to(slp::bounds(-12, U, 12));
+  if (bounded) problem->subject_to(slp::bounds(-12, U, 12));
 
   slp::Matrix<double> r{{10.0}};
   slp::Variable<double> J = 0.0;
@@ -291,6 +295,22 @@ inline std::unique_ptr<slp::Problem<double>> gfold(int N, double T_f = 48.0) {
   return P;
 }
 
+/// Σ 100(xᵢ₊₁ − xᵢ²)² + (1 − xᵢ)² from the classic (−1.2, 1, −1.2, …) start: an
+/// unconstrained problem of any size for the Newton branch.
+inline std::unique_ptr<slp::Problem<double>> chained_rosenbrock(int N) {
+  auto problem = std::make_unique<slp::Problem<double>>();
+  auto X = problem->decision_variable(N + 1, 1);
+  for (int k = 0; k < N + 1; ++k) X[k, 0].set_value(k % 2 == 0 ? -1.2 : 1.0);
+  slp::Variable<double> J = 0.0;
+  for (int k = 0; k < N; ++k) {
+    slp::Variable<double> x = X[k, 0];
+    slp::Variable<double> y = X[k + 1, 0];
+    J += 100.0 * slp::pow(y - slp::pow(x, 2.0), 2.0) + slp::pow(1.0 - x, 2.0);
+  }
+  problem->minimize(J);
+  return problem;
+}
+
 inline std::unique_ptr<slp::Problem<double>> small_problem(
     const std::string& name, double p0, double p1) {
   using T = double;
@@ -366,6 +386,68 @@ inline std::unique_ptr<slp::Problem<double>> small_problem(
   } else if (name == "nonfinite_ineq_jacobian") {
     auto x = problem.decision_variable();
     problem.subject_to(sqrt(x) > T(1));
+  } else if (name == "unconstrained_1d") {
+    auto x = problem.decision_variable();
+    x.set_value(T(2));
+    problem.minimize(x * x - T(6) * x);
+  } else if (name == "unconstrained_2d") {
+    auto x = problem.decision_variable();
+    auto y = problem.decision_variable();
+    x.set_value(T(1));
+    y.set_value(T(2));
+    problem.minimize(x * x + y * y);
+  } else if (name == "eq_maximize_xy") {
+    auto x = problem.decision_variable();
+    auto y = problem.decision_variable();
+    problem.maximize(x * y);
+    problem.subject_to(x + T(3) * y == T(36));
+  } else if (name == "eq_pin_2d") {
+    auto x = problem.decision_variable(2);
+    x[0].set_value(T(1));
+    x[1].set_value(T(2));
+    problem.minimize(x.T() * x);
+    problem.subject_to(x == slp::Matrix<double>{{3.0}, {3.0}});
+  } else if (name == "min_distance_line") {
+    auto x = problem.decision_variable();
+    auto y = problem.decision_variable();
+    x.set_value(T(20));
+    y.set_value(T(50));
+    problem.minimize(sqrt(x * x + y * y));
+    problem.subject_to(y == -x + T(5));
+  } else if (name == "too_few_dofs") {
+    auto x = problem.decision_variable();
+    auto y = problem.decision_variable();
+    auto z = problem.decision_variable();
+    problem.subject_to(x == T(1));
+    problem.subject_to(x == T(2));
+    problem.subject_to(y == T(1));
+    problem.subject_to(z == T(1));
+  } else if (name == "locally_infeasible_eq") {
+    auto x = problem.decision_variable();
+    auto y = problem.decision_variable();
+    auto z = problem.decision_variable();
+    problem.subject_to(x == y + T(1));
+    problem.subject_to(y == z + T(1));
+    problem.subject_to(z == x + T(1));
+  } else if (name == "nonfinite_cost") {
+    auto x = problem.decision_variable();
+    problem.minimize(T(1) / x);
+  } else if (name == "nonfinite_gradient") {
+    auto x = problem.decision_variable();
+    problem.minimize(sqrt(x));
+  } else if (name == "nonfinite_eq") {
+    auto x = problem.decision_variable();
+    problem.subject_to(T(1) / x == T(1));
+  } else if (name == "nonfinite_eq_jacobian") {
+    auto x = problem.decision_variable();
+    problem.subject_to(sqrt(x) == T(1));
+  } else if (name == "diverging") {
+    auto x = problem.decision_variable();
+    problem.minimize(x);
+  } else if (name == "min_x_squared") {
+    auto x = problem.decision_variable();
+    x.set_value(T(1));
+    problem.minimize(x * x);
   } else {
     throw std::invalid_argument("unknown problem: " + name);
   }
@@ -377,6 +459,9 @@ inline std::unique_ptr<slp::Problem<double>> make_problem(
   if (name == "cart_pole") return cart_pole(N, p0 > 0 ? p0 : 5.0);
   if (name == "flywheel") return flywheel(N, p0 > 0 ? p0 : 5.0);
   if (name == "gfold") return gfold(N, p0 > 0 ? p0 : 48.0);
+  if (name == "cart_pole_eq") return cart_pole(N, p0 > 0 ? p0 : 5.0, false);
+  if (name == "flywheel_eq") return flywheel(N, p0 > 0 ? p0 : 5.0, false);
+  if (name == "chained_rosenbrock") return chained_rosenbrock(N);
   return small_problem(name, p0, p1);
 }
 

@@ -23,14 +23,23 @@ assert have_reference(), "build oracle/_ref first: make -C oracle ref"
 EVAL_CASES = [("cart_pole", 8, 0.0, 0.0), ("cart_pole", 40, 0.0, 0.0),
               ("flywheel", 50, 0.0, 0.0), ("rosenbrock_cubic_line", 0, 0.3, 0.7),
               ("rosenbrock_disk", 0, -0.5, 1.2), ("wachter_biegler", 0, 0.0, 0.0),
-              ("gfold", 12, 0.0, 0.0)]
+              ("gfold", 12, 0.0, 0.0),
+              # Newton / SQP branches (no inequality constraints)
+              ("chained_rosenbrock", 30, 0.0, 0.0),
+              ("cart_pole_eq", 12, 0.0, 0.0),
+              ("min_distance_line", 0, 0.0, 0.0)]
 SOLVE_CASES = [("flywheel", 50, 0.0, 0.0), ("cart_pole", 50, 0.0, 0.0),
                ("lp_maximize", 0, 0.0, 0.0), ("quartic", 0, 0.0, 0.0),
                ("qp_inequality_2d", 0, 0.0, 0.0),
                ("wachter_biegler", 0, 0.0, 0.0),
                ("rosenbrock_disk", 0, -0.5, 1.2),
                ("rosenbrock_cubic_line", 0, 0.3, 0.7),
-               ("gfold", 20, 0.0, 0.0)]
+               ("gfold", 20, 0.0, 0.0),
+               ("chained_rosenbrock", 50, 0.0, 0.0),
+               ("flywheel_eq", 50, 0.0, 0.0),
+               ("cart_pole_eq", 30, 0.0, 0.0),
+               ("eq_maximize_xy", 0, 0.0, 0.0),
+               ("min_distance_line", 0, 0.0, 0.0)]
 
 
 def eval_case(name, N, p0, p1):

@@ -284,7 +284,22 @@ KNOWN = [("lp_maximize", "SUCCESS", (375, 250), 1e-6),
          ("conflicting_bounds", "GLOBALLY_INFEASIBLE", None, 0),
          ("locally_infeasible_ineq", "LOCALLY_INFEASIBLE", None, 0),
          ("nonfinite_ineq", "NONFINITE_INITIAL_GUESS", None, 0),
-         ("nonfinite_ineq_jacobian", "NONFINITE_INITIAL_GUESS", None, 0)]
+         ("nonfinite_ineq_jacobian", "NONFINITE_INITIAL_GUESS", None, 0),
+         # Newton and SQP branches (quadratic_problem_test.cpp:15-161,
+         # nonlinear_problem_test.cpp:120-143, exit_status_test.cpp:17-194)
+         ("unconstrained_1d", "SUCCESS", (3,), 1e-6),
+         ("unconstrained_2d", "SUCCESS", (0, 0), 1e-6),
+         ("eq_maximize_xy", "SUCCESS", (18, 6), 1e-5),
+         ("eq_pin_2d", "SUCCESS", (3, 3), 1e-5),
+         ("min_distance_line", "SUCCESS", (2.5, 2.5), 1e-2),
+         ("min_x_squared", "SUCCESS", (0,), 1e-6),
+         ("too_few_dofs", "TOO_FEW_DOFS", None, 0),
+         ("locally_infeasible_eq", "LOCALLY_INFEASIBLE", None, 0),
+         ("nonfinite_cost", "NONFINITE_INITIAL_GUESS", None, 0),
+         ("nonfinite_gradient", "NONFINITE_INITIAL_GUESS", None, 0),
+         ("nonfinite_eq", "NONFINITE_INITIAL_GUESS", None, 0),
+         ("nonfinite_eq_jacobian", "NONFINITE_INITIAL_GUESS", None, 0),
+         ("diverging", "DIVERGING_ITERATES", None, 0)]
 
 
 @pytest.mark.parametrize("name,status,expect,tol", KNOWN)
@@ -407,6 +422,130 @@ def test_iteration_callbacks_and_off_nominal_exits():
     Q.set_timeout(0.0)
     assert sb.EXIT_STATUS[Q.solve()] == "TIMEOUT"
     assert len(Q.trace()) == 1
+    Q.close()
+
+
+@pytest.mark.parametrize("name,N,kind,tol,prefix", [
+    ("chained_rosenbrock", 50, "NEWTON", 1e-9, None),
+    # a long walk over a non-convex landscape: rounding differences grow by
+    # about one decade per ten iterations (1e-14 → 1e-8 over the first 60)
+    ("chained_rosenbrock", 2000, "NEWTON", 1e-9, 30),
+    ("flywheel_eq", 50, "SQP", 1e-10, None),
+    ("flywheel_eq", 400, "SQP", 1e-10, None),
+    # cart-pole's sensitivity floor ("Parity"): 3e-9 after the first
+    # step, 1e-4 after six; the decisions and the end point still agree
+    ("cart_pole_eq", 30, "SQP", 1e-5, 4),
+    ("min_distance_line", 0, "SQP", 1e-10, None)])
+def test_newton_and_sqp_branches_match_oracle(name, N, kind, tol, prefix):
+    """Problems without inequality constraints take the reference's SQP loop
+    (sqp.hpp:91-596), those without any constraint its Newton loop
+    (newton.hpp:50-290); both run on the same device kernels as the
+    interior-point method. Same decisions and iterates as the oracle's
+    restatement along the solve, and the golden solution where one is
+    committed."""
+    P = sb.Problem(name, N)
+    st = P.solve(keep_iterates=True)
+    assert P.solver_kind() == kind
+    tr = P.trace()
+    perm = None
+    if P.n + P.me > 1:
+        D = P.open_device(); D.analyze(); perm = D.permutation(); P.close_device()
+    O = OracleProblem(name, N)
+    so = O.solve(perm=perm, force_sparse=1)
+    to = O.trace()
+    assert sb.EXIT_STATUS[st] == EXIT_STATUS[so] == "SUCCESS"
+    if prefix is None or name == "cart_pole_eq":
+        assert len(tr) == len(to)
+    for k, (a, b) in enumerate(zip(tr, to)):
+        if name == "cart_pole_eq":
+            assert a.factorizations == b.factorizations and a.delta == b.delta
+        if prefix is not None and k >= prefix:
+            continue
+        assert a.factorizations == b.factorizations
+        assert a.delta == b.delta and a.alpha == b.alpha
+        # min_distance_line: the constraint is linear, so after the first full
+        # step its residual is rounding noise and "did the violation grow?"
+        # (the second-order-correction trigger, sqp.hpp:379) is a coin toss
+        assert a.trials == b.trials or name == "min_distance_line"
+        assert a.mu == b.mu == tr[0].mu          # no barrier update off the IPM
+        assert rel(a.x, b.x) < tol
+        if P.me:
+            assert rel(a.y, b.y) < 100 * tol
+    path = os.path.join(GOLDEN, f"solve_{name}_{N}.npz")
+    if os.path.exists(path):
+        g = np.load(path)
+        assert len(tr) == int(g["iterations"])
+        np.testing.assert_allclose(P.solution()[0], g["x"], atol=1e-6)
+    P.close(); O.close()
+
+
+def test_second_order_correction_without_inequalities():
+    """The corrected c_i − s array is empty when there are no inequality
+    constraints; the correction solves must still rebuild the right-hand side
+    instead of reusing the forward substitution the factorisation carried."""
+    name, N = "cart_pole_eq", 30
+    P, O = sb.Problem(name, N), OracleProblem(name, N)
+    O.eval_setup()
+    d_f, d_ce, d_ci = O.scaling()
+    D = P.open_device()
+    D.set_scaling(d_f, d_ce, d_ci)
+    x, e = O.initial_guess(), np.zeros(0)
+    D.set_iterate(x, e, np.zeros(P.me), e)
+    D.eval_current(1)
+    D.analyze()
+    mu = 0.1 * d_f
+
+    def corrections(fused):
+        if fused:
+            D.prepare_rhs(mu)
+        D.factor(1e-4, 1e-10, True)
+        D.solve(mu, 0.99)
+        D.trial(1.0, 1.0)
+        D.soc_begin()
+        out = []
+        for _ in range(2):
+            si = D.soc_iterate(mu, 0.99, 1.0)
+            out.append(D.trial(si.alpha_max, si.alpha_max, 1, 0).ce_l1)
+        return out
+    plain, fused = corrections(False), corrections(True)
+    assert plain == fused
+    # 99.4 → 96.4 → 162.4 on the reference's algebra (checked against a dense
+    # solve of the same system while writing the test)
+    assert plain[0] == pytest.approx(96.368, rel=1e-4)
+    assert plain[1] == pytest.approx(162.43, rel=1e-4)
+    P.close_device(); P.close(); O.close()
+
+
+def test_exit_statuses_on_the_newton_branch():
+    """exit_status_test.cpp:17-50 (callbacks), :196-234 (max iterations,
+    timeout) as the reference runs them: on minimize(x²)."""
+    P = sb.Problem("min_x_squared", 0)
+    P.add_callback(stop_at=-1)
+    assert sb.EXIT_STATUS[P.solve()] == "SUCCESS"
+    assert P.solver_kind() == "NEWTON"
+    assert P.solution()[0][0] == pytest.approx(0.0, abs=1e-6)
+    log, _ = P.callback_log()
+    # IterationInfo of the Newton loop: x and g filled, no s / y / z
+    assert int(log[0][1]) == 1 and int(log[0][7]) == 1
+    assert int(log[0][3]) == int(log[0][4]) == int(log[0][5]) == 0
+    P.add_callback(stop_at=0)
+    P.set_guess([1.0])                       # the reference test re-seeds x too
+    assert sb.EXIT_STATUS[P.solve()] == "CALLBACK_REQUESTED_STOP"
+    P.clear_callbacks()
+    P.add_callback(stop_at=-1)
+    P.set_guess([1.0])
+    assert sb.EXIT_STATUS[P.solve()] == "SUCCESS"
+    P.add_callback(stop_at=0, persistent=True)
+    P.clear_callbacks()
+    P.set_guess([1.0])
+    assert sb.EXIT_STATUS[P.solve()] == "CALLBACK_REQUESTED_STOP"
+    P.close()
+
+    Q = sb.Problem("min_x_squared", 0)
+    assert sb.EXIT_STATUS[Q.solve(max_iterations=0)] == "MAX_ITERATIONS_EXCEEDED"
+    Q.set_guess([1.0])
+    Q.set_timeout(0.0)
+    assert sb.EXIT_STATUS[Q.solve()] == "TIMEOUT"
     Q.close()
 
 

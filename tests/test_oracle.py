@@ -24,6 +24,20 @@ KNOWN = [
     ("locally_infeasible_ineq", "LOCALLY_INFEASIBLE", None, 0),    # exit_status_test.cpp:97-117
     ("nonfinite_ineq", "NONFINITE_INITIAL_GUESS", None, 0),        # :160-166
     ("nonfinite_ineq_jacobian", "NONFINITE_INITIAL_GUESS", None, 0),  # :169-175
+    # the Newton (problem.hpp:335) and SQP (:403) branches
+    ("unconstrained_1d", "SUCCESS", (3,), 1e-6),             # quadratic_problem_test.cpp:15-34
+    ("unconstrained_2d", "SUCCESS", (0, 0), 1e-6),           # :36-58
+    ("eq_maximize_xy", "SUCCESS", (18, 6), 1e-5),            # :80-141
+    ("eq_pin_2d", "SUCCESS", (3, 3), 1e-5),                  # :143-161
+    ("min_distance_line", "SUCCESS", (2.5, 2.5), 1e-2),      # nonlinear_problem_test.cpp:120-143
+    ("min_x_squared", "SUCCESS", (0,), 1e-6),                # exit_status_test.cpp:17-27
+    ("too_few_dofs", "TOO_FEW_DOFS", None, 0),               # :52-72
+    ("locally_infeasible_eq", "LOCALLY_INFEASIBLE", None, 0),  # :78-95
+    ("nonfinite_cost", "NONFINITE_INITIAL_GUESS", None, 0),  # :124-130
+    ("nonfinite_gradient", "NONFINITE_INITIAL_GUESS", None, 0),  # :133-139
+    ("nonfinite_eq", "NONFINITE_INITIAL_GUESS", None, 0),    # :142-148
+    ("nonfinite_eq_jacobian", "NONFINITE_INITIAL_GUESS", None, 0),  # :151-157
+    ("diverging", "DIVERGING_ITERATES", None, 0),            # :178-194
 ]
 
 
