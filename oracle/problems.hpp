@@ -224,6 +224,16 @@ std::unique_ptr<Problem<B>> small_problem(const std::string& name, double p0,
   } else if (name == "nonfinite_ineq_jacobian") {  // :169-175
     V x = P->decision_variable();
     P->subject_to_ineq(ge1(sqrt(x), V{1}));
+  } else if (name == "mishra_bird") {  // multistart_test.cpp:17-55
+    V x = P->decision_variable();
+    V y = P->decision_variable();
+    x.set_value(p0);
+    y.set_value(p1);
+    V J = sin(y) * exp(pow(V{1} - cos(x), 2.0)) +
+          cos(x) * exp(pow(V{1} - sin(y), 2.0)) + pow(x - y, 2.0);
+    P->minimize(J);
+    P->subject_to_ineq(
+        le1(pow(x + V{5}, 2.0) + pow(y + V{5}, 2.0), V{25}));
   } else if (name == "unconstrained_1d") {  // quadratic_problem_test.cpp:15-34
     V x = P->decision_variable();
     x.set_value(2);

@@ -175,6 +175,35 @@ def comm_unique_id() -> bytes:
     return buf.raw
 
 
+def multistart(name, N, p0, p1=None, perturb=0.0, max_concurrency=0,
+               max_iterations=5000, device=0, n_vars=None):
+    """slp::multistart (reference multistart.hpp:44-73) over len(p0) starts of
+    a named problem, every start on its own host thread and device stream.
+    Returns dict(status, cost, index, x, wall_s, starts=[(status, cost,
+    iterations, seconds), …])."""
+    p0 = np.ascontiguousarray(p0, dtype=np.float64)
+    p1 = np.zeros_like(p0) if p1 is None else \
+        np.ascontiguousarray(p1, dtype=np.float64)
+    count = len(p0)
+    if n_vars is None:
+        P = Problem(name, N, float(p0[0]), float(p1[0]))
+        n_vars = P.n
+        P.close()
+    best, best_x = np.zeros(3), np.zeros(n_vars)
+    per = np.zeros(4 * count)
+    wall = host_lib().slpbh_multistart(
+        name.encode(), N, count, _d(p0), _d(p1), float(perturb),
+        int(max_concurrency), int(max_iterations), int(device), _d(best),
+        _d(best_x), n_vars, _d(per))
+    if wall < 0:
+        raise DeviceError("slpbh_multistart: a device call failed")
+    per = per.reshape(count, 4)
+    return dict(status=int(best[0]), cost=float(best[1]), index=int(best[2]),
+                x=best_x, wall_s=wall,
+                starts=[(int(r[0]), float(r[1]), int(r[2]), float(r[3]))
+                        for r in per])
+
+
 def host_lib() -> C.CDLL:
     global _host
     if _host is None:
@@ -203,6 +232,10 @@ def host_lib() -> C.CDLL:
         L.slpbh_solution.argtypes = [vp, _dp, _dp, _dp, _dp]
         L.slpbh_loop_seconds.restype = C.c_double
         L.slpbh_loop_seconds.argtypes = [vp]
+        L.slpbh_multistart.restype = C.c_double
+        L.slpbh_multistart.argtypes = [C.c_char_p, C.c_int, C.c_int, _dp, _dp,
+                                       C.c_double, C.c_int, C.c_int, C.c_int,
+                                       _dp, _dp, C.c_int, _dp]
         L.slpbh_solver_kind.restype = C.c_int
         L.slpbh_solver_kind.argtypes = [vp]
         L.slpbh_set_flush_l2.argtypes = [vp, C.c_int]

@@ -13,6 +13,7 @@
 #include <vector>
 
 #include "problems/problems.hpp"
+#include "sleipnir/optimization/multistart.hpp"
 
 namespace {
 
@@ -107,6 +108,91 @@ int slpbh_solve(void* h, double tolerance, int max_iterations, int feasible_ipm,
     return -100;
   }
   return hd->last_status;
+}
+
+/// slp::multistart (reference multistart.hpp:44-73) over `count` starts of a
+/// named problem, each built and solved on its own thread through its own
+/// device handle. Start i is make_problem(name, N, p0[i], p1[i]) with its
+/// initial guess shifted by perturb·i·sin(1 + j) in component j (0 keeps the
+/// builder's guess). best[3] = status, cost, winning index; best_x = its
+/// decision variables (x_cap doubles at most); per_start[4·i..] = status, cost,
+/// iterations, seconds inside solve(). Returns the wall time of the whole
+/// multistart call in seconds, or −1 when a device call failed.
+double slpbh_multistart(const char* name, int N, int count, const double* p0,
+                        const double* p1, double perturb, int max_concurrency,
+                        int max_iterations, int device, double* best,
+                        double* best_x, int x_cap, double* per_start) {
+  struct Start {
+    int index;
+    double p0, p1;
+  };
+  struct Vars {
+    int index = 0;
+    int iterations = 0;
+    double seconds = 0.0;
+    std::vector<double> x;
+  };
+  const std::string problem_name{name};
+  std::vector<Start> starts(count);
+  for (int i = 0; i < count; ++i) starts[i] = {i, p0[i], p1[i]};
+  using Result = slp::MultistartResult<double, Vars>;
+  const std::function<Result(const Start&)> solve_one =
+      [&](const Start& st) -> Result {
+    auto problem = slpb_problems::make_problem(problem_name, N, st.p0, st.p1);
+    auto& vars = problem->decision_variables();
+    if (perturb != 0.0) {
+      for (size_t j = 0; j < vars.size(); ++j) {
+        vars[j].set_value(vars[j].value() +
+                          perturb * st.index * std::sin(1.0 + double(j)));
+      }
+    }
+    slp::Options opt;
+    opt.max_iterations = max_iterations;
+    slp::DeviceOptions dopt;
+    dopt.device = device;
+    const auto t0 = std::chrono::steady_clock::now();
+    const slp::ExitStatus status = problem->solve(opt, dopt);
+    Vars out;
+    out.index = st.index;
+    out.seconds = std::chrono::duration<double>(
+                      std::chrono::steady_clock::now() - t0)
+                      .count();
+    out.iterations = static_cast<int>(problem->last_trace().rows.size());
+    out.x.resize(vars.size());
+    for (size_t j = 0; j < vars.size(); ++j) out.x[j] = vars[j].value();
+    auto cost = problem->cost();
+    return {status, cost ? cost->value() : 0.0, std::move(out)};
+  };
+  // multistart() is written over DecisionVariables for both the guess and the
+  // result; adapt by carrying the start inside Vars
+  std::vector<Vars> guesses(count);
+  for (int i = 0; i < count; ++i) guesses[i].index = i;
+  const std::function<Result(const Vars&)> solve =
+      [&](const Vars& g) { return solve_one(starts[g.index]); };
+  std::vector<Result> all;
+  const auto t0 = std::chrono::steady_clock::now();
+  try {
+    const Result win = slp::multistart<double, Vars>(
+        solve, std::span<const Vars>{guesses}, max_concurrency, &all);
+    const double wall = std::chrono::duration<double>(
+                            std::chrono::steady_clock::now() - t0)
+                            .count();
+    best[0] = static_cast<double>(static_cast<int>(win.status));
+    best[1] = win.cost;
+    best[2] = win.variables.index;
+    for (size_t j = 0; j < win.variables.x.size() && int(j) < x_cap; ++j) {
+      best_x[j] = win.variables.x[j];
+    }
+    for (int i = 0; i < count; ++i) {
+      per_start[4 * i + 0] = static_cast<double>(static_cast<int>(all[i].status));
+      per_start[4 * i + 1] = all[i].cost;
+      per_start[4 * i + 2] = all[i].variables.iterations;
+      per_start[4 * i + 3] = all[i].variables.seconds;
+    }
+    return wall;
+  } catch (const std::exception&) {
+    return -1.0;
+  }
 }
 
 /// Benchmark hygiene: evict the device L2 before every iteration of the next

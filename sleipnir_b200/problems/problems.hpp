@@ -386,6 +386,16 @@ inline std::unique_ptr<slp::Problem<double>> small_problem(
   } else if (name == "nonfinite_ineq_jacobian") {
     auto x = problem.decision_variable();
     problem.subject_to(sqrt(x) > T(1));
+  } else if (name == "mishra_bird") {  // multistart_test.cpp:17-55
+    auto x = problem.decision_variable();
+    auto y = problem.decision_variable();
+    x.set_value(T(p0));
+    y.set_value(T(p1));
+    slp::Variable<double> J =
+        sin(y) * exp(pow(T(1) - cos(x), T(2))) +
+        cos(x) * exp(pow(T(1) - sin(y), T(2))) + pow(x - y, T(2));
+    problem.minimize(J);
+    problem.subject_to(pow(x + T(5), T(2)) + pow(y + T(5), T(2)) < T(25));
   } else if (name == "unconstrained_1d") {
     auto x = problem.decision_variable();
     x.set_value(T(2));

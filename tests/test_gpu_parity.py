@@ -549,6 +549,44 @@ def test_exit_statuses_on_the_newton_branch():
     Q.close()
 
 
+def test_multistart_mishra_bird_on_gpu():
+    """multistart_test.cpp:17-55 through slp::multistart on the device path:
+    two starts on two host threads and two CUDA streams; the lower cost wins."""
+    r = sb.multistart("mishra_bird", 0, [-3.0, -3.0], [-8.0, -1.5])
+    assert sb.EXIT_STATUS[r["status"]] == "SUCCESS" and r["index"] == 1
+    np.testing.assert_allclose(r["x"], (-3.13024680, -1.58214218), atol=1e-8)
+    assert [sb.EXIT_STATUS[s[0]] for s in r["starts"]] == ["SUCCESS"] * 2
+    assert r["starts"][0][1] == pytest.approx(-87.3108827, abs=1e-6)
+    assert r["starts"][1][1] == pytest.approx(-106.7645367, abs=1e-6)
+
+
+def test_concurrent_starts_do_not_disturb_each_other():
+    """Eight cart-pole solves at once on one GPU (own handle, stream and
+    expression pool each; kernels of different starts overlap on the SMs):
+    every start must reproduce the solve that runs alone, bit for bit, and
+    perturbed starts must still be solved independently."""
+    N = 60
+    P = sb.Problem("cart_pole", N)
+    st = P.solve()
+    x_alone, iters_alone = P.solution()[0], len(P.trace())
+    P.close()
+    r = sb.multistart("cart_pole", N, [5.0] * 8)
+    assert all(s[0] == st and s[2] == iters_alone for s in r["starts"])
+    assert len({s[1] for s in r["starts"]}) == 1          # identical costs
+    np.testing.assert_array_equal(r["x"], x_alone)
+    # the sequential wave (max_concurrency = 1) gives the same answer
+    r1 = sb.multistart("cart_pole", N, [5.0] * 3, max_concurrency=1)
+    np.testing.assert_array_equal(r1["x"], x_alone)
+    # different horizons per start: 8 different problems in flight
+    Ts = [4.0 + 0.25 * i for i in range(8)]
+    r2 = sb.multistart("cart_pole", N, Ts)
+    for T, s in zip(Ts, r2["starts"]):
+        Q = sb.Problem("cart_pole", N, T)
+        sq = Q.solve()
+        assert s[0] == sq and s[2] == len(Q.trace())
+        Q.close()
+
+
 def test_flywheel_trajectory_matches_oracle():
     """Well-conditioned problem: same decisions and iterates to 1e-10 along the
     whole solve (same permutation on both sides)."""

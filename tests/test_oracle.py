@@ -52,6 +52,21 @@ def test_known_answers(name, status, expect, tol):
     P.close()
 
 
+def test_multistart_mishra_bird():
+    # multistart_test.cpp:17-55: two starts, the one with the lower cost wins
+    runs = []
+    for guess in ((-3.0, -8.0), (-3.0, -1.5)):
+        P = OracleProblem("mishra_bird", 0, *guess)
+        st = P.solve()
+        x, *_ = P.solution()
+        J = (np.sin(x[1]) * np.exp((1 - np.cos(x[0])) ** 2) +
+             np.cos(x[0]) * np.exp((1 - np.sin(x[1])) ** 2) + (x[0] - x[1]) ** 2)
+        runs.append((EXIT_STATUS[st] != "SUCCESS", J, x))
+        P.close()
+    _, _, best = min(runs, key=lambda r: (r[0], r[1]))
+    np.testing.assert_allclose(best, (-3.13024680, -1.58214218), atol=1e-8)
+
+
 def test_rosenbrock_disk_grid():
     # nonlinear_problem_test.cpp:84-118 sweeps a 30x30 grid of starts; a coarse
     # sub-grid keeps the CPU tier fast.
