@@ -2,7 +2,7 @@
 """Benchmark of the interior-point Newton step (BASELINE.json metric).
 
     python bench.py [--gpus N] [--steps K] [--warmup W] [--impl reference]
-                    [--horizon 5000] [--no-cpu-baseline]
+                    [--horizon 5000] [--no-cpu-baseline] [--multistart B]
 
 A *step* is one Newton iteration of the interior-point loop
 (reference: include/sleipnir/optimization/solver/interior_point.hpp:382-863) on
@@ -175,6 +175,9 @@ def main():
     ap.add_argument("--no-cpu-baseline", action="store_true")
     ap.add_argument("--no-clock-sampler", action="store_true",
                     help="experiments only: do not poll NVML during the run")
+    ap.add_argument("--multistart", type=int, default=8,
+                    help="also time B concurrent solves of the workload on each "
+                         "GPU through slp::multistart (0: skip)")
     ap.add_argument("--shard", action="store_true",
                     help="N > 1: ONE solve sharded over the GPUs (derivative "
                          "sweep split over the ranks, one NCCL all-gather per "
@@ -300,6 +303,15 @@ def main():
         dt2 = max_over_ranks(dt2)
         total_s = max_over_ranks(total_s)
         cnt2, phases = P2.counters(), P2.phase_seconds()
+        # (3) the library's data-parallel axis: B independent solves in flight
+        #     on this GPU (slp::multistart, one host thread + stream each).
+        ms = None
+        if args.multistart > 1 and not shard:
+            if world > 1:
+                dist.barrier()
+            ms = sb.multistart("cart_pole", N, [5.0] * args.multistart,
+                               device=local_rank, n_vars=5 * N + 4)
+            ms["wall_s"] = max_over_ranks(ms["wall_s"])
     replicas = 1 if shard else world   # independent solves running side by side
     rate = replicas * k / dt
 
@@ -389,6 +401,17 @@ def main():
             "h2d_bytes_per_step": cnt2["h2d_bytes"] / len(tr2),
             "d2h_bytes_per_step": cnt2["d2h_bytes"] / len(tr2),
             "solve_call_s": total_s},
+        "multistart": None if ms is None else {
+            "value": world * sum(s_[2] for s_ in ms["starts"]) / ms["wall_s"],
+            "unit": UNIT, "starts_per_gpu": args.multistart,
+            "wall_s": ms["wall_s"],
+            "exit_statuses": sorted({sb.EXIT_STATUS[s_[0]] for s_ in ms["starts"]}),
+            "what": "slp::multistart (reference multistart.hpp:44-73): that many "
+                    "independent Problem::solve() calls of the same workload in "
+                    "flight per GPU, each on its own host thread, device handle "
+                    "and CUDA stream, host setup included; total iterations ÷ "
+                    "wall time of the call. One solve is latency-bound, so "
+                    "concurrent solves overlap on the SMs"},
         "gpu_launches": int(cnt["kernel_launches"] * k / iters),
         "clocks": clk.summary(),
     }

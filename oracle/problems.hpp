@@ -12,6 +12,7 @@
 
 #include <algorithm>
 #include <cmath>
+#include <functional>
 #include <memory>
 #include <numbers>
 #include <stdexcept>
@@ -142,6 +143,227 @@ std::unique_ptr<Problem<B>> chained_rosenbrock_problem(int N) {
     J += V{100} * pow(y - pow(x, 2.0), 2.0) + pow(V{1} - x, 2.0);
   }
   problem->minimize(J);
+  return problem;
+}
+
+// ---- slp::OCP (optimization/ocp.hpp:49-414) ----------------------------------
+enum class OcpDynamics { EXPLICIT_ODE, DISCRETE };
+enum class OcpTimestep { FIXED, VARIABLE_SINGLE, VARIABLE };
+enum class OcpTranscription {
+  DIRECT_TRANSCRIPTION,
+  DIRECT_COLLOCATION,
+  SINGLE_SHOOTING
+};
+
+/// What the OCP constructor and its helpers add to a Problem, in the
+/// reference's order: U, then the time step(s), then X (ocp.hpp:141-178).
+template <class B>
+struct Ocp {
+  using M = Mat<B>;
+  using V = Var<B>;
+  using Dynamics =
+      std::function<M(const V& t, const M& x, const M& u, const V& dt)>;
+
+  Problem<B>& problem;
+  int num_steps;
+  Dynamics f;
+  OcpDynamics dynamics_type;
+  M X, U, DT;
+
+  Ocp(Problem<B>& p, int num_states, int num_inputs, double dt, int steps,
+      Dynamics dynamics, OcpDynamics dyn_type, OcpTimestep timestep,
+      OcpTranscription transcription)
+      : problem{p}, num_steps{steps}, f{std::move(dynamics)},
+        dynamics_type{dyn_type} {
+    const int samples = num_steps + 1;
+    U = problem.decision_variable(num_inputs, samples);
+    DT = M{1, samples};
+    if (timestep == OcpTimestep::FIXED) {
+      for (int i = 0; i < samples; ++i) DT(0, i) = V{dt};
+    } else if (timestep == OcpTimestep::VARIABLE_SINGLE) {
+      V single = problem.decision_variable();
+      single.set_value(dt);
+      for (int i = 0; i < samples; ++i) DT(0, i) = single;
+    } else {
+      DT = problem.decision_variable(1, samples);
+      for (int i = 0; i < samples; ++i) DT(0, i).set_value(dt);
+    }
+    if (transcription == OcpTranscription::SINGLE_SHOOTING) {
+      X = M{num_states, samples};
+      V time{0.0};
+      for (int i = 0; i < num_steps; ++i) {  // :394-414
+        X.set_block(0, i + 1, advance(X.col(i), U.col(i), time, DT(0, i)));
+        time += DT(0, i);
+      }
+    } else if (transcription == OcpTranscription::DIRECT_TRANSCRIPTION) {
+      X = problem.decision_variable(num_states, samples);
+      V time{0.0};
+      for (int i = 0; i < num_steps; ++i) {  // :371-392
+        problem.subject_to_eq(
+            eq(X.col(i + 1), advance(X.col(i), U.col(i), time, DT(0, i))));
+        time += DT(0, i);
+      }
+    } else {
+      X = problem.decision_variable(num_states, samples);
+      V time{0.0};
+      for (int i = 0; i < num_steps; ++i) {  // :334-369
+        V h = DT(0, i);
+        V t_begin = time;
+        V t_end = t_begin + h;
+        M x_begin = X.col(i), x_end = X.col(i + 1);
+        M u_begin = U.col(i), u_end = U.col(i + 1);
+        M xdot_begin = f(t_begin, x_begin, u_begin, h);
+        M xdot_end = f(t_end, x_end, u_end, h);
+        M xdot_c = V{-3.0} / (V{2.0} * h) * (x_begin - x_end) -
+                   V{0.25} * (xdot_begin + xdot_end);
+        V t_c = t_begin + V{0.5} * h;
+        M x_c = V{0.5} * (x_begin + x_end) +
+                h / V{8.0} * (xdot_begin - xdot_end);
+        M u_c = V{0.5} * (u_begin + u_end);
+        problem.subject_to_eq(eq(xdot_c, f(t_c, x_c, u_c, h)));
+        time += h;
+      }
+    }
+  }
+
+  M rk4(const M& x, const M& u, const V& t0, const V& dt) const {  // :322-332
+    V halfdt = dt * V{0.5};
+    M k1 = f(t0, x, u, dt);
+    M k2 = f(t0 + halfdt, x + k1 * halfdt, u, dt);
+    M k3 = f(t0 + halfdt, x + k2 * halfdt, u, dt);
+    M k4 = f(t0 + dt, x + k3 * dt, u, dt);
+    return x + (k1 + k2 * V{2.0} + k3 * V{2.0} + k4) * (dt / V{6.0});
+  }
+  M advance(const M& x, const M& u, const V& t, const V& dt) const {
+    return dynamics_type == OcpDynamics::EXPLICIT_ODE ? rk4(x, u, t, dt)
+                                                       : f(t, x, u, dt);
+  }
+  void lower_input_bound(const M& lo) {  // :242-254
+    for (int i = 0; i < num_steps + 1; ++i) {
+      problem.subject_to_ineq(ge(U.col(i), lo));
+    }
+  }
+  void upper_input_bound(const M& hi) {  // :256-268
+    for (int i = 0; i < num_steps + 1; ++i) {
+      problem.subject_to_ineq(le(U.col(i), hi));
+    }
+  }
+};
+
+/// flywheel_ocp_test.cpp:38-201 with dt = 5 s / N.
+template <class B>
+std::unique_ptr<Problem<B>> flywheel_ocp_problem(int N, int method,
+                                                 int discrete) {
+  using M = Mat<B>;
+  using V = Var<B>;
+  const double dt = 5.0 / N;
+  constexpr double A = -1.0, Bc = 1.0;
+  const double A_d = std::exp(A * dt);
+  const double B_d = (1.0 - A_d) * Bc;
+  auto problem = std::make_unique<Problem<B>>();
+  typename Ocp<B>::Dynamics f;
+  if (discrete) {
+    f = [=](const V&, const M& x, const M& u, const V&) {
+      return V{A_d} * x + V{B_d} * u;
+    };
+  } else {
+    f = [=](const V&, const M& x, const M& u, const V&) {
+      return V{A} * x + V{Bc} * u;
+    };
+  }
+  Ocp<B> ocp{*problem, 1, 1, dt, N, f,
+             discrete ? OcpDynamics::DISCRETE : OcpDynamics::EXPLICIT_ODE,
+             OcpTimestep::FIXED, static_cast<OcpTranscription>(method)};
+  problem->subject_to_eq(eq(ocp.X.col(0), V{0.0}));
+  ocp.upper_input_bound(M::constants(1, 1, {12.0}));
+  ocp.lower_input_bound(M::constants(1, 1, {-12.0}));
+  M r = M::constants(1, N + 1, std::vector<double>(N + 1, 10.0));
+  M J = (r - ocp.X) * (r - ocp.X).T();
+  problem->minimize(J(0, 0));
+  return problem;
+}
+
+/// cart_pole_ocp_test.cpp:29-86 with dt = 5 s / N: Hermite–Simpson
+/// collocation, one shared variable time step.
+template <class B>
+std::unique_ptr<Problem<B>> cart_pole_ocp_problem(int N) {
+  using M = Mat<B>;
+  using V = Var<B>;
+  const double dt = 5.0 / N;
+  const std::vector<double> x_initial{0.0, 0.0, 0.0, 0.0};
+  const std::vector<double> x_final{1.0, std::numbers::pi, 0.0, 0.0};
+  auto problem = std::make_unique<Problem<B>>();
+  Ocp<B> ocp{*problem, 4, 1, dt, N,
+             [](const V&, const M& x, const M& u, const V&) {
+               return cart_pole_dynamics<B>(x, u);
+             },
+             OcpDynamics::EXPLICIT_ODE, OcpTimestep::VARIABLE_SINGLE,
+             OcpTranscription::DIRECT_COLLOCATION};
+  for (int k = 0; k < N + 1; ++k) {
+    ocp.X(0, k).set_value(
+        std::lerp(x_initial[0], x_final[0], static_cast<double>(k) / N));
+    ocp.X(1, k).set_value(
+        std::lerp(x_initial[1], x_final[1], static_cast<double>(k) / N));
+  }
+  problem->subject_to_eq(eq(ocp.X.col(0), M::constants(4, 1, x_initial)));
+  problem->subject_to_eq(eq(ocp.X.col(N), M::constants(4, 1, x_final)));
+  for (int k = 0; k < N + 1; ++k) {
+    problem->subject_to_ineq(
+        bounds(V{0.0}, M{ocp.X(0, k)}, V{2.0}));
+  }
+  ocp.lower_input_bound(M::constants(1, 1, {-20.0}));
+  ocp.upper_input_bound(M::constants(1, 1, {20.0}));
+  V J{0.0};
+  for (int k = 0; k < N; ++k) {
+    M uu = ocp.U.col(k).T() * ocp.U.col(k);
+    J += uu(0, 0);
+  }
+  problem->minimize(J);
+  return problem;
+}
+
+/// differential_drive_ocp_test.cpp:25-66: minimum time, one shared variable
+/// time step, direct transcription.
+template <class B>
+std::unique_ptr<Problem<B>> differential_drive_ocp_problem(int N) {
+  using M = Mat<B>;
+  using V = Var<B>;
+  constexpr double trackwidth = 0.699, Kv_l = 3.02, Ka_l = 0.642;
+  constexpr double Kv_a = 1.382, Ka_a = 0.08495;
+  constexpr double A1 = -(Kv_l / Ka_l + Kv_a / Ka_a) / 2.0;
+  constexpr double A2 = -(Kv_l / Ka_l - Kv_a / Ka_a) / 2.0;
+  constexpr double B1 = 0.5 / Ka_l + 0.5 / Ka_a;
+  constexpr double B2 = 0.5 / Ka_l - 0.5 / Ka_a;
+  constexpr double min_timestep = 0.05;
+  auto problem = std::make_unique<Problem<B>>();
+  Ocp<B> ocp{*problem, 5, 2, min_timestep, N,
+             [=](const V&, const M& x, const M& u, const V&) {
+               M Am = M::constants(2, 2, {A1, A2, A2, A1});
+               M Bm = M::constants(2, 2, {B1, B2, B2, B1});
+               M xdot{5, 1};
+               V v = (x[3] + x[4]) / V{2.0};
+               xdot[0] = v * cos(x[2]);
+               xdot[1] = v * sin(x[2]);
+               xdot[2] = (x[4] - x[3]) / V{trackwidth};
+               xdot.set_block(3, 0, Am * x.segment(3, 2) + Bm * u);
+               return xdot;
+             },
+             OcpDynamics::EXPLICIT_ODE, OcpTimestep::VARIABLE_SINGLE,
+             OcpTranscription::DIRECT_TRANSCRIPTION};
+  for (int i = 0; i < N + 1; ++i) {
+    ocp.X(0, i).set_value(static_cast<double>(i) / (N + 1));
+    ocp.X(1, i).set_value(static_cast<double>(i) / (N + 1));
+  }
+  problem->subject_to_eq(
+      eq(ocp.X.col(0), M::constants(5, 1, {0.0, 0.0, 0.0, 0.0, 0.0})));
+  problem->subject_to_eq(
+      eq(ocp.X.col(N), M::constants(5, 1, {1.0, 1.0, 0.0, 0.0, 0.0})));
+  ocp.lower_input_bound(M::constants(2, 1, {-12.0, -12.0}));
+  ocp.upper_input_bound(M::constants(2, 1, {12.0, 12.0}));
+  problem->subject_to_ineq(ge(ocp.DT, V{min_timestep}));
+  problem->subject_to_ineq(le(ocp.DT, V{3.0}));
+  M J = ocp.DT * M::constants(N + 1, 1, std::vector<double>(N + 1, 1.0));
+  problem->minimize(J(0, 0));
   return problem;
 }
 
@@ -494,6 +716,18 @@ std::unique_ptr<Problem<B>> make_problem(const std::string& name, int N,
     return flywheel_problem<B>(N, p0 > 0 ? p0 : 5.0, false);
   }
   if (name == "chained_rosenbrock") return chained_rosenbrock_problem<B>(N);
+  if (name == "flywheel_ocp") {
+    return flywheel_ocp_problem<B>(N, static_cast<int>(p0),
+                                   static_cast<int>(p1));
+  }
+  // the transcription variants of the reference's flywheel OCP test by name
+  if (name == "flywheel_ocp_collocation") return flywheel_ocp_problem<B>(N, 1, false);
+  if (name == "flywheel_ocp_shooting") return flywheel_ocp_problem<B>(N, 2, false);
+  if (name == "flywheel_ocp_discrete") return flywheel_ocp_problem<B>(N, 0, true);
+  if (name == "cart_pole_ocp") return cart_pole_ocp_problem<B>(N);
+  if (name == "differential_drive_ocp") {
+    return differential_drive_ocp_problem<B>(N);
+  }
   return small_problem<B>(name, p0, p1);
 }
 

@@ -281,6 +281,8 @@ std::vector<Var<B>> ge(const Var<B>& l, const Mat<B>& r) {
   return out;
 }
 template <class B>
+std::vector<Var<B>> le(const Mat<B>& l, const Mat<B>& r) { return eq(r, l); }
+template <class B>
 std::vector<Var<B>> le(const Mat<B>& l, const Var<B>& r) { return ge(r, l); }
 template <class B>
 std::vector<Var<B>> le(const Var<B>& l, const Mat<B>& r) { return ge(r, l); }

@@ -76,6 +76,8 @@ template <typename Scalar>
 class Problem {
  public:
   Problem() = default;
+  /// OCP derives from Problem and is handed around as a Problem.
+  virtual ~Problem() = default;
 
   /// Creates a decision variable in the optimization problem.
   [[nodiscard]] Variable<Scalar> decision_variable() {

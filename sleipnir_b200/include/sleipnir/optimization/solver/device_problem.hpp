@@ -169,6 +169,19 @@ class Flattener {
     remap(F.leaf_x);
     remap(F.leaf_y);
     remap(F.leaf_z);
+    // A Variable that no Problem::decision_variable() created (the initial
+    // state of a single-shooting OCP, ocp.hpp:171-174) is a leaf nobody
+    // differentiates with respect to or moves during the solve: the device
+    // sees it as a constant holding its current value.
+    {
+      std::vector<uint8_t> is_leaf(count, 0);
+      for (const auto* list : {&F.leaf_x, &F.leaf_y, &F.leaf_z}) {
+        for (int32_t id : *list) is_leaf[id] = 1;
+      }
+      for (int32_t id = 0; id < count; ++id) {
+        if (F.op[id] == SLPB_OP_VAR && !is_leaf[id]) F.op[id] = SLPB_OP_CONST;
+      }
+    }
     return std::move(m_out);
   }
 

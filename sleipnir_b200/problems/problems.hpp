@@ -17,6 +17,7 @@
 
 #include <sleipnir/autodiff/variable.hpp>
 #include <sleipnir/autodiff/variable_matrix.hpp>
+#include <sleipnir/optimization/ocp.hpp>
 #include <sleipnir/optimization/problem.hpp>
 
 namespace slpb_problems {
@@ -311,6 +312,118 @@ inline std::unique_ptr<slp::Problem<double>> chained_rosenbrock(int N) {
   return problem;
 }
 
+// ---- the reference's OCP tests, written against slp::OCP ---------------------
+
+/// flywheel_ocp_test.cpp:38-201 with dt = 5 s / N. method: 0 direct
+/// transcription, 1 direct collocation, 2 single shooting.
+inline std::unique_ptr<slp::Problem<double>> flywheel_ocp(int N, int method,
+                                                          bool discrete) {
+  using T = double;
+  const std::chrono::duration<T> dt{T(5) / N};
+  constexpr T A(-1), B(1);
+  const T A_discrete = std::exp(A * dt.count());
+  const T B_discrete = (T(1) - A_discrete) * B;
+  slp::OCP<T>::Dynamics f;
+  if (discrete) {
+    f = [=](const slp::VariableMatrix<T>& x, const slp::VariableMatrix<T>& u) {
+      return A_discrete * x + B_discrete * u;
+    };
+  } else {
+    f = [=](const slp::VariableMatrix<T>& x, const slp::VariableMatrix<T>& u) {
+      return A * x + B * u;
+    };
+  }
+  auto problem = std::make_unique<slp::OCP<T>>(
+      1, 1, dt, N, f,
+      discrete ? slp::DynamicsType::DISCRETE : slp::DynamicsType::EXPLICIT_ODE,
+      slp::TimestepMethod::FIXED,
+      static_cast<slp::TranscriptionMethod>(method));
+  problem->constrain_initial_state(T(0));
+  problem->set_upper_input_bound(T(12));
+  problem->set_lower_input_bound(T(-12));
+  slp::Matrix<T> r_mat{1, N + 1};
+  for (int k = 0; k < N + 1; ++k) r_mat(0, k) = 10.0;
+  problem->minimize((r_mat - problem->X()) * (r_mat - problem->X()).T());
+  return problem;
+}
+
+/// cart_pole_ocp_test.cpp:29-86 with dt = 5 s / N.
+inline std::unique_ptr<slp::Problem<double>> cart_pole_ocp(int N) {
+  using T = double;
+  const std::chrono::duration<T> dt{T(5) / N};
+  constexpr T u_max(20), d_max(2);
+  const slp::Matrix<T> x_initial{{0.0}, {0.0}, {0.0}, {0.0}};
+  const slp::Matrix<T> x_final{{1.0}, {std::numbers::pi}, {0.0}, {0.0}};
+  auto problem = std::make_unique<slp::OCP<T>>(
+      4, 1, dt, N, slp::OCP<T>::Dynamics{cart_pole_dynamics},
+      slp::DynamicsType::EXPLICIT_ODE, slp::TimestepMethod::VARIABLE_SINGLE,
+      slp::TranscriptionMethod::DIRECT_COLLOCATION);
+  auto& X = problem->X();
+  for (int k = 0; k < N + 1; ++k) {
+    X[0, k].set_value(std::lerp(x_initial(0, 0), x_final(0, 0), T(k) / T(N)));
+    X[1, k].set_value(std::lerp(x_initial(1, 0), x_final(1, 0), T(k) / T(N)));
+  }
+  problem->constrain_initial_state(x_initial);
+  problem->constrain_final_state(x_final);
+  auto* raw = problem.get();
+  problem->for_each_step([&](const slp::VariableMatrix<T>& x,
+                             const slp::VariableMatrix<T>&) {
+    raw->subject_to(slp::bounds(T(0), x[0], d_max));
+  });
+  problem->set_lower_input_bound(-u_max);
+  problem->set_upper_input_bound(u_max);
+  auto& U = problem->U();
+  slp::Variable<T> J = T(0);
+  for (int k = 0; k < N; ++k) J += U.col(k).T() * U.col(k);
+  problem->minimize(J);
+  return problem;
+}
+
+/// differential_drive_ocp_test.cpp:25-66 (dynamics:
+/// test/include/differential_drive_util.hpp:16-61).
+inline std::unique_ptr<slp::Problem<double>> differential_drive_ocp(int N) {
+  using T = double;
+  constexpr T trackwidth = 0.699, Kv_linear = 3.02, Ka_linear = 0.642;
+  constexpr T Kv_angular = 1.382, Ka_angular = 0.08495;
+  constexpr T A1 = -(Kv_linear / Ka_linear + Kv_angular / Ka_angular) / T(2);
+  constexpr T A2 = -(Kv_linear / Ka_linear - Kv_angular / Ka_angular) / T(2);
+  constexpr T B1 = T(0.5) / Ka_linear + T(0.5) / Ka_angular;
+  constexpr T B2 = T(0.5) / Ka_linear - T(0.5) / Ka_angular;
+  constexpr std::chrono::duration<T> min_timestep{T(0.05)};
+  auto dynamics = [=](const slp::VariableMatrix<T>& x,
+                      const slp::VariableMatrix<T>& u) {
+    const slp::Matrix<T> A{{A1, A2}, {A2, A1}};
+    const slp::Matrix<T> B{{B1, B2}, {B2, B1}};
+    slp::VariableMatrix<T> xdot{5};
+    auto v = (x[3] + x[4]) / T(2);
+    xdot[0] = v * cos(x[2]);
+    xdot[1] = v * sin(x[2]);
+    xdot[2] = (x[4] - x[3]) / trackwidth;
+    xdot.segment(3, 2) = A * x.segment(3, 2) + B * u;
+    return xdot;
+  };
+  auto problem = std::make_unique<slp::OCP<T>>(
+      5, 2, min_timestep, N, slp::OCP<T>::Dynamics{dynamics},
+      slp::DynamicsType::EXPLICIT_ODE, slp::TimestepMethod::VARIABLE_SINGLE,
+      slp::TranscriptionMethod::DIRECT_TRANSCRIPTION);
+  for (int i = 0; i < N + 1; ++i) {
+    problem->X()[0, i].set_value(T(i) / T(N + 1));
+    problem->X()[1, i].set_value(T(i) / T(N + 1));
+  }
+  problem->constrain_initial_state(
+      slp::Matrix<T>{{0.0}, {0.0}, {0.0}, {0.0}, {0.0}});
+  problem->constrain_final_state(
+      slp::Matrix<T>{{1.0}, {1.0}, {0.0}, {0.0}, {0.0}});
+  problem->set_lower_input_bound(slp::Matrix<T>{{-12.0}, {-12.0}});
+  problem->set_upper_input_bound(slp::Matrix<T>{{12.0}, {12.0}});
+  problem->set_min_timestep(min_timestep);
+  problem->set_max_timestep(std::chrono::duration<T>{T(3)});
+  slp::Matrix<T> ones{N + 1, 1};
+  for (int i = 0; i < N + 1; ++i) ones(i, 0) = 1.0;
+  problem->minimize(problem->dt() * ones);
+  return problem;
+}
+
 inline std::unique_ptr<slp::Problem<double>> small_problem(
     const std::string& name, double p0, double p1) {
   using T = double;
@@ -472,6 +585,15 @@ inline std::unique_ptr<slp::Problem<double>> make_problem(
   if (name == "cart_pole_eq") return cart_pole(N, p0 > 0 ? p0 : 5.0, false);
   if (name == "flywheel_eq") return flywheel(N, p0 > 0 ? p0 : 5.0, false);
   if (name == "chained_rosenbrock") return chained_rosenbrock(N);
+  if (name == "flywheel_ocp") {
+    return flywheel_ocp(N, static_cast<int>(p0), p1 != 0.0);
+  }
+  // the transcription variants of the reference's flywheel OCP test by name
+  if (name == "flywheel_ocp_collocation") return flywheel_ocp(N, 1, false);
+  if (name == "flywheel_ocp_shooting") return flywheel_ocp(N, 2, false);
+  if (name == "flywheel_ocp_discrete") return flywheel_ocp(N, 0, true);
+  if (name == "cart_pole_ocp") return cart_pole_ocp(N);
+  if (name == "differential_drive_ocp") return differential_drive_ocp(N);
   return small_problem(name, p0, p1);
 }
 

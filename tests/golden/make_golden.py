@@ -27,7 +27,14 @@ EVAL_CASES = [("cart_pole", 8, 0.0, 0.0), ("cart_pole", 40, 0.0, 0.0),
               # Newton / SQP branches (no inequality constraints)
               ("chained_rosenbrock", 30, 0.0, 0.0),
               ("cart_pole_eq", 12, 0.0, 0.0),
-              ("min_distance_line", 0, 0.0, 0.0)]
+              ("min_distance_line", 0, 0.0, 0.0),
+              # slp::OCP front end (optimization/ocp.hpp)
+              ("flywheel_ocp", 30, 0.0, 0.0),
+              ("flywheel_ocp_collocation", 30, 0.0, 0.0),
+              ("flywheel_ocp_shooting", 12, 0.0, 0.0),
+              ("flywheel_ocp_discrete", 30, 0.0, 0.0),
+              ("cart_pole_ocp", 20, 0.0, 0.0),
+              ("differential_drive_ocp", 20, 0.0, 0.0)]
 SOLVE_CASES = [("flywheel", 50, 0.0, 0.0), ("cart_pole", 50, 0.0, 0.0),
                ("lp_maximize", 0, 0.0, 0.0), ("quartic", 0, 0.0, 0.0),
                ("qp_inequality_2d", 0, 0.0, 0.0),
@@ -39,7 +46,13 @@ SOLVE_CASES = [("flywheel", 50, 0.0, 0.0), ("cart_pole", 50, 0.0, 0.0),
                ("flywheel_eq", 50, 0.0, 0.0),
                ("cart_pole_eq", 30, 0.0, 0.0),
                ("eq_maximize_xy", 0, 0.0, 0.0),
-               ("min_distance_line", 0, 0.0, 0.0)]
+               ("min_distance_line", 0, 0.0, 0.0),
+               ("flywheel_ocp", 100, 0.0, 0.0),
+               ("flywheel_ocp_collocation", 100, 0.0, 0.0),
+               ("flywheel_ocp_shooting", 40, 0.0, 0.0),
+               ("flywheel_ocp_discrete", 100, 0.0, 0.0),
+               ("cart_pole_ocp", 100, 0.0, 0.0),
+               ("differential_drive_ocp", 50, 0.0, 0.0)]
 
 
 def eval_case(name, N, p0, p1):

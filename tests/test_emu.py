@@ -32,7 +32,16 @@ def test_interpreter_matches_reference_core_bit_for_bit(path):
     assert out["f"] == g["f"]
     np.testing.assert_array_equal(out["c_e"], g["c_e"])
     np.testing.assert_array_equal(out["c_i"], g["c_i"])
-    if name == "chained_rosenbrock":
+    # One decision variable shared by every step (the OCPs' single variable time
+    # step; the inputs of a single-shooting OCP) collects adjoint contributions
+    # from all the per-step clusters: they are added cluster by cluster, not in
+    # the reference's node order — a few entries differ in the last bit or two.
+    shared = name in ("cart_pole_ocp", "differential_drive_ocp",
+                      "flywheel_ocp_shooting")
+    if shared:
+        np.testing.assert_allclose(out["g"], g["g"], rtol=1e-14,
+                                   atol=1e-15 * np.abs(g["g"]).max())
+    elif name == "chained_rosenbrock":
         # A cost sum cut into terms adds each term's partial adjoint as a whole,
         # x + (c1 + c2), where the reference's sweep adds contribution by
         # contribution, (x + c1) + c2. The two agree bit for bit unless a leaf
@@ -46,7 +55,12 @@ def test_interpreter_matches_reference_core_bit_for_bit(path):
         _, _, cp, ri = E.pattern(which)
         np.testing.assert_array_equal(cp, g[nm + "_colptr"])
         np.testing.assert_array_equal(ri, g[nm + "_rowidx"])
-        np.testing.assert_array_equal(out[nm], g[nm + "_val"])
+        if shared:
+            np.testing.assert_allclose(
+                out[nm], g[nm + "_val"], rtol=1e-14,
+                atol=1e-15 * np.abs(g[nm + "_val"]).max(initial=0.0))
+        else:
+            np.testing.assert_array_equal(out[nm], g[nm + "_val"])
     E.close()
 
 

@@ -549,6 +549,61 @@ def test_exit_statuses_on_the_newton_branch():
     Q.close()
 
 
+@pytest.mark.parametrize("name,N", [
+    ("flywheel_ocp", 100), ("flywheel_ocp_collocation", 100),
+    ("flywheel_ocp_shooting", 40), ("flywheel_ocp_discrete", 100)])
+def test_ocp_flywheel_transcriptions(name, N):
+    """flywheel_ocp_test.cpp:38-201 through slp::OCP on the device path: direct
+    transcription (ODE + RK4, and the discrete map), Hermite–Simpson
+    collocation and single shooting of the same convex problem. Decision
+    variables: U (1 × N+1), then X (1 × N+1) unless shooting."""
+    P = sb.Problem(name, N)
+    assert sb.EXIT_STATUS[P.solve()] == "SUCCESS"
+    x = P.solution()[0]
+    g = np.load(os.path.join(GOLDEN, f"solve_{name}_{N}.npz"))
+    assert len(P.trace()) == int(g["iterations"])
+    np.testing.assert_allclose(x, g["x"], atol=1e-6)
+    # the reference test's own bars: full voltage until the reference speed is
+    # reached, then the steady-state voltage; final state r = 10
+    dt = 5.0 / N
+    A_d = np.exp(-dt); B_d = 1.0 - A_d
+    U = x[:N + 1]
+    u_ss = (1.0 - A_d) / B_d * 10.0
+    if name != "flywheel_ocp_shooting":
+        X = x[N + 1:]
+        assert abs(X[0]) < 1e-8 and abs(X[N] - 10.0) < 2e-6
+    assert U[0] == pytest.approx(12.0, abs=2e-4)
+    if name != "flywheel_ocp_collocation":       # splines chatter (ref: ±2)
+        assert U[N - 2] == pytest.approx(u_ss, abs=2e-4)
+    P.close()
+
+
+@pytest.mark.parametrize("name,N,ns,ni,x_final", [
+    ("cart_pole_ocp", 100, 4, 1, (1.0, np.pi, 0.0, 0.0)),
+    ("differential_drive_ocp", 50, 5, 2, (1.0, 1.0, 0.0, 0.0, 0.0))])
+def test_ocp_variable_time_step(name, N, ns, ni, x_final):
+    """cart_pole_ocp_test.cpp:29-125 (collocation) and
+    differential_drive_ocp_test.cpp:25-125 (minimum time, direct
+    transcription), both with ONE time-step variable shared by all steps — a
+    dense row of the KKT matrix. The reference's bars: SUCCESS, initial and
+    final state to 1e-8."""
+    P = sb.Problem(name, N)
+    assert sb.EXIT_STATUS[P.solve()] == "SUCCESS"
+    x = P.solution()[0]
+    X = x[ni * (N + 1) + 1:].reshape(ns, N + 1)      # after U and dt
+    np.testing.assert_allclose(X[:, 0], 0.0, atol=1e-8)
+    np.testing.assert_allclose(X[:, N], x_final, atol=1e-8)
+    U, step = x[:ni * (N + 1)], x[ni * (N + 1)]
+    bound = 20.0 if name == "cart_pole_ocp" else 12.0
+    assert np.all(np.abs(U) <= bound + 1e-6)
+    g = np.load(os.path.join(GOLDEN, f"solve_{name}_{N}.npz"))
+    if name == "differential_drive_ocp":
+        # minimum time: the time step is the cost; same optimum as the oracle
+        assert 0.05 - 1e-9 <= step <= 3.0
+        assert step == pytest.approx(g["x"][ni * (N + 1)], rel=1e-5)
+    P.close()
+
+
 def test_multistart_mishra_bird_on_gpu():
     """multistart_test.cpp:17-55 through slp::multistart on the device path:
     two starts on two host threads and two CUDA streams; the lower cost wins."""
