@@ -51,6 +51,9 @@ struct StageTimer {
 };
 
 constexpr int kSplitThreshold = 16;  // root sums shorter than this stay whole
+// Sub-rows are fused into one cluster while the sum of their node lists stays
+// below this (cart-pole's per-step cluster: 1 642, g-fold's: 400).
+constexpr int64_t kMaxClusterVisits = 4000;
 
 struct SubRow {
   int out = 0;          // slpb_output
@@ -770,6 +773,16 @@ struct Compiler {
       for (int32_t s = b; s < e; ++s) analyze_subrow(subs[s], sc.pos);
     });
     timer.lap("analyze_subrow");
+    // Fusing is an optimisation (shared nodes are evaluated once); clusters
+    // that stay apart each evaluate their own copy, as the reference does per
+    // row. Without a bound, rows that overlap pairwise — the Lagrangian
+    // gradient rows of a collocation OCP, where every state enters two
+    // consecutive defects nonlinearly — chain ALL time steps into one cluster
+    // that no thread block can hold.
+    std::vector<int64_t> weight(ns);
+    for (int32_t s = 0; s < ns; ++s) {
+      weight[s] = static_cast<int64_t>(subs[s].nodes.size());
+    }
     for (int32_t s = 0; s < ns; ++s) {
       const SubRow& sr = subs[s];
       for (size_t i = 0; i < sr.nodes.size(); ++i) {
@@ -778,8 +791,15 @@ struct Compiler {
         if (owner[nd] < 0) {
           owner[nd] = s;
         } else {
-          int32_t a = find(owner[nd]), b = find(s);
-          if (a != b) uf[std::max(a, b)] = std::min(a, b);
+          const int32_t a = find(owner[nd]), b = find(s);
+          if (a == b) continue;
+          if (weight[a] + weight[b] > kMaxClusterVisits) {
+            owner[nd] = s;  // later rows sharing nd may still join this one
+            continue;
+          }
+          const int32_t root = std::min(a, b), child = std::max(a, b);
+          uf[child] = root;
+          weight[root] += weight[child];
         }
       }
     }
@@ -799,6 +819,18 @@ struct Compiler {
     }
 
     timer.lap("union-find + members");
+    if (timer.on) {
+      size_t biggest = 0;
+      for (const auto& m : members) {
+        size_t total = 0;
+        for (int32_t sub : m) total += subs[sub].nodes.size();
+        biggest = std::max(biggest, total);
+      }
+      std::fprintf(stderr,
+                   "[slpb compile] %d sub-rows in %zu clusters, largest %zu "
+                   "node visits\n",
+                   ns, members.size(), biggest);
+    }
     // --- per cluster, in parallel: local slot numbering, binding data and a
     // 128-bit hash of the structural signature (everything the program depends
     // on, in cluster-local terms: slot numbers, positions inside each sub-row).
