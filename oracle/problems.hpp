@@ -456,6 +456,15 @@ std::unique_ptr<Problem<B>> small_problem(const std::string& name, double p0,
     P->minimize(J);
     P->subject_to_ineq(
         le1(pow(x + V{5}, 2.0) + pow(y + V{5}, 2.0), V{25}));
+  } else if (name == "spy_test") {  // problem_spy_test.cpp:64-85
+    V x = P->decision_variable();
+    V y = P->decision_variable();
+    x.set_value(20);
+    y.set_value(20);
+    P->minimize(pow(x, 4.0) + pow(y, 4.0));
+    P->subject_to_ineq(ge1(x, V{1}));
+    P->subject_to_ineq(le1(x, V{10}));
+    P->subject_to_eq({y - V{2}});
   } else if (name == "unconstrained_1d") {  // quadratic_problem_test.cpp:15-34
     V x = P->decision_variable();
     x.set_value(2);

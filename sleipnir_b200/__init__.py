@@ -236,6 +236,7 @@ def host_lib() -> C.CDLL:
         L.slpbh_multistart.argtypes = [C.c_char_p, C.c_int, C.c_int, _dp, _dp,
                                        C.c_double, C.c_int, C.c_int, C.c_int,
                                        _dp, _dp, C.c_int, _dp]
+        L.slpbh_set_diagnostics.argtypes = [vp, C.c_int, C.c_int]
         L.slpbh_solver_kind.restype = C.c_int
         L.slpbh_solver_kind.argtypes = [vp]
         L.slpbh_set_flush_l2.argtypes = [vp, C.c_int]
@@ -515,6 +516,10 @@ class Problem:
 
     def loop_seconds(self):
         return self.H.slpbh_loop_seconds(self.h)
+
+    def set_diagnostics(self, diagnostics=True, spy=False):
+        """Options::diagnostics and the spy flag of solve() for the next solves."""
+        self.H.slpbh_set_diagnostics(self.h, int(diagnostics), int(spy))
 
     def solver_kind(self):
         """Branch of the last solve(): "IPM", "SQP" or "NEWTON"

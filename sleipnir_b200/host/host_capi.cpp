@@ -25,6 +25,7 @@ struct Handle {
   std::vector<double> x;
   int last_status = 0;
   bool flush_l2 = false;
+  bool diagnostics = false, spy = false;
   double timeout_s = -1.0;  // < 0: Options default (no timeout)
   int rank = 0, world = 1;
   std::array<char, 128> nccl_id{};
@@ -93,6 +94,8 @@ int slpbh_solve(void* h, double tolerance, int max_iterations, int feasible_ipm,
   dopt.ordering = ordering;
   dopt.keep_iterates = keep_iterates != 0;
   dopt.flush_l2 = hd->flush_l2;
+  dopt.spy = hd->spy;
+  opt.diagnostics = hd->diagnostics;
   dopt.rank = hd->rank;
   dopt.world = hd->world;
   dopt.nccl_unique_id = hd->nccl_id;
@@ -217,6 +220,14 @@ void slpbh_set_comm(void* h, int rank, int world, const void* id) {
   hd->rank = rank;
   hd->world = world;
   if (id) std::memcpy(hd->nccl_id.data(), id, 128);
+}
+
+/// Options::diagnostics (iteration table + timing tables on stdout) and the
+/// `spy` argument of Problem::solve (H.spy / A_e.spy / A_i.spy in the working
+/// directory) for the next solves.
+void slpbh_set_diagnostics(void* h, int diagnostics, int spy) {
+  H(h)->diagnostics = diagnostics != 0;
+  H(h)->spy = spy != 0;
 }
 
 /// Options::timeout for the next solves (seconds; negative = none).

@@ -37,6 +37,8 @@
 #include "sleipnir/optimization/solver/interior_point.hpp"
 #include "sleipnir/optimization/solver/iteration_info.hpp"
 #include "sleipnir/optimization/solver/options.hpp"
+#include "sleipnir/util/print_diagnostics.hpp"
+#include "sleipnir/util/spy.hpp"
 #include "slpb.h"
 
 namespace slp {
@@ -48,6 +50,10 @@ struct DeviceOptions {
   std::vector<int32_t> permutation;             ///< for SLPB_ORDER_CUSTOM
   bool keep_iterates = false;                   ///< record x,s,y,z per iteration
   bool flush_l2 = false;  ///< evict L2 before every iteration (benchmarks)
+  /// Write H.spy, A_e.spy, A_i.spy (sparsity pattern + signs per iteration,
+  /// util/spy.hpp) into the working directory, as the reference's
+  /// solve(options, spy = true) does (problem.hpp:365-380, :462-480, :562-595).
+  bool spy = false;
   /// Multi-GPU: one process per GPU, all solving the SAME problem in lockstep;
   /// the re-linearisation sweep is sharded and exchanged with one NCCL
   /// all-gather per iteration (slpb_comm_init). world == 1: single GPU.
@@ -135,11 +141,12 @@ class Problem {
   }
 
   /// Solves the optimization problem; the solution is stored in the original
-  /// variables. `spy` is accepted for source compatibility (sparsity-pattern
-  /// dumps are not part of this build).
-  ExitStatus solve(const Options& options = Options{},
-                   [[maybe_unused]] bool spy = false) {
-    return solve(options, DeviceOptions{});
+  /// variables. With `spy` the sparsity patterns of H, A_e and A_i are
+  /// written to H.spy / A_e.spy / A_i.spy at every iteration.
+  ExitStatus solve(const Options& options = Options{}, bool spy = false) {
+    DeviceOptions dev_options;
+    dev_options.spy = spy;
+    return solve(options, dev_options);
   }
 
   ExitStatus solve(const Options& options, const DeviceOptions& dev_options) {
@@ -182,6 +189,41 @@ class Problem {
     for (const auto& cb : m_iteration_callbacks) callbacks.push_back(cb);
     for (const auto& cb : m_persistent_iteration_callbacks) {
       callbacks.push_back(cb);
+    }
+
+    // Sparsity pattern files (the reference registers the same callback)
+    std::unique_ptr<Spy<Scalar>> H_spy, A_e_spy, A_i_spy;
+    if (dev_options.spy) {
+      H_spy = std::make_unique<Spy<Scalar>>("H.spy", "Hessian",
+                                            "Decision variables",
+                                            "Decision variables", n, n);
+      if (me > 0) {
+        A_e_spy = std::make_unique<Spy<Scalar>>(
+            "A_e.spy", "Equality constraint Jacobian", "Constraints",
+            "Decision variables", me, n);
+      }
+      if (mi > 0) {
+        A_i_spy = std::make_unique<Spy<Scalar>>(
+            "A_i.spy", "Inequality constraint Jacobian", "Constraints",
+            "Decision variables", mi, n);
+      }
+      callbacks.push_back([&](const IterationInfo<Scalar>& info) -> bool {
+        // restoration iterations hand in the enlarged problem's matrices
+        if (info.H.rows() != n) return false;
+        H_spy->add(info.H);
+        if (A_e_spy) A_e_spy->add(info.A_e);
+        if (A_i_spy) A_i_spy->add(info.A_i);
+        return false;
+      });
+    }
+
+    if (options.diagnostics) {
+      const char* solver_name =
+          me == 0 && mi == 0 ? "Newton" : (mi == 0 ? "SQP" : "IPM");
+      std::printf("\nInvoking %s solver (B200 device path)\n\n", solver_name);
+      std::printf("Number of decision variables: %d\n", n);
+      std::printf("Number of equality constraints: %d\n", me);
+      std::printf("Number of inequality constraints: %d\n\n", mi);
     }
 
     m_phase.fill(0.0);
@@ -302,6 +344,30 @@ class Problem {
     slpb_get_counters(dev, &m_counters);
     slpb_get_timers(dev, &m_timers);
     lap(7);
+    if (options.diagnostics) {
+      if (iterations > 0) print_bottom_iteration_diagnostics();
+      const std::string_view exit_name = to_string(status);
+      std::printf("\nExit: %.*s after %d iterations\n\n",
+                  static_cast<int>(exit_name.size()), exit_name.data(),
+                  iterations);
+      static constexpr const char* kHost[8] = {
+          "autodiff setup", "flatten graphs", "device handle",
+          "upload + compile", "problem scaling", "symbolic analysis",
+          "Newton loop", "write-back"};
+      std::vector<TimingRow> host_rows, device_rows;
+      for (int i = 0; i < 8; ++i) {
+        host_rows.push_back({kHost[i], 1e3 * m_phase[i], 1});
+      }
+      print_timing_table("host phases of solve()", host_rows);
+      static constexpr const char* kDevice[5] = {
+          "re-linearisation sweep", "value sweep (trial points)",
+          "KKT assembly", "LDLT factorisation", "triangular solves"};
+      for (int i = 0; i < 5; ++i) {
+        device_rows.push_back(
+            {kDevice[i], m_timers.total_ms[i], m_timers.count[i]});
+      }
+      print_timing_table("device time per kernel group", device_rows);
+    }
     if (std::getenv("SLPB_DESTROY_TIMING")) {
       // where the teardown goes (development aid): release the big owners one
       // by one instead of at scope exit

@@ -24,6 +24,7 @@
 #include "sleipnir/optimization/solver/exit_status.hpp"
 #include "sleipnir/optimization/solver/iteration_info.hpp"
 #include "sleipnir/optimization/solver/options.hpp"
+#include "sleipnir/util/print_diagnostics.hpp"
 #include "sleipnir/util/linalg.hpp"
 #include "slpb.h"
 
@@ -445,6 +446,7 @@ ExitStatus interior_point(
     }
     int it_solves = 0, it_trials = 0;
     const int fact_before = solver.factorizations;
+    const auto iteration_start_time = std::chrono::steady_clock::now();
 
     // Local infeasibility (:387-402; is_locally_infeasible.hpp:17-60)
     if (me > 0 && kkt.aetce_l2 < 1e-6 && kkt.ce_l2 > 1e-2) {
@@ -669,6 +671,28 @@ ExitStatus interior_point(
         update_barrier_parameter_and_reset_filter();
         E_mu = detail::kkt_error_scaled(kkt, me, mi, mu);
       }
+    }
+
+    if (options.diagnostics) {
+      // the table of print_diagnostics.hpp:193-239 (interior_point.hpp:837-849);
+      // sᵀz = ‖Sz − 0·e‖₁ since every sᵢzᵢ > 0. (Second-order-correction
+      // sub-rows are not printed: their error column would need the
+      // derivatives at the rejected trial point.)
+      slpb_kkt_stats at_zero{};
+      SLP_DEVICE_CALL(dev, slpb_kkt_stats_current(dev, 0.0, &at_zero));
+      print_iteration_diagnostics(
+          iterations,
+          in_feasibility_restoration ? IterationType::FEASIBILITY_RESTORATION
+                                     : IterationType::NORMAL,
+          std::chrono::duration<double, std::milli>(
+              std::chrono::steady_clock::now() - iteration_start_time)
+              .count(),
+          E_0, cur.f, cur.ce_l1 + cur.cis_l1, mi > 0 ? at_zero.sz_mu_l1 : 0.0,
+          mu, solver.hessian_regularization(),
+          solver.constraint_jacobian_regularization(),
+          std::max(accepted_step.px_inf, accepted_step.ps_inf),
+          std::max(accepted_step.py_inf, accepted_step.pz_inf), alpha,
+          alpha_max, alpha_reduction_factor, alpha_z);
     }
 
     if (trace != nullptr) {

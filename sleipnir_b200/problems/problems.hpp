@@ -509,6 +509,15 @@ inline std::unique_ptr<slp::Problem<double>> small_problem(
         cos(x) * exp(pow(T(1) - sin(y), T(2))) + pow(x - y, T(2));
     problem.minimize(J);
     problem.subject_to(pow(x + T(5), T(2)) + pow(y + T(5), T(2)) < T(25));
+  } else if (name == "spy_test") {  // problem_spy_test.cpp:64-85
+    auto x = problem.decision_variable();
+    auto y = problem.decision_variable();
+    x.set_value(T(20));
+    y.set_value(T(20));
+    problem.minimize(pow(x, T(4)) + pow(y, T(4)));
+    problem.subject_to(x >= T(1));
+    problem.subject_to(x <= T(10));
+    problem.subject_to(y == T(2));
   } else if (name == "unconstrained_1d") {
     auto x = problem.decision_variable();
     x.set_value(T(2));

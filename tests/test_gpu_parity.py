@@ -566,7 +566,13 @@ def test_ocp_flywheel_transcriptions(name, N):
         # chatter", says the reference test — and takes 18 iterations here
         # against the oracle's 16; the optimum is the same)
         assert len(P.trace()) == int(g["iterations"])
-    np.testing.assert_allclose(x, g["x"], atol=1e-5)
+    if name == "flywheel_ocp_collocation":
+        # the cost sees X only; the spline's input samples are determined far
+        # less sharply (the reference test allows ±2 V on them, 1e-2 on X)
+        np.testing.assert_allclose(x[N + 1:], g["x"][N + 1:], atol=1e-3)
+        np.testing.assert_allclose(x[:N + 1], g["x"][:N + 1], atol=2.0)
+    else:
+        np.testing.assert_allclose(x, g["x"], atol=1e-5)
     # the reference test's own bars: full voltage until the reference speed is
     # reached, then the steady-state voltage; final state r = 10
     dt = 5.0 / N
@@ -606,6 +612,71 @@ def test_ocp_variable_time_step(name, N, ns, ni, x_final):
         assert 0.05 - 1e-9 <= step <= 3.0
         assert step == pytest.approx(g["x"][ni * (N + 1)], rel=1e-5)
     P.close()
+
+
+def test_spy_files_and_diagnostics(tmp_path, capfd):
+    """problem_spy_test.cpp:64-158: solve(options{diagnostics}, spy = true)
+    writes H.spy / A_e.spy / A_i.spy, one frame per iteration, in the
+    reference's binary layout; the iteration table goes to stdout."""
+    import struct
+    cwd = os.getcwd()
+    os.chdir(tmp_path)
+    try:
+        P = sb.Problem("spy_test", 0)
+        P.set_diagnostics(True, spy=True)
+        P.add_callback(stop_at=-1)
+        assert sb.EXIT_STATUS[P.solve()] == "SUCCESS"
+        np.testing.assert_allclose(P.solution()[0], (1.0, 2.0), atol=1e-8)
+        iterations = len(P.callback_log()[0])
+        assert iterations == len(P.trace()) > 0
+        P.close()
+
+        def frames(path, title, rows, cols):
+            with open(path, "rb") as f:
+                blob = f.read()
+            at = 0
+
+            def i32():
+                nonlocal at
+                v = struct.unpack_from("<i", blob, at)[0]
+                at += 4
+                return v
+
+            def string():
+                nonlocal at
+                n = i32()
+                v = blob[at:at + n].decode()
+                at += n
+                return v
+            assert string() == title
+            assert string() == ("Decision variables" if title == "Hessian"
+                                else "Constraints")
+            assert string() == "Decision variables"
+            assert (i32(), i32()) == (rows, cols)
+            out = []
+            while at < len(blob):
+                coords = []
+                for _ in range(i32()):
+                    r, c = i32(), i32()
+                    coords.append((r, c, chr(blob[at])))
+                    at += 1
+                out.append(coords)
+            return out
+        H = frames("H.spy", "Hessian", 2, 2)
+        Ae = frames("A_e.spy", "Equality constraint Jacobian", 1, 2)
+        Ai = frames("A_i.spy", "Inequality constraint Jacobian", 2, 2)
+        assert len(H) == len(Ae) == len(Ai) == iterations
+        assert all(f == [(0, 0, "+"), (1, 1, "+")] for f in H)
+        assert all(f == [(0, 1, "+")] for f in Ae)
+        assert all(f == [(0, 0, "+"), (1, 0, "-")] for f in Ai)
+    finally:
+        os.chdir(cwd)
+    text = capfd.readouterr().out
+    assert "Invoking IPM solver" in text and "Exit: success" in text
+    rows = [ln for ln in text.splitlines() if ln.startswith("│") and "%" not in ln]
+    assert len(rows) == iterations
+    assert [int(r.lstrip("│").split()[0]) for r in rows] == list(range(iterations))
+    assert "LDLT factorisation" in text and "Newton loop" in text
 
 
 def test_multistart_mishra_bird_on_gpu():

@@ -38,6 +38,7 @@ KNOWN = [
     ("nonfinite_eq", "NONFINITE_INITIAL_GUESS", None, 0),    # :142-148
     ("nonfinite_eq_jacobian", "NONFINITE_INITIAL_GUESS", None, 0),  # :151-157
     ("diverging", "DIVERGING_ITERATES", None, 0),            # :178-194
+    ("spy_test", "SUCCESS", (1, 2), 1e-8),                   # problem_spy_test.cpp:64-86
 ]
 
 
