@@ -146,6 +146,33 @@ std::unique_ptr<Problem<B>> chained_rosenbrock_problem(int N) {
   return problem;
 }
 
+/// double_integrator_problem_test.cpp:27-127 with dt = 3.5 s / N.
+template <class B>
+std::unique_ptr<Problem<B>> double_integrator_problem(int N) {
+  using M = Mat<B>;
+  using V = Var<B>;
+  const double t = 3.5 / N;
+  constexpr double r = 2.0;
+  auto problem = std::make_unique<Problem<B>>();
+  M X = problem->decision_variable(2, N + 1);
+  M U = problem->decision_variable(1, N);
+  for (int k = 0; k < N; ++k) {
+    V p_k1 = X(0, k + 1), v_k1 = X(1, k + 1);
+    V p_k = X(0, k), v_k = X(1, k), a_k = U(0, k);
+    problem->subject_to_eq(
+        {p_k1 - (p_k + v_k * V{t} + V{0.5} * a_k * V{t} * V{t})});
+    problem->subject_to_eq({v_k1 - (v_k + a_k * V{t})});
+  }
+  problem->subject_to_eq(eq(X.col(0), M::constants(2, 1, {0.0, 0.0})));
+  problem->subject_to_eq(eq(X.col(N), M::constants(2, 1, {r, 0.0})));
+  problem->subject_to_ineq(bounds(V{-1.0}, X.row(1), V{1.0}));
+  problem->subject_to_ineq(bounds(V{-1.0}, U, V{1.0}));
+  V J{0.0};
+  for (int k = 0; k < N + 1; ++k) J += pow(V{r} - X(0, k), 2.0);
+  problem->minimize(J);
+  return problem;
+}
+
 // ---- slp::OCP (optimization/ocp.hpp:49-414) ----------------------------------
 enum class OcpDynamics { EXPLICIT_ODE, DISCRETE };
 enum class OcpTimestep { FIXED, VARIABLE_SINGLE, VARIABLE };
@@ -456,6 +483,10 @@ std::unique_ptr<Problem<B>> small_problem(const std::string& name, double p0,
     P->minimize(J);
     P->subject_to_ineq(
         le1(pow(x + V{5}, 2.0) + pow(y + V{5}, 2.0), V{25}));
+  } else if (name == "empty") {  // trivial_problem_test.cpp:14-24
+  } else if (name == "no_cost_unconstrained") {  // :26-66
+    M X = P->decision_variable(2, 3);
+    for (int i = 0; i < 6; ++i) X[i].set_value(p0);
   } else if (name == "spy_test") {  // problem_spy_test.cpp:64-85
     V x = P->decision_variable();
     V y = P->decision_variable();
@@ -725,6 +756,7 @@ std::unique_ptr<Problem<B>> make_problem(const std::string& name, int N,
     return flywheel_problem<B>(N, p0 > 0 ? p0 : 5.0, false);
   }
   if (name == "chained_rosenbrock") return chained_rosenbrock_problem<B>(N);
+  if (name == "double_integrator") return double_integrator_problem<B>(N);
   if (name == "flywheel_ocp") {
     return flywheel_ocp_problem<B>(N, static_cast<int>(p0),
                                    static_cast<int>(p1));

@@ -312,6 +312,36 @@ inline std::unique_ptr<slp::Problem<double>> chained_rosenbrock(int N) {
   return problem;
 }
 
+/// double_integrator_problem_test.cpp:27-127 with dt = 3.5 s / N: minimum
+/// position error under velocity and acceleration limits (a bang-coast-bang
+/// profile).
+inline std::unique_ptr<slp::Problem<double>> double_integrator(int N) {
+  using T = double;
+  const T t = T(3.5) / N;
+  constexpr T r(2);
+  auto P = std::make_unique<slp::Problem<T>>();
+  auto& problem = *P;
+  auto X = problem.decision_variable(2, N + 1);
+  auto U = problem.decision_variable(1, N);
+  for (int k = 0; k < N; ++k) {
+    auto p_k1 = X[0, k + 1];
+    auto v_k1 = X[1, k + 1];
+    auto p_k = X[0, k];
+    auto v_k = X[1, k];
+    auto a_k = U[0, k];
+    problem.subject_to(p_k1 == p_k + v_k * t + 0.5 * a_k * t * t);
+    problem.subject_to(v_k1 == v_k + a_k * t);
+  }
+  problem.subject_to(X.col(0) == slp::Matrix<T>{{0.0}, {0.0}});
+  problem.subject_to(X.col(N) == slp::Matrix<T>{{r}, {0.0}});
+  problem.subject_to(slp::bounds(T(-1), X.row(1), T(1)));
+  problem.subject_to(slp::bounds(T(-1), U, T(1)));
+  slp::Variable<T> J = T(0);
+  for (int k = 0; k < N + 1; ++k) J += pow(r - X[0, k], 2);
+  problem.minimize(J);
+  return P;
+}
+
 // ---- the reference's OCP tests, written against slp::OCP ---------------------
 
 /// flywheel_ocp_test.cpp:38-201 with dt = 5 s / N. method: 0 direct
@@ -509,6 +539,10 @@ inline std::unique_ptr<slp::Problem<double>> small_problem(
         cos(x) * exp(pow(T(1) - sin(y), T(2))) + pow(x - y, T(2));
     problem.minimize(J);
     problem.subject_to(pow(x + T(5), T(2)) + pow(y + T(5), T(2)) < T(25));
+  } else if (name == "empty") {  // trivial_problem_test.cpp:14-24
+  } else if (name == "no_cost_unconstrained") {  // :26-66
+    auto X = problem.decision_variable(2, 3);
+    for (int i = 0; i < 6; ++i) X[i].set_value(p0);
   } else if (name == "spy_test") {  // problem_spy_test.cpp:64-85
     auto x = problem.decision_variable();
     auto y = problem.decision_variable();
@@ -594,6 +628,7 @@ inline std::unique_ptr<slp::Problem<double>> make_problem(
   if (name == "cart_pole_eq") return cart_pole(N, p0 > 0 ? p0 : 5.0, false);
   if (name == "flywheel_eq") return flywheel(N, p0 > 0 ? p0 : 5.0, false);
   if (name == "chained_rosenbrock") return chained_rosenbrock(N);
+  if (name == "double_integrator") return double_integrator(N);
   if (name == "flywheel_ocp") {
     return flywheel_ocp(N, static_cast<int>(p0), p1 != 0.0);
   }

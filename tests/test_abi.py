@@ -65,6 +65,46 @@ def test_fails_loudly_without_a_device():
     P.close()
 
 
+def test_trivial_problems_need_no_solver():
+    """trivial_problem_test.cpp:14-66: an empty problem and one with neither
+    cost nor constraints return SUCCESS before any solver (or device) is
+    touched, and leave the variables alone."""
+    P = sb.Problem("empty")
+    assert (P.n, P.me, P.mi) == (0, 0, 0) and P.types() == (0, 0, 0)
+    assert sb.EXIT_STATUS[P.solve()] == "SUCCESS"
+    P.close()
+    for value in (0.0, 1.0):
+        P = sb.Problem("no_cost_unconstrained", 0, value)
+        assert (P.n, P.me, P.mi) == (6, 0, 0) and P.types() == (0, 0, 0)
+        assert sb.EXIT_STATUS[P.solve()] == "SUCCESS"
+        assert list(P.initial_guess()) == [value] * 6
+        P.close()
+
+
+def test_ocp_front_end_shapes_and_types():
+    """What the reference's OCP tests CHECK before solving
+    (flywheel_ocp_test.cpp:66-68, cart_pole_ocp_test.cpp:83-85,
+    differential_drive_ocp_test.cpp:59-61): expression types, and the decision
+    variable layout U | dt | X."""
+    QUADRATIC, LINEAR, NONLINEAR = 3, 2, 4
+    for name, N, dims in (("flywheel_ocp", 50, (102, 51, 102)),
+                          ("flywheel_ocp_collocation", 50, (102, 51, 102)),
+                          ("flywheel_ocp_discrete", 50, (102, 51, 102)),
+                          ("flywheel_ocp_shooting", 50, (51, 1, 102))):
+        P = sb.Problem(name, N)
+        assert (P.n, P.me, P.mi) == dims
+        assert P.types() == (QUADRATIC, LINEAR, LINEAR)
+        P.close()
+    P = sb.Problem("cart_pole_ocp", 100)
+    assert (P.n, P.me, P.mi) == (101 + 1 + 404, 400 + 8, 202 + 202)
+    assert P.types() == (QUADRATIC, NONLINEAR, LINEAR)
+    P.close()
+    P = sb.Problem("differential_drive_ocp", 50)
+    assert (P.n, P.me, P.mi) == (102 + 1 + 255, 250 + 10, 204 + 102)
+    assert P.types() == (LINEAR, NONLINEAR, LINEAR)
+    P.close()
+
+
 def test_product_does_not_reference_the_oracle():
     """Nothing under sleipnir_b200/ (nor include/) may include, import or link
     anything under oracle/."""

@@ -614,6 +614,38 @@ def test_ocp_variable_time_step(name, N, ns, ni, x_final):
     P.close()
 
 
+def test_double_integrator_matches_oracle_and_reference_profile():
+    """double_integrator_problem_test.cpp:27-127 at its own size (N = 700, a
+    QP with 2 103 variables): same decisions and iterates as the oracle along
+    the whole solve, the golden optimum, and the reference test's
+    accelerate / coast / brake profile."""
+    N = 700
+    P = sb.Problem("double_integrator", N)
+    st = P.solve(keep_iterates=True)
+    tr = P.trace()
+    D = P.open_device(); D.analyze(); perm = D.permutation(); P.close_device()
+    O = OracleProblem("double_integrator", N)
+    so = O.solve(perm=perm, force_sparse=1)
+    to = O.trace()
+    assert sb.EXIT_STATUS[st] == EXIT_STATUS[so] == "SUCCESS"
+    assert len(tr) == len(to)
+    for a, b in zip(tr, to):
+        assert a.factorizations == b.factorizations and a.trials == b.trials
+        assert a.delta == b.delta and a.mu == b.mu
+        assert rel(a.x, b.x) < 1e-8
+    g = np.load(os.path.join(GOLDEN, f"solve_double_integrator_{N}.npz"))
+    x = P.solution()[0]
+    np.testing.assert_allclose(x, g["x"], atol=1e-6)
+    U = x[2 * (N + 1):]
+    dt = 3.5 / N
+    for k in range(1, N - 1):
+        t = k * dt
+        u = 1.0 if t < 1 else 0.0 if t < 2.05 else -1.0 if t < 3.275 else 1.0
+        if abs(U[k - 1] - U[k + 1]) < 1 - 1e-2:
+            assert abs(U[k] - u) < 1e-4
+    P.close(); O.close()
+
+
 def test_spy_files_and_diagnostics(tmp_path, capfd):
     """problem_spy_test.cpp:64-158: solve(options{diagnostics}, spy = true)
     writes H.spy / A_e.spy / A_i.spy, one frame per iteration, in the

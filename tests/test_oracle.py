@@ -39,7 +39,32 @@ KNOWN = [
     ("nonfinite_eq_jacobian", "NONFINITE_INITIAL_GUESS", None, 0),  # :151-157
     ("diverging", "DIVERGING_ITERATES", None, 0),            # :178-194
     ("spy_test", "SUCCESS", (1, 2), 1e-8),                   # problem_spy_test.cpp:64-86
+    ("empty", "SUCCESS", (), 0),                             # trivial_problem_test.cpp:14-24
+    ("no_cost_unconstrained", "SUCCESS", (0,) * 6, 0),       # :26-46
 ]
+
+
+def test_double_integrator_profile():
+    # double_integrator_problem_test.cpp:27-127: accelerate, coast, brake
+    N = 700
+    dt = 3.5 / N
+    P = OracleProblem("double_integrator", N)
+    assert EXIT_STATUS[P.solve()] == "SUCCESS"
+    x, *_ = P.solution()
+    X, U = x[:2 * (N + 1)].reshape(2, N + 1), x[2 * (N + 1):]
+    assert abs(X[0, 0]) < 1e-8 and abs(X[1, 0]) < 1e-8
+    state = np.zeros(2)
+    for k in range(N):
+        assert abs(X[0, k] - state[0]) < 1e-2 and abs(X[1, k] - state[1]) < 1e-2
+        t = k * dt
+        u = 1.0 if t < 1 else 0.0 if t < 2.05 else -1.0 if t < 3.275 else 1.0
+        if not (0 < k < N - 1 and abs(U[k - 1] - U[k + 1]) >= 1 - 1e-2):
+            assert abs(U[k] - u) < 1e-4
+        state = np.array([state[0] + dt * state[1] + 0.5 * dt * dt * u,
+                          state[1] + dt * u])
+    assert abs(X[0, N] - 2.0) < 1e-8 and abs(X[1, N]) < 1e-8
+    P.close()
+
 
 
 @pytest.mark.parametrize("name,status,expect,tol", KNOWN)
