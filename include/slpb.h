@@ -251,6 +251,13 @@ int slpb_kkt_stats_current(slpb_solver* s, double mu, slpb_kkt_stats* out);
 /* Same quantities for the trial point, using the trial point's own g/A_e/A_i
  * (the α<α_min fallback, interior_point.hpp:692-706); evaluates them first. */
 int slpb_kkt_stats_trial(slpb_solver* s, double mu, slpb_kkt_stats* out);
+/* slpb_accept, slpb_eval_current(derivatives = 2) and slpb_kkt_stats_current in
+ * ONE host round trip — the tail of an accepted iteration,
+ * interior_point.hpp:779-832: x, s, y, z ← trial (z clamped), g, A_e, A_i, H
+ * re-evaluated there, then the error reductions. *finite receives the
+ * SLPB_FINITE_G/A_E/A_I/H bits. */
+int slpb_accept_relinearize(slpb_solver* s, double mu, int32_t* finite,
+                            slpb_kkt_stats* out);
 
 /* ---- Newton system -------------------------------------------------------- */
 
@@ -317,6 +324,15 @@ int slpb_soc_iterate(slpb_solver* s, double mu, double tau, double alpha_soc,
  * step. slack_from_ci != 0 sets trial_s = trial_c_i (feasible_ipm, :515-520). */
 int slpb_trial(slpb_solver* s, double alpha, double alpha_z, int which_step,
                int slack_from_ci, slpb_point_info* info);
+
+/* slpb_solve followed by slpb_trial at the full step (α = α_max; the dual step
+ * α_z, or α_max too when dual_uses_primal_alpha != 0 — the SQP rule, sqp.hpp:346)
+ * in ONE host round trip: the trial-point kernel reads the step lengths the
+ * step reductions just left on the device (interior_point.hpp:470-528). The
+ * caller ignores *trial when α_max sends it to feasibility restoration. */
+int slpb_solve_trial(slpb_solver* s, double mu, double tau,
+                     int dual_uses_primal_alpha, int slack_from_ci,
+                     slpb_step_info* step, slpb_point_info* trial);
 
 /* Evaluates f, c_e, c_i at a HOST-supplied point (x, s) without touching the
  * current iterate (it lands in the trial buffers): the acceptance test of

@@ -111,7 +111,8 @@ ABI_SYMBOLS = [
     "slpb_factor", "slpb_factor_pair", "slpb_select_factor",
     "slpb_prepare_rhs", "slpb_solve",
     "slpb_soc_begin", "slpb_soc_iterate",
-    "slpb_trial", "slpb_probe_point", "slpb_multiplier_estimate", "slpb_accept", "slpb_array_size", "slpb_download",
+    "slpb_trial", "slpb_solve_trial", "slpb_accept_relinearize",
+    "slpb_probe_point", "slpb_multiplier_estimate", "slpb_accept", "slpb_array_size", "slpb_download",
     "slpb_pattern", "slpb_get_counters", "slpb_get_timers",
     "slpb_last_device_ms", "slpb_flush_l2", "slpb_stream",
 ]
@@ -152,6 +153,12 @@ def device_lib() -> C.CDLL:
         L.slpb_trial.argtypes = [vp, C.c_double, C.c_double, C.c_int, C.c_int,
                                  C.POINTER(PointInfo)]
         L.slpb_accept.argtypes = [vp, C.c_double]
+        L.slpb_solve_trial.argtypes = [vp, C.c_double, C.c_double, C.c_int,
+                                       C.c_int, C.POINTER(StepInfo),
+                                       C.POINTER(PointInfo)]
+        L.slpb_accept_relinearize.argtypes = [vp, C.c_double,
+                                              C.POINTER(C.c_int32),
+                                              C.POINTER(KktStats)]
         L.slpb_probe_point.argtypes = [vp, _dp, _dp, C.POINTER(PointInfo)]
         L.slpb_multiplier_estimate.argtypes = [vp, C.c_double,
                                                C.POINTER(FactorInfo)]
@@ -400,6 +407,23 @@ class DeviceSession:
 
     def accept(self, mu):
         self._check(self.L.slpb_accept(self.raw, mu), "slpb_accept")
+
+    def solve_trial(self, mu, tau, dual_uses_primal_alpha=0, slack_from_ci=0):
+        """slpb_solve + slpb_trial at the full step in one host round trip."""
+        step, trial = StepInfo(), PointInfo()
+        self._check(self.L.slpb_solve_trial(
+            self.raw, mu, tau, dual_uses_primal_alpha, slack_from_ci,
+            C.byref(step), C.byref(trial)), "slpb_solve_trial")
+        return step, trial
+
+    def accept_relinearize(self, mu):
+        """slpb_accept + slpb_eval_current(2) + slpb_kkt_stats_current in one
+        host round trip; returns (finite bits of the derivatives, KktStats)."""
+        finite, st = C.c_int32(), KktStats()
+        self._check(self.L.slpb_accept_relinearize(
+            self.raw, mu, C.byref(finite), C.byref(st)),
+            "slpb_accept_relinearize")
+        return finite.value, st
 
     def download(self, which):
         cnt = C.c_int64()

@@ -205,7 +205,7 @@ struct slpb_solver {
   DevBuf<FrontMeta> sy_metas;
   DevBuf<unsigned long long> tree_debug;
   bool use_tree = false;
-  int tree_blocks = 0, tree_smem_doubles = 0;
+  int tree_blocks = 0, solve_blocks = 0, tree_smem_doubles = 0;
   int factor_sel = 0;  // which variant of the last factorisation the solves use
   // forward substitution fused into the factorisation (slpb_prepare_rhs)
   bool rhs_ready = false;
@@ -1247,11 +1247,18 @@ __global__ void k_trial_point(const double* __restrict__ x,
                               const double* __restrict__ ps,
                               const double* __restrict__ py,
                               const double* __restrict__ pz, double alpha,
-                              double alpha_z, int n, int me, int mi,
+                              double alpha_z,
+                              const double* __restrict__ alpha_dev,
+                              int dual_uses_primal, int n, int me, int mi,
                               double* __restrict__ tx, double* __restrict__ ts,
                               double* __restrict__ ty, double* __restrict__ tz,
                               double* __restrict__ leaf_trial) {
   const int i = blockIdx.x * blockDim.x + threadIdx.x;
+  if (alpha_dev != nullptr) {
+    // α_max, α_z as k_step_stats just left them (slpb_solve_trial)
+    alpha = alpha_dev[0];
+    alpha_z = dual_uses_primal ? alpha_dev[0] : alpha_dev[1];
+  }
   if (i < n) {
     const double v = x[i] + alpha * px[i];
     tx[i] = v;
@@ -1574,17 +1581,24 @@ void fill_point_info(const double* r, slpb_point_info* info) {
   info->ci_all_positive = static_cast<int32_t>(r[5]);
 }
 
-int kkt_stats(slpb_solver* S, const double* c_e, const double* c_i,
-              const double* x, const double* s, const double* y,
-              const double* z, double mu, slpb_kkt_stats* out) {
+/// Where the merged calls park their results in the 64-double result block.
+constexpr int kResStep = 0;    // 9 doubles of k_step_stats
+constexpr int kResPoint = 16;  // 6 (+1) doubles of k_point_info / k_deriv_finite
+constexpr int kResKkt = 32;    // 25 doubles of k_kkt_stats
+
+int kkt_stats_enqueue(slpb_solver* S, const double* c_e, const double* c_i,
+                      const double* x, const double* s, const double* y,
+                      const double* z, double mu, int offset) {
   k_kkt_stats<<<red_blocks(S->n + S->mi), kReduceThreads, 0, S->stream>>>(
       ae_view(S), ai_view(S), S->dvals.p + S->ad.off_g, c_e, c_i, x, s, y, z,
-      S->d_c.p, S->d_f, mu, S->n, S->me, S->mi, red_buf(S), S->d_results.p);
+      S->d_c.p, S->d_f, mu, S->n, S->me, S->mi, red_buf(S),
+      S->d_results.p + offset);
   ++S->counters.kernel_launches;
   CU(cudaGetLastError());
-  int rc = fetch_results(S, 25);
-  if (rc) return rc;
-  const double* r = S->h_results;
+  return SLPB_OK;
+}
+
+void fill_kkt_stats(const double* r, slpb_kkt_stats* out) {
   out->r_inf = r[0];
   out->r_l1 = r[1];
   out->y_l1 = r[2];
@@ -1611,6 +1625,15 @@ int kkt_stats(slpb_solver* S, const double* c_e, const double* c_i,
   out->s_inf = r[23];
   out->xs_finite = static_cast<int32_t>(r[24]);
   out->pad = 0;
+}
+
+int kkt_stats(slpb_solver* S, const double* c_e, const double* c_i,
+              const double* x, const double* s, const double* y,
+              const double* z, double mu, slpb_kkt_stats* out) {
+  int rc = kkt_stats_enqueue(S, c_e, c_i, x, s, y, z, mu, 0);
+  if (rc) return rc;
+  if ((rc = fetch_results(S, 25))) return rc;
+  fill_kkt_stats(S->h_results, out);
   return SLPB_OK;
 }
 
@@ -1658,7 +1681,7 @@ int launch_solve(slpb_solver* S, bool skip_forward) {
     k_init_solve_sync<<<blocks_for(Y.n_super, 256), 256, 0, S->stream>>>(
         S->tree_sync.p, Y.n_super, skip_forward ? 1 : 0);
     const TreeView T = tree_view(S);
-    k_solve_tree<<<S->tree_blocks, kTreeWarps * 32, 0, S->stream>>>(
+    k_solve_tree<<<S->solve_blocks, kTreeWarps * 32, 0, S->stream>>>(
         T, S->panels.p + sel * Y.panel_size, S->D.p + size_t(sel) * Y.dim,
         S->rhs.p, S->xperm.p + size_t(sel) * Y.dim,
         S->uvecs.p + size_t(sel) * Y.rel_ptr.back(), S->sol.p);
@@ -1690,6 +1713,8 @@ int launch_solve(slpb_solver* S, bool skip_forward) {
   return SLPB_OK;
 }
 
+void fill_step_info(const double* r, slpb_step_info* info);
+
 /// rhs → solve → step recovery → step stats, into the given step arrays.
 int solve_into(slpb_solver* S, double mu, double tau, bool soc,
                const double* cis_soc, const double* ce_for_rhs, double* px,
@@ -1719,9 +1744,14 @@ int solve_into(slpb_solver* S, double mu, double tau, bool soc,
       n, me, mi, red_buf(S), S->d_results.p);
   S->counters.kernel_launches += 2;
   CU(cudaGetLastError());
+  if (info == nullptr) return SLPB_OK;  // the caller fetches (slpb_solve_trial)
   rc = fetch_results(S, 9);
   if (rc) return rc;
-  const double* r = S->h_results;
+  fill_step_info(S->h_results, info);
+  return SLPB_OK;
+}
+
+void fill_step_info(const double* r, slpb_step_info* info) {
   info->alpha_max = r[0];
   info->alpha_z = r[1];
   info->g_dot_px = r[2];
@@ -1732,7 +1762,6 @@ int solve_into(slpb_solver* S, double mu, double tau, bool soc,
   info->pz_inf = r[7];
   info->finite = static_cast<int32_t>(r[8]);
   info->pad = 0;
-  return SLPB_OK;
 }
 
 }  // namespace slpb
@@ -2092,14 +2121,28 @@ int slpb_analyze(slpb_solver* S, int ordering, const int32_t* perm,
   // fronts of order ≤ 32: one warp per front, one launch per factorisation
   S->use_tree = Y.max_front <= 32;
   S->tree_smem_doubles = Y.max_front * Y.max_front + 64;
-  // about two blocks of warps per SM: enough to cover the widest level in a
-  // couple of passes without parking thousands of warps on a spin-wait
-  S->tree_blocks = std::max(
-      1, std::min(blocks_for(2 * Y.n_super, kTreeWarps), 148 * 2));
   {
     const int tree_smem =
         kTreeWarps * S->tree_smem_doubles * static_cast<int>(sizeof(double));
     if (S->use_tree) CU(raise_dynamic_smem(k_factor_tree, tree_smem));
+    // Persistent grids: as many blocks as are resident at once (SMs × blocks
+    // per SM at this kernel's register and shared-memory footprint), never more
+    // than there is work for. Fronts are handed out by ticket, so blocks of a
+    // second wave would only find the tickets gone.
+    int sms = 148;
+    cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, S->device);
+    int per_sm_factor = 1, per_sm_solve = 1;
+    if (S->use_tree) {
+      CU(cudaOccupancyMaxActiveBlocksPerMultiprocessor(
+          &per_sm_factor, k_factor_tree, kTreeWarps * 32, tree_smem));
+      CU(cudaOccupancyMaxActiveBlocksPerMultiprocessor(
+          &per_sm_solve, k_solve_tree, kTreeWarps * 32, 0));
+    }
+    const int useful = blocks_for(2 * Y.n_super, kTreeWarps);
+    S->tree_blocks =
+        std::max(1, std::min(useful, sms * std::max(1, per_sm_factor)));
+    S->solve_blocks = std::max(
+        1, std::min(useful, sms * std::min(2, std::max(1, per_sm_solve))));
   }
   CU(cudaStreamSynchronize(S->stream));
   SymbolicView& V = S->sview;
@@ -2393,18 +2436,20 @@ int slpb_soc_iterate(slpb_solver* S, double mu, double tau, double alpha_soc,
                     S->sps.p, S->spy.p, S->spz.p, info);
 }
 
-int slpb_trial(slpb_solver* S, double alpha, double alpha_z, int which_step,
-               int slack_from_ci, slpb_point_info* info) {
-  if (!S || !S->analyzed || !info) return SLPB_ERR_STATE;
-  CU(cudaSetDevice(S->device));
+namespace {
+/// Trial point + f, c_e, c_i there + its reductions at d_results[offset..];
+/// no host round trip.
+int trial_enqueue(slpb_solver* S, double alpha, double alpha_z,
+                  const double* alpha_dev, int dual_uses_primal,
+                  int which_step, int slack_from_ci, int offset) {
   const int n = S->n, me = S->me, mi = S->mi;
   const bool soc = which_step != 0;
   const int m = std::max(n, std::max(me, mi));
   k_trial_point<<<blocks_for(m, 256), 256, 0, S->stream>>>(
       S->x.p, S->s.p, S->y.p, S->z.p, soc ? S->spx.p : S->px.p,
       soc ? S->sps.p : S->ps.p, soc ? S->spy.p : S->py.p,
-      soc ? S->spz.p : S->pz.p, alpha, alpha_z, n, me, mi, S->tx.p, S->ts.p,
-      S->ty.p, S->tz.p, S->leaf_trial.p);
+      soc ? S->spz.p : S->pz.p, alpha, alpha_z, alpha_dev, dual_uses_primal, n,
+      me, mi, S->tx.p, S->ts.p, S->ty.p, S->tz.p, S->leaf_trial.p);
   ++S->counters.kernel_launches;
   int rc;
   if ((rc = eval_values(S, S->leaf_trial.p, S->vals_trial.p))) return rc;
@@ -2413,9 +2458,42 @@ int slpb_trial(slpb_solver* S, double alpha, double alpha_z, int which_step,
         S->vals_trial.p + 1 + me, S->ts.p, mi);
     ++S->counters.kernel_launches;
   }
-  if ((rc = point_info(S, S->vals_trial.p, S->ts.p, S->d_results.p))) return rc;
+  return point_info(S, S->vals_trial.p, S->ts.p, S->d_results.p + offset);
+}
+}  // namespace
+
+int slpb_trial(slpb_solver* S, double alpha, double alpha_z, int which_step,
+               int slack_from_ci, slpb_point_info* info) {
+  if (!S || !S->analyzed || !info) return SLPB_ERR_STATE;
+  CU(cudaSetDevice(S->device));
+  int rc;
+  if ((rc = trial_enqueue(S, alpha, alpha_z, nullptr, 0, which_step,
+                                slack_from_ci, 0))) {
+    return rc;
+  }
   if ((rc = fetch_results(S, 6))) return rc;
   fill_point_info(S->h_results, info);
+  return SLPB_OK;
+}
+
+int slpb_solve_trial(slpb_solver* S, double mu, double tau,
+                     int dual_uses_primal_alpha, int slack_from_ci,
+                     slpb_step_info* step, slpb_point_info* trial) {
+  if (!S || !S->analyzed || !step || !trial) return SLPB_ERR_STATE;
+  CU(cudaSetDevice(S->device));
+  int rc;
+  if ((rc = solve_into(S, mu, tau, false, nullptr, S->vals_cur.p + 1, S->px.p,
+                       S->ps.p, S->py.p, S->pz.p, nullptr))) {
+    return rc;
+  }
+  if ((rc = trial_enqueue(S, 0.0, 0.0, S->d_results.p + kResStep,
+                                dual_uses_primal_alpha, 0, slack_from_ci,
+                                kResPoint))) {
+    return rc;
+  }
+  if ((rc = fetch_results(S, kResPoint + 6))) return rc;
+  fill_step_info(S->h_results + kResStep, step);
+  fill_point_info(S->h_results + kResPoint, trial);
   return SLPB_OK;
 }
 
@@ -2508,6 +2586,28 @@ int slpb_accept(slpb_solver* S, double mu) {
     ++S->counters.kernel_launches;
   }
   CU(cudaGetLastError());
+  return SLPB_OK;
+}
+
+int slpb_accept_relinearize(slpb_solver* S, double mu, int32_t* finite,
+                            slpb_kkt_stats* stats) {
+  if (!S || !S->analyzed || !finite || !stats) return SLPB_ERR_STATE;
+  int rc = slpb_accept(S, mu);
+  if (rc) return rc;
+  if ((rc = refresh_leaves(S, S->x.p, S->y.p, S->z.p, S->leaf_cur.p))) return rc;
+  if ((rc = eval_derivs(S, S->leaf_cur.p))) return rc;
+  k_deriv_finite<<<red_blocks(S->ad.off_h + S->ad.H.nnz()), kReduceThreads, 0,
+                   S->stream>>>(S->dvals.p, S->ad.off_ae, S->ad.off_ai,
+                                S->ad.off_h, S->ad.off_h + S->ad.H.nnz(),
+                                red_buf(S), S->d_results.p + kResPoint);
+  ++S->counters.kernel_launches;
+  if ((rc = kkt_stats_enqueue(S, S->vals_cur.p + 1, S->vals_cur.p + 1 + S->me,
+                              S->x.p, S->s.p, S->y.p, S->z.p, mu, kResKkt))) {
+    return rc;
+  }
+  if ((rc = fetch_results(S, kResKkt + 25))) return rc;
+  *finite = static_cast<int32_t>(S->h_results[kResPoint]);
+  fill_kkt_stats(S->h_results + kResKkt, stats);
   return SLPB_OK;
 }
 

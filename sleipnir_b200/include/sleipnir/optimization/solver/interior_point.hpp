@@ -385,6 +385,9 @@ ExitStatus interior_point(
                                in_feasibility_restoration ? 0.0 : 1e-10};
   solver.set_previous_regularization(initial_delta, 0.0);
   if (std::getenv("SLPB_NO_SPECULATION")) solver.set_speculation(false);
+  // slpb_solve_trial / slpb_accept_relinearize: three host round trips per
+  // iteration instead of five (development switch: the call-per-step path)
+  const bool merged_calls = std::getenv("SLPB_NO_MERGED_CALLS") == nullptr;
 
   constexpr Scalar alpha_reduction_factor(0.5);
   constexpr Scalar alpha_min(1e-7);
@@ -477,6 +480,7 @@ ExitStatus interior_point(
 
     Scalar alpha_max(1), alpha(1), alpha_z(1);
     bool call_feasibility_restoration = false;
+    bool relinearized = false;
 
     // lhs assembly + factorisation with inertia correction (:426-465)
     // The right-hand side does not depend on δ/γ: build it first so that the
@@ -488,9 +492,22 @@ ExitStatus interior_point(
       return ExitStatus::FACTORIZATION_FAILED;  // newton.hpp:183 carries on
     }
 
-    // rhs, solve, step recovery, fraction-to-the-boundary (:444-497)
+    // rhs, solve, step recovery, fraction-to-the-boundary (:444-497) — and,
+    // in the same host round trip, the trial point at the full step
+    // (slpb_solve_trial): the first trial of the line search below.
     slpb_step_info step{};
-    SLP_DEVICE_CALL(dev, slpb_solve(dev, mu, tau, &step));
+    slpb_point_info trial{};
+    const int slack_from_ci =
+        options.feasible_ipm && cur.ci_all_positive ? 1 : 0;
+    bool have_full_step_trial = false;
+    if (merged_calls) {
+      SLP_DEVICE_CALL(dev, slpb_solve_trial(dev, mu, tau,
+                                            kind != SolverKind::IPM ? 1 : 0,
+                                            slack_from_ci, &step, &trial));
+      have_full_step_trial = true;
+    } else {
+      SLP_DEVICE_CALL(dev, slpb_solve(dev, mu, tau, &step));
+    }
     ++it_solves;
     alpha_max = step.alpha_max;
     alpha = alpha_max;
@@ -502,15 +519,16 @@ ExitStatus interior_point(
                                             cur.ce_l1 + cur.cis_l1};  // :499
     const Scalar D_phi = step.g_dot_px - mu * step.sinv_dot_ps;       // :508
 
-    slpb_point_info trial{};
     slpb_step_info accepted_step = step;
     while (true) {  // :512-717
       ++it_trials;
-      const int slack_from_ci =
-          options.feasible_ipm && cur.ci_all_positive ? 1 : 0;
       if (kind != SolverKind::IPM) alpha_z = alpha;
-      SLP_DEVICE_CALL(dev,
-                      slpb_trial(dev, alpha, alpha_z, 0, slack_from_ci, &trial));
+      if (have_full_step_trial) {
+        have_full_step_trial = false;  // α = α_max: already evaluated
+      } else {
+        SLP_DEVICE_CALL(
+            dev, slpb_trial(dev, alpha, alpha_z, 0, slack_from_ci, &trial));
+      }
 
       constexpr int kTrialFinite =
           SLPB_FINITE_F | SLPB_FINITE_C_E | SLPB_FINITE_C_I;
@@ -650,19 +668,29 @@ ExitStatus interior_point(
     } else {
       if (alpha == alpha_max) full_step_rejected_counter = 0;  // :774-776
       // x, s, y, z, f, c_e, c_i ← trial; clamp z (:779-805)
-      SLP_DEVICE_CALL(dev, slpb_accept(dev, mu));
-      cur = trial;
+      if (merged_calls) {
+        // … re-linearise and reduce the errors in the same round trip
+        int32_t finite = 0;
+        SLP_DEVICE_CALL(dev, slpb_accept_relinearize(dev, mu, &finite, &kkt));
+        cur = trial;
+        cur.finite = finite;
+        relinearized = true;
+      } else {
+        SLP_DEVICE_CALL(dev, slpb_accept(dev, mu));
+        cur = trial;
+      }
     }
 
-    // Re-linearise: A_e, A_i, g, H at the new iterate (:809-812)
-    {
+    if (!relinearized) {
+      // Re-linearise: A_e, A_i, g, H at the new iterate (:809-812)
       slpb_point_info derivs{};
       SLP_DEVICE_CALL(dev, slpb_eval_current(dev, 2, &derivs));
       cur.finite = derivs.finite;
+      // error reductions (:815-832)
+      SLP_DEVICE_CALL(dev, slpb_kkt_stats_current(dev, mu, &kkt));
     }
 
     // E_0 and the barrier update (:815-832)
-    SLP_DEVICE_CALL(dev, slpb_kkt_stats_current(dev, mu, &kkt));
     E_0 = detail::kkt_error_unscaled_mu0(kkt, me, mi);
     if (kind == SolverKind::IPM && E_0 > Scalar(options.tolerance)) {
       constexpr Scalar kappa_eps(10);

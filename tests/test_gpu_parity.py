@@ -302,6 +302,52 @@ KNOWN = [("lp_maximize", "SUCCESS", (375, 250), 1e-6),
          ("diverging", "DIVERGING_ITERATES", None, 0)]
 
 
+def _fields(st):
+    return [getattr(st, f) for f, _ in st._fields_]
+
+
+@pytest.mark.parametrize("name,N,sqp", [("cart_pole", 60, 0), ("cart_pole_eq", 30, 1)])
+def test_merged_calls_equal_the_separate_ones(name, N, sqp):
+    """slpb_solve_trial and slpb_accept_relinearize (three host round trips per
+    iteration instead of five) return, bit for bit, what slpb_solve +
+    slpb_trial and slpb_accept + slpb_eval_current + slpb_kkt_stats_current
+    return, and leave the same iterate behind."""
+    P, O = sb.Problem(name, N), OracleProblem(name, N)
+    O.eval_setup()
+    d_f, d_ce, d_ci = O.scaling()
+    D = P.open_device()
+    D.set_scaling(d_f, d_ce, d_ci)
+    x, s, y, z = _state(P, O, 5)
+    mu, tau = 0.05, 0.99
+
+    def run(merged):
+        D.set_iterate(x, s, y, z)
+        D.eval_current(1)
+        D.analyze()
+        D.prepare_rhs(mu)
+        D.factor(1.0, 1e-6, True)
+        if merged:
+            si, ti = D.solve_trial(mu, tau, sqp)
+            finite, ks = D.accept_relinearize(mu)
+        else:
+            si = D.solve(mu, tau)
+            ti = D.trial(si.alpha_max, si.alpha_max if sqp else si.alpha_z)
+            D.accept(mu)
+            finite = D.eval_current(2).finite
+            ks = D.kkt_stats(mu)
+        return (_fields(si), _fields(ti), finite & 0x78, _fields(ks),
+                D.get_iterate(), D.download(sb.ARR_G), D.download(sb.ARR_H_VAL))
+    a, b = run(False), run(True)
+    for k in (0, 1, 3):
+        np.testing.assert_array_equal(np.array(a[k], float), np.array(b[k], float))
+    assert a[2] == b[2]
+    for u, v in zip(a[4], b[4]):
+        np.testing.assert_array_equal(u, v)
+    np.testing.assert_array_equal(a[5], b[5])
+    np.testing.assert_array_equal(a[6], b[6])
+    P.close_device(); P.close(); O.close()
+
+
 @pytest.mark.parametrize("name,status,expect,tol", KNOWN)
 def test_reference_known_answers_on_gpu(name, status, expect, tol):
     """The reference's own solution-level tests (test/src/optimization/*),
