@@ -955,7 +955,14 @@ __global__ void k_unpermute(const double* __restrict__ xperm,
 // per-front counter in global memory.
 // ---------------------------------------------------------------------------
 
-constexpr int kTreeWarps = 8;
+// Warps per block of the tree kernels. k_factor_tree needs 168 registers per
+// thread, i.e. 12 resident warps per SM: 3 blocks of 4 reach that, 1 block of
+// 8 does not (measured: 0.198 → 0.189 ms per factorisation at N=5000; capping
+// the registers to fit more warps costs more in spills than it gains).
+#ifndef SLPB_TREE_WARPS
+#define SLPB_TREE_WARPS 4
+#endif
+constexpr int kTreeWarps = SLPB_TREE_WARPS;
 
 __device__ __forceinline__ int ld_acquire_gpu(const int* p) {
   int v;
@@ -1018,7 +1025,10 @@ struct FactorPair {
   double* uvecs;      // variant v: uvecs + v·uvec_stride
 };
 
-__global__ void __launch_bounds__(kTreeWarps * 32)
+#ifndef SLPB_TREE_MIN_BLOCKS
+#define SLPB_TREE_MIN_BLOCKS 1
+#endif
+__global__ void __launch_bounds__(kTreeWarps * 32, SLPB_TREE_MIN_BLOCKS)
 k_factor_tree(TreeView T, const double* __restrict__ Kval, double delta,
               double gamma, FactorPair pair, double* __restrict__ panels,
               double* updates, double* __restrict__ D,
@@ -2124,7 +2134,13 @@ int slpb_analyze(slpb_solver* S, int ordering, const int32_t* perm,
   {
     const int tree_smem =
         kTreeWarps * S->tree_smem_doubles * static_cast<int>(sizeof(double));
-    if (S->use_tree) CU(raise_dynamic_smem(k_factor_tree, tree_smem));
+    if (S->use_tree) {
+      CU(raise_dynamic_smem(k_factor_tree, tree_smem));
+      // registers, not shared memory, should bound the resident blocks
+      CU(cudaFuncSetAttribute(k_factor_tree,
+                              cudaFuncAttributePreferredSharedMemoryCarveout,
+                              50));
+    }
     // Persistent grids: as many blocks as are resident at once (SMs × blocks
     // per SM at this kernel's register and shared-memory footprint), never more
     // than there is work for. Fronts are handed out by ticket, so blocks of a
@@ -2141,8 +2157,10 @@ int slpb_analyze(slpb_solver* S, int ordering, const int32_t* perm,
     const int useful = blocks_for(2 * Y.n_super, kTreeWarps);
     S->tree_blocks =
         std::max(1, std::min(useful, sms * std::max(1, per_sm_factor)));
+    // (the solve's warps mostly wait on flags: 16 per SM are plenty)
     S->solve_blocks = std::max(
-        1, std::min(useful, sms * std::min(2, std::max(1, per_sm_solve))));
+        1, std::min(useful, sms * std::min(std::max(1, 16 / kTreeWarps),
+                                           std::max(1, per_sm_solve))));
   }
   CU(cudaStreamSynchronize(S->stream));
   SymbolicView& V = S->sview;
