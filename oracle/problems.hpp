@@ -173,6 +173,52 @@ std::unique_ptr<Problem<B>> double_integrator_problem(int N) {
   return problem;
 }
 
+/// arm_on_elevator_problem_test.cpp:27-122 with dt = 4 s / N.
+template <class B>
+std::unique_ptr<Problem<B>> arm_on_elevator_problem(int N) {
+  using M = Mat<B>;
+  using V = Var<B>;
+  constexpr double pi = std::numbers::pi;
+  const double dt = 4.0 / N;
+  auto problem = std::make_unique<Problem<B>>();
+  M elevator = problem->decision_variable(2, N + 1);
+  M elevator_accel = problem->decision_variable(1, N);
+  M arm = problem->decision_variable(2, N + 1);
+  M arm_accel = problem->decision_variable(1, N);
+  for (int k = 0; k < N; ++k) {
+    problem->subject_to_eq(
+        {elevator(0, k + 1) -
+         (elevator(0, k) + elevator(1, k) * V{dt} +
+          V{0.5} * elevator_accel(0, k) * V{dt} * V{dt})});
+    problem->subject_to_eq(
+        {elevator(1, k + 1) -
+         (elevator(1, k) + elevator_accel(0, k) * V{dt})});
+    problem->subject_to_eq(
+        {arm(0, k + 1) - (arm(0, k) + arm(1, k) * V{dt} +
+                          V{0.5} * arm_accel(0, k) * V{dt} * V{dt})});
+    problem->subject_to_eq(
+        {arm(1, k + 1) - (arm(1, k) + arm_accel(0, k) * V{dt})});
+  }
+  problem->subject_to_eq(eq(elevator.col(0), M::constants(2, 1, {1.0, 0.0})));
+  problem->subject_to_eq(eq(elevator.col(N), M::constants(2, 1, {1.25, 0.0})));
+  problem->subject_to_eq(eq(arm.col(0), M::constants(2, 1, {0.0, 0.0})));
+  problem->subject_to_eq(eq(arm.col(N), M::constants(2, 1, {pi, 0.0})));
+  problem->subject_to_ineq(bounds(V{-1.0}, elevator.row(1), V{1.0}));
+  problem->subject_to_ineq(bounds(V{-2.0}, elevator_accel, V{2.0}));
+  problem->subject_to_ineq(bounds(V{-2.0 * pi}, arm.row(1), V{2.0 * pi}));
+  problem->subject_to_ineq(bounds(V{-4.0 * pi}, arm_accel, V{4.0 * pi}));
+  M sines{1, N + 1};
+  for (int k = 0; k < N + 1; ++k) sines(0, k) = sin(arm(0, k));
+  M heights = elevator.row(0) + V{1.0} * sines;
+  problem->subject_to_ineq(le(heights, V{1.8}));
+  V J{0.0};
+  for (int k = 0; k < N + 1; ++k) {
+    J += pow(V{1.25} - elevator(0, k), 2.0) + pow(V{pi} - arm(0, k), 2.0);
+  }
+  problem->minimize(J);
+  return problem;
+}
+
 // ---- slp::OCP (optimization/ocp.hpp:49-414) ----------------------------------
 enum class OcpDynamics { EXPLICIT_ODE, DISCRETE };
 enum class OcpTimestep { FIXED, VARIABLE_SINGLE, VARIABLE };
@@ -757,6 +803,7 @@ std::unique_ptr<Problem<B>> make_problem(const std::string& name, int N,
   }
   if (name == "chained_rosenbrock") return chained_rosenbrock_problem<B>(N);
   if (name == "double_integrator") return double_integrator_problem<B>(N);
+  if (name == "arm_on_elevator") return arm_on_elevator_problem<B>(N);
   if (name == "flywheel_ocp") {
     return flywheel_ocp_problem<B>(N, static_cast<int>(p0),
                                    static_cast<int>(p1));

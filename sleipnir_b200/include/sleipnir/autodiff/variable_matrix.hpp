@@ -15,6 +15,7 @@
 #include <span>
 #include <type_traits>
 #include <utility>
+#include <functional>
 #include <vector>
 
 #include "sleipnir/autodiff/variable.hpp"
@@ -132,6 +133,17 @@ class VariableMatrix : public SleipnirBase {
     return out;
   }
 
+  /// Applies a unary operator to every element, row-major
+  /// (variable_matrix.hpp:1027-1039).
+  VariableMatrix cwise_transform(
+      const std::function<V(const V& x)>& unary_op) const {
+    VariableMatrix out{detail::empty, m_rows, m_cols};
+    for (int r = 0; r < m_rows; ++r) {
+      for (int c = 0; c < m_cols; ++c) out(r, c) = unary_op((*this)(r, c));
+    }
+    return out;
+  }
+
   void set_value(const Matrix<Scalar>& values) {
     slp_assert(values.rows() == m_rows && values.cols() == m_cols);
     for (int r = 0; r < m_rows; ++r) {
@@ -219,6 +231,10 @@ class VariableBlock : public SleipnirBase {
   VariableBlock col(int c) const { return block(0, c, m_rows, 1); }
 
   VariableMatrix<Scalar> T() const { return VariableMatrix<Scalar>{*this}.T(); }
+  VariableMatrix<Scalar> cwise_transform(
+      const std::function<V(const V& x)>& unary_op) const {
+    return VariableMatrix<Scalar>{*this}.cwise_transform(unary_op);
+  }
 
   void set_value(const Matrix<Scalar>& values) const {
     for (int r = 0; r < m_rows; ++r) {

@@ -342,6 +342,63 @@ inline std::unique_ptr<slp::Problem<double>> double_integrator(int N) {
   return P;
 }
 
+/// arm_on_elevator_problem_test.cpp:27-122 with dt = 4 s / N: two double
+/// integrators coupled by a nonlinear end-effector height limit.
+inline std::unique_ptr<slp::Problem<double>> arm_on_elevator(int N) {
+  using T = double;
+  constexpr T ELEVATOR_START_HEIGHT(1), ELEVATOR_END_HEIGHT(1.25);
+  constexpr T ELEVATOR_MAX_VELOCITY(1), ELEVATOR_MAX_ACCELERATION(2);
+  constexpr T ARM_LENGTH(1), ARM_START_ANGLE(0);
+  constexpr T ARM_END_ANGLE(std::numbers::pi);
+  constexpr T ARM_MAX_VELOCITY(2.0 * std::numbers::pi);
+  constexpr T ARM_MAX_ACCELERATION(4.0 * std::numbers::pi);
+  constexpr T END_EFFECTOR_MAX_HEIGHT(1.8);
+  const T dt = T(4) / T(N);
+  auto P = std::make_unique<slp::Problem<T>>();
+  auto& problem = *P;
+  auto elevator = problem.decision_variable(2, N + 1);
+  auto elevator_accel = problem.decision_variable(1, N);
+  auto arm = problem.decision_variable(2, N + 1);
+  auto arm_accel = problem.decision_variable(1, N);
+  for (int k = 0; k < N; ++k) {
+    problem.subject_to(elevator[0, k + 1] ==
+                       elevator[0, k] + elevator[1, k] * dt +
+                           T(0.5) * elevator_accel[0, k] * dt * dt);
+    problem.subject_to(elevator[1, k + 1] ==
+                       elevator[1, k] + elevator_accel[0, k] * dt);
+    problem.subject_to(arm[0, k + 1] ==
+                       arm[0, k] + arm[1, k] * dt +
+                           T(0.5) * arm_accel[0, k] * dt * dt);
+    problem.subject_to(arm[1, k + 1] == arm[1, k] + arm_accel[0, k] * dt);
+  }
+  problem.subject_to(elevator.col(0) ==
+                     slp::Matrix<T>{{ELEVATOR_START_HEIGHT}, {0.0}});
+  problem.subject_to(elevator.col(N) ==
+                     slp::Matrix<T>{{ELEVATOR_END_HEIGHT}, {0.0}});
+  problem.subject_to(arm.col(0) == slp::Matrix<T>{{ARM_START_ANGLE}, {0.0}});
+  problem.subject_to(arm.col(N) == slp::Matrix<T>{{ARM_END_ANGLE}, {0.0}});
+  problem.subject_to(slp::bounds(-ELEVATOR_MAX_VELOCITY, elevator.row(1),
+                                 ELEVATOR_MAX_VELOCITY));
+  problem.subject_to(slp::bounds(-ELEVATOR_MAX_ACCELERATION, elevator_accel,
+                                 ELEVATOR_MAX_ACCELERATION));
+  problem.subject_to(
+      slp::bounds(-ARM_MAX_VELOCITY, arm.row(1), ARM_MAX_VELOCITY));
+  problem.subject_to(
+      slp::bounds(-ARM_MAX_ACCELERATION, arm_accel, ARM_MAX_ACCELERATION));
+  auto heights =
+      elevator.row(0) +
+      ARM_LENGTH * arm.row(0).cwise_transform(
+                       [](const slp::Variable<T>& x) { return sin(x); });
+  problem.subject_to(heights <= END_EFFECTOR_MAX_HEIGHT);
+  slp::Variable<T> J = T(0);
+  for (int k = 0; k < N + 1; ++k) {
+    J += pow(ELEVATOR_END_HEIGHT - elevator[0, k], T(2)) +
+         pow(ARM_END_ANGLE - arm[0, k], T(2));
+  }
+  problem.minimize(J);
+  return P;
+}
+
 // ---- the reference's OCP tests, written against slp::OCP ---------------------
 
 /// flywheel_ocp_test.cpp:38-201 with dt = 5 s / N. method: 0 direct
@@ -629,6 +686,7 @@ inline std::unique_ptr<slp::Problem<double>> make_problem(
   if (name == "flywheel_eq") return flywheel(N, p0 > 0 ? p0 : 5.0, false);
   if (name == "chained_rosenbrock") return chained_rosenbrock(N);
   if (name == "double_integrator") return double_integrator(N);
+  if (name == "arm_on_elevator") return arm_on_elevator(N);
   if (name == "flywheel_ocp") {
     return flywheel_ocp(N, static_cast<int>(p0), p1 != 0.0);
   }

@@ -692,6 +692,31 @@ def test_double_integrator_matches_oracle_and_reference_profile():
     P.close(); O.close()
 
 
+def test_arm_on_elevator_matches_oracle():
+    """arm_on_elevator_problem_test.cpp:27-122 at its own size (N = 800:
+    4 804 variables, 3 208 equality and 7 205 inequality constraints, one of
+    them nonlinear per step): SUCCESS like the reference test demands, the
+    oracle's decisions and iterates, the golden optimum."""
+    N = 800
+    P = sb.Problem("arm_on_elevator", N)
+    st = P.solve(keep_iterates=True)
+    tr = P.trace()
+    D = P.open_device(); D.analyze(); perm = D.permutation(); P.close_device()
+    O = OracleProblem("arm_on_elevator", N)
+    so = O.solve(perm=perm, force_sparse=1)
+    to = O.trace()
+    assert sb.EXIT_STATUS[st] == EXIT_STATUS[so] == "SUCCESS"
+    assert len(tr) == len(to)
+    for a, b in zip(tr, to):
+        assert a.factorizations == b.factorizations and a.trials == b.trials
+        assert a.delta == b.delta and a.mu == b.mu
+        assert rel(a.x, b.x) < 1e-7
+    g = np.load(os.path.join(GOLDEN, f"solve_arm_on_elevator_{N}.npz"))
+    assert len(tr) == int(g["iterations"])
+    np.testing.assert_allclose(P.solution()[0], g["x"], atol=1e-6)
+    P.close(); O.close()
+
+
 def test_spy_files_and_diagnostics(tmp_path, capfd):
     """problem_spy_test.cpp:64-158: solve(options{diagnostics}, spy = true)
     writes H.spy / A_e.spy / A_i.spy, one frame per iteration, in the

@@ -44,6 +44,20 @@ KNOWN = [
 ]
 
 
+def test_arm_on_elevator_succeeds():
+    # arm_on_elevator_problem_test.cpp:27-122 REQUIREs SUCCESS at N = 800
+    P = OracleProblem("arm_on_elevator", 800)
+    assert EXIT_STATUS[P.solve()] == "SUCCESS"
+    x, *_ = P.solution()
+    N = 800
+    elevator = x[:2 * (N + 1)].reshape(2, N + 1)
+    arm = x[2 * (N + 1) + N:2 * (N + 1) + N + 2 * (N + 1)].reshape(2, N + 1)
+    assert abs(elevator[0, 0] - 1.0) < 1e-8 and abs(elevator[0, N] - 1.25) < 1e-8
+    assert abs(arm[0, 0]) < 1e-8 and abs(arm[0, N] - np.pi) < 1e-8
+    assert np.all(elevator[0] + np.sin(arm[0]) <= 1.8 + 1e-6)
+    P.close()
+
+
 def test_double_integrator_profile():
     # double_integrator_problem_test.cpp:27-127: accelerate, coast, brake
     N = 700
