@@ -241,7 +241,7 @@ void slpbh_add_recording_callback(void* h, int stop_at, int persistent) {
   Handle* hd = H(h);
   auto cb = [hd, stop_at](const slp::IterationInfo<double>& info) -> bool {
     double xinf = 0.0;
-    for (size_t i = 0; i < info.x.size(); ++i) {
+    for (int i = 0; i < static_cast<int>(info.x.size()); ++i) {
       xinf = std::max(xinf, std::abs(info.x[i]));
     }
     const double rec[8] = {double(info.iteration), double(info.x.size()), xinf,
