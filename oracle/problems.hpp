@@ -533,6 +533,28 @@ std::unique_ptr<Problem<B>> small_problem(const std::string& name, double p0,
   } else if (name == "no_cost_unconstrained") {  // :26-66
     M X = P->decision_variable(2, 3);
     for (int i = 0; i < 6; ++i) X[i].set_value(p0);
+  } else if (name == "all_ops") {
+    // every operation of autodiff/expression.hpp once (see the product's
+    // problems.hpp): golden vectors from the reference core pin them
+    M v = P->decision_variable(6, 1);
+    const double guess[6] = {0.3, 0.5, 0.7, 1.1, 1.3, 0.9};
+    for (int i = 0; i < 6; ++i) v[i].set_value(guess[i]);
+    V x0 = v[0], x1 = v[1], x2 = v[2], x3 = v[3], x4 = v[4], x5 = v[5];
+    V J = abs(x0 - V{0.1}) + acos(x0 * x1) + asin(x1 * x2) + atan(x2 * x3) +
+          atan2(x3, x4) + cbrt(x4 * x5 + V{1}) + cosh(x0) + erf(x1) +
+          exp(x2 * V{0.5}) + hypot(x3, x5) + log(x4 + V{1}) +
+          log10(x5 + V{2});
+    P->minimize(J);
+    P->subject_to_eq({sin(x0) * cos(x1) - V{0.2}});
+    P->subject_to_eq({x2 * x3 / (x4 + V{1}) - V{0.3}});
+    P->subject_to_eq({max(x0 * x0, x1) + min(x2 * x3, x4) + pow(x3, x5) +
+                      pow(x0 + V{2}, 2.5) - V{12}});
+    P->subject_to_ineq(le1(hypot3(x0, x1, x2), V{5}));
+    P->subject_to_ineq(le1(exp(x3) * tanh(x4), V{40}));
+    P->subject_to_ineq(ge1(sign(x1) * x2 + sinh(x3) + tan(x4 * V{0.3}) +
+                               tanh(x5) + sqrt(x0 + x1 + V{1}),
+                           V{0}));
+    P->subject_to_ineq(ge1(x5, V{-1}));
   } else if (name == "spy_test") {  // problem_spy_test.cpp:64-85
     V x = P->decision_variable();
     V y = P->decision_variable();

@@ -87,6 +87,12 @@ ORC_BINARY(atan2) ORC_BINARY(hypot) ORC_BINARY(max) ORC_BINARY(min)
 ORC_BINARY(pow)
 #undef ORC_BINARY
 
+/// hypot(x, y, z) = sqrt(x² + y² + z²) (variable.hpp:711-714).
+template <class B>
+Var<B> hypot3(const Var<B>& x, const Var<B>& y, const Var<B>& z) {
+  return sqrt(pow(x, 2.0) + pow(y, 2.0) + pow(z, 2.0));
+}
+
 /// Dense row-major matrix of Var handles (variable_matrix.hpp). Blocks are
 /// taken by copy of the handles (the nodes are shared), written with
 /// set_block — the oracle's builders do not need view types.

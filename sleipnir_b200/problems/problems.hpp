@@ -600,6 +600,33 @@ inline std::unique_ptr<slp::Problem<double>> small_problem(
   } else if (name == "no_cost_unconstrained") {  // :26-66
     auto X = problem.decision_variable(2, 3);
     for (int i = 0; i < 6; ++i) X[i].set_value(p0);
+  } else if (name == "all_ops") {
+    // every opcode of the tape (include/slpb.h, slpb_op) in the cost, an
+    // equality and an inequality constraint, so that golden vectors from the
+    // reference's own expression core pin value, gradient and Hessian of each
+    auto v = problem.decision_variable(6);
+    const double guess[6] = {0.3, 0.5, 0.7, 1.1, 1.3, 0.9};
+    for (int i = 0; i < 6; ++i) v[i].set_value(guess[i]);
+    slp::Variable<T> x0 = v[0], x1 = v[1], x2 = v[2], x3 = v[3], x4 = v[4],
+                     x5 = v[5];
+    // (fewer than 16 root terms per sum: a longer one would be cut into
+    // per-term sub-rows, which moves the last bit of some adjoints)
+    slp::Variable<T> J =
+        abs(x0 - T(0.1)) + acos(x0 * x1) + asin(x1 * x2) + atan(x2 * x3) +
+        atan2(x3, x4) + cbrt(x4 * x5 + T(1)) + cosh(x0) + erf(x1) +
+        exp(x2 * T(0.5)) + hypot(x3, x5) + log(x4 + T(1)) + log10(x5 + T(2));
+    problem.minimize(J);
+    problem.subject_to(sin(x0) * cos(x1) == T(0.2));
+    problem.subject_to(x2 * x3 / (x4 + T(1)) == T(0.3));
+    problem.subject_to(max(x0 * x0, x1) + min(x2 * x3, x4) + pow(x3, x5) +
+                           pow(x0 + T(2), T(2.5)) ==
+                       T(12));
+    problem.subject_to(hypot(x0, x1, x2) <= T(5));
+    problem.subject_to(exp(x3) * tanh(x4) <= T(40));
+    problem.subject_to(sign(x1) * x2 + sinh(x3) + tan(x4 * T(0.3)) +
+                           tanh(x5) + sqrt(x0 + x1 + T(1)) >=
+                       T(0));
+    problem.subject_to(x5 >= T(-1));
   } else if (name == "spy_test") {  // problem_spy_test.cpp:64-85
     auto x = problem.decision_variable();
     auto y = problem.decision_variable();

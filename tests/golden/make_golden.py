@@ -29,6 +29,7 @@ EVAL_CASES = [("cart_pole", 8, 0.0, 0.0), ("cart_pole", 40, 0.0, 0.0),
               ("cart_pole_eq", 12, 0.0, 0.0),
               ("min_distance_line", 0, 0.0, 0.0),
               # slp::OCP front end (optimization/ocp.hpp)
+              ("all_ops", 0, 0.0, 0.0),
               ("double_integrator", 40, 0.0, 0.0),
               ("arm_on_elevator", 30, 0.0, 0.0),
               ("flywheel_ocp", 30, 0.0, 0.0),
