@@ -306,7 +306,9 @@ def main():
         # (3) the library's data-parallel axis: B independent solves in flight
         #     on this GPU (slp::multistart, one host thread + stream each).
         ms = None
-        if args.multistart > 1 and not shard:
+        # (skipped when the ranks would not have a few host cores each for
+        #  the starts' setup threads)
+        if args.multistart > 1 and not shard and (cores or 1) // world >= 4:
             if world > 1:
                 dist.barrier()
             ms = sb.multistart("cart_pole", N, [5.0] * args.multistart,
