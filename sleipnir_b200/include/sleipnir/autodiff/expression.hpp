@@ -14,7 +14,9 @@
 
 #include <algorithm>
 #include <cmath>
+#include <atomic>
 #include <cstdint>
+#include <mutex>
 #include <numbers>
 #include <utility>
 #include <vector>
@@ -80,9 +82,75 @@ class ExpressionPool {
   int64_t m_live = 0;
 };
 
+namespace pool_detail {
+
+/// In a shared library every access to a thread_local goes through the dynamic
+/// loader (__tls_get_addr), and the pool is reached on every handle copy —
+/// a third of the graph-construction time. The thread that builds the graphs
+/// is almost always one and the same, so its pool is also published in a
+/// process-wide slot keyed by the thread pointer (one register read): that
+/// thread skips the TLS machinery, every other thread takes the ordinary path.
+struct FastSlot {
+  std::atomic<void*> owner{nullptr};  // thread pointer of the owning thread
+  ExpressionPool* pool = nullptr;
+};
+inline FastSlot& fast_slot() {
+  static FastSlot slot;
+  return slot;
+}
+inline void* thread_key() {
+#if defined(__GNUC__) && (defined(__x86_64__) || defined(__aarch64__))
+  return __builtin_thread_pointer();
+#else
+  return nullptr;  // no fast path: always the thread_local
+#endif
+}
+
+/// The thread's pool; claims the fast slot if nobody holds it and gives it
+/// back when the thread ends.
+struct ThreadPool {
+  ExpressionPool pool;
+  bool owns_slot = false;
+  ThreadPool() {
+    void* me = thread_key();
+    void* expected = nullptr;
+    FastSlot& slot = fast_slot();
+    if (me != nullptr) {
+      // publish the pool before the owner becomes visible
+      if (slot.owner.load(std::memory_order_acquire) == nullptr) {
+        static std::mutex claim;
+        std::lock_guard<std::mutex> lock{claim};
+        if (slot.owner.load(std::memory_order_relaxed) == expected) {
+          slot.pool = &pool;
+          slot.owner.store(me, std::memory_order_release);
+          owns_slot = true;
+        }
+      }
+    }
+  }
+  ~ThreadPool() {
+    if (owns_slot) {
+      FastSlot& slot = fast_slot();
+      slot.owner.store(nullptr, std::memory_order_release);
+      slot.pool = nullptr;
+    }
+  }
+};
+
+inline ExpressionPool& slow_path() {
+  thread_local ThreadPool p;
+  return p.pool;
+}
+
+}  // namespace pool_detail
+
 inline ExpressionPool& pool() {
-  thread_local ExpressionPool p;
-  return p;
+  pool_detail::FastSlot& slot = pool_detail::fast_slot();
+  void* me = pool_detail::thread_key();
+  if (me != nullptr && slot.owner.load(std::memory_order_acquire) == me) {
+    return *slot.pool;
+  }
+  return pool_detail::slow_path();
 }
 
 /// Nullable owning handle (plays the role of ExpressionPtr).
