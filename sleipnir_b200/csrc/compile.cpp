@@ -102,27 +102,33 @@ Pattern pattern_from_positions(int32_t rows, int32_t cols,
   return p;
 }
 
-/// Growing gather description: sources are appended per final entry.
+/// Growing gather description: (entry, source, scale) records in arrival
+/// order; finish() groups them by entry with a stable counting sort, so every
+/// entry keeps its sources in the order they were added.
 struct GatherBuilder {
-  std::vector<std::vector<std::pair<int32_t, int32_t>>> src;  // (idx, scale)
-  explicit GatherBuilder(int64_t n) : src(n) {}
+  struct Record {
+    int64_t entry;
+    int32_t idx, scale;
+  };
+  int64_t n_entries;
+  std::vector<Record> records;
+  explicit GatherBuilder(int64_t n) : n_entries{n} {}
   void add(int64_t entry, int32_t stage, int32_t scale, bool negate = false) {
-    src[entry].emplace_back(negate ? (stage | int32_t(0x80000000)) : stage,
-                            scale);
+    records.push_back(
+        {entry, negate ? (stage | int32_t(0x80000000)) : stage, scale});
   }
   Gather finish() const {
     Gather g;
-    g.ptr.assign(src.size() + 1, 0);
-    for (size_t e = 0; e < src.size(); ++e) {
-      g.ptr[e + 1] = g.ptr[e] + static_cast<int32_t>(src[e].size());
-    }
-    g.src_idx.reserve(g.ptr.back());
-    g.src_scale.reserve(g.ptr.back());
-    for (const auto& list : src) {
-      for (auto [i, s] : list) {
-        g.src_idx.push_back(i);
-        g.src_scale.push_back(s);
-      }
+    g.ptr.assign(n_entries + 1, 0);
+    for (const Record& r : records) ++g.ptr[r.entry + 1];
+    for (int64_t e = 0; e < n_entries; ++e) g.ptr[e + 1] += g.ptr[e];
+    g.src_idx.resize(records.size());
+    g.src_scale.resize(records.size());
+    std::vector<int32_t> cursor(g.ptr.begin(), g.ptr.end() - 1);
+    for (const Record& r : records) {
+      const int32_t at = cursor[r.entry]++;
+      g.src_idx[at] = r.idx;
+      g.src_scale[at] = r.scale;
     }
     return g;
   }
@@ -139,6 +145,11 @@ struct Compiler {
   std::vector<int32_t> local;     // local slot in the current cluster
   std::vector<int32_t> owner;     // first sub-row that touched an interior node
   std::vector<int32_t> outcol;    // output column of a node in the current row
+  std::vector<int32_t> term_count;  // split_row: flattened terms under a sum
+  // split_row's work lists (one allocation for all rows)
+  std::vector<int32_t> sr_order, sr_stack;
+  std::vector<std::pair<int32_t, int8_t>> sr_terms, sr_signed_stack;
+  std::vector<uint8_t> sr_spine;
   int32_t stamp_counter = 0;
 
   Compiler(const Tape& t, std::string& err) : tape{t}, error{err} {
@@ -147,6 +158,7 @@ struct Compiler {
     stamp.assign(t.n_nodes, 0);
     local.assign(t.n_nodes, -1);
     outcol.assign(t.n_nodes, -1);
+    term_count.assign(t.n_nodes, 0);
   }
 
   bool is_interior(int32_t node) const { return tape.lhs[node] >= 0; }
@@ -167,9 +179,13 @@ struct Compiler {
     auto expandable = [&](int32_t nd) {
       return is_sum_op(tape.op[nd]) && (nd == root || cnt[nd] == 1);
     };
-    std::unordered_map<int32_t, int32_t> n_terms;
+    // (node-indexed scratch, 0 = not an expandable sum; reset below)
+    std::vector<int32_t>& n_terms = term_count;
+    std::vector<int32_t>& order = sr_order;
+    order.clear();
     {
-      std::vector<int32_t> order, st{root};
+      std::vector<int32_t>& st = sr_stack;
+      st.assign(1, root);
       while (!st.empty()) {
         const int32_t nd = st.back();
         st.pop_back();
@@ -179,10 +195,7 @@ struct Compiler {
         if (tape.op[nd] != SLPB_OP_NEG) st.push_back(tape.rhs[nd]);
       }
       for (auto it = order.rbegin(); it != order.rend(); ++it) {
-        auto count = [&](int32_t ch) {
-          auto f = n_terms.find(ch);
-          return f == n_terms.end() ? 1 : f->second;
-        };
+        auto count = [&](int32_t ch) { return std::max(n_terms[ch], 1); };
         int32_t c = count(tape.lhs[*it]);
         if (tape.op[*it] != SLPB_OP_NEG) c += count(tape.rhs[*it]);
         n_terms[*it] = c;
@@ -193,9 +206,12 @@ struct Compiler {
     // order of the reference's sweep survive. A right operand stays one term
     // (x + (a + b) is not (x + a) + b) unless it is itself a long sum, which
     // must be cut to keep clusters small; that reassociates it (a few ulp).
-    std::vector<std::pair<int32_t, int8_t>> terms;
-    std::vector<std::pair<int32_t, int8_t>> stack{{root, int8_t(1)}};
-    std::vector<uint8_t> on_spine{1};
+    std::vector<std::pair<int32_t, int8_t>>& terms = sr_terms;
+    std::vector<std::pair<int32_t, int8_t>>& stack = sr_signed_stack;
+    std::vector<uint8_t>& on_spine = sr_spine;
+    terms.clear();
+    stack.assign(1, {root, int8_t(1)});
+    on_spine.assign(1, 1);
     while (!stack.empty()) {
       auto [nd, sg] = stack.back();
       const bool spine = on_spine.back() != 0;
@@ -219,6 +235,7 @@ struct Compiler {
       }
     }
     for (int32_t i = 0; i < len; ++i) cnt[list[i]] = 0;
+    for (int32_t nd : order) n_terms[nd] = 0;
 
     if (static_cast<int>(terms.size()) < kSplitThreshold) {
       make(int8_t(1), std::vector<int32_t>(list, list + len));
