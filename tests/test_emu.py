@@ -239,3 +239,22 @@ def test_ordering_keeps_every_multiplier_behind_a_neighbour(name, N):
         assert nbrs[d], "a multiplier without neighbours"
         assert min(pos[u] for u in nbrs[d]) < pos[d]
     E.close()
+
+
+@pytest.mark.parametrize("name,N", [
+    ("cart_pole", 100), ("cart_pole", 5000), ("flywheel", 200), ("gfold", 40),
+    ("gfold", 2000), ("cart_pole_eq", 30), ("chained_rosenbrock", 2000),
+    ("flywheel_eq", 400), ("flywheel_ocp", 100),
+    ("flywheel_ocp_collocation", 100), ("flywheel_ocp_shooting", 40),
+    ("flywheel_ocp_discrete", 100), ("cart_pole_ocp", 100),
+    ("differential_drive_ocp", 50), ("double_integrator", 700),
+    ("arm_on_elevator", 800), ("all_ops", 0)])
+def test_clusters_fit_one_thread_block(name, N, monkeypatch):
+    """Every problem the GPU tier solves compiles into clusters that fit the
+    224 KB of shared memory one thread block can have (kAdSmemMax in slpb.cu);
+    unbounded cluster fusion once chained all steps of a collocation OCP into
+    one 747 KB cluster."""
+    monkeypatch.setenv("SLPB_EMU_SMEM_BUDGET", str(224 * 1024))
+    E = Emu(name, N)
+    assert E.n > 0
+    E.close()
