@@ -219,6 +219,61 @@ std::unique_ptr<Problem<B>> arm_on_elevator_problem(int N) {
   return problem;
 }
 
+/// test/include/differential_drive_util.hpp:16-61.
+template <class B>
+Mat<B> differential_drive_dynamics(const Mat<B>& x, const Mat<B>& u) {
+  using M = Mat<B>;
+  using V = Var<B>;
+  constexpr double trackwidth = 0.699, Kv_l = 3.02, Ka_l = 0.642;
+  constexpr double Kv_a = 1.382, Ka_a = 0.08495;
+  constexpr double A1 = -(Kv_l / Ka_l + Kv_a / Ka_a) / 2.0;
+  constexpr double A2 = -(Kv_l / Ka_l - Kv_a / Ka_a) / 2.0;
+  constexpr double B1 = 0.5 / Ka_l + 0.5 / Ka_a;
+  constexpr double B2 = 0.5 / Ka_l - 0.5 / Ka_a;
+  M Am = M::constants(2, 2, {A1, A2, A2, A1});
+  M Bm = M::constants(2, 2, {B1, B2, B2, B1});
+  M xdot{5, 1};
+  V v = (x[3] + x[4]) / V{2.0};
+  xdot[0] = v * cos(x[2]);
+  xdot[1] = v * sin(x[2]);
+  xdot[2] = (x[4] - x[3]) / V{trackwidth};
+  xdot.set_block(3, 0, Am * x.segment(3, 2) + Bm * u);
+  return xdot;
+}
+
+/// differential_drive_problem_test.cpp:28-138 with dt = 5 s / N.
+template <class B>
+std::unique_ptr<Problem<B>> differential_drive_problem(int N) {
+  using M = Mat<B>;
+  using V = Var<B>;
+  const double dt = 5.0 / N;
+  auto problem = std::make_unique<Problem<B>>();
+  M X = problem->decision_variable(5, N + 1);
+  for (int k = 0; k < N; ++k) {
+    X(0, k).set_value(std::lerp(0.0, 1.0, static_cast<double>(k) / N));
+    X(1, k).set_value(std::lerp(0.0, 1.0, static_cast<double>(k) / N));
+  }
+  M U = problem->decision_variable(2, N);
+  problem->subject_to_eq(
+      eq(X.col(0), M::constants(5, 1, {0.0, 0.0, 0.0, 0.0, 0.0})));
+  problem->subject_to_eq(
+      eq(X.col(N), M::constants(5, 1, {1.0, 1.0, 0.0, 0.0, 0.0})));
+  problem->subject_to_ineq(bounds(V{-12.0}, U, V{12.0}));
+  for (int k = 0; k < N; ++k) {
+    problem->subject_to_eq(
+        eq(X.col(k + 1),
+           rk4<B>(differential_drive_dynamics<B>, X.col(k), U.col(k), dt)));
+  }
+  V J{0.0};
+  for (int k = 0; k < N; ++k) {
+    M xx = X.col(k).T() * X.col(k);
+    M uu = U.col(k).T() * U.col(k);
+    J += xx(0, 0) + uu(0, 0);
+  }
+  problem->minimize(J);
+  return problem;
+}
+
 // ---- slp::OCP (optimization/ocp.hpp:49-414) ----------------------------------
 enum class OcpDynamics { EXPLICIT_ODE, DISCRETE };
 enum class OcpTimestep { FIXED, VARIABLE_SINGLE, VARIABLE };
@@ -826,6 +881,7 @@ std::unique_ptr<Problem<B>> make_problem(const std::string& name, int N,
   if (name == "chained_rosenbrock") return chained_rosenbrock_problem<B>(N);
   if (name == "double_integrator") return double_integrator_problem<B>(N);
   if (name == "arm_on_elevator") return arm_on_elevator_problem<B>(N);
+  if (name == "differential_drive") return differential_drive_problem<B>(N);
   if (name == "flywheel_ocp") {
     return flywheel_ocp_problem<B>(N, static_cast<int>(p0),
                                    static_cast<int>(p1));

@@ -399,6 +399,60 @@ inline std::unique_ptr<slp::Problem<double>> arm_on_elevator(int N) {
   return P;
 }
 
+/// test/include/differential_drive_util.hpp:16-61.
+inline slp::VariableMatrix<double> differential_drive_dynamics(
+    const slp::VariableMatrix<double>& x, const slp::VariableMatrix<double>& u) {
+  using T = double;
+  constexpr T trackwidth = 0.699, Kv_linear = 3.02, Ka_linear = 0.642;
+  constexpr T Kv_angular = 1.382, Ka_angular = 0.08495;
+  constexpr T A1 = -(Kv_linear / Ka_linear + Kv_angular / Ka_angular) / T(2);
+  constexpr T A2 = -(Kv_linear / Ka_linear - Kv_angular / Ka_angular) / T(2);
+  constexpr T B1 = T(0.5) / Ka_linear + T(0.5) / Ka_angular;
+  constexpr T B2 = T(0.5) / Ka_linear - T(0.5) / Ka_angular;
+  const slp::Matrix<T> A{{A1, A2}, {A2, A1}};
+  const slp::Matrix<T> B{{B1, B2}, {B2, B1}};
+  slp::VariableMatrix<T> xdot{5};
+  auto v = (x[3] + x[4]) / T(2);
+  xdot[0] = v * cos(x[2]);
+  xdot[1] = v * sin(x[2]);
+  xdot[2] = (x[4] - x[3]) / trackwidth;
+  xdot.segment(3, 2) = A * x.segment(3, 2) + B * u;
+  return xdot;
+}
+
+/// differential_drive_problem_test.cpp:28-138 with dt = 5 s / N.
+inline std::unique_ptr<slp::Problem<double>> differential_drive(int N) {
+  using T = double;
+  const std::chrono::duration<T> dt{T(5) / N};
+  constexpr T u_max(12);
+  const slp::Matrix<T> x_initial{{0.0}, {0.0}, {0.0}, {0.0}, {0.0}};
+  const slp::Matrix<T> x_final{{1.0}, {1.0}, {0.0}, {0.0}, {0.0}};
+  auto P = std::make_unique<slp::Problem<T>>();
+  auto& problem = *P;
+  auto X = problem.decision_variable(5, N + 1);
+  for (int k = 0; k < N; ++k) {
+    X[0, k].set_value(std::lerp(x_initial(0, 0), x_final(0, 0), T(k) / T(N)));
+    X[1, k].set_value(std::lerp(x_initial(1, 0), x_final(1, 0), T(k) / T(N)));
+  }
+  auto U = problem.decision_variable(2, N);
+  problem.subject_to(X.col(0) == x_initial);
+  problem.subject_to(X.col(N) == x_final);
+  problem.subject_to(slp::bounds(-u_max, U, u_max));
+  for (int k = 0; k < N; ++k) {
+    problem.subject_to(
+        X.col(k + 1) ==
+        rk4<decltype(differential_drive_dynamics), slp::VariableMatrix<T>,
+            slp::VariableMatrix<T>>(differential_drive_dynamics, X.col(k),
+                                    U.col(k), dt));
+  }
+  slp::Variable<T> J = T(0);
+  for (int k = 0; k < N; ++k) {
+    J += X.col(k).T() * X.col(k) + U.col(k).T() * U.col(k);
+  }
+  problem.minimize(J);
+  return P;
+}
+
 // ---- the reference's OCP tests, written against slp::OCP ---------------------
 
 /// flywheel_ocp_test.cpp:38-201 with dt = 5 s / N. method: 0 direct
@@ -714,6 +768,7 @@ inline std::unique_ptr<slp::Problem<double>> make_problem(
   if (name == "chained_rosenbrock") return chained_rosenbrock(N);
   if (name == "double_integrator") return double_integrator(N);
   if (name == "arm_on_elevator") return arm_on_elevator(N);
+  if (name == "differential_drive") return differential_drive(N);
   if (name == "flywheel_ocp") {
     return flywheel_ocp(N, static_cast<int>(p0), p1 != 0.0);
   }

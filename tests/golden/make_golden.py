@@ -32,6 +32,7 @@ EVAL_CASES = [("cart_pole", 8, 0.0, 0.0), ("cart_pole", 40, 0.0, 0.0),
               ("all_ops", 0, 0.0, 0.0),
               ("double_integrator", 40, 0.0, 0.0),
               ("arm_on_elevator", 30, 0.0, 0.0),
+              ("differential_drive", 20, 0.0, 0.0),
               ("flywheel_ocp", 30, 0.0, 0.0),
               ("flywheel_ocp_collocation", 30, 0.0, 0.0),
               ("flywheel_ocp_shooting", 12, 0.0, 0.0),
@@ -52,6 +53,7 @@ SOLVE_CASES = [("flywheel", 50, 0.0, 0.0), ("cart_pole", 50, 0.0, 0.0),
                ("min_distance_line", 0, 0.0, 0.0),
                ("double_integrator", 700, 0.0, 0.0),
                ("arm_on_elevator", 800, 0.0, 0.0),
+               ("differential_drive", 100, 0.0, 0.0),
                ("flywheel_ocp", 100, 0.0, 0.0),
                ("flywheel_ocp_collocation", 100, 0.0, 0.0),
                ("flywheel_ocp_shooting", 40, 0.0, 0.0),

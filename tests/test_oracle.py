@@ -58,6 +58,41 @@ def test_arm_on_elevator_succeeds():
     P.close()
 
 
+def test_differential_drive_replay():
+    # differential_drive_problem_test.cpp:28-138: SUCCESS, and the states are
+    # the RK4 replay of the inputs to 1e-8
+    N = 100
+    dt = 5.0 / N
+    P = OracleProblem("differential_drive", N)
+    assert EXIT_STATUS[P.solve()] == "SUCCESS"
+    x, *_ = P.solution()
+    X = x[:5 * (N + 1)].reshape(5, N + 1)
+    U = x[5 * (N + 1):].reshape(2, N)
+    assert np.all(np.abs(U) <= 12.0 + 1e-9)
+    Kv_l, Ka_l, Kv_a, Ka_a, trackwidth = 3.02, 0.642, 1.382, 0.08495, 0.699
+    A1 = -(Kv_l / Ka_l + Kv_a / Ka_a) / 2.0
+    A2 = -(Kv_l / Ka_l - Kv_a / Ka_a) / 2.0
+    B1 = 0.5 / Ka_l + 0.5 / Ka_a
+    B2 = 0.5 / Ka_l - 0.5 / Ka_a
+    A, B = np.array([[A1, A2], [A2, A1]]), np.array([[B1, B2], [B2, B1]])
+
+    def f(s, u):
+        v = (s[3] + s[4]) / 2.0
+        return np.concatenate([[v * np.cos(s[2]), v * np.sin(s[2]),
+                                (s[4] - s[3]) / trackwidth], A @ s[3:] + B @ u])
+    state = np.zeros(5)
+    for k in range(N):
+        np.testing.assert_allclose(X[:, k], state, atol=1e-8)
+        u = U[:, k]
+        k1 = f(state, u)
+        k2 = f(state + dt * 0.5 * k1, u)
+        k3 = f(state + dt * 0.5 * k2, u)
+        k4 = f(state + dt * k3, u)
+        state = state + dt / 6.0 * (k1 + 2.0 * k2 + 2.0 * k3 + k4)
+    np.testing.assert_allclose(X[:, N], (1.0, 1.0, 0.0, 0.0, 0.0), atol=1e-8)
+    P.close()
+
+
 def test_double_integrator_profile():
     # double_integrator_problem_test.cpp:27-127: accelerate, coast, brake
     N = 700
