@@ -65,6 +65,21 @@ def test_fails_loudly_without_a_device():
     P.close()
 
 
+@pytest.mark.skipif(not _no_gpu(), reason="only meaningful without a GPU")
+def test_concurrent_graph_building_fails_loudly_too():
+    """slp::multistart builds one problem per host thread (each with its own
+    expression pool) before any start reaches the device: without a GPU all
+    eight threads must get as far as the device call and report it — no crash
+    in the thread-local pool machinery, no silent CPU path."""
+    for _ in range(3):
+        with pytest.raises(sb.DeviceError):
+            sb.multistart("cart_pole", 40, [5.0] * 8)
+    # the calling thread's DSL still works afterwards
+    P = sb.Problem("flywheel", 20)
+    assert (P.n, P.me, P.mi) == (41, 21, 40)
+    P.close()
+
+
 def test_trivial_problems_need_no_solver():
     """trivial_problem_test.cpp:14-66: an empty problem and one with neither
     cost nor constraints return SUCCESS before any solver (or device) is
