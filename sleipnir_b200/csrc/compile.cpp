@@ -1166,6 +1166,73 @@ bool compile_autodiff(const Tape& tape, const RowSet rows[SLPB_OUT_COUNT],
     }
   };
 
+  // ---- value sub-rows ------------------------------------------------------------
+  // The value programs (f, c_e, c_i) share nothing with the derivative
+  // programs but the tape and the row descriptors, both read-only here: they
+  // are compiled on a second thread, with a compiler (scratch) of their own,
+  // while this thread does the derivative set.
+  std::string value_error;
+  auto compile_values = [&]() -> bool {
+    StageTimer vtimer;
+    Compiler Cv{tape, value_error};
+    std::vector<SubRow> vsubs;
+    int32_t next_vstage = 0;
+    auto value_entry = [&](int which, int32_t row) -> int64_t {
+      return which == SLPB_OUT_F ? 0
+             : which == SLPB_OUT_C_E ? 1 + row : 1 + int64_t(me) + row;
+    };
+    std::vector<double> vconst;
+    struct PendingConst { int64_t entry; int32_t scale; double v; };
+    std::vector<PendingConst> pend;
+    for (int which : {SLPB_OUT_F, SLPB_OUT_C_E, SLPB_OUT_C_I}) {
+      const RowSet& rs = rows[which];
+      if (!rs.present) continue;
+      for (int32_t r = 0; r < rs.n_rows; ++r) {
+        const int32_t b = rs.row_ptr[r], e = rs.row_ptr[r + 1];
+        if (e == b) {
+          pend.push_back({value_entry(which, r), scale_of(which, r),
+                          rs.const_val.empty() ? 0.0 : rs.const_val[r]});
+          continue;
+        }
+        Cv.split_row(rs.row_nodes.data() + b, e - b,
+                    [&](int8_t seed, std::vector<int32_t> nodes) {
+                      SubRow sr;
+                      sr.out = which;
+                      sr.row = r;
+                      sr.seed = seed;
+                      sr.is_value = true;
+                      sr.value_stage = next_vstage;
+                      vgather.add(value_entry(which, r), next_vstage,
+                                  scale_of(which, r), seed < 0);
+                      ++next_vstage;
+                      sr.nodes = std::move(nodes);
+                      vsubs.push_back(std::move(sr));
+                    });
+      }
+    }
+    // constants go after the swept slots for the value stage
+    out.value_stage_init.assign(next_vstage, 0.0);
+    for (auto& p : pend) {
+      vgather.add(p.entry, static_cast<int32_t>(out.value_stage_init.size()),
+                  p.scale);
+      out.value_stage_init.push_back(p.v);
+    }
+    out.value_stage_size = static_cast<int32_t>(out.value_stage_init.size());
+    vtimer.lap("value sub-rows");
+    if (!Cv.build_programs(vsubs, out.values)) return false;
+    out.value_gather = vgather.finish();
+    vtimer.lap("build_programs(values) total");
+    return true;
+  };
+  bool values_ok = false;
+  std::thread values_thread{[&] { values_ok = compile_values(); }};
+  struct Joiner {
+    std::thread& t;
+    ~Joiner() {
+      if (t.joinable()) t.join();
+    }
+  } joiner{values_thread};
+
   // ---- derivative sub-rows -------------------------------------------------------
   std::vector<SubRow> dsubs;
   for (int which : {SLPB_OUT_G, SLPB_OUT_A_E, SLPB_OUT_A_I, SLPB_OUT_H_F,
@@ -1233,54 +1300,11 @@ bool compile_autodiff(const Tape& tape, const RowSet rows[SLPB_OUT_COUNT],
   timer.lap("build_programs(derivs) total");
   out.deriv_gather = dgather.finish();
 
-  // ---- value sub-rows ------------------------------------------------------------
-  std::vector<SubRow> vsubs;
-  int32_t next_vstage = 0;
-  auto value_entry = [&](int which, int32_t row) -> int64_t {
-    return which == SLPB_OUT_F ? 0
-           : which == SLPB_OUT_C_E ? 1 + row : 1 + int64_t(me) + row;
-  };
-  std::vector<double> vconst;
-  struct PendingConst { int64_t entry; int32_t scale; double v; };
-  std::vector<PendingConst> pend;
-  for (int which : {SLPB_OUT_F, SLPB_OUT_C_E, SLPB_OUT_C_I}) {
-    const RowSet& rs = rows[which];
-    if (!rs.present) continue;
-    for (int32_t r = 0; r < rs.n_rows; ++r) {
-      const int32_t b = rs.row_ptr[r], e = rs.row_ptr[r + 1];
-      if (e == b) {
-        pend.push_back({value_entry(which, r), scale_of(which, r),
-                        rs.const_val.empty() ? 0.0 : rs.const_val[r]});
-        continue;
-      }
-      C.split_row(rs.row_nodes.data() + b, e - b,
-                  [&](int8_t seed, std::vector<int32_t> nodes) {
-                    SubRow sr;
-                    sr.out = which;
-                    sr.row = r;
-                    sr.seed = seed;
-                    sr.is_value = true;
-                    sr.value_stage = next_vstage;
-                    vgather.add(value_entry(which, r), next_vstage,
-                                scale_of(which, r), seed < 0);
-                    ++next_vstage;
-                    sr.nodes = std::move(nodes);
-                    vsubs.push_back(std::move(sr));
-                  });
-    }
+  values_thread.join();
+  if (!values_ok) {
+    out.error = value_error;
+    return false;
   }
-  // constants go after the swept slots for the value stage
-  out.value_stage_init.assign(next_vstage, 0.0);
-  for (auto& p : pend) {
-    vgather.add(p.entry, static_cast<int32_t>(out.value_stage_init.size()),
-                p.scale);
-    out.value_stage_init.push_back(p.v);
-  }
-  out.value_stage_size = static_cast<int32_t>(out.value_stage_init.size());
-  timer.lap("value sub-rows");
-  if (!C.build_programs(vsubs, out.values)) return false;
-  out.value_gather = vgather.finish();
-  timer.lap("build_programs(values) total");
   return true;
 }
 
