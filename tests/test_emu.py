@@ -258,3 +258,32 @@ def test_clusters_fit_one_thread_block(name, N, monkeypatch):
     E = Emu(name, N)
     assert E.n > 0
     E.close()
+
+
+def test_concurrent_builds_are_independent():
+    """Eight threads each build the cart-pole problem (thread-local expression
+    pool; one of them also holds the process-wide fast slot), flatten it and
+    compile it (the compiler starts threads of its own) at the same time — what
+    slp::multistart does before its starts reach the device. Every one must
+    reproduce the golden vector bit for bit."""
+    import threading
+    z = np.load(os.path.join(GOLDEN, "eval_cart_pole_40.npz"))
+    g = {k: z[k] for k in z.files}          # (npz members load lazily)
+    for _ in range(3):
+        out = [None] * 8
+
+        def work(i):
+            E = Emu("cart_pole", 40)
+            r = E.eval(g["x"], g["y"], g["z"], float(g["d_f"]), g["d_ce"], g["d_ci"])
+            out[i] = (r["f"], r["g"].copy(), r["H"].copy(), r["A_e"].copy())
+            E.close()
+        threads = [threading.Thread(target=work, args=(i,)) for i in range(8)]
+        for t in threads:
+            t.start()
+        for t in threads:
+            t.join()
+        for o in out:
+            assert o is not None and o[0] == g["f"]
+            np.testing.assert_array_equal(o[1], g["g"])
+            np.testing.assert_array_equal(o[2], g["H_val"])
+            np.testing.assert_array_equal(o[3], g["A_e_val"])
