@@ -1145,6 +1145,7 @@ bool compile_autodiff(const Tape& tape, const RowSet rows[SLPB_OUT_COUNT],
   out.off_ai = out.off_ae + out.A_e.nnz();
   out.off_h = out.off_ai + out.A_i.nnz();
   const int64_t n_deriv_entries = out.off_h + out.H.nnz();
+  timer.lap("static patterns");
   GatherBuilder dgather{n_deriv_entries};
   GatherBuilder vgather{1 + int64_t(me) + mi};
 
@@ -1295,7 +1296,7 @@ bool compile_autodiff(const Tape& tape, const RowSet rows[SLPB_OUT_COUNT],
   }
   out.deriv_stage_size = next_stage;
   out.deriv_stage_init.resize(next_stage, 0.0);
-  timer.lap("patterns + derivative sub-rows");
+  timer.lap("derivative sub-rows");
   if (!C.build_programs(dsubs, out.derivs)) return false;
   timer.lap("build_programs(derivs) total");
   out.deriv_gather = dgather.finish();
