@@ -15,6 +15,12 @@ iteration ends with a device→host read of its scalars, so the host timestamps
 taken at iteration boundaries are device-complete. The L2 is evicted before
 every timed iteration (excluded from the timestamps).
 
+Besides the contract's keys the line carries `roofline` (k_factor_tree against
+the measured HBM peak, plus the derivative sweep), `cpu_baseline` (the oracle on
+one host core), `e2e` (one Problem::solve() to its exit status from host
+buffers, setup included) and `multistart` (B such solves in flight on each GPU
+through slp::multistart; --multistart 0 skips it).
+
 Prints ONE JSON line (see README/DESIGN for the field meanings).
 """
 from __future__ import annotations
