@@ -751,8 +751,13 @@ struct Compiler {
         for (const ContribTmp& c : visits[vi].contribs) {
           Contrib rec{};
           rec.parent_adj = ap(c.parent_visit);
-          rec.l = vp(c.l);
-          rec.r = vp(c.r);
+          // An operand the partial does not use still gets loaded by the
+          // interpreter (unconditional loads keep the inner loop branch-free).
+          // Point it at the parent's adjoint slot: live and not written during
+          // this level, unlike physical slot 0, which a visit of the same
+          // level may own (compute-sanitizer racecheck flagged that dead read).
+          rec.l = c.l >= 0 ? vp(c.l) : rec.parent_adj;
+          rec.r = c.r >= 0 ? vp(c.r) : rec.parent_adj;
           rec.op = c.op;
           rec.side = c.side;
           push_record(&rec);

@@ -407,6 +407,11 @@ bool analyze_kkt(const Pattern& K, int32_t n_primal, int ordering,
     case SLPB_ORDER_NESTED_DISSECTION:
       perm = defer_leading_multipliers(K, n_primal, order_nested_dissection(K));
       break;
+    case SLPB_ORDER_AMD:
+      // the reference's own order (Eigen::SimplicialLDLT's default AMDOrdering,
+      // sparse_regularized_ldlt.hpp:183), taken as is: no multiplier deferral
+      perm = order_amd(K);
+      break;
     case SLPB_ORDER_NATURAL:
       perm.resize(dim);
       std::iota(perm.begin(), perm.end(), 0);

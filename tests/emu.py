@@ -35,6 +35,7 @@ def lib():
         L.emu_analyze.restype = C.c_int
         L.emu_analyze.argtypes = [vp, C.c_int, _ip, _lp]
         L.emu_get_perm.argtypes = [vp, _ip]
+        L.emu_order_amd.argtypes = [C.c_int, _ip, _ip, _ip]
         L.emu_factor.restype = C.c_double
         L.emu_factor.argtypes = [vp, C.c_double, C.c_double, _ip, _dp]
         L.emu_solve.argtypes = [vp, _dp, _dp]
@@ -48,6 +49,15 @@ def _d(a):
 
 def _i(a):
     return a.ctypes.data_as(_ip)
+
+
+def order_amd(n, colptr, rowidx):
+    """The product's AMD ordering (csrc/amd.cpp) of a lower-triangular pattern."""
+    cp = np.ascontiguousarray(colptr, dtype=np.int32)
+    ri = np.ascontiguousarray(rowidx, dtype=np.int32)
+    p = np.zeros(n, dtype=np.int32)
+    lib().emu_order_amd(n, _i(cp), _i(ri), _i(p))
+    return p
 
 
 class Emu:

@@ -361,6 +361,18 @@ int emu_analyze(void* h, int ordering, const int* perm, int64_t* out) {
   return 0;
 }
 
+/// Raw output of the product's approximate-minimum-degree ordering
+/// (csrc/amd.cpp) on a lower-triangular pattern, before analyze_kkt folds the
+/// elimination-tree postorder into it.
+void emu_order_amd(int n, const int* colptr, const int* rowidx, int* perm) {
+  slpb::Pattern L;
+  L.rows = L.cols = n;
+  L.colptr.assign(colptr, colptr + n + 1);
+  L.rowidx.assign(rowidx, rowidx + colptr[n]);
+  const std::vector<int32_t> p = slpb::order_amd(L);
+  std::memcpy(perm, p.data(), n * sizeof(int));
+}
+
 void emu_get_perm(void* h, int* perm) {
   auto* e = static_cast<Emu*>(h);
   std::memcpy(perm, e->sym.perm.data(), e->sym.dim * sizeof(int));

@@ -164,6 +164,32 @@ def test_multifrontal_ldlt_matches_oracle(ordering):
     E.close(); O.close()
 
 
+@pytest.mark.parametrize("name,N", [("cart_pole", 40), ("cart_pole", 300),
+                                    ("gfold", 12), ("flywheel", 50),
+                                    ("arm_on_elevator", 30)])
+def test_product_amd_equals_the_oracle_amd(name, N):
+    """SLPB_ORDER_AMD (csrc/amd.cpp) returns the permutation of the oracle's
+    restatement of Eigen's AMDOrdering (oracle/ldlt.hpp; reference call site
+    sparse_regularized_ldlt.hpp:183) on the KKT patterns of the configs, and
+    analysing with it reproduces the oracle's nnz(L) for that order."""
+    from oracle.pyoracle import amd
+    from emu import order_amd
+    E, O = Emu(name, N), OracleProblem(name, N)
+    E.eval(O.initial_guess(), np.zeros(E.me), np.ones(E.mi), 1.0,
+           np.ones(E.me), np.ones(E.mi))
+    O.close()
+    cp, ri, kv = E.kkt(np.ones(E.mi))
+    dim = E.n + E.me
+    p_product = order_amd(dim, cp, ri)
+    p_oracle = amd(dim, cp, ri)
+    np.testing.assert_array_equal(p_product, p_oracle)
+    st = E.analyze(1)   # SLPB_ORDER_AMD
+    nnzL, *_ = ldlt(dim, cp, ri, np.where(ri == np.repeat(np.arange(dim), np.diff(cp)), 4.0, 0.01),
+                    None, p_oracle)
+    assert st["nnz_l"] == nnzL
+    E.close()
+
+
 def test_nested_dissection_gives_a_shallow_tree():
     """The assembly tree's depth grows like log N (the reference's AMD order
     has an O(N) chain)."""
