@@ -377,6 +377,47 @@ int slpb_download(slpb_solver* s, int which, double* dst);
 int slpb_pattern(const slpb_solver* s, int which, int32_t* rows, int32_t* cols,
                  int64_t* nnz, int32_t* colptr, int32_t* rowidx);
 
+/* ---- many instances over one symbolic structure ---------------------------
+ * slp::multistart (optimization/multistart.hpp:44-73) solves one problem from
+ * many initial guesses: every start has the lhs pattern of
+ * interior_point.hpp:426-440 and differs only in values. A batch factors and
+ * solves `batch` such systems side by side — lane = instance, SoA storage
+ * [entry][32] per group of 32 instances, one walk over the assembly tree for
+ * all of them — with the arithmetic of slpb_factor / slpb_solve per instance
+ * (bit-identical D and solutions). It borrows the symbolic analysis, the
+ * stream and the device of `s`, which must outlive it. */
+typedef struct slpb_batch slpb_batch;
+int slpb_batch_create(slpb_solver* s, int32_t batch, slpb_batch** out);
+void slpb_batch_destroy(slpb_batch* b);
+int slpb_batch_size(const slpb_batch* b, int32_t* batch, int32_t* groups);
+/* Instance i <- host arrays: lhs values in slpb_pattern(-1) order (without
+ * delta/gamma) and/or a right-hand side of length n + m_e (either may be NULL). */
+int slpb_batch_set_system(slpb_batch* b, int32_t instance,
+                          const double* kkt_val, const double* rhs);
+/* Instance i <- the assembled lhs values and the rhs resident in `src` (any
+ * solver with the same KKT pattern on the same device, e.g. one start of a
+ * multistart after slpb_factor / slpb_prepare_rhs): device-to-device. */
+int slpb_batch_capture(slpb_batch* b, int32_t instance, slpb_solver* src);
+/* Factors lhs_i + diag(delta_i, -gamma_i) for every instance in ONE launch
+ * (RegularizedLDLT::compute's numeric step, sparse_regularized_ldlt.hpp:74,105);
+ * info[i] as slpb_factor reports it. */
+int slpb_batch_factor(slpb_batch* b, const double* delta, const double* gamma,
+                      slpb_factor_info* info);
+/* Forward and backward substitution of every instance's rhs in ONE launch
+ * (sparse_regularized_ldlt.hpp:159-161). */
+int slpb_batch_solve(slpb_batch* b);
+enum slpb_batch_array { SLPB_BATCH_SOLUTION = 0, SLPB_BATCH_D = 1 };
+/* Copies out instance i's solution (original order, n + m_e) or D
+ * (elimination order). */
+int slpb_batch_get(slpb_batch* b, int32_t instance, int what, double* dst);
+/* Device time of the last slpb_batch_factor / slpb_batch_solve launch (CUDA
+ * events on the stream, milliseconds). */
+int slpb_batch_last_ms(const slpb_batch* b, float* factor_ms, float* solve_ms);
+/* Doubles stored per instance: packed panels (= nnz(L) incl. supernodal
+ * padding + dim) and packed update matrices. */
+int slpb_batch_bytes(const slpb_batch* b, int64_t* panel_entries,
+                     int64_t* update_entries);
+
 /* ---- instrumentation ------------------------------------------------------ */
 
 typedef struct slpb_counters {

@@ -115,6 +115,10 @@ ABI_SYMBOLS = [
     "slpb_probe_point", "slpb_multiplier_estimate", "slpb_accept", "slpb_array_size", "slpb_download",
     "slpb_pattern", "slpb_get_counters", "slpb_get_timers",
     "slpb_last_device_ms", "slpb_flush_l2", "slpb_stream",
+    "slpb_batch_create", "slpb_batch_destroy", "slpb_batch_size",
+    "slpb_batch_set_system", "slpb_batch_capture", "slpb_batch_factor",
+    "slpb_batch_solve", "slpb_batch_get", "slpb_batch_last_ms",
+    "slpb_batch_bytes",
 ]
 
 _dev = None
@@ -169,6 +173,18 @@ def device_lib() -> C.CDLL:
         L.slpb_last_device_ms.argtypes = [vp, C.c_int, C.POINTER(C.c_float)]
         L.slpb_stream.restype = vp
         L.slpb_stream.argtypes = [vp]
+        L.slpb_batch_create.argtypes = [vp, C.c_int32, C.POINTER(vp)]
+        L.slpb_batch_destroy.argtypes = [vp]
+        L.slpb_batch_destroy.restype = None
+        L.slpb_batch_size.argtypes = [vp, _ip, _ip]
+        L.slpb_batch_set_system.argtypes = [vp, C.c_int32, _dp, _dp]
+        L.slpb_batch_capture.argtypes = [vp, C.c_int32, vp]
+        L.slpb_batch_factor.argtypes = [vp, _dp, _dp, C.POINTER(FactorInfo)]
+        L.slpb_batch_solve.argtypes = [vp]
+        L.slpb_batch_get.argtypes = [vp, C.c_int32, C.c_int, _dp]
+        L.slpb_batch_last_ms.argtypes = [vp, C.POINTER(C.c_float),
+                                         C.POINTER(C.c_float)]
+        L.slpb_batch_bytes.argtypes = [vp, _lp, _lp]
         _dev = L
     return _dev
 
@@ -455,6 +471,66 @@ class DeviceSession:
         self._check(self.L.slpb_last_device_ms(self.raw, which, C.byref(ms)),
                     "slpb_last_device_ms")
         return ms.value
+
+
+class Batch:
+    """Many KKT systems over the symbolic structure of one DeviceSession,
+    factored and solved side by side (slpb_batch_*, lane = instance)."""
+
+    SOLUTION, D = 0, 1
+
+    def __init__(self, session: DeviceSession, batch: int):
+        self.L = device_lib()
+        self.session = session
+        self.batch = batch
+        self.dim = session.n + session.me
+        h = C.c_void_p()
+        session._check(self.L.slpb_batch_create(session.raw, batch, C.byref(h)),
+                       "slpb_batch_create")
+        self.h = h
+
+    def close(self):
+        if self.h:
+            self.L.slpb_batch_destroy(self.h)
+            self.h = None
+
+    def set_system(self, instance, kkt_val=None, rhs=None):
+        k = None if kkt_val is None else np.ascontiguousarray(kkt_val, dtype=np.float64)
+        r = None if rhs is None else np.ascontiguousarray(rhs, dtype=np.float64)
+        self.session._check(self.L.slpb_batch_set_system(self.h, instance, _d(k), _d(r)),
+                            "slpb_batch_set_system")
+
+    def capture(self, instance, source: DeviceSession = None):
+        src = (source or self.session).raw
+        self.session._check(self.L.slpb_batch_capture(self.h, instance, src),
+                            "slpb_batch_capture")
+
+    def factor(self, delta, gamma):
+        d = np.ascontiguousarray(np.broadcast_to(delta, (self.batch,)), dtype=np.float64)
+        g = np.ascontiguousarray(np.broadcast_to(gamma, (self.batch,)), dtype=np.float64)
+        info = (FactorInfo * self.batch)()
+        self.session._check(self.L.slpb_batch_factor(self.h, _d(d), _d(g), info),
+                            "slpb_batch_factor")
+        return list(info)
+
+    def solve(self):
+        self.session._check(self.L.slpb_batch_solve(self.h), "slpb_batch_solve")
+
+    def get(self, instance, what=0):
+        out = np.zeros(self.dim)
+        self.session._check(self.L.slpb_batch_get(self.h, instance, what, _d(out)),
+                            "slpb_batch_get")
+        return out
+
+    def last_ms(self):
+        f, s = C.c_float(), C.c_float()
+        self.L.slpb_batch_last_ms(self.h, C.byref(f), C.byref(s))
+        return f.value, s.value
+
+    def stored_entries(self):
+        p, u = C.c_int64(), C.c_int64()
+        self.L.slpb_batch_bytes(self.h, C.byref(p), C.byref(u))
+        return p.value, u.value
 
 
 class Problem:

@@ -1,0 +1,766 @@
+// Many KKT systems over ONE symbolic structure, factored and solved side by
+// side with lane = instance (included at the end of slpb.cu).
+//
+// Reference surface: slp::multistart (optimization/multistart.hpp:44-73) solves
+// the same problem from many initial guesses; every start has the lhs pattern
+// of interior_point.hpp:426-440 and differs only in values. One numeric LDLᵀ of
+// that system is a 13-level dependency chain over a factor that fits L2 many
+// times over: latency-bound, ≈1 % of the HBM roofline. B
+// systems in SoA layout walk the SAME chain once and move B× the bytes — the
+// regime in which the factorisation and the triangular solves are bound by
+// memory traffic.
+//
+// Layout. Instances come in groups of 32; every per-entry array of a group is
+// stored [entry][32], so the 32 lanes of a warp read one 256-byte line per
+// entry (fully coalesced), and group g of an array with E entries starts at
+// g·E·32. A warp owns one (front, group) task: lane ℓ runs the scalar
+// elimination of ldlt_core.hpp (ldlt_factor_front with NT = 1) for instance
+// 32·g + ℓ — the same products in the same order, hence bit-identical D, L and
+// solutions to the single-instance kernels — on a frontal matrix whose lower
+// triangle sits interleaved in shared memory (W[e·32 + ℓ], conflict-free, no
+// cross-lane traffic and no barrier inside a front). Tasks are drawn from a
+// ticket counter in level order, children before parents, and hand over through
+// per-(group, front) counters exactly like k_factor_tree.
+//
+// Storage is packed: a front keeps the lower trapezoid of its panel
+// (np·F − np(np−1)/2 entries, column-major) and the lower triangle of its update
+// matrix (m(m+1)/2) — in the column-major packed lower triangle of the F×F front
+// the two are contiguous, so the write-out is one flat copy.
+#pragma once
+
+namespace slpb {
+
+constexpr int kBatchLanes = 32;
+constexpr int kBatchRank = 4;  // pivots applied to the trailing matrix at once
+
+struct BatchView {
+  const int32_t* order;      // fronts by ascending level
+  const FrontMeta* metas;    // panel_off / update_off: PACKED offsets (entries)
+  const int32_t* child_idx;
+  const int32_t* rel_idx;
+  const int32_t* rows_idx;
+  const int32_t* asm_src;    // KKT entry of each own value
+  const int32_t* asm_tri;    // its packed position in the front
+  const int32_t* umap;       // packed update entry → packed position in parent
+  const uint8_t* col_is_primal;
+  const int32_t* perm;
+  int32_t* sync;             // [0] ticket | fcount[G·ns] | fflag[G·ns] | bflag[G·ns]
+  int32_t n_super, groups, dim, tri_cap;
+  int64_t nK, panel_total, update_total, rel_total;
+};
+
+/// Offset of column j of a packed lower triangle of order F, minus j, so that
+/// entry (i, j), i ≥ j, sits at tri_col(j, F) + i.
+__device__ __forceinline__ int tri_col(int j, int F) {
+  return j * F - (j * (j - 1)) / 2 - j;
+}
+
+/// x / d with the structural-zero shortcut of ldlt_eliminate_rows: when the
+/// dividend is zero in every lane (a structural zero of the column) the
+/// quotient is the signed zero div.rn.f64 would return, without its slow path.
+__device__ __forceinline__ double batch_div(double w, double d) {
+  const bool simple = w == 0.0 && d == d && d != 0.0;
+  if (__all_sync(0xffffffffu, simple)) {
+    return (signbit(w) != signbit(d)) ? -0.0 : 0.0;
+  }
+  return w / d;
+}
+
+/// One (front, group) task of the batched factorisation. W: packed lower
+/// triangle [n_tri][32] (shared memory, or global scratch for the rare front
+/// above the shared-memory cap), lbuf: [kBatchRank][F][32] scaled columns of the
+/// current pivot block.
+__device__ __forceinline__ void batch_factor_front(
+    int lane, const FrontMeta& fm, const BatchView& T, int g,
+    const double* __restrict__ Kb, double delta, double gamma,
+    double* __restrict__ Pb, double* Ub, double* __restrict__ Db, double* W,
+    double* lbuf, const int* dep, int* stats_out /*[6], per lane*/) {
+  const int F = fm.F, np = fm.np, c0 = fm.c0;
+  const int n_tri = F * (F + 1) / 2;
+  const int n_panel = np * F - (np * (np - 1)) / 2;
+  double* Wl = W + lane;
+  // ---- child-independent part ---------------------------------------------
+  for (int e = 0; e < n_tri; ++e) Wl[e * 32] = 0.0;
+  {
+    const double* Kg = Kb + int64_t(g) * T.nK * 32 + lane;
+    int k = fm.asm_begin;
+    for (; k + 4 <= fm.asm_end; k += 4) {
+      double v[4];
+#pragma unroll
+      for (int q = 0; q < 4; ++q) v[q] = __ldg(Kg + int64_t(T.asm_src[k + q]) * 32);
+#pragma unroll
+      for (int q = 0; q < 4; ++q) Wl[T.asm_tri[k + q] * 32] = v[q];
+    }
+    for (; k < fm.asm_end; ++k) {
+      Wl[T.asm_tri[k] * 32] = __ldg(Kg + int64_t(T.asm_src[k]) * 32);
+    }
+  }
+  for (int j = 0; j < np; ++j) {
+    Wl[(tri_col(j, F) + j) * 32] += T.col_is_primal[c0 + j] ? delta : -gamma;
+  }
+  // ---- children: wait, then extend-add in child order ------------------------
+  if (lane == 0) wait_children(dep, fm.n_child);
+  __syncwarp();
+  for (int ck = 0; ck < fm.n_child; ++ck) {
+    const FrontMeta cm = load_front_meta(T.metas + T.child_idx[fm.child_begin + ck]);
+    const int mc = cm.F - cm.np;
+    const int nt = mc * (mc + 1) / 2;
+    const double* U =
+        Ub + (int64_t(g) * T.update_total + cm.update_off) * 32 + lane;
+    const int32_t* map = T.umap + cm.update_off;
+    int e = 0;
+    for (; e + 4 <= nt; e += 4) {
+      double u[4];
+#pragma unroll
+      for (int q = 0; q < 4; ++q) u[q] = __ldcg(U + int64_t(e + q) * 32);
+#pragma unroll
+      for (int q = 0; q < 4; ++q) Wl[map[e + q] * 32] += u[q];
+    }
+    for (; e < nt; ++e) Wl[map[e] * 32] += __ldcg(U + int64_t(e) * 32);
+  }
+  // ---- elimination of the own columns ----------------------------------------
+  // Blocks of up to kBatchRank pivots: the block's columns are eliminated
+  // right-looking among themselves (scaled columns parked in lbuf, the
+  // unscaled ones left in W), then every trailing entry takes the block's
+  // updates in pivot order — W(i,j) −= l_ik·w_jk for k ascending, the sequence
+  // of ldlt_factor_front — with ONE load and ONE store of W(i,j) per block.
+  int pos = 0, neg = 0, zero = 0, zpiv = 0;
+  double min_abs = INFINITY;
+  double* Dg = Db + (int64_t(g) * T.dim + c0) * 32 + lane;
+  double* Ll = lbuf + lane;
+  for (int k0 = 0; k0 < np; k0 += kBatchRank) {
+    const int kb = min(kBatchRank, np - k0);
+    const int jend = k0 + kb;  // first column behind the block
+    for (int q = 0; q < kb; ++q) {
+      const int k = k0 + q;
+      const int ck = tri_col(k, F);
+      const double d = Wl[(ck + k) * 32];
+      {
+        const double eps = 2.220446049250313e-16;
+        pos += d > eps ? 1 : 0;
+        neg += d < -eps ? 1 : 0;
+        zero += (d > eps || d < -eps) ? 0 : 1;
+        zpiv |= d == 0.0 ? 1 : 0;
+        min_abs = fmin(min_abs, fabs(d));
+      }
+      Dg[k * 32] = d;
+      double* Lq = Ll + q * F * 32;
+      for (int i = k + 1; i < F; ++i) {
+        Lq[i * 32] = batch_div(Wl[(ck + i) * 32], d);
+      }
+      // rank-1 update of the remaining columns of the block
+      for (int j = k + 1; j < jend; ++j) {
+        const double wjk = Wl[(ck + j) * 32];
+        double* Wj = Wl + tri_col(j, F) * 32;
+        for (int i = j; i < F; ++i) Wj[i * 32] -= Lq[i * 32] * wjk;
+      }
+    }
+    // trailing columns: all pivots of the block at once
+    for (int j = jend; j < F; ++j) {
+      double wj[kBatchRank];
+#pragma unroll
+      for (int q = 0; q < kBatchRank; ++q) {
+        wj[q] = q < kb ? Wl[(tri_col(k0 + q, F) + j) * 32] : 0.0;
+      }
+      double* Wj = Wl + tri_col(j, F) * 32;
+      if (kb == kBatchRank) {
+        for (int i = j; i < F; ++i) {
+          double w = Wj[i * 32];
+#pragma unroll
+          for (int q = 0; q < kBatchRank; ++q) w -= Ll[(q * F + i) * 32] * wj[q];
+          Wj[i * 32] = w;
+        }
+      } else {
+        for (int i = j; i < F; ++i) {
+          double w = Wj[i * 32];
+          for (int q = 0; q < kb; ++q) w -= Ll[(q * F + i) * 32] * wj[q];
+          Wj[i * 32] = w;
+        }
+      }
+    }
+    // the block's columns now take their scaled values (diagonal keeps d)
+    for (int q = 0; q < kb; ++q) {
+      const int k = k0 + q;
+      const int ck = tri_col(k, F);
+      for (int i = k + 1; i < F; ++i) Wl[(ck + i) * 32] = Ll[(q * F + i) * 32];
+    }
+  }
+  // ---- write-out: [panel | update] is contiguous in the packed triangle -------
+  {
+    double* Pg = Pb + (int64_t(g) * T.panel_total + fm.panel_off) * 32 + lane;
+    for (int e = 0; e < n_panel; ++e) Pg[int64_t(e) * 32] = Wl[e * 32];
+    double* Ug = Ub + (int64_t(g) * T.update_total + fm.update_off) * 32 + lane;
+    const int nu = n_tri - n_panel;
+    for (int e = 0; e < nu; ++e) Ug[int64_t(e) * 32] = Wl[(n_panel + e) * 32];
+  }
+  stats_out[0] = pos;
+  stats_out[1] = neg;
+  stats_out[2] = zero;
+  stats_out[3] = zpiv;
+  const unsigned long long bits = __double_as_longlong(min_abs);
+  stats_out[4] = static_cast<int>(bits & 0xffffffffull);
+  stats_out[5] = static_cast<int>(bits >> 32);
+}
+
+#ifndef SLPB_BATCH_WARPS
+#define SLPB_BATCH_WARPS 1
+#endif
+
+/// stats: per instance 8 ints (n_pos n_neg n_zero zero_pivot | min|D| bits | pad).
+__global__ void __launch_bounds__(SLPB_BATCH_WARPS * 32)
+k_batch_factor(BatchView T, const double* __restrict__ Kb,
+               const double* __restrict__ delta,
+               const double* __restrict__ gamma, double* __restrict__ Pb,
+               double* Ub, double* __restrict__ Db, int32_t* __restrict__ stats,
+               double* gscratch, int smem_doubles_per_warp) {
+  extern __shared__ double smem[];
+  const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+  double* Wsh = smem + size_t(warp) * smem_doubles_per_warp;
+  const int total = T.n_super * T.groups;
+  int32_t* fcount = T.sync + 4;
+  for (;;) {
+    int t = 0;
+    if (lane == 0) t = atomicAdd(&T.sync[0], 1);
+    t = __shfl_sync(0xffffffffu, t, 0);
+    if (t >= total) break;
+    // the groups of one front hold neighbouring tickets (metadata stays hot);
+    // children of (s, g) are (c, g) with smaller tickets
+    const int s = T.order[t / T.groups];
+    const int g = t % T.groups;
+    const FrontMeta fm = load_front_meta(T.metas + s);
+    const int n_tri = fm.F * (fm.F + 1) / 2;
+    double* W;
+    double* lbuf;
+    if (n_tri <= T.tri_cap) {
+      W = Wsh;
+      lbuf = Wsh + size_t(T.tri_cap) * 32;
+    } else {
+      // rare oversized front: global scratch of this warp (L2-resident)
+      const size_t per_warp = (size_t(64) * 65 / 2 + kBatchRank * 64) * 32;
+      W = gscratch + (size_t(blockIdx.x) * SLPB_BATCH_WARPS + warp) * per_warp;
+      lbuf = W + size_t(64) * 65 / 2 * 32;
+    }
+    int st[6];
+    const int inst = g * 32 + lane;
+    batch_factor_front(lane, fm, T, g, Kb, delta[inst], gamma[inst], Pb, Ub, Db,
+                       W, lbuf, &fcount[size_t(g) * T.n_super + s], st);
+    __syncwarp();
+    if (lane == 0 && fm.parent >= 0) {
+      red_release_add(&fcount[size_t(g) * T.n_super + fm.parent], 1);
+    }
+    int32_t* vs = stats + size_t(inst) * 8;
+    if (st[0]) atomicAdd(&vs[0], st[0]);
+    if (st[1]) atomicAdd(&vs[1], st[1]);
+    if (st[2]) atomicAdd(&vs[2], st[2]);
+    if (st[3]) atomicOr(&vs[3], st[3]);
+    const unsigned long long bits =
+        (unsigned long long)(unsigned)st[4] |
+        ((unsigned long long)(unsigned)st[5] << 32);
+    atomicMin(reinterpret_cast<unsigned long long*>(&vs[4]), bits);
+  }
+}
+
+/// Forward then backward substitution of every instance; tickets [0, ns·G) are
+/// forward tasks, [ns·G, 2·ns·G) backward tasks (the arithmetic of
+/// ldlt_forward_front / ldlt_backward_front per lane). The panels stream
+/// through once per direction in 256-byte lines.
+__global__ void __launch_bounds__(128)
+k_batch_solve(BatchView T, const double* __restrict__ Pb,
+              const double* __restrict__ Db, const double* __restrict__ rhs,
+              double* xperm, double* uvecs, double* __restrict__ sol,
+              int fmax) {
+  extern __shared__ double smem[];
+  const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+  double* wl = smem + size_t(warp) * fmax * 32 + lane;
+  const int ns = T.n_super, G = T.groups;
+  const int total = ns * G;
+  int32_t* fcount = T.sync + 4;
+  int32_t* fflag = fcount + size_t(total);
+  int32_t* bflag = fflag + size_t(total);
+  for (;;) {
+    int t = 0;
+    if (lane == 0) t = atomicAdd(&T.sync[1], 1);
+    t = __shfl_sync(0xffffffffu, t, 0);
+    if (t >= 2 * total) break;
+    const bool fwd = t < total;
+    const int tt = fwd ? t : 2 * total - 1 - t;
+    const int s = T.order[tt / G];
+    const int g = fwd ? tt % G : G - 1 - tt % G;
+    const FrontMeta fm = load_front_meta(T.metas + s);
+    const int F = fm.F, np = fm.np, c0 = fm.c0;
+    const double* P = Pb + (int64_t(g) * T.panel_total + fm.panel_off) * 32 + lane;
+    double* xp = xperm + int64_t(g) * T.dim * 32 + lane;
+    double* uv = uvecs + int64_t(g) * T.rel_total * 32 + lane;
+    const size_t fi = size_t(g) * ns + s;
+    if (fwd) {
+      const double* r = rhs + int64_t(g) * T.dim * 32 + lane;
+      for (int i = 0; i < F; ++i) {
+        wl[i * 32] = i < np ? __ldg(r + int64_t(T.perm[c0 + i]) * 32) : 0.0;
+      }
+      if (lane == 0) wait_children(&fcount[fi], fm.n_child);
+      __syncwarp();
+      for (int ck = 0; ck < fm.n_child; ++ck) {
+        const FrontMeta cm =
+            load_front_meta(T.metas + T.child_idx[fm.child_begin + ck]);
+        const int mc = cm.F - cm.np;
+        const int32_t* rel = T.rel_idx + cm.rel_off;
+        const double* u = uv + int64_t(cm.rel_off) * 32;
+        for (int i = 0; i < mc; ++i) wl[rel[i] * 32] += __ldcg(u + int64_t(i) * 32);
+      }
+      for (int k = 0; k < np; ++k) {
+        const double yk = wl[k * 32];
+        const double* Pk = P + int64_t(tri_col(k, F)) * 32;
+        int i = k + 1;
+        for (; i + 4 <= F; i += 4) {
+          double l[4];
+#pragma unroll
+          for (int q = 0; q < 4; ++q) l[q] = __ldcs(Pk + int64_t(i + q) * 32);
+#pragma unroll
+          for (int q = 0; q < 4; ++q) wl[(i + q) * 32] -= l[q] * yk;
+        }
+        for (; i < F; ++i) wl[i * 32] -= __ldcs(Pk + int64_t(i) * 32) * yk;
+      }
+      for (int i = 0; i < np; ++i) xp[int64_t(c0 + i) * 32] = wl[i * 32];
+      for (int i = np; i < F; ++i) {
+        uv[int64_t(fm.rel_off + i - np) * 32] = wl[i * 32];
+      }
+      __syncwarp();
+      if (lane == 0) {
+        if (fm.parent >= 0) red_release_add(&fcount[size_t(g) * ns + fm.parent], 1);
+        st_release(&fflag[fi], 1);
+      }
+    } else {
+      const double* Dg = Db + int64_t(g) * T.dim * 32 + lane;
+      const int32_t* rows = T.rows_idx + fm.rows_off;
+      if (lane == 0) {
+        wait_children(fm.parent >= 0 ? &bflag[size_t(g) * ns + fm.parent]
+                                     : &fflag[fi], 1);
+      }
+      __syncwarp();
+      for (int i = 0; i < F; ++i) {
+        wl[i * 32] = i < np ? __ldcg(xp + int64_t(c0 + i) * 32) /
+                                  __ldg(Dg + int64_t(c0 + i) * 32)
+                            : __ldcg(xp + int64_t(rows[i]) * 32);
+      }
+      // t_k = z_k − Σ_{i ≥ np} L(i,k)·x_i, i ascending
+      for (int k = 0; k < np; ++k) {
+        const double* Pk = P + int64_t(tri_col(k, F)) * 32;
+        double acc = wl[k * 32];
+        int i = np;
+        for (; i + 4 <= F; i += 4) {
+          double l[4];
+#pragma unroll
+          for (int q = 0; q < 4; ++q) l[q] = __ldcs(Pk + int64_t(i + q) * 32);
+#pragma unroll
+          for (int q = 0; q < 4; ++q) acc -= l[q] * wl[(i + q) * 32];
+        }
+        for (; i < F; ++i) acc -= __ldcs(Pk + int64_t(i) * 32) * wl[i * 32];
+        wl[k * 32] = acc;
+      }
+      // L11ᵀ x = t, column-oriented
+      for (int i = np - 1; i >= 1; --i) {
+        const double xi = wl[i * 32];
+        for (int k = 0; k < i; ++k) {
+          wl[k * 32] -= __ldcs(P + int64_t(tri_col(k, F) + i) * 32) * xi;
+        }
+      }
+      double* so = sol + int64_t(g) * T.dim * 32 + lane;
+      for (int i = 0; i < np; ++i) {
+        const double v = wl[i * 32];
+        xp[int64_t(c0 + i) * 32] = v;
+        so[int64_t(T.perm[c0 + i]) * 32] = v;
+      }
+      __syncwarp();
+      if (lane == 0) st_release(&bflag[fi], 1);
+    }
+  }
+}
+
+/// dst[(g·E + e)·32 + ℓ] ← src[e] for one instance (g, ℓ): setup only.
+__global__ void k_batch_scatter(const double* __restrict__ src, int64_t n,
+                                double* __restrict__ dst_lane) {
+  const int64_t e = int64_t(blockIdx.x) * blockDim.x + threadIdx.x;
+  if (e < n) dst_lane[e * 32] = src[e];
+}
+__global__ void k_batch_gather(const double* __restrict__ src_lane, int64_t n,
+                               double* __restrict__ dst) {
+  const int64_t e = int64_t(blockIdx.x) * blockDim.x + threadIdx.x;
+  if (e < n) dst[e] = src_lane[e * 32];
+}
+
+}  // namespace slpb
+
+struct slpb_batch {
+  slpb_solver* S = nullptr;  // owner of the symbolic structure and the stream
+  int batch = 0, groups = 0;
+  int tri_cap = 0, fmax = 0, factor_warps = 1;
+  int factor_blocks = 0, solve_blocks = 0, factor_smem = 0, solve_smem = 0;
+  int64_t nK = 0, panel_total = 0, update_total = 0, rel_total = 0;
+  slpb::DevBuf<slpb::FrontMeta> metas;
+  slpb::DevBuf<int32_t> asm_tri, umap, sync, stats;
+  slpb::DevBuf<double> Kb, rhs, Pb, Ub, Db, xperm, uvecs, sol, delta, gamma,
+      staging, gscratch;
+  cudaEvent_t ev[4] = {};
+  float factor_ms = 0.0f, solve_ms = 0.0f;
+  std::string error;
+};
+
+namespace slpb {
+
+#define CUB(call)                                                         \
+  do {                                                                    \
+    cudaError_t e_ = (call);                                              \
+    if (e_ != cudaSuccess) {                                              \
+      B->error = std::string(#call) + ": " + cudaGetErrorString(e_);      \
+      B->S->error = B->error;                                             \
+      return SLPB_ERR_CUDA;                                               \
+    }                                                                     \
+  } while (0)
+
+inline BatchView batch_view(slpb_batch* B) {
+  slpb_solver* S = B->S;
+  BatchView T{};
+  T.order = S->sy_level_supers.p;
+  T.metas = B->metas.p;
+  T.child_idx = S->sy_child_idx.p;
+  T.rel_idx = S->sy_rel_idx.p;
+  T.rows_idx = S->sy_rows_idx.p;
+  T.asm_src = S->sy_asm_src.p;
+  T.asm_tri = B->asm_tri.p;
+  T.umap = B->umap.p;
+  T.col_is_primal = S->sy_col_is_primal.p;
+  T.perm = S->sy_perm.p;
+  T.sync = B->sync.p;
+  T.n_super = S->sym.n_super;
+  T.groups = B->groups;
+  T.dim = S->sym.dim;
+  T.tri_cap = B->tri_cap;
+  T.nK = B->nK;
+  T.panel_total = B->panel_total;
+  T.update_total = B->update_total;
+  T.rel_total = B->rel_total;
+  return T;
+}
+
+}  // namespace slpb
+
+extern "C" {
+
+int slpb_batch_create(slpb_solver* S, int32_t batch, slpb_batch** out) {
+  using namespace slpb;
+  if (!S || !out || batch < 1) return SLPB_ERR_ARGUMENT;
+  *out = nullptr;
+  if (!S->analyzed) {
+    return fail(S, SLPB_ERR_STATE, "slpb_batch_create needs slpb_analyze first");
+  }
+  const Symbolic& Y = S->sym;
+  if (Y.max_front > 64) {
+    return fail(S, SLPB_ERR_UNSUPPORTED,
+                "batched factorisation: fronts above order 64 are not supported");
+  }
+  CU(cudaSetDevice(S->device));
+  const AllocScope alloc_scope{S->stream};
+  auto B = std::make_unique<slpb_batch>();
+  B->S = S;
+  B->batch = batch;
+  B->groups = (batch + 31) / 32;
+  const int ns = Y.n_super;
+  const int64_t G = B->groups;
+  // packed offsets, packed assembly positions, child → parent maps
+  std::vector<FrontMeta> metas(ns);
+  std::vector<int64_t> uoff(ns + 1, 0), poff(ns + 1, 0);
+  for (int s = 0; s < ns; ++s) {
+    const int64_t F = Y.front_dim[s];
+    const int64_t np = Y.super_first[s + 1] - Y.super_first[s];
+    const int64_t m = F - np;
+    poff[s + 1] = poff[s] + np * F - np * (np - 1) / 2;
+    uoff[s + 1] = uoff[s] + m * (m + 1) / 2;
+  }
+  std::vector<int32_t> nchild(ns, 0);
+  for (int s = 0; s < ns; ++s) {
+    nchild[s] = static_cast<int32_t>(Y.child_ptr[s + 1] - Y.child_ptr[s]);
+  }
+  auto tri = [](int64_t i, int64_t j, int64_t F) {
+    return static_cast<int32_t>(j * F - j * (j - 1) / 2 + (i - j));
+  };
+  // fronts whose triangle fits the shared-memory cap take the fast path: the
+  // cap is the largest order that still lets two warps share an SM, or the
+  // 98th percentile of the front orders when that is smaller
+  std::vector<int32_t> orders(Y.front_dim);
+  std::sort(orders.begin(), orders.end());
+  int f_cap = orders[std::min<size_t>(orders.size() - 1,
+                                       (orders.size() * 98) / 100)];
+  f_cap = std::max(f_cap, 8);
+  if (const char* e = std::getenv("SLPB_BATCH_FCAP")) f_cap = std::atoi(e);
+  f_cap = std::min(f_cap, 28);  // (28·29/2 + 4·28)·256 B = 132 KB
+  f_cap = std::min<int>(f_cap, Y.max_front);
+  B->tri_cap = f_cap * (f_cap + 1) / 2;
+  B->fmax = Y.max_front;
+  for (int s = 0; s < ns; ++s) {
+    FrontMeta& fm = metas[s];
+    fm.F = Y.front_dim[s];
+    fm.c0 = Y.super_first[s];
+    fm.np = Y.super_first[s + 1] - Y.super_first[s];
+    fm.n_child = nchild[s];
+    fm.child_begin = static_cast<int32_t>(Y.child_ptr[s]);
+    fm.asm_begin = static_cast<int32_t>(Y.asm_ptr[s]);
+    fm.asm_end = static_cast<int32_t>(Y.asm_ptr[s + 1]);
+    fm.rel_off = static_cast<int32_t>(Y.rel_ptr[s]);
+    fm.panel_off = poff[s];
+    fm.update_off = uoff[s];
+    fm.rows_off = Y.rows_ptr[s];
+    fm.parent = Y.super_parent[s];
+    fm.pad = 0;
+  }
+  std::vector<int32_t> asm_tri(Y.asm_dst.size());
+  for (int s = 0; s < ns; ++s) {
+    const int64_t F = Y.front_dim[s];
+    for (int64_t k = Y.asm_ptr[s]; k < Y.asm_ptr[s + 1]; ++k) {
+      const int64_t lr = Y.asm_dst[k] % F, lc = Y.asm_dst[k] / F;
+      asm_tri[k] = tri(lr, lc, F);
+    }
+  }
+  std::vector<int32_t> umap(std::max<int64_t>(uoff[ns], 1), 0);
+  for (int c = 0; c < ns; ++c) {
+    const int p = Y.super_parent[c];
+    if (p < 0) continue;
+    const int64_t Fp = Y.front_dim[p];
+    const int64_t mc = Y.front_dim[c] - (Y.super_first[c + 1] - Y.super_first[c]);
+    const int32_t* rel = Y.rel_idx.data() + Y.rel_ptr[c];
+    int64_t e = uoff[c];
+    for (int64_t j = 0; j < mc; ++j) {
+      for (int64_t i = j; i < mc; ++i) umap[e++] = tri(rel[i], rel[j], Fp);
+    }
+  }
+  B->nK = S->recipe.K.nnz();
+  B->panel_total = poff[ns];
+  B->update_total = std::max<int64_t>(uoff[ns], 1);
+  B->rel_total = std::max<int64_t>(Y.rel_ptr.back(), 1);
+  CU(B->metas.upload(metas, S->stream));
+  CU(B->asm_tri.upload(asm_tri, S->stream));
+  CU(B->umap.upload(umap, S->stream));
+  CU(B->sync.alloc(4 + 3 * size_t(G) * ns));
+  CU(B->stats.alloc(size_t(G) * 32 * 8));
+  CU(B->Kb.alloc(size_t(G) * B->nK * 32));
+  CU(B->rhs.alloc(size_t(G) * Y.dim * 32));
+  CU(B->Pb.alloc(size_t(G) * B->panel_total * 32));
+  CU(B->Ub.alloc(size_t(G) * B->update_total * 32));
+  CU(B->Db.alloc(size_t(G) * Y.dim * 32));
+  CU(B->xperm.alloc(size_t(G) * Y.dim * 32));
+  CU(B->uvecs.alloc(size_t(G) * B->rel_total * 32));
+  CU(B->sol.alloc(size_t(G) * Y.dim * 32));
+  CU(B->delta.alloc(size_t(G) * 32));
+  CU(B->gamma.alloc(size_t(G) * 32));
+  CU(B->staging.alloc(std::max<size_t>(B->nK, Y.dim)));
+  CU(B->Kb.zero(S->stream));
+  CU(B->rhs.zero(S->stream));
+  CU(B->delta.zero(S->stream));
+  CU(B->gamma.zero(S->stream));
+  // launch geometry
+  int sms = 148;
+  cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, S->device);
+  const int per_warp_doubles = (B->tri_cap + kBatchRank * f_cap) * 32;
+  B->factor_smem = SLPB_BATCH_WARPS * per_warp_doubles * 8;
+  CU(raise_dynamic_smem(k_batch_factor, B->factor_smem));
+  int per_sm = 1;
+  CU(cudaOccupancyMaxActiveBlocksPerMultiprocessor(
+      &per_sm, k_batch_factor, SLPB_BATCH_WARPS * 32, B->factor_smem));
+  per_sm = std::max(per_sm, 1);
+  const int64_t tasks = int64_t(ns) * G;
+  B->factor_blocks = static_cast<int>(std::min<int64_t>(
+      (tasks + SLPB_BATCH_WARPS - 1) / SLPB_BATCH_WARPS, int64_t(sms) * per_sm));
+  B->solve_smem = 4 * B->fmax * 32 * 8;
+  CU(raise_dynamic_smem(k_batch_solve, B->solve_smem));
+  int per_sm_solve = 1;
+  CU(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm_solve, k_batch_solve,
+                                                   128, B->solve_smem));
+  per_sm_solve = std::max(per_sm_solve, 1);
+  B->solve_blocks = static_cast<int>(
+      std::min<int64_t>((2 * tasks + 3) / 4, int64_t(sms) * per_sm_solve));
+  if (Y.max_front > f_cap) {
+    const size_t per_warp = (size_t(64) * 65 / 2 + kBatchRank * 64) * 32;
+    CU(B->gscratch.alloc(size_t(B->factor_blocks) * SLPB_BATCH_WARPS * per_warp));
+  }
+  for (auto& e : B->ev) CU(cudaEventCreate(&e));
+  CU(cudaStreamSynchronize(S->stream));
+  *out = B.release();
+  return SLPB_OK;
+}
+
+void slpb_batch_destroy(slpb_batch* B) {
+  if (!B) return;
+  slpb_solver* S = B->S;
+  cudaSetDevice(S->device);
+  cudaStreamSynchronize(S->stream);
+  for (auto& e : B->ev) {
+    if (e) cudaEventDestroy(e);
+  }
+  const slpb::AllocScope alloc_scope{S->stream};
+  delete B;
+}
+
+int slpb_batch_size(const slpb_batch* B, int32_t* batch, int32_t* groups) {
+  if (!B) return SLPB_ERR_ARGUMENT;
+  if (batch) *batch = B->batch;
+  if (groups) *groups = B->groups;
+  return SLPB_OK;
+}
+
+int slpb_batch_set_system(slpb_batch* B, int32_t instance,
+                          const double* kkt_val, const double* rhs) {
+  using namespace slpb;
+  if (!B || instance < 0 || instance >= B->batch) return SLPB_ERR_ARGUMENT;
+  slpb_solver* S = B->S;
+  CUB(cudaSetDevice(S->device));
+  const int g = instance / 32, l = instance % 32;
+  const int dim = S->sym.dim;
+  if (kkt_val) {
+    CUB(cudaMemcpyAsync(B->staging.p, kkt_val, B->nK * 8, cudaMemcpyHostToDevice,
+                        S->stream));
+    k_batch_scatter<<<blocks_for(B->nK, 256), 256, 0, S->stream>>>(
+        B->staging.p, B->nK, B->Kb.p + int64_t(g) * B->nK * 32 + l);
+    CUB(cudaStreamSynchronize(S->stream));
+  }
+  if (rhs) {
+    CUB(cudaMemcpyAsync(B->staging.p, rhs, size_t(dim) * 8,
+                        cudaMemcpyHostToDevice, S->stream));
+    k_batch_scatter<<<blocks_for(dim, 256), 256, 0, S->stream>>>(
+        B->staging.p, dim, B->rhs.p + int64_t(g) * dim * 32 + l);
+    CUB(cudaStreamSynchronize(S->stream));
+  }
+  CUB(cudaGetLastError());
+  return SLPB_OK;
+}
+
+int slpb_batch_capture(slpb_batch* B, int32_t instance, slpb_solver* src) {
+  using namespace slpb;
+  if (!B || !src || instance < 0 || instance >= B->batch) return SLPB_ERR_ARGUMENT;
+  slpb_solver* S = B->S;
+  if (!src->finalized || src->recipe.K.nnz() != B->nK || src->dim != S->dim ||
+      src->device != S->device) {
+    return fail(S, SLPB_ERR_ARGUMENT,
+                "slpb_batch_capture: the source solver has another KKT pattern");
+  }
+  CUB(cudaSetDevice(S->device));
+  CUB(cudaStreamSynchronize(src->stream));
+  const int g = instance / 32, l = instance % 32;
+  const int dim = S->sym.dim;
+  k_batch_scatter<<<blocks_for(B->nK, 256), 256, 0, S->stream>>>(
+      src->Kval.p, B->nK, B->Kb.p + int64_t(g) * B->nK * 32 + l);
+  k_batch_scatter<<<blocks_for(dim, 256), 256, 0, S->stream>>>(
+      src->rhs.p, dim, B->rhs.p + int64_t(g) * dim * 32 + l);
+  CUB(cudaGetLastError());
+  CUB(cudaStreamSynchronize(S->stream));
+  return SLPB_OK;
+}
+
+int slpb_batch_factor(slpb_batch* B, const double* delta, const double* gamma,
+                      slpb_factor_info* info) {
+  using namespace slpb;
+  if (!B || !delta || !gamma) return SLPB_ERR_ARGUMENT;
+  slpb_solver* S = B->S;
+  CUB(cudaSetDevice(S->device));
+  const int ns = S->sym.n_super;
+  const size_t lanes = size_t(B->groups) * 32;
+  std::vector<double> d(lanes, 1.0), gm(lanes, 1.0);  // padding lanes: identity-ish
+  std::copy(delta, delta + B->batch, d.begin());
+  std::copy(gamma, gamma + B->batch, gm.begin());
+  CUB(cudaMemcpyAsync(B->delta.p, d.data(), lanes * 8, cudaMemcpyHostToDevice,
+                      S->stream));
+  CUB(cudaMemcpyAsync(B->gamma.p, gm.data(), lanes * 8, cudaMemcpyHostToDevice,
+                      S->stream));
+  std::vector<int32_t> init(lanes * 8, 0);
+  {
+    const double inf = INFINITY;
+    for (size_t i = 0; i < lanes; ++i) std::memcpy(&init[i * 8 + 4], &inf, 8);
+  }
+  CUB(cudaMemcpyAsync(B->stats.p, init.data(), init.size() * 4,
+                      cudaMemcpyHostToDevice, S->stream));
+  CUB(cudaMemsetAsync(B->sync.p, 0, (4 + size_t(B->groups) * ns) * 4, S->stream));
+  CUB(cudaEventRecord(B->ev[0], S->stream));
+  const BatchView T = batch_view(B);
+  const int per_warp_doubles = B->factor_smem / 8 / SLPB_BATCH_WARPS;
+  k_batch_factor<<<B->factor_blocks, SLPB_BATCH_WARPS * 32, B->factor_smem,
+                   S->stream>>>(T, B->Kb.p, B->delta.p, B->gamma.p, B->Pb.p,
+                                B->Ub.p, B->Db.p, B->stats.p, B->gscratch.p,
+                                per_warp_doubles);
+  CUB(cudaEventRecord(B->ev[1], S->stream));
+  CUB(cudaGetLastError());
+  std::vector<int32_t> host(lanes * 8);
+  CUB(cudaMemcpyAsync(host.data(), B->stats.p, host.size() * 4,
+                      cudaMemcpyDeviceToHost, S->stream));
+  CUB(cudaStreamSynchronize(S->stream));
+  CUB(cudaEventElapsedTime(&B->factor_ms, B->ev[0], B->ev[1]));
+  ++S->counters.kernel_launches;
+  S->counters.factorizations += B->batch;
+  if (info) {
+    for (int i = 0; i < B->batch; ++i) {
+      info[i].n_pos = host[size_t(i) * 8 + 0];
+      info[i].n_neg = host[size_t(i) * 8 + 1];
+      info[i].n_zero = host[size_t(i) * 8 + 2];
+      info[i].zero_pivot = host[size_t(i) * 8 + 3];
+      std::memcpy(&info[i].min_abs_d, &host[size_t(i) * 8 + 4], 8);
+    }
+  }
+  return SLPB_OK;
+}
+
+int slpb_batch_solve(slpb_batch* B) {
+  using namespace slpb;
+  if (!B) return SLPB_ERR_ARGUMENT;
+  slpb_solver* S = B->S;
+  CUB(cudaSetDevice(S->device));
+  const int ns = S->sym.n_super;
+  CUB(cudaMemsetAsync(B->sync.p, 0, (4 + 3 * size_t(B->groups) * ns) * 4,
+                      S->stream));
+  CUB(cudaEventRecord(B->ev[2], S->stream));
+  const BatchView T = batch_view(B);
+  k_batch_solve<<<B->solve_blocks, 128, B->solve_smem, S->stream>>>(
+      T, B->Pb.p, B->Db.p, B->rhs.p, B->xperm.p, B->uvecs.p, B->sol.p, B->fmax);
+  CUB(cudaEventRecord(B->ev[3], S->stream));
+  CUB(cudaGetLastError());
+  CUB(cudaStreamSynchronize(S->stream));
+  CUB(cudaEventElapsedTime(&B->solve_ms, B->ev[2], B->ev[3]));
+  ++S->counters.kernel_launches;
+  S->counters.solves += B->batch;
+  return SLPB_OK;
+}
+
+int slpb_batch_get(slpb_batch* B, int32_t instance, int what, double* dst) {
+  using namespace slpb;
+  if (!B || !dst || instance < 0 || instance >= B->batch) return SLPB_ERR_ARGUMENT;
+  slpb_solver* S = B->S;
+  CUB(cudaSetDevice(S->device));
+  const int g = instance / 32, l = instance % 32;
+  const int dim = S->sym.dim;
+  const double* src = nullptr;
+  switch (what) {
+    case SLPB_BATCH_SOLUTION: src = B->sol.p; break;
+    case SLPB_BATCH_D: src = B->Db.p; break;
+    default: return SLPB_ERR_ARGUMENT;
+  }
+  k_batch_gather<<<blocks_for(dim, 256), 256, 0, S->stream>>>(
+      src + int64_t(g) * dim * 32 + l, dim, B->staging.p);
+  CUB(cudaGetLastError());
+  CUB(cudaMemcpyAsync(dst, B->staging.p, size_t(dim) * 8, cudaMemcpyDeviceToHost,
+                      S->stream));
+  CUB(cudaStreamSynchronize(S->stream));
+  return SLPB_OK;
+}
+
+int slpb_batch_last_ms(const slpb_batch* B, float* factor_ms, float* solve_ms) {
+  if (!B) return SLPB_ERR_ARGUMENT;
+  if (factor_ms) *factor_ms = B->factor_ms;
+  if (solve_ms) *solve_ms = B->solve_ms;
+  return SLPB_OK;
+}
+
+int slpb_batch_bytes(const slpb_batch* B, int64_t* panel_entries,
+                     int64_t* update_entries) {
+  if (!B) return SLPB_ERR_ARGUMENT;
+  if (panel_entries) *panel_entries = B->panel_total;
+  if (update_entries) *update_entries = B->update_total;
+  return SLPB_OK;
+}
+
+}  // extern "C"

@@ -2774,3 +2774,5 @@ int slpb_flush_l2(slpb_solver* S) {
 void* slpb_stream(slpb_solver* S) { return S ? S->stream : nullptr; }
 
 }  // extern "C"
+
+#include "batch.cuh"

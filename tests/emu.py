@@ -35,6 +35,7 @@ def lib():
         L.emu_analyze.restype = C.c_int
         L.emu_analyze.argtypes = [vp, C.c_int, _ip, _lp]
         L.emu_get_perm.argtypes = [vp, _ip]
+        L.emu_fronts.argtypes = [vp, _ip, _ip, _ip, _ip]
         L.emu_order_amd.argtypes = [C.c_int, _ip, _ip, _ip]
         L.emu_factor.restype = C.c_double
         L.emu_factor.argtypes = [vp, C.c_double, C.c_double, _ip, _dp]
@@ -128,6 +129,12 @@ class Emu:
         keys = ("dim", "nnz_l", "n_super", "n_levels", "max_front",
                 "etree_height", "panel", "update")
         return dict(zip(keys, out))
+
+    def fronts(self, n_super):
+        """(F, np, level, parent) of every front of the last analysis."""
+        a = [np.zeros(n_super, dtype=np.int32) for _ in range(4)]
+        self.L.emu_fronts(self.h, *[_i(v) for v in a])
+        return a
 
     def perm(self):
         p = np.zeros(self.n + self.me, dtype=np.int32)

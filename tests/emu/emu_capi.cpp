@@ -361,6 +361,19 @@ int emu_analyze(void* h, int ordering, const int* perm, int64_t* out) {
   return 0;
 }
 
+/// Per front of the last analysis: order, own columns, level, parent.
+int emu_fronts(void* h, int* F, int* np, int* level, int* parent) {
+  auto* e = static_cast<Emu*>(h);
+  const auto& S = e->sym;
+  for (int s = 0; s < S.n_super; ++s) {
+    F[s] = S.front_dim[s];
+    np[s] = S.super_first[s + 1] - S.super_first[s];
+    level[s] = S.super_level[s];
+    parent[s] = S.super_parent[s];
+  }
+  return S.n_super;
+}
+
 /// Raw output of the product's approximate-minimum-degree ordering
 /// (csrc/amd.cpp) on a lower-triangular pattern, before analyze_kkt folds the
 /// elimination-tree postorder into it.
