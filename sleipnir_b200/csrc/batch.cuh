@@ -31,7 +31,26 @@
 namespace slpb {
 
 constexpr int kBatchLanes = 32;
-constexpr int kBatchRank = 4;  // pivots applied to the trailing matrix at once
+// Pivots applied to the trailing matrix at once, and warps that share one
+// (front, group) task: all of them work for the SAME 32 instances (lane =
+// instance) and split the rows / columns of the front between them.
+// (measured on B200, cart-pole N=5000, B=512: rank 2 / 6 warps 3.47 ms,
+// rank 2 / 8 warps 3.67, rank 2 / 4 warps 3.76, rank 4 / 8 warps 4.7 — rank 4
+// halves the shared-memory traffic per update but its larger column buffer
+// leaves room for two blocks per SM instead of three)
+#ifndef SLPB_BATCH_RANK
+#define SLPB_BATCH_RANK 2
+#endif
+#ifndef SLPB_BATCH_WARPS
+#define SLPB_BATCH_WARPS 6
+#endif
+#ifndef SLPB_BATCH_MIN_BLOCKS
+#define SLPB_BATCH_MIN_BLOCKS (SLPB_BATCH_RANK <= 2 ? 3 : 2)
+#endif
+constexpr int kBatchRank = SLPB_BATCH_RANK;
+constexpr int kBatchWarps = SLPB_BATCH_WARPS;
+/// Barrier between the phases of a task.
+__device__ __forceinline__ void compute_sync() { __syncthreads(); }
 
 struct BatchView {
   const int32_t* order;      // fronts by ascending level
@@ -40,7 +59,7 @@ struct BatchView {
   const int32_t* rel_idx;
   const int32_t* rows_idx;
   const int32_t* asm_src;    // KKT entry of each own value
-  const int32_t* asm_tri;    // its packed position in the front
+  const int32_t* asm_tri;    // its packed position in the front | diagonal flags
   const int32_t* umap;       // packed update entry → packed position in parent
   const uint8_t* col_is_primal;
   const int32_t* perm;
@@ -49,58 +68,109 @@ struct BatchView {
   int64_t nK, panel_total, update_total, rel_total;
 };
 
+/// asm_tri entries: packed position in the low bits; the own diagonal entries
+/// carry which regularisation they take.
+constexpr int32_t kAsmPrimalDiag = 1 << 30, kAsmDualDiag = 1 << 29;
+constexpr int32_t kAsmIndexMask = (1 << 29) - 1;
+
 /// Offset of column j of a packed lower triangle of order F, minus j, so that
 /// entry (i, j), i ≥ j, sits at tri_col(j, F) + i.
 __device__ __forceinline__ int tri_col(int j, int F) {
   return j * F - (j * (j - 1)) / 2 - j;
 }
 
-/// x / d with the structural-zero shortcut of ldlt_eliminate_rows: when the
-/// dividend is zero in every lane (a structural zero of the column) the
-/// quotient is the signed zero div.rn.f64 would return, without its slow path.
-__device__ __forceinline__ double batch_div(double w, double d) {
-  const bool simple = w == 0.0 && d == d && d != 0.0;
-  if (__all_sync(0xffffffffu, simple)) {
+/// Reciprocal of a pivot, correctly rounded (computed once per pivot and reused
+/// by every division of its column).
+__device__ __forceinline__ double batch_rcp(double d) { return __drcp_rn(d); }
+
+/// w / d, correctly rounded like div.rn.f64 (so that the batch stays
+/// bit-identical to the single-instance kernels and to the reference's
+/// x86-64 division), from the correctly rounded reciprocal y = RN(1/d):
+/// q0 = RN(w·y) is within two ulps of the quotient; r = w − q·d is exact in one
+/// FMA, and q ← RN(q + r·y) (Markstein's division step) first makes q faithful
+/// and then, applied once more, correctly rounded. A column costs ONE
+/// reciprocal and five FP64 operations per entry instead of a full division
+/// (≈30 instructions) per entry. Whenever a lane falls outside the range in
+/// which the steps are exact (subnormal, huge or non-finite quotient or pivot)
+/// the whole warp takes div.rn.f64. tests/test_division_step.py checks the
+/// sequence against exact rational arithmetic.
+__device__ __forceinline__ double batch_div(double w, double d, double y) {
+  // biased exponent in [123, 1923] ⇔ 2^-900 ≤ |x| < 2^901
+  const unsigned ed = (static_cast<unsigned>(__double2hiint(d)) >> 20) & 0x7ffu;
+  const bool d_ok = ed - 123u <= 1800u;
+  // a structural zero of the column (zero in every lane): the signed zero
+  // div.rn.f64 returns, no arithmetic at all
+  if (__all_sync(0xffffffffu, w == 0.0 && d_ok)) {
     return (signbit(w) != signbit(d)) ? -0.0 : 0.0;
   }
+  // (these must stay fused even though the file is built with -fmad=false)
+  double q = __dmul_rn(w, y);
+  q = __fma_rn(__fma_rn(-q, d, w), y, q);
+  q = __fma_rn(__fma_rn(-q, d, w), y, q);
+  const unsigned eq = (static_cast<unsigned>(__double2hiint(q)) >> 20) & 0x7ffu;
+  // (a lane whose dividend alone is zero, or any value out of range, sends
+  // the warp to the full division)
+  if (__all_sync(0xffffffffu, d_ok && eq - 123u <= 1800u)) return q;
   return w / d;
 }
 
-/// One (front, group) task of the batched factorisation. W: packed lower
-/// triangle [n_tri][32] (shared memory, or global scratch for the rare front
-/// above the shared-memory cap), lbuf: [kBatchRank][F][32] scaled columns of the
-/// current pivot block.
+/// One (front, group) task of the batched factorisation, run by the kBatchWarps
+/// warps of a thread block: every warp works on the same 32 instances (lane =
+/// instance) and takes the entries / rows / columns congruent to its index.
+/// W: packed lower triangle [n_tri][32] (shared memory, or global scratch for
+/// the rare front above the shared-memory cap), lbuf: [kBatchRank][F][32] scaled
+/// columns of the current pivot block.
+///
+/// Pivots go in blocks of up to kBatchRank. Phase A (one barrier): every warp
+/// eliminates the small diagonal block redundantly in registers, then takes
+/// its rows below the block through the block's pivots — updated unscaled
+/// entries back to W (the trailing update reads them as w_jk), scaled ones to
+/// lbuf and straight to the packed panel in global memory. Phase B (one
+/// barrier): the trailing columns, split over the warps, take all pivots of
+/// the block at once. Per entry the operations and their order are those of
+/// ldlt_factor_front: W(i,j) −= l_ik·w_jk for k ascending, l_ik = w_ik / d_k.
+/// kShared: W and lbuf are shared memory (the compiler must see that to emit
+/// LDS/STS with 32-bit addresses instead of generic loads).
+template <bool kShared>
 __device__ __forceinline__ void batch_factor_front(
-    int lane, const FrontMeta& fm, const BatchView& T, int g,
+    int warp, int lane, const FrontMeta& fm, const BatchView& T, int g,
     const double* __restrict__ Kb, double delta, double gamma,
     double* __restrict__ Pb, double* Ub, double* __restrict__ Db, double* W,
-    double* lbuf, const int* dep, int* stats_out /*[6], per lane*/) {
+    double* lbuf, const int* dep, int* stats_out /*[6], warp 0 only*/) {
+  constexpr int NW = kBatchWarps;
+  constexpr int R = kBatchRank;
   const int F = fm.F, np = fm.np, c0 = fm.c0;
   const int n_tri = F * (F + 1) / 2;
   const int n_panel = np * F - (np * (np - 1)) / 2;
   double* Wl = W + lane;
-  // ---- child-independent part ---------------------------------------------
-  for (int e = 0; e < n_tri; ++e) Wl[e * 32] = 0.0;
+  // ---- own KKT entries (+δ / −γ on the own diagonal) -------------------------
+  // W is all zeros here (every task leaves it so): only the entries that
+  // have a source are touched, four value loads in flight per warp.
   {
     const double* Kg = Kb + int64_t(g) * T.nK * 32 + lane;
-    int k = fm.asm_begin;
-    for (; k + 4 <= fm.asm_end; k += 4) {
+    int k = fm.asm_begin + warp * 4;
+    for (; k < fm.asm_end; k += 4 * NW) {
       double v[4];
+      int dst[4];
 #pragma unroll
-      for (int q = 0; q < 4; ++q) v[q] = __ldg(Kg + int64_t(T.asm_src[k + q]) * 32);
+      for (int q = 0; q < 4; ++q) {
+        const bool in = k + q < fm.asm_end;
+        dst[q] = in ? __ldg(T.asm_tri + k + q) : 0;
+        v[q] = in ? __ldg(Kg + int64_t(__ldg(T.asm_src + k + q)) * 32) : 0.0;
+      }
 #pragma unroll
-      for (int q = 0; q < 4; ++q) Wl[T.asm_tri[k + q] * 32] = v[q];
+      for (int q = 0; q < 4; ++q) {
+        if (k + q < fm.asm_end) {
+          if (dst[q] & kAsmPrimalDiag) v[q] += delta;
+          if (dst[q] & kAsmDualDiag) v[q] += -gamma;
+          Wl[(dst[q] & kAsmIndexMask) * 32] = v[q];
+        }
+      }
     }
-    for (; k < fm.asm_end; ++k) {
-      Wl[T.asm_tri[k] * 32] = __ldg(Kg + int64_t(T.asm_src[k]) * 32);
-    }
-  }
-  for (int j = 0; j < np; ++j) {
-    Wl[(tri_col(j, F) + j) * 32] += T.col_is_primal[c0 + j] ? delta : -gamma;
   }
   // ---- children: wait, then extend-add in child order ------------------------
-  if (lane == 0) wait_children(dep, fm.n_child);
-  __syncwarp();
+  if (threadIdx.x == 0) wait_children(dep, fm.n_child);
+  compute_sync();
   for (int ck = 0; ck < fm.n_child; ++ck) {
     const FrontMeta cm = load_front_meta(T.metas + T.child_idx[fm.child_begin + ck]);
     const int mc = cm.F - cm.np;
@@ -108,155 +178,256 @@ __device__ __forceinline__ void batch_factor_front(
     const double* U =
         Ub + (int64_t(g) * T.update_total + cm.update_off) * 32 + lane;
     const int32_t* map = T.umap + cm.update_off;
-    int e = 0;
-    for (; e + 4 <= nt; e += 4) {
+    // entries of ONE child land on distinct parent entries: the warps split
+    // them freely; the barrier keeps the children in order
+    for (int e = warp * 4; e < nt; e += 4 * NW) {
       double u[4];
+      int dst[4];
 #pragma unroll
-      for (int q = 0; q < 4; ++q) u[q] = __ldcg(U + int64_t(e + q) * 32);
+      for (int q = 0; q < 4; ++q) {
+        const bool in = e + q < nt;
+        u[q] = in ? __ldcg(U + int64_t(e + q) * 32) : 0.0;
+        dst[q] = in ? __ldg(map + e + q) : 0;
+      }
 #pragma unroll
-      for (int q = 0; q < 4; ++q) Wl[map[e + q] * 32] += u[q];
+      for (int q = 0; q < 4; ++q) {
+        if (e + q < nt) Wl[dst[q] * 32] += u[q];
+      }
     }
-    for (; e < nt; ++e) Wl[map[e] * 32] += __ldcg(U + int64_t(e) * 32);
+    compute_sync();
   }
   // ---- elimination of the own columns ----------------------------------------
-  // Blocks of up to kBatchRank pivots: the block's columns are eliminated
-  // right-looking among themselves (scaled columns parked in lbuf, the
-  // unscaled ones left in W), then every trailing entry takes the block's
-  // updates in pivot order — W(i,j) −= l_ik·w_jk for k ascending, the sequence
-  // of ldlt_factor_front — with ONE load and ONE store of W(i,j) per block.
   int pos = 0, neg = 0, zero = 0, zpiv = 0;
   double min_abs = INFINITY;
   double* Dg = Db + (int64_t(g) * T.dim + c0) * 32 + lane;
+  double* Pg = Pb + (int64_t(g) * T.panel_total + fm.panel_off) * 32 + lane;
   double* Ll = lbuf + lane;
-  for (int k0 = 0; k0 < np; k0 += kBatchRank) {
-    const int kb = min(kBatchRank, np - k0);
-    const int jend = k0 + kb;  // first column behind the block
-    for (int q = 0; q < kb; ++q) {
-      const int k = k0 + q;
-      const int ck = tri_col(k, F);
-      const double d = Wl[(ck + k) * 32];
-      {
-        const double eps = 2.220446049250313e-16;
-        pos += d > eps ? 1 : 0;
-        neg += d < -eps ? 1 : 0;
-        zero += (d > eps || d < -eps) ? 0 : 1;
-        zpiv |= d == 0.0 ? 1 : 0;
-        min_abs = fmin(min_abs, fabs(d));
-      }
-      Dg[k * 32] = d;
-      double* Lq = Ll + q * F * 32;
-      for (int i = k + 1; i < F; ++i) {
-        Lq[i * 32] = batch_div(Wl[(ck + i) * 32], d);
-      }
-      // rank-1 update of the remaining columns of the block
-      for (int j = k + 1; j < jend; ++j) {
-        const double wjk = Wl[(ck + j) * 32];
-        double* Wj = Wl + tri_col(j, F) * 32;
-        for (int i = j; i < F; ++i) Wj[i * 32] -= Lq[i * 32] * wjk;
+  for (int k0 = 0; k0 < np; k0 += R) {
+    const int kb = min(R, np - k0);
+    const int jend = k0 + kb;  // first row/column behind the block
+    int cb[R];                 // tri_col of the block's columns
+#pragma unroll
+    for (int q = 0; q < R; ++q) cb[q] = tri_col(min(k0 + q, F - 1), F);
+    // -- phase A.1: the kb×kb diagonal block, redundantly in every warp --------
+    double a[R][R], ls[R][R], dd[R], ry[R];
+#pragma unroll
+    for (int q = 0; q < R; ++q) {
+#pragma unroll
+      for (int p = q; p < R; ++p) {
+        a[p][q] = p < kb ? Wl[(cb[q] + k0 + p) * 32] : 0.0;
       }
     }
-    // trailing columns: all pivots of the block at once
-    for (int j = jend; j < F; ++j) {
-      double wj[kBatchRank];
 #pragma unroll
-      for (int q = 0; q < kBatchRank; ++q) {
-        wj[q] = q < kb ? Wl[(tri_col(k0 + q, F) + j) * 32] : 0.0;
+    for (int q = 0; q < R; ++q) {
+      dd[q] = 1.0;
+      ry[q] = 1.0;
+      if (q < kb) {
+        dd[q] = a[q][q];
+        ry[q] = batch_rcp(dd[q]);
+#pragma unroll
+        for (int p = q + 1; p < R; ++p) {
+          if (p < kb) {
+            ls[p][q] = batch_div(a[p][q], dd[q], ry[q]);
+#pragma unroll
+            for (int q2 = q + 1; q2 <= p; ++q2) a[p][q2] -= ls[p][q] * a[q2][q];
+          }
+        }
       }
-      double* Wj = Wl + tri_col(j, F) * 32;
-      if (kb == kBatchRank) {
-        for (int i = j; i < F; ++i) {
-          double w = Wj[i * 32];
+    }
+    if (warp == 0) {
 #pragma unroll
-          for (int q = 0; q < kBatchRank; ++q) w -= Ll[(q * F + i) * 32] * wj[q];
-          Wj[i * 32] = w;
+      for (int q = 0; q < R; ++q) {
+        if (q < kb) {
+          const double d = dd[q];
+          const double eps = 2.220446049250313e-16;
+          pos += d > eps ? 1 : 0;
+          neg += d < -eps ? 1 : 0;
+          zero += (d > eps || d < -eps) ? 0 : 1;
+          zpiv |= d == 0.0 ? 1 : 0;
+          min_abs = fmin(min_abs, fabs(d));
+          Dg[(k0 + q) * 32] = d;
+          Pg[int64_t(cb[q] + k0 + q) * 32] = d;
+#pragma unroll
+          for (int p = q + 1; p < R; ++p) {
+            if (p < kb) Pg[int64_t(cb[q] + k0 + p) * 32] = ls[p][q];
+          }
+        }
+      }
+    }
+    // -- phase A.2: rows below the block, two at a time per warp ---------------
+    for (int i0 = jend + warp; i0 < F; i0 += 2 * NW) {
+      const int i1 = i0 + NW;
+      const bool two = i1 < F;
+      double w0[R], w1[R], l0[R], l1[R];
+#pragma unroll
+      for (int q = 0; q < R; ++q) {
+        w0[q] = q < kb ? Wl[(cb[q] + i0) * 32] : 0.0;
+        w1[q] = (q < kb && two) ? Wl[(cb[q] + i1) * 32] : 0.0;
+      }
+#pragma unroll
+      for (int q = 0; q < R; ++q) {
+        if (q < kb) {
+#pragma unroll
+          for (int q1 = 0; q1 < q; ++q1) {
+            w0[q] -= l0[q1] * a[q][q1];
+            w1[q] -= l1[q1] * a[q][q1];
+          }
+          l0[q] = batch_div(w0[q], dd[q], ry[q]);
+          l1[q] = batch_div(w1[q], dd[q], ry[q]);
+        }
+      }
+#pragma unroll
+      for (int q = 0; q < R; ++q) {
+        if (q < kb) {
+          Wl[(cb[q] + i0) * 32] = w0[q];
+          Ll[(q * F + i0) * 32] = l0[q];
+          Pg[int64_t(cb[q] + i0) * 32] = l0[q];
+          if (two) {
+            Wl[(cb[q] + i1) * 32] = w1[q];
+            Ll[(q * F + i1) * 32] = l1[q];
+            Pg[int64_t(cb[q] + i1) * 32] = l1[q];
+          }
+        }
+      }
+    }
+    if (jend >= F) break;  // nothing behind the block
+    compute_sync();
+    // -- phase B: trailing columns, all pivots of the block at once ------------
+    for (int j = jend + warp; j < F; j += NW) {
+      double wj[R];
+#pragma unroll
+      for (int q = 0; q < R; ++q) wj[q] = q < kb ? Wl[(cb[q] + j) * 32] : 0.0;
+      double* Wj = Wl + tri_col(j, F) * 32;
+      if (kb == R) {
+        int i = j;
+        for (; i + 2 <= F; i += 2) {
+          double x0 = Wj[i * 32], x1 = Wj[(i + 1) * 32];
+          double m0[R], m1[R];
+#pragma unroll
+          for (int q = 0; q < R; ++q) {
+            m0[q] = Ll[(q * F + i) * 32];
+            m1[q] = Ll[(q * F + i + 1) * 32];
+          }
+#pragma unroll
+          for (int q = 0; q < R; ++q) {
+            x0 -= m0[q] * wj[q];
+            x1 -= m1[q] * wj[q];
+          }
+          Wj[i * 32] = x0;
+          Wj[(i + 1) * 32] = x1;
+        }
+        for (; i < F; ++i) {
+          double x = Wj[i * 32];
+#pragma unroll
+          for (int q = 0; q < R; ++q) x -= Ll[(q * F + i) * 32] * wj[q];
+          Wj[i * 32] = x;
         }
       } else {
         for (int i = j; i < F; ++i) {
-          double w = Wj[i * 32];
-          for (int q = 0; q < kb; ++q) w -= Ll[(q * F + i) * 32] * wj[q];
-          Wj[i * 32] = w;
+          double x = Wj[i * 32];
+#pragma unroll
+          for (int q = 0; q < R; ++q) {
+            if (q < kb) x -= Ll[(q * F + i) * 32] * wj[q];
+          }
+          Wj[i * 32] = x;
         }
       }
     }
-    // the block's columns now take their scaled values (diagonal keeps d)
-    for (int q = 0; q < kb; ++q) {
-      const int k = k0 + q;
-      const int ck = tri_col(k, F);
-      for (int i = k + 1; i < F; ++i) Wl[(ck + i) * 32] = Ll[(q * F + i) * 32];
+    compute_sync();
+  }
+  // ---- update matrix: the tail of the packed triangle; W goes back to zero ----
+  {
+    for (int e = warp; e < n_panel; e += NW) Wl[e * 32] = 0.0;
+    double* Ug = Ub + (int64_t(g) * T.update_total + fm.update_off) * 32 + lane;
+    double* Wu = Wl + n_panel * 32;
+    const int nu = n_tri - n_panel;
+    int e = warp;
+    for (; e + 3 * NW < nu; e += 4 * NW) {
+      double v[4];
+#pragma unroll
+      for (int q = 0; q < 4; ++q) v[q] = Wu[(e + q * NW) * 32];
+#pragma unroll
+      for (int q = 0; q < 4; ++q) {
+        Ug[int64_t(e + q * NW) * 32] = v[q];
+        Wu[(e + q * NW) * 32] = 0.0;
+      }
+    }
+    for (; e < nu; e += NW) {
+      Ug[int64_t(e) * 32] = Wu[e * 32];
+      Wu[e * 32] = 0.0;
     }
   }
-  // ---- write-out: [panel | update] is contiguous in the packed triangle -------
-  {
-    double* Pg = Pb + (int64_t(g) * T.panel_total + fm.panel_off) * 32 + lane;
-    for (int e = 0; e < n_panel; ++e) Pg[int64_t(e) * 32] = Wl[e * 32];
-    double* Ug = Ub + (int64_t(g) * T.update_total + fm.update_off) * 32 + lane;
-    const int nu = n_tri - n_panel;
-    for (int e = 0; e < nu; ++e) Ug[int64_t(e) * 32] = Wl[(n_panel + e) * 32];
+  if (warp == 0) {
+    stats_out[0] = pos;
+    stats_out[1] = neg;
+    stats_out[2] = zero;
+    stats_out[3] = zpiv;
+    const unsigned long long bits = __double_as_longlong(min_abs);
+    stats_out[4] = static_cast<int>(bits & 0xffffffffull);
+    stats_out[5] = static_cast<int>(bits >> 32);
   }
-  stats_out[0] = pos;
-  stats_out[1] = neg;
-  stats_out[2] = zero;
-  stats_out[3] = zpiv;
-  const unsigned long long bits = __double_as_longlong(min_abs);
-  stats_out[4] = static_cast<int>(bits & 0xffffffffull);
-  stats_out[5] = static_cast<int>(bits >> 32);
 }
 
-#ifndef SLPB_BATCH_WARPS
-#define SLPB_BATCH_WARPS 1
-#endif
-
 /// stats: per instance 8 ints (n_pos n_neg n_zero zero_pivot | min|D| bits | pad).
-__global__ void __launch_bounds__(SLPB_BATCH_WARPS * 32)
+__global__ void __launch_bounds__(kBatchWarps * 32, SLPB_BATCH_MIN_BLOCKS)
 k_batch_factor(BatchView T, const double* __restrict__ Kb,
                const double* __restrict__ delta,
                const double* __restrict__ gamma, double* __restrict__ Pb,
                double* Ub, double* __restrict__ Db, int32_t* __restrict__ stats,
-               double* gscratch, int smem_doubles_per_warp) {
+               double* gscratch, int lbuf_offset_doubles) {
   extern __shared__ double smem[];
+  __shared__ int s_ticket;
   const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
-  double* Wsh = smem + size_t(warp) * smem_doubles_per_warp;
   const int total = T.n_super * T.groups;
   int32_t* fcount = T.sync + 4;
+  // invariant: the frontal workspace is all zeros between tasks
+  for (int e = threadIdx.x; e < T.tri_cap * 32; e += blockDim.x) smem[e] = 0.0;
+  int next = 0;
+  if (threadIdx.x == 0) next = atomicAdd(&T.sync[0], 1);
   for (;;) {
-    int t = 0;
-    if (lane == 0) t = atomicAdd(&T.sync[0], 1);
-    t = __shfl_sync(0xffffffffu, t, 0);
+    if (threadIdx.x == 0) s_ticket = next;
+    __syncthreads();
+    const int t = s_ticket;
     if (t >= total) break;
+    // the next ticket is drawn now: its latency hides behind this task
+    if (threadIdx.x == 0) next = atomicAdd(&T.sync[0], 1);
     // the groups of one front hold neighbouring tickets (metadata stays hot);
     // children of (s, g) are (c, g) with smaller tickets
     const int s = T.order[t / T.groups];
     const int g = t % T.groups;
     const FrontMeta fm = load_front_meta(T.metas + s);
     const int n_tri = fm.F * (fm.F + 1) / 2;
-    double* W;
-    double* lbuf;
-    if (n_tri <= T.tri_cap) {
-      W = Wsh;
-      lbuf = Wsh + size_t(T.tri_cap) * 32;
-    } else {
-      // rare oversized front: global scratch of this warp (L2-resident)
-      const size_t per_warp = (size_t(64) * 65 / 2 + kBatchRank * 64) * 32;
-      W = gscratch + (size_t(blockIdx.x) * SLPB_BATCH_WARPS + warp) * per_warp;
-      lbuf = W + size_t(64) * 65 / 2 * 32;
-    }
     int st[6];
     const int inst = g * 32 + lane;
-    batch_factor_front(lane, fm, T, g, Kb, delta[inst], gamma[inst], Pb, Ub, Db,
-                       W, lbuf, &fcount[size_t(g) * T.n_super + s], st);
-    __syncwarp();
-    if (lane == 0 && fm.parent >= 0) {
+    const int* dep = &fcount[size_t(g) * T.n_super + s];
+    if (n_tri <= T.tri_cap) {
+      batch_factor_front<true>(warp, lane, fm, T, g, Kb, delta[inst],
+                               gamma[inst], Pb, Ub, Db, smem,
+                               smem + lbuf_offset_doubles, dep, st);
+    } else {
+      // rare oversized front: global scratch of this block (L2-resident,
+      // zero-initialised at creation and left zero by every task)
+      const size_t per_block = (size_t(64) * 65 / 2 + kBatchRank * 64) * 32;
+      double* W = gscratch + size_t(blockIdx.x) * per_block;
+      batch_factor_front<false>(warp, lane, fm, T, g, Kb, delta[inst],
+                                gamma[inst], Pb, Ub, Db, W,
+                                W + size_t(64) * 65 / 2 * 32, dep, st);
+    }
+    __syncthreads();  // also protects s_ticket and W against the next task
+    if (threadIdx.x == 0 && fm.parent >= 0) {
       red_release_add(&fcount[size_t(g) * T.n_super + fm.parent], 1);
     }
-    int32_t* vs = stats + size_t(inst) * 8;
-    if (st[0]) atomicAdd(&vs[0], st[0]);
-    if (st[1]) atomicAdd(&vs[1], st[1]);
-    if (st[2]) atomicAdd(&vs[2], st[2]);
-    if (st[3]) atomicOr(&vs[3], st[3]);
-    const unsigned long long bits =
-        (unsigned long long)(unsigned)st[4] |
-        ((unsigned long long)(unsigned)st[5] << 32);
-    atomicMin(reinterpret_cast<unsigned long long*>(&vs[4]), bits);
+    if (warp == 0) {
+      int32_t* vs = stats + size_t(inst) * 8;
+      if (st[0]) atomicAdd(&vs[0], st[0]);
+      if (st[1]) atomicAdd(&vs[1], st[1]);
+      if (st[2]) atomicAdd(&vs[2], st[2]);
+      if (st[3]) atomicOr(&vs[3], st[3]);
+      const unsigned long long bits =
+          (unsigned long long)(unsigned)st[4] |
+          ((unsigned long long)(unsigned)st[5] << 32);
+      atomicMin(reinterpret_cast<unsigned long long*>(&vs[4]), bits);
+    }
   }
 }
 
@@ -492,7 +663,7 @@ int slpb_batch_create(slpb_solver* S, int32_t batch, slpb_batch** out) {
                                        (orders.size() * 98) / 100)];
   f_cap = std::max(f_cap, 8);
   if (const char* e = std::getenv("SLPB_BATCH_FCAP")) f_cap = std::atoi(e);
-  f_cap = std::min(f_cap, 28);  // (28·29/2 + 4·28)·256 B = 132 KB
+  f_cap = std::min(f_cap, 28);  // (28·29/2 + 4·28)·256 B = 132 KB per block
   f_cap = std::min<int>(f_cap, Y.max_front);
   B->tri_cap = f_cap * (f_cap + 1) / 2;
   B->fmax = Y.max_front;
@@ -512,12 +683,19 @@ int slpb_batch_create(slpb_solver* S, int32_t batch, slpb_batch** out) {
     fm.parent = Y.super_parent[s];
     fm.pad = 0;
   }
+  // packed position of every own KKT entry; the own diagonal entries (always
+  // present in the pattern) carry which regularisation they take
   std::vector<int32_t> asm_tri(Y.asm_dst.size());
   for (int s = 0; s < ns; ++s) {
     const int64_t F = Y.front_dim[s];
+    const int64_t np = Y.super_first[s + 1] - Y.super_first[s];
     for (int64_t k = Y.asm_ptr[s]; k < Y.asm_ptr[s + 1]; ++k) {
       const int64_t lr = Y.asm_dst[k] % F, lc = Y.asm_dst[k] / F;
-      asm_tri[k] = tri(lr, lc, F);
+      int32_t v = tri(lr, lc, F);
+      if (lr == lc && lc < np) {
+        v |= Y.col_is_primal[Y.super_first[s] + lc] ? kAsmPrimalDiag : kAsmDualDiag;
+      }
+      asm_tri[k] = v;
     }
   }
   std::vector<int32_t> umap(std::max<int64_t>(uoff[ns], 1), 0);
@@ -559,16 +737,15 @@ int slpb_batch_create(slpb_solver* S, int32_t batch, slpb_batch** out) {
   // launch geometry
   int sms = 148;
   cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, S->device);
-  const int per_warp_doubles = (B->tri_cap + kBatchRank * f_cap) * 32;
-  B->factor_smem = SLPB_BATCH_WARPS * per_warp_doubles * 8;
+  B->factor_smem = (B->tri_cap + kBatchRank * f_cap) * 32 * 8;
   CU(raise_dynamic_smem(k_batch_factor, B->factor_smem));
   int per_sm = 1;
   CU(cudaOccupancyMaxActiveBlocksPerMultiprocessor(
-      &per_sm, k_batch_factor, SLPB_BATCH_WARPS * 32, B->factor_smem));
+      &per_sm, k_batch_factor, kBatchWarps * 32, B->factor_smem));
   per_sm = std::max(per_sm, 1);
   const int64_t tasks = int64_t(ns) * G;
-  B->factor_blocks = static_cast<int>(std::min<int64_t>(
-      (tasks + SLPB_BATCH_WARPS - 1) / SLPB_BATCH_WARPS, int64_t(sms) * per_sm));
+  B->factor_blocks =
+      static_cast<int>(std::min<int64_t>(tasks, int64_t(sms) * per_sm));
   B->solve_smem = 4 * B->fmax * 32 * 8;
   CU(raise_dynamic_smem(k_batch_solve, B->solve_smem));
   int per_sm_solve = 1;
@@ -578,8 +755,9 @@ int slpb_batch_create(slpb_solver* S, int32_t batch, slpb_batch** out) {
   B->solve_blocks = static_cast<int>(
       std::min<int64_t>((2 * tasks + 3) / 4, int64_t(sms) * per_sm_solve));
   if (Y.max_front > f_cap) {
-    const size_t per_warp = (size_t(64) * 65 / 2 + kBatchRank * 64) * 32;
-    CU(B->gscratch.alloc(size_t(B->factor_blocks) * SLPB_BATCH_WARPS * per_warp));
+    const size_t per_block = (size_t(64) * 65 / 2 + kBatchRank * 64) * 32;
+    CU(B->gscratch.alloc(size_t(B->factor_blocks) * per_block));
+    CU(B->gscratch.zero(S->stream));
   }
   for (auto& e : B->ev) CU(cudaEventCreate(&e));
   CU(cudaStreamSynchronize(S->stream));
@@ -679,11 +857,10 @@ int slpb_batch_factor(slpb_batch* B, const double* delta, const double* gamma,
   CUB(cudaMemsetAsync(B->sync.p, 0, (4 + size_t(B->groups) * ns) * 4, S->stream));
   CUB(cudaEventRecord(B->ev[0], S->stream));
   const BatchView T = batch_view(B);
-  const int per_warp_doubles = B->factor_smem / 8 / SLPB_BATCH_WARPS;
-  k_batch_factor<<<B->factor_blocks, SLPB_BATCH_WARPS * 32, B->factor_smem,
+  k_batch_factor<<<B->factor_blocks, kBatchWarps * 32, B->factor_smem,
                    S->stream>>>(T, B->Kb.p, B->delta.p, B->gamma.p, B->Pb.p,
                                 B->Ub.p, B->Db.p, B->stats.p, B->gscratch.p,
-                                per_warp_doubles);
+                                B->tri_cap * 32);
   CUB(cudaEventRecord(B->ev[1], S->stream));
   CUB(cudaGetLastError());
   std::vector<int32_t> host(lanes * 8);
