@@ -151,10 +151,35 @@ def steady_rate(trace, warmup, steps):
     return steps, (t1 - t0)
 
 
-def run_cpu(horizon, steps, warmup):
+def pin_to_one_core(index=0):
+    """taskset for this process (the reference path runs on one
+    pinned core). Returns the core, or None when the platform refuses."""
+    try:
+        cores = sorted(os.sched_getaffinity(0))
+        core = cores[index % len(cores)]
+        os.sched_setaffinity(0, {core})
+        return core
+    except Exception:
+        return None
+
+
+def golden_iterations(horizon):
+    """Iterations the reference algorithm (oracle, AMD order, default Options)
+    runs to its own exit status on this workload — committed golden,
+    tests/golden/make_convergence_golden.py. None when there is no golden."""
+    path = os.path.join(ROOT, "tests", "golden", f"converge_cart_pole_{horizon}.npz")
+    if not os.path.exists(path):
+        return None, None
+    import numpy as np
+    g = np.load(path)
+    return int(g["iterations"]), int(g["status"])
+
+
+def run_cpu(horizon, steps, warmup, core_index=0):
     """The reference-style CPU path (oracle), single thread like the reference
-    (it never uses more than one thread per solve)."""
+    (it never uses more than one thread per solve), pinned to one core."""
     from oracle.pyoracle import OracleProblem, have_reference
+    core = pin_to_one_core(core_index)
     backend = "reference" if have_reference() else "restated"
     t0 = time.perf_counter()
     P = OracleProblem("cart_pole", horizon, backend=backend)
@@ -166,9 +191,86 @@ def run_cpu(horizon, steps, warmup):
     k, dt = steady_rate(tr, warmup, steps)
     P.close()
     return {"rate": k / dt, "steps": k, "loop_s": dt, "total_s": total_s,
-            "build_s": build_s, "backend": backend,
+            "build_s": build_s, "backend": backend, "core": core,
+            "setup_s": build_s + max(total_s - (tr[-1].t_end if tr else 0.0), 0.0),
             "fact_per_step": sum(r.factorizations for r in tr) / len(tr),
             "iters": len(tr)}
+
+
+def amd_nnz_l(sb, N, device):
+    """nnz(L) of the workload's KKT system under the reference's minimum-degree
+    order (SLPB_ORDER_AMD), for the roofline's second denominator."""
+    P = sb.Problem("cart_pole", N)
+    D = P.open_device(device)
+    import numpy as np
+    D.set_iterate(P.initial_guess(), np.ones(P.mi), np.zeros(P.me), np.ones(P.mi))
+    D.eval_current(1)
+    st = D.analyze(sb.ORDER_AMD)
+    nnz = int(st.nnz_l)
+    P.close_device()
+    P.close()
+    return nnz
+
+
+def run_batch(sb, N, B, device, peak, fac_bytes, sol_bytes, fac_bytes_amd, sol_bytes_amd):
+    """The many-instance regime (SURVEY §8(f).1, slp::multistart's data-parallel
+    axis): B KKT systems of the workload — the lhs of one iterate and B − 1
+    perturbed copies — factored and solved by ONE launch each (slpb_batch_factor,
+    slpb_batch_solve; lane = instance, SoA [entry][32]). Same dependency chain
+    as one factorisation, B× the bytes: the regime in which the LDLT is bound by
+    memory traffic. Inputs (B × 1.2 MB of values) and the factor (B × 5 MB)
+    exceed the L2 for B ≥ 32, so every launch streams from HBM."""
+    import numpy as np
+    P = sb.Problem("cart_pole", N)
+    D = P.open_device(device)
+    rng = np.random.default_rng(0)
+    x = P.initial_guess() + 0.01 * rng.standard_normal(P.n)
+    D.set_iterate(x, 0.5 + rng.random(P.mi), 0.1 * rng.standard_normal(P.me),
+                  0.5 + rng.random(P.mi))
+    D.eval_current(1)
+    D.analyze()
+    fi = D.factor(1.0, 1e-6, True)
+    D.solve(0.1, 0.99)
+    kkt, rhs = D.download(sb.ARR_KKT_VAL), D.download(sb.ARR_RHS)
+    sol1 = np.concatenate([D.download(sb.ARR_P_X), -D.download(sb.ARR_P_Y)])
+    Bt = sb.Batch(D, B)
+    for i in range(B):
+        Bt.set_system(i, kkt if i == 0 else kkt * (1 + 1e-3 * rng.standard_normal(kkt.size)), rhs)
+    f_ms, s_ms = [], []
+    for rep in range(5):
+        info = Bt.factor(1.0, 1e-6)
+        Bt.solve()
+        f, s_ = Bt.last_ms()
+        f_ms.append(f)
+        s_ms.append(s_)
+    f_ms, s_ms = sorted(f_ms)[len(f_ms) // 2], sorted(s_ms)[len(s_ms) // 2]
+    identical = bool(np.array_equal(Bt.get(0), sol1))
+    inertia_ok = all((i.n_pos, i.n_neg, i.n_zero) == (fi.n_pos, fi.n_neg, 0) for i in info)
+    pe, ue = Bt.stored_entries()
+    Bt.close()
+    P.close_device()
+    P.close()
+    gb = lambda by, ms: B * by / (ms * 1e-3) / 1e9
+    out = {
+        "instances": B, "kernels": "k_batch_factor + k_batch_solve (csrc/batch.cuh)",
+        "factor_ms": f_ms, "solve_ms": s_ms,
+        "factor": {"achieved": gb(fac_bytes, f_ms), "frac": gb(fac_bytes, f_ms) / peak},
+        "solve": {"achieved": gb(sol_bytes, s_ms), "frac": gb(sol_bytes, s_ms) / peak},
+        "factor_plus_solve": {
+            "achieved": gb(fac_bytes + sol_bytes, f_ms + s_ms),
+            "frac": gb(fac_bytes + sol_bytes, f_ms + s_ms) / peak},
+        "with_min_degree_nnz_l": {
+            "factor_plus_solve_frac": gb(fac_bytes_amd + sol_bytes_amd, f_ms + s_ms) / peak},
+        "unit": "GB/s", "peak": peak,
+        "algorithmic_bytes_per_instance": {"factor": fac_bytes, "solve": sol_bytes},
+        "stored_doubles_per_instance": {"panels": pe, "updates": ue},
+        "us_per_instance": (f_ms + s_ms) * 1e3 / B,
+        "instance0_bit_identical_to_single_solve": identical,
+        "inertia_of_every_instance_correct": inertia_ok,
+        "timing": "median of 5 launches, CUDA events on the solver's stream; "
+                  "inputs and factor exceed the L2 (no flush needed)",
+    }
+    return out
 
 
 def main():
@@ -184,6 +286,9 @@ def main():
     ap.add_argument("--multistart", type=int, default=8,
                     help="also time B concurrent solves of the workload on each "
                          "GPU through slp::multistart (0: skip)")
+    ap.add_argument("--batch", type=int, default=512,
+                    help="instances of the batched many-instance LDLT leg "
+                         "(slpb_batch_*: lane = instance; 0: skip)")
     ap.add_argument("--shard", action="store_true",
                     help="N > 1: ONE solve sharded over the GPUs (derivative "
                          "sweep split over the ranks, one NCCL all-gather per "
@@ -218,11 +323,21 @@ def main():
             import concurrent.futures as cf
             import multiprocessing as mp
             with cf.ProcessPoolExecutor(n_rep, mp_context=mp.get_context("spawn")) as ex:
-                results = list(ex.map(run_cpu, [N] * n_rep, [k] * n_rep, [w] * n_rep))
+                results = list(ex.map(run_cpu, [N] * n_rep, [k] * n_rep, [w] * n_rep,
+                                      range(n_rep)))
         r = results[0]
         steps_done = min(x["steps"] for x in results)
         rate = sum(x["steps"] for x in results) / max(x["loop_s"] for x in results)
-        e2e = sum(x["iters"] for x in results) / max(x["total_s"] for x in results)
+        # End to end like the GPU arm's e2e (one whole Problem::solve(), setup
+        # amortised over ALL its iterations): the sample's setup time plus the
+        # sample's steady rate carried over the iterations the reference
+        # algorithm needs to reach its own exit status on this workload (the
+        # committed golden; the sample's own count if there is none).
+        full_iters, full_status = golden_iterations(N)
+        if full_iters is None:
+            full_iters = max(x["iters"] for x in results)
+        setup_s = max(x["setup_s"] for x in results)
+        e2e = n_rep * full_iters / (setup_s + full_iters * n_rep / rate)
         line = {
             "impl": "reference", "metric": METRIC, "value": rate,
             "unit": UNIT, "n_gpus": args.gpus, "steps": steps_done, "warmup": w,
@@ -241,9 +356,20 @@ def main():
                               "(oracle/_ref)" if r["backend"] == "reference"
                               else "")
                            + "; one thread per replica because the reference "
-                             "path is single-threaded")},
+                             "path is single-threaded; each replica pinned to its "
+                             f"own core (sched_setaffinity, core {r['core']} …)")},
             "e2e": {"value": e2e, "unit": UNIT,
-                    "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
+                    "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0,
+                    "what": (f"setup of the sample ({setup_s:.2f} s: problem "
+                             "construction + autodiff setup) + its steady rate "
+                             f"carried over {full_iters} iterations (what the "
+                             "reference algorithm runs to its own exit status on "
+                             "this workload, tests/golden/converge_cart_pole_"
+                             f"{N}.npz"
+                             + (f", status {full_status}" if full_status is not None else "")
+                             + "): setup amortised over a whole solve, like the "
+                             "GPU arm's e2e"),
+                    "setup_s": setup_s, "iterations_projected": full_iters},
         }
         print(json.dumps(line), flush=True)
         return
@@ -323,27 +449,43 @@ def main():
     replicas = 1 if shard else world   # independent solves running side by side
     rate = replicas * k / dt
 
-    # roofline of the dominant kernel, k_factor_tree (supernodal LDLT; also the
-    # kernel BASELINE.json's metric names). Algorithmic bytes per numeric
-    # factorisation = 12·nnz(K) + 12·nnz(L) + 8·dim;
-    # a launch factors one matrix, or two when the regularisation pair is
-    # speculated, so bytes per launch = bytes × factorisations ÷ launches.
+    # ---- roofline -----------------------------------------------------------
+    # Dominant kernel of ONE solve: k_factor_tree (supernodal LDLT). Algorithmic
+    # bytes per numeric factorisation = 12·nnz(K) + 12·nnz(L) + 8·dim (SURVEY
+    # §8d). Only factorisations that RAN TO COMPLETION are counted
+    # (a speculated (0, 0) variant that meets a zero pivot is abandoned and moves
+    # almost nothing); the figure is also given with the minimum-degree nnz(L)
+    # (the reference's AMD order), so that the fill of the dissection order does
+    # not inflate it.
+    nnz_l_amd = amd_nnz_l(sb, N, local_rank)
     fac_bytes = 12 * sym["nnz_kkt"] + 12 * sym["nnz_l"] + 8 * sym["dim"]
+    fac_bytes_amd = 12 * sym["nnz_kkt"] + 12 * nnz_l_amd + 8 * sym["dim"]
     n_launch = max(tim["factor"]["count"], 1)
     fac_ms = tim["factor"]["total_ms"] / n_launch
-    fac_per_launch = cnt["factorizations"] / n_launch
+    fac_per_launch = cnt["factorizations_completed"] / n_launch
     achieved = (fac_bytes * fac_per_launch) / (fac_ms * 1e-3) / 1e9 if fac_ms > 0 else 0.0
+    achieved_amd = (fac_bytes_amd * fac_per_launch) / (fac_ms * 1e-3) / 1e9 if fac_ms > 0 else 0.0
     peak = float(peaks["hbm_gbs"])
     phase_ms = {k_: (v["total_ms"] / max(v["count"], 1)) for k_, v in tim.items()}
     per_step_ms = {k_: v["total_ms"] / iters for k_, v in tim.items()}
-    traffic = None
+    traffic = {}
     tpath = os.path.join(ROOT, "profiles", "traffic.json")
     if os.path.exists(tpath):
         with open(tpath) as f:
-            traffic = json.load(f).get("k_factor_tree_dram_bytes_per_launch")
+            traffic = json.load(f)
+    # k_solve_tree: the fused forward substitution rides in the factor launch,
+    # so most solve launches are the backward half: 12·nnz(L) + 8·dim + 16·dim
+    sol_bytes_full = 2 * 12 * sym["nnz_l"] + 8 * sym["dim"] + 4 * 8 * sym["dim"]
+    sol_bytes_half = 12 * sym["nnz_l"] + 8 * sym["dim"] + 2 * 8 * sym["dim"]
+    sol_ms = phase_ms["solve"]
     # autodiff sweep (second kernel of the step): algorithmic bytes of one full
     # re-linearisation = program stream + bindings + leaves + outputs
     ad_bytes = cnt["program_bytes"] + 8 * (5 * N + 4 + 8 * N + 10) + 8 * sym["nnz_kkt"]
+    batch = None
+    if world == 1 and args.batch > 0:
+        batch = run_batch(sb, N, args.batch, local_rank, peak, fac_bytes,
+                          sol_bytes_full, fac_bytes_amd,
+                          2 * 12 * nnz_l_amd + 40 * sym["dim"])
 
     line = {
         "metric": METRIC, "value": rate, "unit": UNIT, "n_gpus": world,
@@ -381,15 +523,30 @@ def main():
             "kernel": "k_factor_tree (dependency-driven supernodal LDLT, one "
                       "launch per factorisation or speculated pair)",
             "achieved": achieved, "peak": peak, "unit": "GB/s",
-            "frac": achieved / peak if peak else None, "traffic": traffic,
+            "frac": achieved / peak if peak else None,
+            "traffic": traffic.get("k_factor_tree_dram_bytes_per_launch"),
             "peak_kind": peak_kind + " (MEASURED_PEAKS.json hbm_gbs, burst copy)",
             "algorithmic_bytes_per_factorization": fac_bytes,
             "factorizations_per_launch": fac_per_launch,
+            "factorizations_per_launch_what": "completed numeric factorisations "
+                "÷ launches (abandoned zero-pivot variants not counted)",
+            "with_min_degree_nnz_l": {
+                "nnz_l": nnz_l_amd, "algorithmic_bytes_per_factorization": fac_bytes_amd,
+                "achieved": achieved_amd, "frac": achieved_amd / peak if peak else None},
             "ms_per_launch": fac_ms,
             "share_of_step_device_time": per_step_ms["factor"] / max(sum(per_step_ms.values()), 1e-12),
             "note": "latency-bound: the factor (≈7 MB) is L2-sized and the "
                     "assembly tree has 13 dependent levels; see DESIGN.md",
+            "solve": {
+                "kernel": "k_solve_tree (backward substitution; the forward half "
+                          "is carried by the factor launch)",
+                "algorithmic_bytes": sol_bytes_half, "ms": sol_ms,
+                "achieved": sol_bytes_half / (sol_ms * 1e-3) / 1e9 if sol_ms > 0 else None,
+                "frac": sol_bytes_half / (sol_ms * 1e-3) / 1e9 / peak if sol_ms > 0 else None,
+                "traffic": traffic.get("k_solve_tree_dram_bytes_per_launch")},
+            "batch": batch,
             "ad_sweep": {
+                "traffic": traffic.get("k_ad_sweep_dram_bytes_per_launch"),
                 "kernel": "k_ad_sweep (full re-linearisation)",
                 "algorithmic_bytes": ad_bytes,
                 "ms": phase_ms["eval_full"],

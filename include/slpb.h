@@ -425,6 +425,9 @@ typedef struct slpb_counters {
   int64_t factorizations, solves, evals_full, evals_values;
   int64_t tape_nodes, program_bytes, n_clusters, n_program_classes;
   int64_t h2d_bytes, d2h_bytes;
+  /* numeric factorisations that ran through all fronts (a variant that meets
+   * an exactly zero pivot is abandoned and not counted here) */
+  int64_t factorizations_completed;
 } slpb_counters;
 int slpb_get_counters(const slpb_solver* s, slpb_counters* out);
 

@@ -96,7 +96,8 @@ class Counters(C.Structure):
     _fields_ = [(k, C.c_int64) for k in (
         "kernel_launches", "factorizations", "solves", "evals_full",
         "evals_values", "tape_nodes", "program_bytes", "n_clusters",
-        "n_program_classes", "h2d_bytes", "d2h_bytes")]
+        "n_program_classes", "h2d_bytes", "d2h_bytes",
+        "factorizations_completed")]
 
 
 # Every symbol include/slpb.h declares (tests check that the library exports
@@ -678,7 +679,7 @@ class Problem:
         return dict(zip(keys, (int(v) for v in out)))
 
     def counters(self):
-        out = np.zeros(11, dtype=np.int64)
+        out = np.zeros(12, dtype=np.int64)
         self.H.slpbh_counters(self.h, out.ctypes.data_as(_lp))
         keys = [k for k, _ in Counters._fields_]
         return dict(zip(keys, (int(v) for v in out)))

@@ -870,6 +870,7 @@ int slpb_batch_factor(slpb_batch* B, const double* delta, const double* gamma,
   CUB(cudaEventElapsedTime(&B->factor_ms, B->ev[0], B->ev[1]));
   ++S->counters.kernel_launches;
   S->counters.factorizations += B->batch;
+  S->counters.factorizations_completed += B->batch;
   if (info) {
     for (int i = 0; i < B->batch; ++i) {
       info[i].n_pos = host[size_t(i) * 8 + 0];

@@ -2378,7 +2378,11 @@ int factor_impl(slpb_solver* S, int n_variants, const double* delta,
     info[v].n_zero = host_stats[8 * v + 2];
     info[v].zero_pivot = host_stats[8 * v + 3];
     std::memcpy(&info[v].min_abs_d, &host_stats[8 * v + 4], 8);
-    if (info[v].zero_pivot) S->fwd_valid[v] = false;  // factor was abandoned
+    if (info[v].zero_pivot) {
+      S->fwd_valid[v] = false;  // factor was abandoned
+    } else {
+      ++S->counters.factorizations_completed;
+    }
   }
   S->counters.factorizations += n_variants;
   S->factor_sel = 0;

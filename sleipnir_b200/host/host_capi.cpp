@@ -333,13 +333,13 @@ void slpbh_symbolic_stats(void* h, int64_t* out) {
   out[7] = s.etree_height;
 }
 
-/// out[11]: the fields of slpb_counters in declaration order.
+/// out[12]: the fields of slpb_counters in declaration order.
 void slpbh_counters(void* h, int64_t* out) {
   const auto& c = H(h)->problem->last_counters();
-  const int64_t v[11] = {c.kernel_launches, c.factorizations, c.solves,
+  const int64_t v[12] = {c.kernel_launches, c.factorizations, c.solves,
                          c.evals_full, c.evals_values, c.tape_nodes,
                          c.program_bytes, c.n_clusters, c.n_program_classes,
-                         c.h2d_bytes, c.d2h_bytes};
+                         c.h2d_bytes, c.d2h_bytes, c.factorizations_completed};
   std::memcpy(out, v, sizeof(v));
 }
 
