@@ -8,16 +8,23 @@
 // structure-of-arrays pool addressed by 32-bit ids, which is already the
 // layout the device tape is uploaded in (include/slpb.h, slpb_upload_tape).
 // There is one opcode per reference Expression subclass instead of a virtual
-// class hierarchy, and no per-node reference count: the pool is released when
-// the last handle into it dies.
+// class hierarchy, and no per-node reference count: regions of the pool are
+// reclaimed when the PoolScope that created them closes with no handle left
+// into them, and the whole pool when the last handle dies. A handle is a bare
+// id resolved against the CALLING thread's pool: Variables, VariableMatrices
+// and Problems must stay on the thread that created them (Problem::solve
+// checks this); the reference's pointers, by contrast, stay valid across
+// threads.
 #pragma once
 
 #include <algorithm>
 #include <cmath>
 #include <atomic>
 #include <cstdint>
+#include <limits>
 #include <mutex>
 #include <numbers>
+#include <stdexcept>
 #include <utility>
 #include <vector>
 
@@ -50,6 +57,9 @@ class ExpressionPool {
   std::vector<int32_t> scratch;
 
   ExprId make(Op o, ExpressionType t, ExprId l, ExprId r, double v) {
+    if (op.size() >= static_cast<size_t>(std::numeric_limits<ExprId>::max())) {
+      throw std::length_error("expression pool: more than 2^31 - 1 nodes");
+    }
     op.push_back(static_cast<uint8_t>(o));
     type.push_back(static_cast<uint8_t>(t));
     lhs.push_back(l);
@@ -60,8 +70,19 @@ class ExpressionPool {
   }
   size_t size() const { return op.size(); }
 
-  void acquire() { ++m_live; }
-  void release() {
+  /// Handles are counted in total and, while a PoolScope is open, separately
+  /// for nodes created inside it (id ≥ mark): when the scope closes and none of
+  /// those is referenced any more, the pool shrinks back to the mark. The
+  /// reference frees unreferenced nodes one by one through intrusive reference
+  /// counts (util/intrusive_shared_ptr.hpp); here whole regions are reclaimed —
+  /// the gradient trees, the Lagrangian and the restoration problem that every
+  /// Problem::solve() builds and drops.
+  void acquire(ExprId id) {
+    ++m_live;
+    if (static_cast<size_t>(id) >= m_mark) ++m_live_above;
+  }
+  void release(ExprId id) {
+    if (static_cast<size_t>(id) >= m_mark) --m_live_above;
     if (--m_live == 0) clear();
   }
   /// Number of live handles; the analogue of
@@ -71,6 +92,7 @@ class ExpressionPool {
   size_t nodes_in_use() const { return op.size(); }
 
  private:
+  friend class PoolScope;
   void clear() {
     op = {};
     type = {};
@@ -79,7 +101,50 @@ class ExpressionPool {
     val = {};
     scratch = {};
   }
+  void truncate(size_t n) {
+    if (n >= op.size()) return;
+    op.resize(n);
+    type.resize(n);
+    lhs.resize(n);
+    rhs.resize(n);
+    val.resize(n);
+    scratch.resize(n);
+  }
   int64_t m_live = 0;
+  /// Nodes with id ≥ m_mark belong to the innermost open PoolScope.
+  size_t m_mark = std::numeric_limits<size_t>::max();
+  int64_t m_live_above = 0;
+};
+
+/// Reclaims the nodes created while it is open (Problem::solve wraps itself in
+/// one): on destruction, if no handle refers to a node created inside the
+/// scope, the pool is truncated back to its size at entry. Scopes nest
+/// (feasibility restoration builds its own problem inside the outer solve).
+class PoolScope {
+ public:
+  explicit PoolScope(ExpressionPool& pool)
+      : m_pool{pool}, m_saved_mark{pool.m_mark},
+        m_saved_live_above{pool.m_live_above} {
+    m_pool.m_mark = m_pool.size();
+    m_pool.m_live_above = 0;
+  }
+  PoolScope(const PoolScope&) = delete;
+  PoolScope& operator=(const PoolScope&) = delete;
+  ~PoolScope() {
+    const int64_t survivors = m_pool.m_live_above;
+    if (survivors == 0) m_pool.truncate(m_pool.m_mark);
+    // whatever survives is above the enclosing scope's mark as well
+    m_pool.m_mark = m_saved_mark;
+    m_pool.m_live_above =
+        m_saved_mark == std::numeric_limits<size_t>::max()
+            ? 0
+            : m_saved_live_above + survivors;
+  }
+
+ private:
+  ExpressionPool& m_pool;
+  size_t m_saved_mark;
+  int64_t m_saved_live_above;
 };
 
 namespace pool_detail {
@@ -93,6 +158,7 @@ namespace pool_detail {
 struct FastSlot {
   std::atomic<void*> owner{nullptr};  // thread pointer of the owning thread
   ExpressionPool* pool = nullptr;
+  std::mutex claim;  // serialises claiming and giving back
 };
 inline FastSlot& fast_slot() {
   static FastSlot slot;
@@ -118,8 +184,7 @@ struct ThreadPool {
     if (me != nullptr) {
       // publish the pool before the owner becomes visible
       if (slot.owner.load(std::memory_order_acquire) == nullptr) {
-        static std::mutex claim;
-        std::lock_guard<std::mutex> lock{claim};
+        std::lock_guard<std::mutex> lock{slot.claim};
         if (slot.owner.load(std::memory_order_relaxed) == expected) {
           slot.pool = &pool;
           slot.owner.store(me, std::memory_order_release);
@@ -130,9 +195,13 @@ struct ThreadPool {
   }
   ~ThreadPool() {
     if (owns_slot) {
+      // Under the claim mutex, and the pool pointer first: a thread that
+      // claims the slot right after the owner is cleared must not see its
+      // own `pool` overwritten by this teardown.
       FastSlot& slot = fast_slot();
-      slot.owner.store(nullptr, std::memory_order_release);
+      std::lock_guard<std::mutex> lock{slot.claim};
       slot.pool = nullptr;
+      slot.owner.store(nullptr, std::memory_order_release);
     }
   }
 };
@@ -159,10 +228,10 @@ class Expr {
   Expr() = default;
   Expr(std::nullptr_t) {}  // NOLINT
   explicit Expr(ExprId i) : m_id{i} {
-    if (m_id != kNull) pool().acquire();
+    if (m_id != kNull) pool().acquire(m_id);
   }
   Expr(const Expr& o) : m_id{o.m_id} {
-    if (m_id != kNull) pool().acquire();
+    if (m_id != kNull) pool().acquire(m_id);
   }
   Expr(Expr&& o) noexcept : m_id{o.m_id} { o.m_id = kNull; }
   Expr& operator=(const Expr& o) {
@@ -177,7 +246,7 @@ class Expr {
     return *this;
   }
   ~Expr() {
-    if (m_id != kNull) pool().release();
+    if (m_id != kNull) pool().release(m_id);
   }
 
   ExprId id() const { return m_id; }

@@ -4,7 +4,8 @@
 // autodiff/hessian.hpp:49-52), so construction runs detail::gradient_tree once
 // and then the Jacobian row analysis (:55-103). UpLo == Lower keeps only
 // row ≥ col entries when the device assembles the matrix (the reference filters
-// after setFromTriplets, :151-154).
+// after setFromTriplets, :151-154). value() and get() are inherited from
+// Jacobian (hessian.hpp:107-157 of the reference).
 #pragma once
 
 #include <utility>
@@ -32,6 +33,12 @@ class Hessian : public Jacobian<Scalar> {
     this->init();
   }
   static constexpr bool lower_only = (UpLo == Lower);
+
+ protected:
+  /// triangularView<Lower> of the evaluated matrix (hessian.hpp:151-154)
+  bool keep(int row, int col) const override {
+    return !lower_only || row >= col;
+  }
 };
 
 }  // namespace slp

@@ -3,10 +3,11 @@
 // Constructor logic follows the reference's autodiff/jacobian.hpp:54-105: one
 // parent→child list per row, (column, node) output lists found by tagging the
 // wrt leaves through `scratch` AFTER sorting, LINEAR rows evaluated once and
-// cached, QUADRATIC/NONLINEAR rows recorded for re-evaluation. Where the
-// reference's value() (:134-156) re-walks those lists on the CPU every call,
-// this class only exposes them; Problem::solve uploads them through
-// slpb_upload_rows and the per-iteration sweeps run on the device.
+// cached, QUADRATIC/NONLINEAR rows recorded for re-evaluation. Inside
+// Problem::solve these lists are uploaded through slpb_upload_rows and the
+// per-iteration sweeps run on the device; value() and get() (:107-156) are the
+// reference's host walks, for code that uses the autodiff classes on their
+// own outside a solve.
 #pragma once
 
 #include <utility>
@@ -15,6 +16,7 @@
 #include "sleipnir/autodiff/expression_graph.hpp"
 #include "sleipnir/autodiff/variable.hpp"
 #include "sleipnir/autodiff/variable_matrix.hpp"
+#include "sleipnir/util/linalg.hpp"
 
 namespace slp {
 
@@ -33,6 +35,7 @@ class Jacobian {
     init();
   }
 
+  virtual ~Jacobian() = default;
   int rows() const { return m_variables.rows(); }
   int cols() const { return m_wrt.rows(); }
   const VariableMatrix<Scalar>& variables() const { return m_variables; }
@@ -49,6 +52,44 @@ class Jacobian {
   }
   /// Rows whose gradients must be recomputed at every evaluation.
   const std::vector<int>& nonlinear_rows() const { return m_nonlinear_rows; }
+
+  /// The Jacobian as a matrix of expressions (jacobian.hpp:107-127): row by
+  /// row the symbolic gradient of the row's variable.
+  VariableMatrix<Scalar> get() const {
+    VariableMatrix<Scalar> result{detail::empty, m_variables.size(),
+                                  m_wrt.size()};
+    for (int row = 0; row < m_variables.size(); ++row) {
+      const auto grad = detail::gradient_tree(m_top_lists[row], m_wrt);
+      for (int col = 0; col < m_wrt.size(); ++col) {
+        if (grad(col).expr != nullptr) {
+          result(row, col) = grad(col);
+        } else {
+          result(row, col) = Variable<Scalar>{Scalar(0)};
+        }
+      }
+    }
+    return result;
+  }
+
+  /// Evaluates the Jacobian at wrt's current values (jacobian.hpp:134-156):
+  /// values of every row's graph, then one reverse sweep per non-linear row
+  /// on top of the cached triplets of the linear rows; duplicates summed,
+  /// column-major, like Eigen's setFromTriplets.
+  const SparseMatrix<Scalar>& value() {
+    if (m_valued && m_nonlinear_rows.empty()) return m_J;
+    for (const auto& list : m_top_lists) detail::update_values(list);
+    std::vector<detail::Triplet> triplets = m_cached_triplets;
+    std::vector<double> adjoint;
+    for (int row : m_nonlinear_rows) {
+      detail::append_triplets(m_top_lists[row], m_output_lists[row], adjoint,
+                              triplets, row);
+    }
+    m_J = SparseMatrix<Scalar>::from_triplets(
+        m_variables.size(), m_wrt.size(), triplets,
+        [this](int r, int c) { return keep(r, c); });
+    m_valued = true;
+    return m_J;
+  }
 
  protected:
   struct deferred_t {};
@@ -86,8 +127,13 @@ class Jacobian {
     }
   }
 
+  /// Which entries value() keeps (Hessian<Lower>: row ≥ col).
+  virtual bool keep(int, int) const { return true; }
+
   VariableMatrix<Scalar> m_variables;
   VariableMatrix<Scalar> m_wrt;
+  SparseMatrix<Scalar> m_J;
+  bool m_valued = false;
   std::vector<detail::ExpressionGraph> m_top_lists;
   std::vector<std::vector<std::pair<int, detail::ExprId>>> m_output_lists;
   std::vector<detail::Triplet> m_cached_triplets;

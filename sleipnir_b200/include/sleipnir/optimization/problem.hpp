@@ -17,6 +17,7 @@
 #include <concepts>
 #include <array>
 #include <chrono>
+#include <stdexcept>
 #include <cstdio>
 #include <cstdlib>
 #include <functional>
@@ -81,7 +82,7 @@ struct DeviceHandle {
 template <typename Scalar>
 class Problem {
  public:
-  Problem() = default;
+  Problem() : m_pool{&detail::pool()} {}
   /// OCP derives from Problem and is handed around as a Problem.
   virtual ~Problem() = default;
 
@@ -150,8 +151,23 @@ class Problem {
   }
 
   ExitStatus solve(const Options& options, const DeviceOptions& dev_options) {
+    // Expression handles are ids into the CREATING thread's pool: a Problem
+    // cannot be solved from another thread (the reference's pointers could).
+    if (&detail::pool() != m_pool) {
+      throw std::logic_error(
+          "slp::Problem::solve called on another thread than the one that "
+          "built the problem: expression handles are thread-local");
+    }
     const auto t0 = std::chrono::steady_clock::now();
-    const ExitStatus status = solve_impl(options, dev_options);
+    ExitStatus status;
+    {
+      // the gradient trees, the Lagrangian and (if entered) the feasibility
+      // restoration problem built below are dropped again before this returns:
+      // give their nodes back to the pool, so that re-solving a long-lived
+      // Problem (MPC, warm starts) does not grow it
+      detail::PoolScope reclaim{detail::pool()};
+      status = solve_impl(options, dev_options);
+    }
     // everything solve_impl owned (graphs, flattened tape, device handle) has
     // been released by now: the remainder is teardown
     double accounted = 0.0;
@@ -752,6 +768,7 @@ class Problem {
   SolveTrace m_trace;
   slpb_symbolic_stats m_symbolic{};
   SolverKind m_solver_kind = SolverKind::IPM;
+  detail::ExpressionPool* m_pool;  ///< pool of the thread that built the problem
   slpb_counters m_counters{};
   slpb_timers m_timers{};
   std::array<double, 9> m_phase{};

@@ -7,6 +7,7 @@
 // linear-algebra library — the arithmetic of the path runs on the device.
 #pragma once
 
+#include <algorithm>
 #include <cmath>
 #include <cstdint>
 #include <initializer_list>
@@ -52,6 +53,7 @@ class Vector {
     }
     return true;
   }
+  Scalar coeff(int i) const { return m_data[i]; }
   Scalar lpNormInf() const {
     Scalar m(0);
     for (const auto& v : m_data) m = std::max(m, std::abs(v));
@@ -119,6 +121,47 @@ class SparseMatrix {
       if (m_inner[k] == row) return m_values[k];
     }
     return Scalar(0);
+  }
+  /// Eigen's setFromTriplets: duplicates are summed in triplet order, explicit
+  /// zeros are kept, rows sorted within each column. keep(row, col) filters
+  /// (triangularView).
+  template <typename TripletRange, typename Keep>
+  static SparseMatrix from_triplets(int rows, int cols,
+                                    const TripletRange& triplets, Keep keep) {
+    std::vector<int32_t> count(cols + 1, 0);
+    for (const auto& t : triplets) {
+      if (keep(t.row, t.col)) ++count[t.col + 1];
+    }
+    for (int c = 0; c < cols; ++c) count[c + 1] += count[c];
+    std::vector<int32_t> r(count[cols]);
+    std::vector<Scalar> v(count[cols]);
+    std::vector<int32_t> nxt(count.begin(), count.end() - 1);
+    for (const auto& t : triplets) {  // stable within a column
+      if (!keep(t.row, t.col)) continue;
+      r[nxt[t.col]] = t.row;
+      v[nxt[t.col]++] = static_cast<Scalar>(t.value);
+    }
+    SparseMatrix out{rows, cols};
+    out.m_outer.assign(cols + 1, 0);
+    std::vector<int32_t> order;
+    for (int c = 0; c < cols; ++c) {
+      const int32_t b = count[c], e = count[c + 1];
+      order.resize(e - b);
+      for (int32_t k = 0; k < e - b; ++k) order[k] = b + k;
+      std::stable_sort(order.begin(), order.end(),
+                       [&](int32_t x, int32_t y) { return r[x] < r[y]; });
+      for (size_t k = 0; k < order.size(); ++k) {
+        const int32_t q = order[k];
+        if (k > 0 && r[q] == out.m_inner.back()) {
+          out.m_values.back() += v[q];
+        } else {
+          out.m_inner.push_back(r[q]);
+          out.m_values.push_back(v[q]);
+        }
+      }
+      out.m_outer[c + 1] = static_cast<int32_t>(out.m_inner.size());
+    }
+    return out;
   }
 
  private:

@@ -6,6 +6,8 @@
 // Built and run by tests/test_dsl.py; prints "ok <n checks>" or the failures.
 #include <array>
 #include <cstdio>
+#include <stdexcept>
+#include <thread>
 #include <tuple>
 
 #include "sleipnir/optimization/multistart.hpp"
@@ -234,6 +236,150 @@ void multistart_picks_the_best() {
 
 }  // namespace
 
+// jacobian_test.cpp:15-80 (y = x, y = 3x, products), hessian_test.cpp:364-404
+// (Rosenbrock grid, bit-exact off-diagonals), gradient_test.cpp (trig): the
+// standalone value() / get() of the autodiff classes on the host
+void standalone_autodiff_values() {
+  using slp::Gradient;
+  using slp::Hessian;
+  using slp::Jacobian;
+  {
+    VariableMatrix<T> x{3};
+    for (int i = 0; i < 3; ++i) x[i].set_value(T(i + 1));
+    auto y = T(3) * x;
+    Jacobian<T> J{y, x};
+    const auto& Jv = J.value();
+    auto Jg = J.get();
+    for (int r = 0; r < 3; ++r) {
+      for (int c = 0; c < 3; ++c) {
+        CHECK(Jv.coeff(r, c) == (r == c ? T(3) : T(0)));
+        CHECK(Jg(r, c).value() == (r == c ? T(3) : T(0)));
+      }
+    }
+  }
+  {
+    //     [x₁x₂]           [x₂ x₁ 0 ]
+    // y = [x₂x₃]   dy/dx = [0  x₃ x₂]
+    //     [x₁x₃]           [x₃ 0  x₁]
+    VariableMatrix<T> x{3};
+    for (int i = 0; i < 3; ++i) x[i].set_value(T(i + 1));
+    VariableMatrix<T> y{3};
+    y[0] = x[0] * x[1];
+    y[1] = x[1] * x[2];
+    y[2] = x[0] * x[2];
+    Jacobian<T> J{y, x};
+    const T expect[3][3] = {{2, 1, 0}, {0, 3, 2}, {3, 0, 1}};
+    const auto& Jv = J.value();
+    auto Jg = J.get();
+    for (int r = 0; r < 3; ++r) {
+      for (int c = 0; c < 3; ++c) {
+        CHECK(Jv.coeff(r, c) == expect[r][c]);
+        CHECK(Jg(r, c).value() == expect[r][c]);
+      }
+    }
+    // re-evaluation follows the variables (non-linear rows are re-swept)
+    x[0].set_value(T(5));
+    CHECK(J.value().coeff(0, 1) == T(5));
+    CHECK(J.value().coeff(2, 2) == T(5));
+  }
+  {
+    // z = (1 − x)² + 100(y − x²)²
+    VariableMatrix<T> input{2};
+    auto& x = input[0];
+    auto& y = input[1];
+    Hessian<T> hessian{
+        slp::pow(T(1) - x, T(2)) + T(100) * slp::pow(y - slp::pow(x, T(2)), T(2)),
+        input};
+    Hessian<T, slp::Lower> lower{
+        slp::pow(T(1) - x, T(2)) + T(100) * slp::pow(y - slp::pow(x, T(2)), T(2)),
+        input};
+    for (T x0 = T(-2.5); x0 < T(2.5); x0 += T(0.1)) {
+      for (T y0 = T(-2.5); y0 < T(2.5); y0 += T(0.1)) {
+        x.set_value(x0);
+        y.set_value(y0);
+        const auto& H = hessian.value();
+        CHECK(std::abs(H.coeff(0, 0) - (T(1200) * x0 * x0 - T(400) * y0 + T(2))) <= 1e-11);
+        CHECK(H.coeff(0, 1) == T(-400) * x0);
+        CHECK(H.coeff(1, 0) == T(-400) * x0);
+        CHECK(H.coeff(1, 1) == T(200));
+        const auto& L = lower.value();
+        CHECK(L.coeff(1, 0) == T(-400) * x0);
+        CHECK(L.coeff(0, 1) == T(0));  // upper triangle filtered
+      }
+    }
+  }
+  {
+    Variable<T> a, b;
+    a.set_value(T(0.7));
+    b.set_value(T(1.3));
+    VariableMatrix<T> wrt{2};
+    wrt[0] = a;
+    wrt[1] = b;
+    Gradient<T> g{slp::sin(a) * b + a / b, wrt};
+    const auto& gv = g.value();
+    CHECK(gv.coeff(0) == std::cos(T(0.7)) * T(1.3) + T(1) / T(1.3));
+    CHECK(std::abs(gv.coeff(1) - (std::sin(T(0.7)) - T(0.7) / (T(1.3) * T(1.3)))) <= 1e-15);
+    auto gg = g.get();
+    CHECK(std::abs(gg(0).value() - gv.coeff(0)) <= 1e-15);
+    CHECK(std::abs(gg(1).value() - gv.coeff(1)) <= 1e-15);
+  }
+}
+
+// the nodes a PoolScope's body created are reclaimed when it closes
+// with no handle left into them (what Problem::solve does around itself), and
+// kept when one survives; nested scopes hand survivors to the outer one.
+void pool_scope_reclaims_regions() {
+  auto& P = slp::detail::pool();
+  Variable<T> x;
+  x.set_value(T(2));
+  const size_t base = P.nodes_in_use();
+  {
+    slp::detail::PoolScope scope{P};
+    auto tmp = slp::sin(x) * x + x * x;
+    CHECK(P.nodes_in_use() > base);
+  }
+  CHECK(P.nodes_in_use() == base);
+  Variable<T> kept;
+  {
+    slp::detail::PoolScope scope{P};
+    kept = slp::cos(x) * x;
+    {
+      slp::detail::PoolScope inner{P};
+      auto tmp = kept * kept;
+    }
+  }
+  CHECK(P.nodes_in_use() > base);         // `kept` still refers into the region
+  CHECK(kept.value() == std::cos(T(2)) * T(2));
+  // repeated scoped work on a long-lived graph does not grow the pool
+  const size_t steady = P.nodes_in_use();
+  for (int rep = 0; rep < 5; ++rep) {
+    slp::detail::PoolScope scope{P};
+    slp::Hessian<T> H{kept * kept + slp::exp(x), VariableMatrix<T>{x}};
+    (void)H.value();
+  }
+  CHECK(P.nodes_in_use() == steady);
+}
+
+// expression handles are ids into the creating thread's pool, so a
+// Problem refuses to be solved from another thread instead of reading
+// another pool's nodes.
+void problem_is_bound_to_its_thread() {
+  slp::Problem<T> problem;
+  auto x = problem.decision_variable();
+  problem.minimize(x * x);
+  bool threw = false;
+  std::thread th([&] {
+    try {
+      problem.solve();
+    } catch (const std::logic_error&) {
+      threw = true;
+    } catch (...) {
+    }
+  });
+  th.join();
+  CHECK(threw);
+}
+
 int main() {
   equality_constraint_boolean_comparison();
   inequality_constraint_boolean_comparisons();
@@ -242,6 +388,9 @@ int main() {
   expression_types();
   pool_is_returned();
   multistart_picks_the_best();
+  standalone_autodiff_values();
+  pool_scope_reclaims_regions();
+  problem_is_bound_to_its_thread();
   if (g_failures == 0) {
     std::printf("ok %d checks\n", g_checks);
     return 0;
