@@ -120,6 +120,12 @@ const char* slpb_last_error(const slpb_solver* s);
 int slpb_comm_unique_id(void* id_out_128_bytes);
 int slpb_comm_init(slpb_solver* s, int rank, int world,
                    const void* id_128_bytes);
+/* Sharded solves run the host loop on every rank in lockstep; a decision taken
+ * from rank-local information (the wall-clock TIMEOUT of interior_point.hpp:
+ * 860-862, a user callback asking to stop, :414-418) must be taken by all ranks
+ * together or the others block in the next all-gather. *any = OR over the
+ * ranks of local_flag (one tiny all-gather; world == 1: the flag itself). */
+int slpb_comm_agree(slpb_solver* s, int32_t local_flag, int32_t* any);
 
 /* ---- problem upload (once per solve) ------------------------------------ */
 

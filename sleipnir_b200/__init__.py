@@ -104,7 +104,7 @@ class Counters(C.Structure):
 # all of them).
 ABI_SYMBOLS = [
     "slpb_create", "slpb_destroy", "slpb_last_error", "slpb_comm_unique_id",
-    "slpb_comm_init", "slpb_upload_tape",
+    "slpb_comm_init", "slpb_comm_agree", "slpb_upload_tape",
     "slpb_upload_rows", "slpb_finalize", "slpb_set_scaling",
     "slpb_set_ignore_constraint_hessian", "slpb_analyze",
     "slpb_get_permutation", "slpb_set_iterate", "slpb_get_iterate",

@@ -1231,7 +1231,20 @@ bool compile_autodiff(const Tape& tape, const RowSet rows[SLPB_OUT_COUNT],
     return true;
   };
   bool values_ok = false;
-  std::thread values_thread{[&] { values_ok = compile_values(); }};
+  std::string values_exception;
+  // (an exception must not leave the thread: std::terminate would take the
+  // whole process down instead of failing this one solve)
+  std::thread values_thread{[&] {
+    try {
+      values_ok = compile_values();
+    } catch (const std::exception& e) {
+      values_ok = false;
+      values_exception = e.what();
+    } catch (...) {
+      values_ok = false;
+      values_exception = "unknown exception";
+    }
+  }};
   struct Joiner {
     std::thread& t;
     ~Joiner() {
@@ -1308,7 +1321,9 @@ bool compile_autodiff(const Tape& tape, const RowSet rows[SLPB_OUT_COUNT],
 
   values_thread.join();
   if (!values_ok) {
-    out.error = value_error;
+    out.error = values_exception.empty()
+                    ? value_error
+                    : "compiling the value programs: " + values_exception;
     return false;
   }
   return true;

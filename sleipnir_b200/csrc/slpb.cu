@@ -225,7 +225,7 @@ struct slpb_solver {
   NcclComm comm = nullptr;
   ShardPlan shard;
   DevBuf<int32_t> shard_slots;
-  DevBuf<double> shard_buf;
+  DevBuf<double> shard_buf, agree_buf;
   // timing
   cudaEvent_t ev[10] = {};
   float last_ms[5] = {0, 0, 0, 0, 0};
@@ -1887,6 +1887,27 @@ int slpb_comm_init(slpb_solver* S, int rank, int world, const void* id) {
   }
   S->rank = rank;
   S->world = world;
+  return SLPB_OK;
+}
+
+int slpb_comm_agree(slpb_solver* S, int32_t local_flag, int32_t* any) {
+  if (!S || !any) return SLPB_ERR_ARGUMENT;
+  *any = local_flag != 0;
+  if (S->world <= 1) return SLPB_OK;
+  CU(cudaSetDevice(S->device));
+  const AllocScope alloc_scope{S->stream};
+  if (S->agree_buf.n < size_t(S->world)) CU(S->agree_buf.alloc(S->world));
+  const double mine = local_flag != 0 ? 1.0 : 0.0;
+  CU(cudaMemcpyAsync(S->agree_buf.p + S->rank, &mine, sizeof(double),
+                     cudaMemcpyHostToDevice, S->stream));
+  const int rc = nccl_api().AllGather(S->agree_buf.p + S->rank, S->agree_buf.p,
+                                      1, kNcclFloat64, S->comm, S->stream);
+  if (rc != 0) return fail(S, SLPB_ERR_NCCL, "ncclAllGather (slpb_comm_agree)");
+  std::vector<double> all(S->world, 0.0);
+  CU(cudaMemcpyAsync(all.data(), S->agree_buf.p, S->world * sizeof(double),
+                     cudaMemcpyDeviceToHost, S->stream));
+  CU(cudaStreamSynchronize(S->stream));
+  for (double v : all) *any |= v != 0.0;
   return SLPB_OK;
 }
 

@@ -281,7 +281,7 @@ class Problem {
 
     // Problem scaling from g(x₀), A_e(x₀), A_i(x₀) (:615-616;
     // problem_scaling.hpp:100-107)
-    DeviceProblemInfo info{n, me, mi, 1.0};
+    DeviceProblemInfo info{n, me, mi, 1.0, dev_options.world};
     std::vector<Scalar> d_ce, d_ci;
     {
       slpb_point_info pi{};

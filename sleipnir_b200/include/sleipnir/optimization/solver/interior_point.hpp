@@ -316,6 +316,9 @@ struct DeviceProblemInfo {
   int num_equality_constraints = 0;
   int num_inequality_constraints = 0;
   double scaling_f = 1.0;
+  /// Ranks solving this problem in lockstep (slpb_comm_init); > 1 makes the
+  /// rank-local stop decisions collective (slpb_comm_agree).
+  int world = 1;
 };
 
 /// Hook used by Problem::solve to run feasibility restoration on a second
@@ -471,11 +474,19 @@ ExitStatus interior_point(
       hH = download_matrix(SLPB_OUT_H_C, SLPB_ARR_H_VAL);
       hAe = download_matrix(SLPB_OUT_A_E, SLPB_ARR_A_E_VAL);
       hAi = download_matrix(SLPB_OUT_A_I, SLPB_ARR_A_I_VAL);
+      bool stop = false;
       for (const auto& callback : iteration_callbacks) {
         if (callback({iterations, hx, hs, hy, hz, hg, hH, hAe, hAi})) {
-          return ExitStatus::CALLBACK_REQUESTED_STOP;
+          stop = true;
+          break;
         }
       }
+      if (problem.world > 1) {
+        int32_t any = 0;
+        SLP_DEVICE_CALL(dev, slpb_comm_agree(dev, stop ? 1 : 0, &any));
+        stop = any != 0;
+      }
+      if (stop) return ExitStatus::CALLBACK_REQUESTED_STOP;
     }
 
     Scalar alpha_max(1), alpha(1), alpha_z(1);
@@ -763,10 +774,15 @@ ExitStatus interior_point(
     if (iterations >= options.max_iterations) {  // :855-857
       return ExitStatus::MAX_ITERATIONS_EXCEEDED;
     }
-    if (std::chrono::steady_clock::now() - solve_start_time >
-        options.timeout) {  // :860-862
-      return ExitStatus::TIMEOUT;
+    bool timed_out = std::chrono::steady_clock::now() - solve_start_time >
+                     options.timeout;  // :860-862
+    if (problem.world > 1) {
+      // every rank reads its own clock: leave together or not at all
+      int32_t any = 0;
+      SLP_DEVICE_CALL(dev, slpb_comm_agree(dev, timed_out ? 1 : 0, &any));
+      timed_out = any != 0;
     }
+    if (timed_out) return ExitStatus::TIMEOUT;
   }
   return ExitStatus::SUCCESS;
 }

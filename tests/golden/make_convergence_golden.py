@@ -3,7 +3,7 @@ reference's OWN autodiff core, AMD ordering like Eigen::SimplicialLDLT, default
 Options) run to its exit status on the BASELINE.json configurations. Run in
 the authoring container only (minutes per case):
 
-    python tests/golden/make_convergence_golden.py [name:N ...]
+    python tests/golden/make_convergence_golden.py [name:N[:T] ...]
 
 Stored per case: exit status, iteration count, the iteration at which
 feasibility restoration was entered (−1: never), the scalar trace (error, cost,
@@ -24,9 +24,9 @@ CASES = [("cart_pole", 300), ("cart_pole", 1000), ("cart_pole", 5000),
          ("gfold", 2000)]
 
 
-def run(name, N, max_iterations=5000):
+def run(name, N, T=0.0, max_iterations=5000):
     backend = "reference" if have_reference() else "restated"
-    P = OracleProblem(name, N, backend=backend)
+    P = OracleProblem(name, N, T, backend=backend)
     t0 = time.perf_counter()
     st = P.solve(max_iterations=max_iterations, keep_iterates=False)
     dt = time.perf_counter() - t0
@@ -56,9 +56,13 @@ def run(name, N, max_iterations=5000):
 
 
 if __name__ == "__main__":
-    cases = CASES
-    if len(sys.argv) > 1:
-        cases = [(a.split(":")[0], int(a.split(":")[1])) for a in sys.argv[1:]]
-    for name, N in cases:
-        np.savez_compressed(os.path.join(HERE, f"converge_{name}_{N}.npz"),
-                            **run(name, N))
+    cases = [c + (0.0,) for c in CASES]
+    if len(sys.argv) > 1:   # name:N[:T]  (T: horizon in seconds, default the config's)
+        cases = []
+        for a in sys.argv[1:]:
+            f = a.split(":")
+            cases.append((f[0], int(f[1]), float(f[2]) if len(f) > 2 else 0.0))
+    for name, N, T in cases:
+        tag = f"{name}_{N}" + (f"_T{T:g}" if T else "")
+        np.savez_compressed(os.path.join(HERE, f"converge_{tag}.npz"),
+                            **run(name, N, T))
