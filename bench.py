@@ -273,6 +273,58 @@ def run_batch(sb, N, B, device, peak, fac_bytes, sol_bytes, fac_bytes_amd, sol_b
     return out
 
 
+def run_sharded_leg(sb, dist, torch, rank, world, local_rank, warmup, steps,
+                    N=20000, T=10.0):
+    """BASELINE config 4: ONE cart-pole N = 20000 solve over all the GPUs of the
+    run — the re-linearisation sweep split by time steps, every
+    rank eliminating its own subtrees of the assembly tree, one small
+    all-gather of the subtree roots, the top of the tree replicated, solution
+    pieces gathered — against the same solve on one GPU. Strong scaling; the
+    horizon is T = 10 s because with T = 5 s the reference algorithm leaves
+    the Newton loop for feasibility restoration after 27 iterations
+    (tests/test_gpu_configs.py)."""
+    def timed(problem):
+        problem.set_flush_l2(True)
+        dist.barrier()
+        torch.cuda.synchronize()
+        problem.solve(max_iterations=warmup + steps, device=local_rank)
+        tr = problem.trace()
+        k, dt = steady_rate(tr, warmup, steps)
+        t = torch.tensor([dt], device="cuda", dtype=torch.float64)
+        dist.all_reduce(t, op=dist.ReduceOp.MAX)
+        return k, float(t.item())
+
+    single = sb.Problem("cart_pole", N, T)
+    k1, dt1 = timed(single)
+    single.close()
+    box = [sb.comm_unique_id() if rank == 0 else None]
+    dist.broadcast_object_list(box, src=0)
+    P = sb.Problem("cart_pole", N, T)
+    P.set_comm(rank, world, box[0])
+    k2, dt2 = timed(P)
+    cs = P.comm_stats()
+    iters = max(len(P.trace()), 1)
+    P.close()
+    v1, v2 = k1 / dt1, k2 / dt2
+    return {
+        "workload": f"cart-pole direct transcription N={N}, T={T:g} s, ONE solve "
+                    f"sharded over {world} GPUs (strong scaling)",
+        "n_gpus": world, "value": v2, "unit": UNIT, "steps": k2,
+        "ms_per_step": 1e3 * dt2 / k2,
+        "single_gpu_value": v1, "single_gpu_ms_per_step": 1e3 * dt1 / k1,
+        "speedup": v2 / v1, "efficiency": v2 / v1 / world,
+        "allgather": {kind: {"calls_per_step": c["count"] / iters,
+                             "bytes_per_call_per_rank": c["bytes"] / max(c["count"], 1),
+                             "us_per_call": 1e3 * c["total_ms"] / max(c["count"], 1)}
+                      for kind, c in cs.items()},
+        "what": "per Newton iteration: one all-gather of the derivative rows "
+                "(sweep split by tasks), one of the subtree roots per "
+                "factorisation launch (update matrices, update vectors, inertia "
+                "counts), one of the solution pieces per solve; NCCL channel "
+                "set-up happens at slpb_comm_init, outside the timed window",
+    }
+
+
 def main():
     ap = argparse.ArgumentParser()
     ap.add_argument("--gpus", type=int, default=1)
@@ -289,6 +341,9 @@ def main():
     ap.add_argument("--batch", type=int, default=512,
                     help="instances of the batched many-instance LDLT leg "
                          "(slpb_batch_*: lane = instance; 0: skip)")
+    ap.add_argument("--no-sharded-leg", action="store_true",
+                    help="N > 1: skip the strong-scaling leg (ONE cart-pole "
+                         "N=20000 solve sharded over the GPUs)")
     ap.add_argument("--shard", action="store_true",
                     help="N > 1: ONE solve sharded over the GPUs (derivative "
                          "sweep split over the ranks, one NCCL all-gather per "
@@ -446,6 +501,10 @@ def main():
             ms = sb.multistart("cart_pole", N, [5.0] * args.multistart,
                                device=local_rank, n_vars=5 * N + 4)
             ms["wall_s"] = max_over_ranks(ms["wall_s"])
+        sharded = None
+        if world > 1 and not shard and not args.no_sharded_leg:
+            sharded = run_sharded_leg(sb, dist, torch, rank, world, local_rank,
+                                      args.warmup, min(args.steps, 100))
     replicas = 1 if shard else world   # independent solves running side by side
     rate = replicas * k / dt
 
@@ -566,6 +625,7 @@ def main():
             "h2d_bytes_per_step": cnt2["h2d_bytes"] / len(tr2),
             "d2h_bytes_per_step": cnt2["d2h_bytes"] / len(tr2),
             "solve_call_s": total_s},
+        "sharded": sharded,
         "multistart": None if ms is None else {
             "value": world * sum(s_[2] for s_ in ms["starts"]) / ms["wall_s"],
             "unit": UNIT, "starts_per_gpu": args.multistart,

@@ -437,6 +437,17 @@ typedef struct slpb_counters {
 } slpb_counters;
 int slpb_get_counters(const slpb_solver* s, slpb_counters* out);
 
+/* Collectives of a sharded solve (slpb_comm_init with world > 1), per kind:
+ * [0] derivative rows of the re-linearisation sweep, [1] roots of the locally
+ * eliminated subtrees (update matrices, update vectors, inertia counts),
+ * [2] solution pieces. bytes = payload this rank contributes per call × calls. */
+typedef struct slpb_comm_stats {
+  int64_t count[3];
+  int64_t bytes[3];
+  double total_ms[3];   /* pack + all-gather + unpack, CUDA events */
+} slpb_comm_stats;
+int slpb_get_comm_stats(slpb_solver* s, slpb_comm_stats* out);
+
 /* Device time accumulated per phase since the handle was created, measured
  * with CUDA events on the handle's stream (milliseconds) and the number of
  * times each phase ran: [0] eval(full) [1] eval(values) [2] assemble

@@ -114,7 +114,7 @@ ABI_SYMBOLS = [
     "slpb_soc_begin", "slpb_soc_iterate",
     "slpb_trial", "slpb_solve_trial", "slpb_accept_relinearize",
     "slpb_probe_point", "slpb_multiplier_estimate", "slpb_accept", "slpb_array_size", "slpb_download",
-    "slpb_pattern", "slpb_get_counters", "slpb_get_timers",
+    "slpb_pattern", "slpb_get_counters", "slpb_get_timers", "slpb_get_comm_stats",
     "slpb_last_device_ms", "slpb_flush_l2", "slpb_stream",
     "slpb_batch_create", "slpb_batch_destroy", "slpb_batch_size",
     "slpb_batch_set_system", "slpb_batch_capture", "slpb_batch_factor",
@@ -276,6 +276,7 @@ def host_lib() -> C.CDLL:
         L.slpbh_symbolic_stats.argtypes = [vp, _lp]
         L.slpbh_counters.argtypes = [vp, _lp]
         L.slpbh_timers.argtypes = [vp, _dp]
+        L.slpbh_comm_stats.argtypes = [vp, _dp]
         L.slpbh_device_open.restype = vp
         L.slpbh_device_open.argtypes = [vp, C.c_int]
         L.slpbh_device_close.argtypes = [vp]
@@ -690,6 +691,15 @@ class Problem:
         names = ("eval_full", "eval_values", "assemble", "factor", "solve")
         return {k: {"total_ms": float(out[i]), "count": int(out[5 + i])}
                 for i, k in enumerate(names)}
+
+    def comm_stats(self):
+        """Collectives of the last sharded solve: per kind (derivative rows,
+        subtree roots, solution pieces) calls, bytes contributed, device ms."""
+        out = np.zeros(9)
+        self.H.slpbh_comm_stats(self.h, _d(out))
+        names = ("derivative_rows", "subtree_roots", "solution")
+        return {k: {"count": int(out[i]), "bytes": int(out[3 + i]),
+                    "total_ms": float(out[6 + i])} for i, k in enumerate(names)}
 
     def open_device(self, device=0) -> DeviceSession:
         raw = self.H.slpbh_device_open(self.h, device)

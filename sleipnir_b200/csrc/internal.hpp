@@ -263,6 +263,26 @@ struct Symbolic {
 bool analyze_kkt(const Pattern& K, int32_t n_primal, int ordering,
                  const int32_t* user_perm, Symbolic& out, std::string& error);
 
+/// Multi-GPU partition of the assembly tree: the top of the tree
+/// (the interface between the time chunks) is replicated on every rank, every
+/// subtree hanging below it is owned by one rank. A rank eliminates its own
+/// subtrees locally, the ranks exchange the subtree roots' update matrices,
+/// update vectors and inertia counts in one small all-gather, every rank then
+/// eliminates the top redundantly and back-substitutes into its own subtrees.
+struct TreeShard {
+  int32_t world = 1;
+  std::vector<int32_t> owner;        // per front: rank, or −1 = top
+  std::vector<int32_t> top_order;    // top fronts by ascending level
+  /// per rank: own fronts by ascending level, and the roots of its subtrees
+  std::vector<std::vector<int32_t>> rank_order, rank_roots;
+  /// per front (top fronts only, 0 elsewhere): children that are NOT top —
+  /// complete by the time the top is processed
+  std::vector<int32_t> top_fcount_init;
+  std::vector<double> rank_work;     // Σ np·F² of what each rank owns
+  double top_work = 0.0;
+};
+void build_tree_shard(const Symbolic& Y, int32_t world, TreeShard& out);
+
 std::vector<int32_t> order_nested_dissection(const Pattern& lowerK);
 std::vector<int32_t> order_amd(const Pattern& lowerK);
 

@@ -226,6 +226,19 @@ struct slpb_solver {
   ShardPlan shard;
   DevBuf<int32_t> shard_slots;
   DevBuf<double> shard_buf, agree_buf;
+  // multi-GPU sharded factorisation / solve (TreeShard)
+  bool tree_sharded = false;
+  TreeShard tshard;
+  DevBuf<int32_t> ts_my_order, ts_top_order, ts_bwd_order, ts_top_fcount_init;
+  DevBuf<int64_t> ts_pack_pos;   // world × ts_pack_max
+  DevBuf<int32_t> ts_pack_len, ts_sol_idx, ts_sol_len;
+  DevBuf<double> ts_pack_buf, ts_sol_buf;
+  int ts_pack_max = 0, ts_sol_max = 0;
+  std::vector<int32_t> ts_pack_len_host, ts_sol_len_host;
+  slpb_comm_stats comm_stats{};
+  cudaEvent_t cev[6] = {};
+  bool cpending[3] = {false, false, false};
+  int64_t comm_timed[3] = {0, 0, 0};  // calls that were timed
   // timing
   cudaEvent_t ev[10] = {};
   float last_ms[5] = {0, 0, 0, 0, 0};
@@ -243,6 +256,8 @@ namespace slpb {
       return SLPB_ERR_CUDA;                                               \
     }                                                                     \
   } while (0)
+
+void harvest_comm_timers(slpb_solver* S);
 
 inline int fail(slpb_solver* S, int code, const std::string& msg) {
   S->error = msg;
@@ -992,7 +1007,10 @@ __device__ __forceinline__ void st_release(int* p, int v) {
 }
 
 struct TreeView {
-  const int32_t* order;      // fronts by ascending level
+  const int32_t* order;      // fronts to process, by ascending level
+  int32_t n_order;           // how many (single GPU: all n_super of them)
+  const int32_t* order_bwd;  // k_solve_tree, backward pass: walked in reverse
+  int32_t n_fwd, n_bwd;      // fronts of the forward / backward pass
   const FrontMeta* metas;    // one packed record per front
   const int32_t* child_idx;
   const int32_t* rel_idx;
@@ -1047,7 +1065,7 @@ k_factor_tree(TreeView T, const double* __restrict__ Kval, double delta,
     int t = 0;
     if (lane == 0) t = atomicAdd(&T.sync[0], 1);
     t = __shfl_sync(0xffffffffu, t, 0);
-    if (t >= nv * T.n_super) break;
+    if (t >= nv * T.n_order) break;
     // both variants of a front hold neighbouring tickets: children (of either
     // variant) always hold smaller tickets than their parents
     const int v = nv == 2 ? (t & 1) : 0;
@@ -1108,22 +1126,26 @@ k_factor_tree(TreeView T, const double* __restrict__ Kval, double delta,
 }
 
 /// Prepares the ticket/flag words of k_solve_tree. With skip_forward the
-/// forward substitution was carried by the factorisation: tickets start at ns
-/// and every "forward done" flag is already set.
+/// forward substitution was carried by the factorisation: every "forward
+/// done" flag is already set. fcount_init (optional): children of each front
+/// that are complete before the launch (sharded solves: the subtree roots that
+/// arrived through the exchange).
 __global__ void k_init_solve_sync(int32_t* __restrict__ sync, int ns,
-                                  int skip_forward) {
+                                  int skip_forward,
+                                  const int32_t* __restrict__ fcount_init) {
   const int i = blockIdx.x * blockDim.x + threadIdx.x;
-  if (i == 0) sync[0] = skip_forward ? ns : 0;
+  if (i == 0) sync[0] = 0;
   if (i < ns) {
-    sync[1 + i] = 0;                          // fcount
-    sync[1 + ns + i] = skip_forward ? 1 : 0;  // fflag
-    sync[1 + 2 * ns + i] = 0;                 // bflag
+    sync[1 + i] = fcount_init ? fcount_init[i] : 0;  // fcount
+    sync[1 + ns + i] = skip_forward ? 1 : 0;         // fflag
+    sync[1 + 2 * ns + i] = 0;                        // bflag
   }
 }
 
 /// Forward (leaves→roots) then backward (roots→leaves) substitution in one
-/// launch; tickets [0, ns) are forward fronts, [ns, 2ns) backward fronts. The
-/// backward pass writes the un-permuted solution directly.
+/// launch; tickets [0, n_fwd) are forward fronts (T.order), the next n_bwd
+/// backward fronts (T.order_bwd in reverse). The backward pass writes the
+/// un-permuted solution directly.
 __global__ void __launch_bounds__(kTreeWarps * 32)
 k_solve_tree(TreeView T, const double* __restrict__ panels,
              const double* __restrict__ D, const double* __restrict__ rhs,
@@ -1139,8 +1161,8 @@ k_solve_tree(TreeView T, const double* __restrict__ panels,
     int t = 0;
     if (lane == 0) t = atomicAdd(&T.sync[0], 1);
     t = __shfl_sync(0xffffffffu, t, 0);
-    if (t >= 2 * ns) break;
-    if (t < ns) {
+    if (t >= T.n_fwd + T.n_bwd) break;
+    if (t < T.n_fwd) {
       const int s = T.order[t];
       const FrontMeta fm = load_front_meta(T.metas + s);
       ldlt_forward_front_warp(lane, fm, T.metas, T.child_idx, T.rel_idx, T.perm,
@@ -1153,7 +1175,7 @@ k_solve_tree(TreeView T, const double* __restrict__ panels,
         st_release(&fflag[s], 1);
       }
     } else {
-      const int s = T.order[2 * ns - 1 - t];
+      const int s = T.order_bwd[T.n_fwd + T.n_bwd - 1 - t];
       const FrontMeta fm = load_front_meta(T.metas + s);
       ldlt_backward_front_warp(lane, fm, T.rows_idx, panels, D, xperm,
                                fm.parent >= 0 ? &bflag[fm.parent] : &fflag[s]);
@@ -1163,6 +1185,93 @@ k_solve_tree(TreeView T, const double* __restrict__ panels,
       if (lane == 0) st_release(&bflag[s], 1);
     }
   }
+}
+
+// ---- multi-GPU sharded factorisation: exchange of the subtree roots ----------
+// Segment of one rank in the exchange buffer, per variant:
+//   [8 doubles of inertia statistics | len doubles of root data]
+// pos[i]: bit 60 set → update-vector entry, else update-matrix entry.
+constexpr int64_t kPackVecTag = int64_t(1) << 60;
+constexpr int kPackStats = 8;
+
+__global__ void k_tree_pack(const int64_t* __restrict__ pos, int len, int seg,
+                            int nv, const double* __restrict__ updates,
+                            int64_t update_stride,
+                            const double* __restrict__ uvecs,
+                            int64_t uvec_stride,
+                            const int32_t* __restrict__ stats,
+                            double* __restrict__ buf) {
+  const int i = blockIdx.x * blockDim.x + threadIdx.x;
+  const int v = blockIdx.y;
+  if (v >= nv) return;
+  double* out = buf + size_t(v) * seg;
+  if (i < kPackStats) {
+    // n_pos n_neg n_zero zero_pivot as numbers, min|D| as it is
+    double x = 0.0;
+    if (i < 4) {
+      x = static_cast<double>(stats[8 * v + i]);
+    } else if (i == 4) {
+      x = __longlong_as_double(
+          *reinterpret_cast<const long long*>(&stats[8 * v + 4]));
+    }
+    out[i] = x;
+  }
+  if (i < len) {
+    const int64_t p = pos[i];
+    out[kPackStats + i] = (p & kPackVecTag)
+                              ? uvecs[v * uvec_stride + (p & ~kPackVecTag)]
+                              : updates[v * update_stride + p];
+  }
+}
+
+/// After the all-gather: the other ranks' root data goes where the top fronts
+/// expect it, their inertia counts are added to this rank's.
+__global__ void k_tree_unpack(const int64_t* __restrict__ pos_all,
+                              const int32_t* __restrict__ len_all, int max_len,
+                              int seg, int nv, int world, int rank,
+                              const double* __restrict__ buf,
+                              double* __restrict__ updates,
+                              int64_t update_stride, double* __restrict__ uvecs,
+                              int64_t uvec_stride, int32_t* __restrict__ stats,
+                              int with_stats) {
+  const int i = blockIdx.x * blockDim.x + threadIdx.x;
+  const int r = blockIdx.y / nv, v = blockIdx.y % nv;
+  if (r == rank || r >= world) return;
+  const double* in = buf + (size_t(r) * nv + v) * seg;
+  if (with_stats && i == 0) {
+    atomicAdd(&stats[8 * v + 0], static_cast<int>(in[0]));
+    atomicAdd(&stats[8 * v + 1], static_cast<int>(in[1]));
+    atomicAdd(&stats[8 * v + 2], static_cast<int>(in[2]));
+    atomicOr(&stats[8 * v + 3], static_cast<int>(in[3]));
+    atomicMin(reinterpret_cast<unsigned long long*>(&stats[8 * v + 4]),
+              static_cast<unsigned long long>(__double_as_longlong(in[4])));
+  }
+  if (i < len_all[r]) {
+    const int64_t p = pos_all[size_t(r) * max_len + i];
+    const double x = in[kPackStats + i];
+    if (p & kPackVecTag) {
+      uvecs[v * uvec_stride + (p & ~kPackVecTag)] = x;
+    } else {
+      updates[v * update_stride + p] = x;
+    }
+  }
+}
+
+__global__ void k_gather_idx(const double* __restrict__ src,
+                             const int32_t* __restrict__ idx, int len,
+                             double* __restrict__ dst) {
+  const int i = blockIdx.x * blockDim.x + threadIdx.x;
+  if (i < len) dst[i] = src[idx[i]];
+}
+/// After the all-gather: sol[idx[r][i]] = buf[r][i] for every other rank.
+__global__ void k_scatter_idx(const double* __restrict__ buf,
+                              const int32_t* __restrict__ idx_all,
+                              const int32_t* __restrict__ len_all, int max_len,
+                              int world, int rank, double* __restrict__ dst) {
+  const int i = blockIdx.x * blockDim.x + threadIdx.x;
+  const int r = blockIdx.y;
+  if (r == rank || r >= world || i >= len_all[r]) return;
+  dst[idx_all[size_t(r) * max_len + i]] = buf[size_t(r) * max_len + i];
 }
 
 // ---------------------------------------------------------------------------
@@ -1461,6 +1570,8 @@ int run_sweep_sharded(slpb_solver* S, const DevProgramSet& d, const double* leaf
   }
   CU(cudaGetLastError());
   if (plan.max_len == 0) return SLPB_OK;
+  const bool timed = !S->cpending[0];
+  if (timed) CU(cudaEventRecord(S->cev[0], S->stream));
   double* mine = S->shard_buf.p + size_t(r) * plan.max_len;
   if (plan.len[r] > 0) {
     k_shard_pack<<<blocks_for(plan.len[r], 256), 256, 0, S->stream>>>(
@@ -1478,6 +1589,13 @@ int run_sweep_sharded(slpb_solver* S, const DevProgramSet& d, const double* leaf
   k_shard_unpack<<<blocks_for(int64_t(W) * plan.max_len, 256), 256, 0,
                    S->stream>>>(S->shard_buf.p, S->shard_slots.p, plan.max_len,
                                 W, r, stage);
+  if (timed) {
+    CU(cudaEventRecord(S->cev[1], S->stream));
+    S->cpending[0] = true;
+    ++S->comm_timed[0];
+  }
+  ++S->comm_stats.count[0];
+  S->comm_stats.bytes[0] += int64_t(plan.max_len) * 8;
   ++S->counters.kernel_launches;
   CU(cudaGetLastError());
   return SLPB_OK;
@@ -1503,6 +1621,7 @@ int run_gather(slpb_solver* S, const DevGather& d, const double* stage,
 /// After a stream synchronisation: folds the event pairs that were recorded
 /// since the last harvest into the per-phase timers.
 void harvest_timers(slpb_solver* S) {
+  harvest_comm_timers(S);
   for (int w = 0; w < 5; ++w) {
     if (!S->pending[w]) continue;
     float ms = 0.0f;
@@ -1650,6 +1769,10 @@ int kkt_stats(slpb_solver* S, const double* c_e, const double* c_i,
 TreeView tree_view(slpb_solver* S) {
   TreeView T{};
   T.order = S->sy_level_supers.p;
+  T.n_order = S->sym.n_super;
+  T.order_bwd = S->sy_level_supers.p;
+  T.n_fwd = S->sym.n_super;
+  T.n_bwd = S->sym.n_super;
   T.metas = S->sy_metas.p;
   T.child_idx = S->sy_child_idx.p;
   T.rel_idx = S->sy_rel_idx.p;
@@ -1683,19 +1806,157 @@ int build_rhs(slpb_solver* S, double mu, const double* cis_soc,
   return SLPB_OK;
 }
 
+/// Folds the finished event pairs of the collectives into comm_stats (after a
+/// stream synchronisation).
+void harvest_comm_timers(slpb_solver* S) {
+  for (int w = 0; w < 3; ++w) {
+    if (!S->cpending[w]) continue;
+    float ms = 0.0f;
+    if (cudaEventElapsedTime(&ms, S->cev[2 * w], S->cev[2 * w + 1]) ==
+        cudaSuccess) {
+      S->comm_stats.total_ms[w] += ms;
+    } else {
+      cudaGetLastError();
+    }
+    S->cpending[w] = false;
+  }
+}
+
+int nccl_all_gather(slpb_solver* S, const double* mine, double* all,
+                    size_t count) {
+  const int rc =
+      nccl_api().AllGather(mine, all, count, kNcclFloat64, S->comm, S->stream);
+  if (rc != 0) {
+    return fail(S, SLPB_ERR_NCCL,
+                std::string("ncclAllGather: ") +
+                    (nccl_api().GetErrorString ? nccl_api().GetErrorString(rc)
+                                               : "error"));
+  }
+  return SLPB_OK;
+}
+
+/// Sharded factorisation: every rank sends the update matrices and update
+/// vectors of its subtree roots (and, with_stats, its inertia counts) and
+/// receives everybody else's — ONE all-gather of a few KB per rank.
+int exchange_roots(slpb_solver* S, int nv, bool with_stats) {
+  const Symbolic& Y = S->sym;
+  const TreeShard& H = S->tshard;
+  const int W = H.world, r = S->rank;
+  const int seg = kPackStats + S->ts_pack_max;
+  // (timed only when the previous event pair has been read back: no host
+  // synchronisation is added for the sake of the statistics)
+  const bool timed = !S->cpending[1];
+  if (timed) CU(cudaEventRecord(S->cev[2], S->stream));
+  double* mine = S->ts_pack_buf.p + size_t(r) * nv * seg;
+  const int len = static_cast<int>(H.rank_roots.empty() ? 0 : S->ts_pack_len_host[r]);
+  const dim3 gp(blocks_for(std::max(len, kPackStats), 256), nv);
+  k_tree_pack<<<gp, 256, 0, S->stream>>>(
+      S->ts_pack_pos.p + size_t(r) * S->ts_pack_max, len, seg, nv,
+      S->updates.p, Y.update_size, S->uvecs.p,
+      static_cast<int64_t>(Y.rel_ptr.back()), S->fstats.p, mine);
+  int rc = nccl_all_gather(S, mine, S->ts_pack_buf.p, size_t(nv) * seg);
+  if (rc) return rc;
+  const dim3 gu(blocks_for(std::max(S->ts_pack_max, 1), 256), W * nv);
+  k_tree_unpack<<<gu, 256, 0, S->stream>>>(
+      S->ts_pack_pos.p, S->ts_pack_len.p, S->ts_pack_max, seg, nv, W, r,
+      S->ts_pack_buf.p, S->updates.p, Y.update_size, S->uvecs.p,
+      static_cast<int64_t>(Y.rel_ptr.back()), S->fstats.p, with_stats ? 1 : 0);
+  if (timed) {
+    CU(cudaEventRecord(S->cev[3], S->stream));
+    S->cpending[1] = true;
+    ++S->comm_timed[1];
+  }
+  S->counters.kernel_launches += 2;
+  ++S->comm_stats.count[1];
+  S->comm_stats.bytes[1] += int64_t(nv) * seg * 8;
+  CU(cudaGetLastError());
+  return SLPB_OK;
+}
+
+/// Sharded solve: the solution entries of every rank's own columns travel to
+/// all the others (the top's are computed everywhere).
+int exchange_solution(slpb_solver* S) {
+  const TreeShard& H = S->tshard;
+  const int W = H.world, r = S->rank;
+  const bool timed = !S->cpending[2];
+  if (timed) CU(cudaEventRecord(S->cev[4], S->stream));
+  double* mine = S->ts_sol_buf.p + size_t(r) * S->ts_sol_max;
+  const int len = S->ts_sol_len_host[r];
+  if (len > 0) {
+    k_gather_idx<<<blocks_for(len, 256), 256, 0, S->stream>>>(
+        S->sol.p, S->ts_sol_idx.p + size_t(r) * S->ts_sol_max, len, mine);
+  }
+  int rc = nccl_all_gather(S, mine, S->ts_sol_buf.p, S->ts_sol_max);
+  if (rc) return rc;
+  const dim3 g(blocks_for(S->ts_sol_max, 256), W);
+  k_scatter_idx<<<g, 256, 0, S->stream>>>(S->ts_sol_buf.p, S->ts_sol_idx.p,
+                                          S->ts_sol_len.p, S->ts_sol_max, W, r,
+                                          S->sol.p);
+  if (timed) {
+    CU(cudaEventRecord(S->cev[5], S->stream));
+    S->cpending[2] = true;
+    ++S->comm_timed[2];
+  }
+  S->counters.kernel_launches += 2;
+  ++S->comm_stats.count[2];
+  S->comm_stats.bytes[2] += int64_t(S->ts_sol_max) * 8;
+  CU(cudaGetLastError());
+  return SLPB_OK;
+}
+
 int launch_solve(slpb_solver* S, bool skip_forward) {
   const Symbolic& Y = S->sym;
   CU(cudaEventRecord(S->ev[8], S->stream));
   if (S->use_tree) {
     const int sel = S->factor_sel;
-    k_init_solve_sync<<<blocks_for(Y.n_super, 256), 256, 0, S->stream>>>(
-        S->tree_sync.p, Y.n_super, skip_forward ? 1 : 0);
-    const TreeView T = tree_view(S);
-    k_solve_tree<<<S->solve_blocks, kTreeWarps * 32, 0, S->stream>>>(
-        T, S->panels.p + sel * Y.panel_size, S->D.p + size_t(sel) * Y.dim,
-        S->rhs.p, S->xperm.p + size_t(sel) * Y.dim,
-        S->uvecs.p + size_t(sel) * Y.rel_ptr.back(), S->sol.p);
-    S->counters.kernel_launches += 2;
+    const double* panels = S->panels.p + sel * Y.panel_size;
+    const double* Dsel = S->D.p + size_t(sel) * Y.dim;
+    double* xperm = S->xperm.p + size_t(sel) * Y.dim;
+    double* uvecs = S->uvecs.p + size_t(sel) * Y.rel_ptr.back();
+    TreeView T = tree_view(S);
+    if (!S->tree_sharded) {
+      k_init_solve_sync<<<blocks_for(Y.n_super, 256), 256, 0, S->stream>>>(
+          S->tree_sync.p, Y.n_super, skip_forward ? 1 : 0, nullptr);
+      if (skip_forward) T.n_fwd = 0;
+      k_solve_tree<<<S->solve_blocks, kTreeWarps * 32, 0, S->stream>>>(
+          T, panels, Dsel, S->rhs.p, xperm, uvecs, S->sol.p);
+      S->counters.kernel_launches += 2;
+    } else {
+      // Sharded: forward over the own subtrees, exchange of the roots' update
+      // vectors, then forward over the replicated top and backward over top
+      // and own subtrees; the solution pieces travel last.
+      const TreeShard& H = S->tshard;
+      const int n_mine = static_cast<int>(H.rank_order[S->rank].size());
+      const int n_top = static_cast<int>(H.top_order.size());
+      if (!skip_forward) {
+        k_init_solve_sync<<<blocks_for(Y.n_super, 256), 256, 0, S->stream>>>(
+            S->tree_sync.p, Y.n_super, 0, nullptr);
+        T.order = S->ts_my_order.p;
+        T.n_fwd = n_mine;
+        T.n_bwd = 0;
+        if (n_mine > 0) {
+          k_solve_tree<<<S->solve_blocks, kTreeWarps * 32, 0, S->stream>>>(
+              T, panels, Dsel, S->rhs.p, xperm, uvecs, S->sol.p);
+        }
+        S->counters.kernel_launches += 2;
+        // (the roots' data of the selected variant sits at variant offset sel:
+        // exchange both halves' worth only when both exist)
+        int rc = exchange_roots(S, sel + 1, false);
+        if (rc) return rc;
+      }
+      k_init_solve_sync<<<blocks_for(Y.n_super, 256), 256, 0, S->stream>>>(
+          S->tree_sync.p, Y.n_super, skip_forward ? 1 : 0,
+          S->ts_top_fcount_init.p);
+      T.order = S->ts_top_order.p;
+      T.n_fwd = skip_forward ? 0 : n_top;
+      T.order_bwd = S->ts_bwd_order.p;
+      T.n_bwd = n_mine + n_top;
+      k_solve_tree<<<S->solve_blocks, kTreeWarps * 32, 0, S->stream>>>(
+          T, panels, Dsel, S->rhs.p, xperm, uvecs, S->sol.p);
+      S->counters.kernel_launches += 2;
+      int rc = exchange_solution(S);
+      if (rc) return rc;
+    }
   } else {
     const int smem = Y.max_front * static_cast<int>(sizeof(double));
     const double* panels = S->panels.p + S->factor_sel * Y.panel_size;
@@ -1841,6 +2102,9 @@ void slpb_destroy(slpb_solver* S) {
   for (auto& e : S->ev) {
     if (e) cudaEventDestroy(e);
   }
+  for (auto& e : S->cev) {
+    if (e) cudaEventDestroy(e);
+  }
   lap("events");
   if (S->comm && nccl_api().ok) nccl_api().CommDestroy(S->comm);
   if (S->h_results) pinned_pool().give_back(S->h_results);
@@ -1887,7 +2151,13 @@ int slpb_comm_init(slpb_solver* S, int rank, int world, const void* id) {
   }
   S->rank = rank;
   S->world = world;
-  return SLPB_OK;
+  for (auto& e : S->cev) {
+    if (!e) CU(cudaEventCreate(&e));
+  }
+  // NCCL sets its channels up lazily inside the first collective (seconds):
+  // pay for that here, not inside the first Newton iteration
+  int32_t any = 0;
+  return slpb_comm_agree(S, 0, &any);
 }
 
 int slpb_comm_agree(slpb_solver* S, int32_t local_flag, int32_t* any) {
@@ -2183,6 +2453,65 @@ int slpb_analyze(slpb_solver* S, int ordering, const int32_t* perm,
         1, std::min(useful, sms * std::min(std::max(1, 16 / kTreeWarps),
                                            std::max(1, per_sm_solve))));
   }
+  S->tree_sharded = false;
+  if (S->world > 1 && S->use_tree && !std::getenv("SLPB_NO_TREE_SHARD")) {
+    build_tree_shard(Y, S->world, S->tshard);
+    const TreeShard& H = S->tshard;
+    const int W = S->world;
+    std::vector<int32_t> bwd(H.rank_order[S->rank]);
+    bwd.insert(bwd.end(), H.top_order.begin(), H.top_order.end());
+    CU(S->ts_my_order.upload(H.rank_order[S->rank], S->stream));
+    CU(S->ts_top_order.upload(H.top_order, S->stream));
+    CU(S->ts_bwd_order.upload(bwd, S->stream));
+    CU(S->ts_top_fcount_init.upload(H.top_fcount_init, S->stream));
+    // what every rank contributes to the exchange of the subtree roots: the
+    // lower triangle of each root's update matrix and its update vector
+    std::vector<std::vector<int64_t>> pos(W);
+    std::vector<std::vector<int32_t>> sol_idx(W);
+    for (int q = 0; q < W; ++q) {
+      for (int32_t r : H.rank_roots[q]) {
+        const int64_t m =
+            Y.front_dim[r] - (Y.super_first[r + 1] - Y.super_first[r]);
+        for (int64_t j = 0; j < m; ++j) {
+          for (int64_t i = j; i < m; ++i) pos[q].push_back(Y.update_ptr[r] + i + j * m);
+        }
+        for (int64_t i = 0; i < m; ++i) pos[q].push_back((Y.rel_ptr[r] + i) | kPackVecTag);
+      }
+      for (int32_t f : H.rank_order[q]) {
+        for (int32_t c = Y.super_first[f]; c < Y.super_first[f + 1]; ++c) {
+          sol_idx[q].push_back(Y.perm[c]);
+        }
+      }
+    }
+    S->ts_pack_max = 1;
+    S->ts_sol_max = 1;
+    for (int q = 0; q < W; ++q) {
+      S->ts_pack_max = std::max<int>(S->ts_pack_max, static_cast<int>(pos[q].size()));
+      S->ts_sol_max = std::max<int>(S->ts_sol_max, static_cast<int>(sol_idx[q].size()));
+    }
+    std::vector<int64_t> pos_all(size_t(W) * S->ts_pack_max, 0);
+    std::vector<int32_t> sol_all(size_t(W) * S->ts_sol_max, 0);
+    S->ts_pack_len_host.assign(W, 0);
+    S->ts_sol_len_host.assign(W, 0);
+    for (int q = 0; q < W; ++q) {
+      std::copy(pos[q].begin(), pos[q].end(), pos_all.begin() + size_t(q) * S->ts_pack_max);
+      std::copy(sol_idx[q].begin(), sol_idx[q].end(), sol_all.begin() + size_t(q) * S->ts_sol_max);
+      S->ts_pack_len_host[q] = static_cast<int32_t>(pos[q].size());
+      S->ts_sol_len_host[q] = static_cast<int32_t>(sol_idx[q].size());
+    }
+    CU(S->ts_pack_pos.upload(pos_all, S->stream));
+    CU(S->ts_sol_idx.upload(sol_all, S->stream));
+    CU(S->ts_pack_len.upload(S->ts_pack_len_host, S->stream));
+    CU(S->ts_sol_len.upload(S->ts_sol_len_host, S->stream));
+    CU(S->ts_pack_buf.alloc(size_t(W) * 2 * (kPackStats + S->ts_pack_max)));
+    CU(S->ts_pack_buf.zero(S->stream));
+    CU(S->ts_sol_buf.alloc(size_t(W) * S->ts_sol_max));
+    CU(S->ts_sol_buf.zero(S->stream));
+    for (auto& e : S->cev) {
+      if (!e) CU(cudaEventCreate(&e));
+    }
+    S->tree_sharded = true;
+  }
   CU(cudaStreamSynchronize(S->stream));
   SymbolicView& V = S->sview;
   V.dim = Y.dim;
@@ -2364,9 +2693,44 @@ int factor_impl(slpb_solver* S, int n_variants, const double* delta,
                           S->xperm.p,
                           S->uvecs.p};
     for (int v = 0; v < 2; ++v) S->fwd_valid[v] = S->rhs_ready && v < n_variants;
-    k_factor_tree<<<S->tree_blocks, kTreeWarps * 32, smem, S->stream>>>(
-        T, S->Kval.p, delta[0], gamma[0], pair, S->panels.p, S->updates.p,
-        S->D.p, S->fstats.p, S->tree_smem_doubles);
+    if (!S->tree_sharded) {
+      k_factor_tree<<<S->tree_blocks, kTreeWarps * 32, smem, S->stream>>>(
+          T, S->Kval.p, delta[0], gamma[0], pair, S->panels.p, S->updates.p,
+          S->D.p, S->fstats.p, S->tree_smem_doubles);
+    } else {
+      // Sharded: own subtrees → one small all-gather of the
+      // subtree roots (update matrices, update vectors, inertia counts) → the
+      // replicated top, identically on every rank.
+      const TreeShard& H = S->tshard;
+      const int n_mine = static_cast<int>(H.rank_order[S->rank].size());
+      const int n_top = static_cast<int>(H.top_order.size());
+      TreeView Tm = T;
+      Tm.order = S->ts_my_order.p;
+      Tm.n_order = n_mine;
+      if (n_mine > 0) {
+        k_factor_tree<<<S->tree_blocks, kTreeWarps * 32, smem, S->stream>>>(
+            Tm, S->Kval.p, delta[0], gamma[0], pair, S->panels.p, S->updates.p,
+            S->D.p, S->fstats.p, S->tree_smem_doubles);
+        ++S->counters.kernel_launches;
+      }
+      int rc = exchange_roots(S, n_variants, true);
+      if (rc) return rc;
+      CU(cudaMemsetAsync(S->tree_sync.p, 0, 4, S->stream));  // ticket
+      for (int v = 0; v < n_variants; ++v) {
+        CU(cudaMemcpyAsync(S->tree_sync.p + 1 + size_t(v) * Y.n_super,
+                           S->ts_top_fcount_init.p, size_t(Y.n_super) * 4,
+                           cudaMemcpyDeviceToDevice, S->stream));
+      }
+      TreeView Tt = T;
+      Tt.order = S->ts_top_order.p;
+      Tt.n_order = n_top;
+      const int blocks = std::max(
+          1, std::min(S->tree_blocks,
+                      blocks_for(int64_t(n_variants) * n_top, kTreeWarps)));
+      k_factor_tree<<<blocks, kTreeWarps * 32, smem, S->stream>>>(
+          Tt, S->Kval.p, delta[0], gamma[0], pair, S->panels.p, S->updates.p,
+          S->D.p, S->fstats.p, S->tree_smem_doubles);
+    }
     ++S->counters.kernel_launches;
   } else {
     S->fwd_valid[0] = S->fwd_valid[1] = false;
@@ -2773,6 +3137,22 @@ int slpb_last_device_ms(slpb_solver* S, int which, float* ms) {
   CU(cudaStreamSynchronize(S->stream));
   harvest_timers(S);
   *ms = S->last_ms[which];
+  return SLPB_OK;
+}
+
+int slpb_get_comm_stats(slpb_solver* S, slpb_comm_stats* out) {
+  if (!S || !out) return SLPB_ERR_ARGUMENT;
+  CU(cudaSetDevice(S->device));
+  CU(cudaStreamSynchronize(S->stream));
+  harvest_timers(S);
+  *out = S->comm_stats;
+  // (not every call is timed: scale the timed ones to the call count)
+  for (int w = 0; w < 3; ++w) {
+    if (S->comm_timed[w] > 0) {
+      out->total_ms[w] = S->comm_stats.total_ms[w] *
+                         (double(S->comm_stats.count[w]) / double(S->comm_timed[w]));
+    }
+  }
   return SLPB_OK;
 }
 

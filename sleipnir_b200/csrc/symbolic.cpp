@@ -763,4 +763,99 @@ bool analyze_kkt(const Pattern& K, int32_t n_primal, int ordering,
   return true;
 }
 
+void build_tree_shard(const Symbolic& Y, int32_t world, TreeShard& out) {
+  out = TreeShard{};
+  out.world = std::max(world, 1);
+  const int32_t ns = Y.n_super;
+  out.owner.assign(ns, -1);
+  out.top_fcount_init.assign(ns, 0);
+  out.rank_order.assign(out.world, {});
+  out.rank_roots.assign(out.world, {});
+  out.rank_work.assign(out.world, 0.0);
+  // work of every front and of every subtree (children precede parents)
+  std::vector<double> work(ns), subtree(ns);
+  for (int32_t s = 0; s < ns; ++s) {
+    const double F = Y.front_dim[s];
+    const double np = Y.super_first[s + 1] - Y.super_first[s];
+    work[s] = np * F * F + 64.0;
+    subtree[s] = work[s];
+  }
+  double total = 0.0;
+  for (int32_t s = 0; s < ns; ++s) {
+    if (Y.super_parent[s] >= 0) {
+      subtree[Y.super_parent[s]] += subtree[s];
+    } else {
+      total += subtree[s];
+    }
+  }
+  // frontier of subtree roots: start at the roots of the forest and keep
+  // opening the heaviest one (it joins the top, its children the frontier)
+  // until there are enough pieces to balance and none of them dominates
+  std::vector<int32_t> frontier;
+  std::vector<uint8_t> is_top(ns, 0);
+  for (int32_t s = 0; s < ns; ++s) {
+    if (Y.super_parent[s] < 0) frontier.push_back(s);
+  }
+  if (out.world > 1) {
+    const size_t want = static_cast<size_t>(8 * out.world);
+    const double fine = total / (16.0 * out.world);
+    for (;;) {
+      int32_t best = -1;
+      for (size_t k = 0; k < frontier.size(); ++k) {
+        const int32_t s = frontier[k];
+        if (Y.child_ptr[s + 1] == Y.child_ptr[s]) continue;  // a leaf stays
+        if (best < 0 || subtree[s] > subtree[frontier[best]]) {
+          best = static_cast<int32_t>(k);
+        }
+      }
+      if (best < 0) break;
+      const int32_t s = frontier[best];
+      if (frontier.size() >= want && subtree[s] <= fine) break;
+      is_top[s] = 1;
+      frontier.erase(frontier.begin() + best);
+      for (int64_t c = Y.child_ptr[s]; c < Y.child_ptr[s + 1]; ++c) {
+        frontier.push_back(Y.child_idx[c]);
+      }
+    }
+  }
+  // heaviest subtree first, each to the least loaded rank
+  std::sort(frontier.begin(), frontier.end(), [&](int32_t a, int32_t b) {
+    return subtree[a] != subtree[b] ? subtree[a] > subtree[b] : a < b;
+  });
+  std::vector<int32_t> root_owner(ns, -1);
+  for (int32_t r : frontier) {
+    int32_t rank = 0;
+    for (int32_t q = 1; q < out.world; ++q) {
+      if (out.rank_work[q] < out.rank_work[rank]) rank = q;
+    }
+    root_owner[r] = rank;
+    out.rank_work[rank] += subtree[r];
+    out.rank_roots[rank].push_back(r);
+  }
+  // owners flow down from the subtree roots (parents have larger indices)
+  for (int32_t s = ns - 1; s >= 0; --s) {
+    if (is_top[s]) {
+      out.owner[s] = -1;
+      out.top_work += work[s];
+    } else if (root_owner[s] >= 0) {
+      out.owner[s] = root_owner[s];
+    } else {
+      out.owner[s] = out.owner[Y.super_parent[s]];
+    }
+  }
+  for (int32_t k = 0; k < ns; ++k) {
+    const int32_t s = Y.level_supers[k];  // ascending level
+    if (out.owner[s] < 0) {
+      out.top_order.push_back(s);
+    } else {
+      out.rank_order[out.owner[s]].push_back(s);
+    }
+  }
+  for (int32_t s = 0; s < ns; ++s) {
+    const int32_t p = Y.super_parent[s];
+    if (p >= 0 && out.owner[p] < 0 && out.owner[s] >= 0) ++out.top_fcount_init[p];
+  }
+  for (auto& roots : out.rank_roots) std::sort(roots.begin(), roots.end());
+}
+
 }  // namespace slpb

@@ -352,6 +352,16 @@ void slpbh_timers(void* h, double* out) {
   }
 }
 
+/// out[9]: count[3], bytes[3], total_ms[3] of slpb_comm_stats (sharded solves).
+void slpbh_comm_stats(void* h, double* out) {
+  const auto& c = H(h)->problem->last_comm_stats();
+  for (int i = 0; i < 3; ++i) {
+    out[i] = static_cast<double>(c.count[i]);
+    out[3 + i] = static_cast<double>(c.bytes[i]);
+    out[6 + i] = c.total_ms[i];
+  }
+}
+
 /// Builds the autodiff graphs, opens a device handle, uploads and finalises.
 /// Returns the raw slpb_solver* (owned by this handle) so a test can drive the
 /// C ABI of include/slpb.h directly, or NULL on failure.

@@ -359,6 +359,7 @@ class Problem {
     m_last_z = std::move(z);
     slpb_get_counters(dev, &m_counters);
     slpb_get_timers(dev, &m_timers);
+    slpb_get_comm_stats(dev, &m_comm_stats);
     lap(7);
     if (options.diagnostics) {
       if (iterations > 0) print_bottom_iteration_diagnostics();
@@ -446,6 +447,7 @@ class Problem {
   SolverKind last_solver_kind() const { return m_solver_kind; }
   const slpb_counters& last_counters() const { return m_counters; }
   const slpb_timers& last_timers() const { return m_timers; }
+  const slpb_comm_stats& last_comm_stats() const { return m_comm_stats; }
   /// Host seconds of the phases of the last solve(): build_graphs, flatten,
   /// device_create, upload+compile, scaling, analyze, newton loop, write-back,
   /// teardown (release of graphs, tape and device handle).
@@ -771,6 +773,7 @@ class Problem {
   detail::ExpressionPool* m_pool;  ///< pool of the thread that built the problem
   slpb_counters m_counters{};
   slpb_timers m_timers{};
+  slpb_comm_stats m_comm_stats{};
   std::array<double, 9> m_phase{};
   int64_t m_restoration_launches = 0;
   std::vector<Scalar> m_last_s, m_last_y, m_last_z;

@@ -36,6 +36,8 @@ def lib():
         L.emu_analyze.argtypes = [vp, C.c_int, _ip, _lp]
         L.emu_get_perm.argtypes = [vp, _ip]
         L.emu_fronts.argtypes = [vp, _ip, _ip, _ip, _ip]
+        L.emu_tree_shard.restype = C.c_int
+        L.emu_tree_shard.argtypes = [vp, C.c_int, _ip, _dp]
         L.emu_order_amd.argtypes = [C.c_int, _ip, _ip, _ip]
         L.emu_factor.restype = C.c_double
         L.emu_factor.argtypes = [vp, C.c_double, C.c_double, _ip, _dp]
@@ -135,6 +137,13 @@ class Emu:
         a = [np.zeros(n_super, dtype=np.int32) for _ in range(4)]
         self.L.emu_fronts(self.h, *[_i(v) for v in a])
         return a
+
+    def tree_shard(self, world, n_super):
+        """(n_top, owner per front, work per rank + [top])."""
+        owner = np.zeros(n_super, dtype=np.int32)
+        work = np.zeros(world + 1)
+        n_top = self.L.emu_tree_shard(self.h, world, _i(owner), _d(work))
+        return n_top, owner, work
 
     def perm(self):
         p = np.zeros(self.n + self.me, dtype=np.int32)

@@ -374,6 +374,29 @@ int emu_fronts(void* h, int* F, int* np, int* level, int* parent) {
   return S.n_super;
 }
 
+/// Multi-GPU partition of the assembly tree of the last analysis
+/// (build_tree_shard): owner per front (−1: replicated top), and per rank the
+/// work it owns; work[world] = work of the top. Returns the number of top fronts.
+int emu_tree_shard(void* h, int world, int* owner, double* work) {
+  auto* e = static_cast<Emu*>(h);
+  slpb::TreeShard sh;
+  slpb::build_tree_shard(e->sym, world, sh);
+  for (int s = 0; s < e->sym.n_super; ++s) owner[s] = sh.owner[s];
+  for (int r = 0; r < world; ++r) work[r] = sh.rank_work[r];
+  work[world] = sh.top_work;
+  // self-checks of the lists the device side relies on
+  size_t listed = sh.top_order.size();
+  for (const auto& o : sh.rank_order) listed += o.size();
+  if (listed != static_cast<size_t>(e->sym.n_super)) return -1;
+  for (int s = 0; s < e->sym.n_super; ++s) {
+    const int p = e->sym.super_parent[s];
+    // the top is closed upwards; a subtree has one owner
+    if (sh.owner[s] < 0 && p >= 0 && sh.owner[p] >= 0) return -2;
+    if (sh.owner[s] >= 0 && p >= 0 && sh.owner[p] >= 0 && sh.owner[p] != sh.owner[s]) return -3;
+  }
+  return static_cast<int>(sh.top_order.size());
+}
+
 /// Raw output of the product's approximate-minimum-degree ordering
 /// (csrc/amd.cpp) on a lower-triangular pattern, before analyze_kkt folds the
 /// elimination-tree postorder into it.

@@ -1,8 +1,10 @@
 """Worker of tests/test_gpu_parity.py::test_sharded_two_gpu (one process per
 GPU under torch.distributed.run): both ranks solve the same cart-pole problem
-with the re-linearisation sweep sharded over the ranks (one NCCL all-gather per
-Newton iteration) and compare with an unsharded solve on their own GPU —
-the iterates must be bit-identical."""
+with the re-linearisation sweep, the factorisation and the triangular solves
+sharded over the ranks (own subtrees eliminated locally, one small
+all-gather of the subtree roots, the top of the tree replicated, solution
+pieces gathered) and compare with an unsharded solve on their own GPU — the
+iterates must be bit-identical."""
 import os
 import sys
 
@@ -42,8 +44,13 @@ dist.all_gather(xs, x)
 assert all(torch.equal(xs[0], t) for t in xs)
 t_ref = tr_ref[-1].t_end - tr_ref[4].t_end
 t_sh = tr[-1].t_end - tr[4].t_end
+cs = P.comm_stats()
+assert cs["subtree_roots"]["count"] > 0 and cs["solution"]["count"] > 0, cs
 if rank == 0:
+    per = {k: (v["bytes"] / max(v["count"], 1), 1e3 * v["total_ms"] / max(v["count"], 1))
+           for k, v in cs.items()}
     print(f"SHARDED_OK N={N} world={world} iterations={iters} "
-          f"ms/step single={1e3 * t_ref / (iters - 5):.3f} sharded={1e3 * t_sh / (iters - 5):.3f}")
+          f"ms/step single={1e3 * t_ref / (iters - 5):.3f} sharded={1e3 * t_sh / (iters - 5):.3f} "
+          + " ".join(f"{k}: {b / 1024:.1f} KiB {us:.0f} us" for k, (b, us) in per.items()))
 dist.barrier()
 dist.destroy_process_group()

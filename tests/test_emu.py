@@ -190,6 +190,28 @@ def test_product_amd_equals_the_oracle_amd(name, N):
     E.close()
 
 
+@pytest.mark.parametrize("N,world", [(5000, 2), (5000, 4), (20000, 4), (20000, 8), (300, 8)])
+def test_tree_partition_for_the_sharded_factorisation(N, world):
+    """build_tree_shard (csrc/symbolic.cpp): a small replicated top, every
+    subtree below it owned by exactly one rank, balanced work (SURVEY §8(e):
+    local elimination to the interface, redundant interface solve)."""
+    E = Emu("cart_pole", N)
+    E.eval(np.zeros(E.n), np.zeros(E.me), np.ones(E.mi), 1.0, np.ones(E.me),
+           np.ones(E.mi))
+    E.kkt(np.ones(E.mi))
+    st = E.analyze(0)
+    n_top, owner, work = E.tree_shard(world, st["n_super"])
+    assert n_top >= 1                      # (negative: a structural self-check failed)
+    assert set(owner.tolist()) == set(range(-1, world))
+    assert (owner < 0).sum() == n_top
+    total = work.sum()
+    assert work[world] <= (0.05 if N >= 5000 else 0.4) * total   # small replicated part
+    assert work[:world].max() <= 1.25 * work[:world].mean()   # balanced
+    F, npv, lvl, par = E.fronts(st["n_super"])
+    assert lvl[owner < 0].min() >= lvl[owner >= 0].max() - 8
+    E.close()
+
+
 def test_nested_dissection_gives_a_shallow_tree():
     """The assembly tree's depth grows like log N (the reference's AMD order
     has an O(N) chain)."""
