@@ -424,6 +424,32 @@ int slpb_batch_last_ms(const slpb_batch* b, float* factor_ms, float* solve_ms);
 int slpb_batch_bytes(const slpb_batch* b, int64_t* panel_entries,
                      int64_t* update_entries);
 
+/* ---- dynamic batching of concurrent solves (slp::multistart) ---------------
+ * Starts of a multistart run on their own threads with their own handles; what
+ * they share is the lhs pattern. Members of a group hand slpb_factor /
+ * slpb_factor_pair / slpb_solve* / slpb_soc_iterate / slpb_multiplier_estimate
+ * to ONE batched launch per round (slpb_batch_*): a call parks until every
+ * active member has parked one or has left, then the last arriver runs the
+ * round for all. Results per member are bit-identical to the ungrouped solve. */
+typedef struct slpb_group slpb_group;
+int slpb_group_create(int device, int32_t expected_members, slpb_group** out);
+void slpb_group_destroy(slpb_group* g);
+/* After slpb_analyze; blocks until all expected members have joined or been
+ * abandoned. The first member's pattern and elimination order become the
+ * group's; a solver with another pattern is refused (SLPB_ERR_ARGUMENT, counted
+ * as abandoned) and carries on alone. */
+int slpb_group_join(slpb_group* g, slpb_solver* s);
+/* An expected member will not join (its start failed earlier, or it is not
+ * an interior-point problem of this shape). */
+int slpb_group_abandon(slpb_group* g);
+/* The member stops / resumes taking part in the rounds (e.g. around feasibility
+ * restoration, which runs on another handle for many iterations). */
+int slpb_group_pause(slpb_solver* s);
+int slpb_group_resume(slpb_solver* s);
+/* Before slpb_destroy of a member. */
+int slpb_group_leave(slpb_solver* s);
+int slpb_group_stats(slpb_group* g, int64_t* rounds, int64_t* requests);
+
 /* ---- instrumentation ------------------------------------------------------ */
 
 typedef struct slpb_counters {

@@ -120,6 +120,9 @@ ABI_SYMBOLS = [
     "slpb_batch_set_system", "slpb_batch_capture", "slpb_batch_factor",
     "slpb_batch_solve", "slpb_batch_get", "slpb_batch_last_ms",
     "slpb_batch_bytes",
+    "slpb_group_create", "slpb_group_destroy", "slpb_group_join",
+    "slpb_group_abandon", "slpb_group_pause", "slpb_group_resume",
+    "slpb_group_leave", "slpb_group_stats",
 ]
 
 _dev = None

@@ -562,7 +562,14 @@ __global__ void k_batch_gather(const double* __restrict__ src_lane, int64_t n,
 }  // namespace slpb
 
 struct slpb_batch {
-  slpb_solver* S = nullptr;  // owner of the symbolic structure and the stream
+  // Self-contained: own stream and own copies of the symbolic arrays, so that a
+  // batch outlives the solver it was created from (slpb_group).
+  int device = 0;
+  cudaStream_t stream = nullptr;
+  slpb_counters* counters = nullptr;  // optional: where launches are counted
+  int n_super = 0, dim = 0;
+  slpb::DevBuf<int32_t> order, child_idx, rel_idx, rows_idx, asm_src, perm;
+  slpb::DevBuf<uint8_t> col_is_primal;
   int batch = 0, groups = 0;
   int tri_cap = 0, fmax = 0, factor_warps = 1;
   int factor_blocks = 0, solve_blocks = 0, factor_smem = 0, solve_smem = 0;
@@ -583,28 +590,26 @@ namespace slpb {
     cudaError_t e_ = (call);                                              \
     if (e_ != cudaSuccess) {                                              \
       B->error = std::string(#call) + ": " + cudaGetErrorString(e_);      \
-      B->S->error = B->error;                                             \
       return SLPB_ERR_CUDA;                                               \
     }                                                                     \
   } while (0)
 
 inline BatchView batch_view(slpb_batch* B) {
-  slpb_solver* S = B->S;
   BatchView T{};
-  T.order = S->sy_level_supers.p;
+  T.order = B->order.p;
   T.metas = B->metas.p;
-  T.child_idx = S->sy_child_idx.p;
-  T.rel_idx = S->sy_rel_idx.p;
-  T.rows_idx = S->sy_rows_idx.p;
-  T.asm_src = S->sy_asm_src.p;
+  T.child_idx = B->child_idx.p;
+  T.rel_idx = B->rel_idx.p;
+  T.rows_idx = B->rows_idx.p;
+  T.asm_src = B->asm_src.p;
   T.asm_tri = B->asm_tri.p;
   T.umap = B->umap.p;
-  T.col_is_primal = S->sy_col_is_primal.p;
-  T.perm = S->sy_perm.p;
+  T.col_is_primal = B->col_is_primal.p;
+  T.perm = B->perm.p;
   T.sync = B->sync.p;
-  T.n_super = S->sym.n_super;
+  T.n_super = B->n_super;
   T.groups = B->groups;
-  T.dim = S->sym.dim;
+  T.dim = B->dim;
   T.tri_cap = B->tri_cap;
   T.nK = B->nK;
   T.panel_total = B->panel_total;
@@ -630,9 +635,22 @@ int slpb_batch_create(slpb_solver* S, int32_t batch, slpb_batch** out) {
                 "batched factorisation: fronts above order 64 are not supported");
   }
   CU(cudaSetDevice(S->device));
-  const AllocScope alloc_scope{S->stream};
   auto B = std::make_unique<slpb_batch>();
-  B->S = S;
+  B->device = S->device;
+  CU(cudaStreamCreateWithFlags(&B->stream, cudaStreamNonBlocking));
+  cudaStream_t bstream = B->stream;
+  const AllocScope alloc_scope{bstream};
+  // (on any failure below the unique_ptr frees the buffers on this stream)
+  B->counters = &S->counters;
+  B->n_super = Y.n_super;
+  B->dim = Y.dim;
+  CU(B->order.upload(Y.level_supers, bstream));
+  CU(B->child_idx.upload(Y.child_idx, bstream));
+  CU(B->rel_idx.upload(Y.rel_idx, bstream));
+  CU(B->rows_idx.upload(Y.rows_idx, bstream));
+  CU(B->asm_src.upload(Y.asm_src, bstream));
+  CU(B->perm.upload(Y.perm, bstream));
+  CU(B->col_is_primal.upload(Y.col_is_primal, bstream));
   B->batch = batch;
   B->groups = (batch + 31) / 32;
   const int ns = Y.n_super;
@@ -714,9 +732,9 @@ int slpb_batch_create(slpb_solver* S, int32_t batch, slpb_batch** out) {
   B->panel_total = poff[ns];
   B->update_total = std::max<int64_t>(uoff[ns], 1);
   B->rel_total = std::max<int64_t>(Y.rel_ptr.back(), 1);
-  CU(B->metas.upload(metas, S->stream));
-  CU(B->asm_tri.upload(asm_tri, S->stream));
-  CU(B->umap.upload(umap, S->stream));
+  CU(B->metas.upload(metas, bstream));
+  CU(B->asm_tri.upload(asm_tri, bstream));
+  CU(B->umap.upload(umap, bstream));
   CU(B->sync.alloc(4 + 3 * size_t(G) * ns));
   CU(B->stats.alloc(size_t(G) * 32 * 8));
   CU(B->Kb.alloc(size_t(G) * B->nK * 32));
@@ -730,10 +748,10 @@ int slpb_batch_create(slpb_solver* S, int32_t batch, slpb_batch** out) {
   CU(B->delta.alloc(size_t(G) * 32));
   CU(B->gamma.alloc(size_t(G) * 32));
   CU(B->staging.alloc(std::max<size_t>(B->nK, Y.dim)));
-  CU(B->Kb.zero(S->stream));
-  CU(B->rhs.zero(S->stream));
-  CU(B->delta.zero(S->stream));
-  CU(B->gamma.zero(S->stream));
+  CU(B->Kb.zero(bstream));
+  CU(B->rhs.zero(bstream));
+  CU(B->delta.zero(bstream));
+  CU(B->gamma.zero(bstream));
   // launch geometry
   int sms = 148;
   cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, S->device);
@@ -757,24 +775,27 @@ int slpb_batch_create(slpb_solver* S, int32_t batch, slpb_batch** out) {
   if (Y.max_front > f_cap) {
     const size_t per_block = (size_t(64) * 65 / 2 + kBatchRank * 64) * 32;
     CU(B->gscratch.alloc(size_t(B->factor_blocks) * per_block));
-    CU(B->gscratch.zero(S->stream));
+    CU(B->gscratch.zero(bstream));
   }
   for (auto& e : B->ev) CU(cudaEventCreate(&e));
-  CU(cudaStreamSynchronize(S->stream));
+  CU(cudaStreamSynchronize(bstream));
   *out = B.release();
   return SLPB_OK;
 }
 
 void slpb_batch_destroy(slpb_batch* B) {
   if (!B) return;
-  slpb_solver* S = B->S;
-  cudaSetDevice(S->device);
-  cudaStreamSynchronize(S->stream);
+  cudaSetDevice(B->device);
+  cudaStream_t st = B->stream;
+  if (st) cudaStreamSynchronize(st);
   for (auto& e : B->ev) {
     if (e) cudaEventDestroy(e);
   }
-  const slpb::AllocScope alloc_scope{S->stream};
-  delete B;
+  {
+    const slpb::AllocScope alloc_scope{st};
+    delete B;
+  }
+  if (st) cudaStreamDestroy(st);
 }
 
 int slpb_batch_size(const slpb_batch* B, int32_t* batch, int32_t* groups) {
@@ -788,23 +809,22 @@ int slpb_batch_set_system(slpb_batch* B, int32_t instance,
                           const double* kkt_val, const double* rhs) {
   using namespace slpb;
   if (!B || instance < 0 || instance >= B->batch) return SLPB_ERR_ARGUMENT;
-  slpb_solver* S = B->S;
-  CUB(cudaSetDevice(S->device));
+  CUB(cudaSetDevice(B->device));
   const int g = instance / 32, l = instance % 32;
-  const int dim = S->sym.dim;
+  const int dim = B->dim;
   if (kkt_val) {
     CUB(cudaMemcpyAsync(B->staging.p, kkt_val, B->nK * 8, cudaMemcpyHostToDevice,
-                        S->stream));
-    k_batch_scatter<<<blocks_for(B->nK, 256), 256, 0, S->stream>>>(
+                        B->stream));
+    k_batch_scatter<<<blocks_for(B->nK, 256), 256, 0, B->stream>>>(
         B->staging.p, B->nK, B->Kb.p + int64_t(g) * B->nK * 32 + l);
-    CUB(cudaStreamSynchronize(S->stream));
+    CUB(cudaStreamSynchronize(B->stream));
   }
   if (rhs) {
     CUB(cudaMemcpyAsync(B->staging.p, rhs, size_t(dim) * 8,
-                        cudaMemcpyHostToDevice, S->stream));
-    k_batch_scatter<<<blocks_for(dim, 256), 256, 0, S->stream>>>(
+                        cudaMemcpyHostToDevice, B->stream));
+    k_batch_scatter<<<blocks_for(dim, 256), 256, 0, B->stream>>>(
         B->staging.p, dim, B->rhs.p + int64_t(g) * dim * 32 + l);
-    CUB(cudaStreamSynchronize(S->stream));
+    CUB(cudaStreamSynchronize(B->stream));
   }
   CUB(cudaGetLastError());
   return SLPB_OK;
@@ -813,22 +833,21 @@ int slpb_batch_set_system(slpb_batch* B, int32_t instance,
 int slpb_batch_capture(slpb_batch* B, int32_t instance, slpb_solver* src) {
   using namespace slpb;
   if (!B || !src || instance < 0 || instance >= B->batch) return SLPB_ERR_ARGUMENT;
-  slpb_solver* S = B->S;
-  if (!src->finalized || src->recipe.K.nnz() != B->nK || src->dim != S->dim ||
-      src->device != S->device) {
-    return fail(S, SLPB_ERR_ARGUMENT,
-                "slpb_batch_capture: the source solver has another KKT pattern");
+  if (!src->finalized || src->recipe.K.nnz() != B->nK || src->dim != B->dim ||
+      src->device != B->device) {
+    B->error = "slpb_batch_capture: the source solver has another KKT pattern";
+    return SLPB_ERR_ARGUMENT;
   }
-  CUB(cudaSetDevice(S->device));
+  CUB(cudaSetDevice(B->device));
   CUB(cudaStreamSynchronize(src->stream));
   const int g = instance / 32, l = instance % 32;
-  const int dim = S->sym.dim;
-  k_batch_scatter<<<blocks_for(B->nK, 256), 256, 0, S->stream>>>(
+  const int dim = B->dim;
+  k_batch_scatter<<<blocks_for(B->nK, 256), 256, 0, B->stream>>>(
       src->Kval.p, B->nK, B->Kb.p + int64_t(g) * B->nK * 32 + l);
-  k_batch_scatter<<<blocks_for(dim, 256), 256, 0, S->stream>>>(
+  k_batch_scatter<<<blocks_for(dim, 256), 256, 0, B->stream>>>(
       src->rhs.p, dim, B->rhs.p + int64_t(g) * dim * 32 + l);
   CUB(cudaGetLastError());
-  CUB(cudaStreamSynchronize(S->stream));
+  CUB(cudaStreamSynchronize(B->stream));
   return SLPB_OK;
 }
 
@@ -836,41 +855,42 @@ int slpb_batch_factor(slpb_batch* B, const double* delta, const double* gamma,
                       slpb_factor_info* info) {
   using namespace slpb;
   if (!B || !delta || !gamma) return SLPB_ERR_ARGUMENT;
-  slpb_solver* S = B->S;
-  CUB(cudaSetDevice(S->device));
-  const int ns = S->sym.n_super;
+  CUB(cudaSetDevice(B->device));
+  const int ns = B->n_super;
   const size_t lanes = size_t(B->groups) * 32;
   std::vector<double> d(lanes, 1.0), gm(lanes, 1.0);  // padding lanes: identity-ish
   std::copy(delta, delta + B->batch, d.begin());
   std::copy(gamma, gamma + B->batch, gm.begin());
   CUB(cudaMemcpyAsync(B->delta.p, d.data(), lanes * 8, cudaMemcpyHostToDevice,
-                      S->stream));
+                      B->stream));
   CUB(cudaMemcpyAsync(B->gamma.p, gm.data(), lanes * 8, cudaMemcpyHostToDevice,
-                      S->stream));
+                      B->stream));
   std::vector<int32_t> init(lanes * 8, 0);
   {
     const double inf = INFINITY;
     for (size_t i = 0; i < lanes; ++i) std::memcpy(&init[i * 8 + 4], &inf, 8);
   }
   CUB(cudaMemcpyAsync(B->stats.p, init.data(), init.size() * 4,
-                      cudaMemcpyHostToDevice, S->stream));
-  CUB(cudaMemsetAsync(B->sync.p, 0, (4 + size_t(B->groups) * ns) * 4, S->stream));
-  CUB(cudaEventRecord(B->ev[0], S->stream));
+                      cudaMemcpyHostToDevice, B->stream));
+  CUB(cudaMemsetAsync(B->sync.p, 0, (4 + size_t(B->groups) * ns) * 4, B->stream));
+  CUB(cudaEventRecord(B->ev[0], B->stream));
   const BatchView T = batch_view(B);
   k_batch_factor<<<B->factor_blocks, kBatchWarps * 32, B->factor_smem,
-                   S->stream>>>(T, B->Kb.p, B->delta.p, B->gamma.p, B->Pb.p,
+                   B->stream>>>(T, B->Kb.p, B->delta.p, B->gamma.p, B->Pb.p,
                                 B->Ub.p, B->Db.p, B->stats.p, B->gscratch.p,
                                 B->tri_cap * 32);
-  CUB(cudaEventRecord(B->ev[1], S->stream));
+  CUB(cudaEventRecord(B->ev[1], B->stream));
   CUB(cudaGetLastError());
   std::vector<int32_t> host(lanes * 8);
   CUB(cudaMemcpyAsync(host.data(), B->stats.p, host.size() * 4,
-                      cudaMemcpyDeviceToHost, S->stream));
-  CUB(cudaStreamSynchronize(S->stream));
+                      cudaMemcpyDeviceToHost, B->stream));
+  CUB(cudaStreamSynchronize(B->stream));
   CUB(cudaEventElapsedTime(&B->factor_ms, B->ev[0], B->ev[1]));
-  ++S->counters.kernel_launches;
-  S->counters.factorizations += B->batch;
-  S->counters.factorizations_completed += B->batch;
+  if (B->counters) {
+    ++B->counters->kernel_launches;
+    B->counters->factorizations += B->batch;
+    B->counters->factorizations_completed += B->batch;
+  }
   if (info) {
     for (int i = 0; i < B->batch; ++i) {
       info[i].n_pos = host[size_t(i) * 8 + 0];
@@ -886,43 +906,43 @@ int slpb_batch_factor(slpb_batch* B, const double* delta, const double* gamma,
 int slpb_batch_solve(slpb_batch* B) {
   using namespace slpb;
   if (!B) return SLPB_ERR_ARGUMENT;
-  slpb_solver* S = B->S;
-  CUB(cudaSetDevice(S->device));
-  const int ns = S->sym.n_super;
+  CUB(cudaSetDevice(B->device));
+  const int ns = B->n_super;
   CUB(cudaMemsetAsync(B->sync.p, 0, (4 + 3 * size_t(B->groups) * ns) * 4,
-                      S->stream));
-  CUB(cudaEventRecord(B->ev[2], S->stream));
+                      B->stream));
+  CUB(cudaEventRecord(B->ev[2], B->stream));
   const BatchView T = batch_view(B);
-  k_batch_solve<<<B->solve_blocks, 128, B->solve_smem, S->stream>>>(
+  k_batch_solve<<<B->solve_blocks, 128, B->solve_smem, B->stream>>>(
       T, B->Pb.p, B->Db.p, B->rhs.p, B->xperm.p, B->uvecs.p, B->sol.p, B->fmax);
-  CUB(cudaEventRecord(B->ev[3], S->stream));
+  CUB(cudaEventRecord(B->ev[3], B->stream));
   CUB(cudaGetLastError());
-  CUB(cudaStreamSynchronize(S->stream));
+  CUB(cudaStreamSynchronize(B->stream));
   CUB(cudaEventElapsedTime(&B->solve_ms, B->ev[2], B->ev[3]));
-  ++S->counters.kernel_launches;
-  S->counters.solves += B->batch;
+  if (B->counters) {
+    ++B->counters->kernel_launches;
+    B->counters->solves += B->batch;
+  }
   return SLPB_OK;
 }
 
 int slpb_batch_get(slpb_batch* B, int32_t instance, int what, double* dst) {
   using namespace slpb;
   if (!B || !dst || instance < 0 || instance >= B->batch) return SLPB_ERR_ARGUMENT;
-  slpb_solver* S = B->S;
-  CUB(cudaSetDevice(S->device));
+  CUB(cudaSetDevice(B->device));
   const int g = instance / 32, l = instance % 32;
-  const int dim = S->sym.dim;
+  const int dim = B->dim;
   const double* src = nullptr;
   switch (what) {
     case SLPB_BATCH_SOLUTION: src = B->sol.p; break;
     case SLPB_BATCH_D: src = B->Db.p; break;
     default: return SLPB_ERR_ARGUMENT;
   }
-  k_batch_gather<<<blocks_for(dim, 256), 256, 0, S->stream>>>(
+  k_batch_gather<<<blocks_for(dim, 256), 256, 0, B->stream>>>(
       src + int64_t(g) * dim * 32 + l, dim, B->staging.p);
   CUB(cudaGetLastError());
   CUB(cudaMemcpyAsync(dst, B->staging.p, size_t(dim) * 8, cudaMemcpyDeviceToHost,
-                      S->stream));
-  CUB(cudaStreamSynchronize(S->stream));
+                      B->stream));
+  CUB(cudaStreamSynchronize(B->stream));
   return SLPB_OK;
 }
 

@@ -164,6 +164,7 @@ constexpr int kReduceBlocks = 296;  // two per SM
 
 using namespace slpb;
 
+struct slpb_group;
 struct slpb_solver {
   int device = 0;
   cudaStream_t stream = nullptr;
@@ -239,6 +240,9 @@ struct slpb_solver {
   cudaEvent_t cev[6] = {};
   bool cpending[3] = {false, false, false};
   int64_t comm_timed[3] = {0, 0, 0};  // calls that were timed
+  // dynamic batching with other solvers of the same pattern (group.cuh)
+  slpb_group* group = nullptr;
+  int group_slot = -1;
   // timing
   cudaEvent_t ev[10] = {};
   float last_ms[5] = {0, 0, 0, 0, 0};
@@ -258,6 +262,11 @@ namespace slpb {
   } while (0)
 
 void harvest_comm_timers(slpb_solver* S);
+// group.cuh: the member's request joins the group's next batched launch
+int group_factor(slpb_solver* S, int nv, const double* delta,
+                 const double* gamma, slpb_factor_info* info);
+int group_solve(slpb_solver* S);
+int group_download_d(slpb_solver* S, double* dst);
 
 inline int fail(slpb_solver* S, int code, const std::string& msg) {
   S->error = msg;
@@ -1906,6 +1915,11 @@ int exchange_solution(slpb_solver* S) {
 
 int launch_solve(slpb_solver* S, bool skip_forward) {
   const Symbolic& Y = S->sym;
+  if (S->group != nullptr) {
+    CU(cudaStreamSynchronize(S->stream));  // the rhs is complete
+    harvest_timers(S);
+    return group_solve(S);  // forward + backward in the batched launch → S->sol
+  }
   CU(cudaEventRecord(S->ev[8], S->stream));
   if (S->use_tree) {
     const int sel = S->factor_sel;
@@ -2087,6 +2101,7 @@ int slpb_create(int device, slpb_solver** out) {
 
 void slpb_destroy(slpb_solver* S) {
   if (!S) return;
+  if (S->group) slpb_group_leave(S);
   const bool timing = std::getenv("SLPB_DESTROY_TIMING") != nullptr;
   const auto t_begin = std::chrono::steady_clock::now();
   auto lap = [&, last = t_begin](const char* what) mutable {
@@ -2664,6 +2679,13 @@ int factor_impl(slpb_solver* S, int n_variants, const double* delta,
     CU(cudaEventRecord(S->ev[5], S->stream));
     S->pending[2] = true;
   }
+  if (S->group != nullptr) {
+    // member of a batching group: the lhs values are ready on this stream;
+    // the factorisation itself runs in the group's next batched launch
+    CU(cudaStreamSynchronize(S->stream));
+    harvest_timers(S);
+    return group_factor(S, n_variants, delta, gamma, info);
+  }
   CU(cudaEventRecord(S->ev[6], S->stream));
   // stats per variant: n_pos n_neg n_zero zero_pivot | min|D| bits (+inf)
   {
@@ -3063,7 +3085,10 @@ int slpb_download(slpb_solver* S, int which, double* dst) {
     case SLPB_ARR_A_I_VAL: src = S->dvals.p + S->ad.off_ai; break;
     case SLPB_ARR_H_VAL: src = S->dvals.p + S->ad.off_h; break;
     case SLPB_ARR_KKT_VAL: src = S->Kval.p; break;
-    case SLPB_ARR_D: src = S->D.p + size_t(S->factor_sel) * S->dim; break;
+    case SLPB_ARR_D:
+      if (S->group != nullptr) return group_download_d(S, dst);
+      src = S->D.p + size_t(S->factor_sel) * S->dim;
+      break;
     case SLPB_ARR_RHS: src = S->rhs.p; break;
     case SLPB_ARR_P_X: src = S->px.p; break;
     case SLPB_ARR_P_S: src = S->ps.p; break;
@@ -3181,3 +3206,4 @@ void* slpb_stream(slpb_solver* S) { return S ? S->stream : nullptr; }
 }  // extern "C"
 
 #include "batch.cuh"
+#include "group.cuh"

@@ -6,6 +6,7 @@
 #include <algorithm>
 #include <array>
 #include <chrono>
+#include <cstdlib>
 #include <cmath>
 #include <cstring>
 #include <memory>
@@ -175,8 +176,12 @@ double slpbh_multistart(const char* name, int N, int count, const double* p0,
   std::vector<Result> all;
   const auto t0 = std::chrono::steady_clock::now();
   try {
+    // SLPB_NO_GROUP=1: every start factors and solves on its own (round 1's
+    // behaviour), for comparisons
+    const int batch_device = std::getenv("SLPB_NO_GROUP") ? -1 : device;
     const Result win = slp::multistart<double, Vars>(
-        solve, std::span<const Vars>{guesses}, max_concurrency, &all);
+        solve, std::span<const Vars>{guesses}, max_concurrency, &all,
+        batch_device);
     const double wall = std::chrono::duration<double>(
                             std::chrono::steady_clock::now() - t0)
                             .count();

@@ -11,6 +11,13 @@
 // assembly tree) and leaves most of the GPU idle, so kernels of
 // concurrent starts overlap on the SMs. `max_concurrency` bounds how many
 // run at once (0: all of them, as the reference does).
+//
+// Starts that turn out to share one KKT pattern (the usual case: the same
+// problem from different guesses) also share their linear algebra: the first
+// Problem::solve() of every start joins a slpb_group (include/slpb.h), and the
+// factorisations and triangular solves of all starts run as ONE batched launch
+// per round (lane = instance) instead of one latency-bound launch per start.
+// Each start's iterates are bit-identical to what it computes alone.
 #pragma once
 
 #include <algorithm>
@@ -20,8 +27,19 @@
 #include <vector>
 
 #include "sleipnir/optimization/solver/exit_status.hpp"
+#include "slpb.h"
 
 namespace slp {
+
+namespace detail {
+/// What a start's thread knows about the multistart it belongs to.
+struct MultistartContext {
+  slpb_group* group = nullptr;
+};
+inline thread_local MultistartContext* tls_multistart = nullptr;
+/// The start's first Problem::solve() has already answered the group's call.
+inline thread_local bool tls_multistart_answered = false;
+}  // namespace detail
 
 /// The result of a multistart solve (multistart.hpp:16-29).
 template <typename Scalar, typename DecisionVariables>
@@ -45,7 +63,8 @@ MultistartResult<Scalar, DecisionVariables> multistart(
     std::span<const DecisionVariables> initial_guesses,
     int max_concurrency = 0,
     std::vector<MultistartResult<Scalar, DecisionVariables>>* all_results =
-        nullptr) {
+        nullptr,
+    int batch_device = 0) {
   using Result = MultistartResult<Scalar, DecisionVariables>;
   const size_t count = initial_guesses.size();
   std::vector<Result> results;
@@ -53,12 +72,39 @@ MultistartResult<Scalar, DecisionVariables> multistart(
   const size_t wave =
       max_concurrency > 0 ? static_cast<size_t>(max_concurrency) : count;
   for (size_t begin = 0; begin < count; begin += wave) {
+    const size_t end = std::min(count, begin + wave);
+    // the starts of a wave batch their linear algebra (batch_device < 0: off)
+    detail::MultistartContext context;
+    if (batch_device >= 0 && end - begin > 1) {
+      if (slpb_group_create(batch_device, static_cast<int32_t>(end - begin),
+                            &context.group) != SLPB_OK) {
+        context.group = nullptr;
+      }
+    }
     std::vector<std::future<Result>> futures;
-    for (size_t i = begin; i < std::min(count, begin + wave); ++i) {
-      futures.emplace_back(std::async(std::launch::async, std::cref(solve),
-                                      std::cref(initial_guesses[i])));
+    for (size_t i = begin; i < end; ++i) {
+      futures.emplace_back(std::async(
+          std::launch::async,
+          [&solve, &context](const DecisionVariables& guess) -> Result {
+            detail::tls_multistart = &context;
+            detail::tls_multistart_answered = false;
+            struct Answer {
+              detail::MultistartContext& c;
+              ~Answer() {
+                // a start that never reached a device solve must not keep the
+                // others waiting at the group's start gate
+                if (c.group && !detail::tls_multistart_answered) {
+                  slpb_group_abandon(c.group);
+                }
+                detail::tls_multistart = nullptr;
+              }
+            } answer{context};
+            return solve(guess);
+          },
+          std::cref(initial_guesses[i])));
     }
     for (auto& future : futures) results.emplace_back(future.get());
+    if (context.group) slpb_group_destroy(context.group);
   }
   if (all_results) *all_results = results;
 

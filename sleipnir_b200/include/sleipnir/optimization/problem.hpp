@@ -35,6 +35,7 @@
 #include "sleipnir/autodiff/variable_matrix.hpp"
 #include "sleipnir/optimization/solver/device_problem.hpp"
 #include "sleipnir/optimization/solver/exit_status.hpp"
+#include "sleipnir/optimization/multistart.hpp"
 #include "sleipnir/optimization/solver/interior_point.hpp"
 #include "sleipnir/optimization/solver/iteration_info.hpp"
 #include "sleipnir/optimization/solver/options.hpp"
@@ -325,6 +326,13 @@ class Problem {
                                           : dev_options.permutation.data(),
                                       &sym));
     m_symbolic = sym;
+    // one start of a slp::multistart: batch the linear algebra with the other
+    // starts (refused — and then solved alone — if the pattern differs)
+    if (detail::tls_multistart != nullptr && detail::tls_multistart->group &&
+        !detail::tls_multistart_answered && dev_options.world == 1) {
+      detail::tls_multistart_answered = true;
+      (void)slpb_group_join(detail::tls_multistart->group, dev);
+    }
     lap(5);
 
     // Interior-point method (:663-668; overload 1, interior_point.hpp:74-86)

@@ -671,6 +671,13 @@ ExitStatus interior_point(
       };
       // the SQP variant enters with μ = tolerance/10
       // (feasibility_restoration.hpp:121)
+      // restoration runs on another handle for many iterations: the other
+      // members of a batching group must not wait for this one meanwhile
+      SLP_DEVICE_CALL(dev, slpb_group_pause(dev));
+      struct Resume {
+        slpb_solver* d;
+        ~Resume() { slpb_group_resume(d); }
+      } resume{dev};
       ExitStatus status = (*restoration)(
           kind == SolverKind::IPM ? mu : Scalar(options.tolerance) / 10.0,
           iterations, accept_test);
