@@ -191,47 +191,58 @@ SLPB_HD void ad_run_group(int tid, int nthreads, int count,
     const uint32_t* Bk = stream.acquire(blk);
     const uint32_t kind = Bk[0];
     const int n_items = static_cast<int>(Bk[1]);
+    // workers' private lists: {kind, n_items, n_contrib, W | off[W + 1] | pad}
+    const int Wb = static_cast<int>(Bk[3]);
+    const uint32_t* off = Bk + 4;
+    const uint32_t* body = Bk + 4 + ((Wb + 2) & ~1);
     if (kind == kBlockForward) {
-      // ---- one level of the forward value sweep ------------------------------
-      const FwdInstr* fwd = reinterpret_cast<const FwdInstr*>(Bk + 4);
-      for (int i = q; i < n_items; i += R) {
-        const FwdInstr in = fwd[i];
-        const double l = S[in.a * LC], r = S[in.b * LC];
-        double v;
-        if (in.op == SLPB_OP_MUL) {  // the common ops first
-          v = l * r;
-        } else if (in.op == SLPB_OP_ADD) {
-          v = l + r;
-        } else {
-          v = ad_op_value(in.op, l, r);
+      // ---- one super-level of the forward value sweep: every worker runs its
+      // list in order (it reads back its own results in program order) --------
+      const FwdInstr* fwd = reinterpret_cast<const FwdInstr*>(body);
+      for (int w = q; w < Wb; w += R) {
+        const int e = static_cast<int>(off[w + 1]);
+        for (int i = static_cast<int>(off[w]); i < e; ++i) {
+          const FwdInstr in = fwd[i];
+          const double l = S[in.a * LC], r = S[in.b * LC];
+          double v;
+          if (in.op == SLPB_OP_MUL) {  // the common ops first
+            v = l * r;
+          } else if (in.op == SLPB_OP_ADD) {
+            v = l + r;
+          } else {
+            v = ad_op_value(in.op, l, r);
+          }
+          S[in.dst * LC] = v;
         }
-        S[in.dst * LC] = v;
       }
     } else if (kind == kBlockReverse) {
-      // ---- one level of the reverse sweeps: each visit pulls from its
+      // ---- one super-level of the reverse sweeps: each visit pulls from its
       // parents' adjoints, in the row's parent order --------------------------
-      const Visit* visit = reinterpret_cast<const Visit*>(Bk + 4);
+      const Visit* visit = reinterpret_cast<const Visit*>(body);
       const Contrib* contrib =
-          reinterpret_cast<const Contrib*>(Bk + 4 + 2 * n_items);
-      for (int i = q; i < n_items; i += R) {
-        const Visit v = visit[i];
-        double a;
-        if (v.n_contrib == 0) {
-          a = static_cast<double>(v.seed);
-        } else {
-          a = 0.0;
-          const Contrib* ct = contrib + v.contrib_begin;
-          for (int k = 0; k < v.n_contrib; ++k) {
-            const Contrib ck = ct[k];
-            const double pa = S[ck.parent_adj * LC], lv = S[ck.l * LC];
-            if (ck.op == kOpLinear) {
-              a += pa * lv;  // adjoint × (±1 or the other factor): no decode
-            } else {
-              a += ad_op_grad(ck.op, ck.side, pa, lv, S[ck.r * LC]);
+          reinterpret_cast<const Contrib*>(body + 2 * n_items);
+      for (int w = q; w < Wb; w += R) {
+        const int e = static_cast<int>(off[w + 1]);
+        for (int i = static_cast<int>(off[w]); i < e; ++i) {
+          const Visit v = visit[i];
+          double a;
+          if (v.n_contrib == 0) {
+            a = static_cast<double>(v.seed);
+          } else {
+            a = 0.0;
+            const Contrib* ct = contrib + v.contrib_begin;
+            for (int k = 0; k < v.n_contrib; ++k) {
+              const Contrib ck = ct[k];
+              const double pa = S[ck.parent_adj * LC], lv = S[ck.l * LC];
+              if (ck.op == kOpLinear) {
+                a += pa * lv;  // adjoint × (±1 or the other factor): no decode
+              } else {
+                a += ad_op_grad(ck.op, ck.side, pa, lv, S[ck.r * LC]);
+              }
             }
           }
+          S[v.adj * LC] = a;
         }
-        S[v.adj * LC] = a;
       }
     } else {
       // ---- value outputs (slots read here may be recycled afterwards) --------

@@ -544,11 +544,145 @@ struct Compiler {
       for (int32_t i = 0; i < len; ++i) pos[sr.nodes[i]] = -1;
     }
     const int32_t n_visits = static_cast<int32_t>(visits.size());
+
+    // --- worker chains ---------------------------------------------------------
+    // A block of the instruction stream is not one dependency level but a
+    // SUPER-LEVEL: every worker (a row of LC threads, lane = cluster) runs a
+    // private list of items in order, and the thread block synchronises only
+    // between super-levels. A thread reads back what it wrote itself in program
+    // order, so an item whose newest operands were all produced by ONE worker
+    // in the current super-level joins that worker's list and needs no barrier;
+    // only an item that joins results of different workers waits for the next
+    // one. A direct-transcription stage (four RK4 evaluations of the dynamics,
+    // ~145 dependency levels) collapses to a few dozen barriers this way.
+    int32_t widest = 1;
+    for (const auto& lv : fwd_levels) widest = std::max<int32_t>(widest, lv.size());
+    {
+      std::vector<int32_t> cnt;
+      for (const auto& v : visits) {
+        if (v.rlevel >= static_cast<int32_t>(cnt.size())) cnt.resize(v.rlevel + 1, 0);
+        widest = std::max(widest, ++cnt[v.rlevel]);
+      }
+    }
+    int32_t n_workers = 1;
+    while (n_workers < 16 && n_workers < widest) n_workers <<= 1;
+    constexpr int32_t kChainCap = 24;  // weight a worker takes per super-level
+    struct Loads {
+      int32_t W;
+      std::vector<std::vector<int32_t>> load;  // [super-level][worker]
+      int32_t& at(int32_t sl, int32_t w) {
+        if (sl >= static_cast<int32_t>(load.size())) {
+          load.resize(sl + 1, std::vector<int32_t>(W, 0));
+        }
+        return load[sl][w];
+      }
+      int32_t lightest(int32_t sl) {
+        at(sl, 0);
+        int32_t best = 0;
+        for (int32_t w = 1; w < W; ++w) {
+          if (load[sl][w] < load[sl][best]) best = w;
+        }
+        return best;
+      }
+    };
+    // dep = (super-level, worker) of every producer this item reads; returns
+    // where the item goes
+    auto place = [&](Loads& L, const std::pair<int32_t, int32_t>* deps, int n_deps,
+                     int32_t first_sl, int32_t weight) {
+      int32_t s_max = -1;
+      for (int k = 0; k < n_deps; ++k) s_max = std::max(s_max, deps[k].first);
+      int32_t sl, w;
+      if (s_max < first_sl) {
+        sl = first_sl;  // reads only what was there before the sweep began
+        w = L.lightest(sl);
+      } else {
+        int32_t same = -2;  // −2: none yet, −1: several workers
+        for (int k = 0; k < n_deps; ++k) {
+          if (deps[k].first != s_max) continue;
+          same = same == -2 ? deps[k].second
+                            : (same == deps[k].second ? same : -1);
+        }
+        if (same >= 0 && L.at(s_max, same) + weight <= kChainCap) {
+          sl = s_max;  // continues that worker's chain: no barrier
+          w = same;
+        } else {
+          sl = s_max + 1;
+          w = same >= 0 ? same : -1;
+          if (w < 0 || L.at(sl, w) + weight > kChainCap) {
+            // prefer a producer's worker (its chain may continue), else the
+            // lightest one
+            w = -1;
+            for (int k = 0; k < n_deps; ++k) {
+              if (deps[k].first != s_max) continue;
+              if (w < 0 || L.at(sl, deps[k].second) < L.at(sl, w)) w = deps[k].second;
+            }
+            if (L.at(sl, w) + weight > kChainCap) w = L.lightest(sl);
+          }
+        }
+      }
+      L.at(sl, w) += weight;
+      return std::pair<int32_t, int32_t>{sl, w};
+    };
+    std::vector<int32_t> fwd_worker(n_slots, -1);
+    {
+      Loads L{n_workers, {}};
+      std::vector<int32_t> sl_of(n_slots, 0);  // 0: leaf / constant
+      for (int32_t nd : sorted_ids) {
+        if (!is_interior(nd)) continue;
+        const int32_t slot = local[nd];
+        std::pair<int32_t, int32_t> deps[2];
+        int n_deps = 0;
+        const int32_t a = local[tape.lhs[nd]];
+        if (sl_of[a] > 0) deps[n_deps++] = {sl_of[a], fwd_worker[a]};
+        if (tape.rhs[nd] >= 0) {
+          const int32_t b = local[tape.rhs[nd]];
+          if (sl_of[b] > 0) deps[n_deps++] = {sl_of[b], fwd_worker[b]};
+        }
+        const auto [sl, w] = place(L, deps, n_deps, 1, 1);
+        sl_of[slot] = sl;
+        fwd_worker[slot] = w;
+      }
+      max_level = 0;
+      for (int32_t slot = 0; slot < n_slots; ++slot) {
+        level[slot] = sl_of[slot];
+        max_level = std::max(max_level, sl_of[slot]);
+      }
+      fwd_levels.assign(max_level, {});
+      for (int32_t nd : sorted_ids) {  // topological order inside every list
+        if (is_interior(nd)) fwd_levels[level[local[nd]] - 1].push_back(local[nd]);
+      }
+      for (auto& lv : fwd_levels) {
+        std::stable_sort(lv.begin(), lv.end(), [&](int32_t x, int32_t y) {
+          return fwd_worker[x] < fwd_worker[y];
+        });
+      }
+    }
+    std::vector<int32_t> rev_worker(n_visits, -1);
+    {
+      Loads L{n_workers, {}};
+      std::vector<std::pair<int32_t, int32_t>> deps;
+      for (int32_t i = 0; i < n_visits; ++i) {  // parents come first in visit order
+        deps.clear();
+        for (const ContribTmp& c : visits[i].contribs) {
+          deps.push_back({visits[c.parent_visit].rlevel, rev_worker[c.parent_visit]});
+        }
+        const int32_t weight = 1 + static_cast<int32_t>(visits[i].contribs.size());
+        const auto [sl, w] =
+            place(L, deps.data(), static_cast<int>(deps.size()), 0, weight);
+        visits[i].rlevel = sl;
+        rev_worker[i] = w;
+      }
+    }
     int32_t max_rlevel = -1;
     for (auto& v : visits) max_rlevel = std::max(max_rlevel, v.rlevel);
     std::vector<std::vector<int32_t>> rev_levels(max_rlevel + 1);
     for (int32_t i = 0; i < n_visits; ++i) {
       rev_levels[visits[i].rlevel].push_back(i);
+    }
+    for (auto& lv : rev_levels) {
+      std::stable_sort(lv.begin(), lv.end(), [&](int32_t x, int32_t y) {
+        return rev_worker[x] < rev_worker[y];
+      });
     }
 
     // --- physical slot allocation (liveness over the level schedule) ---------
@@ -560,67 +694,138 @@ struct Compiler {
     auto t_rev = [&](int32_t rl) { return Lf + 2 + rl; };
     const int32_t n_synth = uses_unit_consts ? 2 : 0;
     const int32_t n_val = n_slots + n_synth;  // value-like items
-    std::vector<int32_t> v_last(n_val), a_last(n_visits);
     level.resize(n_val, 0);  // synthetic constants are loaded at time 0
-    for (int32_t slot = 0; slot < n_val; ++slot) v_last[slot] = level[slot];
+    // item id: value slot s → s ; visit i → n_val + i. For every item: when it
+    // is read last, and — if all its readers at that time sit on ONE worker —
+    // by which worker and at which position of that worker's list.
+    const int32_t n_items = n_val + n_visits;
+    std::vector<int32_t> last_t(n_items, 0), last_w(n_items, -1), last_pos(n_items, 0);
+    std::vector<int32_t> fwd_pos(n_slots, 0), rev_pos(n_visits, 0);
+    for (auto& lv : fwd_levels) {
+      std::vector<int32_t> next(n_workers, 0);
+      for (int32_t slot : lv) fwd_pos[slot] = next[fwd_worker[slot]]++;
+    }
+    for (auto& lv : rev_levels) {
+      std::vector<int32_t> next(n_workers, 0);
+      for (int32_t vi : lv) rev_pos[vi] = next[rev_worker[vi]]++;
+    }
+    auto note = [&](int32_t item, int32_t t, int32_t w, int32_t pos) {
+      if (t > last_t[item]) {
+        last_t[item] = t;
+        last_w[item] = w;
+        last_pos[item] = pos;
+      } else if (t == last_t[item]) {
+        if (last_w[item] != w) {
+          last_w[item] = -1;
+        } else {
+          last_pos[item] = std::max(last_pos[item], pos);
+        }
+      }
+    };
+    for (int32_t slot = 0; slot < n_slots; ++slot) {  // an item "reads" itself
+      if (is_interior(cl_nodes[slot])) {
+        note(slot, level[slot], fwd_worker[slot], fwd_pos[slot]);
+      }
+    }
+    for (int32_t i = 0; i < n_visits; ++i) {
+      note(n_val + i, t_rev(visits[i].rlevel), rev_worker[i], rev_pos[i]);
+    }
     for (int32_t slot = 0; slot < n_slots; ++slot) {
       const int32_t nd = cl_nodes[slot];
       if (!is_interior(nd)) continue;
-      const int32_t a = local[tape.lhs[nd]];
-      v_last[a] = std::max(v_last[a], level[slot]);
+      note(local[tape.lhs[nd]], level[slot], fwd_worker[slot], fwd_pos[slot]);
       if (tape.rhs[nd] >= 0) {
-        const int32_t b = local[tape.rhs[nd]];
-        v_last[b] = std::max(v_last[b], level[slot]);
+        note(local[tape.rhs[nd]], level[slot], fwd_worker[slot], fwd_pos[slot]);
       }
     }
-    for (int32_t slot : val_out_slots) {
-      v_last[slot] = std::max(v_last[slot], t_valout);
-    }
-    for (int32_t i = 0; i < n_visits; ++i) {
-      const int32_t t = t_rev(visits[i].rlevel);
-      a_last[i] = t;
-    }
+    for (int32_t slot : val_out_slots) note(slot, t_valout, -1, 0);
     for (int32_t i = 0; i < n_visits; ++i) {
       const int32_t t = t_rev(visits[i].rlevel);
       for (const ContribTmp& c : visits[i].contribs) {
-        a_last[c.parent_visit] = std::max(a_last[c.parent_visit], t);
-        if (c.l >= 0) v_last[c.l] = std::max(v_last[c.l], t);
-        if (c.r >= 0) v_last[c.r] = std::max(v_last[c.r], t);
+        note(n_val + c.parent_visit, t, rev_worker[i], rev_pos[i]);
+        if (c.l >= 0) note(c.l, t, rev_worker[i], rev_pos[i]);
+        if (c.r >= 0) note(c.r, t, rev_worker[i], rev_pos[i]);
       }
     }
-    for (int32_t vi : adj_out_visit) a_last[vi] = t_end;
-    // items defined at each time, in a fixed order (values by slot, adjoints by
-    // visit index); items released after each time
-    std::vector<std::vector<int32_t>> defs(t_end + 1), frees(t_end + 1);
-    // item id: value slot s → s ; visit i → n_slots + i
-    for (int32_t slot = 0; slot < n_val; ++slot) {
-      defs[level[slot]].push_back(slot);
-      frees[v_last[slot]].push_back(slot);
-    }
-    for (int32_t i = 0; i < n_visits; ++i) {
-      defs[t_rev(visits[i].rlevel)].push_back(n_val + i);
-      frees[a_last[i]].push_back(n_val + i);
-    }
-    std::vector<int32_t> phys(n_val + n_visits, -1);
-    std::vector<int32_t> free_list;  // min-heap
+    for (int32_t vi : adj_out_visit) note(n_val + vi, t_end, -1, 0);
+
+    // Allocation in execution order. A slot whose last reader runs at time t
+    // is reusable from t + 1 on (other workers may still be reading it during
+    // t) — unless everything that reads it at time t belongs to one worker:
+    // then that worker may take it again right after its last read (program
+    // order protects it), which is what keeps the temporaries of a long
+    // private chain from piling up.
+    std::vector<int32_t> phys(n_items, -1);
+    std::vector<int32_t> free_list;  // min-heap of slots any worker may take
     int32_t n_scratch = 0;
     auto heap_cmp = std::greater<int32_t>{};
-    for (int32_t t = 0; t <= t_end; ++t) {
-      for (int32_t item : defs[t]) {
-        if (free_list.empty()) {
-          phys[item] = n_scratch++;
-        } else {
-          std::pop_heap(free_list.begin(), free_list.end(), heap_cmp);
-          phys[item] = free_list.back();
-          free_list.pop_back();
+    auto heap_push = [&](std::vector<int32_t>& h, int32_t v) {
+      h.push_back(v);
+      std::push_heap(h.begin(), h.end(), heap_cmp);
+    };
+    auto heap_pop = [&](std::vector<int32_t>& h) {
+      std::pop_heap(h.begin(), h.end(), heap_cmp);
+      const int32_t v = h.back();
+      h.pop_back();
+      return v;
+    };
+    std::vector<std::vector<int32_t>> shared_frees(t_end + 1);
+    for (int32_t item = 0; item < n_items; ++item) {
+      if (last_w[item] < 0) shared_frees[last_t[item]].push_back(item);
+    }
+    // time 0: leaves, constants, synthetic constants
+    for (int32_t slot = 0; slot < n_val; ++slot) {
+      if (slot >= n_slots || !is_interior(cl_nodes[slot])) phys[slot] = n_scratch++;
+    }
+    std::vector<int32_t> pending, local_free, operands;
+    auto run_lists = [&](int32_t t, const std::vector<int32_t>& list, bool reverse) {
+      // `list` is grouped by worker, each group in execution order
+      size_t k = 0;
+      while (k < list.size()) {
+        const int32_t w = reverse ? rev_worker[list[k]] : fwd_worker[list[k]];
+        local_free.clear();
+        int32_t pos = 0;
+        for (; k < list.size() &&
+               (reverse ? rev_worker[list[k]] : fwd_worker[list[k]]) == w;
+             ++k, ++pos) {
+          const int32_t x = list[k];
+          const int32_t item = reverse ? n_val + x : x;
+          phys[item] = !local_free.empty() ? heap_pop(local_free)
+                       : !free_list.empty() ? heap_pop(free_list)
+                                            : n_scratch++;
+          operands.clear();
+          operands.push_back(item);
+          if (reverse) {
+            for (const ContribTmp& c : visits[x].contribs) {
+              operands.push_back(n_val + c.parent_visit);
+              if (c.l >= 0) operands.push_back(c.l);
+              if (c.r >= 0) operands.push_back(c.r);
+            }
+          } else {
+            const int32_t nd = cl_nodes[x];
+            operands.push_back(local[tape.lhs[nd]]);
+            if (tape.rhs[nd] >= 0) operands.push_back(local[tape.rhs[nd]]);
+          }
+          std::sort(operands.begin(), operands.end());
+          operands.erase(std::unique(operands.begin(), operands.end()), operands.end());
+          for (int32_t o : operands) {
+            if (last_t[o] == t && last_w[o] == w && last_pos[o] == pos) {
+              heap_push(local_free, phys[o]);
+            }
+          }
         }
+        pending.insert(pending.end(), local_free.begin(), local_free.end());
       }
-      // a slot whose last reader runs at time t is reusable from t+1 on (other
-      // lanes may still be reading it during t)
-      for (int32_t item : frees[t]) {
-        free_list.push_back(phys[item]);
-        std::push_heap(free_list.begin(), free_list.end(), heap_cmp);
+    };
+    for (int32_t t = 0; t <= t_end; ++t) {
+      pending.clear();
+      if (t >= 1 && t <= Lf) {
+        run_lists(t, fwd_levels[t - 1], false);
+      } else if (t >= Lf + 2 && t < t_end) {
+        run_lists(t, rev_levels[t - Lf - 2], true);
       }
+      for (int32_t item : shared_frees[t]) pending.push_back(phys[item]);
+      for (int32_t v : pending) heap_push(free_list, v);
     }
     if (n_scratch > 65535) {
       error = "an expression cluster needs more than 65535 scratch slots; the "
@@ -685,13 +890,24 @@ struct Compiler {
     // level blocks, each 16-byte aligned: {kind, n_items, n_contrib, 0} + payload
     int32_t max_width = 1, blk = 0;
     uint32_t max_block_words = 4, n_instr = 0, n_contrib_total = 0;
-    auto begin_block = [&](uint32_t kind, uint32_t items, uint32_t contribs) {
+    // {kind, n_items, n_contrib, W} then, for W > 0, W + 1 item offsets (one
+    // list per worker) padded to an even number of words
+    auto begin_block = [&](uint32_t kind, uint32_t items, uint32_t contribs,
+                           const std::vector<int32_t>* list = nullptr,
+                           const std::vector<int32_t>* worker_of = nullptr) {
       align4();
       prog[table_at + blk] = static_cast<uint32_t>(prog.size());
       prog.push_back(kind);
       prog.push_back(items);
       prog.push_back(contribs);
-      prog.push_back(0);
+      prog.push_back(list ? static_cast<uint32_t>(n_workers) : 0u);
+      if (list) {
+        std::vector<uint32_t> off(n_workers + 1, 0);
+        for (int32_t x : *list) ++off[(*worker_of)[x] + 1];
+        for (int32_t w = 0; w < n_workers; ++w) off[w + 1] += off[w];
+        prog.insert(prog.end(), off.begin(), off.end());
+        if ((n_workers + 1) & 1) prog.push_back(0);
+      }
     };
     auto end_block = [&] {
       align4();
@@ -701,7 +917,8 @@ struct Compiler {
       ++blk;
     };
     for (auto& lv : fwd_levels) {
-      begin_block(kBlockForward, static_cast<uint32_t>(lv.size()), 0);
+      begin_block(kBlockForward, static_cast<uint32_t>(lv.size()), 0, &lv,
+                  &fwd_worker);
       max_width = std::max<int32_t>(max_width, lv.size());
       for (int32_t slot : lv) {
         const int32_t nd = cl_nodes[slot];
@@ -722,7 +939,8 @@ struct Compiler {
     for (auto& lv : rev_levels) {
       uint32_t nc = 0;
       for (int32_t vi : lv) nc += static_cast<uint32_t>(visits[vi].contribs.size());
-      begin_block(kBlockReverse, static_cast<uint32_t>(lv.size()), nc);
+      begin_block(kBlockReverse, static_cast<uint32_t>(lv.size()), nc, &lv,
+                  &rev_worker);
       max_width = std::max<int32_t>(max_width, lv.size());
       uint32_t crun = 0;
       for (int32_t vi : lv) {
@@ -773,6 +991,18 @@ struct Compiler {
     prog[13] = static_cast<uint32_t>(rev_levels.size());
     prog[14] = n_instr;
     prog[17] = static_cast<uint32_t>(max_width);
+    prog[21] = static_cast<uint32_t>(n_workers);
+    {
+      const uint32_t stream_words =
+          prog[table_at + n_blocks] - prog[table_at];
+      const uint32_t with_stream =
+          static_cast<uint32_t>(n_scratch) * 32u * 8u + prog[5] * 4u +
+          stream_words * 4u + 64u;
+      const bool resident =
+          stream_words * 4u <= kAdResidentBytes && with_stream <= kAdHalfSmBytes;
+      prog[22] = resident ? stream_words : kAdStages * max_block_words;
+      prog[23] = resident ? 1u : 0u;
+    }
     prog[18] = n_contrib_total;
     prog[19] = static_cast<uint32_t>(n_visits);
     prog[20] = static_cast<uint32_t>(n_synth);  // trailing ±1 constants
@@ -920,7 +1150,7 @@ struct Compiler {
         ps.blob.insert(ps.blob.end(), prog.begin(), prog.end());
         const int32_t smem = static_cast<int32_t>(prog[0]) * 8;
         ps.prog_smem.push_back(smem);
-        ps.prog_width.push_back(static_cast<int32_t>(prog[17]));
+        ps.prog_width.push_back(static_cast<int32_t>(prog[21]));
         ps.max_smem = std::max(ps.max_smem, smem);
         by_hash.emplace(key, pid);
       }
@@ -980,7 +1210,7 @@ bool build_task_plan(ProgramSet& ps, int32_t smem_budget, std::string& error) {
   std::vector<int32_t> lanes(n_prog), threads(n_prog);
   auto task_bytes = [&](int32_t p, int32_t L) {
     const uint32_t* P = ps.blob.data() + ps.prog_offset[p];
-    return ad_smem_layout(P[0], P[5], P[11], L).total;
+    return ad_smem_layout(P[0], P[5], P[22], L).total;
   };
   for (int32_t p = 0; p < n_prog; ++p) {
     if (task_bytes(p, 1) > smem_budget) {
@@ -994,11 +1224,8 @@ bool build_task_plan(ProgramSet& ps, int32_t smem_budget, std::string& error) {
     // no wider than the clusters available
     while (L > 1 && L / 2 >= static_cast<int32_t>(by_prog[p].size())) L >>= 1;
     lanes[p] = L;
-    // enough threads for the widest level, between one warp and 16
-    const int64_t want = int64_t(ps.prog_width[p]) * L;
-    int32_t T = 32;
-    while (T < 512 && T < want) T <<= 1;
-    threads[p] = T;
+    // one row of L threads per worker of the program's schedule (≤ 16 × 32)
+    threads[p] = std::max<int32_t>(1, ps.prog_width[p]) * L;
   }
   // launches: one per block size, biggest first; inside, heavy programs first
   std::vector<int32_t> order(n_prog);

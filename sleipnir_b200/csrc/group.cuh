@@ -47,6 +47,10 @@ struct slpb_group {
   uint64_t round = 0;
   int64_t rounds_run = 0, requests_served = 0;
   std::vector<double> cur_delta, cur_gamma;  // per batch instance
+  // where the wall time of the rounds goes (host clock, seconds)
+  double t_scatter = 0, t_factor = 0, t_solve = 0, t_gather = 0, t_quorum = 0;
+  int64_t n_factor_rounds = 0, n_solve_rounds = 0, n_factor_req = 0, n_solve_req = 0;
+  std::chrono::steady_clock::time_point last_round_end = std::chrono::steady_clock::now();
   std::string error;
 };
 
@@ -72,7 +76,19 @@ inline void group_run_round(slpb_group* G) {
     }
   };
   cudaSetDevice(G->device);
+  using clk = std::chrono::steady_clock;
+  auto secs = [](clk::time_point a, clk::time_point b) {
+    return std::chrono::duration<double>(b - a).count();
+  };
+  const auto t_begin = clk::now();
+  G->t_quorum += secs(G->last_round_end, t_begin);
+  struct Stamp {
+    slpb_group* G;
+    ~Stamp() { G->last_round_end = clk::now(); }
+  } stamp{G};
   if (any_factor) {
+    ++G->n_factor_rounds;
+    const auto t0 = clk::now();
     // A launch factors EVERY slot: the slots without a request keep the
     // regularisation of their last one, so that their factor — which their
     // owner may still be about to solve with — is reproduced, not clobbered.
@@ -95,7 +111,10 @@ inline void group_run_round(slpb_group* G) {
       }
     }
     std::vector<slpb_factor_info> info(B->batch);
+    const auto t1 = clk::now();
+    G->t_scatter += secs(t0, t1);
     const int rc = slpb_batch_factor(B, d.data(), g.data(), info.data());
+    G->t_factor += secs(t1, clk::now());
     if (rc != SLPB_OK) {
       G->error = B->error;
       fail_all(rc);
@@ -104,12 +123,15 @@ inline void group_run_round(slpb_group* G) {
     for (size_t i = 0; i < G->members.size(); ++i) {
       auto& m = G->members[i];
       if (m.req.kind != 1) continue;
+      G->n_factor_req += m.req.nv;
       for (int v = 0; v < m.req.nv; ++v) m.req.info[v] = info[2 * i + v];
       m.req.rc = SLPB_OK;
       m.req.kind = 0;  // served: the answer stays in the slot for its owner
     }
   }
   if (any_solve) {
+    ++G->n_solve_rounds;
+    const auto t0 = clk::now();
     for (size_t i = 0; i < G->members.size(); ++i) {
       auto& m = G->members[i];
       if (m.req.kind != 2) continue;
@@ -118,7 +140,11 @@ inline void group_run_round(slpb_group* G) {
       k_batch_scatter<<<blocks_for(B->dim, 256), 256, 0, B->stream>>>(
           m.S->rhs.p, B->dim, B->rhs.p + int64_t(gidx) * B->dim * 32 + l);
     }
+    const auto t1 = clk::now();
+    G->t_scatter += secs(t0, t1);
     const int rc = slpb_batch_solve(B);
+    const auto t2 = clk::now();
+    G->t_solve += secs(t1, t2);
     if (rc != SLPB_OK) {
       G->error = B->error;
       fail_all(rc);
@@ -134,8 +160,10 @@ inline void group_run_round(slpb_group* G) {
       m.req.rc = SLPB_OK;
     }
     const bool ok = cudaStreamSynchronize(B->stream) == cudaSuccess;
+    G->t_gather += secs(t2, clk::now());
     for (auto& m : G->members) {
       if (m.req.kind != 2) continue;
+      ++G->n_solve_req;
       if (!ok) m.req.rc = SLPB_ERR_CUDA;
       m.req.kind = 0;
     }
@@ -284,6 +312,15 @@ int slpb_group_create(int device, int32_t expected_members, slpb_group** out) {
 
 void slpb_group_destroy(slpb_group* G) {
   if (!G) return;
+  if (std::getenv("SLPB_GROUP_TIMING")) {
+    std::fprintf(stderr,
+                 "[slpb group] %d members: %lld factor rounds (%lld requests), "
+                 "%lld solve rounds (%lld requests); host seconds: scatter %.3f "
+                 "factor %.3f solve %.3f gather %.3f, waiting for the quorum %.3f\n",
+                 G->joined, (long long)G->n_factor_rounds, (long long)G->n_factor_req,
+                 (long long)G->n_solve_rounds, (long long)G->n_solve_req,
+                 G->t_scatter, G->t_factor, G->t_solve, G->t_gather, G->t_quorum);
+  }
   if (G->batch) slpb_batch_destroy(G->batch);
   delete G;
 }

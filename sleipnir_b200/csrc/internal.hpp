@@ -77,10 +77,15 @@ struct Pattern {
 //   [17] max_width      widest level (forward or reverse)
 //   [18] n_contrib [19] n_visits (stats)
 //   [20] n_synth     trailing constants +1, −1 appended by the compiler
-//   [21..23] reserved
-//   tables …, then the INSTRUCTION STREAM: one 16-byte-aligned block per level,
-//   in execution order, {kind, n_items, n_contrib, 0} followed by
-//     kBlockForward:  FwdInstr[n_items]
+//   [21] n_workers   rows of lanes that run private item lists (≤ 16)
+//   [22] ring_words  words of shared memory the instruction stream needs
+//   [23] resident    1: the whole stream is copied in once (it is small);
+//                    0: kAdStages blocks travel through a ring
+//   tables …, then the INSTRUCTION STREAM: one 16-byte-aligned block per
+//   SUPER-LEVEL, in execution order (the thread block synchronises between
+//   blocks only): {kind, n_items, n_contrib, W}, then for W > 0 the W + 1 item
+//   offsets of the workers' private lists (padded to an even word count), then
+//     kBlockForward:  FwdInstr[n_items]      worker w runs [off[w], off[w+1]) in order
 //     kBlockValueOut: nothing (value outputs are stored at this point)
 //     kBlockReverse:  Visit[n_items], Contrib[n_contrib]
 //   The device streams these blocks through a shared-memory ring with TMA bulk
@@ -98,7 +103,12 @@ constexpr uint32_t kBlockForward = 0, kBlockReverse = 1, kBlockValueOut = 2;
 /// Contrib.op of a contribution that is adjoint × (value in slot l): the
 /// partials of +, −, unary − (multiplier ±1) and × (the other operand).
 constexpr uint8_t kOpLinear = 255;
-constexpr int kAdStages = 4;  // ring-buffer stages of the instruction stream
+constexpr int kAdStages = 3;  // ring-buffer stages of the instruction stream
+/// An instruction stream stays resident in shared memory when it is at most
+/// this big AND a full task (32 lanes of scratch + stream) still leaves room
+/// for a second task on the SM; otherwise it travels through the ring.
+constexpr uint32_t kAdResidentBytes = 64 * 1024;
+constexpr uint32_t kAdHalfSmBytes = 112 * 1024;
 
 /// Shared-memory layout of one task (bytes from the start of dynamic shared
 /// memory): scratch | header+tables | instruction ring | mbarriers.
@@ -109,13 +119,13 @@ struct AdSmemLayout {
 __host__ __device__
 #endif
 inline AdSmemLayout ad_smem_layout(uint32_t n_scratch, uint32_t prologue_words,
-                                   uint32_t max_block_words, int lanes) {
+                                   uint32_t ring_words, int lanes) {
   AdSmemLayout L;
   const uint32_t scratch = (n_scratch * uint32_t(lanes) * 8u + 15u) & ~15u;
   L.off_prologue = static_cast<int32_t>(scratch);
   L.off_ring =
       static_cast<int32_t>((scratch + prologue_words * 4u + 15u) & ~15u);
-  L.off_bars = L.off_ring + kAdStages * static_cast<int32_t>(max_block_words) * 4;
+  L.off_bars = L.off_ring + static_cast<int32_t>(ring_words) * 4;
   L.total = L.off_bars + kAdStages * 8;
   return L;
 }
@@ -140,7 +150,7 @@ struct ProgramSet {
   std::vector<uint32_t> blob;          // all programs back to back
   std::vector<int64_t> prog_offset;    // word offset of each program
   std::vector<int32_t> prog_smem;      // bytes of shared memory per cluster
-  std::vector<int32_t> prog_width;     // widest level
+  std::vector<int32_t> prog_width;     // workers of the program's schedule
   // one entry per cluster
   std::vector<int32_t> cluster_prog;
   std::vector<int64_t> cluster_bind;   // word offset into `bindings`

@@ -348,20 +348,42 @@ struct TmaStream {
   uint64_t* bars;
   int n_blocks, stage_words;
   bool issuer;
+  bool resident;           // the whole stream sits in `ring`, copied once
   __device__ __forceinline__ void issue(int b) const {
     const int st = b % kAdStages;
     const uint32_t bytes = (table[b + 1] - table[b]) * 4u;
     mbar_expect_tx(&bars[st], bytes);
     tma_bulk_g2s(ring + st * stage_words, Pg + table[b], bytes, &bars[st]);
   }
+  /// Called by the issuing thread once, before the first acquire.
+  __device__ __forceinline__ void start() const {
+    if (resident) {
+      // small programs (a direct-transcription stage is ≈30 KB): ONE phase of
+      // bulk copies brings every block in; nothing is waited for afterwards
+      const uint32_t total = (table[n_blocks] - table[0]) * 4u;
+      mbar_expect_tx(&bars[0], total);
+      for (uint32_t done = 0; done < total; done += 32768u) {
+        const uint32_t bytes = min(32768u, total - done);
+        tma_bulk_g2s(reinterpret_cast<unsigned char*>(ring) + done,
+                     reinterpret_cast<const unsigned char*>(Pg + table[0]) + done,
+                     bytes, &bars[0]);
+      }
+    } else {
+      for (int b = 0; b < kAdStages && b < n_blocks; ++b) issue(b);
+    }
+  }
   __device__ __forceinline__ const uint32_t* acquire(int b) const {
+    if (resident) {
+      mbar_wait(&bars[0], 0);
+      return ring + (table[b] - table[0]);
+    }
     const int st = b % kAdStages;
     mbar_wait(&bars[st], (b / kAdStages) & 1);
     return ring + st * stage_words;
   }
   /// Called by every thread after the level barrier of block b.
   __device__ __forceinline__ void release(int b) const {
-    if (issuer && b + kAdStages < n_blocks) issue(b + kAdStages);
+    if (!resident && issuer && b + kAdStages < n_blocks) issue(b + kAdStages);
   }
 };
 
@@ -385,7 +407,7 @@ k_ad_sweep(AdTasks A, int first_task, const double* __restrict__ leaf,
   const int tid = threadIdx.x, nt = blockDim.x;
   const uint32_t n_scratch = __ldg(P + 0), pro_words = __ldg(P + 5);
   const uint32_t stage_words = __ldg(P + 11);
-  const AdSmemLayout lay = ad_smem_layout(n_scratch, pro_words, stage_words, lanes);
+  const AdSmemLayout lay = ad_smem_layout(n_scratch, pro_words, __ldg(P + 22), lanes);
   double* scratch = reinterpret_cast<double*>(smem_raw);
   uint32_t* H = reinterpret_cast<uint32_t*>(smem_raw + lay.off_prologue);
   uint32_t* ring = reinterpret_cast<uint32_t*>(smem_raw + lay.off_ring);
@@ -402,10 +424,8 @@ k_ad_sweep(AdTasks A, int first_task, const double* __restrict__ leaf,
   }
   __syncthreads();
   TmaStream stream{P, H + H[10], ring, bars, static_cast<int>(H[4]),
-                   static_cast<int>(stage_words), tid == 0};
-  if (tid == 0) {
-    for (int b = 0; b < kAdStages && b < stream.n_blocks; ++b) stream.issue(b);
-  }
+                   static_cast<int>(stage_words), tid == 0, H[23] != 0};
+  if (tid == 0) stream.start();
   const BlockSync sync{};
   switch (lanes) {
     case 32: ad_run_group<32>(tid, nt, count, H, stream, B, leaf, stage, scratch, sync); break;
