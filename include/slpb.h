@@ -182,6 +182,26 @@ int slpb_set_scaling(slpb_solver* s, double d_f, const double* d_ce,
  * feasibility_restoration.hpp:485-495). */
 int slpb_set_ignore_constraint_hessian(slpb_solver* s, int ignore);
 
+/* Arithmetic of the Schur-complement updates of the LDLᵀ factorisation.
+ * REFERENCE (default): W(i,j) -= l_ik * w_jk with the product and the
+ *   difference rounded separately, as Eigen::SimplicialLDLT does in the
+ *   reference's x86-64 build (sparse_regularized_ldlt.hpp:74,105): whole solves
+ *   follow the reference's regularisation decisions.
+ * TENSOR: every term is one fused multiply-add and the rank-4 updates of dense
+ *   frontal matrices of order >= 16 run on the FP64 tensor cores (BASELINE
+ *   config 3; replaces the dense kernels behind
+ *   solver/util/dense_regularized_ldlt.hpp:59-136). One rounding per term away
+ *   from the reference; structurally singular pivots no longer cancel to an
+ *   exact zero, so the iteration path of a whole solve may differ.
+ * May be changed between factorisations; batches and groups created from a
+ * solver inherit its mode. The environment variable SLPB_FACTOR_ARITH=tensor
+ * makes TENSOR the initial mode of every new solver. */
+enum slpb_factor_arithmetic {
+  SLPB_ARITH_REFERENCE = 0,
+  SLPB_ARITH_TENSOR = 1
+};
+int slpb_set_factor_arithmetic(slpb_solver* s, int mode);
+
 enum slpb_ordering {
   SLPB_ORDER_NESTED_DISSECTION = 0, /* level-set bisection: log-depth tree     */
   SLPB_ORDER_AMD = 1,               /* approximate minimum degree (Eigen-like) */

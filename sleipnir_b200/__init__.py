@@ -32,6 +32,8 @@ EXIT_STATUS = {
 }
 
 ORDER_NESTED_DISSECTION, ORDER_AMD, ORDER_NATURAL, ORDER_CUSTOM = 0, 1, 2, 3
+# slpb_factor_arithmetic (include/slpb.h)
+ARITH_REFERENCE, ARITH_TENSOR = 0, 1
 
 # enum slpb_output / slpb_array (include/slpb.h)
 OUT_F, OUT_G, OUT_H_F, OUT_H_C, OUT_C_E, OUT_A_E, OUT_C_I, OUT_A_I = range(8)
@@ -106,7 +108,8 @@ ABI_SYMBOLS = [
     "slpb_create", "slpb_destroy", "slpb_last_error", "slpb_comm_unique_id",
     "slpb_comm_init", "slpb_comm_agree", "slpb_upload_tape",
     "slpb_upload_rows", "slpb_finalize", "slpb_set_scaling",
-    "slpb_set_ignore_constraint_hessian", "slpb_analyze",
+    "slpb_set_ignore_constraint_hessian", "slpb_set_factor_arithmetic",
+    "slpb_analyze",
     "slpb_get_permutation", "slpb_set_iterate", "slpb_get_iterate",
     "slpb_eval_current", "slpb_kkt_stats_current", "slpb_kkt_stats_trial",
     "slpb_factor", "slpb_factor_pair", "slpb_select_factor",
@@ -267,6 +270,7 @@ def host_lib() -> C.CDLL:
         L.slpbh_solver_kind.restype = C.c_int
         L.slpbh_solver_kind.argtypes = [vp]
         L.slpbh_set_flush_l2.argtypes = [vp, C.c_int]
+        L.slpbh_set_factor_arithmetic.argtypes = [vp, C.c_int]
         L.slpbh_flush_seconds.restype = C.c_double
         L.slpbh_flush_seconds.argtypes = [vp]
         L.slpbh_phase_seconds.argtypes = [vp, _dp]
@@ -329,6 +333,12 @@ class DeviceSession:
         d_ci = np.ascontiguousarray(d_ci, dtype=np.float64)
         self._check(self.L.slpb_set_scaling(self.raw, d_f, _d(d_ce), _d(d_ci)),
                     "slpb_set_scaling")
+
+    def set_factor_arithmetic(self, mode):
+        """ARITH_REFERENCE (default) or ARITH_TENSOR (fused Schur updates, FP64
+        tensor cores on frontal matrices of order ≥ 16)."""
+        self._check(self.L.slpb_set_factor_arithmetic(self.raw, int(mode)),
+                    "slpb_set_factor_arithmetic")
 
     def analyze(self, ordering=ORDER_NESTED_DISSECTION, perm=None):
         st = SymbolicStats()
@@ -658,6 +668,11 @@ class Problem:
         last_x = np.zeros(max(self.n, 1))
         k = self.H.slpbh_callback_log(self.h, _d(out), 4096, _d(last_x))
         return out[:8 * min(k, 4096)].reshape(-1, 8), last_x[:self.n]
+
+    def set_factor_arithmetic(self, mode):
+        """DeviceOptions::factor_arithmetic of the following solve() calls
+        (ARITH_REFERENCE / ARITH_TENSOR; −1: the library default)."""
+        self.H.slpbh_set_factor_arithmetic(self.h, int(mode))
 
     def set_flush_l2(self, on=True):
         """Benchmark hygiene: evict the device L2 before every iteration of the

@@ -114,6 +114,13 @@ __device__ __forceinline__ double batch_div(double w, double d, double y) {
   return w / d;
 }
 
+/// One Schur-complement term in the two arithmetic modes of ldlt_core.hpp:
+/// c − RN(l·w) (reference) or fma(−l, w, c) (fused / tensor).
+template <bool kFused>
+__device__ __forceinline__ double schur_term(double c, double l, double w) {
+  return kFused ? __fma_rn(-l, w, c) : __dsub_rn(c, __dmul_rn(l, w));
+}
+
 /// One (front, group) task of the batched factorisation, run by the kBatchWarps
 /// warps of a thread block: every warp works on the same 32 instances (lane =
 /// instance) and takes the entries / rows / columns congruent to its index.
@@ -128,10 +135,11 @@ __device__ __forceinline__ double batch_div(double w, double d, double y) {
 /// lbuf and straight to the packed panel in global memory. Phase B (one
 /// barrier): the trailing columns, split over the warps, take all pivots of
 /// the block at once. Per entry the operations and their order are those of
-/// ldlt_factor_front: W(i,j) −= l_ik·w_jk for k ascending, l_ik = w_ik / d_k.
+/// ldlt_factor_front in the same arithmetic mode (kFused): W(i,j) −= l_ik·w_jk
+/// for k ascending, l_ik = w_ik / d_k.
 /// kShared: W and lbuf are shared memory (the compiler must see that to emit
 /// LDS/STS with 32-bit addresses instead of generic loads).
-template <bool kShared>
+template <bool kShared, bool kFused>
 __device__ __forceinline__ void batch_factor_front(
     int warp, int lane, const FrontMeta& fm, const BatchView& T, int g,
     const double* __restrict__ Kb, double delta, double gamma,
@@ -229,7 +237,9 @@ __device__ __forceinline__ void batch_factor_front(
           if (p < kb) {
             ls[p][q] = batch_div(a[p][q], dd[q], ry[q]);
 #pragma unroll
-            for (int q2 = q + 1; q2 <= p; ++q2) a[p][q2] -= ls[p][q] * a[q2][q];
+            for (int q2 = q + 1; q2 <= p; ++q2) {
+              a[p][q2] = schur_term<kFused>(a[p][q2], ls[p][q], a[q2][q]);
+            }
           }
         }
       }
@@ -269,8 +279,8 @@ __device__ __forceinline__ void batch_factor_front(
         if (q < kb) {
 #pragma unroll
           for (int q1 = 0; q1 < q; ++q1) {
-            w0[q] -= l0[q1] * a[q][q1];
-            w1[q] -= l1[q1] * a[q][q1];
+            w0[q] = schur_term<kFused>(w0[q], l0[q1], a[q][q1]);
+            w1[q] = schur_term<kFused>(w1[q], l1[q1], a[q][q1]);
           }
           l0[q] = batch_div(w0[q], dd[q], ry[q]);
           l1[q] = batch_div(w1[q], dd[q], ry[q]);
@@ -310,8 +320,8 @@ __device__ __forceinline__ void batch_factor_front(
           }
 #pragma unroll
           for (int q = 0; q < R; ++q) {
-            x0 -= m0[q] * wj[q];
-            x1 -= m1[q] * wj[q];
+            x0 = schur_term<kFused>(x0, m0[q], wj[q]);
+            x1 = schur_term<kFused>(x1, m1[q], wj[q]);
           }
           Wj[i * 32] = x0;
           Wj[(i + 1) * 32] = x1;
@@ -319,7 +329,9 @@ __device__ __forceinline__ void batch_factor_front(
         for (; i < F; ++i) {
           double x = Wj[i * 32];
 #pragma unroll
-          for (int q = 0; q < R; ++q) x -= Ll[(q * F + i) * 32] * wj[q];
+          for (int q = 0; q < R; ++q) {
+            x = schur_term<kFused>(x, Ll[(q * F + i) * 32], wj[q]);
+          }
           Wj[i * 32] = x;
         }
       } else {
@@ -327,7 +339,7 @@ __device__ __forceinline__ void batch_factor_front(
           double x = Wj[i * 32];
 #pragma unroll
           for (int q = 0; q < R; ++q) {
-            if (q < kb) x -= Ll[(q * F + i) * 32] * wj[q];
+            if (q < kb) x = schur_term<kFused>(x, Ll[(q * F + i) * 32], wj[q]);
           }
           Wj[i * 32] = x;
         }
@@ -369,6 +381,7 @@ __device__ __forceinline__ void batch_factor_front(
 }
 
 /// stats: per instance 8 ints (n_pos n_neg n_zero zero_pivot | min|D| bits | pad).
+template <bool kFused>
 __global__ void __launch_bounds__(kBatchWarps * 32, SLPB_BATCH_MIN_BLOCKS)
 k_batch_factor(BatchView T, const double* __restrict__ Kb,
                const double* __restrict__ delta,
@@ -401,7 +414,7 @@ k_batch_factor(BatchView T, const double* __restrict__ Kb,
     const int inst = g * 32 + lane;
     const int* dep = &fcount[size_t(g) * T.n_super + s];
     if (n_tri <= T.tri_cap) {
-      batch_factor_front<true>(warp, lane, fm, T, g, Kb, delta[inst],
+      batch_factor_front<true, kFused>(warp, lane, fm, T, g, Kb, delta[inst],
                                gamma[inst], Pb, Ub, Db, smem,
                                smem + lbuf_offset_doubles, dep, st);
     } else {
@@ -409,7 +422,7 @@ k_batch_factor(BatchView T, const double* __restrict__ Kb,
       // zero-initialised at creation and left zero by every task)
       const size_t per_block = (size_t(64) * 65 / 2 + kBatchRank * 64) * 32;
       double* W = gscratch + size_t(blockIdx.x) * per_block;
-      batch_factor_front<false>(warp, lane, fm, T, g, Kb, delta[inst],
+      batch_factor_front<false, kFused>(warp, lane, fm, T, g, Kb, delta[inst],
                                 gamma[inst], Pb, Ub, Db, W,
                                 W + size_t(64) * 65 / 2 * 32, dep, st);
     }
@@ -580,6 +593,7 @@ struct slpb_batch {
       staging, gscratch;
   cudaEvent_t ev[4] = {};
   float factor_ms = 0.0f, solve_ms = 0.0f;
+  bool fused_arith = false;  // arithmetic mode of the solver it was created from
   std::string error;
 };
 
@@ -756,10 +770,12 @@ int slpb_batch_create(slpb_solver* S, int32_t batch, slpb_batch** out) {
   int sms = 148;
   cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, S->device);
   B->factor_smem = (B->tri_cap + kBatchRank * f_cap) * 32 * 8;
-  CU(raise_dynamic_smem(k_batch_factor, B->factor_smem));
+  CU(raise_dynamic_smem(k_batch_factor<false>, B->factor_smem));
+  CU(raise_dynamic_smem(k_batch_factor<true>, B->factor_smem));
+  B->fused_arith = S->factor_arith == SLPB_ARITH_TENSOR;
   int per_sm = 1;
   CU(cudaOccupancyMaxActiveBlocksPerMultiprocessor(
-      &per_sm, k_batch_factor, kBatchWarps * 32, B->factor_smem));
+      &per_sm, k_batch_factor<false>, kBatchWarps * 32, B->factor_smem));
   per_sm = std::max(per_sm, 1);
   const int64_t tasks = int64_t(ns) * G;
   B->factor_blocks =
@@ -875,10 +891,17 @@ int slpb_batch_factor(slpb_batch* B, const double* delta, const double* gamma,
   CUB(cudaMemsetAsync(B->sync.p, 0, (4 + size_t(B->groups) * ns) * 4, B->stream));
   CUB(cudaEventRecord(B->ev[0], B->stream));
   const BatchView T = batch_view(B);
-  k_batch_factor<<<B->factor_blocks, kBatchWarps * 32, B->factor_smem,
-                   B->stream>>>(T, B->Kb.p, B->delta.p, B->gamma.p, B->Pb.p,
-                                B->Ub.p, B->Db.p, B->stats.p, B->gscratch.p,
-                                B->tri_cap * 32);
+  if (B->fused_arith) {
+    k_batch_factor<true><<<B->factor_blocks, kBatchWarps * 32, B->factor_smem,
+                           B->stream>>>(T, B->Kb.p, B->delta.p, B->gamma.p,
+                                        B->Pb.p, B->Ub.p, B->Db.p, B->stats.p,
+                                        B->gscratch.p, B->tri_cap * 32);
+  } else {
+    k_batch_factor<false><<<B->factor_blocks, kBatchWarps * 32, B->factor_smem,
+                            B->stream>>>(T, B->Kb.p, B->delta.p, B->gamma.p,
+                                         B->Pb.p, B->Ub.p, B->Db.p, B->stats.p,
+                                         B->gscratch.p, B->tri_cap * 32);
+  }
   CUB(cudaEventRecord(B->ev[1], B->stream));
   CUB(cudaGetLastError());
   std::vector<int32_t> host(lanes * 8);

@@ -4,6 +4,25 @@
 // 74,105 and :159-161): lower triangle, NO pivoting, D diagonal, "failure" only
 // when a pivot is exactly zero.
 //
+// Two arithmetic modes, shared by every factorisation path of this library
+// (this generic body, the warp-per-front kernels of ldlt_warp.cuh /
+// ldlt_dense.cuh and the batched kernels of batch.cuh), so that all paths
+// produce the same bits in either mode; l_ik = w_ik / d_k (correctly rounded
+// division) in both:
+//   reference (default): W(i,j) ← W(i,j) − RN(l_ik · w_jk), product and
+//     difference rounded separately like the reference's x86-64 build;
+//   fused: every Schur-complement term is ONE fused multiply-add,
+//     W(i,j) ← fma(−l_ik, w_jk, W(i,j)), k ascending — what the FP64 tensor
+//     core computes (a chain of FMAs over the four pivots of a block,
+//     measured), the mode in which dense fronts run on the tensor cores.
+// The two differ by one rounding per term, but not harmlessly for the solver
+// above: a structurally singular pivot, mathematically zero, comes out EXACTLY
+// zero under separate rounding in most cases (RN(RN(w/d)·w) lands back on the
+// entry it is subtracted from) and is then caught by the zero-pivot / inertia
+// test of the regularisation loop, while the fused update leaves a residual of
+// ~1e-17 that can pass for a legitimate pivot. Whole solves therefore follow
+// the reference's decisions only in the reference mode.
+//
 // One front = one supernode of the assembly tree (symbolic.cpp): a dense
 // F×F column-major matrix whose first `np` rows/columns are the supernode's own
 // (permuted) columns. Written once as functions of (tid, NT): the kernels run
@@ -53,7 +72,7 @@ SLPB_HD void ldlt_factor_front(int tid, int s, const SymbolicView& S,
                                double gamma, double* __restrict__ panels,
                                double* __restrict__ updates,
                                double* __restrict__ D, double* W, double* lcol,
-                               int* local_stats, Sync sync) {
+                               int* local_stats, Sync sync, bool fused = false) {
   const int F = S.front_dim[s];
   const int c0 = S.super_first[s];
   const int np = S.super_first[s + 1] - c0;
@@ -107,7 +126,13 @@ SLPB_HD void ldlt_factor_front(int tid, int s, const SymbolicView& S,
     // W(i,j) −= l_ik · (d·l_jk) for k < j ≤ i, with d·l_jk still in column k
     for (int j = k + 1; j < F; ++j) {
       const double wjk = W[j + k * F];
-      for (int i = j + tid; i < F; i += NT) W[i + j * F] -= lcol[i] * wjk;
+      if (fused) {
+        for (int i = j + tid; i < F; i += NT) {
+          W[i + j * F] = fma(-lcol[i], wjk, W[i + j * F]);
+        }
+      } else {
+        for (int i = j + tid; i < F; i += NT) W[i + j * F] -= lcol[i] * wjk;
+      }
     }
     sync();
     for (int i = k + 1 + tid; i < F; i += NT) W[i + k * F] = lcol[i];

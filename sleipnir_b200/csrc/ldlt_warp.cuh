@@ -1,17 +1,20 @@
 // Warp-specialised front kernels for fronts of order ≤ 32 (device only).
 //
 // Same assembly and the same per-entry arithmetic as the generic bodies in
-// ldlt_core.hpp — W(i,j) −= l_ik · w_jk for k ascending, l_ik = w_ik / d_k — so
-// both produce identical bits. What changes is the mapping: a front is assembled
-// in shared memory, then lane i takes row i into registers and the pivots are
-// eliminated with warp shuffles (no shared-memory round trip, no barrier per
-// pivot); the right-hand side rides along (forward substitution fused into the
-// factorisation); global loads are batched ahead of the shared-memory
-// read-modify-writes, and all per-front metadata comes from one packed record
-// instead of a chain of dependent index loads.
+// ldlt_core.hpp — W(i,j) ← fma(−l_ik, w_jk, W(i,j)) for k ascending,
+// l_ik = w_ik / d_k — so both produce identical bits. What changes is the
+// mapping: a front is assembled in shared memory (leading dimension kFrontLd)
+// and eliminated in blocks of four pivots, the panel of a block with the rows
+// in registers and warp shuffles, the trailing update of dense fronts on the
+// FP64 tensor cores (ldlt_dense.cuh); the right-hand side rides along (forward
+// substitution fused into the factorisation); the children's update matrices
+// are fetched with every load in flight at once and land through a precomputed
+// position map; all per-front metadata comes from one packed record instead of
+// a chain of dependent index loads.
 #pragma once
 
 #include "ldlt_core.hpp"
+#include "ldlt_dense.cuh"
 
 namespace slpb {
 
@@ -72,103 +75,6 @@ __device__ __forceinline__ void wait_children(const int* p, int need) {
   }
 }
 
-/// Elimination of the own columns of a front of order F ≤ 32 with the rows in
-/// registers, then the write-out of the L panel and the update matrix.
-/// Lane i keeps row i, shifted so that w[0] is always the current pivot column
-/// (w[jj] = W(i, k + jj)): one compact loop body serves every pivot (a fully
-/// unrolled 32 × 32 elimination does not fit the instruction cache). Pivot k:
-/// lane k broadcasts d, every lane i > k forms l_ik = w_ik / d, the unscaled
-/// w_jk travels from lane j by shuffle and W(i,j) −= l_ik · w_jk — the same
-/// products in the same order as ldlt_factor_front, with no shared-memory
-/// round trip and no warp barrier per pivot. Inertia counters are meaningful
-/// in lane 0 only.
-__device__ __noinline__ void ldlt_eliminate_rows(
-    int lane, int F, int np, int m, const double* __restrict__ W,
-    double* __restrict__ Dk, double* __restrict__ P, double* __restrict__ U,
-    int* __restrict__ local_stats, double& rhs_i) {
-  // rhs_i: this lane's entry of the front's right-hand side; it takes part in
-  // the elimination (forward substitution carried along: r_i −= l_ik · r_k,
-  // the arithmetic of ldlt_forward_front) and returns y (lanes < np) and the
-  // update vector (lanes ≥ np).
-  double r = rhs_i;
-  double w[32];
-#pragma unroll
-  for (int j = 0; j < 32; ++j) {
-    w[j] = (lane < F && j <= lane) ? W[lane + j * F] : 0.0;
-  }
-  int pos = 0, neg = 0, zero = 0, zpiv = 0;
-  double min_abs = INFINITY;
-#pragma unroll 1
-  for (int k = 0; k < np; ++k) {
-    const double d = __shfl_sync(0xffffffffu, w[0], k);
-    {
-      // inertia bookkeeping (every lane computes it; lane 0 reports it)
-      const double eps = 2.220446049250313e-16;
-      pos += d > eps ? 1 : 0;
-      neg += d < -eps ? 1 : 0;
-      zero += (d > eps || d < -eps) ? 0 : 1;
-      zpiv |= d == 0.0 ? 1 : 0;
-      min_abs = fmin(min_abs, fabs(d));
-    }
-    if (lane == 0) Dk[k] = d;
-    const double wk = w[0];
-    // 0 / d: div.rn.f64 sends a zero dividend through its ~90-instruction
-    // special-case subroutine, and every lane outside the column (and every
-    // structural zero inside it) would drag the warp through it on every
-    // pivot. The quotient is a signed zero: form it directly (same bits).
-    double l;
-    if (wk == 0.0 && d == d && d != 0.0) {
-      l = (signbit(wk) != signbit(d)) ? -0.0 : 0.0;
-    } else {
-      l = wk / d;
-    }
-    // column k of the L panel (the diagonal slot keeps d, as in the generic body)
-    if (lane < F) P[lane + k * F] = lane > k ? l : wk;
-    {
-      const double rk = __shfl_sync(0xffffffffu, r, k);
-      const double upd = r - l * rk;
-      r = (lane > k && lane < F) ? upd : r;
-    }
-    // trailing update in branch-free groups of 8 columns, so that the eight
-    // shuffles and multiply-subtracts of a group overlap
-#pragma unroll
-    for (int g = 0; g < 4; ++g) {
-      if (k + 1 + 8 * g < F) {
-#pragma unroll
-        for (int q = 0; q < 8; ++q) {
-          const int jj = 1 + 8 * g + q;
-          if (jj < 32) {
-            const int j = k + jj;
-            const double wjk = __shfl_sync(0xffffffffu, wk, j & 31);
-            const double upd = w[jj] - l * wjk;
-            w[jj] = (j < F && lane >= j) ? upd : w[jj];
-          }
-        }
-      }
-    }
-#pragma unroll
-    for (int jj = 0; jj < 31; ++jj) w[jj] = w[jj + 1];
-    w[31] = 0.0;
-  }
-  // update matrix (m × m, lower): w[jj] now holds column np + jj
-#pragma unroll
-  for (int jj = 0; jj < 32; ++jj) {
-    if (jj < m && lane >= np + jj && lane < F) {
-      U[(lane - np) + jj * m] = w[jj];
-    }
-  }
-  rhs_i = r;
-  if (lane == 0) {
-    local_stats[0] = pos;
-    local_stats[1] = neg;
-    local_stats[2] = zero;
-    local_stats[3] = zpiv;
-    const unsigned long long bits = __double_as_longlong(min_abs);
-    local_stats[4] = static_cast<int>(bits & 0xffffffffull);
-    local_stats[5] = static_cast<int>(bits >> 32);
-  }
-}
-
 /// Right-hand side carried through the factorisation (forward substitution
 /// fused into the factor launch); rhs == nullptr switches it off.
 struct FusedRhs {
@@ -178,27 +84,41 @@ struct FusedRhs {
   double* uvecs;          // update vectors, indexed like rel_idx
 };
 
-/// W: F×F column-major in shared memory; col: 64 doubles of shared scratch (the
-/// front's right-hand side while it is assembled). `dep` is polled by lane 0
-/// AFTER everything that does not depend on the children is done.
+/// Children whose update matrices are fetched in one batch right after the
+/// wait, and how many entries per lane each may have there (8 × 32 = 256
+/// entries: update matrices up to 16 × 16). Bigger / further children take the
+/// general loop.
+constexpr int kExtChildren = 2;
+constexpr int kExtPerLane = 8;
+
+/// W: the warp's front workspace (kFrontSmemDoubles of shared memory: the
+/// front with leading dimension kFrontLd, the side buffers of the blocked
+/// elimination, the front's right-hand side). asm_dst: position of each own
+/// KKT entry in that layout; ext_map: for every entry of every update matrix
+/// (indexed like `updates`) its position in the PARENT's front, −1 for the
+/// unused upper triangle. `dep` is polled by lane 0 AFTER everything that does
+/// not depend on the children is done.
 __device__ __forceinline__ void ldlt_factor_front_warp(
     int lane, const FrontMeta& fm, const FrontMeta* __restrict__ metas,
     const int32_t* __restrict__ child_idx, const int32_t* __restrict__ rel_idx,
     const int32_t* __restrict__ asm_src, const int32_t* __restrict__ asm_dst,
+    const int32_t* __restrict__ ext_map,
     const uint8_t* __restrict__ col_is_primal,
     const double* __restrict__ Kval, double delta, double gamma,
     double* __restrict__ panels, double* updates, double* __restrict__ D,
-    double* __restrict__ W, double* __restrict__ col,
-    const int* dep, int* local_stats, const FusedRhs& fr,
+    double* __restrict__ W, const int* dep, int* local_stats,
+    const FusedRhs& fr, bool fused_arith,
     unsigned long long* stamp = nullptr) {
   const int F = fm.F, np = fm.np, c0 = fm.c0, m = F - np;
-  // own part of the right-hand side (col[] doubles as the rhs work vector)
+  double* side = W + kFrontLd * kFrontCols;
+  double* col = side + kDenseSideDoubles;  // the front's right-hand side
+  // own part of the right-hand side
   if (fr.rhs != nullptr && lane < F) {
     col[lane] = lane < np ? fr.rhs[fr.perm[c0 + lane]] : 0.0;
   }
 
   // ---- child-independent part: own KKT entries, δ/γ, child metadata ---------
-  for (int i = lane; i < F * F; i += 32) W[i] = 0.0;
+  for (int j = 0; j < F; ++j) W[lane + j * kFrontLd] = 0.0;
   __syncwarp();
   for (int k = fm.asm_begin + lane; k < fm.asm_end; k += 32) {
     W[asm_dst[k]] = Kval[asm_src[k]];
@@ -211,8 +131,24 @@ __device__ __forceinline__ void ldlt_factor_front_warp(
                              rel_idx, updates);
     }
   }
+  // where the entries of the first children's update matrices go
+  int dst[kExtChildren][kExtPerLane];
+#pragma unroll
+  for (int c = 0; c < kExtChildren; ++c) {
+    if (c < fm.n_child) {
+      const int n_e = pre[c].mc * pre[c].mc;
+      const int32_t* map = ext_map + (pre[c].U - updates);
+#pragma unroll
+      for (int q = 0; q < kExtPerLane; ++q) {
+        const int e = lane + 32 * q;
+        dst[c][q] = e < n_e ? __ldg(map + e) : -1;
+      }
+    }
+  }
   __syncwarp();
-  if (lane < np) W[lane + lane * F] += col_is_primal[c0 + lane] ? delta : -gamma;
+  if (lane < np) {
+    W[lane + lane * kFrontLd] += col_is_primal[c0 + lane] ? delta : -gamma;
+  }
 
   // ---- wait for the children, then extend-add their update matrices ---------
   if (lane == 0) {
@@ -224,47 +160,104 @@ __device__ __forceinline__ void ldlt_factor_front_warp(
     }
   }
   __syncwarp();
-  for (int ck = 0; ck < fm.n_child; ++ck) {
+  {
+    // every load of the first children goes out before the first add
+    double u[kExtChildren][kExtPerLane];
+    double uv[kExtChildren];
+#pragma unroll
+    for (int c = 0; c < kExtChildren; ++c) {
+      if (c < fm.n_child) {
+#pragma unroll
+        for (int q = 0; q < kExtPerLane; ++q) {
+          u[c][q] = dst[c][q] >= 0 ? __ldcg(pre[c].U + lane + 32 * q) : 0.0;
+        }
+        uv[c] = (fr.rhs != nullptr && lane < pre[c].mc)
+                    ? __ldcg(fr.uvecs + pre[c].rel_off + lane)
+                    : 0.0;
+      }
+    }
+#pragma unroll
+    for (int c = 0; c < kExtChildren; ++c) {
+      if (c < fm.n_child) {
+        // entries of ONE child land on distinct entries of the parent; the
+        // children follow each other in child order (fixed summation order)
+#pragma unroll
+        for (int q = 0; q < kExtPerLane; ++q) {
+          if (dst[c][q] >= 0) W[dst[c][q]] += u[c][q];
+        }
+        const int mc = pre[c].mc;
+        if (fr.rhs != nullptr && lane < mc) col[pre[c].ri] += uv[c];
+        // the rare update matrix above 16 × 16: the rest of its entries
+        for (int e0 = 32 * kExtPerLane; e0 < mc * mc; e0 += 32 * kExtPerLane) {
+          const int32_t* map = ext_map + (pre[c].U - updates) + e0;
+          double ux[kExtPerLane];
+          int dx[kExtPerLane];
+#pragma unroll
+          for (int q = 0; q < kExtPerLane; ++q) {
+            const int e = e0 + lane + 32 * q;
+            dx[q] = e < mc * mc ? __ldg(map + lane + 32 * q) : -1;
+            ux[q] = dx[q] >= 0 ? __ldcg(pre[c].U + e) : 0.0;
+          }
+#pragma unroll
+          for (int q = 0; q < kExtPerLane; ++q) {
+            if (dx[q] >= 0) W[dx[q]] += ux[q];
+          }
+        }
+        __syncwarp();
+      }
+    }
+  }
+  for (int ck = kExtChildren; ck < fm.n_child; ++ck) {
     ChildPre cp;
     if (ck < kPreChildren) {
       // static indexing keeps pre[] in registers
-      cp = pre[0];
+      cp = pre[kExtChildren];
 #pragma unroll
-      for (int q = 1; q < kPreChildren; ++q) {
+      for (int q = kExtChildren + 1; q < kPreChildren; ++q) {
         if (ck == q) cp = pre[q];
       }
     } else {
       cp = preload_child(lane, child_idx[fm.child_begin + ck], metas, rel_idx,
                          updates);
     }
-    const int mc = cp.mc, ri = cp.ri;
-    const double* U = cp.U;
+    const int mc = cp.mc;
     if (fr.rhs != nullptr && lane < mc) {
-      col[ri] += __ldcg(fr.uvecs + cp.rel_off + lane);
+      col[cp.ri] += __ldcg(fr.uvecs + cp.rel_off + lane);
     }
-    for (int j0 = 0; j0 < mc; j0 += 8) {
-      double u[8];
+    const int32_t* map = ext_map + (cp.U - updates);
+    for (int e0 = 0; e0 < mc * mc; e0 += 32 * kExtPerLane) {
+      double ux[kExtPerLane];
+      int dx[kExtPerLane];
 #pragma unroll
-      for (int q = 0; q < 8; ++q) {
-        const int j = j0 + q;
-        u[q] = (j < mc && j <= lane && lane < mc) ? __ldcg(U + lane + j * mc)
-                                                  : 0.0;
+      for (int q = 0; q < kExtPerLane; ++q) {
+        const int e = e0 + lane + 32 * q;
+        dx[q] = e < mc * mc ? __ldg(map + e) : -1;
+        ux[q] = dx[q] >= 0 ? __ldcg(cp.U + e) : 0.0;
       }
 #pragma unroll
-      for (int q = 0; q < 8; ++q) {
-        const int j = j0 + q;
-        const int rj = __shfl_sync(0xffffffffu, ri, j & 31);
-        if (j < mc && j <= lane && lane < mc) W[ri + rj * F] += u[q];
+      for (int q = 0; q < kExtPerLane; ++q) {
+        if (dx[q] >= 0) W[dx[q]] += ux[q];
       }
     }
     __syncwarp();
   }
 
-  // ---- elimination of the own columns + write-out (separate function so that
-  // the 32-double row stays in registers) --------------------------------------
+  if (stamp && lane == 0) {  // [1] the children were seen, [2] they are added
+    unsigned long long t;
+    asm volatile("mov.u64 %0, %globaltimer;" : "=l"(t));
+    stamp[1] = t;
+  }
+  // ---- elimination of the own columns + write-out ----------------------------
   double rhs_i = (fr.rhs != nullptr && lane < F) ? col[lane] : 0.0;
-  ldlt_eliminate_rows(lane, F, np, m, W, D + c0, panels + fm.panel_off,
-                      updates + fm.update_off, local_stats, rhs_i);
+  if (fused_arith) {
+    ldlt_eliminate_front<true>(lane, F, np, m, W, side, D + c0,
+                               panels + fm.panel_off, updates + fm.update_off,
+                               local_stats, rhs_i);
+  } else {
+    ldlt_eliminate_front<false>(lane, F, np, m, W, side, D + c0,
+                                panels + fm.panel_off, updates + fm.update_off,
+                                local_stats, rhs_i);
+  }
   if (fr.rhs != nullptr) {
     if (lane < np) {
       fr.xperm[c0 + lane] = rhs_i;

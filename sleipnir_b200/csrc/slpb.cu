@@ -196,7 +196,8 @@ struct slpb_solver {
   DevBuf<double> Kval, sigma, sinv, tvec, rhs, sol;
   // device: symbolic + factor
   DevBuf<int32_t> sy_super_first, sy_front_dim, sy_rows_idx, sy_child_idx,
-      sy_rel_idx, sy_asm_src, sy_asm_dst, sy_perm, sy_level_supers;
+      sy_rel_idx, sy_asm_src, sy_asm_dst, sy_asm_dst_ld, sy_ext_map, sy_perm,
+      sy_level_supers;
   DevBuf<int64_t> sy_rows_ptr, sy_panel_ptr, sy_update_ptr, sy_child_ptr,
       sy_rel_ptr, sy_asm_ptr;
   DevBuf<uint8_t> sy_col_is_primal;
@@ -206,6 +207,7 @@ struct slpb_solver {
   DevBuf<FrontMeta> sy_metas;
   DevBuf<unsigned long long> tree_debug;
   bool use_tree = false;
+  int factor_arith = SLPB_ARITH_REFERENCE;  // slpb_set_factor_arithmetic
   int tree_blocks = 0, solve_blocks = 0, tree_smem_doubles = 0;
   int factor_sel = 0;  // which variant of the last factorisation the solves use
   // forward substitution fused into the factorisation (slpb_prepare_rhs)
@@ -938,7 +940,7 @@ __global__ void k_factor_level(SymbolicView S,
                                double gamma, double* __restrict__ panels,
                                double* __restrict__ updates,
                                double* __restrict__ D,
-                               int32_t* __restrict__ stats) {
+                               int32_t* __restrict__ stats, int fused_arith) {
   extern __shared__ double smem[];
   __shared__ int ls[6];
   const int s = level_supers[blockIdx.x];
@@ -947,7 +949,7 @@ __global__ void k_factor_level(SymbolicView S,
   double* lcol = smem + size_t(F) * F;
   ldlt_factor_front<kFrontThreads>(threadIdx.x, s, S, Kval, delta, gamma,
                                    panels, updates, D, W, lcol, ls,
-                                   BlockSync{});
+                                   BlockSync{}, fused_arith != 0);
   if (threadIdx.x == 0) {
     atomicAdd(&stats[0], ls[0]);
     atomicAdd(&stats[1], ls[1]);
@@ -1045,12 +1047,13 @@ struct TreeView {
   const int32_t* rel_idx;
   const int32_t* rows_idx;
   const int32_t* asm_src;
-  const int32_t* asm_dst;
+  const int32_t* asm_dst;    // position in the warp's front (leading dim kFrontLd)
+  const int32_t* ext_map;    // update-matrix entry → position in the parent's front
   const uint8_t* col_is_primal;
   const int32_t* perm;
   int32_t* sync;             // [0] ticket | fcount[ns] | fflag[ns] | bflag[ns]
   int32_t n_super;
-  unsigned long long* debug; // optional: 3 globaltimer stamps per front
+  unsigned long long* debug; // optional: 4 globaltimer stamps per front
 };
 
 __device__ __forceinline__ unsigned long long global_ns() {
@@ -1070,21 +1073,21 @@ struct FactorPair {
   const double* rhs;  // non-null: carry the forward substitution of this rhs
   double* xperm;      // variant v: xperm + v·dim
   double* uvecs;      // variant v: uvecs + v·uvec_stride
+  int fused_arith;    // SLPB_ARITH_TENSOR: fused Schur updates, DMMA on dense fronts
 };
 
 #ifndef SLPB_TREE_MIN_BLOCKS
-#define SLPB_TREE_MIN_BLOCKS 1
+#define SLPB_TREE_MIN_BLOCKS 3
 #endif
 __global__ void __launch_bounds__(kTreeWarps * 32, SLPB_TREE_MIN_BLOCKS)
 k_factor_tree(TreeView T, const double* __restrict__ Kval, double delta,
               double gamma, FactorPair pair, double* __restrict__ panels,
               double* updates, double* __restrict__ D,
-              int32_t* __restrict__ stats, int smem_doubles_per_warp) {
+              int32_t* __restrict__ stats) {
   extern __shared__ double smem[];
   __shared__ int ls[kTreeWarps][6];
   const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
-  double* W = smem + size_t(warp) * smem_doubles_per_warp;
-  double* col = W + (smem_doubles_per_warp - 64);
+  double* W = smem + size_t(warp) * kFrontSmemDoubles;
   const int nv = pair.n_variants;
   int acc_pos[2] = {0, 0}, acc_neg[2] = {0, 0}, acc_zero[2] = {0, 0};
   int acc_zpiv[2] = {0, 0};
@@ -1111,18 +1114,18 @@ k_factor_tree(TreeView T, const double* __restrict__ Kval, double delta,
       if (lane == 0 && fm.parent >= 0) red_release_add(&fcount[fm.parent], 1);
       continue;
     }
-    if (T.debug && lane == 0 && v == 0) T.debug[3 * s] = global_ns();
+    if (T.debug && lane == 0 && v == 0) T.debug[4 * s] = global_ns();
     const FusedRhs fr{pair.rhs, T.perm, pair.xperm + size_t(v) * pair.dim,
                       pair.uvecs + v * pair.uvec_stride};
     ldlt_factor_front_warp(
         lane, fm, T.metas, T.child_idx, T.rel_idx, T.asm_src, T.asm_dst,
-        T.col_is_primal, Kval, v ? pair.delta1 : delta,
+        T.ext_map, T.col_is_primal, Kval, v ? pair.delta1 : delta,
         v ? pair.gamma1 : gamma, panels + v * pair.panel_stride,
-        updates + v * pair.update_stride, D + v * pair.dim, W, col,
-        &fcount[s], ls[warp], fr,
-        (T.debug && v == 0) ? T.debug + 3 * s + 1 : nullptr);
+        updates + v * pair.update_stride, D + v * pair.dim, W,
+        &fcount[s], ls[warp], fr, pair.fused_arith != 0,
+        (T.debug && v == 0) ? T.debug + 4 * s + 1 : nullptr);
     __syncwarp();
-    if (T.debug && lane == 0 && v == 0) T.debug[3 * s + 2] = global_ns();
+    if (T.debug && lane == 0 && v == 0) T.debug[4 * s + 3] = global_ns();
     if (lane == 0) {
       // hand over to the parent first; the inertia bookkeeping stays in
       // registers until the warp runs out of fronts
@@ -1807,7 +1810,8 @@ TreeView tree_view(slpb_solver* S) {
   T.rel_idx = S->sy_rel_idx.p;
   T.rows_idx = S->sy_rows_idx.p;
   T.asm_src = S->sy_asm_src.p;
-  T.asm_dst = S->sy_asm_dst.p;
+  T.asm_dst = S->sy_asm_dst_ld.p;
+  T.ext_map = S->sy_ext_map.p;
   T.col_is_primal = S->sy_col_is_primal.p;
   T.perm = S->sy_perm.p;
   T.sync = S->tree_sync.p;
@@ -2088,6 +2092,9 @@ int slpb_create(int device, slpb_solver** out) {
   if (cudaSetDevice(device) != cudaSuccess) return SLPB_ERR_CUDA;
   auto S = std::make_unique<slpb_solver>();
   S->device = device;
+  if (const char* mode = std::getenv("SLPB_FACTOR_ARITH")) {
+    if (std::strcmp(mode, "tensor") == 0) S->factor_arith = SLPB_ARITH_TENSOR;
+  }
   if (cudaStreamCreateWithFlags(&S->stream, cudaStreamNonBlocking) !=
       cudaSuccess) {
     return SLPB_ERR_CUDA;
@@ -2261,6 +2268,15 @@ int slpb_set_ignore_constraint_hessian(slpb_solver* S, int ignore) {
                 "slpb_set_ignore_constraint_hessian must precede slpb_finalize");
   }
   S->ignore_h_c = ignore != 0;
+  return SLPB_OK;
+}
+
+int slpb_set_factor_arithmetic(slpb_solver* S, int mode) {
+  if (!S) return SLPB_ERR_ARGUMENT;
+  if (mode != SLPB_ARITH_REFERENCE && mode != SLPB_ARITH_TENSOR) {
+    return fail(S, SLPB_ERR_ARGUMENT, "unknown factor arithmetic mode");
+  }
+  S->factor_arith = mode;
   return SLPB_OK;
 }
 
@@ -2447,7 +2463,7 @@ int slpb_analyze(slpb_solver* S, int ordering, const int32_t* perm,
     }
     CU(S->sy_metas.upload(metas, S->stream));
     if (std::getenv("SLPB_TREE_DEBUG")) {
-      CU(S->tree_debug.alloc(3 * size_t(Y.n_super)));
+      CU(S->tree_debug.alloc(4 * size_t(Y.n_super)));
       CU(S->tree_debug.zero(S->stream));
     }
     // [0] ticket | 3 × n_super dependency words | [1 + 3 n_super + v] "variant v
@@ -2456,16 +2472,38 @@ int slpb_analyze(slpb_solver* S, int ordering, const int32_t* perm,
   }
   // fronts of order ≤ 32: one warp per front, one launch per factorisation
   S->use_tree = Y.max_front <= 32;
-  S->tree_smem_doubles = Y.max_front * Y.max_front + 64;
+  S->tree_smem_doubles = kFrontSmemDoubles;
+  if (S->use_tree) {
+    // the warp kernels keep a front with the fixed leading dimension kFrontLd:
+    // positions of the own KKT entries, and of every update-matrix entry in
+    // the parent's front (−1: upper triangle, not stored)
+    std::vector<int32_t> dst_ld(Y.asm_dst.size());
+    std::vector<int32_t> ext(static_cast<size_t>(Y.update_size), -1);
+    for (int32_t q = 0; q < Y.n_super; ++q) {
+      const int32_t F = Y.front_dim[q];
+      for (int64_t k = Y.asm_ptr[q]; k < Y.asm_ptr[q + 1]; ++k) {
+        dst_ld[k] = Y.asm_dst[k] % F + (Y.asm_dst[k] / F) * kFrontLd;
+      }
+      if (Y.super_parent[q] < 0) continue;
+      const int32_t mc = F - (Y.super_first[q + 1] - Y.super_first[q]);
+      const int32_t* rel = Y.rel_idx.data() + Y.rel_ptr[q];
+      int32_t* e = ext.data() + Y.update_ptr[q];
+      for (int32_t j = 0; j < mc; ++j) {
+        for (int32_t i = j; i < mc; ++i) e[i + j * mc] = rel[i] + rel[j] * kFrontLd;
+      }
+    }
+    CU(S->sy_asm_dst_ld.upload(dst_ld, S->stream));
+    CU(S->sy_ext_map.upload(ext, S->stream));
+  }
   {
     const int tree_smem =
         kTreeWarps * S->tree_smem_doubles * static_cast<int>(sizeof(double));
     if (S->use_tree) {
       CU(raise_dynamic_smem(k_factor_tree, tree_smem));
-      // registers, not shared memory, should bound the resident blocks
+      // each warp keeps a 13 KB front workspace: all the shared memory there is
       CU(cudaFuncSetAttribute(k_factor_tree,
                               cudaFuncAttributePreferredSharedMemoryCarveout,
-                              50));
+                              cudaSharedmemCarveoutMaxShared));
     }
     // Persistent grids: as many blocks as are resident at once (SMs × blocks
     // per SM at this kernel's register and shared-memory footprint), never more
@@ -2733,12 +2771,13 @@ int factor_impl(slpb_solver* S, int n_variants, const double* delta,
                           Y.dim,
                           S->rhs_ready ? S->rhs.p : nullptr,
                           S->xperm.p,
-                          S->uvecs.p};
+                          S->uvecs.p,
+                          S->factor_arith};
     for (int v = 0; v < 2; ++v) S->fwd_valid[v] = S->rhs_ready && v < n_variants;
     if (!S->tree_sharded) {
       k_factor_tree<<<S->tree_blocks, kTreeWarps * 32, smem, S->stream>>>(
           T, S->Kval.p, delta[0], gamma[0], pair, S->panels.p, S->updates.p,
-          S->D.p, S->fstats.p, S->tree_smem_doubles);
+          S->D.p, S->fstats.p);
     } else {
       // Sharded: own subtrees → one small all-gather of the
       // subtree roots (update matrices, update vectors, inertia counts) → the
@@ -2752,7 +2791,7 @@ int factor_impl(slpb_solver* S, int n_variants, const double* delta,
       if (n_mine > 0) {
         k_factor_tree<<<S->tree_blocks, kTreeWarps * 32, smem, S->stream>>>(
             Tm, S->Kval.p, delta[0], gamma[0], pair, S->panels.p, S->updates.p,
-            S->D.p, S->fstats.p, S->tree_smem_doubles);
+            S->D.p, S->fstats.p);
         ++S->counters.kernel_launches;
       }
       int rc = exchange_roots(S, n_variants, true);
@@ -2771,7 +2810,7 @@ int factor_impl(slpb_solver* S, int n_variants, const double* delta,
                       blocks_for(int64_t(n_variants) * n_top, kTreeWarps)));
       k_factor_tree<<<blocks, kTreeWarps * 32, smem, S->stream>>>(
           Tt, S->Kval.p, delta[0], gamma[0], pair, S->panels.p, S->updates.p,
-          S->D.p, S->fstats.p, S->tree_smem_doubles);
+          S->D.p, S->fstats.p);
     }
     ++S->counters.kernel_launches;
   } else {
@@ -2785,7 +2824,7 @@ int factor_impl(slpb_solver* S, int n_variants, const double* delta,
             S->sview, S->sy_level_supers.p + Y.level_ptr[L], S->Kval.p,
             delta[v], gamma[v], S->panels.p + v * Y.panel_size,
             S->updates.p + v * Y.update_size, S->D.p + size_t(v) * Y.dim,
-            S->fstats.p + 8 * v);
+            S->fstats.p + 8 * v, S->factor_arith);
       }
       S->counters.kernel_launches += Y.n_levels;
     }

@@ -26,6 +26,7 @@ struct Handle {
   std::vector<double> x;
   int last_status = 0;
   bool flush_l2 = false;
+  int factor_arithmetic = -1;
   bool diagnostics = false, spy = false;
   double timeout_s = -1.0;  // < 0: Options default (no timeout)
   int rank = 0, world = 1;
@@ -95,6 +96,7 @@ int slpbh_solve(void* h, double tolerance, int max_iterations, int feasible_ipm,
   dopt.ordering = ordering;
   dopt.keep_iterates = keep_iterates != 0;
   dopt.flush_l2 = hd->flush_l2;
+  dopt.factor_arithmetic = hd->factor_arithmetic;
   dopt.spy = hd->spy;
   opt.diagnostics = hd->diagnostics;
   dopt.rank = hd->rank;
@@ -206,6 +208,10 @@ double slpbh_multistart(const char* name, int N, int count, const double* p0,
 /// Benchmark hygiene: evict the device L2 before every iteration of the next
 /// solves (excluded from the iteration timestamps).
 void slpbh_set_flush_l2(void* h, int on) { H(h)->flush_l2 = on != 0; }
+/// DeviceOptions::factor_arithmetic of the following solve() calls.
+void slpbh_set_factor_arithmetic(void* h, int mode) {
+  H(h)->factor_arithmetic = mode;
+}
 double slpbh_flush_seconds(void* h) {
   return H(h)->problem->last_trace().flush_seconds;
 }

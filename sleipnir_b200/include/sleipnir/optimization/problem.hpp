@@ -52,6 +52,9 @@ struct DeviceOptions {
   std::vector<int32_t> permutation;             ///< for SLPB_ORDER_CUSTOM
   bool keep_iterates = false;                   ///< record x,s,y,z per iteration
   bool flush_l2 = false;  ///< evict L2 before every iteration (benchmarks)
+  /// slpb_factor_arithmetic of the LDLᵀ (−1: the library's default, i.e.
+  /// SLPB_ARITH_REFERENCE unless SLPB_FACTOR_ARITH=tensor is set).
+  int factor_arithmetic = -1;
   /// Write H.spy, A_e.spy, A_i.spy (sparsity pattern + signs per iteration,
   /// util/spy.hpp) into the working directory, as the reference's
   /// solve(options, spy = true) does (problem.hpp:365-380, :462-480, :562-595).
@@ -266,6 +269,10 @@ class Problem {
 
     DeviceHandle handle{dev_options.device};
     slpb_solver* dev = handle.s;
+    if (dev_options.factor_arithmetic >= 0) {
+      SLP_DEVICE_CALL(dev, slpb_set_factor_arithmetic(
+                               dev, dev_options.factor_arithmetic));
+    }
     if (dev_options.world > 1) {
       SLP_DEVICE_CALL(dev, slpb_comm_init(dev, dev_options.rank,
                                           dev_options.world,
@@ -653,6 +660,10 @@ class Problem {
 
     DeviceHandle inner{dev_options.device};
     SLP_DEVICE_CALL(inner.s, slpb_set_ignore_constraint_hessian(inner.s, 1));
+    if (dev_options.factor_arithmetic >= 0) {
+      SLP_DEVICE_CALL(inner.s, slpb_set_factor_arithmetic(
+                                   inner.s, dev_options.factor_arithmetic));
+    }
     upload(inner.s, fp);
 
     // initial iterate (:408-424): perfect complementarity with the slacks

@@ -42,6 +42,8 @@ def lib():
         L.emu_factor.restype = C.c_double
         L.emu_factor.argtypes = [vp, C.c_double, C.c_double, _ip, _dp]
         L.emu_solve.argtypes = [vp, _dp, _dp]
+        L.emu_set_fused.argtypes = [vp, C.c_int]
+        L.emu_set_kkt_values.argtypes = [vp, _dp]
         _lib = L
     return _lib
 
@@ -149,6 +151,15 @@ class Emu:
         p = np.zeros(self.n + self.me, dtype=np.int32)
         self.L.emu_get_perm(self.h, _i(p))
         return p
+
+    def set_kkt_values(self, kv):
+        """Overwrites the assembled lhs values (after kkt())."""
+        self.L.emu_set_kkt_values(self.h, _d(np.ascontiguousarray(kv, dtype=np.float64)))
+
+    def set_fused(self, fused=True):
+        """Arithmetic mode of factor(): False = the reference's separate
+        rounding, True = fused Schur updates (SLPB_ARITH_TENSOR)."""
+        self.L.emu_set_fused(self.h, int(fused))
 
     def factor(self, delta, gamma):
         info = (C.c_int * 4)()

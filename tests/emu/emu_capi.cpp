@@ -33,6 +33,7 @@ struct Emu {
   slpb::CompiledAD ad;
   std::string error;
   int n = 0, me = 0, mi = 0;
+  bool fused = false;  // arithmetic mode of the factorisation (ldlt_core.hpp)
   // last evaluation
   std::vector<double> values, derivs;
   // linear algebra
@@ -337,6 +338,13 @@ void emu_kkt_assemble(void* h, const double* sigma, double* kval_out) {
   if (kval_out) std::memcpy(kval_out, e->Kval.data(), e->Kval.size() * 8);
 }
 
+/// Replaces the assembled lhs values (e.g. by the device's, so that the two
+/// factorisations start from the same bits).
+void emu_set_kkt_values(void* h, const double* kval) {
+  auto* e = static_cast<Emu*>(h);
+  e->Kval.assign(kval, kval + e->recipe.K.nnz());
+}
+
 /// out: dim, nnz_l, n_super, n_levels, max_front, etree_height, panel doubles,
 /// update doubles. Returns 0 on success.
 int emu_analyze(void* h, int ordering, const int* perm, int64_t* out) {
@@ -415,6 +423,8 @@ void emu_get_perm(void* h, int* perm) {
 }
 
 /// info: n_pos, n_neg, n_zero, zero_pivot; returns min |D|.
+void emu_set_fused(void* h, int fused) { static_cast<Emu*>(h)->fused = fused != 0; }
+
 double emu_factor(void* h, double delta, double gamma, int* info, double* D) {
   auto* e = static_cast<Emu*>(h);
   const auto& S = e->sym;
@@ -428,7 +438,7 @@ double emu_factor(void* h, double delta, double gamma, int* info, double* D) {
       slpb::ldlt_factor_front<1>(0, S.level_supers[k], V, e->Kval.data(), delta,
                                  gamma, e->panels.data(), e->updates.data(),
                                  e->D.data(), W.data(), lcol.data(), ls,
-                                 slpb::NoSync{});
+                                 slpb::NoSync{}, e->fused);
       for (int i = 0; i < 4; ++i) tot[i] += ls[i];
       unsigned long long bits = (unsigned long long)(unsigned)ls[4] |
                                 ((unsigned long long)(unsigned)ls[5] << 32);
