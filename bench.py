@@ -212,7 +212,8 @@ def amd_nnz_l(sb, N, device):
     return nnz
 
 
-def run_batch(sb, N, B, device, peak, fac_bytes, sol_bytes, fac_bytes_amd, sol_bytes_amd):
+def run_batch(sb, N, B, device, peak, fac_bytes, sol_bytes, fac_bytes_amd, sol_bytes_amd,
+              arithmetic=0):
     """The many-instance regime (SURVEY §8(f).1, slp::multistart's data-parallel
     axis): B KKT systems of the workload — the lhs of one iterate and B − 1
     perturbed copies — factored and solved by ONE launch each (slpb_batch_factor,
@@ -229,6 +230,7 @@ def run_batch(sb, N, B, device, peak, fac_bytes, sol_bytes, fac_bytes_amd, sol_b
                   0.5 + rng.random(P.mi))
     D.eval_current(1)
     D.analyze()
+    D.set_factor_arithmetic(arithmetic)
     fi = D.factor(1.0, 1e-6, True)
     D.solve(0.1, 0.99)
     kkt, rhs = D.download(sb.ARR_KKT_VAL), D.download(sb.ARR_RHS)
@@ -253,6 +255,7 @@ def run_batch(sb, N, B, device, peak, fac_bytes, sol_bytes, fac_bytes_amd, sol_b
     gb = lambda by, ms: B * by / (ms * 1e-3) / 1e9
     out = {
         "instances": B, "kernels": "k_batch_factor + k_batch_solve (csrc/batch.cuh)",
+        "arithmetic": "tensor (fused Schur updates)" if arithmetic else "reference",
         "factor_ms": f_ms, "solve_ms": s_ms,
         "factor": {"achieved": gb(fac_bytes, f_ms), "frac": gb(fac_bytes, f_ms) / peak},
         "solve": {"achieved": gb(sol_bytes, s_ms), "frac": gb(sol_bytes, s_ms) / peak},
@@ -447,9 +450,10 @@ def main():
 
     shard = args.shard and world > 1
 
-    def one_solve(flush, max_iterations):
+    def one_solve(flush, max_iterations, arithmetic=-1):
         Q = sb.Problem("cart_pole", N)
         Q.set_flush_l2(flush)
+        Q.set_factor_arithmetic(arithmetic)
         if shard:
             # a ncclUniqueId serves ONE communicator: a fresh one per solve
             box = [sb.comm_unique_id() if rank == 0 else None]
@@ -480,6 +484,20 @@ def main():
         dt = max_over_ranks(dt)
         cnt, tim, sym = P.counters(), P.timers(), P.symbolic_stats()
         iters = len(tr)
+        # (1b) the same steady-state leg with the LDLT in its tensor-core mode
+        #     (SLPB_ARITH_TENSOR: fused Schur updates, DMMA on fronts ≥ 16)
+        tensor = None
+        if not shard:
+            Pt, _, _ = one_solve(True, args.warmup + args.steps, sb.ARITH_TENSOR)
+            trt = Pt.trace()
+            kt, dtt = steady_rate(trt, args.warmup, args.steps)
+            dtt = max_over_ranks(dtt)
+            timt, cntt = Pt.timers(), Pt.counters()
+            nl = max(timt["factor"]["count"], 1)
+            tensor = {"value": world * kt / dtt, "unit": UNIT, "steps": kt,
+                      "factor_ms_per_launch": timt["factor"]["total_ms"] / nl,
+                      "factorizations_per_launch": cntt["factorizations_completed"] / nl}
+            Pt.close()
         # (2) the solve as a user runs it: Problem::solve() with default Options
         #     (max_iterations = 5000) from host buffers TO CONVERGENCE, no
         #     flushes. Gives the end-to-end number and, from its first W+K
@@ -546,6 +564,13 @@ def main():
                           sol_bytes_full, fac_bytes_amd,
                           2 * 12 * nnz_l_amd + 40 * sym["dim"])
 
+    batch_tensor = None
+    if world == 1 and args.batch > 0 and tensor is not None:
+        batch_tensor = run_batch(sb, N, args.batch, local_rank, peak, fac_bytes,
+                                 sol_bytes_full, fac_bytes_amd,
+                                 2 * 12 * nnz_l_amd + 40 * sym["dim"],
+                                 arithmetic=sb.ARITH_TENSOR)
+
     line = {
         "metric": METRIC, "value": rate, "unit": UNIT, "n_gpus": world,
         "steps": k, "warmup": args.warmup, "ms_per_step": 1e3 * dt / k,
@@ -604,6 +629,20 @@ def main():
                 "frac": sol_bytes_half / (sol_ms * 1e-3) / 1e9 / peak if sol_ms > 0 else None,
                 "traffic": traffic.get("k_solve_tree_dram_bytes_per_launch")},
             "batch": batch,
+            "tensor_fronts": None if tensor is None else dict(tensor, **{
+                "what": "the same steady-state leg with slpb_set_factor_arithmetic("
+                        "SLPB_ARITH_TENSOR): every Schur-complement term one fused "
+                        "multiply-add, rank-4 updates of frontal matrices of order "
+                        ">= 16 on the FP64 tensor cores (mma.sync m8n8k4.f64, SASS "
+                        "DMMA.8x8x4). Not the default: whole solves follow the "
+                        "reference's regularisation decisions only with the "
+                        "reference's separate rounding (DESIGN.md §3.3)",
+                "achieved": (fac_bytes * tensor["factorizations_per_launch"]) /
+                            (tensor["factor_ms_per_launch"] * 1e-3) / 1e9,
+                "frac": (fac_bytes * tensor["factorizations_per_launch"]) /
+                        (tensor["factor_ms_per_launch"] * 1e-3) / 1e9 / peak,
+                "batch_factor_ms": None if batch_tensor is None else batch_tensor["factor_ms"],
+                "batch_factor_frac": None if batch_tensor is None else batch_tensor["factor"]["frac"]}),
             "ad_sweep": {
                 "traffic": traffic.get("k_ad_sweep_dram_bytes_per_launch"),
                 "kernel": "k_ad_sweep (full re-linearisation)",

@@ -177,7 +177,8 @@ __device__ __forceinline__ void batch_factor_front(
     }
   }
   // ---- children: wait, then extend-add in child order ------------------------
-  if (threadIdx.x == 0) wait_children(dep, fm.n_child);
+  // (warp 0 waits as a whole, without a one-lane branch: see wait_children_warp)
+  if (warp == 0) wait_children_warp(lane, dep, fm.n_child);
   compute_sync();
   for (int ck = 0; ck < fm.n_child; ++ck) {
     const FrontMeta cm = load_front_meta(T.metas + T.child_idx[fm.child_begin + ck]);
@@ -481,7 +482,7 @@ k_batch_solve(BatchView T, const double* __restrict__ Pb,
       for (int i = 0; i < F; ++i) {
         wl[i * 32] = i < np ? __ldg(r + int64_t(T.perm[c0 + i]) * 32) : 0.0;
       }
-      if (lane == 0) wait_children(&fcount[fi], fm.n_child);
+      wait_children_warp(lane, &fcount[fi], fm.n_child);
       __syncwarp();
       for (int ck = 0; ck < fm.n_child; ++ck) {
         const FrontMeta cm =
@@ -516,10 +517,9 @@ k_batch_solve(BatchView T, const double* __restrict__ Pb,
     } else {
       const double* Dg = Db + int64_t(g) * T.dim * 32 + lane;
       const int32_t* rows = T.rows_idx + fm.rows_off;
-      if (lane == 0) {
-        wait_children(fm.parent >= 0 ? &bflag[size_t(g) * ns + fm.parent]
-                                     : &fflag[fi], 1);
-      }
+      wait_children_warp(lane,
+                         fm.parent >= 0 ? &bflag[size_t(g) * ns + fm.parent]
+                                        : &fflag[fi], 1);
       __syncwarp();
       for (int i = 0; i < F; ++i) {
         wl[i * 32] = i < np ? __ldcg(xp + int64_t(c0 + i) * 32) /
@@ -714,6 +714,7 @@ int slpb_batch_create(slpb_solver* S, int32_t batch, slpb_batch** out) {
     fm.rows_off = Y.rows_ptr[s];
     fm.parent = Y.super_parent[s];
     fm.pad = 0;
+    fm.ext_begin = fm.ext_chunks = fm.pad2 = fm.pad3 = 0;
   }
   // packed position of every own KKT entry; the own diagonal entries (always
   // present in the pattern) carry which regularisation they take

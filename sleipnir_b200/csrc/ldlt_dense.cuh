@@ -77,6 +77,7 @@ __device__ __noinline__ void ldlt_eliminate_front(
     double* __restrict__ side, double* __restrict__ Dk, double* __restrict__ P,
     double* __restrict__ U, int* __restrict__ local_stats, double& rhs_i) {
 #ifdef SLPB_DENSE_PROFILE
+  const unsigned active_at_entry = __activemask();
   unsigned lap0_ = 0, lap1_ = 0, lap2_ = 0, lap3_ = 0, lap4_ = 0, lapt_ = clock();
 #define DENSE_LAP(i) { const unsigned now_ = clock(); lap##i##_ += now_ - lapt_; lapt_ = now_; }
 #else
@@ -287,8 +288,9 @@ __device__ __noinline__ void ldlt_eliminate_front(
   rhs_i = r;
   DENSE_LAP(4)
 #ifdef SLPB_DENSE_PROFILE
-  if (lane == 0 && blockIdx.x == 0 && threadIdx.x == 0) {
-    printf("   laps: panel load %u, pivots %u, side %u, trailing %u, write-out %u\n", lap0_, lap1_, lap2_, lap3_, lap4_);
+  if (lane == 0 && lap0_ + lap1_ + lap2_ + lap3_ + lap4_ > 16000u) {
+    const unsigned active_at_exit = __activemask();
+    printf("   laps active %08x / %08x F=%d np=%d fused=%d: panel load %u, pivots %u, side %u, trailing %u, write-out %u\n", active_at_entry, active_at_exit, F, np, int(kFused), lap0_, lap1_, lap2_, lap3_, lap4_);
   }
 #endif
   // D and the inertia bookkeeping: lane k holds pivot k

@@ -18,18 +18,21 @@
 
 namespace slpb {
 
-/// Everything a warp needs to know about a front, in one 64-byte record.
+/// Everything a warp needs to know about a front, in one 80-byte record.
 struct alignas(16) FrontMeta {
   int32_t F, np, c0, n_child;
   int32_t child_begin, asm_begin, asm_end, rel_off;
   int64_t panel_off, update_off;
   int64_t rows_off;
   int32_t parent, pad;
+  // extend-add list of the warp-per-front factorisation: chunks of 32
+  // (source, destination) pairs, see ExtendList
+  int32_t ext_begin, ext_chunks, pad2, pad3;
 };
-static_assert(sizeof(FrontMeta) == 64, "FrontMeta must stay one 64-byte line");
+static_assert(sizeof(FrontMeta) == 80, "FrontMeta is five 16-byte words");
 
 __device__ __forceinline__ FrontMeta load_front_meta(const FrontMeta* p) {
-  // four independent 16-byte loads
+  // five independent 16-byte loads
   FrontMeta m;
   const int4* src = reinterpret_cast<const int4*>(p);
   int4* dst = reinterpret_cast<int4*>(&m);
@@ -37,8 +40,26 @@ __device__ __forceinline__ FrontMeta load_front_meta(const FrontMeta* p) {
   dst[1] = __ldg(src + 1);
   dst[2] = __ldg(src + 2);
   dst[3] = __ldg(src + 3);
+  dst[4] = __ldg(src + 4);
   return m;
 }
+
+/// Extend-add of a front as one flat list (built once per symbolic analysis):
+/// for every child, in child order, the lower triangle of its update matrix
+/// and its update vector as (source, destination) pairs, padded per child to a
+/// multiple of 32, so that a chunk of 32 pairs belongs to ONE child (its
+/// entries land on distinct destinations) and chunks follow the fixed child
+/// order of the summation. src: offset into the update-matrix storage, or
+/// kExtVecTag | offset into the update-vector storage; dst: offset from the
+/// start of the warp's front workspace (the front itself, or the right-hand
+/// side behind it); −1 pads.
+constexpr int32_t kExtVecTag = 1 << 30;
+struct ExtendList {
+  const int32_t* src;
+  const int32_t* dst;
+};
+/// Chunks whose loads are all in flight at once.
+constexpr int kExtBatch = 8;
 
 /// What a parent front pre-loads about one child before it starts waiting.
 struct ChildPre {
@@ -75,6 +96,26 @@ __device__ __forceinline__ void wait_children(const int* p, int need) {
   }
 }
 
+/// The same wait for a whole warp, WITHOUT a lane-0 branch: lane 0 loads, every
+/// lane takes the decision from it, so the warp stays converged (a warp that
+/// comes out of a one-lane spin loop split in two runs everything behind it
+/// lane group by lane group; measured on the factorisation: 3–4× slower
+/// eliminations).
+__device__ __forceinline__ void wait_children_warp(int lane, const int* p,
+                                                   int need) {
+  if (need <= 0) return;
+  unsigned spins = 0;
+  for (;;) {
+    int v = 0;
+    if (lane == 0) {
+      asm volatile("ld.acquire.gpu.global.s32 %0, [%1];" : "=r"(v) : "l"(p) : "memory");
+    }
+    v = __shfl_sync(0xffffffffu, v, 0);
+    if (v >= need) break;
+    if (++spins > 16) __nanosleep(spins > 256 ? 200 : 40);
+  }
+}
+
 /// Right-hand side carried through the factorisation (forward substitution
 /// fused into the factor launch); rhs == nullptr switches it off.
 struct FusedRhs {
@@ -84,25 +125,16 @@ struct FusedRhs {
   double* uvecs;          // update vectors, indexed like rel_idx
 };
 
-/// Children whose update matrices are fetched in one batch right after the
-/// wait, and how many entries per lane each may have there (8 × 32 = 256
-/// entries: update matrices up to 16 × 16). Bigger / further children take the
-/// general loop.
-constexpr int kExtChildren = 2;
-constexpr int kExtPerLane = 8;
-
 /// W: the warp's front workspace (kFrontSmemDoubles of shared memory: the
 /// front with leading dimension kFrontLd, the side buffers of the blocked
 /// elimination, the front's right-hand side). asm_dst: position of each own
-/// KKT entry in that layout; ext_map: for every entry of every update matrix
-/// (indexed like `updates`) its position in the PARENT's front, −1 for the
-/// unused upper triangle. `dep` is polled by lane 0 AFTER everything that does
-/// not depend on the children is done.
+/// KKT entry in that layout; ext: the front's extend-add list. `dep` is polled
+/// by lane 0 AFTER everything that does not depend on the children is done —
+/// the indices of the first kExtBatch chunks included, so that behind the wait
+/// there is ONE round trip to the L2 for the children's data.
 __device__ __forceinline__ void ldlt_factor_front_warp(
-    int lane, const FrontMeta& fm, const FrontMeta* __restrict__ metas,
-    const int32_t* __restrict__ child_idx, const int32_t* __restrict__ rel_idx,
-    const int32_t* __restrict__ asm_src, const int32_t* __restrict__ asm_dst,
-    const int32_t* __restrict__ ext_map,
+    int lane, const FrontMeta& fm, const int32_t* __restrict__ asm_src,
+    const int32_t* __restrict__ asm_dst, const ExtendList& ext,
     const uint8_t* __restrict__ col_is_primal,
     const double* __restrict__ Kval, double delta, double gamma,
     double* __restrict__ panels, double* updates, double* __restrict__ D,
@@ -117,138 +149,92 @@ __device__ __forceinline__ void ldlt_factor_front_warp(
     col[lane] = lane < np ? fr.rhs[fr.perm[c0 + lane]] : 0.0;
   }
 
-  // ---- child-independent part: own KKT entries, δ/γ, child metadata ---------
+  // ---- child-independent part: own KKT entries, δ/γ, extend-add indices -----
   for (int j = 0; j < F; ++j) W[lane + j * kFrontLd] = 0.0;
   __syncwarp();
   for (int k = fm.asm_begin + lane; k < fm.asm_end; k += 32) {
     W[asm_dst[k]] = Kval[asm_src[k]];
   }
-  ChildPre pre[kPreChildren];
+  const int32_t* esrc = ext.src + size_t(fm.ext_begin) * 32 + lane;
+  const int32_t* edst = ext.dst + size_t(fm.ext_begin) * 32 + lane;
+  int src[kExtBatch], dst[kExtBatch];
 #pragma unroll
-  for (int q = 0; q < kPreChildren; ++q) {
-    if (q < fm.n_child) {
-      pre[q] = preload_child(lane, child_idx[fm.child_begin + q], metas,
-                             rel_idx, updates);
-    }
-  }
-  // where the entries of the first children's update matrices go
-  int dst[kExtChildren][kExtPerLane];
-#pragma unroll
-  for (int c = 0; c < kExtChildren; ++c) {
-    if (c < fm.n_child) {
-      const int n_e = pre[c].mc * pre[c].mc;
-      const int32_t* map = ext_map + (pre[c].U - updates);
-#pragma unroll
-      for (int q = 0; q < kExtPerLane; ++q) {
-        const int e = lane + 32 * q;
-        dst[c][q] = e < n_e ? __ldg(map + e) : -1;
-      }
-    }
+  for (int q = 0; q < kExtBatch; ++q) {
+    const bool in = q < fm.ext_chunks;
+    src[q] = in ? __ldg(esrc + 32 * q) : 0;
+    dst[q] = in ? __ldg(edst + 32 * q) : -1;
+    // without a right-hand side the update vectors stay where they are
+    if (fr.rhs == nullptr && (src[q] & kExtVecTag)) dst[q] = -1;
   }
   __syncwarp();
   if (lane < np) {
     W[lane + lane * kFrontLd] += col_is_primal[c0 + lane] ? delta : -gamma;
   }
 
-  // ---- wait for the children, then extend-add their update matrices ---------
-  if (lane == 0) {
-    wait_children(dep, fm.n_child);
-    if (stamp) {
-      unsigned long long t;
-      asm volatile("mov.u64 %0, %globaltimer;" : "=l"(t));
-      *stamp = t;
-    }
+  // ---- wait for the children, then extend-add --------------------------------
+  wait_children_warp(lane, dep, fm.n_child);
+  if (stamp) {
+    unsigned long long t;
+    asm volatile("mov.u64 %0, %globaltimer;" : "=l"(t));
+    if (lane == 0) *stamp = t;
   }
   __syncwarp();
   {
-    // every load of the first children goes out before the first add
-    double u[kExtChildren][kExtPerLane];
-    double uv[kExtChildren];
+    double u[kExtBatch];
 #pragma unroll
-    for (int c = 0; c < kExtChildren; ++c) {
-      if (c < fm.n_child) {
-#pragma unroll
-        for (int q = 0; q < kExtPerLane; ++q) {
-          u[c][q] = dst[c][q] >= 0 ? __ldcg(pre[c].U + lane + 32 * q) : 0.0;
-        }
-        uv[c] = (fr.rhs != nullptr && lane < pre[c].mc)
-                    ? __ldcg(fr.uvecs + pre[c].rel_off + lane)
-                    : 0.0;
-      }
+    for (int q = 0; q < kExtBatch; ++q) {
+      const double* from = (src[q] & kExtVecTag)
+                               ? fr.uvecs + (src[q] & (kExtVecTag - 1))
+                               : updates + src[q];
+      u[q] = dst[q] >= 0 ? __ldcg(from) : 0.0;
     }
 #pragma unroll
-    for (int c = 0; c < kExtChildren; ++c) {
-      if (c < fm.n_child) {
-        // entries of ONE child land on distinct entries of the parent; the
-        // children follow each other in child order (fixed summation order)
+    for (int q = 0; q < kExtBatch; ++q) {
+      if (q < fm.ext_chunks) {
+        if (dst[q] >= 0) W[dst[q]] += u[q];
+        __syncwarp();  // the next chunk may belong to the next child
+      }
+    }
+  }
+  for (int q0 = kExtBatch; q0 < fm.ext_chunks; q0 += kExtBatch) {
+    int sx[kExtBatch], dx[kExtBatch];
+    double u[kExtBatch];
 #pragma unroll
-        for (int q = 0; q < kExtPerLane; ++q) {
-          if (dst[c][q] >= 0) W[dst[c][q]] += u[c][q];
-        }
-        const int mc = pre[c].mc;
-        if (fr.rhs != nullptr && lane < mc) col[pre[c].ri] += uv[c];
-        // the rare update matrix above 16 × 16: the rest of its entries
-        for (int e0 = 32 * kExtPerLane; e0 < mc * mc; e0 += 32 * kExtPerLane) {
-          const int32_t* map = ext_map + (pre[c].U - updates) + e0;
-          double ux[kExtPerLane];
-          int dx[kExtPerLane];
+    for (int q = 0; q < kExtBatch; ++q) {
+      const bool in = q0 + q < fm.ext_chunks;
+      sx[q] = in ? __ldg(esrc + 32 * (q0 + q)) : 0;
+      dx[q] = in ? __ldg(edst + 32 * (q0 + q)) : -1;
+      if (fr.rhs == nullptr && (sx[q] & kExtVecTag)) dx[q] = -1;
+    }
 #pragma unroll
-          for (int q = 0; q < kExtPerLane; ++q) {
-            const int e = e0 + lane + 32 * q;
-            dx[q] = e < mc * mc ? __ldg(map + lane + 32 * q) : -1;
-            ux[q] = dx[q] >= 0 ? __ldcg(pre[c].U + e) : 0.0;
-          }
+    for (int q = 0; q < kExtBatch; ++q) {
+      const double* from = (sx[q] & kExtVecTag)
+                               ? fr.uvecs + (sx[q] & (kExtVecTag - 1))
+                               : updates + sx[q];
+      u[q] = dx[q] >= 0 ? __ldcg(from) : 0.0;
+    }
 #pragma unroll
-          for (int q = 0; q < kExtPerLane; ++q) {
-            if (dx[q] >= 0) W[dx[q]] += ux[q];
-          }
-        }
+    for (int q = 0; q < kExtBatch; ++q) {
+      if (q0 + q < fm.ext_chunks) {
+        if (dx[q] >= 0) W[dx[q]] += u[q];
         __syncwarp();
       }
     }
   }
-  for (int ck = kExtChildren; ck < fm.n_child; ++ck) {
-    ChildPre cp;
-    if (ck < kPreChildren) {
-      // static indexing keeps pre[] in registers
-      cp = pre[kExtChildren];
-#pragma unroll
-      for (int q = kExtChildren + 1; q < kPreChildren; ++q) {
-        if (ck == q) cp = pre[q];
-      }
-    } else {
-      cp = preload_child(lane, child_idx[fm.child_begin + ck], metas, rel_idx,
-                         updates);
-    }
-    const int mc = cp.mc;
-    if (fr.rhs != nullptr && lane < mc) {
-      col[cp.ri] += __ldcg(fr.uvecs + cp.rel_off + lane);
-    }
-    const int32_t* map = ext_map + (cp.U - updates);
-    for (int e0 = 0; e0 < mc * mc; e0 += 32 * kExtPerLane) {
-      double ux[kExtPerLane];
-      int dx[kExtPerLane];
-#pragma unroll
-      for (int q = 0; q < kExtPerLane; ++q) {
-        const int e = e0 + lane + 32 * q;
-        dx[q] = e < mc * mc ? __ldg(map + e) : -1;
-        ux[q] = dx[q] >= 0 ? __ldcg(cp.U + e) : 0.0;
-      }
-#pragma unroll
-      for (int q = 0; q < kExtPerLane; ++q) {
-        if (dx[q] >= 0) W[dx[q]] += ux[q];
-      }
-    }
-    __syncwarp();
-  }
-
-  if (stamp && lane == 0) {  // [1] the children were seen, [2] they are added
+  if (stamp) {  // [1] the children were seen, [2] they are added
     unsigned long long t;
     asm volatile("mov.u64 %0, %globaltimer;" : "=l"(t));
-    stamp[1] = t;
+    if (lane == 0) stamp[1] = t;
   }
+  // (the lanes must ENTER the elimination together: a warp that arrives split,
+  // e.g. behind the lane-0 branch above, runs all of it lane group by lane
+  // group and only meets at the shuffles — measured 4× slower)
+  __syncwarp();
   // ---- elimination of the own columns + write-out ----------------------------
   double rhs_i = (fr.rhs != nullptr && lane < F) ? col[lane] : 0.0;
+#ifdef SLPB_DENSE_PROFILE
+  const long long call_t0 = clock64();
+#endif
   if (fused_arith) {
     ldlt_eliminate_front<true>(lane, F, np, m, W, side, D + c0,
                                panels + fm.panel_off, updates + fm.update_off,
@@ -258,6 +244,11 @@ __device__ __forceinline__ void ldlt_factor_front_warp(
                                 panels + fm.panel_off, updates + fm.update_off,
                                 local_stats, rhs_i);
   }
+#ifdef SLPB_DENSE_PROFILE
+  if (lane == 0 && clock64() - call_t0 > 16000) {
+    printf("   call F=%d np=%d children=%d: %lld cycles\n", F, np, fm.n_child, clock64() - call_t0);
+  }
+#endif
   if (fr.rhs != nullptr) {
     if (lane < np) {
       fr.xperm[c0 + lane] = rhs_i;
@@ -292,7 +283,7 @@ __device__ __forceinline__ void ldlt_forward_front_warp(
                              rel_idx, nullptr);
     }
   }
-  if (lane == 0) wait_children(dep, fm.n_child);
+  wait_children_warp(lane, dep, fm.n_child);
   __syncwarp();
   for (int ck = 0; ck < fm.n_child; ++ck) {
     ChildPre cp;
@@ -338,7 +329,7 @@ __device__ __forceinline__ void ldlt_backward_front_warp(
   }
   const double dinv_src = lane < np ? D[c0 + lane] : 1.0;
   const int row = (lane >= np && lane < F) ? rows_idx[fm.rows_off + lane] : 0;
-  if (lane == 0) wait_children(dep, 1);
+  wait_children_warp(lane, dep, 1);
   __syncwarp();
   double wi = 0.0;
   if (lane < np) {

@@ -196,7 +196,7 @@ struct slpb_solver {
   DevBuf<double> Kval, sigma, sinv, tvec, rhs, sol;
   // device: symbolic + factor
   DevBuf<int32_t> sy_super_first, sy_front_dim, sy_rows_idx, sy_child_idx,
-      sy_rel_idx, sy_asm_src, sy_asm_dst, sy_asm_dst_ld, sy_ext_map, sy_perm,
+      sy_rel_idx, sy_asm_src, sy_asm_dst, sy_asm_dst_ld, sy_ext_src, sy_ext_dst, sy_perm,
       sy_level_supers;
   DevBuf<int64_t> sy_rows_ptr, sy_panel_ptr, sy_update_ptr, sy_child_ptr,
       sy_rel_ptr, sy_asm_ptr;
@@ -208,6 +208,7 @@ struct slpb_solver {
   DevBuf<unsigned long long> tree_debug;
   bool use_tree = false;
   int factor_arith = SLPB_ARITH_REFERENCE;  // slpb_set_factor_arithmetic
+  std::vector<int32_t> ext_begin, ext_chunks;  // per front (analysis scratch)
   int tree_blocks = 0, solve_blocks = 0, tree_smem_doubles = 0;
   int factor_sel = 0;  // which variant of the last factorisation the solves use
   // forward substitution fused into the factorisation (slpb_prepare_rhs)
@@ -1048,7 +1049,7 @@ struct TreeView {
   const int32_t* rows_idx;
   const int32_t* asm_src;
   const int32_t* asm_dst;    // position in the warp's front (leading dim kFrontLd)
-  const int32_t* ext_map;    // update-matrix entry → position in the parent's front
+  ExtendList ext;            // per-front extend-add lists (ldlt_warp.cuh)
   const uint8_t* col_is_primal;
   const int32_t* perm;
   int32_t* sync;             // [0] ticket | fcount[ns] | fflag[ns] | bflag[ns]
@@ -1118,8 +1119,8 @@ k_factor_tree(TreeView T, const double* __restrict__ Kval, double delta,
     const FusedRhs fr{pair.rhs, T.perm, pair.xperm + size_t(v) * pair.dim,
                       pair.uvecs + v * pair.uvec_stride};
     ldlt_factor_front_warp(
-        lane, fm, T.metas, T.child_idx, T.rel_idx, T.asm_src, T.asm_dst,
-        T.ext_map, T.col_is_primal, Kval, v ? pair.delta1 : delta,
+        lane, fm, T.asm_src, T.asm_dst, T.ext, T.col_is_primal, Kval,
+        v ? pair.delta1 : delta,
         v ? pair.gamma1 : gamma, panels + v * pair.panel_stride,
         updates + v * pair.update_stride, D + v * pair.dim, W,
         &fcount[s], ls[warp], fr, pair.fused_arith != 0,
@@ -1811,7 +1812,7 @@ TreeView tree_view(slpb_solver* S) {
   T.rows_idx = S->sy_rows_idx.p;
   T.asm_src = S->sy_asm_src.p;
   T.asm_dst = S->sy_asm_dst_ld.p;
-  T.ext_map = S->sy_ext_map.p;
+  T.ext = ExtendList{S->sy_ext_src.p, S->sy_ext_dst.p};
   T.col_is_primal = S->sy_col_is_primal.p;
   T.perm = S->sy_perm.p;
   T.sync = S->tree_sync.p;
@@ -2437,6 +2438,58 @@ int slpb_analyze(slpb_solver* S, int ordering, const int32_t* perm,
   CU(S->uvecs.alloc(2 * size_t(Y.rel_ptr.back())));
   CU(S->xperm.alloc(2 * size_t(Y.dim)));
   CU(S->fstats.alloc(16));
+  // fronts of order ≤ 32: one warp per front, one launch per factorisation
+  S->use_tree = Y.max_front <= 32;
+  S->tree_smem_doubles = kFrontSmemDoubles;
+  if (S->use_tree) {
+    // the warp kernels keep a front with the fixed leading dimension kFrontLd:
+    // positions of the own KKT entries in that layout, and the per-front
+    // extend-add lists (ExtendList, ldlt_warp.cuh)
+    if (Y.update_size >= kExtVecTag || Y.rel_ptr.back() >= kExtVecTag) {
+      return fail(S, SLPB_ERR_UNSUPPORTED,
+                  "update-matrix storage exceeds 2^30 entries");
+    }
+    std::vector<int32_t> dst_ld(Y.asm_dst.size());
+    std::vector<int32_t> ext_src, ext_dst;
+    std::vector<int32_t> ext_begin(Y.n_super, 0), ext_chunks(Y.n_super, 0);
+    const int32_t rhs_at = kFrontLd * kFrontCols + kDenseSideDoubles;
+    for (int32_t q = 0; q < Y.n_super; ++q) {
+      const int32_t F = Y.front_dim[q];
+      for (int64_t k = Y.asm_ptr[q]; k < Y.asm_ptr[q + 1]; ++k) {
+        dst_ld[k] = Y.asm_dst[k] % F + (Y.asm_dst[k] / F) * kFrontLd;
+      }
+      ext_begin[q] = static_cast<int32_t>(ext_src.size() / 32);
+      for (int64_t ck = Y.child_ptr[q]; ck < Y.child_ptr[q + 1]; ++ck) {
+        const int32_t c = Y.child_idx[ck];
+        const int32_t mc = Y.front_dim[c] - (Y.super_first[c + 1] - Y.super_first[c]);
+        const int32_t* rel = Y.rel_idx.data() + Y.rel_ptr[c];
+        for (int32_t j = 0; j < mc; ++j) {
+          for (int32_t i = j; i < mc; ++i) {
+            ext_src.push_back(static_cast<int32_t>(Y.update_ptr[c] + i + int64_t(j) * mc));
+            ext_dst.push_back(rel[i] + rel[j] * kFrontLd);
+          }
+        }
+        for (int32_t i = 0; i < mc; ++i) {
+          ext_src.push_back(kExtVecTag | static_cast<int32_t>(Y.rel_ptr[c] + i));
+          ext_dst.push_back(rhs_at + rel[i]);
+        }
+        while (ext_src.size() % 32 != 0) {
+          ext_src.push_back(0);
+          ext_dst.push_back(-1);
+        }
+      }
+      ext_chunks[q] = static_cast<int32_t>(ext_src.size() / 32) - ext_begin[q];
+    }
+    if (ext_src.empty()) {
+      ext_src.assign(32, 0);
+      ext_dst.assign(32, -1);
+    }
+    CU(S->sy_asm_dst_ld.upload(dst_ld, S->stream));
+    CU(S->sy_ext_src.upload(ext_src, S->stream));
+    CU(S->sy_ext_dst.upload(ext_dst, S->stream));
+    S->ext_begin = std::move(ext_begin);
+    S->ext_chunks = std::move(ext_chunks);
+  }
   {
     std::vector<int32_t> nchild(Y.n_super);
     for (int32_t q = 0; q < Y.n_super; ++q) {
@@ -2460,6 +2513,9 @@ int slpb_analyze(slpb_solver* S, int ordering, const int32_t* perm,
       fm.rows_off = Y.rows_ptr[q];
       fm.parent = Y.super_parent[q];
       fm.pad = 0;
+      fm.ext_begin = S->use_tree ? S->ext_begin[q] : 0;
+      fm.ext_chunks = S->use_tree ? S->ext_chunks[q] : 0;
+      fm.pad2 = fm.pad3 = 0;
     }
     CU(S->sy_metas.upload(metas, S->stream));
     if (std::getenv("SLPB_TREE_DEBUG")) {
@@ -2469,31 +2525,6 @@ int slpb_analyze(slpb_solver* S, int ordering, const int32_t* perm,
     // [0] ticket | 3 × n_super dependency words | [1 + 3 n_super + v] "variant v
     // met an exactly zero pivot" flags of the factor launch
     CU(S->tree_sync.alloc(3 + 3 * size_t(Y.n_super)));
-  }
-  // fronts of order ≤ 32: one warp per front, one launch per factorisation
-  S->use_tree = Y.max_front <= 32;
-  S->tree_smem_doubles = kFrontSmemDoubles;
-  if (S->use_tree) {
-    // the warp kernels keep a front with the fixed leading dimension kFrontLd:
-    // positions of the own KKT entries, and of every update-matrix entry in
-    // the parent's front (−1: upper triangle, not stored)
-    std::vector<int32_t> dst_ld(Y.asm_dst.size());
-    std::vector<int32_t> ext(static_cast<size_t>(Y.update_size), -1);
-    for (int32_t q = 0; q < Y.n_super; ++q) {
-      const int32_t F = Y.front_dim[q];
-      for (int64_t k = Y.asm_ptr[q]; k < Y.asm_ptr[q + 1]; ++k) {
-        dst_ld[k] = Y.asm_dst[k] % F + (Y.asm_dst[k] / F) * kFrontLd;
-      }
-      if (Y.super_parent[q] < 0) continue;
-      const int32_t mc = F - (Y.super_first[q + 1] - Y.super_first[q]);
-      const int32_t* rel = Y.rel_idx.data() + Y.rel_ptr[q];
-      int32_t* e = ext.data() + Y.update_ptr[q];
-      for (int32_t j = 0; j < mc; ++j) {
-        for (int32_t i = j; i < mc; ++i) e[i + j * mc] = rel[i] + rel[j] * kFrontLd;
-      }
-    }
-    CU(S->sy_asm_dst_ld.upload(dst_ld, S->stream));
-    CU(S->sy_ext_map.upload(ext, S->stream));
   }
   {
     const int tree_smem =

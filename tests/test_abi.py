@@ -134,3 +134,30 @@ def test_product_does_not_reference_the_oracle():
                              r'liboracle|pyoracle', text):
                     bad.append(os.path.join(dp, f))
     assert not bad, bad
+
+
+def test_device_code_is_sm100a_with_tensor_core_and_tma_instructions():
+    """What the cubin of libslpb.so contains (cuobjdump runs without a GPU):
+    sm_100a code only; FP64 tensor-core products (DMMA.8x8x4: the rank-4
+    updates of dense fronts, csrc/ldlt_dense.cuh) inside the factorisation
+    kernel; 1-D TMA bulk copies + mbarriers (UBLKCP, SYNCS) inside the autodiff
+    sweep (the instruction stream, slpb.cu TmaStream)."""
+    import shutil
+    import subprocess
+    exe = shutil.which("cuobjdump") or "/usr/local/cuda/bin/cuobjdump"
+    if not os.path.exists(exe):
+        pytest.skip("cuobjdump is not installed")
+    lib = sb.LIB_DEVICE
+    elf = subprocess.run([exe, "-lelf", lib], capture_output=True, text=True).stdout
+    assert "sm_100a" in elf and "sm_90" not in elf and "sm_80" not in elf
+    sass = subprocess.run([exe, "-sass", lib], capture_output=True, text=True).stdout
+    current, found = None, {}
+    for line in sass.splitlines():
+        if "Function :" in line:
+            current = line.split("Function :")[1].strip()
+        for mnemonic in ("DMMA", "UBLKCP", "SYNCS"):
+            if mnemonic in line and current:
+                found.setdefault(mnemonic, set()).add(current)
+    assert any("k_factor_tree" in f for f in found.get("DMMA", ())), found.get("DMMA")
+    assert any("k_ad_sweep" in f for f in found.get("UBLKCP", ()))
+    assert any("k_ad_sweep" in f for f in found.get("SYNCS", ()))
