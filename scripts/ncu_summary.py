@@ -27,6 +27,8 @@ KEYS = [
     "smsp__average_warps_issue_stalled_short_scoreboard_per_issue_active.ratio",
     "smsp__average_warps_issue_stalled_wait_per_issue_active.ratio",
     "smsp__issue_active.avg.pct_of_peak_sustained_active",
+    # < 32: instructions issued for a part of the warp (divergence / predication)
+    "smsp__thread_inst_executed_per_inst_executed.ratio",
 ]
 
 

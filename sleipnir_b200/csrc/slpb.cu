@@ -185,7 +185,7 @@ struct slpb_solver {
   DevGather gv, gd;
   DevBuf<double> vstage, dstage;
   // device: state
-  DevBuf<double> leaf_cur, leaf_trial, d_c;
+  DevBuf<double> leaf_cur, leaf_trial, d_c, inv_d_c;  // inv_d_c = RN(1 / d_c)
   DevBuf<double> x, s, y, z, tx, ts, ty, tz;
   DevBuf<double> vals_cur, vals_trial, dvals;
   DevBuf<int32_t> ae_colptr, ae_rowidx, ai_colptr, ai_rowidx;
@@ -695,8 +695,12 @@ k_kkt_stats(CscView Ae, CscView Ai, const double* __restrict__ g,
             const double* __restrict__ c_e, const double* __restrict__ c_i,
             const double* __restrict__ x, const double* __restrict__ s,
             const double* __restrict__ y, const double* __restrict__ z,
-            const double* __restrict__ d_c, double d_f, double mu, int n,
+            const double* __restrict__ d_c,
+            const double* __restrict__ inv_d_c, double d_f, double mu, int n,
             int me, int mi, RedBuf rb, double* __restrict__ out) {
+  // (inv_d_c[r] = RN(1 / d_c[r]), computed once when the scaling is set: the
+  // reference divides per entry, kkt_error.hpp:150-190 — same value, no
+  // division inside the column loops)
   const double inv_d_f = 1.0 / d_f;
   // 0 r_inf 1 r_l1 2 y_l1 3 z_l1 4 sz_min 5 sz_max 6 sz_mu_l1 7 ce_inf 8 ce_l1
   // 9 cis_inf 10 cis_l1 11 u_r_inf 12 u_y_l1 13 u_z_l1 14 u_sz_min 15 u_sz_max
@@ -719,7 +723,7 @@ k_kkt_stats(CscView Ae, CscView Ai, const double* __restrict__ g,
       const double a = Ae.val[k];
       aty += a * y[r];
       const double dc = d_c[r];
-      u_aty += ((1.0 / dc) * a) * (dc * y[r] * inv_d_f);
+      u_aty += (inv_d_c[r] * a) * (dc * y[r] * inv_d_f);
       atc += a * c_e[r];
     }
     for (int k = Ai.colptr[c]; k < Ai.colptr[c + 1]; ++k) {
@@ -727,7 +731,7 @@ k_kkt_stats(CscView Ae, CscView Ai, const double* __restrict__ g,
       const double a = Ai.val[k];
       atz += a * z[r];
       const double dc = d_c[me + r];
-      u_atz += ((1.0 / dc) * a) * (dc * z[r] * inv_d_f);
+      u_atz += (inv_d_c[me + r] * a) * (dc * z[r] * inv_d_f);
       atcp += a * fmin(c_i[r], 0.0);
     }
     const double r = g[c] - aty - atz;
@@ -747,12 +751,12 @@ k_kkt_stats(CscView Ae, CscView Ai, const double* __restrict__ g,
     v[7] = fmax(v[7], fabs(c));
     v[8] += fabs(c);
     v[12] += fabs(dc * yv * inv_d_f);
-    v[16] = fmax(v[16], fabs((1.0 / dc) * c));
+    v[16] = fmax(v[16], fabs(inv_d_c[i] * c));
     v[19] += c * c;
   }
   for (int i = t0; i < mi; i += stride) {
     const double c = c_i[i], sv = s[i], zv = z[i], dc = d_c[me + i];
-    const double inv = 1.0 / dc;
+    const double inv = inv_d_c[me + i];
     v[3] += fabs(zv);
     const double sz = sv * zv;
     v[4] = fmin(v[4], sz);
@@ -1753,7 +1757,7 @@ int kkt_stats_enqueue(slpb_solver* S, const double* c_e, const double* c_i,
                       const double* z, double mu, int offset) {
   k_kkt_stats<<<red_blocks(S->n + S->mi), kReduceThreads, 0, S->stream>>>(
       ae_view(S), ai_view(S), S->dvals.p + S->ad.off_g, c_e, c_i, x, s, y, z,
-      S->d_c.p, S->d_f, mu, S->n, S->me, S->mi, red_buf(S),
+      S->d_c.p, S->inv_d_c.p, S->d_f, mu, S->n, S->me, S->mi, red_buf(S),
       S->d_results.p + offset);
   ++S->counters.kernel_launches;
   CU(cudaGetLastError());
@@ -2316,6 +2320,7 @@ int slpb_finalize(slpb_solver* S) {
   CU(S->leaf_trial.zero(S->stream));
   std::vector<double> ones(me + mi, 1.0);
   CU(S->d_c.upload(ones, S->stream));
+  CU(S->inv_d_c.upload(ones, S->stream));
   S->d_f = 1.0;
   for (auto* b : {&S->x, &S->tx, &S->px, &S->spx}) CU(b->alloc(n));
   for (auto* b : {&S->y, &S->ty, &S->py, &S->spy, &S->ce_soc}) CU(b->alloc(me));
@@ -2392,6 +2397,10 @@ int slpb_set_scaling(slpb_solver* S, double d_f, const double* d_ce,
   std::copy(d_ci, d_ci + S->mi, d.begin() + S->me);
   if (!d.empty()) {
     CU(cudaMemcpyAsync(S->d_c.p, d.data(), d.size() * sizeof(double),
+                       cudaMemcpyHostToDevice, S->stream));
+    std::vector<double> inv(d.size());
+    for (size_t i = 0; i < d.size(); ++i) inv[i] = 1.0 / d[i];
+    CU(cudaMemcpyAsync(S->inv_d_c.p, inv.data(), inv.size() * sizeof(double),
                        cudaMemcpyHostToDevice, S->stream));
     CU(cudaStreamSynchronize(S->stream));
   }
