@@ -1162,6 +1162,23 @@ k_factor_tree(TreeView T, const double* __restrict__ Kval, double delta,
   }
 }
 
+/// Prepares a factor launch in one go: the inertia statistics of both variants
+/// (zero counts, min|D| = +inf) and, for the tree kernel, the ticket, the
+/// dependency counters of both variants and the "variant is dead" flags.
+__global__ void k_init_factor(int32_t* __restrict__ stats, int32_t* sync,
+                              int ns, int zero_sync) {
+  const int i = blockIdx.x * blockDim.x + threadIdx.x;
+  if (i < 16) {
+    // per variant: n_pos n_neg n_zero zero_pivot | +inf bits | pad
+    const int k = i & 7;
+    stats[i] = k == 5 ? 0x7ff00000 : 0;
+  }
+  if (zero_sync) {
+    if (i < 1 + 2 * ns) sync[i] = 0;
+    if (i < 2) sync[1 + 3 * ns + i] = 0;
+  }
+}
+
 /// Prepares the ticket/flag words of k_solve_tree. With skip_forward the
 /// forward substitution was carried by the factorisation: every "forward
 /// done" flag is already set. fcount_init (optional): children of each front
@@ -2785,20 +2802,15 @@ int factor_impl(slpb_solver* S, int n_variants, const double* delta,
     return group_factor(S, n_variants, delta, gamma, info);
   }
   CU(cudaEventRecord(S->ev[6], S->stream));
-  // stats per variant: n_pos n_neg n_zero zero_pivot | min|D| bits (+inf)
+  // stats per variant: n_pos n_neg n_zero zero_pivot | min|D| bits (+inf);
+  // ticket, dependency counters and dead flags of the tree kernel
   {
-    int32_t init[16] = {};
-    const double inf = INFINITY;
-    std::memcpy(&init[4], &inf, 8);
-    std::memcpy(&init[12], &inf, 8);
-    CU(cudaMemcpyAsync(S->fstats.p, init, sizeof(init), cudaMemcpyHostToDevice,
-                       S->stream));
+    const int words = S->use_tree ? 1 + 2 * Y.n_super : 16;
+    k_init_factor<<<blocks_for(words, 256), 256, 0, S->stream>>>(
+        S->fstats.p, S->tree_sync.p, Y.n_super, S->use_tree ? 1 : 0);
+    ++S->counters.kernel_launches;
   }
   if (S->use_tree) {
-    CU(cudaMemsetAsync(S->tree_sync.p, 0, (1 + 2 * size_t(Y.n_super)) * 4,
-                       S->stream));
-    CU(cudaMemsetAsync(S->tree_sync.p + 1 + 3 * size_t(Y.n_super), 0, 2 * 4,
-                       S->stream));
     const TreeView T = tree_view(S);
     const int smem =
         kTreeWarps * S->tree_smem_doubles * static_cast<int>(sizeof(double));
@@ -2872,12 +2884,14 @@ int factor_impl(slpb_solver* S, int n_variants, const double* delta,
   CU(cudaEventRecord(S->ev[7], S->stream));
   S->pending[3] = true;
   CU(cudaGetLastError());
-  int32_t host_stats[16];
-  CU(cudaMemcpyAsync(host_stats, S->fstats.p, sizeof(host_stats),
+  // (into the pinned result buffer: a pageable destination would be staged)
+  int32_t* host_stats = reinterpret_cast<int32_t*>(S->h_results);
+  static_assert(kResultDoubles * sizeof(double) >= 16 * sizeof(int32_t));
+  CU(cudaMemcpyAsync(host_stats, S->fstats.p, 16 * sizeof(int32_t),
                      cudaMemcpyDeviceToHost, S->stream));
   CU(cudaStreamSynchronize(S->stream));
   harvest_timers(S);
-  S->counters.d2h_bytes += sizeof(host_stats);
+  S->counters.d2h_bytes += 16 * sizeof(int32_t);
   for (int v = 0; v < n_variants; ++v) {
     info[v].n_pos = host_stats[8 * v + 0];
     info[v].n_neg = host_stats[8 * v + 1];

@@ -427,6 +427,8 @@ ExitStatus interior_point(
                                           hz.data()));
   };
 
+  // (development switch, read once per solve — not inside the Newton loop)
+  const bool fused_forward = std::getenv("SLPB_NO_FUSED_FORWARD") == nullptr;
   const auto loop_start_time = std::chrono::steady_clock::now();
   struct LoopTimer {
     SolveTrace* t;
@@ -496,7 +498,7 @@ ExitStatus interior_point(
     // lhs assembly + factorisation with inertia correction (:426-465)
     // The right-hand side does not depend on δ/γ: build it first so that the
     // factorisation carries its forward substitution (slpb_prepare_rhs).
-    if (!std::getenv("SLPB_NO_FUSED_FORWARD")) {
+    if (fused_forward) {
       SLP_DEVICE_CALL(dev, slpb_prepare_rhs(dev, mu));
     }
     if (!solver.compute() && kind != SolverKind::NEWTON) {
