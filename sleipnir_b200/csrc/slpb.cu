@@ -248,6 +248,12 @@ struct slpb_solver {
   int group_slot = -1;
   // timing
   cudaEvent_t ev[10] = {};
+  // side streams for the launches of one sweep (different program classes are
+  // independent of each other): fork/join around run_sweep
+  bool serial_sweeps = std::getenv("SLPB_SERIAL_SWEEPS") != nullptr;
+  static constexpr int kSideStreams = 3;
+  cudaStream_t side[kSideStreams] = {};
+  cudaEvent_t fork_ev = nullptr, join_ev[kSideStreams] = {};
   float last_ms[5] = {0, 0, 0, 0, 0};
   slpb_timers timers{};
   bool pending[5] = {false, false, false, false, false};
@@ -1595,10 +1601,30 @@ int run_sweep(slpb_solver* S, const DevProgramSet& d, const double* leaf,
   const AdTasks A{d.blob.p,      d.prog_offset.p, d.task_prog.p,
                   d.task_count.p, d.task_lanes.p, d.task_bind.p,
                   d.task_bindings.p};
-  for (const auto& L : d.launches) {
-    k_ad_sweep<<<L.n_tasks, L.threads, L.smem_bytes, S->stream>>>(
-        A, L.first_task, leaf, stage);
+  // The launches of a sweep (one per shape of program class) are independent:
+  // the first stays on the solver's stream, the others go to side streams
+  // between a fork and a join, so that the small grids of the boundary rows
+  // overlap the big one instead of queueing behind it.
+  const size_t n_launch = d.launches.size();
+  const bool fork = n_launch > 1 && !S->serial_sweeps;
+  if (fork) CU(cudaEventRecord(S->fork_ev, S->stream));
+  for (size_t i = 0; i < n_launch; ++i) {
+    const auto& L = d.launches[i];
+    cudaStream_t st = S->stream;
+    if (fork && i > 0) {
+      st = S->side[(i - 1) % slpb_solver::kSideStreams];
+      CU(cudaStreamWaitEvent(st, S->fork_ev, 0));
+    }
+    k_ad_sweep<<<L.n_tasks, L.threads, L.smem_bytes, st>>>(A, L.first_task,
+                                                            leaf, stage);
     ++S->counters.kernel_launches;
+  }
+  if (fork) {
+    const size_t used = std::min<size_t>(n_launch - 1, slpb_solver::kSideStreams);
+    for (size_t i = 0; i < used; ++i) {
+      CU(cudaEventRecord(S->join_ev[i], S->side[i]));
+      CU(cudaStreamWaitEvent(S->stream, S->join_ev[i], 0));
+    }
   }
   CU(cudaGetLastError());
   return SLPB_OK;
@@ -2144,6 +2170,15 @@ int slpb_create(int device, slpb_solver** out) {
   for (auto& e : S->ev) {
     if (cudaEventCreate(&e) != cudaSuccess) return SLPB_ERR_CUDA;
   }
+  for (int i = 0; i < slpb_solver::kSideStreams; ++i) {
+    if (cudaStreamCreateWithFlags(&S->side[i], cudaStreamNonBlocking) != cudaSuccess ||
+        cudaEventCreateWithFlags(&S->join_ev[i], cudaEventDisableTiming) != cudaSuccess) {
+      return SLPB_ERR_CUDA;
+    }
+  }
+  if (cudaEventCreateWithFlags(&S->fork_ev, cudaEventDisableTiming) != cudaSuccess) {
+    return SLPB_ERR_CUDA;
+  }
   *out = S.release();
   return SLPB_OK;
 }
@@ -2169,6 +2204,14 @@ void slpb_destroy(slpb_solver* S) {
   for (auto& e : S->cev) {
     if (e) cudaEventDestroy(e);
   }
+  for (int i = 0; i < slpb_solver::kSideStreams; ++i) {
+    if (S->side[i]) {
+      cudaStreamSynchronize(S->side[i]);
+      cudaStreamDestroy(S->side[i]);
+    }
+    if (S->join_ev[i]) cudaEventDestroy(S->join_ev[i]);
+  }
+  if (S->fork_ev) cudaEventDestroy(S->fork_ev);
   lap("events");
   if (S->comm && nccl_api().ok) nccl_api().CommDestroy(S->comm);
   if (S->h_results) pinned_pool().give_back(S->h_results);
