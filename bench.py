@@ -493,9 +493,9 @@ def main():
             kt, dtt = steady_rate(trt, args.warmup, args.steps)
             dtt = max_over_ranks(dtt)
             timt, cntt = Pt.timers(), Pt.counters()
-            nl = max(timt["factor"]["count"], 1)
+            nl = max(timt["factor"]["launches"], 1)
             tensor = {"value": world * kt / dtt, "unit": UNIT, "steps": kt,
-                      "factor_ms_per_launch": timt["factor"]["total_ms"] / nl,
+                      "factor_ms_per_launch": timt["factor"]["mean_ms"],
                       "factorizations_per_launch": cntt["factorizations_completed"] / nl}
             Pt.close()
         # (2) the solve as a user runs it: Problem::solve() with default Options
@@ -537,14 +537,16 @@ def main():
     nnz_l_amd = amd_nnz_l(sb, N, local_rank)
     fac_bytes = 12 * sym["nnz_kkt"] + 12 * sym["nnz_l"] + 8 * sym["dim"]
     fac_bytes_amd = 12 * sym["nnz_kkt"] + 12 * nnz_l_amd + 8 * sym["dim"]
-    n_launch = max(tim["factor"]["count"], 1)
-    fac_ms = tim["factor"]["total_ms"] / n_launch
+    # (the device timers sample one run in eight: mean_ms is over the sampled
+    #  runs, `launches` counts all of them)
+    n_launch = max(tim["factor"]["launches"], 1)
+    fac_ms = tim["factor"]["mean_ms"]
     fac_per_launch = cnt["factorizations_completed"] / n_launch
     achieved = (fac_bytes * fac_per_launch) / (fac_ms * 1e-3) / 1e9 if fac_ms > 0 else 0.0
     achieved_amd = (fac_bytes_amd * fac_per_launch) / (fac_ms * 1e-3) / 1e9 if fac_ms > 0 else 0.0
     peak = float(peaks["hbm_gbs"])
-    phase_ms = {k_: (v["total_ms"] / max(v["count"], 1)) for k_, v in tim.items()}
-    per_step_ms = {k_: v["total_ms"] / iters for k_, v in tim.items()}
+    phase_ms = {k_: v["mean_ms"] for k_, v in tim.items()}
+    per_step_ms = {k_: v["mean_ms"] * v["launches"] / iters for k_, v in tim.items()}
     traffic = {}
     tpath = os.path.join(ROOT, "profiles", "traffic.json")
     if os.path.exists(tpath):
@@ -595,7 +597,7 @@ def main():
             "symbolic": sym,
             "per_step": {
                 "factorizations": sum(r.factorizations for r in tr) / iters,
-                "factor_launches": tim["factor"]["count"] / iters,
+                "factor_launches": tim["factor"]["launches"] / iters,
                 "solves": sum(r.solves for r in tr) / iters,
                 "trial_points": sum(r.trials for r in tr) / iters},
             "device_ms_per_launch_group": phase_ms,

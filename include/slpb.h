@@ -494,13 +494,17 @@ typedef struct slpb_comm_stats {
 } slpb_comm_stats;
 int slpb_get_comm_stats(slpb_solver* s, slpb_comm_stats* out);
 
-/* Device time accumulated per phase since the handle was created, measured
- * with CUDA events on the handle's stream (milliseconds) and the number of
- * times each phase ran: [0] eval(full) [1] eval(values) [2] assemble
- * [3] factor [4] solve. */
+/* Device time per phase since the handle was created, measured with CUDA
+ * events on the handle's stream (milliseconds): [0] eval(full) [1] eval(values)
+ * [2] assemble [3] factor [4] solve. Timing events disturb back-to-back
+ * kernels, so the phases are SAMPLED (one run in SLPB_TIMER_EVERY, default 8;
+ * SLPB_NO_TIMERS=1 switches them off): total_ms and count cover the sampled
+ * runs (total_ms / count = mean device time of a run), launches counts every
+ * run of the phase. */
 typedef struct slpb_timers {
   double total_ms[5];
   int64_t count[5];
+  int64_t launches[5];
 } slpb_timers;
 int slpb_get_timers(slpb_solver* s, slpb_timers* out);
 

@@ -9,6 +9,8 @@ import numpy as np
 
 ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
 sys.path.insert(0, ROOT)
+import os as _os
+_os.environ.setdefault("SLPB_TIMER_EVERY", "1")  # time every launch
 import sleipnir_b200 as sb  # noqa: E402
 
 N = int(sys.argv[1]) if len(sys.argv) > 1 else 5000

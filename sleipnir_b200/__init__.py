@@ -704,10 +704,15 @@ class Problem:
         return dict(zip(keys, (int(v) for v in out)))
 
     def timers(self):
-        out = np.zeros(10)
+        """Device time of the kernel groups of the last solve: total_ms over
+        the `count` SAMPLED runs (one in SLPB_TIMER_EVERY, default 8),
+        `launches` = all runs; mean_ms = total_ms / count."""
+        out = np.zeros(15)
         self.H.slpbh_timers(self.h, _d(out))
         names = ("eval_full", "eval_values", "assemble", "factor", "solve")
-        return {k: {"total_ms": float(out[i]), "count": int(out[5 + i])}
+        return {k: {"total_ms": float(out[i]), "count": int(out[5 + i]),
+                    "launches": int(out[10 + i]),
+                    "mean_ms": float(out[i]) / max(int(out[5 + i]), 1)}
                 for i, k in enumerate(names)}
 
     def comm_stats(self):

@@ -566,7 +566,11 @@ struct Compiler {
     }
     int32_t n_workers = 1;
     while (n_workers < 16 && n_workers < widest) n_workers <<= 1;
-    constexpr int32_t kChainCap = 24;  // weight a worker takes per super-level
+    // weight a worker takes per super-level (development switch SLPB_CHAIN_CAP)
+    static const int32_t kChainCap = [] {
+      const char* e = std::getenv("SLPB_CHAIN_CAP");
+      return e ? std::max(1, std::atoi(e)) : 24;
+    }();
     struct Loads {
       int32_t W;
       std::vector<std::vector<int32_t>> load;  // [super-level][worker]
@@ -683,6 +687,22 @@ struct Compiler {
       std::stable_sort(lv.begin(), lv.end(), [&](int32_t x, int32_t y) {
         return rev_worker[x] < rev_worker[y];
       });
+    }
+    if (std::getenv("SLPB_COMPILE_TIMING")) {
+      // critical path of the schedule: Σ over super-levels of the heaviest list
+      int64_t crit = 0, total = 0;
+      for (const auto& lv : rev_levels) {
+        std::vector<int64_t> load(n_workers, 0);
+        for (int32_t i : lv) load[rev_worker[i]] += 1 + visits[i].contribs.size();
+        crit += *std::max_element(load.begin(), load.end());
+        for (int64_t l : load) total += l;
+      }
+      std::fprintf(stderr,
+                   "[slpb compile] schedule: %d workers, %zu forward + %zu reverse "
+                   "super-levels, reverse weight %lld, critical path %lld "
+                   "(perfect balance: %lld)\n",
+                   n_workers, fwd_levels.size(), rev_levels.size(),
+                   (long long)total, (long long)crit, (long long)(total / n_workers));
     }
 
     // --- physical slot allocation (liveness over the level schedule) ---------

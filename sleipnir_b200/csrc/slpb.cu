@@ -251,6 +251,18 @@ struct slpb_solver {
   // side streams for the launches of one sweep (different program classes are
   // independent of each other): fork/join around run_sweep
   bool serial_sweeps = std::getenv("SLPB_SERIAL_SWEEPS") != nullptr;
+  // per-phase device timers (CUDA events around the kernel groups;
+  // slpb_get_timers). Timing events are not free — ten records per Newton
+  // iteration cost 9 % of the step (gaps between back-to-back kernels) — so
+  // every group is SAMPLED: one launch in timer_every carries events, the
+  // averages (total_ms / count) are over the sampled launches.
+  int timer_every = [] {
+    if (std::getenv("SLPB_NO_TIMERS")) return 0;
+    const char* e = std::getenv("SLPB_TIMER_EVERY");
+    return e ? std::max(1, std::atoi(e)) : 8;
+  }();
+  unsigned timer_tick[5] = {0, 0, 0, 0, 0};
+  bool timing_now[5] = {false, false, false, false, false};
   static constexpr int kSideStreams = 3;
   cudaStream_t side[kSideStreams] = {};
   cudaEvent_t fork_ev = nullptr, join_ev[kSideStreams] = {};
@@ -1700,6 +1712,22 @@ int run_gather(slpb_solver* S, const DevGather& d, const double* stage,
 
 /// After a stream synchronisation: folds the event pairs that were recorded
 /// since the last harvest into the per-phase timers.
+/// Start / end of timed kernel group w (0 eval_full, 1 eval_values, 2 assemble,
+/// 3 factor, 4 solve): events are recorded for one launch in timer_every, and
+/// never while the previous sample of the group has not been read yet.
+cudaError_t timer_begin(slpb_solver* S, int w) {
+  ++S->timers.launches[w];
+  S->timing_now[w] = S->timer_every > 0 && !S->pending[w] &&
+                     (S->timer_tick[w]++ % unsigned(S->timer_every)) == 0;
+  return S->timing_now[w] ? cudaEventRecord(S->ev[2 * w], S->stream) : cudaSuccess;
+}
+cudaError_t timer_end(slpb_solver* S, int w) {
+  if (!S->timing_now[w]) return cudaSuccess;
+  S->timing_now[w] = false;
+  S->pending[w] = true;
+  return cudaEventRecord(S->ev[2 * w + 1], S->stream);
+}
+
 void harvest_timers(slpb_solver* S) {
   harvest_comm_timers(S);
   for (int w = 0; w < 5; ++w) {
@@ -1737,26 +1765,24 @@ CscView ai_view(slpb_solver* S) {
 
 /// Values (f, c_e, c_i) of the point whose leaves are in `leaf`.
 int eval_values(slpb_solver* S, const double* leaf, double* vals) {
-  CU(cudaEventRecord(S->ev[2], S->stream));
+  CU(timer_begin(S, 1));
   int rc = run_sweep(S, S->pv, leaf, S->vstage.p);
   if (rc) return rc;
   rc = run_gather(S, S->gv, S->vstage.p, vals);
   if (rc) return rc;
-  CU(cudaEventRecord(S->ev[3], S->stream));
-  S->pending[1] = true;
+  CU(timer_end(S, 1));
   ++S->counters.evals_values;
   return SLPB_OK;
 }
 
 int eval_derivs(slpb_solver* S, const double* leaf) {
-  CU(cudaEventRecord(S->ev[0], S->stream));
+  CU(timer_begin(S, 0));
   int rc = S->world > 1 ? run_sweep_sharded(S, S->pd, leaf, S->dstage.p)
                         : run_sweep(S, S->pd, leaf, S->dstage.p);
   if (rc) return rc;
   rc = run_gather(S, S->gd, S->dstage.p, S->dvals.p);
   if (rc) return rc;
-  CU(cudaEventRecord(S->ev[1], S->stream));
-  S->pending[0] = true;
+  CU(timer_end(S, 0));
   ++S->counters.evals_full;
   return SLPB_OK;
 }
@@ -1992,7 +2018,7 @@ int launch_solve(slpb_solver* S, bool skip_forward) {
     harvest_timers(S);
     return group_solve(S);  // forward + backward in the batched launch → S->sol
   }
-  CU(cudaEventRecord(S->ev[8], S->stream));
+  CU(timer_begin(S, 4));
   if (S->use_tree) {
     const int sel = S->factor_sel;
     const double* panels = S->panels.p + sel * Y.panel_size;
@@ -2063,8 +2089,7 @@ int launch_solve(slpb_solver* S, bool skip_forward) {
         S->xperm.p, S->sy_perm.p, S->dim, S->sol.p);
     S->counters.kernel_launches += 2 * Y.n_levels + 1;
   }
-  CU(cudaEventRecord(S->ev[9], S->stream));
-  S->pending[4] = true;
+  CU(timer_end(S, 4));
   CU(cudaGetLastError());
   ++S->counters.solves;
   return SLPB_OK;
@@ -2820,7 +2845,7 @@ int factor_impl(slpb_solver* S, int n_variants, const double* delta,
   CU(cudaSetDevice(S->device));
   const Symbolic& Y = S->sym;
   if (reassemble) {
-    CU(cudaEventRecord(S->ev[4], S->stream));
+    CU(timer_begin(S, 2));
     if (S->mi > 0) {
       k_sigma_t<<<blocks_for(S->mi, 256), 256, 0, S->stream>>>(
           S->s.p, S->z.p, S->vals_cur.p + 1 + S->me, nullptr, 0.0, 0, S->mi,
@@ -2834,8 +2859,7 @@ int factor_impl(slpb_solver* S, int n_variants, const double* delta,
         S->dvals.p + S->ad.off_ae, S->dvals.p + S->ad.off_ai, S->sigma.p, nnz,
         S->Kval.p);
     ++S->counters.kernel_launches;
-    CU(cudaEventRecord(S->ev[5], S->stream));
-    S->pending[2] = true;
+    CU(timer_end(S, 2));
   }
   if (S->group != nullptr) {
     // member of a batching group: the lhs values are ready on this stream;
@@ -2844,7 +2868,7 @@ int factor_impl(slpb_solver* S, int n_variants, const double* delta,
     harvest_timers(S);
     return group_factor(S, n_variants, delta, gamma, info);
   }
-  CU(cudaEventRecord(S->ev[6], S->stream));
+  CU(timer_begin(S, 3));
   // stats per variant: n_pos n_neg n_zero zero_pivot | min|D| bits (+inf);
   // ticket, dependency counters and dead flags of the tree kernel
   {
@@ -2924,8 +2948,7 @@ int factor_impl(slpb_solver* S, int n_variants, const double* delta,
       S->counters.kernel_launches += Y.n_levels;
     }
   }
-  CU(cudaEventRecord(S->ev[7], S->stream));
-  S->pending[3] = true;
+  CU(timer_end(S, 3));
   CU(cudaGetLastError());
   // (into the pinned result buffer: a pageable destination would be staged)
   int32_t* host_stats = reinterpret_cast<int32_t*>(S->h_results);

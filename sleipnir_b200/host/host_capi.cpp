@@ -354,12 +354,13 @@ void slpbh_counters(void* h, int64_t* out) {
   std::memcpy(out, v, sizeof(v));
 }
 
-/// out[10]: total_ms[5] then count[5] of slpb_timers.
+/// out[15]: total_ms[5], count[5] (sampled runs), launches[5] of slpb_timers.
 void slpbh_timers(void* h, double* out) {
   const auto& t = H(h)->problem->last_timers();
   for (int i = 0; i < 5; ++i) {
     out[i] = t.total_ms[i];
     out[5 + i] = static_cast<double>(t.count[i]);
+    out[10 + i] = static_cast<double>(t.launches[i]);
   }
 }
 
