@@ -243,6 +243,7 @@ struct slpb_solver {
   cudaEvent_t cev[6] = {};
   bool cpending[3] = {false, false, false};
   int64_t comm_timed[3] = {0, 0, 0};  // calls that were timed
+  bool comm_warm[3] = {false, false, false};  // first sample of a kind dropped
   // dynamic batching with other solvers of the same pattern (group.cuh)
   slpb_group* group = nullptr;
   int group_slot = -1;
@@ -1921,7 +1922,14 @@ void harvest_comm_timers(slpb_solver* S) {
     float ms = 0.0f;
     if (cudaEventElapsedTime(&ms, S->cev[2 * w], S->cev[2 * w + 1]) ==
         cudaSuccess) {
-      S->comm_stats.total_ms[w] += ms;
+      if (!S->comm_warm[w]) {
+        // the first collective of a kind (a new message size) pays NCCL's
+        // one-time buffer / protocol set-up: not part of the steady state
+        S->comm_warm[w] = true;
+        --S->comm_timed[w];
+      } else {
+        S->comm_stats.total_ms[w] += ms;
+      }
     } else {
       cudaGetLastError();
     }
