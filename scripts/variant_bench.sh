@@ -4,7 +4,7 @@
 # Usage (on a GPU box): bash scripts/variant_bench.sh w4 w6 w8
 for tag in "$@"; do
   cp sleipnir_b200/lib/libslpb_$tag.so sleipnir_b200/lib/libslpb.so
-  python bench.py --multistart 0 --no-cpu-baseline > gpurun_out/variant_$tag.json 2> gpurun_out/variant_$tag.err
+  python bench.py --multistart 0 --batch 0 --no-cpu-baseline > gpurun_out/variant_$tag.json 2> gpurun_out/variant_$tag.err
   python - "$tag" <<'PY'
 import json, sys
 tag = sys.argv[1]

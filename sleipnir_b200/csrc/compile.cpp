@@ -696,6 +696,11 @@ struct Compiler {
         for (int32_t i : lv) load[rev_worker[i]] += 1 + visits[i].contribs.size();
         crit += *std::max_element(load.begin(), load.end());
         for (int64_t l : load) total += l;
+        if (std::getenv("SLPB_SCHEDULE_DUMP") && n_workers == 16) {
+          std::fprintf(stderr, "   level %2d:", int(&lv - &rev_levels[0]));
+          for (int64_t l : load) std::fprintf(stderr, " %3lld", (long long)l);
+          std::fprintf(stderr, "\n");
+        }
       }
       std::fprintf(stderr,
                    "[slpb compile] schedule: %d workers, %zu forward + %zu reverse "

@@ -1025,10 +1025,12 @@ __global__ void k_unpermute(const double* __restrict__ xperm,
 // per-front counter in global memory.
 // ---------------------------------------------------------------------------
 
-// Warps per block of the tree kernels. k_factor_tree needs 168 registers per
-// thread, i.e. 12 resident warps per SM: 3 blocks of 4 reach that, 1 block of
-// 8 does not (measured: 0.198 → 0.189 ms per factorisation at N=5000; capping
-// the registers to fit more warps costs more in spills than it gains).
+// Warps per block of the tree kernels and resident blocks per SM. A warp keeps a
+// 13.6 KB front workspace in shared memory and k_factor_tree needs 136
+// registers per thread unconstrained; four blocks of four warps per SM (128
+// registers, 4 bytes of spill, 218 KB of shared memory) measured best on B200:
+// 0.0953 ms per factor launch at N=5000 against 0.0978 (3 × 4 warps, 136
+// registers), 0.0977 (6 × 2) and 0.1054 (blocks of 8).
 #ifndef SLPB_TREE_WARPS
 #define SLPB_TREE_WARPS 4
 #endif
@@ -1101,7 +1103,7 @@ struct FactorPair {
 };
 
 #ifndef SLPB_TREE_MIN_BLOCKS
-#define SLPB_TREE_MIN_BLOCKS 3
+#define SLPB_TREE_MIN_BLOCKS 4
 #endif
 __global__ void __launch_bounds__(kTreeWarps * 32, SLPB_TREE_MIN_BLOCKS)
 k_factor_tree(TreeView T, const double* __restrict__ Kval, double delta,

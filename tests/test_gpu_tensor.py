@@ -200,3 +200,20 @@ def test_tensor_mode_solves_to_the_same_optimum(name, N):
     x1, c1 = sols[sb.ARITH_TENSOR]
     assert c1 == pytest.approx(c0, rel=1e-6, abs=1e-9)
     np.testing.assert_allclose(x1, x0, atol=2e-4 * max(np.abs(x0).max(), 1.0))
+
+
+def test_device_timers_are_sampled_and_counted():
+    """slpb_get_timers: the kernel groups are timed on one run in
+    SLPB_TIMER_EVERY (timing events between back-to-back kernels are not free);
+    `launches` counts every run, `count` the sampled ones."""
+    P = sb.Problem("cart_pole", 100)
+    P.solve(max_iterations=40)
+    tim = P.timers()
+    tr = P.trace()
+    assert tim["eval_full"]["launches"] >= len(tr)
+    for name in ("eval_full", "factor", "solve"):
+        t = tim[name]
+        assert 1 <= t["count"] <= t["launches"]
+        assert t["count"] <= t["launches"] // 8 + 1
+        assert 0.0 < t["mean_ms"] < 5.0
+    P.close()
