@@ -737,7 +737,11 @@ k_kkt_stats(CscView Ae, CscView Ai, const double* __restrict__ g,
     // scaled: g − A_eᵀy − A_iᵀz ; unscaled: g/d_f − (A_e/d_ce)ᵀ(d_ce y/d_f) − …
     double aty = 0.0, atz = 0.0, u_aty = 0.0, u_atz = 0.0, atc = 0.0,
            atcp = 0.0;
-    for (int k = Ae.colptr[c]; k < Ae.colptr[c + 1]; ++k) {
+    const int ae_end = Ae.colptr[c + 1], ai_end = Ai.colptr[c + 1];
+    // (the gathers of four entries are in flight together; the sums keep the
+    // entry order)
+#pragma unroll 4
+    for (int k = Ae.colptr[c]; k < ae_end; ++k) {
       const int r = Ae.rowidx[k];
       const double a = Ae.val[k];
       aty += a * y[r];
@@ -745,7 +749,8 @@ k_kkt_stats(CscView Ae, CscView Ai, const double* __restrict__ g,
       u_aty += (inv_d_c[r] * a) * (dc * y[r] * inv_d_f);
       atc += a * c_e[r];
     }
-    for (int k = Ai.colptr[c]; k < Ai.colptr[c + 1]; ++k) {
+#pragma unroll 4
+    for (int k = Ai.colptr[c]; k < ai_end; ++k) {
       const int r = Ai.rowidx[k];
       const double a = Ai.val[k];
       atz += a * z[r];
