@@ -2,9 +2,9 @@
 //  A. How does mma.sync.m8n8k4.f64 (DMMA) round? Random 8×4 · 4×8 + 8×8
 //     products with wide exponent spreads are compared bit by bit with
 //     candidate evaluation orders computed on the host.
-//  B. Cycles per front of the register elimination (ldlt_eliminate_rows) and of
-//     the tensor-core elimination (ldlt_eliminate_dense), and the latter's bits
-//     against a host elimination that uses one fma per Schur-complement term.
+//  B. Cycles per front of the blocked elimination (ldlt_eliminate_front) in its
+//     two arithmetic modes, and their bits against host eliminations with
+//     separately rounded / fused Schur-complement terms.
 // nvcc -gencode arch=compute_100a,code=sm_100a -O3 -fmad=false -I sleipnir_b200/csrc
 //      -I include scripts/micro/dmma_probe.cu -o scripts/micro/dmma_probe
 #include <cmath>
@@ -90,20 +90,16 @@ __global__ void k_front(const double* Win, double* D, double* P, double* U, long
   double rr = 0;
   long long total = 0;
   for (int r = 0; r < reps; ++r) {
-    if (kDense) {
-      for (int j = 0; j < F; ++j) W[lane + j * kFrontLd] = lane < F ? Win[lane + j * F] : 0.0;
-    } else {
-      for (int i = lane; i < F * F; i += 32) W[i] = Win[i];
-    }
+    for (int j = 0; j < F; ++j) W[lane + j * kFrontLd] = lane < F ? Win[lane + j * F] : 0.0;
     __syncwarp();
     rr = 1.0 + lane;
     long long t0 = clock64();
     if (kDense) {
-      ldlt_eliminate_front(lane, F, np, F - np, W, side, D + gw * 32, P + gw * 1024,
-                           U + gw * 1024, ls[warp], rr);
+      ldlt_eliminate_front<true>(lane, F, np, F - np, W, side, D + gw * 32, P + gw * 1024,
+                                 U + gw * 1024, ls[warp], rr);
     } else {
-      ldlt_eliminate_rows(lane, F, np, F - np, W, D + gw * 32, P + gw * 1024, U + gw * 1024,
-                          ls[warp], rr);
+      ldlt_eliminate_front<false>(lane, F, np, F - np, W, side, D + gw * 32, P + gw * 1024,
+                                  U + gw * 1024, ls[warp], rr);
     }
     __syncwarp();
     total += clock64() - t0;
@@ -114,10 +110,10 @@ __global__ void k_front(const double* Win, double* D, double* P, double* U, long
 
 static void host_front(int F, int np, std::vector<double> W, bool fused, std::vector<double>& P,
                        std::vector<double>& U, std::vector<double>& D) {
-  P.assign(F * np, 0.0);
+  P.assign(F * np, 0.0);  // packed lower trapezoid (tri_col), padded
   D.assign(np, 0.0);
   const int m = F - np;
-  U.assign(m * m, 0.0);
+  U.assign(m * m + 1, 0.0);  // packed lower triangle, padded
   std::vector<double> l(F);
   for (int k = 0; k < np; ++k) {
     const double d = W[k + k * F];
@@ -129,11 +125,11 @@ static void host_front(int F, int np, std::vector<double> W, bool fused, std::ve
         W[i + j * F] = fused ? std::fma(-l[i], wjk, W[i + j * F]) : W[i + j * F] - l[i] * wjk;
       }
     }
-    P[k + k * F] = d;
-    for (int i = k + 1; i < F; ++i) P[i + k * F] = l[i];
+    P[tri_col(k, F) + k] = d;
+    for (int i = k + 1; i < F; ++i) P[tri_col(k, F) + i] = l[i];
   }
   for (int j = 0; j < m; ++j)
-    for (int i = j; i < m; ++i) U[i + j * m] = W[(np + i) + (np + j) * F];
+    for (int i = j; i < m; ++i) U[tri_col(j, m) + i] = W[(np + i) + (np + j) * F];
 }
 
 int main() {
@@ -231,13 +227,17 @@ int main() {
         int bad = 0;
         for (int k = 0; k < np; ++k) {
           bad += memcmp(&gD[k], &rD[k], 8) != 0;
-          for (int i = k; i < F; ++i) bad += memcmp(&gP[i + k * F], &rP[i + k * F], 8) != 0;
+          for (int i = k; i < F; ++i) {
+            bad += memcmp(&gP[tri_col(k, F) + i], &rP[tri_col(k, F) + i], 8) != 0;
+          }
         }
         const int m = F - np;
-        for (int j = 0; j < m; ++j) for (int i = j; i < m; ++i) bad += memcmp(&gU[i + j * m], &rU[i + j * m], 8) != 0;
+        for (int j = 0; j < m; ++j) {
+          for (int i = j; i < m; ++i) bad += memcmp(&gU[tri_col(j, m) + i], &rU[tri_col(j, m) + i], 8) != 0;
+        }
         printf("[front] F=%2d np=%2d %s blocks %3d x %d warps: %s, %lld cycles/front (%.0f per pivot), "
                "entries differing from the host %s elimination: %d\n",
-               F, np, dense ? "DMMA     " : "registers", blocks, threads / 32, cudaGetErrorString(e), h[0],
+               F, np, dense ? "tensor mode   " : "reference mode", blocks, threads / 32, cudaGetErrorString(e), h[0],
                double(h[0]) / np, dense ? "fused" : "unfused", bad);
       }
     }

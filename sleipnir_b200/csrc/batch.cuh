@@ -73,12 +73,6 @@ struct BatchView {
 constexpr int32_t kAsmPrimalDiag = 1 << 30, kAsmDualDiag = 1 << 29;
 constexpr int32_t kAsmIndexMask = (1 << 29) - 1;
 
-/// Offset of column j of a packed lower triangle of order F, minus j, so that
-/// entry (i, j), i ≥ j, sits at tri_col(j, F) + i.
-__device__ __forceinline__ int tri_col(int j, int F) {
-  return j * F - (j * (j - 1)) / 2 - j;
-}
-
 /// Reciprocal of a pivot, correctly rounded (computed once per pivot and reused
 /// by every division of its column).
 __device__ __forceinline__ double batch_rcp(double d) { return __drcp_rn(d); }

@@ -38,6 +38,14 @@
 
 namespace slpb {
 
+/// Packed lower triangle of order n, column-major: offset of column j minus j,
+/// so that entry (i, j), i ≥ j, sits at tri_col(j, n) + i. The L panel of a
+/// front keeps the first np columns of the triangle of order F (its diagonal
+/// slots hold d), the update matrix the triangle of order m = F − np.
+SLPB_HD int tri_col(int j, int n) {
+  return j * n - (j * (j - 1)) / 2 - j;
+}
+
 /// Device-side view of struct Symbolic (plain pointers).
 struct SymbolicView {
   int32_t dim, n_super;
@@ -99,7 +107,8 @@ SLPB_HD void ldlt_factor_front(int tid, int s, const SymbolicView& S,
     const int32_t* rel = S.rel_idx + S.rel_ptr[c];
     for (int j = 0; j < mc; ++j) {
       const int cj = rel[j] * F;
-      for (int i = j + tid; i < mc; i += NT) W[rel[i] + cj] += SLPB_LDCG(U + i + j * mc);
+      const double* Uj = U + tri_col(j, mc);
+      for (int i = j + tid; i < mc; i += NT) W[rel[i] + cj] += SLPB_LDCG(Uj + i);
     }
     sync();
   }
@@ -140,12 +149,14 @@ SLPB_HD void ldlt_factor_front(int tid, int s, const SymbolicView& S,
   }
   // L panel (F × np, unit diagonal implicit) and update matrix (m × m)
   double* P = panels + S.panel_ptr[s];
-  for (int e = tid; e < F * np; e += NT) P[e] = W[e];
+  for (int k = 0; k < np; ++k) {
+    double* Pk = P + tri_col(k, F);
+    for (int i = k + tid; i < F; i += NT) Pk[i] = W[i + k * F];
+  }
   double* U = updates + S.update_ptr[s];
   for (int j = 0; j < m; ++j) {
-    for (int i = j + tid; i < m; i += NT) {
-      U[i + j * m] = W[(np + i) + (np + j) * F];
-    }
+    double* Uj = U + tri_col(j, m);
+    for (int i = j + tid; i < m; i += NT) Uj[i] = W[(np + i) + (np + j) * F];
   }
   if (tid == 0) {
     local_stats[0] = pos;
@@ -188,7 +199,8 @@ SLPB_HD void ldlt_forward_front(int tid, int s, const SymbolicView& S,
   const double* P = panels + S.panel_ptr[s];
   for (int k = 0; k < np; ++k) {
     const double yk = w[k];
-    for (int i = k + 1 + tid; i < F; i += NT) w[i] -= P[i + k * F] * yk;
+    const double* Pk = P + tri_col(k, F);
+    for (int i = k + 1 + tid; i < F; i += NT) w[i] -= Pk[i] * yk;
     sync();
   }
   for (int i = tid; i < F; i += NT) {
@@ -221,14 +233,15 @@ SLPB_HD void ldlt_backward_front(int tid, int s, const SymbolicView& S,
   // t = z − L21ᵀ x_below: one own column per thread
   for (int k = tid; k < np; k += NT) {
     double acc = w[k];
-    for (int i = np; i < F; ++i) acc -= P[i + k * F] * w[i];
+    const double* Pk = P + tri_col(k, F);
+    for (int i = np; i < F; ++i) acc -= Pk[i] * w[i];
     w[k] = acc;
   }
   sync();
   // L11ᵀ x = t, column-oriented: once x_i is final, every k < i takes its term
   for (int i = np - 1; i >= 1; --i) {
     const double xi = w[i];
-    for (int k = tid; k < i; k += NT) w[k] -= P[i + k * F] * xi;
+    for (int k = tid; k < i; k += NT) w[k] -= P[tri_col(k, F) + i] * xi;
     sync();
   }
   for (int i = tid; i < np; i += NT) x_perm[c0 + i] = w[i];

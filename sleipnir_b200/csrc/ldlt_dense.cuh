@@ -65,8 +65,9 @@ __device__ __forceinline__ void dmma_8x8x4(double& c0, double& c1, double a,
 
 /// Elimination of the own columns of a front of order F ≤ 32 assembled in W
 /// (shared memory, kFrontLd × kFrontCols, lower triangle valid), then the
-/// write-out of the L panel (global P, F × np column-major, the diagonal slot
-/// keeps d), D and the update matrix (global U, m × m column-major, lower).
+/// write-out of the L panel (global P: packed lower trapezoid, tri_col of
+/// ldlt_core.hpp, the diagonal slot keeps d), D and the update matrix (global U:
+/// packed lower triangle of order m).
 /// rhs_i: this lane's entry of the front's right-hand side; it takes part in
 /// the elimination (forward substitution carried along: r_i −= l_ik · r_k, the
 /// arithmetic of ldlt_forward_front) and returns y (lanes < np) and the update
@@ -97,7 +98,7 @@ __device__ __noinline__ void ldlt_eliminate_front(
     }
   }
   double d_own = 1.0;  // lane k keeps pivot k
-  double* Pk = P + lane;
+  int pcol = 0;  // tri_col(k, F) of the current pivot k
 #pragma unroll 1
   for (int kb = 0; kb < np; kb += 4) {
     const int nb = min(4, np - kb);
@@ -143,8 +144,8 @@ __device__ __noinline__ void ldlt_eliminate_front(
         const double signed_zero = __hiloint2double(
             (__double2hiint(wk) ^ __double2hiint(d)) & 0x80000000, 0);
         const double l = zero_dividend ? signed_zero : quot;
-        if (lane < F) *Pk = lane > k ? l : wk;
-        Pk += F;
+        if (lane >= k && lane < F) P[pcol + lane] = lane > k ? l : wk;
+        pcol += F - k - 1;
         // (lanes ≥ F hold zeros in p[] and take l = ±0 through everything below;
         // rows above the pivot are masked because their l is not a multiplier)
         if (lane > k) r = r - l * rk;
@@ -270,10 +271,12 @@ __device__ __noinline__ void ldlt_eliminate_front(
     __syncwarp();
     DENSE_LAP(3)
   }
-  // update matrix (m × m, lower), four columns in flight
+  // update matrix (packed lower triangle of order m), four columns in flight;
+  // ucol = tri_col(jj, m) advances by m − jj − 1 per column
   {
     const double* Wu = W + lane + np * kFrontLd;
     double* Ul = U + (lane - np);
+    int ucol = 0;
     for (int j0 = 0; j0 < m; j0 += 4) {
       double v[4];
 #pragma unroll
@@ -281,7 +284,8 @@ __device__ __noinline__ void ldlt_eliminate_front(
 #pragma unroll
       for (int q = 0; q < 4; ++q) {
         const int jj = j0 + q;
-        if (jj < m && lane >= np + jj && lane < F) Ul[jj * m] = v[q];
+        if (jj < m && lane >= np + jj && lane < F) Ul[ucol] = v[q];
+        ucol += m - jj - 1;
       }
     }
   }

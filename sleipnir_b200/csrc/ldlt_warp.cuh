@@ -272,7 +272,7 @@ __device__ __forceinline__ void ldlt_forward_front_warp(
   double Lrow[32];  // L(lane, k), k < lane
 #pragma unroll
   for (int k = 0; k < 32; ++k) {
-    Lrow[k] = (k < np && lane > k && lane < F) ? P[lane + k * F] : 0.0;
+    Lrow[k] = (k < np && lane > k && lane < F) ? P[tri_col(k, F) + lane] : 0.0;
   }
   if (lane < F) w[lane] = lane < np ? rhs[perm[c0 + lane]] : 0.0;
   ChildPre pre[kPreChildren];
@@ -325,7 +325,7 @@ __device__ __forceinline__ void ldlt_backward_front_warp(
   double Lcol[32];  // L(i, lane), i > lane
 #pragma unroll
   for (int i = 0; i < 32; ++i) {
-    Lcol[i] = (lane < np && i > lane && i < F) ? P[i + lane * F] : 0.0;
+    Lcol[i] = (lane < np && i > lane && i < F) ? P[tri_col(lane, F) + i] : 0.0;
   }
   const double dinv_src = lane < np ? D[c0 + lane] : 1.0;
   const int row = (lane >= np && lane < F) ? rows_idx[fm.rows_off + lane] : 0;

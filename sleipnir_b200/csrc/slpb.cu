@@ -2574,7 +2574,7 @@ int slpb_analyze(slpb_solver* S, int ordering, const int32_t* perm,
         const int32_t* rel = Y.rel_idx.data() + Y.rel_ptr[c];
         for (int32_t j = 0; j < mc; ++j) {
           for (int32_t i = j; i < mc; ++i) {
-            ext_src.push_back(static_cast<int32_t>(Y.update_ptr[c] + i + int64_t(j) * mc));
+            ext_src.push_back(static_cast<int32_t>(Y.update_ptr[c] + tri_col(j, mc) + i));
             ext_dst.push_back(rel[i] + rel[j] * kFrontLd);
           }
         }
@@ -2686,7 +2686,9 @@ int slpb_analyze(slpb_solver* S, int ordering, const int32_t* perm,
         const int64_t m =
             Y.front_dim[r] - (Y.super_first[r + 1] - Y.super_first[r]);
         for (int64_t j = 0; j < m; ++j) {
-          for (int64_t i = j; i < m; ++i) pos[q].push_back(Y.update_ptr[r] + i + j * m);
+          for (int64_t i = j; i < m; ++i) {
+            pos[q].push_back(Y.update_ptr[r] + tri_col(static_cast<int>(j), static_cast<int>(m)) + i);
+          }
         }
         for (int64_t i = 0; i < m; ++i) pos[q].push_back((Y.rel_ptr[r] + i) | kPackVecTag);
       }

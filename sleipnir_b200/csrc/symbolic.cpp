@@ -695,8 +695,10 @@ bool analyze_kkt(const Pattern& K, int32_t n_primal, int ordering,
     const int64_t F = S.front_dim[s];
     const int64_t np = first[s + 1] - first[s];
     const int64_t m = F - np;
-    S.panel_ptr[s + 1] = S.panel_ptr[s] + F * np;
-    S.update_ptr[s + 1] = S.update_ptr[s] + m * m;
+    // packed: the lower trapezoid of the panel, the lower triangle of the update
+    // matrix (column j of a triangle of order n: entries i ≥ j at tri_col(j, n) + i)
+    S.panel_ptr[s + 1] = S.panel_ptr[s] + F * np - (np * (np - 1)) / 2;
+    S.update_ptr[s + 1] = S.update_ptr[s] + (m * (m + 1)) / 2;
     S.rel_ptr[s + 1] = S.rel_ptr[s] + m;
   }
   S.panel_size = S.panel_ptr[ns];
