@@ -1354,7 +1354,8 @@ void build_shard_plan(const ProgramSet& ps, int32_t world, ShardPlan& out) {
 }
 
 bool compile_autodiff(const Tape& tape, const RowSet rows[SLPB_OUT_COUNT],
-                      bool ignore_h_c, CompiledAD& out) {
+                      bool ignore_h_c, CompiledAD& out,
+                      const std::function<void()>& on_patterns) {
   out = CompiledAD{};
   StageTimer timer;
   Compiler C{tape, out.error};
@@ -1403,6 +1404,7 @@ bool compile_autodiff(const Tape& tape, const RowSet rows[SLPB_OUT_COUNT],
   out.off_h = out.off_ai + out.A_i.nnz();
   const int64_t n_deriv_entries = out.off_h + out.H.nnz();
   timer.lap("static patterns");
+  if (on_patterns) on_patterns();
   GatherBuilder dgather{n_deriv_entries};
   GatherBuilder vgather{1 + int64_t(me) + mi};
 

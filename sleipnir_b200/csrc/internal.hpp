@@ -3,6 +3,7 @@
 #pragma once
 
 #include <cstdint>
+#include <functional>
 #include <string>
 #include <utility>
 #include <vector>
@@ -217,8 +218,12 @@ bool ingest_tape(Tape& t, int32_t n_nodes, const uint8_t* op,
 bool ingest_rows(RowSet& r, const Tape& t, int which, const slpb_rowset* rows,
                  const double* const_val, std::string& error);
 
+/// on_patterns (optional) is called as soon as out.A_e, out.A_i and out.H — the
+/// static sparsity patterns — are final, while the programs are still being
+/// built (the caller may start the symbolic analysis of the KKT system then).
 bool compile_autodiff(const Tape& tape, const RowSet rows[SLPB_OUT_COUNT],
-                      bool ignore_h_c, CompiledAD& out);
+                      bool ignore_h_c, CompiledAD& out,
+                      const std::function<void()>& on_patterns = {});
 
 // ---------------------------------------------------------------------------
 // Symbolic analysis of the reduced KKT system (symbolic.cpp)

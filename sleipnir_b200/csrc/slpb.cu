@@ -23,6 +23,7 @@
 #include <cstdio>
 #include <cstdlib>
 #include <cstring>
+#include <future>
 #include <map>
 #include <memory>
 #include <mutex>
@@ -209,6 +210,8 @@ struct slpb_solver {
   bool use_tree = false;
   int factor_arith = SLPB_ARITH_REFERENCE;  // slpb_set_factor_arithmetic
   std::vector<int32_t> ext_begin, ext_chunks;  // per front (analysis scratch)
+  Symbolic sym_ahead;        // default-order analysis started inside slpb_finalize
+  bool sym_ahead_ok = false;
   int tree_blocks = 0, solve_blocks = 0, tree_smem_doubles = 0;
   int factor_sel = 0;  // which variant of the last factorisation the solves use
   // forward substitution fused into the factorisation (slpb_prepare_rhs)
@@ -2392,7 +2395,25 @@ int slpb_finalize(slpb_solver* S) {
     return fail(S, SLPB_ERR_STATE, "slpb_finalize before slpb_upload_tape");
   }
   CU(cudaSetDevice(S->device));
-  if (!compile_autodiff(S->tape, S->rows, S->ignore_h_c, S->ad)) {
+  // The symbolic analysis of the KKT system needs only the static patterns,
+  // which the compiler has after its first step: the assembly recipe and the
+  // analysis in the default ordering run on another thread while the programs
+  // are being built (slpb_analyze picks the result up).
+  S->sym_ahead_ok = false;
+  std::future<void> ahead;
+  const auto start_analysis = [&]() {
+    ahead = std::async(std::launch::async, [S]() {
+      build_kkt_recipe(S->n, S->me, S->ad.H, S->ad.A_e, S->ad.A_i, S->recipe);
+      std::string err;
+      S->sym_ahead_ok =
+          analyze_kkt(S->recipe.K, S->n, SLPB_ORDER_NESTED_DISSECTION, nullptr,
+                      S->sym_ahead, err);
+    });
+  };
+  const bool compiled =
+      compile_autodiff(S->tape, S->rows, S->ignore_h_c, S->ad, start_analysis);
+  if (ahead.valid()) ahead.get();
+  if (!compiled) {
     S->error = S->ad.error;
     return SLPB_ERR_UNSUPPORTED;
   }
@@ -2455,8 +2476,7 @@ int slpb_finalize(slpb_solver* S) {
     CU(S->ai_rcol.upload(rcol, S->stream));
     CU(S->ai_ridx.upload(ridx, S->stream));
   }
-  // KKT recipe
-  build_kkt_recipe(n, me, S->ad.H, S->ad.A_e, S->ad.A_i, S->recipe);
+  // KKT recipe (built beside the compiler, see above)
   CU(S->k_h_idx.upload(S->recipe.h_idx, S->stream));
   CU(S->k_ae_idx.upload(S->recipe.ae_idx, S->stream));
   CU(S->k_prod_ptr.upload(S->recipe.prod_ptr, S->stream));
@@ -2512,7 +2532,11 @@ int slpb_analyze(slpb_solver* S, int ordering, const int32_t* perm,
   if (!S || !S->finalized) return SLPB_ERR_STATE;
   const AllocScope alloc_scope{S->stream};
   CU(cudaSetDevice(S->device));
-  if (!analyze_kkt(S->recipe.K, S->n, ordering, perm, S->sym, S->error)) {
+  if (ordering == SLPB_ORDER_NESTED_DISSECTION && perm == nullptr &&
+      S->sym_ahead_ok) {
+    S->sym = std::move(S->sym_ahead);  // analysed beside the compiler
+    S->sym_ahead_ok = false;
+  } else if (!analyze_kkt(S->recipe.K, S->n, ordering, perm, S->sym, S->error)) {
     return SLPB_ERR_ARGUMENT;
   }
   const Symbolic& Y = S->sym;
