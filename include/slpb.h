@@ -508,9 +508,10 @@ typedef struct slpb_timers {
 } slpb_timers;
 int slpb_get_timers(slpb_solver* s, slpb_timers* out);
 
-/* Device time of the most recent factor / solve / eval, measured with CUDA
- * events on the handle's stream (milliseconds; 0 if not yet run). which:
- * 0 eval(full), 1 eval(values), 2 assemble, 3 factor, 4 solve. */
+/* Device time of the most recent SAMPLED factor / solve / eval (see
+ * slpb_timers; SLPB_TIMER_EVERY=1 times every run), measured with CUDA events
+ * on the handle's stream (milliseconds; 0 if not yet run). which: 0 eval(full),
+ * 1 eval(values), 2 assemble, 3 factor, 4 solve. */
 int slpb_last_device_ms(slpb_solver* s, int which, float* ms);
 /* Benchmark hygiene: overwrites a 256 MiB scratch buffer (larger than the
  * 126 MB L2) on the handle's stream and waits, so that the next phase starts
