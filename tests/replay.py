@@ -104,13 +104,16 @@ def exact_solution(K_full, rhs, x0=None):
     return x, lu
 
 
-def replay(name, N, iterations, ordering, compare_amd_factor=True):
+def replay(name, N, iterations, ordering, compare_amd_factor=True,
+           arithmetic=None):
     """Returns (rows, report): report[k] is a dict of the quantities listed in
     the module docstring for iteration k = 1 … iterations−1."""
     O, rows, (d_f, d_ce, d_ci) = oracle_rows(name, N, iterations)
     P = sb.Problem(name, N)
     D = P.open_device()
     D.set_scaling(d_f, d_ce, d_ci)
+    if arithmetic is not None:
+        D.set_factor_arithmetic(arithmetic)   # slpb_factor_arithmetic
     n, me, mi, dim = P.n, P.me, P.mi, P.n + P.me
     D.set_iterate(rows[0].x, rows[0].s, rows[0].y, rows[0].z)
     D.eval_current(1)

@@ -95,3 +95,40 @@ def test_one_step_replay_along_the_oracle_trajectory(name, N, iterations, order)
           "(reference's own step accurate to 1e-9)")
     if name == "flywheel":
         assert tight == compared   # a well-conditioned problem meets 1e-8 throughout
+
+
+@pytest.mark.parametrize("name,N,iterations", [("cart_pole", 5000, 10), ("gfold", 2000, 8)])
+def test_one_step_replay_in_the_tensor_core_mode(name, N, iterations):
+    """BASELINE config 3 (cart-pole N = 5000, tensor cores on the dense fronts)
+    and config 5 in the same mode: the one-step replay along the oracle's
+    trajectory with SLPB_ARITH_TENSOR (fused Schur updates, DMMA on fronts of
+    order >= 16), default ordering. One step is not affected by the different
+    rounding: the solve is backward stable against the exact solution of the
+    system the device assembled, the device's step is no further from the exact
+    Newton step than the reference's own (up to the floor), and the next
+    iterates differ by no more than the two sides' own step errors. (Whole
+    solves are a different matter, see csrc/ldlt_core.hpp.)"""
+    rows, report, sym = replay(name, N, iterations, sb.ORDER_NESTED_DISSECTION,
+                               arithmetic=sb.ARITH_TENSOR)
+    print(f"\n{name} N={N} tensor mode nnz(L)={sym['nnz_l']} max front {sym['max_front']}")
+    print(format_report(report))
+    assert sym["max_front"] >= 16 and len(report) >= iterations - 2
+    floor = 1e-7
+    compared = 0
+    for r in report:
+        k = r["iteration"]
+        assert r["inertia"][2] == 0, k
+        assert r["e_gpu"] <= 2.0 * r["cond1"] * EPS, (k, r["e_gpu"], r["cond1"])
+        assert r["pert"] <= 1e-12, k
+        same = (r["factorizations"][0] == r["factorizations"][1]
+                and r["delta"][0] == r["delta"][1] and r["gamma"][0] == r["gamma"][1])
+        if not same or "next" not in r:
+            continue
+        compared += 1
+        blocks = "xysz" if r["next"]["s"] <= 1e-6 else "xys"
+        for b in blocks:
+            own_cpu, own_gpu = r["err_run"][b], r["err_dev"][b]
+            assert own_gpu <= max(10.0 * own_cpu, floor), (k, b, own_gpu, own_cpu)
+            assert r["next"][b] <= 1.05 * (own_cpu + own_gpu) + 1e-12, \
+                (k, b, r["next"][b], own_cpu, own_gpu)
+    assert compared >= 3
