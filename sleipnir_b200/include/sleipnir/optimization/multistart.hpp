@@ -12,15 +12,23 @@
 // concurrent starts overlap on the SMs. `max_concurrency` bounds how many
 // run at once (0: all of them, as the reference does).
 //
-// Starts that turn out to share one KKT pattern (the usual case: the same
-// problem from different guesses) also share their linear algebra: the first
+// Starts that share one KKT pattern (the usual case: the same problem from
+// different guesses) CAN also share their linear algebra: the first
 // Problem::solve() of every start joins a slpb_group (include/slpb.h), and the
 // factorisations and triangular solves of all starts run as ONE batched launch
-// per round (lane = instance) instead of one latency-bound launch per start.
-// Each start's iterates are bit-identical to what it computes alone.
+// per round (lane = instance, groups of 32) instead of one launch per start;
+// each start's iterates are bit-identical to what it computes alone. Since the
+// single-instance tree kernels became 1.8× faster in round 2 this no longer
+// pays on one GPU with 16 host cores — measured on B200, cart-pole N = 5000,
+// aggregate steps/s of independent launches vs grouped: 8 starts 3 628 / 2 123,
+// 32 starts 3 370 / 3 083…3 608, 64 starts 4 061 / 3 667 — so it is opt-in:
+// SLPB_GROUP_MIN_STARTS=k batches waves of at least k starts. (The batched
+// kernels themselves, slpb_batch_*, are what many-instance callers with the
+// systems already on the device use: 512 systems at 1.0 / 3.6 TB/s.)
 #pragma once
 
 #include <algorithm>
+#include <cstdlib>
 #include <functional>
 #include <future>
 #include <span>
@@ -30,6 +38,10 @@
 #include "slpb.h"
 
 namespace slp {
+
+/// Waves of at least this many starts batch their linear algebra by default
+/// (never: see the measurements above; SLPB_GROUP_MIN_STARTS opts in).
+inline constexpr int kGroupMinStarts = 1 << 30;
 
 namespace detail {
 /// What a start's thread knows about the multistart it belongs to.
@@ -75,7 +87,11 @@ MultistartResult<Scalar, DecisionVariables> multistart(
     const size_t end = std::min(count, begin + wave);
     // the starts of a wave batch their linear algebra (batch_device < 0: off)
     detail::MultistartContext context;
-    if (batch_device >= 0 && end - begin > 1) {
+    const char* group_env = std::getenv("SLPB_GROUP_MIN_STARTS");
+    const size_t group_min_starts =
+        group_env ? static_cast<size_t>(std::max(2, std::atoi(group_env)))
+                  : static_cast<size_t>(kGroupMinStarts);
+    if (batch_device >= 0 && end - begin >= group_min_starts) {
       if (slpb_group_create(batch_device, static_cast<int32_t>(end - begin),
                             &context.group) != SLPB_OK) {
         context.group = nullptr;

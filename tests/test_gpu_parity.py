@@ -817,6 +817,15 @@ def test_concurrent_starts_do_not_disturb_each_other():
     P.close()
     r = sb.multistart("cart_pole", N, [5.0] * 8)
     assert all(s[0] == st and s[2] == iters_alone for s in r["starts"])
+    # … and so does a wave that batches its linear algebra (slpb_group: one
+    # batched factor / solve launch per round, lane = instance; opt-in)
+    os.environ["SLPB_GROUP_MIN_STARTS"] = "2"
+    try:
+        rg = sb.multistart("cart_pole", N, [5.0] * 8)
+    finally:
+        del os.environ["SLPB_GROUP_MIN_STARTS"]
+    assert all(s[0] == st and s[2] == iters_alone for s in rg["starts"])
+    np.testing.assert_array_equal(rg["x"], x_alone)
     assert len({s[1] for s in r["starts"]}) == 1          # identical costs
     np.testing.assert_array_equal(r["x"], x_alone)
     # the sequential wave (max_concurrency = 1) gives the same answer
