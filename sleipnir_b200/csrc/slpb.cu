@@ -2404,15 +2404,24 @@ int slpb_finalize(slpb_solver* S) {
   const auto start_analysis = [&]() {
     ahead = std::async(std::launch::async, [S]() {
       build_kkt_recipe(S->n, S->me, S->ad.H, S->ad.A_e, S->ad.A_i, S->recipe);
-      std::string err;
-      S->sym_ahead_ok =
-          analyze_kkt(S->recipe.K, S->n, SLPB_ORDER_NESTED_DISSECTION, nullptr,
-                      S->sym_ahead, err);
+      try {
+        std::string err;
+        S->sym_ahead_ok =
+            analyze_kkt(S->recipe.K, S->n, SLPB_ORDER_NESTED_DISSECTION, nullptr,
+                        S->sym_ahead, err);
+      } catch (...) {
+        S->sym_ahead_ok = false;  // slpb_analyze will run it again and report
+      }
     });
   };
   const bool compiled =
       compile_autodiff(S->tape, S->rows, S->ignore_h_c, S->ad, start_analysis);
-  if (ahead.valid()) ahead.get();
+  try {
+    if (ahead.valid()) ahead.get();
+  } catch (const std::exception& e) {
+    return fail(S, SLPB_ERR_UNSUPPORTED,
+                std::string("building the KKT assembly recipe: ") + e.what());
+  }
   if (!compiled) {
     S->error = S->ad.error;
     return SLPB_ERR_UNSUPPORTED;
