@@ -1491,6 +1491,46 @@ __global__ void k_clamp_z(const double* __restrict__ s, double mu, int mi,
   z[i] = v < lo ? lo : (hi < v ? hi : v);  // std::clamp
 }
 
+/// The whole commit in one launch (interior_point.hpp:779-805): x, s, y, z and
+/// the values f, c_e, c_i ← trial; z clamped like k_clamp_z (same expressions);
+/// and the leaves of the accepted point [x ‖ d_ce⊙y ‖ d_ci⊙z] for the
+/// re-linearisation that follows (k_prepare_leaves). Replaces five device
+/// copies and two kernels.
+__global__ void k_accept(const double* __restrict__ tx,
+                         const double* __restrict__ ts,
+                         const double* __restrict__ ty,
+                         const double* __restrict__ tz,
+                         const double* __restrict__ vals_trial,
+                         const double* __restrict__ d_c, double mu, int n, int me,
+                         int mi, double* __restrict__ x, double* __restrict__ s,
+                         double* __restrict__ y, double* __restrict__ z,
+                         double* __restrict__ vals_cur,
+                         double* __restrict__ leaf) {
+  const int i = blockIdx.x * blockDim.x + threadIdx.x;
+  if (i < n) {
+    const double v = tx[i];
+    x[i] = v;
+    leaf[i] = v;
+  }
+  if (i < me) {
+    const double v = ty[i];
+    y[i] = v;
+    leaf[n + i] = d_c[i] * v;
+  }
+  if (i < mi) {
+    const double si = ts[i];
+    s[i] = si;
+    const double kappa = 1e10;
+    const double lo = 1.0 / kappa * mu / si;
+    const double hi = kappa * mu / si;
+    const double v = tz[i];
+    const double zc = v < lo ? lo : (hi < v ? hi : v);  // std::clamp
+    z[i] = zc;
+    leaf[n + me + i] = d_c[me + i] * zc;
+  }
+  if (i < 1 + me + mi) vals_cur[i] = vals_trial[i];
+}
+
 __global__ void k_soc_begin(const double* __restrict__ c_e,
                             const double* __restrict__ c_i,
                             const double* __restrict__ s, int me, int mi,
@@ -3250,9 +3290,19 @@ int slpb_accept(slpb_solver* S, double mu) {
 int slpb_accept_relinearize(slpb_solver* S, double mu, int32_t* finite,
                             slpb_kkt_stats* stats) {
   if (!S || !S->analyzed || !finite || !stats) return SLPB_ERR_STATE;
-  int rc = slpb_accept(S, mu);
-  if (rc) return rc;
-  if ((rc = refresh_leaves(S, S->x.p, S->y.p, S->z.p, S->leaf_cur.p))) return rc;
+  int rc;
+  {
+    // slpb_accept + the leaves of the accepted point, in one launch
+    S->rhs_ready = false;
+    CU(cudaSetDevice(S->device));
+    const int n = S->n, me = S->me, mi = S->mi;
+    const int m = std::max(std::max(n, 1 + me + mi), std::max(me, mi));
+    k_accept<<<blocks_for(m, 256), 256, 0, S->stream>>>(
+        S->tx.p, S->ts.p, S->ty.p, S->tz.p, S->vals_trial.p, S->d_c.p, mu, n, me,
+        mi, S->x.p, S->s.p, S->y.p, S->z.p, S->vals_cur.p, S->leaf_cur.p);
+    ++S->counters.kernel_launches;
+    CU(cudaGetLastError());
+  }
   if ((rc = eval_derivs(S, S->leaf_cur.p))) return rc;
   k_deriv_finite<<<red_blocks(S->ad.off_h + S->ad.H.nnz()), kReduceThreads, 0,
                    S->stream>>>(S->dvals.p, S->ad.off_ae, S->ad.off_ai,
