@@ -882,6 +882,32 @@ __global__ void k_kkt_assemble(const int32_t* __restrict__ h_idx,
                       Aev, Aiv, sigma);
 }
 
+/// k_kkt_assemble and k_init_factor in one launch (the first factorisation
+/// attempt of an iteration needs both).
+__global__ void k_kkt_assemble_init(const int32_t* __restrict__ h_idx,
+                                    const int32_t* __restrict__ ae_idx,
+                                    const int32_t* __restrict__ prod_ptr,
+                                    const int32_t* __restrict__ prod_a,
+                                    const int32_t* __restrict__ prod_b,
+                                    const int32_t* __restrict__ prod_row,
+                                    const double* __restrict__ Hv,
+                                    const double* __restrict__ Aev,
+                                    const double* __restrict__ Aiv,
+                                    const double* __restrict__ sigma, int nnz,
+                                    double* __restrict__ Kval,
+                                    int32_t* __restrict__ stats, int32_t* sync,
+                                    int ns, int zero_sync) {
+  const int e = blockIdx.x * blockDim.x + threadIdx.x;
+  if (e < 16) stats[e] = (e & 7) == 5 ? 0x7ff00000 : 0;
+  if (zero_sync) {
+    if (e < 1 + 2 * ns) sync[e] = 0;
+    if (e < 2) sync[1 + 3 * ns + e] = 0;
+  }
+  if (e >= nnz) return;
+  Kval[e] = kkt_entry(e, h_idx, ae_idx, prod_ptr, prod_a, prod_b, prod_row, Hv,
+                      Aev, Aiv, sigma);
+}
+
 // ---- Lagrange multiplier estimate (lagrange_multiplier_estimate.hpp:55-131) ---
 // The reference solves the normal equations (ÂÂᵀ)[y; z] = Â[∇f; −μe] with
 // Â = [A_e 0; A_i −S]. Eliminating the slack block of the equivalent augmented
@@ -2934,20 +2960,34 @@ int factor_impl(slpb_solver* S, int n_variants, const double* delta,
                 const double* gamma, int reassemble, slpb_factor_info* info) {
   CU(cudaSetDevice(S->device));
   const Symbolic& Y = S->sym;
+  // The first attempt of an iteration assembles the lhs and prepares the launch
+  // (statistics, ticket, dependency counters, dead flags) in ONE kernel; Σ is
+  // already there when slpb_prepare_rhs has just run for this iterate.
+  const bool fuse_init = reassemble && S->group == nullptr;
+  const int init_words = S->use_tree ? 1 + 2 * Y.n_super : 16;
   if (reassemble) {
     CU(timer_begin(S, 2));
-    if (S->mi > 0) {
+    if (S->mi > 0 && !S->rhs_ready) {
       k_sigma_t<<<blocks_for(S->mi, 256), 256, 0, S->stream>>>(
           S->s.p, S->z.p, S->vals_cur.p + 1 + S->me, nullptr, 0.0, 0, S->mi,
           S->sinv.p, S->sigma.p, S->tvec.p);
       ++S->counters.kernel_launches;
     }
     const int nnz = static_cast<int>(S->recipe.K.nnz());
-    k_kkt_assemble<<<blocks_for(nnz, 256), 256, 0, S->stream>>>(
-        S->k_h_idx.p, S->k_ae_idx.p, S->k_prod_ptr.p, S->k_prod_a.p,
-        S->k_prod_b.p, S->k_prod_row.p, S->dvals.p + S->ad.off_h,
-        S->dvals.p + S->ad.off_ae, S->dvals.p + S->ad.off_ai, S->sigma.p, nnz,
-        S->Kval.p);
+    if (fuse_init) {
+      k_kkt_assemble_init<<<blocks_for(std::max(nnz, init_words), 256), 256, 0,
+                            S->stream>>>(
+          S->k_h_idx.p, S->k_ae_idx.p, S->k_prod_ptr.p, S->k_prod_a.p,
+          S->k_prod_b.p, S->k_prod_row.p, S->dvals.p + S->ad.off_h,
+          S->dvals.p + S->ad.off_ae, S->dvals.p + S->ad.off_ai, S->sigma.p, nnz,
+          S->Kval.p, S->fstats.p, S->tree_sync.p, Y.n_super, S->use_tree ? 1 : 0);
+    } else {
+      k_kkt_assemble<<<blocks_for(nnz, 256), 256, 0, S->stream>>>(
+          S->k_h_idx.p, S->k_ae_idx.p, S->k_prod_ptr.p, S->k_prod_a.p,
+          S->k_prod_b.p, S->k_prod_row.p, S->dvals.p + S->ad.off_h,
+          S->dvals.p + S->ad.off_ae, S->dvals.p + S->ad.off_ai, S->sigma.p, nnz,
+          S->Kval.p);
+    }
     ++S->counters.kernel_launches;
     CU(timer_end(S, 2));
   }
@@ -2961,9 +3001,8 @@ int factor_impl(slpb_solver* S, int n_variants, const double* delta,
   CU(timer_begin(S, 3));
   // stats per variant: n_pos n_neg n_zero zero_pivot | min|D| bits (+inf);
   // ticket, dependency counters and dead flags of the tree kernel
-  {
-    const int words = S->use_tree ? 1 + 2 * Y.n_super : 16;
-    k_init_factor<<<blocks_for(words, 256), 256, 0, S->stream>>>(
+  if (!fuse_init) {
+    k_init_factor<<<blocks_for(init_words, 256), 256, 0, S->stream>>>(
         S->fstats.p, S->tree_sync.p, Y.n_super, S->use_tree ? 1 : 0);
     ++S->counters.kernel_launches;
   }
