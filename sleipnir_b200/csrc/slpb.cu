@@ -205,6 +205,8 @@ struct slpb_solver {
   DevBuf<double> panels, updates, D, uvecs, xperm;
   DevBuf<int32_t> fstats;  // FactorStats as 6 ints
   DevBuf<int32_t> sy_super_parent, sy_nchild, tree_sync;
+  DevBuf<int32_t> solve_sync;       // dependency words of k_solve_tree
+  bool solve_sync_preset = false;   // written by the last factor launch's init
   DevBuf<FrontMeta> sy_metas;
   DevBuf<unsigned long long> tree_debug;
   bool use_tree = false;
@@ -719,7 +721,9 @@ k_kkt_stats(CscView Ae, CscView Ai, const double* __restrict__ g,
             const double* __restrict__ y, const double* __restrict__ z,
             const double* __restrict__ d_c,
             const double* __restrict__ inv_d_c, double d_f, double mu, int n,
-            int me, int mi, RedBuf rb, double* __restrict__ out) {
+            int me, int mi, RedBuf rb, double* __restrict__ out,
+            const double* __restrict__ scan, int64_t off_ae, int64_t off_ai,
+            int64_t off_h, int64_t scan_total, double* __restrict__ finite_out) {
   // (inv_d_c[r] = RN(1 / d_c[r]), computed once when the scaling is set: the
   // reference divides per entry, kkt_error.hpp:150-190 — same value, no
   // division inside the column loops)
@@ -728,8 +732,10 @@ k_kkt_stats(CscView Ae, CscView Ai, const double* __restrict__ g,
   // 9 cis_inf 10 cis_l1 11 u_r_inf 12 u_y_l1 13 u_z_l1 14 u_sz_min 15 u_sz_max
   // 16 u_ce_inf 17 u_cis_inf 18 aetce_sq 19 ce_sq 20 aitcip_sq 21 cip_sq
   // 22 x_inf 23 s_inf 24 nonfinite count
-  double v[25];
-  for (int q = 0; q < 25; ++q) v[q] = 0.0;
+  // 25…28 (scan != nullptr: k_deriv_finite in the same launch) non-finite
+  // entries of g, A_e, A_i, H
+  double v[29];
+  for (int q = 0; q < 29; ++q) v[q] = 0.0;
   v[4] = INFINITY;
   v[5] = -INFINITY;
   v[14] = INFINITY;
@@ -802,13 +808,30 @@ k_kkt_stats(CscView Ae, CscView Ai, const double* __restrict__ g,
     v[23] = fmax(v[23], fabs(sv));
     if (!isfinite(sv)) v[24] += 1.0;
   }
-  const int op[25] = {RED_MAX, RED_SUM, RED_SUM, RED_SUM, RED_MIN, RED_MAX,
+  if (scan != nullptr) {
+    const int64_t sstride = int64_t(gridDim.x) * blockDim.x;
+    for (int64_t i = t0; i < scan_total; i += sstride) {
+      if (!isfinite(scan[i])) {
+        const int seg = i < off_ae ? 0 : (i < off_ai ? 1 : (i < off_h ? 2 : 3));
+        v[25 + seg] += 1.0;
+      }
+    }
+  }
+  const int op[29] = {RED_MAX, RED_SUM, RED_SUM, RED_SUM, RED_MIN, RED_MAX,
                       RED_SUM, RED_MAX, RED_SUM, RED_MAX, RED_SUM, RED_MAX,
                       RED_SUM, RED_SUM, RED_MIN, RED_MAX, RED_MAX, RED_MAX,
                       RED_SUM, RED_SUM, RED_SUM, RED_SUM, RED_MAX, RED_MAX,
-                      RED_SUM};
-  __shared__ double res[25];
-  if (!grid_reduce<25>(v, op, rb.partials, rb.counter, res)) return;
+                      RED_SUM, RED_SUM, RED_SUM, RED_SUM, RED_SUM};
+  __shared__ double res[29];
+  if (!grid_reduce<29>(v, op, rb.partials, rb.counter, res)) return;
+  if (threadIdx.x == 0 && finite_out != nullptr) {
+    int bits = 0;
+    if (res[25] == 0.0) bits |= SLPB_FINITE_G;
+    if (res[26] == 0.0) bits |= SLPB_FINITE_A_E;
+    if (res[27] == 0.0) bits |= SLPB_FINITE_A_I;
+    if (res[28] == 0.0) bits |= SLPB_FINITE_H;
+    finite_out[0] = static_cast<double>(bits);
+  }
   if (threadIdx.x == 0) {
     for (int q = 0; q < 18; ++q) out[q] = res[q];
     out[18] = sqrt(res[18]);
@@ -865,6 +888,47 @@ __global__ void k_rhs(CscView Ae, CscView Ai, const double* __restrict__ g,
   }
 }
 
+/// k_sigma_t and k_rhs in one launch: thread c < n + m_e forms its right-hand
+/// side entry with t recomputed entry by entry from the same expressions (so
+/// nothing waits for the Σ/t arrays), thread i < m_i stores S⁻¹, Σ and t for
+/// the kernels that follow (assembly, step recovery).
+__global__ void k_rhs_sigma(CscView Ae, CscView Ai, const double* __restrict__ g,
+                            const double* __restrict__ y,
+                            const double* __restrict__ c_e,
+                            const double* __restrict__ s,
+                            const double* __restrict__ z,
+                            const double* __restrict__ c_i,
+                            const double* __restrict__ cis_soc, double mu,
+                            int mode, int n, int me, int mi,
+                            double* __restrict__ sinv, double* __restrict__ sigma,
+                            double* __restrict__ t, double* __restrict__ rhs) {
+  const int c = blockIdx.x * blockDim.x + threadIdx.x;
+  if (c < mi) {
+    const double si = 1.0 / s[c];
+    const double sg = si * z[c];
+    sinv[c] = si;
+    sigma[c] = sg;
+    t[c] = mode == 0 ? (-sg * c_i[c] + mu * si + z[c]) : (mu * si - sg * cis_soc[c]);
+  }
+  if (c < n) {
+    double aty = 0.0, att = 0.0;
+    for (int k = Ae.colptr[c]; k < Ae.colptr[c + 1]; ++k) {
+      aty += Ae.val[k] * y[Ae.rowidx[k]];
+    }
+    for (int k = Ai.colptr[c]; k < Ai.colptr[c + 1]; ++k) {
+      const int r = Ai.rowidx[k];
+      const double si = 1.0 / s[r];
+      const double sg = si * z[r];
+      const double tr =
+          mode == 0 ? (-sg * c_i[r] + mu * si + z[r]) : (mu * si - sg * cis_soc[r]);
+      att += Ai.val[k] * tr;
+    }
+    rhs[c] = -g[c] + aty + att;
+  } else if (c < n + me) {
+    rhs[c] = -c_e[c - n];
+  }
+}
+
 __global__ void k_kkt_assemble(const int32_t* __restrict__ h_idx,
                                const int32_t* __restrict__ ae_idx,
                                const int32_t* __restrict__ prod_ptr,
@@ -896,8 +960,11 @@ __global__ void k_kkt_assemble_init(const int32_t* __restrict__ h_idx,
                                     const double* __restrict__ sigma, int nnz,
                                     double* __restrict__ Kval,
                                     int32_t* __restrict__ stats, int32_t* sync,
-                                    int ns, int zero_sync) {
+                                    int ns, int zero_sync, int32_t* solve_sync) {
   const int e = blockIdx.x * blockDim.x + threadIdx.x;
+  if (solve_sync != nullptr && e < 1 + 3 * ns) {
+    solve_sync[e] = (e > ns && e <= 2 * ns) ? 1 : 0;  // see k_init_factor
+  }
   if (e < 16) stats[e] = (e & 7) == 5 ? 0x7ff00000 : 0;
   if (zero_sync) {
     if (e < 1 + 2 * ns) sync[e] = 0;
@@ -1221,8 +1288,14 @@ k_factor_tree(TreeView T, const double* __restrict__ Kval, double delta,
 /// (zero counts, min|D| = +inf) and, for the tree kernel, the ticket, the
 /// dependency counters of both variants and the "variant is dead" flags.
 __global__ void k_init_factor(int32_t* __restrict__ stats, int32_t* sync,
-                              int ns, int zero_sync) {
+                              int ns, int zero_sync, int32_t* solve_sync) {
   const int i = blockIdx.x * blockDim.x + threadIdx.x;
+  // (solve_sync != nullptr: the words of the solve that will follow, preset
+  // for "forward substitution already carried by the factorisation" — what
+  // k_init_solve_sync(…, skip_forward = 1) writes)
+  if (solve_sync != nullptr && i < 1 + 3 * ns) {
+    solve_sync[i] = (i > ns && i <= 2 * ns) ? 1 : 0;
+  }
   if (i < 16) {
     // per variant: n_pos n_neg n_zero zero_pivot | +inf bits | pad
     const int k = i & 7;
@@ -1900,11 +1973,14 @@ constexpr int kResKkt = 32;    // 25 doubles of k_kkt_stats
 
 int kkt_stats_enqueue(slpb_solver* S, const double* c_e, const double* c_i,
                       const double* x, const double* s, const double* y,
-                      const double* z, double mu, int offset) {
+                      const double* z, double mu, int offset,
+                      bool with_deriv_finite = false) {
   k_kkt_stats<<<red_blocks(S->n + S->mi), kReduceThreads, 0, S->stream>>>(
       ae_view(S), ai_view(S), S->dvals.p + S->ad.off_g, c_e, c_i, x, s, y, z,
       S->d_c.p, S->inv_d_c.p, S->d_f, mu, S->n, S->me, S->mi, red_buf(S),
-      S->d_results.p + offset);
+      S->d_results.p + offset, with_deriv_finite ? S->dvals.p : nullptr,
+      S->ad.off_ae, S->ad.off_ai, S->ad.off_h, S->ad.off_h + S->ad.H.nnz(),
+      with_deriv_finite ? S->d_results.p + kResPoint : nullptr);
   ++S->counters.kernel_launches;
   CU(cudaGetLastError());
   return SLPB_OK;
@@ -1976,15 +2052,11 @@ TreeView tree_view(slpb_solver* S) {
 int build_rhs(slpb_solver* S, double mu, const double* cis_soc,
               const double* ce_for_rhs) {
   const int n = S->n, me = S->me, mi = S->mi;
-  if (mi > 0) {
-    k_sigma_t<<<blocks_for(mi, 256), 256, 0, S->stream>>>(
-        S->s.p, S->z.p, S->vals_cur.p + 1 + me, cis_soc, mu,
-        cis_soc ? 1 : 0, mi, S->sinv.p, S->sigma.p, S->tvec.p);
-    ++S->counters.kernel_launches;
-  }
-  k_rhs<<<blocks_for(S->dim, 256), 256, 0, S->stream>>>(
-      ae_view(S), ai_view(S), S->dvals.p + S->ad.off_g, S->y.p, S->tvec.p,
-      ce_for_rhs, n, me, S->rhs.p);
+  // Σ, S⁻¹, t and the right-hand side in one launch
+  k_rhs_sigma<<<blocks_for(std::max(S->dim, mi), 256), 256, 0, S->stream>>>(
+      ae_view(S), ai_view(S), S->dvals.p + S->ad.off_g, S->y.p, ce_for_rhs,
+      S->s.p, S->z.p, S->vals_cur.p + 1 + me, cis_soc, mu, cis_soc ? 1 : 0, n,
+      me, mi, S->sinv.p, S->sigma.p, S->tvec.p, S->rhs.p);
   ++S->counters.kernel_launches;
   CU(cudaGetLastError());
   return SLPB_OK;
@@ -2110,13 +2182,18 @@ int launch_solve(slpb_solver* S, bool skip_forward) {
     double* xperm = S->xperm.p + size_t(sel) * Y.dim;
     double* uvecs = S->uvecs.p + size_t(sel) * Y.rel_ptr.back();
     TreeView T = tree_view(S);
+    T.sync = S->solve_sync.p;  // the solve's own dependency words
     if (!S->tree_sharded) {
-      k_init_solve_sync<<<blocks_for(Y.n_super, 256), 256, 0, S->stream>>>(
-          S->tree_sync.p, Y.n_super, skip_forward ? 1 : 0, nullptr);
+      if (!(skip_forward && S->solve_sync_preset)) {
+        k_init_solve_sync<<<blocks_for(Y.n_super, 256), 256, 0, S->stream>>>(
+            S->solve_sync.p, Y.n_super, skip_forward ? 1 : 0, nullptr);
+        ++S->counters.kernel_launches;
+      }
+      S->solve_sync_preset = false;  // the words are used up
       if (skip_forward) T.n_fwd = 0;
       k_solve_tree<<<S->solve_blocks, kTreeWarps * 32, 0, S->stream>>>(
           T, panels, Dsel, S->rhs.p, xperm, uvecs, S->sol.p);
-      S->counters.kernel_launches += 2;
+      ++S->counters.kernel_launches;
     } else {
       // Sharded: forward over the own subtrees, exchange of the roots' update
       // vectors, then forward over the replicated top and backward over top
@@ -2126,7 +2203,7 @@ int launch_solve(slpb_solver* S, bool skip_forward) {
       const int n_top = static_cast<int>(H.top_order.size());
       if (!skip_forward) {
         k_init_solve_sync<<<blocks_for(Y.n_super, 256), 256, 0, S->stream>>>(
-            S->tree_sync.p, Y.n_super, 0, nullptr);
+            S->solve_sync.p, Y.n_super, 0, nullptr);
         T.order = S->ts_my_order.p;
         T.n_fwd = n_mine;
         T.n_bwd = 0;
@@ -2141,7 +2218,7 @@ int launch_solve(slpb_solver* S, bool skip_forward) {
         if (rc) return rc;
       }
       k_init_solve_sync<<<blocks_for(Y.n_super, 256), 256, 0, S->stream>>>(
-          S->tree_sync.p, Y.n_super, skip_forward ? 1 : 0,
+          S->solve_sync.p, Y.n_super, skip_forward ? 1 : 0,
           S->ts_top_fcount_init.p);
       T.order = S->ts_top_order.p;
       T.n_fwd = skip_forward ? 0 : n_top;
@@ -2733,6 +2810,8 @@ int slpb_analyze(slpb_solver* S, int ordering, const int32_t* perm,
     // [0] ticket | 3 × n_super dependency words | [1 + 3 n_super + v] "variant v
     // met an exactly zero pivot" flags of the factor launch
     CU(S->tree_sync.alloc(3 + 3 * size_t(Y.n_super)));
+    CU(S->solve_sync.alloc(1 + 3 * size_t(Y.n_super)));
+    S->solve_sync_preset = false;
   }
   {
     const int tree_smem =
@@ -2964,7 +3043,14 @@ int factor_impl(slpb_solver* S, int n_variants, const double* delta,
   // (statistics, ticket, dependency counters, dead flags) in ONE kernel; Σ is
   // already there when slpb_prepare_rhs has just run for this iterate.
   const bool fuse_init = reassemble && S->group == nullptr;
-  const int init_words = S->use_tree ? 1 + 2 * Y.n_super : 16;
+  // a fused solve is expected behind this factorisation: its dependency words
+  // are preset here, so that the solve is ONE launch
+  const bool preset_solve = S->use_tree && !S->tree_sharded && S->rhs_ready &&
+                            S->group == nullptr;
+  int32_t* preset_ptr = preset_solve ? S->solve_sync.p : nullptr;
+  const int init_words =
+      S->use_tree ? std::max(1 + 2 * Y.n_super, preset_solve ? 1 + 3 * Y.n_super : 0)
+                  : 16;
   if (reassemble) {
     CU(timer_begin(S, 2));
     if (S->mi > 0 && !S->rhs_ready) {
@@ -2980,7 +3066,8 @@ int factor_impl(slpb_solver* S, int n_variants, const double* delta,
           S->k_h_idx.p, S->k_ae_idx.p, S->k_prod_ptr.p, S->k_prod_a.p,
           S->k_prod_b.p, S->k_prod_row.p, S->dvals.p + S->ad.off_h,
           S->dvals.p + S->ad.off_ae, S->dvals.p + S->ad.off_ai, S->sigma.p, nnz,
-          S->Kval.p, S->fstats.p, S->tree_sync.p, Y.n_super, S->use_tree ? 1 : 0);
+          S->Kval.p, S->fstats.p, S->tree_sync.p, Y.n_super, S->use_tree ? 1 : 0,
+          preset_ptr);
     } else {
       k_kkt_assemble<<<blocks_for(nnz, 256), 256, 0, S->stream>>>(
           S->k_h_idx.p, S->k_ae_idx.p, S->k_prod_ptr.p, S->k_prod_a.p,
@@ -3003,9 +3090,10 @@ int factor_impl(slpb_solver* S, int n_variants, const double* delta,
   // ticket, dependency counters and dead flags of the tree kernel
   if (!fuse_init) {
     k_init_factor<<<blocks_for(init_words, 256), 256, 0, S->stream>>>(
-        S->fstats.p, S->tree_sync.p, Y.n_super, S->use_tree ? 1 : 0);
+        S->fstats.p, S->tree_sync.p, Y.n_super, S->use_tree ? 1 : 0, preset_ptr);
     ++S->counters.kernel_launches;
   }
+  S->solve_sync_preset = preset_solve;
   if (S->use_tree) {
     const TreeView T = tree_view(S);
     const int smem =
@@ -3343,13 +3431,10 @@ int slpb_accept_relinearize(slpb_solver* S, double mu, int32_t* finite,
     CU(cudaGetLastError());
   }
   if ((rc = eval_derivs(S, S->leaf_cur.p))) return rc;
-  k_deriv_finite<<<red_blocks(S->ad.off_h + S->ad.H.nnz()), kReduceThreads, 0,
-                   S->stream>>>(S->dvals.p, S->ad.off_ae, S->ad.off_ai,
-                                S->ad.off_h, S->ad.off_h + S->ad.H.nnz(),
-                                red_buf(S), S->d_results.p + kResPoint);
-  ++S->counters.kernel_launches;
+  // error reductions and the finiteness scan of the new derivatives, one launch
   if ((rc = kkt_stats_enqueue(S, S->vals_cur.p + 1, S->vals_cur.p + 1 + S->me,
-                              S->x.p, S->s.p, S->y.p, S->z.p, mu, kResKkt))) {
+                              S->x.p, S->s.p, S->y.p, S->z.p, mu, kResKkt,
+                              /*with_deriv_finite=*/true))) {
     return rc;
   }
   if ((rc = fetch_results(S, kResKkt + 25))) return rc;
