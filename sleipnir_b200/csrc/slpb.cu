@@ -867,29 +867,8 @@ __global__ void k_sigma_t(const double* __restrict__ s,
                    : (mu * si - sg * cis_soc[i]);
 }
 
-/// rhs = −[g − A_eᵀy − A_iᵀt ; c_e] (interior_point.hpp:444-448).
-__global__ void k_rhs(CscView Ae, CscView Ai, const double* __restrict__ g,
-                      const double* __restrict__ y,
-                      const double* __restrict__ t,
-                      const double* __restrict__ c_e, int n, int me,
-                      double* __restrict__ rhs) {
-  const int c = blockIdx.x * blockDim.x + threadIdx.x;
-  if (c < n) {
-    double aty = 0.0, att = 0.0;
-    for (int k = Ae.colptr[c]; k < Ae.colptr[c + 1]; ++k) {
-      aty += Ae.val[k] * y[Ae.rowidx[k]];
-    }
-    for (int k = Ai.colptr[c]; k < Ai.colptr[c + 1]; ++k) {
-      att += Ai.val[k] * t[Ai.rowidx[k]];
-    }
-    rhs[c] = -g[c] + aty + att;
-  } else if (c < n + me) {
-    rhs[c] = -c_e[c - n];
-  }
-}
-
-/// k_sigma_t and k_rhs in one launch: thread c < n + m_e forms its right-hand
-/// side entry with t recomputed entry by entry from the same expressions (so
+/// rhs = −[g − A_eᵀy − A_iᵀt ; c_e] (interior_point.hpp:444-448) and k_sigma_t in
+/// one launch: thread c < n + m_e forms its right-hand side entry with t recomputed entry by entry from the same expressions (so
 /// nothing waits for the Σ/t arrays), thread i < m_i stores S⁻¹, Σ and t for
 /// the kernels that follow (assembly, step recovery).
 __global__ void k_rhs_sigma(CscView Ae, CscView Ai, const double* __restrict__ g,
@@ -1460,61 +1439,54 @@ __global__ void k_scatter_idx(const double* __restrict__ buf,
 // kernels: step recovery, line search
 // ---------------------------------------------------------------------------
 
-/// p_x, p_y = −p₂, p_s = cis + A_i p_x, p_z = μ/s − z − Σ p_s
-/// (interior_point.hpp:470-481). cis = c_i − s, or the SOC accumulator.
-__global__ void k_step_recover(const double* __restrict__ sol,
-                               const int32_t* __restrict__ ai_rowptr,
-                               const int32_t* __restrict__ ai_rcol,
-                               const int32_t* __restrict__ ai_ridx,
-                               const double* __restrict__ ai_val,
-                               const double* __restrict__ c_i,
-                               const double* __restrict__ s,
-                               const double* __restrict__ z,
-                               const double* __restrict__ cis_soc,
-                               const double* __restrict__ sinv,
-                               const double* __restrict__ sigma, double mu,
-                               int n, int me, int mi, double* __restrict__ px,
-                               double* __restrict__ py,
-                               double* __restrict__ ps,
-                               double* __restrict__ pz) {
-  const int i = blockIdx.x * blockDim.x + threadIdx.x;
-  if (i < n) px[i] = sol[i];
-  if (i < me) py[i] = -sol[n + i];
-  if (i < mi) {
+/// Step recovery (interior_point.hpp:470-481: pˢ = (c_i − s) + A_i pˣ,
+/// pᶻ = μ/s − z − Σpˢ) and, in the same launch, the fraction-to-the-boundary
+/// rule on (s, pˢ) and (z, pᶻ) (fraction_to_the_boundary_rule.hpp:19-43:
+/// α = min(1, min −τ/pᵢ·xᵢ over the blocking components)), gᵀpˣ, (S⁻¹e)ᵀpˢ and
+/// the step norms: every thread recovers the entries of its grid-stride slice
+/// and feeds them straight into the reductions.
+__global__ void __launch_bounds__(kReduceThreads)
+k_step_recover_stats(const double* __restrict__ sol,
+                     const int32_t* __restrict__ ai_rowptr,
+                     const int32_t* __restrict__ ai_rcol,
+                     const int32_t* __restrict__ ai_ridx,
+                     const double* __restrict__ ai_val,
+                     const double* __restrict__ c_i,
+                     const double* __restrict__ s, const double* __restrict__ z,
+                     const double* __restrict__ cis_soc,
+                     const double* __restrict__ sinv,
+                     const double* __restrict__ sigma,
+                     const double* __restrict__ g, double mu, double tau, int n,
+                     int me, int mi, double* __restrict__ px,
+                     double* __restrict__ py, double* __restrict__ ps,
+                     double* __restrict__ pz, RedBuf rb,
+                     double* __restrict__ out) {
+  // 0 alpha_max 1 alpha_z 2 g·px 3 sinv·ps 4..7 inf norms 8 nonfinite
+  double v[9] = {1.0, 1.0, 0.0, 0.0, 0.0, 0.0, 0.0, 0.0, 0.0};
+  const int stride = gridDim.x * blockDim.x;
+  const int t0 = blockIdx.x * blockDim.x + threadIdx.x;
+  for (int i = t0; i < n; i += stride) {
+    const double p = sol[i];
+    px[i] = p;
+    v[2] += g[i] * p;
+    v[4] = fmax(v[4], fabs(p));
+    if (!isfinite(p)) v[8] += 1.0;
+  }
+  for (int i = t0; i < me; i += stride) {
+    const double p = -sol[n + i];
+    py[i] = p;
+    v[6] = fmax(v[6], fabs(p));
+  }
+  for (int i = t0; i < mi; i += stride) {
     double acc = 0.0;
     for (int k = ai_rowptr[i]; k < ai_rowptr[i + 1]; ++k) {
       acc += ai_val[ai_ridx[k]] * sol[ai_rcol[k]];
     }
     const double cis = cis_soc ? cis_soc[i] : (c_i[i] - s[i]);
     const double p = cis + acc;
+    const double q = mu * sinv[i] - z[i] - sigma[i] * p;
     ps[i] = p;
-    pz[i] = mu * sinv[i] - z[i] - sigma[i] * p;
-  }
-}
-
-/// fraction-to-the-boundary rule on (s,p_s) and (z,p_z)
-/// (fraction_to_the_boundary_rule.hpp:19-43: α = min(1, min −τ/pᵢ·xᵢ over the
-/// blocking components), gᵀpˣ, (S⁻¹e)ᵀpˢ and step norms.
-__global__ void __launch_bounds__(kReduceThreads)
-k_step_stats(const double* __restrict__ g, const double* __restrict__ s,
-             const double* __restrict__ z, const double* __restrict__ sinv,
-             const double* __restrict__ px, const double* __restrict__ ps,
-             const double* __restrict__ py, const double* __restrict__ pz,
-             double tau, int n, int me, int mi, RedBuf rb,
-             double* __restrict__ out) {
-  // 0 alpha_max 1 alpha_z 2 g·px 3 sinv·ps 4..7 inf norms 8 nonfinite
-  double v[9] = {1.0, 1.0, 0.0, 0.0, 0.0, 0.0, 0.0, 0.0, 0.0};
-  const int stride = gridDim.x * blockDim.x;
-  const int t0 = blockIdx.x * blockDim.x + threadIdx.x;
-  for (int i = t0; i < n; i += stride) {
-    const double p = px[i];
-    v[2] += g[i] * p;
-    v[4] = fmax(v[4], fabs(p));
-    if (!isfinite(p)) v[8] += 1.0;
-  }
-  for (int i = t0; i < me; i += stride) v[6] = fmax(v[6], fabs(py[i]));
-  for (int i = t0; i < mi; i += stride) {
-    const double p = ps[i], q = pz[i];
+    pz[i] = q;
     if (p < 0.0) {
       const double cand = -tau / p * s[i];
       if (cand < v[0]) v[0] = cand;
@@ -1556,7 +1528,7 @@ __global__ void k_trial_point(const double* __restrict__ x,
                               double* __restrict__ leaf_trial) {
   const int i = blockIdx.x * blockDim.x + threadIdx.x;
   if (alpha_dev != nullptr) {
-    // α_max, α_z as k_step_stats just left them (slpb_solve_trial)
+    // α_max, α_z as k_step_recover_stats just left them (slpb_solve_trial)
     alpha = alpha_dev[0];
     alpha_z = dual_uses_primal ? alpha_dev[0] : alpha_dev[1];
   }
@@ -1967,7 +1939,7 @@ void fill_point_info(const double* r, slpb_point_info* info) {
 }
 
 /// Where the merged calls park their results in the 64-double result block.
-constexpr int kResStep = 0;    // 9 doubles of k_step_stats
+constexpr int kResStep = 0;    // 9 doubles of k_step_recover_stats
 constexpr int kResPoint = 16;  // 6 (+1) doubles of k_point_info / k_deriv_finite
 constexpr int kResKkt = 32;    // 25 doubles of k_kkt_stats
 
@@ -2277,15 +2249,13 @@ int solve_into(slpb_solver* S, double mu, double tau, bool soc,
   }
   int rc = launch_solve(S, fused);
   if (rc) return rc;
-  const int m = std::max(n, std::max(me, mi));
-  k_step_recover<<<blocks_for(m, 256), 256, 0, S->stream>>>(
+  // step recovery and its reductions in one launch
+  k_step_recover_stats<<<red_blocks(n + mi), kReduceThreads, 0, S->stream>>>(
       S->sol.p, S->ai_rowptr.p, S->ai_rcol.p, S->ai_ridx.p,
       S->dvals.p + S->ad.off_ai, S->vals_cur.p + 1 + me, S->s.p, S->z.p,
-      cis_soc, S->sinv.p, S->sigma.p, mu, n, me, mi, px, py, ps, pz);
-  k_step_stats<<<red_blocks(n + mi), kReduceThreads, 0, S->stream>>>(
-      S->dvals.p + S->ad.off_g, S->s.p, S->z.p, S->sinv.p, px, ps, py, pz, tau,
-      n, me, mi, red_buf(S), S->d_results.p);
-  S->counters.kernel_launches += 2;
+      cis_soc, S->sinv.p, S->sigma.p, S->dvals.p + S->ad.off_g, mu, tau, n, me,
+      mi, px, py, ps, pz, red_buf(S), S->d_results.p);
+  ++S->counters.kernel_launches;
   CU(cudaGetLastError());
   if (info == nullptr) return SLPB_OK;  // the caller fetches (slpb_solve_trial)
   rc = fetch_results(S, 9);
