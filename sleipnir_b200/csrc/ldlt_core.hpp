@@ -105,10 +105,16 @@ SLPB_HD void ldlt_factor_front(int tid, int s, const SymbolicView& S,
     const int mc = S.front_dim[c] - (S.super_first[c + 1] - S.super_first[c]);
     const double* U = updates + S.update_ptr[c];
     const int32_t* rel = S.rel_idx + S.rel_ptr[c];
-    for (int j = 0; j < mc; ++j) {
-      const int cj = rel[j] * F;
-      const double* Uj = U + tri_col(j, mc);
-      for (int i = j + tid; i < mc; i += NT) W[rel[i] + cj] += SLPB_LDCG(Uj + i);
+    {
+      constexpr int LW = NT >= 32 ? 32 : NT;
+      constexpr int NG = NT / LW;
+      for (int j = tid / LW; j < mc; j += NG) {
+        const int cj = rel[j] * F;
+        const double* Uj = U + tri_col(j, mc);
+        for (int i = j + tid % LW; i < mc; i += LW) {
+          W[rel[i] + cj] += SLPB_LDCG(Uj + i);
+        }
+      }
     }
     sync();
   }
@@ -132,15 +138,26 @@ SLPB_HD void ldlt_factor_front(int tid, int s, const SymbolicView& S,
     }
     for (int i = k + 1 + tid; i < F; i += NT) lcol[i] = W[i + k * F] / d;
     sync();
-    // W(i,j) −= l_ik · (d·l_jk) for k < j ≤ i, with d·l_jk still in column k
-    for (int j = k + 1; j < F; ++j) {
-      const double wjk = W[j + k * F];
-      if (fused) {
-        for (int i = j + tid; i < F; i += NT) {
-          W[i + j * F] = fma(-lcol[i], wjk, W[i + j * F]);
+    // W(i,j) −= l_ik · (d·l_jk) for k < j ≤ i, with d·l_jk still in column k.
+    // Threads are laid out two-dimensionally — groups of up to 32 take a column
+    // each, the threads of a group its rows — so that a big front keeps a whole
+    // thread block busy (every entry still receives exactly this one update
+    // per pivot: the mapping does not change any bit).
+    {
+      constexpr int LW = NT >= 32 ? 32 : NT;
+      constexpr int NG = NT / LW;
+      const int lane_in_group = tid % LW, group = tid / LW;
+      for (int j = k + 1 + group; j < F; j += NG) {
+        const double wjk = W[j + k * F];
+        if (fused) {
+          for (int i = j + lane_in_group; i < F; i += LW) {
+            W[i + j * F] = fma(-lcol[i], wjk, W[i + j * F]);
+          }
+        } else {
+          for (int i = j + lane_in_group; i < F; i += LW) {
+            W[i + j * F] -= lcol[i] * wjk;
+          }
         }
-      } else {
-        for (int i = j + tid; i < F; i += NT) W[i + j * F] -= lcol[i] * wjk;
       }
     }
     sync();

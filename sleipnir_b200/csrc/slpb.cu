@@ -205,6 +205,14 @@ struct slpb_solver {
   DevBuf<double> panels, updates, D, uvecs, xperm;
   DevBuf<int32_t> fstats;  // FactorStats as 6 ints
   DevBuf<int32_t> sy_super_parent, sy_nchild, tree_sync;
+  // Fronts above order 32 (a dense row of the KKT system, e.g. a time-step
+  // variable shared by every stage) and their ancestors — the "top" — take one
+  // block per front and one launch per level; everything below them, nearly
+  // all of the tree, still takes the warp-per-front tree kernels.
+  bool hybrid = false;
+  int n_small = 0;
+  DevBuf<int32_t> hy_small_order, hy_top_supers, hy_bflag_init;
+  std::vector<int32_t> hy_level_off;  // offsets of the top's levels in hy_top_supers
   DevBuf<int32_t> solve_sync;       // dependency words of k_solve_tree
   bool solve_sync_preset = false;   // written by the last factor launch's init
   DevBuf<FrontMeta> sy_metas;
@@ -1036,7 +1044,9 @@ __global__ void k_estimate_finish(const double* __restrict__ sol,
 // level of the assembly tree
 // ---------------------------------------------------------------------------
 
-constexpr int kFrontThreads = 128;
+// (one block per front; the level kernels only see the rare fronts above order
+// 32 and their ancestors, which are big: 16 warps)
+constexpr int kFrontThreads = 512;
 
 __global__ void k_factor_level(SymbolicView S,
                                const int32_t* __restrict__ level_supers,
@@ -1293,13 +1303,16 @@ __global__ void k_init_factor(int32_t* __restrict__ stats, int32_t* sync,
 /// arrived through the exchange).
 __global__ void k_init_solve_sync(int32_t* __restrict__ sync, int ns,
                                   int skip_forward,
-                                  const int32_t* __restrict__ fcount_init) {
+                                  const int32_t* __restrict__ fcount_init,
+                                  const int32_t* __restrict__ bflag_init = nullptr) {
   const int i = blockIdx.x * blockDim.x + threadIdx.x;
   if (i == 0) sync[0] = 0;
   if (i < ns) {
     sync[1 + i] = fcount_init ? fcount_init[i] : 0;  // fcount
     sync[1 + ns + i] = skip_forward ? 1 : 0;         // fflag
-    sync[1 + 2 * ns + i] = 0;                        // bflag
+    // bflag (hybrid: the fronts of the top, solved by the level kernels, count
+    // as done)
+    sync[1 + 2 * ns + i] = bflag_init ? bflag_init[i] : 0;
   }
 }
 
@@ -2155,7 +2168,44 @@ int launch_solve(slpb_solver* S, bool skip_forward) {
     double* uvecs = S->uvecs.p + size_t(sel) * Y.rel_ptr.back();
     TreeView T = tree_view(S);
     T.sync = S->solve_sync.p;  // the solve's own dependency words
-    if (!S->tree_sharded) {
+    if (S->hybrid) {
+      // forward: the small fronts in one tree launch, the top level by level;
+      // backward: the top level by level, then the small fronts (whose parents
+      // in the top count as done: hy_bflag_init)
+      const int top_smem = Y.max_front * static_cast<int>(sizeof(double));
+      const int n_top_levels = static_cast<int>(S->hy_level_off.size()) - 1;
+      T.order = S->hy_small_order.p;
+      T.order_bwd = S->hy_small_order.p;
+      k_init_solve_sync<<<blocks_for(Y.n_super, 256), 256, 0, S->stream>>>(
+          S->solve_sync.p, Y.n_super, 0, nullptr, nullptr);
+      T.n_fwd = S->n_small;
+      T.n_bwd = 0;
+      k_solve_tree<<<S->solve_blocks, kTreeWarps * 32, 0, S->stream>>>(
+          T, panels, Dsel, S->rhs.p, xperm, uvecs, S->sol.p);
+      for (int L = 0; L < n_top_levels; ++L) {
+        const int cnt = S->hy_level_off[L + 1] - S->hy_level_off[L];
+        k_forward_level<<<cnt, kFrontThreads, top_smem, S->stream>>>(
+            S->sview, S->hy_top_supers.p + S->hy_level_off[L], panels, S->rhs.p,
+            xperm, uvecs);
+      }
+      for (int L = n_top_levels - 1; L >= 0; --L) {
+        const int cnt = S->hy_level_off[L + 1] - S->hy_level_off[L];
+        k_backward_level<<<cnt, kFrontThreads, top_smem, S->stream>>>(
+            S->sview, S->hy_top_supers.p + S->hy_level_off[L], panels, Dsel,
+            xperm);
+      }
+      k_init_solve_sync<<<blocks_for(Y.n_super, 256), 256, 0, S->stream>>>(
+          S->solve_sync.p, Y.n_super, 1, nullptr, S->hy_bflag_init.p);
+      T.n_fwd = 0;
+      T.n_bwd = S->n_small;
+      k_solve_tree<<<S->solve_blocks, kTreeWarps * 32, 0, S->stream>>>(
+          T, panels, Dsel, S->rhs.p, xperm, uvecs, S->sol.p);
+      // (the tree kernel un-permutes its own fronts; this covers the top)
+      k_unpermute<<<blocks_for(S->dim, 256), 256, 0, S->stream>>>(
+          xperm, S->sy_perm.p, S->dim, S->sol.p);
+      S->counters.kernel_launches += 5 + 2 * n_top_levels;
+      S->solve_sync_preset = false;
+    } else if (!S->tree_sharded) {
       if (!(skip_forward && S->solve_sync_preset)) {
         k_init_solve_sync<<<blocks_for(Y.n_super, 256), 256, 0, S->stream>>>(
             S->solve_sync.p, Y.n_super, skip_forward ? 1 : 0, nullptr);
@@ -2693,8 +2743,45 @@ int slpb_analyze(slpb_solver* S, int ordering, const int32_t* perm,
   CU(S->uvecs.alloc(2 * size_t(Y.rel_ptr.back())));
   CU(S->xperm.alloc(2 * size_t(Y.dim)));
   CU(S->fstats.alloc(16));
-  // fronts of order ≤ 32: one warp per front, one launch per factorisation
-  S->use_tree = Y.max_front <= 32;
+  // fronts of order ≤ 32: one warp per front, one launch per factorisation;
+  // larger ones and their ancestors: the level kernels (hybrid)
+  std::vector<uint8_t> in_top(Y.n_super, 0);
+  S->hybrid = false;
+  for (int32_t s : Y.level_supers) {  // ascending level: children come first
+    if (Y.front_dim[s] > 32) in_top[s] = 1;
+    if (in_top[s]) {
+      S->hybrid = true;
+      if (Y.super_parent[s] >= 0) in_top[Y.super_parent[s]] = 1;
+    }
+  }
+  S->n_small = 0;
+  S->hy_level_off.clear();
+  if (S->hybrid) {
+    std::vector<int32_t> small, top, bflag(Y.n_super, 0);
+    S->hy_level_off.push_back(0);
+    for (int L = 0; L < Y.n_levels; ++L) {
+      for (int k = Y.level_ptr[L]; k < Y.level_ptr[L + 1]; ++k) {
+        const int32_t s = Y.level_supers[k];
+        (in_top[s] ? top : small).push_back(s);
+        bflag[s] = in_top[s];
+      }
+      if (static_cast<int32_t>(top.size()) > S->hy_level_off.back()) {
+        S->hy_level_off.push_back(static_cast<int32_t>(top.size()));
+      }
+    }
+    S->n_small = static_cast<int>(small.size());
+    if (small.empty()) small.push_back(0);
+    CU(S->hy_small_order.upload(small, S->stream));
+    CU(S->hy_top_supers.upload(top, S->stream));
+    CU(S->hy_bflag_init.upload(bflag, S->stream));
+  }
+  S->use_tree = !S->hybrid || S->n_small > 0;
+  if (S->hybrid && std::getenv("SLPB_NO_HYBRID")) {
+    // development switch: round 1's behaviour (every front through the level
+    // kernels as soon as one front exceeds order 32)
+    S->hybrid = false;
+    S->use_tree = false;
+  }
   S->tree_smem_doubles = kFrontSmemDoubles;
   if (S->use_tree) {
     // the warp kernels keep a front with the fixed leading dimension kFrontLd:
@@ -2710,10 +2797,11 @@ int slpb_analyze(slpb_solver* S, int ordering, const int32_t* perm,
     const int32_t rhs_at = kFrontLd * kFrontCols + kDenseSideDoubles;
     for (int32_t q = 0; q < Y.n_super; ++q) {
       const int32_t F = Y.front_dim[q];
+      ext_begin[q] = static_cast<int32_t>(ext_src.size() / 32);
+      if (in_top[q]) continue;  // handled by the level kernels
       for (int64_t k = Y.asm_ptr[q]; k < Y.asm_ptr[q + 1]; ++k) {
         dst_ld[k] = Y.asm_dst[k] % F + (Y.asm_dst[k] / F) * kFrontLd;
       }
-      ext_begin[q] = static_cast<int32_t>(ext_src.size() / 32);
       for (int64_t ck = Y.child_ptr[q]; ck < Y.child_ptr[q + 1]; ++ck) {
         const int32_t c = Y.child_idx[ck];
         const int32_t mc = Y.front_dim[c] - (Y.super_first[c + 1] - Y.super_first[c]);
@@ -2815,7 +2903,8 @@ int slpb_analyze(slpb_solver* S, int ordering, const int32_t* perm,
                                            std::max(1, per_sm_solve))));
   }
   S->tree_sharded = false;
-  if (S->world > 1 && S->use_tree && !std::getenv("SLPB_NO_TREE_SHARD")) {
+  if (S->world > 1 && S->use_tree && !S->hybrid &&
+      !std::getenv("SLPB_NO_TREE_SHARD")) {
     build_tree_shard(Y, S->world, S->tshard);
     const TreeShard& H = S->tshard;
     const int W = S->world;
@@ -3015,8 +3104,8 @@ int factor_impl(slpb_solver* S, int n_variants, const double* delta,
   const bool fuse_init = reassemble && S->group == nullptr;
   // a fused solve is expected behind this factorisation: its dependency words
   // are preset here, so that the solve is ONE launch
-  const bool preset_solve = S->use_tree && !S->tree_sharded && S->rhs_ready &&
-                            S->group == nullptr;
+  const bool preset_solve = S->use_tree && !S->tree_sharded && !S->hybrid &&
+                            S->rhs_ready && S->group == nullptr;
   int32_t* preset_ptr = preset_solve ? S->solve_sync.p : nullptr;
   const int init_words =
       S->use_tree ? std::max(1 + 2 * Y.n_super, preset_solve ? 1 + 3 * Y.n_super : 0)
@@ -3075,12 +3164,38 @@ int factor_impl(slpb_solver* S, int n_variants, const double* delta,
                           Y.update_size,
                           static_cast<int64_t>(Y.rel_ptr.back()),
                           Y.dim,
-                          S->rhs_ready ? S->rhs.p : nullptr,
+                          // (hybrid: the level kernels of the top do not carry
+                          // a right-hand side; the solve runs both halves)
+                          S->rhs_ready && !S->hybrid ? S->rhs.p : nullptr,
                           S->xperm.p,
                           S->uvecs.p,
                           S->factor_arith};
-    for (int v = 0; v < 2; ++v) S->fwd_valid[v] = S->rhs_ready && v < n_variants;
-    if (!S->tree_sharded) {
+    for (int v = 0; v < 2; ++v) {
+      S->fwd_valid[v] = S->rhs_ready && !S->hybrid && v < n_variants;
+    }
+    if (S->hybrid) {
+      // everything below the oversized fronts in one tree launch, then the
+      // top level by level, one block per front
+      TreeView Ts = T;
+      Ts.order = S->hy_small_order.p;
+      Ts.n_order = S->n_small;
+      k_factor_tree<<<S->tree_blocks, kTreeWarps * 32, smem, S->stream>>>(
+          Ts, S->Kval.p, delta[0], gamma[0], pair, S->panels.p, S->updates.p,
+          S->D.p, S->fstats.p);
+      const int top_smem = static_cast<int>(
+          (size_t(Y.max_front) * Y.max_front + Y.max_front) * sizeof(double));
+      for (int v = 0; v < n_variants; ++v) {
+        for (size_t L = 0; L + 1 < S->hy_level_off.size(); ++L) {
+          const int cnt = S->hy_level_off[L + 1] - S->hy_level_off[L];
+          k_factor_level<<<cnt, kFrontThreads, top_smem, S->stream>>>(
+              S->sview, S->hy_top_supers.p + S->hy_level_off[L], S->Kval.p,
+              delta[v], gamma[v], S->panels.p + v * Y.panel_size,
+              S->updates.p + v * Y.update_size, S->D.p + size_t(v) * Y.dim,
+              S->fstats.p + 8 * v, S->factor_arith);
+          ++S->counters.kernel_launches;
+        }
+      }
+    } else if (!S->tree_sharded) {
       k_factor_tree<<<S->tree_blocks, kTreeWarps * 32, smem, S->stream>>>(
           T, S->Kval.p, delta[0], gamma[0], pair, S->panels.p, S->updates.p,
           S->D.p, S->fstats.p);

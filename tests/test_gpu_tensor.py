@@ -39,6 +39,9 @@ def _point(P, O, seed):
     ("cart_pole", 400, sb.ORDER_AMD),
     ("gfold", 60, sb.ORDER_NESTED_DISSECTION),
     ("arm_on_elevator", 100, sb.ORDER_NESTED_DISSECTION),
+    # a time-step variable shared by all stages: fronts above order 32 — the
+    # hybrid path (tree kernel below them, one block per front above)
+    ("differential_drive_ocp", 50, sb.ORDER_NESTED_DISSECTION),
     ("flywheel", 50, sb.ORDER_NATURAL)])
 def test_device_factor_equals_the_host_emulation_bit_for_bit(name, N, order, mode):
     P, O = sb.Problem(name, N), OracleProblem(name, N)
@@ -72,6 +75,16 @@ def test_device_factor_equals_the_host_emulation_bit_for_bit(name, N, order, mod
     # the tensor-core path was actually exercised
     if mode == sb.ARITH_TENSOR and name != "flywheel":
         assert (F >= 16).sum() > 0
+    if name == "differential_drive_ocp":
+        assert F.max() > 32 and (F <= 32).sum() > 0.8 * len(F)   # hybrid
+        # … and the solve through both kinds of kernels: L D Lᵀ x = rhs
+        D.factor(1.0, 1e-6, True)
+        E.set_kkt_values(D.download(sb.ARR_KKT_VAL))
+        E.factor(1.0, 1e-6)
+        D.solve(0.1, 0.99)
+        x_dev = np.concatenate([D.download(sb.ARR_P_X), -D.download(sb.ARR_P_Y)])
+        x_emu = E.solve(D.download(sb.ARR_RHS))
+        assert x_dev.tobytes() == x_emu.tobytes(), np.abs(x_dev - x_emu).max()
     E.close(); P.close_device(); P.close(); O.close()
 
 
