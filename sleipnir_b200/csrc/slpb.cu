@@ -211,6 +211,11 @@ struct slpb_solver {
   // all of the tree, still takes the warp-per-front tree kernels.
   bool hybrid = false;
   int n_small = 0;
+  // fronts beyond the shared-memory cap of one block: global workspaces
+  DevBuf<double> front_scratch;
+  DevBuf<int32_t> front_slot;
+  int64_t front_stride = 0;
+  int front_cap_doubles = 0, front_smem_bytes = 0;
   DevBuf<int32_t> hy_small_order, hy_top_supers, hy_bflag_init;
   std::vector<int32_t> hy_level_off;  // offsets of the top's levels in hy_top_supers
   DevBuf<int32_t> solve_sync;       // dependency words of k_solve_tree
@@ -1054,13 +1059,18 @@ __global__ void k_factor_level(SymbolicView S,
                                double gamma, double* __restrict__ panels,
                                double* __restrict__ updates,
                                double* __restrict__ D,
-                               int32_t* __restrict__ stats, int fused_arith) {
+                               int32_t* __restrict__ stats, int fused_arith,
+                               double* gscratch, const int32_t* __restrict__ gslot,
+                               int64_t gstride, int smem_cap_doubles) {
   extern __shared__ double smem[];
   __shared__ int ls[6];
   const int s = level_supers[blockIdx.x];
   const int F = S.front_dim[s];
+  // a front beyond the shared-memory cap is eliminated in a workspace in
+  // global memory (L2): slow, but any order works
   double* W = smem;
-  double* lcol = smem + size_t(F) * F;
+  if (F * F + F > smem_cap_doubles) W = gscratch + int64_t(gslot[s]) * gstride;
+  double* lcol = W + size_t(F) * F;
   ldlt_factor_front<kFrontThreads>(threadIdx.x, s, S, Kval, delta, gamma,
                                    panels, updates, D, W, lcol, ls,
                                    BlockSync{}, fused_arith != 0);
@@ -2714,12 +2724,37 @@ int slpb_analyze(slpb_solver* S, int ordering, const int32_t* perm,
   const Symbolic& Y = S->sym;
   const size_t front_smem =
       (size_t(Y.max_front) * Y.max_front + Y.max_front) * sizeof(double);
-  if (front_smem > 200 * 1024) {
-    return fail(S, SLPB_ERR_UNSUPPORTED,
-                "a frontal matrix exceeds 200 KB of shared memory (front order " +
-                    std::to_string(Y.max_front) + ")");
+  // One block per front keeps the front in shared memory up to 200 KB (order
+  // 158); a bigger front — a variable shared by hundreds of stages — gets a
+  // workspace in global memory instead: slots for as many of them as one level
+  // of the tree holds.
+  constexpr size_t kFrontSmemCap = 200 * 1024;
+  S->front_cap_doubles = static_cast<int>(kFrontSmemCap / sizeof(double));
+  S->front_smem_bytes = static_cast<int>(std::min(front_smem, kFrontSmemCap));
+  S->front_stride = int64_t(Y.max_front) * Y.max_front + Y.max_front;
+  {
+    std::vector<int32_t> slot(Y.n_super, 0);
+    int32_t max_slots = 0;
+    for (int L = 0; L < Y.n_levels; ++L) {
+      int32_t used = 0;
+      for (int k = Y.level_ptr[L]; k < Y.level_ptr[L + 1]; ++k) {
+        const int32_t q = Y.level_supers[k];
+        const int64_t F = Y.front_dim[q];
+        if (F * F + F > S->front_cap_doubles) slot[q] = used++;
+      }
+      max_slots = std::max(max_slots, used);
+    }
+    if (max_slots > 0) {
+      if (size_t(max_slots) * S->front_stride * sizeof(double) > (size_t(8) << 30)) {
+        return fail(S, SLPB_ERR_UNSUPPORTED,
+                    "the frontal matrices of one level exceed 8 GB (front order " +
+                        std::to_string(Y.max_front) + ")");
+      }
+      CU(S->front_scratch.alloc(size_t(max_slots) * S->front_stride));
+    }
+    CU(S->front_slot.upload(slot, S->stream));
   }
-  CU(raise_dynamic_smem(k_factor_level, static_cast<int>(front_smem)));
+  CU(raise_dynamic_smem(k_factor_level, S->front_smem_bytes));
   CU(S->sy_super_first.upload(Y.super_first, S->stream));
   CU(S->sy_front_dim.upload(Y.front_dim, S->stream));
   CU(S->sy_rows_ptr.upload(Y.rows_ptr, S->stream));
@@ -3182,8 +3217,7 @@ int factor_impl(slpb_solver* S, int n_variants, const double* delta,
       k_factor_tree<<<S->tree_blocks, kTreeWarps * 32, smem, S->stream>>>(
           Ts, S->Kval.p, delta[0], gamma[0], pair, S->panels.p, S->updates.p,
           S->D.p, S->fstats.p);
-      const int top_smem = static_cast<int>(
-          (size_t(Y.max_front) * Y.max_front + Y.max_front) * sizeof(double));
+      const int top_smem = S->front_smem_bytes;
       for (int v = 0; v < n_variants; ++v) {
         for (size_t L = 0; L + 1 < S->hy_level_off.size(); ++L) {
           const int cnt = S->hy_level_off[L + 1] - S->hy_level_off[L];
@@ -3191,7 +3225,8 @@ int factor_impl(slpb_solver* S, int n_variants, const double* delta,
               S->sview, S->hy_top_supers.p + S->hy_level_off[L], S->Kval.p,
               delta[v], gamma[v], S->panels.p + v * Y.panel_size,
               S->updates.p + v * Y.update_size, S->D.p + size_t(v) * Y.dim,
-              S->fstats.p + 8 * v, S->factor_arith);
+              S->fstats.p + 8 * v, S->factor_arith, S->front_scratch.p,
+              S->front_slot.p, S->front_stride, S->front_cap_doubles);
           ++S->counters.kernel_launches;
         }
       }
@@ -3236,8 +3271,7 @@ int factor_impl(slpb_solver* S, int n_variants, const double* delta,
     ++S->counters.kernel_launches;
   } else {
     S->fwd_valid[0] = S->fwd_valid[1] = false;
-    const int smem = static_cast<int>(
-        (size_t(Y.max_front) * Y.max_front + Y.max_front) * sizeof(double));
+    const int smem = S->front_smem_bytes;
     for (int v = 0; v < n_variants; ++v) {
       for (int L = 0; L < Y.n_levels; ++L) {
         const int cnt = Y.level_ptr[L + 1] - Y.level_ptr[L];
@@ -3245,7 +3279,8 @@ int factor_impl(slpb_solver* S, int n_variants, const double* delta,
             S->sview, S->sy_level_supers.p + Y.level_ptr[L], S->Kval.p,
             delta[v], gamma[v], S->panels.p + v * Y.panel_size,
             S->updates.p + v * Y.update_size, S->D.p + size_t(v) * Y.dim,
-            S->fstats.p + 8 * v, S->factor_arith);
+            S->fstats.p + 8 * v, S->factor_arith, S->front_scratch.p,
+            S->front_slot.p, S->front_stride, S->front_cap_doubles);
       }
       S->counters.kernel_launches += Y.n_levels;
     }
