@@ -123,6 +123,12 @@ SLPB_HD double ad_op_grad(uint8_t op, uint8_t side, double a, double l,
   }
 }
 
+/// Development aid (scripts/sweep_debug.py): slpb.cu defines SLPB_AD_STAMP to
+/// record clock64() at the phase boundaries of one thread block.
+#ifndef SLPB_AD_STAMP
+#define SLPB_AD_STAMP(k)
+#endif
+
 struct NoSync {
   SLPB_HD void operator()() const {}
 };
@@ -186,6 +192,7 @@ SLPB_HD void ad_run_group(int tid, int nthreads, int count,
     S[const_slot[i] * LC] = const_val[i * LC + c];
   }
   sync();
+  SLPB_AD_STAMP(2);
 
   for (int blk = 0; blk < n_blocks; ++blk) {
     const uint32_t* Bk = stream.acquire(blk);
@@ -253,12 +260,14 @@ SLPB_HD void ad_run_group(int tid, int nthreads, int count,
       }
     }
     sync();
+    SLPB_AD_STAMP(3 + blk);
     stream.release(blk);
   }
   const uint16_t* adj_out_slot = reinterpret_cast<const uint16_t*>(H + H[16]);
   for (int i = q; i < n_adj_out; i += R) {
     if (active) stage[adj_out_stage[i * LC + c]] = S[adj_out_slot[i] * LC];
   }
+  SLPB_AD_STAMP(62);
 }
 
 /// Scale reference of a gather source: −1 → 1, −2 → d_f, k ≥ 0 → d_c[k].

@@ -20,6 +20,7 @@
 #include <cstring>
 #include <map>
 #include <numeric>
+#include <queue>
 #include <thread>
 #include <unordered_map>
 
@@ -437,6 +438,61 @@ struct Compiler {
   /// schedule: load → forward levels → value outputs → reverse levels → adjoint
   /// outputs). That keeps a cart-pole stage at a few hundred doubles instead of
   /// 1 700, so that 32 stages fit in one CTA's shared memory side by side.
+  /// Cost model of the schedule, in units of one multiply-add contribution
+  /// (≈140 cycles of a lone warp: two dependent shared-memory loads and the
+  /// arithmetic): divisions, square roots and the transcendental functions
+  /// run for several hundred cycles (scripts/sweep_debug.py: super-levels of
+  /// equal item count took 3.4k … 11.8k cycles).
+  static int32_t forward_cost(uint8_t op) {
+    if (flat_costs()) return 1;
+    switch (op) {
+      case SLPB_OP_ADD: case SLPB_OP_SUB: case SLPB_OP_MUL: case SLPB_OP_NEG:
+      case SLPB_OP_ABS: case SLPB_OP_SIGN: case SLPB_OP_MAX: case SLPB_OP_MIN:
+        return 1;
+      case SLPB_OP_DIV: case SLPB_OP_SQRT:
+        return 2;
+      case SLPB_OP_POW: case SLPB_OP_ATAN2: case SLPB_OP_HYPOT:
+        return 6;
+      default:
+        return 4;  // sin, cos, exp, log, …
+    }
+  }
+  static int32_t contrib_cost(uint8_t op) {
+    if (op == kOpLinear || flat_costs()) return 1;
+    switch (op) {
+      case SLPB_OP_ADD: case SLPB_OP_SUB: case SLPB_OP_MUL: case SLPB_OP_NEG:
+      case SLPB_OP_ABS: case SLPB_OP_SIGN: case SLPB_OP_MAX: case SLPB_OP_MIN:
+        return 1;
+      case SLPB_OP_DIV:
+        return 3;
+      case SLPB_OP_SQRT:
+        return 4;
+      case SLPB_OP_POW: case SLPB_OP_ATAN2: case SLPB_OP_HYPOT: case SLPB_OP_TAN:
+      case SLPB_OP_TANH:
+        return 8;
+      default:
+        return 5;  // a transcendental function and a multiplication
+    }
+  }
+  static bool flat_costs() {
+    static const bool flat = std::getenv("SLPB_SCHED_FLAT_COSTS") != nullptr || legacy_schedule();
+    return flat;
+  }
+  static bool legacy_schedule() {
+    static const bool legacy = std::getenv("SLPB_SCHED_LEGACY") != nullptr;
+    return legacy;
+  }
+  /// Set by the caller of emit_program / reported by it.
+  int32_t m_window = 1 << 30;
+  int64_t m_last_critical_path = 0;
+  int32_t m_last_visits = 0;
+  template <typename V>
+  static int32_t visit_cost(const V& v) {
+    int32_t w = 1;
+    for (const auto& c : v.contribs) w += contrib_cost(c.op);
+    return w;
+  }
+
   bool emit_program(std::vector<SubRow>& subs, const std::vector<int32_t>& mem,
                     const std::vector<int32_t>& cl_nodes,
                     std::vector<int32_t>& level,
@@ -571,6 +627,7 @@ struct Compiler {
       const char* e = std::getenv("SLPB_CHAIN_CAP");
       return e ? std::max(1, std::atoi(e)) : 24;
     }();
+    const bool kLegacySchedule = legacy_schedule();
     struct Loads {
       int32_t W;
       std::vector<std::vector<int32_t>> load;  // [super-level][worker]
@@ -610,17 +667,24 @@ struct Compiler {
           sl = s_max;  // continues that worker's chain: no barrier
           w = same;
         } else {
+          // behind a barrier anyway: any worker may take it. The lightest one
+          // does (stacking it on its producer's worker left most workers idle
+          // in the deep super-levels: critical path 467 → 341 weight units on
+          // the cart-pole stage together with the priority order below).
+          // Development switch SLPB_SCHED_LEGACY=1: the previous placement.
           sl = s_max + 1;
-          w = same >= 0 ? same : -1;
-          if (w < 0 || L.at(sl, w) + weight > kChainCap) {
-            // prefer a producer's worker (its chain may continue), else the
-            // lightest one
-            w = -1;
-            for (int k = 0; k < n_deps; ++k) {
-              if (deps[k].first != s_max) continue;
-              if (w < 0 || L.at(sl, deps[k].second) < L.at(sl, w)) w = deps[k].second;
+          if (!kLegacySchedule) {
+            w = L.lightest(sl);
+          } else {
+            w = same >= 0 ? same : -1;
+            if (w < 0 || L.at(sl, w) + weight > kChainCap) {
+              w = -1;
+              for (int k = 0; k < n_deps; ++k) {
+                if (deps[k].first != s_max) continue;
+                if (w < 0 || L.at(sl, deps[k].second) < L.at(sl, w)) w = deps[k].second;
+              }
+              if (L.at(sl, w) + weight > kChainCap) w = L.lightest(sl);
             }
-            if (L.at(sl, w) + weight > kChainCap) w = L.lightest(sl);
           }
         }
       }
@@ -642,7 +706,7 @@ struct Compiler {
           const int32_t b = local[tape.rhs[nd]];
           if (sl_of[b] > 0) deps[n_deps++] = {sl_of[b], fwd_worker[b]};
         }
-        const auto [sl, w] = place(L, deps, n_deps, 1, 1);
+        const auto [sl, w] = place(L, deps, n_deps, 1, forward_cost(tape.op[nd]));
         sl_of[slot] = sl;
         fwd_worker[slot] = w;
       }
@@ -665,16 +729,78 @@ struct Compiler {
     {
       Loads L{n_workers, {}};
       std::vector<std::pair<int32_t, int32_t>> deps;
-      for (int32_t i = 0; i < n_visits; ++i) {  // parents come first in visit order
+      auto place_visit = [&](int32_t i) {
         deps.clear();
         for (const ContribTmp& c : visits[i].contribs) {
           deps.push_back({visits[c.parent_visit].rlevel, rev_worker[c.parent_visit]});
         }
-        const int32_t weight = 1 + static_cast<int32_t>(visits[i].contribs.size());
+        const int32_t weight = visit_cost(visits[i]);
         const auto [sl, w] =
             place(L, deps.data(), static_cast<int>(deps.size()), 0, weight);
         visits[i].rlevel = sl;
         rev_worker[i] = w;
+      };
+      if (kLegacySchedule) {
+        for (int32_t i = 0; i < n_visits; ++i) place_visit(i);  // parents first
+      } else {
+        // list scheduling: among the visits whose parents are placed, the one
+        // with the longest remaining dependency chain goes first
+        std::vector<int64_t> bottom(n_visits, 0);
+        std::vector<int32_t> child_ptr(n_visits + 1, 0), pending(n_visits, 0);
+        for (int32_t i = 0; i < n_visits; ++i) {
+          for (const ContribTmp& c : visits[i].contribs) ++child_ptr[c.parent_visit + 1];
+          pending[i] = static_cast<int32_t>(visits[i].contribs.size());
+        }
+        for (int32_t i = 0; i < n_visits; ++i) child_ptr[i + 1] += child_ptr[i];
+        std::vector<int32_t> child(child_ptr[n_visits]), fill(child_ptr.begin(), child_ptr.end() - 1);
+        for (int32_t i = 0; i < n_visits; ++i) {
+          for (const ContribTmp& c : visits[i].contribs) child[fill[c.parent_visit]++] = i;
+        }
+        for (int32_t i = n_visits - 1; i >= 0; --i) {
+          int64_t below = 0;
+          for (int32_t k = child_ptr[i]; k < child_ptr[i + 1]; ++k) below = std::max(below, bottom[child[k]]);
+          bottom[i] = below + visit_cost(visits[i]);
+        }
+        // … among those at most kWindow visits ahead of the oldest unplaced
+        // one: running far ahead along the critical chains keeps the operands
+        // of everything left behind alive (60 more scratch slots on the
+        // cart-pole stage, which then no longer fits twice on an SM)
+        const int32_t kWindow = m_window;
+        using Key = std::pair<int64_t, int32_t>;  // (−bottom, index): smallest first
+        std::priority_queue<Key, std::vector<Key>, std::greater<Key>> ready;
+        std::priority_queue<int32_t, std::vector<int32_t>, std::greater<int32_t>> waiting;
+        std::vector<uint8_t> placed(n_visits, 0);
+        int32_t lo = 0;  // oldest unplaced visit
+        auto offer = [&](int32_t i) {
+          if (i < lo + kWindow) {
+            ready.push({-bottom[i], i});
+          } else {
+            waiting.push(i);
+          }
+        };
+        for (int32_t i = 0; i < n_visits; ++i) {
+          if (pending[i] == 0) offer(i);
+        }
+        int32_t n_placed = 0;
+        while (n_placed < n_visits) {
+          // (the oldest unplaced visit is always ready or behind a ready one,
+          // so `ready` cannot run dry before everything is placed)
+          const int32_t i = ready.top().second;
+          ready.pop();
+          place_visit(i);
+          placed[i] = 1;
+          ++n_placed;
+          for (int32_t k = child_ptr[i]; k < child_ptr[i + 1]; ++k) {
+            if (--pending[child[k]] == 0) offer(child[k]);
+          }
+          if (i == lo) {
+            while (lo < n_visits && placed[lo]) ++lo;
+            while (!waiting.empty() && waiting.top() < lo + kWindow) {
+              ready.push({-bottom[waiting.top()], waiting.top()});
+              waiting.pop();
+            }
+          }
+        }
       }
     }
     int32_t max_rlevel = -1;
@@ -688,26 +814,49 @@ struct Compiler {
         return rev_worker[x] < rev_worker[y];
       });
     }
-    if (std::getenv("SLPB_COMPILE_TIMING")) {
+    {
       // critical path of the schedule: Σ over super-levels of the heaviest list
+      const bool report = std::getenv("SLPB_COMPILE_TIMING") != nullptr;
       int64_t crit = 0, total = 0;
       for (const auto& lv : rev_levels) {
         std::vector<int64_t> load(n_workers, 0);
-        for (int32_t i : lv) load[rev_worker[i]] += 1 + visits[i].contribs.size();
+        for (int32_t i : lv) load[rev_worker[i]] += visit_cost(visits[i]);
         crit += *std::max_element(load.begin(), load.end());
         for (int64_t l : load) total += l;
-        if (std::getenv("SLPB_SCHEDULE_DUMP") && n_workers == 16) {
+        if (report && std::getenv("SLPB_SCHEDULE_DUMP") && n_workers == 16) {
           std::fprintf(stderr, "   level %2d:", int(&lv - &rev_levels[0]));
           for (int64_t l : load) std::fprintf(stderr, " %3lld", (long long)l);
           std::fprintf(stderr, "\n");
         }
       }
-      std::fprintf(stderr,
-                   "[slpb compile] schedule: %d workers, %zu forward + %zu reverse "
-                   "super-levels, reverse weight %lld, critical path %lld "
-                   "(perfect balance: %lld)\n",
-                   n_workers, fwd_levels.size(), rev_levels.size(),
-                   (long long)total, (long long)crit, (long long)(total / n_workers));
+      int64_t fcrit = 0, ftotal = 0;
+      for (const auto& lv : fwd_levels) {
+        std::vector<int64_t> load(n_workers, 0);
+        for (int32_t slot : lv) load[fwd_worker[slot]] += forward_cost(tape.op[cl_nodes[slot]]);
+        fcrit += *std::max_element(load.begin(), load.end());
+        ftotal += static_cast<int64_t>(lv.size());
+      }
+      m_last_critical_path = fcrit + crit;
+      m_last_visits = n_visits;
+      if (report) {
+        // longest weighted dependency chain of the reverse sweep: no schedule
+        // can be shorter
+        int64_t dag = 0;
+        std::vector<int64_t> cp(n_visits, 0);
+        for (int32_t i = 0; i < n_visits; ++i) {
+          int64_t in = 0;
+          for (const ContribTmp& c : visits[i].contribs) in = std::max(in, cp[c.parent_visit]);
+          cp[i] = in + visit_cost(visits[i]);
+          dag = std::max(dag, cp[i]);
+        }
+        std::fprintf(stderr,
+                     "[slpb compile] schedule (window %d): %d workers, forward %zu super-levels, "
+                     "weight %lld, critical path %lld; reverse %zu super-levels, weight %lld, "
+                     "critical path %lld (perfect balance %lld, longest dependency chain %lld)\n",
+                     m_window, n_workers, fwd_levels.size(), (long long)ftotal, (long long)fcrit,
+                     rev_levels.size(), (long long)total, (long long)crit,
+                     (long long)(total / n_workers), (long long)dag);
+      }
     }
 
     // --- physical slot allocation (liveness over the level schedule) ---------
@@ -1027,6 +1176,14 @@ struct Compiler {
           stream_words * 4u <= kAdResidentBytes && with_stream <= kAdHalfSmBytes;
       prog[22] = resident ? stream_words : kAdStages * max_block_words;
       prog[23] = resident ? 1u : 0u;
+      if (std::getenv("SLPB_COMPILE_TIMING") && n_workers == 16) {
+        std::fprintf(stderr,
+                     "[slpb compile] %d scratch slots (%u B at 32 lanes), tables %u B, "
+                     "stream %u B in %d blocks (largest %u B), %s\n",
+                     n_scratch, static_cast<uint32_t>(n_scratch) * 256u, prog[5] * 4u,
+                     stream_words * 4u, n_blocks, max_block_words * 4u,
+                     resident ? "resident" : "ring");
+      }
     }
     prog[18] = n_contrib_total;
     prog[19] = static_cast<uint32_t>(n_visits);
@@ -1163,8 +1320,40 @@ struct Compiler {
         for (size_t k = 0; k < cl_nodes.size(); ++k) {
           local[cl_nodes[k]] = static_cast<int32_t>(k);
         }
-        const bool ok =
-            emit_program(subs, mem, cl_nodes, level, sorted_ids, prog, ps);
+        // The reverse sweep is list-scheduled by remaining chain length inside
+        // a window of the visit order (emit_program): a wide window shortens
+        // the critical path, a narrow one keeps fewer operands alive. Take the
+        // shortest schedule among those whose task (32 lanes) still fits twice
+        // on an SM; SLPB_SCHED_WINDOW pins the window (development).
+        bool ok = true;
+        {
+          static const int32_t kPinned = [] {
+            const char* e = std::getenv("SLPB_SCHED_WINDOW");
+            return e ? std::max(1, std::atoi(e)) : 0;
+          }();
+          const int32_t windows[] = {1 << 30, 512, 256, 128, 64, 32};
+          std::vector<uint32_t> best;
+          int64_t best_cost = -1;
+          bool best_fits = false;
+          for (int32_t window : windows) {
+            // (a window that covers the whole sweep is the unbounded one)
+            if (best_cost >= 0 && window >= m_last_visits) continue;
+            m_window = kPinned > 0 ? kPinned : window;
+            ok = emit_program(subs, mem, cl_nodes, level, sorted_ids, prog, ps);
+            if (!ok) break;
+            const bool fits =
+                static_cast<uint32_t>(ad_smem_layout(prog[0], prog[5], prog[22], 32).total) <=
+                kAdHalfSmBytes;
+            if (best_cost < 0 || (fits && !best_fits) ||
+                (fits == best_fits && m_last_critical_path < best_cost)) {
+              best = prog;
+              best_cost = m_last_critical_path;
+              best_fits = fits;
+            }
+            if (kPinned > 0 || legacy_schedule()) break;
+          }
+          if (ok) prog.swap(best);
+        }
         for (int32_t nd : cl_nodes) {
           local[nd] = -1;
           main_sc.local[nd] = -1;

@@ -30,6 +30,22 @@
 #include <string>
 #include <vector>
 
+#ifdef SLPB_SWEEP_STAMPS
+// development build (make EXTRA=-DSLPB_SWEEP_STAMPS; scripts/sweep_debug.py):
+// block 0 of a 512-thread sweep (16 workers × 32 lanes) records clock64() at
+// its phase boundaries
+__device__ long long g_sweep_stamps[128];  // block 0 | block 75 (alone on its SM)
+#ifdef __CUDA_ARCH__
+#define SLPB_AD_STAMP(k)                                                      \
+  do {                                                                        \
+    if (threadIdx.x == 0 && (blockIdx.x == 0 || blockIdx.x == 75) &&         \
+        blockDim.x == 512 && (k) < 64)                                        \
+      g_sweep_stamps[(blockIdx.x ? 64 : 0) + (k)] = clock64();                \
+  } while (0)
+#else
+#define SLPB_AD_STAMP(k)
+#endif
+#endif
 #include "ad_core.hpp"
 #include "internal.hpp"
 #include "kkt_core.hpp"
@@ -439,6 +455,7 @@ __global__ void __launch_bounds__(512)
 k_ad_sweep(AdTasks A, int first_task, const double* __restrict__ leaf,
            double* __restrict__ stage) {
   extern __shared__ __align__(16) unsigned char smem_raw[];
+  SLPB_AD_STAMP(0);
   const int t = first_task + blockIdx.x;
   const uint32_t* P = A.blob + A.prog_offset[A.task_prog[t]];
   const uint32_t* B = A.task_bindings + A.task_bind[t];
@@ -466,6 +483,7 @@ k_ad_sweep(AdTasks A, int first_task, const double* __restrict__ leaf,
   TmaStream stream{P, H + H[10], ring, bars, static_cast<int>(H[4]),
                    static_cast<int>(stage_words), tid == 0, H[23] != 0};
   if (tid == 0) stream.start();
+  SLPB_AD_STAMP(1);
   const BlockSync sync{};
   switch (lanes) {
     case 32: ad_run_group<32>(tid, nt, count, H, stream, B, leaf, stage, scratch, sync); break;
@@ -3656,6 +3674,26 @@ int slpb_pattern(const slpb_solver* S, int which, int32_t* rows, int32_t* cols,
     std::memcpy(rowidx, p->rowidx.data(), p->nnz() * sizeof(int32_t));
   }
   return SLPB_OK;
+}
+
+/* Undocumented debugging aid (a build with -DSLPB_SWEEP_STAMPS): clock64() at
+ * the phase boundaries of blocks 0 and 75 (out[64..]) of the last 512-thread
+ * k_ad_sweep launch — with 157 tasks on 148 SMs block 0 shares its SM:
+ * [0] entry, [1] tables in shared memory, [2] leaves loaded, [3 + b] after the
+ * barrier of instruction block b, [62] outputs stored. Not part of
+ * include/slpb.h. */
+int slpb_debug_sweep_stamps(long long* out) {
+#ifdef SLPB_SWEEP_STAMPS
+  if (cudaDeviceSynchronize() != cudaSuccess) return SLPB_ERR_CUDA;
+  void* addr = nullptr;
+  if (cudaGetSymbolAddress(&addr, g_sweep_stamps) != cudaSuccess) return SLPB_ERR_CUDA;
+  return cudaMemcpy(out, addr, sizeof(long long) * 128, cudaMemcpyDeviceToHost) == cudaSuccess
+             ? SLPB_OK
+             : SLPB_ERR_CUDA;
+#else
+  (void)out;
+  return SLPB_ERR_UNSUPPORTED;
+#endif
 }
 
 /* Undocumented debugging aid (SLPB_TREE_DEBUG=1): per front, globaltimer ns at
