@@ -243,6 +243,8 @@ SLPB_HD void ad_run_group(int tid, int nthreads, int count,
               const double pa = S[ck.parent_adj * LC], lv = S[ck.l * LC];
               if (ck.op == kOpLinear) {
                 a += pa * lv;  // adjoint × (±1 or the other factor): no decode
+              } else if (ck.op == kOpLinearNeg) {
+                a -= pa * lv;  // = a + pa·(−lv) bit for bit
               } else {
                 a += ad_op_grad(ck.op, ck.side, pa, lv, S[ck.r * LC]);
               }

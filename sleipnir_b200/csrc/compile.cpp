@@ -70,10 +70,22 @@ struct SubRow {
 constexpr uint8_t kActive = 1;  // the node's adjoint reaches an output leaf
 constexpr uint8_t kValue = 2;   // the node's value is read by some partial
 
-/// Which operand values the partial of `op` w.r.t. `side` reads
-/// (bit 0: lhs value, bit 1: rhs value); see ad_op_grad in ad_core.hpp.
+/// Partials that the forward sweep has already computed as a value are read
+/// from that node's slot (emit_program); SLPB_NO_VALUE_REUSE=1 evaluates them
+/// again (development switch).
+bool value_reuse_enabled() {
+  static const bool on = std::getenv("SLPB_NO_VALUE_REUSE") == nullptr;
+  return on;
+}
+
+/// Which values the partial of `op` w.r.t. `side` reads (bit 0: lhs value,
+/// bit 1: rhs value, bit 2: the node's own value); see ad_op_grad in
+/// ad_core.hpp.
 uint8_t grad_value_needs(uint8_t op, int side) {
   switch (op) {
+    // d exp(x) = exp(x): the node's own value (x stays marked: the forward
+    // sweep needs it to evaluate the node)
+    case SLPB_OP_EXP: return value_reuse_enabled() ? 5 : 3;
     case SLPB_OP_ADD: case SLPB_OP_SUB: case SLPB_OP_NEG: return 0;
     case SLPB_OP_MUL: return side == 0 ? 2 : 1;
     case SLPB_OP_DIV: return side == 0 ? 2 : 3;
@@ -304,6 +316,7 @@ struct Compiler {
           const uint8_t needs = grad_value_needs(tape.op[nd], side);
           if (needs & 1) sr.flags[pos[l]] |= kValue;
           if ((needs & 2) && r >= 0) sr.flags[pos[r]] |= kValue;
+          if (needs & 4) sr.flags[i] |= kValue;
         }
       }
     }
@@ -458,7 +471,7 @@ struct Compiler {
     }
   }
   static int32_t contrib_cost(uint8_t op) {
-    if (op == kOpLinear || flat_costs()) return 1;
+    if (op == kOpLinear || op == kOpLinearNeg || flat_costs()) return 1;
     switch (op) {
       case SLPB_OP_ADD: case SLPB_OP_SUB: case SLPB_OP_MUL: case SLPB_OP_NEG:
       case SLPB_OP_ABS: case SLPB_OP_SIGN: case SLPB_OP_MAX: case SLPB_OP_MIN:
@@ -542,6 +555,18 @@ struct Compiler {
     };
     std::vector<VisitTmp> visits;
     std::vector<int32_t> adj_out_visit, val_out_slots;
+    // (op, argument node) → slot of the sin / cos / sinh / cosh nodes of the
+    // cluster
+    const bool kNoValueReuse = !value_reuse_enabled();
+    std::map<std::pair<uint8_t, int32_t>, int32_t> twins;
+    for (int32_t slot = 0; slot < n_slots; ++slot) {
+      const int32_t nd = cl_nodes[slot];
+      const uint8_t op = tape.op[nd];
+      if (op == SLPB_OP_SIN || op == SLPB_OP_COS || op == SLPB_OP_SINH ||
+          op == SLPB_OP_COSH) {
+        twins.emplace(std::make_pair(op, tape.lhs[nd]), slot);
+      }
+    }
     for (int32_t s : mem) {
       SubRow& sr = subs[s];
       if (sr.is_value) {
@@ -588,6 +613,30 @@ struct Compiler {
               c.op = kOpLinear, c.l = side == 0 ? local[r] : local[l];
               c.r = -1;
               break;
+            // Partials that the forward sweep of this cluster has already
+            // computed as a VALUE: exp(x) itself, cos(x) beside sin(x) and the
+            // like. The same device function on the same argument gives the
+            // same bits, so a·cos(x) is read from that node's slot instead of
+            // running a second FP64 cosine (several hundred cycles of one
+            // warp's critical path).
+            case SLPB_OP_EXP:
+              if (needs & 4) c.op = kOpLinear, c.l = local[nd], c.r = -1;
+              break;
+            case SLPB_OP_SIN:
+            case SLPB_OP_COS:
+            case SLPB_OP_SINH:
+            case SLPB_OP_COSH: {
+              const uint8_t twin_op = tape.op[nd] == SLPB_OP_SIN    ? SLPB_OP_COS
+                                      : tape.op[nd] == SLPB_OP_COS  ? SLPB_OP_SIN
+                                      : tape.op[nd] == SLPB_OP_SINH ? SLPB_OP_COSH
+                                                                    : SLPB_OP_SINH;
+              const auto twin = twins.find({twin_op, l});
+              if (!kNoValueReuse && twin != twins.end()) {
+                c.op = tape.op[nd] == SLPB_OP_COS ? kOpLinearNeg : kOpLinear;
+                c.l = twin->second, c.r = -1;
+              }
+              break;
+            }
             default:
               break;
           }

@@ -104,6 +104,10 @@ constexpr uint32_t kBlockForward = 0, kBlockReverse = 1, kBlockValueOut = 2;
 /// Contrib.op of a contribution that is adjoint × (value in slot l): the
 /// partials of +, −, unary − (multiplier ±1) and × (the other operand).
 constexpr uint8_t kOpLinear = 255;
+/// The same with the product subtracted: the partial of cos(x) is
+/// a·(−sin x) = −(a·sin x) exactly, taken from the slot of a sin(x) node of the
+/// same cluster instead of evaluating the sine again.
+constexpr uint8_t kOpLinearNeg = 254;
 constexpr int kAdStages = 3;  // ring-buffer stages of the instruction stream
 /// An instruction stream stays resident in shared memory when it is at most
 /// this big AND a full task (32 lanes of scratch + stream) still leaves room
