@@ -885,6 +885,20 @@ struct Compiler {
         fcrit += *std::max_element(load.begin(), load.end());
         ftotal += static_cast<int64_t>(lv.size());
       }
+      if (report && n_workers == 16) {
+        std::map<int, int> fh, ch;
+        for (const auto& lv : fwd_levels) {
+          for (int32_t slot : lv) ++fh[tape.op[cl_nodes[slot]]];
+        }
+        for (const auto& v : visits) {
+          for (const auto& c : v.contribs) ++ch[c.op * 2 + c.side];
+        }
+        std::fprintf(stderr, "[slpb compile] forward ops:");
+        for (auto& [op, n] : fh) std::fprintf(stderr, " %d×%d", op, n);
+        std::fprintf(stderr, " | contributions (op.side):");
+        for (auto& [k, n] : ch) std::fprintf(stderr, " %d.%d×%d", k / 2, k % 2, n);
+        std::fprintf(stderr, "\n");
+      }
       m_last_critical_path = fcrit + crit;
       m_last_visits = n_visits;
       if (report) {
