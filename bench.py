@@ -650,10 +650,10 @@ def main():
                 "kernel": "k_ad_sweep (full re-linearisation)",
                 "share_of_step_device_time": (per_step_ms["eval_full"] + per_step_ms["eval_values"]) /
                                              max(sum(per_step_ms.values()), 1e-12),
-                "note": "as a kernel (derivative set + value set) k_ad_sweep now has the "
-                        "larger share of the step than k_factor_tree; it is bound by the "
-                        "dependency depth of the expression graph (DESIGN.md §3.1), its "
-                        "algorithmic bytes are negligible against the HBM peak",
+                "note": "as a kernel (derivative set + value set) k_ad_sweep takes about as "
+                        "much of the step as k_factor_tree; it is bound by the dependency "
+                        "depth of the expression graph (DESIGN.md §3.1), its algorithmic "
+                        "bytes are negligible against the HBM peak",
                 "algorithmic_bytes": ad_bytes,
                 "ms": phase_ms["eval_full"],
                 "achieved_gbs": ad_bytes / (phase_ms["eval_full"] * 1e-3) / 1e9 if phase_ms["eval_full"] > 0 else None},
