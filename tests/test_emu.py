@@ -335,3 +335,91 @@ def test_concurrent_builds_are_independent():
             np.testing.assert_array_equal(o[1], g["g"])
             np.testing.assert_array_equal(o[2], g["H_val"])
             np.testing.assert_array_equal(o[3], g["A_e_val"])
+
+
+_SCHED_WORKER = r"""
+import sys, numpy as np
+sys.path.insert(0, sys.argv[1])
+from emu import Emu
+out = {}
+for name, N in (("cart_pole", 40), ("all_ops", 0), ("flywheel", 60)):
+    E = Emu(name, N)
+    rng = np.random.default_rng(11)
+    x = 0.3 + 0.5 * rng.random(E.n)
+    y, z = rng.standard_normal(E.me), np.abs(rng.standard_normal(E.mi)) + 0.1
+    r = E.eval(x, y, z, 0.7, np.full(max(E.me, 1), 1.3)[:E.me], np.full(max(E.mi, 1), 0.9)[:E.mi])
+    for k, v in r.items():
+        out[f"{name}.{k}"] = np.asarray(v)
+    import ctypes as C
+    hdr = (C.c_uint32 * 24)()
+    n_prog = E.L.emu_program_header(E.h, 1, 0, hdr)
+    best = None
+    for p in range(n_prog):
+        E.L.emu_program_header(E.h, 1, p, hdr)
+        if best is None or hdr[14] > best[14]:
+            best = list(hdr)
+    out[f"{name}.header"] = np.array(best, dtype=np.int64)
+    E.close()
+np.savez(sys.argv[2], **out)
+"""
+
+
+def _run_schedule_variant(tmp_path, tag, env_extra):
+    import subprocess
+    import sys
+    script = tmp_path / "sched_worker.py"
+    script.write_text(_SCHED_WORKER)
+    out = tmp_path / f"{tag}.npz"
+    env = dict(os.environ)
+    for k in ("SLPB_SCHED_LEGACY", "SLPB_NO_VALUE_REUSE", "SLPB_SCHED_WINDOW",
+              "SLPB_SCHED_FLAT_COSTS", "SLPB_CHAIN_CAP"):
+        env.pop(k, None)
+    env.update(env_extra)
+    subprocess.run([sys.executable, str(script), os.path.dirname(__file__), str(out)],
+                   check=True, env=env, timeout=600)
+    return np.load(out)
+
+
+def test_schedule_and_value_reuse_do_not_change_a_single_bit(tmp_path):
+    """The sweep compiler's list scheduling (which worker runs an item, in which
+    super-level), its window, its cost model and the reuse of forward values as
+    partials (d sin = the cos node, d exp = the node itself) only move work
+    around: every output of the interpreter is bit-identical to the previous
+    placement with every partial evaluated (the switches are read once per
+    process, hence the subprocesses)."""
+    ref = _run_schedule_variant(tmp_path, "default", {})
+    variants = {
+        "legacy": {"SLPB_SCHED_LEGACY": "1"},
+        "no_reuse": {"SLPB_NO_VALUE_REUSE": "1"},
+        "legacy_no_reuse": {"SLPB_SCHED_LEGACY": "1", "SLPB_NO_VALUE_REUSE": "1"},
+        "window32": {"SLPB_SCHED_WINDOW": "32"},
+        "flat": {"SLPB_SCHED_FLAT_COSTS": "1"},
+    }
+    for tag, env in variants.items():
+        got = _run_schedule_variant(tmp_path, tag, env)
+        for k in ref.files:
+            if k.endswith(".header"):
+                continue
+            np.testing.assert_array_equal(got[k], ref[k], err_msg=f"{tag}: {k}")
+    # the switches did something: the legacy placement needs more barriers for
+    # the cart-pole stage, and without reuse no partial is a negated product
+    legacy = _run_schedule_variant(tmp_path, "legacy2", {"SLPB_SCHED_LEGACY": "1"})
+    h_new, h_old = ref["cart_pole.header"], legacy["cart_pole.header"]
+    assert h_new[12] + h_new[13] < h_old[12] + h_old[13]  # forward + reverse super-levels
+
+
+def test_cart_pole_stage_fits_twice_on_an_sm():
+    """The window of the list scheduler is chosen so that a 32-lane task of the
+    cart-pole stage (scratch + tables + instruction ring) stays within 112 KB:
+    two tasks per SM, as 157 tasks on 148 SMs need."""
+    E = Emu("cart_pole", 64)
+    hdr = (ctypes.c_uint32 * 24)()
+    n_prog = E.L.emu_program_header(E.h, 1, 0, hdr)
+    worst = 0
+    for p in range(n_prog):
+        E.L.emu_program_header(E.h, 1, p, hdr)
+        scratch = (hdr[0] * 32 * 8 + 15) & ~15
+        ring = (scratch + hdr[5] * 4 + 15) & ~15
+        worst = max(worst, ring + hdr[22] * 4 + 3 * 8)
+    assert 64 * 1024 < worst <= 112 * 1024
+    E.close()
