@@ -456,35 +456,41 @@ struct Compiler {
   /// arithmetic): divisions, square roots and the transcendental functions
   /// run for several hundred cycles (scripts/sweep_debug.py: super-levels of
   /// equal item count took 3.4k … 11.8k cycles).
-  static int32_t forward_cost(uint8_t op) {
-    if (flat_costs()) return 1;
+  static constexpr int32_t kExpensive = 20;
+  static bool is_cheap(uint8_t op) {
     switch (op) {
       case SLPB_OP_ADD: case SLPB_OP_SUB: case SLPB_OP_MUL: case SLPB_OP_NEG:
       case SLPB_OP_ABS: case SLPB_OP_SIGN: case SLPB_OP_MAX: case SLPB_OP_MIN:
-        return 1;
-      case SLPB_OP_DIV: case SLPB_OP_SQRT:
-        return 2;
-      case SLPB_OP_POW: case SLPB_OP_ATAN2: case SLPB_OP_HYPOT:
-        return 6;
+      case SLPB_OP_IS_NONNEG: case SLPB_OP_IS_POS:
+        return true;
       default:
-        return 4;  // sin, cos, exp, log, …
+        return false;
+    }
+  }
+  static int32_t forward_cost(uint8_t op) {
+    if (flat_costs() || is_cheap(op)) return 1;
+    switch (op) {
+      case SLPB_OP_DIV:
+        return 3;
+      case SLPB_OP_POW: case SLPB_OP_ATAN2: case SLPB_OP_HYPOT:
+        return 24;
+      default:
+        return kExpensive;  // sqrt, sin, cos, exp, log, … (FP64, one warp)
     }
   }
   static int32_t contrib_cost(uint8_t op) {
     if (op == kOpLinear || op == kOpLinearNeg || flat_costs()) return 1;
+    if (is_cheap(op)) return 1;
     switch (op) {
-      case SLPB_OP_ADD: case SLPB_OP_SUB: case SLPB_OP_MUL: case SLPB_OP_NEG:
-      case SLPB_OP_ABS: case SLPB_OP_SIGN: case SLPB_OP_MAX: case SLPB_OP_MIN:
-        return 1;
       case SLPB_OP_DIV:
         return 3;
-      case SLPB_OP_SQRT:
-        return 4;
+      case SLPB_OP_SQRT: case SLPB_OP_LOG: case SLPB_OP_LOG10:
+        return 5;  // divisions
       case SLPB_OP_POW: case SLPB_OP_ATAN2: case SLPB_OP_HYPOT: case SLPB_OP_TAN:
       case SLPB_OP_TANH:
-        return 8;
+        return 24;
       default:
-        return 5;  // a transcendental function and a multiplication
+        return kExpensive;  // a transcendental function and a multiplication
     }
   }
   static bool flat_costs() {
@@ -516,13 +522,43 @@ struct Compiler {
     // --- forward levels ------------------------------------------------------
     sorted_ids.assign(cl_nodes.begin(), cl_nodes.end());
     std::sort(sorted_ids.begin(), sorted_ids.end());
+    // Forward instruction of every interior slot: operand slots and opcode.
+    // The DSL does not share sub-expressions: a dynamics function that writes
+    // sin(θ) four times makes four nodes (the cart-pole stage: 32 sin/cos for 8
+    // distinct ones, each ≈3 000 cycles of one warp in FP64). A repeated
+    // function of the same argument node becomes a COPY of the first one's
+    // value (max(v, v) — the same device function on the same argument gives
+    // the same bits); SLPB_NO_VALUE_REUSE=1 evaluates every node.
+    std::vector<int32_t> f_lhs(n_slots, -1), f_rhs(n_slots, -1);
+    std::vector<uint8_t> f_op(n_slots, 0);
+    {
+      std::map<std::pair<uint8_t, int32_t>, int32_t> first_of;
+      for (int32_t nd : sorted_ids) {
+        if (!is_interior(nd)) continue;
+        const int32_t slot = local[nd];
+        f_lhs[slot] = local[tape.lhs[nd]];
+        f_rhs[slot] = tape.rhs[nd] >= 0 ? local[tape.rhs[nd]] : -1;
+        f_op[slot] = tape.op[nd];
+        if (tape.rhs[nd] >= 0 || is_cheap(tape.op[nd]) || tape.op[nd] == SLPB_OP_DIV ||
+            !value_reuse_enabled()) {
+          continue;
+        }
+        const auto [it, fresh] =
+            first_of.emplace(std::make_pair(tape.op[nd], tape.lhs[nd]), slot);
+        if (!fresh) {
+          f_lhs[slot] = f_rhs[slot] = it->second;
+          f_op[slot] = SLPB_OP_MAX;
+        }
+      }
+    }
     level.assign(n_slots, 0);
     int32_t max_level = 0;
     for (int32_t nd : sorted_ids) {
       if (!is_interior(nd)) continue;
-      int32_t lv = level[local[tape.lhs[nd]]];
-      if (tape.rhs[nd] >= 0) lv = std::max(lv, level[local[tape.rhs[nd]]]);
-      level[local[nd]] = lv + 1;
+      const int32_t slot = local[nd];
+      int32_t lv = level[f_lhs[slot]];
+      if (f_rhs[slot] >= 0) lv = std::max(lv, level[f_rhs[slot]]);
+      level[slot] = lv + 1;
       max_level = std::max(max_level, lv + 1);
     }
     std::vector<std::vector<int32_t>> fwd_levels(max_level);  // logical slots
@@ -749,13 +785,13 @@ struct Compiler {
         const int32_t slot = local[nd];
         std::pair<int32_t, int32_t> deps[2];
         int n_deps = 0;
-        const int32_t a = local[tape.lhs[nd]];
+        const int32_t a = f_lhs[slot];
         if (sl_of[a] > 0) deps[n_deps++] = {sl_of[a], fwd_worker[a]};
-        if (tape.rhs[nd] >= 0) {
-          const int32_t b = local[tape.rhs[nd]];
+        if (f_rhs[slot] >= 0 && f_rhs[slot] != a) {
+          const int32_t b = f_rhs[slot];
           if (sl_of[b] > 0) deps[n_deps++] = {sl_of[b], fwd_worker[b]};
         }
-        const auto [sl, w] = place(L, deps, n_deps, 1, forward_cost(tape.op[nd]));
+        const auto [sl, w] = place(L, deps, n_deps, 1, forward_cost(f_op[slot]));
         sl_of[slot] = sl;
         fwd_worker[slot] = w;
       }
@@ -881,14 +917,19 @@ struct Compiler {
       int64_t fcrit = 0, ftotal = 0;
       for (const auto& lv : fwd_levels) {
         std::vector<int64_t> load(n_workers, 0);
-        for (int32_t slot : lv) load[fwd_worker[slot]] += forward_cost(tape.op[cl_nodes[slot]]);
+        for (int32_t slot : lv) load[fwd_worker[slot]] += forward_cost(f_op[slot]);
+        if (report && std::getenv("SLPB_SCHEDULE_DUMP") && n_workers == 16) {
+          std::fprintf(stderr, "   forward %2d:", int(&lv - &fwd_levels[0]));
+          for (int64_t l : load) std::fprintf(stderr, " %3lld", (long long)l);
+          std::fprintf(stderr, "\n");
+        }
         fcrit += *std::max_element(load.begin(), load.end());
         ftotal += static_cast<int64_t>(lv.size());
       }
       if (report && n_workers == 16) {
         std::map<int, int> fh, ch;
         for (const auto& lv : fwd_levels) {
-          for (int32_t slot : lv) ++fh[tape.op[cl_nodes[slot]]];
+          for (int32_t slot : lv) ++fh[f_op[slot]];
         }
         for (const auto& v : visits) {
           for (const auto& c : v.contribs) ++ch[c.op * 2 + c.side];
@@ -970,9 +1011,9 @@ struct Compiler {
     for (int32_t slot = 0; slot < n_slots; ++slot) {
       const int32_t nd = cl_nodes[slot];
       if (!is_interior(nd)) continue;
-      note(local[tape.lhs[nd]], level[slot], fwd_worker[slot], fwd_pos[slot]);
-      if (tape.rhs[nd] >= 0) {
-        note(local[tape.rhs[nd]], level[slot], fwd_worker[slot], fwd_pos[slot]);
+      note(f_lhs[slot], level[slot], fwd_worker[slot], fwd_pos[slot]);
+      if (f_rhs[slot] >= 0) {
+        note(f_rhs[slot], level[slot], fwd_worker[slot], fwd_pos[slot]);
       }
     }
     for (int32_t slot : val_out_slots) note(slot, t_valout, -1, 0);
@@ -1039,9 +1080,8 @@ struct Compiler {
               if (c.r >= 0) operands.push_back(c.r);
             }
           } else {
-            const int32_t nd = cl_nodes[x];
-            operands.push_back(local[tape.lhs[nd]]);
-            if (tape.rhs[nd] >= 0) operands.push_back(local[tape.rhs[nd]]);
+            operands.push_back(f_lhs[x]);
+            if (f_rhs[x] >= 0) operands.push_back(f_rhs[x]);
           }
           std::sort(operands.begin(), operands.end());
           operands.erase(std::unique(operands.begin(), operands.end()), operands.end());
@@ -1158,12 +1198,11 @@ struct Compiler {
                   &fwd_worker);
       max_width = std::max<int32_t>(max_width, lv.size());
       for (int32_t slot : lv) {
-        const int32_t nd = cl_nodes[slot];
         FwdInstr in{};
         in.dst = vp(slot);
-        in.a = vp(local[tape.lhs[nd]]);
-        in.b = tape.rhs[nd] >= 0 ? vp(local[tape.rhs[nd]]) : in.a;
-        in.op = tape.op[nd];
+        in.a = vp(f_lhs[slot]);
+        in.b = f_rhs[slot] >= 0 ? vp(f_rhs[slot]) : in.a;
+        in.op = f_op[slot];
         push_record(&in);
         ++n_instr;
       }
