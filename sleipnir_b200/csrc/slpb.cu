@@ -605,8 +605,8 @@ __device__ __forceinline__ double red_identity(int op) {
 }
 
 template <int NV>
-__device__ void block_reduce(double (&v)[NV], const int (&op)[NV],
-                             double* out) {
+__device__ __forceinline__ void block_reduce(double (&v)[NV], const int (&op)[NV],
+                                             double* out) {
   __shared__ double red[NV][kReduceThreads / 32];
   const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
 #pragma unroll
@@ -634,7 +634,7 @@ __device__ void block_reduce(double (&v)[NV], const int (&op)[NV],
 
 /// Returns true in the (single) block that holds the grid-wide result in res.
 template <int NV>
-__device__ bool grid_reduce(double (&v)[NV], const int (&op)[NV],
+__device__ __forceinline__ bool grid_reduce(double (&v)[NV], const int (&op)[NV],
                             double* __restrict__ partials,
                             unsigned int* __restrict__ counter, double* res) {
   __shared__ bool is_last;
@@ -719,8 +719,15 @@ k_deriv_finite(const double* __restrict__ dvals, int64_t off_ae, int64_t off_ai,
   for (int64_t i = int64_t(blockIdx.x) * blockDim.x + threadIdx.x; i < total;
        i += stride) {
     if (!isfinite(dvals[i])) {
-      const int seg = i < off_ae ? 0 : (i < off_ai ? 1 : (i < off_h ? 2 : 3));
-      w[seg] += 1.0;
+      if (i < off_ae) {
+        w[0] += 1.0;
+      } else if (i < off_ai) {
+        w[1] += 1.0;
+      } else if (i < off_h) {
+        w[2] += 1.0;
+      } else {
+        w[3] += 1.0;
+      }
     }
   }
   const int op[4] = {RED_SUM, RED_SUM, RED_SUM, RED_SUM};
@@ -766,6 +773,7 @@ k_kkt_stats(CscView Ae, CscView Ai, const double* __restrict__ g,
   // 25…28 (scan != nullptr: k_deriv_finite in the same launch) non-finite
   // entries of g, A_e, A_i, H
   double v[29];
+#pragma unroll
   for (int q = 0; q < 29; ++q) v[q] = 0.0;
   v[4] = INFINITY;
   v[5] = -INFINITY;
@@ -843,8 +851,16 @@ k_kkt_stats(CscView Ae, CscView Ai, const double* __restrict__ g,
     const int64_t sstride = int64_t(gridDim.x) * blockDim.x;
     for (int64_t i = t0; i < scan_total; i += sstride) {
       if (!isfinite(scan[i])) {
-        const int seg = i < off_ae ? 0 : (i < off_ai ? 1 : (i < off_h ? 2 : 3));
-        v[25 + seg] += 1.0;
+        // (static indices: v[] must stay in registers)
+        if (i < off_ae) {
+          v[25] += 1.0;
+        } else if (i < off_ai) {
+          v[26] += 1.0;
+        } else if (i < off_h) {
+          v[27] += 1.0;
+        } else {
+          v[28] += 1.0;
+        }
       }
     }
   }
