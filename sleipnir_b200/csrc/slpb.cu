@@ -604,45 +604,80 @@ __device__ __forceinline__ double red_identity(int op) {
   return op == RED_SUM ? 0.0 : (op == RED_MAX ? -INFINITY : INFINITY);
 }
 
+/// The warp-level tree runs through SHARED MEMORY, eight quantities at a time:
+/// lane l adds the value of lane l + o for o = 16, 8, …, 1 — the pairing of a
+/// __shfl_down tree, hence the same bits — because 64-bit warp shuffles are
+/// the bottleneck of a 29-quantity reduction (2 × 29 × 5 shuffles per warp,
+/// ≈4 cycles each per SM: 4.7 µs per block, measured with clock64() stamps).
 template <int NV>
 __device__ __forceinline__ void block_reduce(double (&v)[NV], const int (&op)[NV],
                                              double* out) {
+  constexpr int kChunk = 8;
+  __shared__ double tile[kChunk][kReduceThreads];
   __shared__ double red[NV][kReduceThreads / 32];
   const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+  auto warp_tree = [&](double (&a)[NV]) {
+    // a[q] of lane 0 ends up holding the warp's result
 #pragma unroll
-  for (int q = 0; q < NV; ++q) {
-    double a = v[q];
-    for (int o = 16; o > 0; o >>= 1) {
-      a = red_combine(op[q], a, __shfl_down_sync(0xffffffffu, a, o));
+    for (int c0 = 0; c0 < NV; c0 += kChunk) {
+#pragma unroll
+      for (int q = 0; q < kChunk; ++q) {
+        if (c0 + q < NV) tile[q][threadIdx.x] = a[c0 + q];
+      }
+      __syncwarp();
+#pragma unroll
+      for (int o = 16; o > 0; o >>= 1) {
+        if (lane < o) {
+#pragma unroll
+          for (int q = 0; q < kChunk; ++q) {
+            if (c0 + q < NV) {
+              a[c0 + q] = red_combine(op[c0 + q], a[c0 + q], tile[q][threadIdx.x + o]);
+              if (o > 1) tile[q][threadIdx.x] = a[c0 + q];
+            }
+          }
+        }
+        __syncwarp();
+      }
     }
-    if (lane == 0) red[q][warp] = a;
+  };
+  double a[NV];
+#pragma unroll
+  for (int q = 0; q < NV; ++q) a[q] = v[q];
+  warp_tree(a);
+  if (lane == 0) {
+#pragma unroll
+    for (int q = 0; q < NV; ++q) red[q][warp] = a[q];
   }
   __syncthreads();
   if (warp == 0) {
     const int nw = blockDim.x >> 5;
 #pragma unroll
-    for (int q = 0; q < NV; ++q) {
-      double a = lane < nw ? red[q][lane] : red_identity(op[q]);
-      for (int o = 16; o > 0; o >>= 1) {
-        a = red_combine(op[q], a, __shfl_down_sync(0xffffffffu, a, o));
-      }
-      if (lane == 0) out[q] = a;
+    for (int q = 0; q < NV; ++q) a[q] = lane < nw ? red[q][lane] : red_identity(op[q]);
+    warp_tree(a);
+    if (lane == 0) {
+#pragma unroll
+      for (int q = 0; q < NV; ++q) out[q] = a[q];
     }
   }
   __syncthreads();
 }
 
 /// Returns true in the (single) block that holds the grid-wide result in res.
+/// Partials are stored quantity-major (partials[q·gridDim + block]): NV threads
+/// of a block write them side by side and the last block reads them coalesced.
 template <int NV>
 __device__ __forceinline__ bool grid_reduce(double (&v)[NV], const int (&op)[NV],
-                            double* __restrict__ partials,
-                            unsigned int* __restrict__ counter, double* res) {
+                                            double* __restrict__ partials,
+                                            unsigned int* __restrict__ counter, double* res) {
   __shared__ bool is_last;
   block_reduce<NV>(v, op, res);
   if (gridDim.x == 1) return true;
-  if (threadIdx.x == 0) {
-    for (int q = 0; q < NV; ++q) partials[blockIdx.x * NV + q] = res[q];
+  if (threadIdx.x < NV) {
+    partials[threadIdx.x * gridDim.x + blockIdx.x] = res[threadIdx.x];
     __threadfence();
+  }
+  __syncthreads();
+  if (threadIdx.x == 0) {
     // atomicInc wraps to 0 at gridDim.x − 1: the counter resets itself
     const unsigned int t = atomicInc(counter, gridDim.x - 1);
     is_last = (t == gridDim.x - 1);
@@ -654,10 +689,11 @@ __device__ __forceinline__ bool grid_reduce(double (&v)[NV], const int (&op)[NV]
 #pragma unroll
   for (int q = 0; q < NV; ++q) w[q] = red_identity(op[q]);
   for (int b = threadIdx.x; b < gridDim.x; b += blockDim.x) {
+    double p[NV];
 #pragma unroll
-    for (int q = 0; q < NV; ++q) {
-      w[q] = red_combine(op[q], w[q], __ldcg(&partials[b * NV + q]));
-    }
+    for (int q = 0; q < NV; ++q) p[q] = __ldcg(&partials[q * gridDim.x + b]);
+#pragma unroll
+    for (int q = 0; q < NV; ++q) w[q] = red_combine(op[q], w[q], p[q]);
   }
   block_reduce<NV>(w, op, res);
   return true;
