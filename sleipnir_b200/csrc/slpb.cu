@@ -604,11 +604,12 @@ __device__ __forceinline__ double red_identity(int op) {
   return op == RED_SUM ? 0.0 : (op == RED_MAX ? -INFINITY : INFINITY);
 }
 
-/// The warp-level tree runs through SHARED MEMORY, eight quantities at a time:
-/// lane l adds the value of lane l + o for o = 16, 8, …, 1 — the pairing of a
-/// __shfl_down tree, hence the same bits — because 64-bit warp shuffles are
-/// the bottleneck of a 29-quantity reduction (2 × 29 × 5 shuffles per warp,
-/// ≈4 cycles each per SM: 4.7 µs per block, measured with clock64() stamps).
+/// Many quantities (k_kkt_stats: 29): the warp-level tree runs through SHARED
+/// MEMORY, eight quantities at a time: lane l adds the value of lane l + o for
+/// o = 16, 8, …, 1 — the pairing of a __shfl_down tree, hence the same bits —
+/// because 64-bit warp shuffles are the bottleneck there (2 × 29 × 5 shuffles
+/// per warp, ≈4 cycles each per SM: 4.7 µs per block, measured with clock64()
+/// stamps; 27.6 → 25.1 µs per launch). Few quantities keep the shuffles.
 template <int NV>
 __device__ __forceinline__ void block_reduce(double (&v)[NV], const int (&op)[NV],
                                              double* out) {
@@ -618,6 +619,19 @@ __device__ __forceinline__ void block_reduce(double (&v)[NV], const int (&op)[NV
   const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
   auto warp_tree = [&](double (&a)[NV]) {
     // a[q] of lane 0 ends up holding the warp's result
+    if constexpr (NV <= 16) {
+      // few quantities: shuffles, step by step over all of them (the NV
+      // shuffles of a step are independent and overlap their latency)
+#pragma unroll
+      for (int o = 16; o > 0; o >>= 1) {
+        double b[NV];
+#pragma unroll
+        for (int q = 0; q < NV; ++q) b[q] = __shfl_down_sync(0xffffffffu, a[q], o);
+#pragma unroll
+        for (int q = 0; q < NV; ++q) a[q] = red_combine(op[q], a[q], b[q]);
+      }
+      return;
+    }
 #pragma unroll
     for (int c0 = 0; c0 < NV; c0 += kChunk) {
 #pragma unroll
